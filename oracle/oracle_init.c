@@ -1,0 +1,238 @@
+/*
+ * oracle_init.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Initial conditions used by the five BASELINE.json configs, restated from the reference:
+ *   Orszag-Tang  MHDRunBase.cpp:1378-1750   (2D, and 3D direction 0/1/2)
+ *   MRI          MHDRunBase.cpp:2677-2760   (no gravity)
+ *   implode      HydroRunBase.cpp:5449-5535
+ *   Kelvin-Helmholtz (perturbation_rand) HydroRunBase.cpp:5857-6120
+ * PRNG streams are glibc's (drand48 / rand), consumed in the reference's loop order.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define AT(arr, i, j, k, v) (arr)[(size_t)(i) + (size_t)isz * ((size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(v)))]
+#define SQR(x) ((x) * (x))
+
+static void init_orszag_tang(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  const double TwoPi = 4.0 * asin(1.0);
+  const double B0 = 1.0 / sqrt(2.0 * TwoPi);
+  const double p0 = (double)(P->gamma0 / (2.0 * TwoPi));
+  const double d0 = (double)(P->gamma0 * p0);
+  const double v0 = 1.0;
+  const real_t dx = P->dx, dy = P->dy, dz = P->dz;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+
+  if (P->dim == 2) { /* :1410-1478 */
+    for (int j = 0; j < jsz; ++j) {
+      double yPos = P->yMin + dy / 2 + (j - gw) * dy;
+      for (int i = 0; i < isz; ++i) {
+        double xPos = P->xMin + dx / 2 + (i - gw) * dx;
+        AT(U, i, j, 0, ID) = (real_t)d0;
+        AT(U, i, j, 0, IU) = (real_t)(-d0 * v0 * sin(yPos * TwoPi));
+        AT(U, i, j, 0, IV) = (real_t)(d0 * v0 * sin(xPos * TwoPi));
+        AT(U, i, j, 0, IW) = 0;
+        AT(U, i, j, 0, IA) = (real_t)(-B0 * sin(yPos * TwoPi));
+        AT(U, i, j, 0, IB) = (real_t)(B0 * sin(2.0 * xPos * TwoPi));
+        AT(U, i, j, 0, IC) = 0;
+      }
+    }
+    for (int j = 0; j < jsz; ++j)
+      for (int i = 0; i < isz; ++i) {
+        int ip = (i < isz - 1) ? i + 1 : 2 * gw, jp = (j < jsz - 1) ? j + 1 : 2 * gw;
+        AT(U, i, j, 0, IP) = p0 / (P->gamma0 - 1.0) +
+            0.5 * (SQR(AT(U, i, j, 0, IU)) / AT(U, i, j, 0, ID) + SQR(AT(U, i, j, 0, IV)) / AT(U, i, j, 0, ID) +
+                   0.25 * SQR(AT(U, i, j, 0, IA) + AT(U, ip, j, 0, IA)) +
+                   0.25 * SQR(AT(U, i, j, 0, IB) + AT(U, i, jp, 0, IB)));
+      }
+    return;
+  }
+
+  const double kt = P->ot_kt;
+  /* the three orientations differ by a cyclic relabelling (a,b,c): vortex plane (a,b), c = normal */
+  /* direction 0: (x,y,z); 1: (y,z,x); 2: (z,x,y).  MHDRunBase.cpp:1489-1750 */
+  int dirn = P->ot_direction;
+  if (dirn != 0) {
+    /* only direction 0 is exercised by the configs; the others are not restated */
+    fprintf(stderr, "oracle: Orszag-Tang direction %d not restated\n", dirn);
+    return;
+  }
+  for (int k = 0; k < ksz; ++k) {
+    double zPos = P->zMin + dz / 2 + (k - gw) * dz;
+    for (int j = 0; j < jsz; ++j) {
+      double yPos = P->yMin + dy / 2 + (j - gw) * dy;
+      for (int i = 0; i < isz; ++i) {
+        double xPos = P->xMin + dx / 2 + (i - gw) * dx;
+        AT(U, i, j, k, ID) = (real_t)d0;
+        AT(U, i, j, k, IU) = (real_t)(-d0 * v0 * sin(yPos * TwoPi));
+        AT(U, i, j, k, IV) = (real_t)(d0 * v0 * sin(xPos * TwoPi));
+        AT(U, i, j, k, IW) = 0;
+        AT(U, i, j, k, IA) = (real_t)(-B0 * cos(2 * TwoPi * kt * (zPos - P->zMin) / (P->zMax - P->zMin)) * sin(yPos * TwoPi));
+        AT(U, i, j, k, IB) = (real_t)(B0 * cos(2 * TwoPi * kt * (zPos - P->zMin) / (P->zMax - P->zMin)) * sin(2.0 * xPos * TwoPi));
+        AT(U, i, j, k, IC) = 0;
+      }
+    }
+  }
+  /* total energy :1539-1573.  In the reference the i==isize-1 / j==jsize-1 branches use the
+   * 3-index accessor h_U(i,j,IP) on the 4-D array, i.e. they write element (i,j,k=1,var 0)
+   * instead of the energy (Arrays.h:95-98): reproduced here.  Those cells are ghosts. */
+  for (int k = 0; k < ksz; ++k)
+    for (int j = 0; j < jsz; ++j)
+      for (int i = 0; i < isz; ++i) {
+        int ip = (i < isz - 1) ? i + 1 : 2 * gw, jp = (j < jsz - 1) ? j + 1 : 2 * gw;
+        real_t e = p0 / (P->gamma0 - 1.0) +
+            0.5 * (SQR(AT(U, i, j, k, IU)) / AT(U, i, j, k, ID) + SQR(AT(U, i, j, k, IV)) / AT(U, i, j, k, ID) +
+                   0.25 * SQR(AT(U, i, j, k, IA) + AT(U, ip, j, k, IA)) +
+                   0.25 * SQR(AT(U, i, j, k, IB) + AT(U, i, jp, k, IB)));
+        if (i < isz - 1 && j < jsz - 1) AT(U, i, j, k, IP) = e;
+        else AT(U, i, j, 1, ID) = e;
+      }
+}
+
+static void init_mri(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  if (!P->mhdEnabled || P->dim == 2) return;
+  if (P->bc[0] != BC_SHEARINGBOX || P->bc[1] != BC_SHEARINGBOX) return;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  const double TwoPi = 4.0 * asin(1.0);
+  const double d0 = P->mri_density, beta = P->mri_beta;
+  const double p0 = d0 * P->cIso * P->cIso;
+  double B0;
+  if (!strcmp(P->mri_type, "pyl"))
+    B0 = 3.0 / 2.0 * sqrt(d0 * P->Omega0 * P->Omega0 * (P->zMax - P->zMin) * (P->zMax - P->zMin) / beta);
+  else
+    B0 = 2.0 * sqrt(p0 / beta);
+  const double amp = P->mri_amp, d_amp = P->mri_densfluct;
+  srand48(P->mri_seed);
+  for (int k = 0; k < ksz; ++k)
+    for (int j = 0; j < jsz; ++j)
+      for (int i = 0; i < isz; ++i) {
+        double xPos = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+        AT(U, i, j, k, ID) = d0 * (1 + d_amp * 2 * (drand48() - 0.5));
+        AT(U, i, j, k, IP) = 0;
+        AT(U, i, j, k, IU) = d0 * amp * (drand48() - 0.5) * sqrt(p0);
+        AT(U, i, j, k, IV) = d0 * amp * (drand48() - 0.5) * sqrt(p0);
+        AT(U, i, j, k, IW) = d0 * amp * (drand48() - 0.5) * sqrt(p0);
+        AT(U, i, j, k, IA) = 0;
+        AT(U, i, j, k, IB) = 0;
+        if (!strcmp(P->mri_type, "noflux")) AT(U, i, j, k, IC) = B0 * sin(TwoPi * xPos);
+        else if (!strcmp(P->mri_type, "pyl") || !strcmp(P->mri_type, "fluxZ")) AT(U, i, j, k, IC) = B0;
+        else AT(U, i, j, k, IC) = 0;
+      }
+}
+
+static void fill_corners_gw2(const orc_params *P, real_t *U) {
+  /* HydroRunBase.cpp:5490-5503 / :5526-5543: only when ghostWidth == 2 */
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, nx = P->nx, ny = P->ny, nz = P->nz;
+  if (P->ghostWidth != 2) return;
+  for (int v = 0; v < P->nbVar; ++v) {
+    if (P->dim == 2) {
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+          AT(U, i, j, 0, v) = AT(U, 2, 2, 0, v);
+          AT(U, nx + 2 + i, j, 0, v) = AT(U, nx + 1, 2, 0, v);
+          AT(U, i, ny + 2 + j, 0, v) = AT(U, 2, ny + 1, 0, v);
+          AT(U, nx + 2 + i, ny + 2 + j, 0, v) = AT(U, nx + 1, ny + 1, 0, v);
+        }
+    } else {
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+          for (int k = 0; k < 2; ++k) {
+            AT(U, i, j, k, v) = AT(U, 2, 2, 2, v);
+            AT(U, nx + 2 + i, j, k, v) = AT(U, nx + 1, 2, 2, v);
+            AT(U, i, ny + 2 + j, k, v) = AT(U, 2, ny + 1, 2, v);
+            AT(U, nx + 2 + i, ny + 2 + j, k, v) = AT(U, nx + 1, ny + 1, 2, v);
+            AT(U, i, j, nz + 2 + k, v) = AT(U, 2, 2, nz + 1, v);
+            AT(U, nx + 2 + i, j, nz + 2 + k, v) = AT(U, nx + 1, 2, nz + 1, v);
+            AT(U, i, ny + 2 + j, nz + 2 + k, v) = AT(U, 2, ny + 1, nz + 1, v);
+            AT(U, nx + 2 + i, ny + 2 + j, nz + 2 + k, v) = AT(U, nx + 1, ny + 1, nz + 1, v);
+          }
+    }
+  }
+}
+
+static void init_implode(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  const int nx = P->nx, ny = P->ny, nz = P->nz;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  srand(P->implode_seed);
+  const real_t amplitude = P->implode_amp;
+  if (P->dim == 2) {
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        if (((float)i / nx + (float)j / ny) > 0.5) {
+          AT(U, i, j, 0, ID) = 1.0f + amplitude * (1.0 * rand() / RAND_MAX - 0.5);
+          AT(U, i, j, 0, IP) = 1.0f / (P->gamma0 - 1.0f);
+        } else {
+          AT(U, i, j, 0, ID) = 0.125f + amplitude * (1.0 * rand() / RAND_MAX - 0.5);
+          AT(U, i, j, 0, IP) = 0.14f / (P->gamma0 - 1.0f);
+        }
+        AT(U, i, j, 0, IU) = 0.0f; AT(U, i, j, 0, IV) = 0.0f;
+      }
+  } else {
+    for (int k = gw; k < ksz - gw; ++k)
+      for (int j = gw; j < jsz - gw; ++j)
+        for (int i = gw; i < isz - gw; ++i) {
+          if (((float)i / nx + (float)j / ny + (float)k / nz) > 0.5) {
+            AT(U, i, j, k, ID) = 1.0f + amplitude * (1.0 * rand() / RAND_MAX - 0.5);
+            AT(U, i, j, k, IP) = 1.0f / (P->gamma0 - 1.0f);
+          } else {
+            AT(U, i, j, k, ID) = 0.125f + amplitude * (1.0 * rand() / RAND_MAX - 0.5);
+            AT(U, i, j, k, IP) = 0.14f / (P->gamma0 - 1.0f);
+          }
+          AT(U, i, j, k, IU) = 0.0f; AT(U, i, j, k, IV) = 0.0f; AT(U, i, j, k, IW) = 0.0f;
+        }
+  }
+  fill_corners_gw2(P, U);
+}
+
+/* 3D Kelvin-Helmholtz, perturbation_rand branch only (the one the configs use):
+ * HydroRunBase.cpp:6073-6120; shear layer normal to z. */
+static int init_kelvin_helmholtz(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  srand(P->kh_seed);
+  if (P->dim != 3 || !P->kh_p_rand) {
+    fprintf(stderr, "oracle: Kelvin-Helmholtz variant not restated (3D perturbation_rand only)\n");
+    return -1;
+  }
+  const real_t amplitude = P->kh_amp, rho_inner = P->kh_rho_in, rho_outer = P->kh_rho_out;
+  const real_t pressure = P->kh_pressure, outer_size = P->kh_outer;
+  const real_t vflow_in = P->kh_vin, vflow_out = P->kh_vout;
+  const real_t zSize = P->zMax - P->zMin, zCenter = (P->zMin + P->zMax) / 2;
+  for (int k = gw; k < ksz - gw; ++k) {
+    real_t zPos = P->zMin + P->dz / 2 + (k - gw) * P->dz;
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        real_t rho = (fabs(zPos - zCenter) > outer_size * zSize) ? rho_outer : rho_inner;
+        real_t vf = (fabs(zPos - zCenter) > outer_size * zSize) ? vflow_out : vflow_in;
+        AT(U, i, j, k, ID) = rho;
+        AT(U, i, j, k, IU) = rho * (vf + amplitude * (1.0 * rand() / RAND_MAX - 0.5));
+        AT(U, i, j, k, IV) = rho * (0.0 + amplitude * (1.0 * rand() / RAND_MAX - 0.5));
+        AT(U, i, j, k, IW) = rho * (0.0 + amplitude * (1.0 * rand() / RAND_MAX - 0.5));
+        AT(U, i, j, k, IP) = pressure / (P->gamma0 - 1.0f) +
+            0.5 * (SQR(AT(U, i, j, k, IU)) + SQR(AT(U, i, j, k, IV)) + SQR(AT(U, i, j, k, IW))) / AT(U, i, j, k, ID);
+      }
+  }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
+/* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
+int orc_init_problem(const orc_params *P, real_t *U) {
+  const char *n = P->problem;
+  if (P->mhdEnabled) {
+    if (!strcmp(n, "Orszag-Tang") || !strcmp(n, "OrszagTang")) { init_orszag_tang(P, U); return 0; }
+    if (!strcmp(n, "MRI") || !strcmp(n, "Mri") || !strcmp(n, "mri")) { init_mri(P, U); return 0; }
+  } else {
+    if (!strcmp(n, "implode")) { init_implode(P, U); return 0; }
+    if (!strcmp(n, "Kelvin-Helmholtz")) return init_kelvin_helmholtz(P, U);
+  }
+  fprintf(stderr, "oracle: problem '%s' not restated\n", n);
+  return -1;
+}

@@ -1,0 +1,110 @@
+/*
+ * oracle_run.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Ghost-cell fill, dt dispatch, step dispatch and the start()/oneStepIntegration loop of the
+ * reference, restated in C.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define AT(arr, i, j, k, v) (arr)[(size_t)(i) + (size_t)isz * ((size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(v)))]
+
+/* implemented in the other oracle_*.c files */
+real_t orc_compute_dt_mhd(const orc_params *P, const real_t *U);
+real_t orc_compute_dt_hydro(const orc_params *P, const real_t *U);
+void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt);
+void orc_mhd2d_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt);
+void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt);
+void orc_mhd3d_rotating_step(const orc_params *P, real_t *Uold, real_t *Unew, real_t dt, real_t totalTime);
+void orc_make_all_boundaries_shear(const orc_params *P, real_t *U, real_t dt, real_t totalTime);
+
+/* make_boundary_base.h:1040-1332 (CPU make_boundary2<bct,loc>); one face.
+ * Dirichlet = mirror and flip the NORMAL momentum only, Neumann = copy edge cell,
+ * periodic = wrap.  Full transverse extent (ghost corners included). */
+static void fill_face(const orc_params *P, real_t *U, int face, int bct) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, ng = P->ghostWidth;
+  const int nn[3] = {P->nx, P->ny, P->nz};
+  const int dir = face / 2, hi = face & 1, n = nn[dir];
+  const int normalVar = IU + dir;
+  if (bct != BC_DIRICHLET && bct != BC_NEUMANN && bct != BC_PERIODIC) return;
+  for (int v = 0; v < P->nbVar; ++v)
+    for (int g = 0; g < ng; ++g) {
+      int gi = hi ? n + ng + g : g, src;
+      real_t sign = 1;
+      if (bct == BC_DIRICHLET) {
+        src = hi ? 2 * n + 2 * ng - 1 - gi : 2 * ng - 1 - gi;
+        if (v == normalVar) sign = -1;
+      } else if (bct == BC_NEUMANN) {
+        src = hi ? n + ng - 1 : ng;
+      } else {
+        src = hi ? gi - n : gi + n;
+      }
+      if (dir == 0) {
+        for (int k = 0; k < ksz; ++k) for (int j = 0; j < jsz; ++j) AT(U, gi, j, k, v) = AT(U, src, j, k, v) * sign;
+      } else if (dir == 1) {
+        for (int k = 0; k < ksz; ++k) for (int i = 0; i < isz; ++i) AT(U, i, gi, k, v) = AT(U, i, src, k, v) * sign;
+      } else {
+        for (int j = 0; j < jsz; ++j) for (int i = 0; i < isz; ++i) AT(U, i, j, gi, v) = AT(U, i, j, src, v) * sign;
+      }
+    }
+}
+
+/* HydroRunBase.cpp:2280-2316 */
+void orc_make_boundaries(const orc_params *P, real_t *U, int idim) {
+  int d = idim - 1;
+  if (d == 2 && P->dim == 2) return;
+  fill_face(P, U, 2 * d, P->bc[2 * d]);
+  fill_face(P, U, 2 * d + 1, P->bc[2 * d + 1]);
+}
+
+/* HydroRunBase.cpp:2333-2342: X, then Y, then Z */
+void orc_make_all_boundaries(const orc_params *P, real_t *U) {
+  orc_make_boundaries(P, U, 1);
+  orc_make_boundaries(P, U, 2);
+  if (P->dim == 3) orc_make_boundaries(P, U, 3);
+}
+
+real_t orc_compute_dt(const orc_params *P, const real_t *U) {
+  return P->mhdEnabled ? orc_compute_dt_mhd(P, U) : orc_compute_dt_hydro(P, U);
+}
+
+/* MHDRunGodunov.cpp:572-594 + :1447-1503 (MHD) ; HydroRunGodunov.cpp:1820-1870 (hydro) */
+void orc_godunov_unsplit(const orc_params *P, real_t *Uold, real_t *Unew, real_t dt, real_t totalTime) {
+  if (P->mhdEnabled && P->Omega0 > 0 && P->dim == 3) {
+    orc_mhd3d_rotating_step(P, Uold, Unew, dt, totalTime);
+    return;
+  }
+  orc_make_all_boundaries(P, Uold);
+  memcpy(Unew, Uold, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->mhdEnabled) {
+    if (P->dim == 3) orc_mhd3d_step_v3(P, Uold, Unew, dt);
+    else orc_mhd2d_step_v1(P, Uold, Unew, dt);
+  } else {
+    orc_hydro_step_v1(P, Uold, Unew, dt);
+  }
+}
+
+/* start() prologue + hot loop: MHDRunGodunov.cpp:3801-3921, :4077-4089 ; the caller has
+ * already run orc_init_problem.  Ghost fill of U, copy to U2, then nsteps of
+ * { dt = compute_dt(U or U2 by parity); godunov_unsplit; ++nStep; t += dt }. */
+int orc_run_steps(const orc_params *P, real_t *U, real_t *U2, int nsteps, real_t *t, real_t *dt_trace) {
+  if (P->mhdEnabled && P->Omega0 > 0 && P->dim == 3 && P->bc[0] == BC_SHEARINGBOX)
+    orc_make_all_boundaries_shear(P, U, 0, 0);
+  else
+    orc_make_all_boundaries(P, U);
+  memcpy(U2, U, (size_t)orc_array_len(P) * sizeof(real_t));
+  real_t time = t ? *t : 0;
+  int nStep = 0;
+  for (; nStep < nsteps; ++nStep) {
+    real_t *a = (nStep % 2 == 0) ? U : U2, *b = (nStep % 2 == 0) ? U2 : U;
+    real_t dt = orc_compute_dt(P, a);
+    if (dt_trace) dt_trace[nStep] = dt;
+    orc_godunov_unsplit(P, a, b, dt, time);
+    time += dt;
+  }
+  if (t) *t = time;
+  return nStep % 2;
+}
