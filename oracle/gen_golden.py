@@ -1,0 +1,62 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference executable (oracle/_ref/euler_cpu,
+built by oracle/Makefile.ref).  Run here (where /root/reference exists); the small fixtures are
+committed and travel to the GPU box.
+
+    python oracle/gen_golden.py
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.oracle import run_reference  # noqa: E402
+from ramsesgpu_b200.io import ini_override, read_vti  # noqa: E402
+
+REF_DATA = os.environ.get("RAMSES_REFERENCE", "/root/reference") + "/data"
+OUT = os.path.join(ROOT, "tests", "golden")
+VTK_ON = {"outputVtk": "yes", "outputVtkAscii": "no", "outputHdf5": "no", "outputXsm": "no", "outputPng": "no",
+          "ghostIncluded": "no", "outputDir": "./"}
+
+
+def case(name, ini_file, overrides, steps, precision="f64"):
+    text = open(os.path.join(REF_DATA, ini_file)).read()
+    ov = {k: dict(v) for k, v in overrides.items()}
+    ov.setdefault("run", {}).update({"nstepmax": steps, "noutput": steps, "tend": 1000.0})
+    ov.setdefault("output", {}).update(VTK_ON)
+    text = ini_override(text, ov)
+    stdout, wd = run_reference(text, precision=precision)
+    prefix = re.search(r"outputPrefix=(\S+)", text).group(1)
+    fields = read_vti(os.path.join(wd, "%s_%07d.vti" % (prefix, steps)))
+    init = read_vti(os.path.join(wd, "%s_%07d.vti" % (prefix, 0)))
+    dt0 = float(re.search(r"Initial dt :\s*(\S+)", stdout).group(1))
+    ttot = float(re.search(r"DEBUG : totalTime\s*(\S+)", stdout).group(1))
+    dtl = float(re.search(r"DEBUG : dt\s*(\S+)", stdout).group(1))
+    names = list(fields.keys())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ini=np.array(text), steps=steps, names=np.array(names),
+                        final=np.stack([fields[n] for n in names]), initial=np.stack([init[n] for n in names]),
+                        dt0=dt0, total_time=ttot, dt_last=dtl, precision=np.array(precision))
+    print(name, "steps", steps, "dt0", dt0, "t", ttot, "last dt", dtl, "vars", names)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    cases = {
+        # BASELINE.json configs[1] at a parity size
+        "ot3d_16_s10": ("orszag-tang3d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}}, 10, "f64"),
+        "ot3d_24x16x20_s6": ("orszag-tang3d.ini", {"mesh": {"nx": 24, "ny": 16, "nz": 20}}, 6, "f64"),
+        # transverse wave number kt=1 makes the problem genuinely three-dimensional
+        "ot3d_kt1_16x20x24_s8": ("orszag-tang3d.ini", {"mesh": {"nx": 16, "ny": 20, "nz": 24}, "OrszagTang": {"kt": 1.0}}, 8, "f64"),
+        # non-periodic boundaries + HLL / HLLA solvers on the same problem (edge cases)
+        "ot3d_16_neumann_hll_s4": ("orszag-tang3d.ini", {
+            "mesh": {"nx": 16, "ny": 16, "nz": 16, "boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1,
+                     "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1},
+            "hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hlla"}}, 4, "f64"),
+    }
+    for name, (ini, ov, steps, prec) in cases.items():
+        if only and name not in only:
+            continue
+        case(name, ini, ov, steps, prec)

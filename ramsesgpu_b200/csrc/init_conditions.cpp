@@ -1,0 +1,303 @@
+#include "init_conditions.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+
+namespace rg {
+
+namespace {
+
+// 48-bit linear congruential generator with the constants of POSIX drand48, written out so that a
+// slab can jump to its position in the GLOBAL stream in O(log n).
+class Rand48 {
+ public:
+  explicit Rand48(long seed) : x_(((uint64_t)(uint32_t)seed << 16) | 0x330Eu) {}
+  double next() {
+    x_ = (kA * x_ + kC) & kMask;
+    return (double)x_ * (1.0 / 281474976710656.0);
+  }
+  void skip(uint64_t n) {
+    uint64_t a = kA, c = kC, accA = 1, accC = 0;  // composition of n affine maps
+    while (n) {
+      if (n & 1) { accA = (accA * a) & kMask; accC = (accC * a + c) & kMask; }
+      c = ((a + 1) * c) & kMask;
+      a = (a * a) & kMask;
+      n >>= 1;
+    }
+    x_ = (accA * x_ + accC) & kMask;
+  }
+
+ private:
+  static constexpr uint64_t kA = 0x5DEECE66DULL, kC = 0xB, kMask = (1ULL << 48) - 1;
+  uint64_t x_;
+};
+
+template <typename T>
+struct Grid {
+  const KParams<T>& kp;
+  std::vector<T>& U;
+  size_t plane, comp;
+  Grid(const KParams<T>& k, std::vector<T>& u) : kp(k), U(u) {
+    plane = (size_t)k.isize * k.jsize;
+    comp = plane * k.ksize;
+  }
+  T& at(int v, int i, int j, int k) { return U[(size_t)v * comp + (size_t)k * plane + (size_t)j * kp.isize + i]; }
+};
+
+template <typename T>
+inline T sqr(T x) { return x * x; }
+
+// Orszag-Tang vortex; reference MHDRunBase.cpp:1378-1573 (2D, and 3D with the vortex in x-y)
+template <typename T>
+bool initOrszagTang(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                    std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "MHD must be enabled for Orszag-Tang"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const double TwoPi = 4.0 * std::asin(1.0);
+  const double B0 = 1.0 / std::sqrt(2.0 * TwoPi);
+  const double p0 = (double)(kp.gamma0 / (2.0 * TwoPi));
+  const double d0 = (double)(kp.gamma0 * p0);
+  const double v0 = 1.0;
+  int direction = (int)cfg.getInteger("OrszagTang", "direction", 0);
+  if (direction < 0 || direction > 3) direction = 0;
+  if (rp.dim == 3 && direction != 0) {
+    if (msg) *msg = "Orszag-Tang: only direction=0 (vortex in the x-y plane) is implemented";
+    return false;
+  }
+  const double kt = (rp.dim == 3) ? cfg.getFloat("OrszagTang", "kt", 0.0f) : 0.0;
+  const T dx = kp.dx, dy = kp.dy, dz = kp.dz;
+  for (int k = 0; k < kp.ksize; ++k) {
+    const int kg = k + kp.kglob0;  // index in the global (ghost-inclusive) array
+    const double zPos = kp.zMin + dz / 2 + (kg - gw) * dz;
+    const double cz = (rp.dim == 3) ? std::cos(2 * TwoPi * kt * (zPos - kp.zMin) / (kp.zMax - kp.zMin)) : 1.0;
+    for (int j = 0; j < kp.jsize; ++j) {
+      const double yPos = kp.yMin + dy / 2 + (j - gw) * dy;
+      for (int i = 0; i < kp.isize; ++i) {
+        const double xPos = kp.xMin + dx / 2 + (i - gw) * dx;
+        g.at(ID, i, j, k) = static_cast<T>(d0);
+        g.at(IU, i, j, k) = static_cast<T>(-d0 * v0 * std::sin(yPos * TwoPi));
+        g.at(IV, i, j, k) = static_cast<T>(d0 * v0 * std::sin(xPos * TwoPi));
+        g.at(IW, i, j, k) = T(0);
+        if (rp.dim == 3) {
+          g.at(IA, i, j, k) = static_cast<T>(-B0 * cz * std::sin(yPos * TwoPi));
+          g.at(IB, i, j, k) = static_cast<T>(B0 * cz * std::sin(2.0 * xPos * TwoPi));
+        } else {
+          g.at(IA, i, j, k) = static_cast<T>(-B0 * std::sin(yPos * TwoPi));
+          g.at(IB, i, j, k) = static_cast<T>(B0 * std::sin(2.0 * xPos * TwoPi));
+        }
+        g.at(IC, i, j, k) = T(0);
+      }
+    }
+  }
+  // total energy with the cell-centred field = average of the two faces; the last row/column
+  // (ghost cells, overwritten by the first ghost fill) wraps like the reference's 2D branch
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < kp.jsize; ++j)
+      for (int i = 0; i < kp.isize; ++i) {
+        const bool last = (i == kp.isize - 1) || (j == kp.jsize - 1);
+        if (last && rp.dim == 3) continue;  // the reference never sets these ghost energies in 3D
+        const int ip = (i < kp.isize - 1) ? i + 1 : 2 * gw, jp = (j < kp.jsize - 1) ? j + 1 : 2 * gw;
+        g.at(IP, i, j, k) = p0 / (kp.gamma0 - 1.0) +
+                            0.5 * (sqr(g.at(IU, i, j, k)) / g.at(ID, i, j, k) + sqr(g.at(IV, i, j, k)) / g.at(ID, i, j, k) +
+                                   0.25 * sqr(g.at(IA, i, j, k) + g.at(IA, ip, j, k)) +
+                                   0.25 * sqr(g.at(IB, i, j, k) + g.at(IB, i, jp, k)));
+      }
+  return true;
+}
+
+// MRI in the shearing box (no gravity); reference MHDRunBase.cpp:2677-2760.
+// One drand48 stream over the GLOBAL array in (k,j,i) order, ghosts included, 4 draws per cell.
+template <typename T>
+bool initMri(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled || rp.dim == 2) { if (msg) *msg = "MRI needs 3D MHD"; return false; }
+  if (rp.bc[0] != BC_SHEARINGBOX || rp.bc[1] != BC_SHEARINGBOX) {
+    if (msg) *msg = "MRI needs shearing-box boundaries along x";
+    return false;
+  }
+  Grid<T> g(kp, U);
+  const double TwoPi = 4.0 * std::asin(1.0);
+  const double d0 = cfg.getFloat("MRI", "density", 1.0f);
+  const double beta = cfg.getFloat("MRI", "beta", 400.0f);
+  const double p0 = d0 * kp.cIso * kp.cIso;
+  const std::string type = cfg.getString("MRI", "type", "noflux");
+  const T zMax = cfg.getFloat("mesh", "zmax", 1.0f);
+  double B0;
+  if (type == "pyl") B0 = 3.0 / 2.0 * std::sqrt(d0 * kp.Omega0 * kp.Omega0 * (zMax - kp.zMin) * (zMax - kp.zMin) / beta);
+  else B0 = 2.0 * std::sqrt(p0 / beta);
+  const double amp = cfg.getFloat("MRI", "amp", 0.01f);
+  const long seed = cfg.getInteger("MRI", "seed", 0);
+  const double d_amp = cfg.getFloat("MRI", "density_fluctuations", 0.0f);
+  Rand48 rng(seed);
+  rng.skip((uint64_t)4 * kp.isize * kp.jsize * (uint64_t)kp.kglob0);
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < kp.jsize; ++j)
+      for (int i = 0; i < kp.isize; ++i) {
+        const double xPos = kp.xMin + kp.dx / 2 + (i - kp.gw) * kp.dx;
+        g.at(ID, i, j, k) = d0 * (1 + d_amp * 2 * (rng.next() - 0.5));
+        g.at(IP, i, j, k) = T(0);
+        g.at(IU, i, j, k) = d0 * amp * (rng.next() - 0.5) * std::sqrt(p0);
+        g.at(IV, i, j, k) = d0 * amp * (rng.next() - 0.5) * std::sqrt(p0);
+        g.at(IW, i, j, k) = d0 * amp * (rng.next() - 0.5) * std::sqrt(p0);
+        g.at(IA, i, j, k) = T(0);
+        g.at(IB, i, j, k) = T(0);
+        if (type == "noflux") g.at(IC, i, j, k) = B0 * std::sin(TwoPi * xPos);
+        else if (type == "pyl" || type == "fluxZ") g.at(IC, i, j, k) = B0;
+        else g.at(IC, i, j, k) = T(0);
+      }
+  return true;
+}
+
+// the reference copies the first inner corner cells into the ghost corners when ghostWidth == 2
+// (HydroRunBase.cpp:5490-5503, 5526-5543); only corners this slab owns are touched
+template <typename T>
+void fillCornersGw2(const RunParams& rp, const KParams<T>& kp, Grid<T>& g) {
+  if (kp.gw != 2) return;
+  const int nx = kp.nx, ny = kp.ny;
+  for (int v = 0; v < kp.nvar; ++v) {
+    if (rp.dim == 2) {
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+          g.at(v, i, j, 0) = g.at(v, 2, 2, 0);
+          g.at(v, nx + 2 + i, j, 0) = g.at(v, nx + 1, 2, 0);
+          g.at(v, i, ny + 2 + j, 0) = g.at(v, 2, ny + 1, 0);
+          g.at(v, nx + 2 + i, ny + 2 + j, 0) = g.at(v, nx + 1, ny + 1, 0);
+        }
+    } else {
+      const bool first = kp.kglob0 == 0, last = kp.kglob0 + kp.nz == kp.nzGlobal;
+      const int nz = kp.nz;
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+          for (int k = 0; k < 2; ++k) {
+            if (first) {
+              g.at(v, i, j, k) = g.at(v, 2, 2, 2);
+              g.at(v, nx + 2 + i, j, k) = g.at(v, nx + 1, 2, 2);
+              g.at(v, i, ny + 2 + j, k) = g.at(v, 2, ny + 1, 2);
+              g.at(v, nx + 2 + i, ny + 2 + j, k) = g.at(v, nx + 1, ny + 1, 2);
+            }
+            if (last) {
+              g.at(v, i, j, nz + 2 + k) = g.at(v, 2, 2, nz + 1);
+              g.at(v, nx + 2 + i, j, nz + 2 + k) = g.at(v, nx + 1, 2, nz + 1);
+              g.at(v, i, ny + 2 + j, nz + 2 + k) = g.at(v, 2, ny + 1, nz + 1);
+              g.at(v, nx + 2 + i, ny + 2 + j, nz + 2 + k) = g.at(v, nx + 1, ny + 1, nz + 1);
+            }
+          }
+    }
+  }
+}
+
+// implosion test; reference HydroRunBase.cpp:5449-5545.  glibc rand() stream over the GLOBAL
+// inner cells in (k,j,i) order, one draw per cell.
+template <typename T>
+bool initImplode(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                 std::string* msg) {
+  if (rp.mhdEnabled) { if (msg) *msg = "implode is a hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw, nx = kp.nx, ny = kp.ny, nzg = kp.nzGlobal;
+  std::srand((unsigned)cfg.getInteger("implode", "seed", 1));
+  const T amplitude = cfg.getFloat("implode", "amplitude", 0.0f);
+  if (rp.dim == 2) {
+    for (int j = gw; j < kp.jsize - gw; ++j)
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        const bool hi = ((float)i / nx + (float)j / ny) > 0.5;
+        g.at(ID, i, j, 0) = (hi ? 1.0f : 0.125f) + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5);
+        g.at(IP, i, j, 0) = (hi ? 1.0f : 0.14f) / (kp.gamma0 - 1.0f);
+        g.at(IU, i, j, 0) = 0.0f;
+        g.at(IV, i, j, 0) = 0.0f;
+      }
+  } else {
+    for (long n = (long)kp.kglob0 * nx * ny; n > 0; --n) (void)std::rand();  // draws of the slabs below
+    for (int k = gw; k < kp.ksize - gw; ++k) {
+      const int kg = k + kp.kglob0;
+      for (int j = gw; j < kp.jsize - gw; ++j)
+        for (int i = gw; i < kp.isize - gw; ++i) {
+          const bool hi = ((float)i / nx + (float)j / ny + (float)kg / nzg) > 0.5;
+          g.at(ID, i, j, k) = (hi ? 1.0f : 0.125f) + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5);
+          g.at(IP, i, j, k) = (hi ? 1.0f : 0.14f) / (kp.gamma0 - 1.0f);
+          g.at(IU, i, j, k) = 0.0f;
+          g.at(IV, i, j, k) = 0.0f;
+          g.at(IW, i, j, k) = 0.0f;
+        }
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
+// 3D Kelvin-Helmholtz (shear layer normal to z), random or single-mode perturbation;
+// reference HydroRunBase.cpp:5857-5892 (parameters) and :6073-6175 (3D branches).
+template <typename T>
+bool initKelvinHelmholtz(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                         std::string* msg) {
+  if (rp.mhdEnabled || rp.dim != 3) {
+    if (msg) *msg = "Kelvin-Helmholtz: only the 3D hydro variants are implemented";
+    return false;
+  }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const char* S = "kelvin-helmholtz";
+  std::srand((unsigned)cfg.getInteger(S, "seed", 1));
+  const T amplitude = cfg.getFloat(S, "amplitude", 0.01f);
+  const bool pRand = cfg.getBool(S, "perturbation_rand", true);
+  const bool pSine = cfg.getBool(S, "perturbation_sine", false);
+  if (!pRand && !pSine) {
+    if (msg) *msg = "Kelvin-Helmholtz: only perturbation_rand / perturbation_sine are implemented";
+    return false;
+  }
+  const T rhoIn = cfg.getFloat(S, "rho_inner", 2.0f), rhoOut = cfg.getFloat(S, "rho_outer", 1.0f);
+  const T pressure = cfg.getFloat(S, "pressure", 2.5f);
+  const T outerSize = cfg.getFloat(S, "outer_size", 0.2f);
+  const T vIn = cfg.getFloat(S, "vflow_in", -0.5f), vOut = cfg.getFloat(S, "vflow_out", 0.5f);
+  const T xSize = kp.xMax - kp.xMin, zSize = kp.zMax - kp.zMin;
+  const T zCenter = (kp.zMin + kp.zMax) / 2;
+  if (pRand)
+    for (long n = 3L * kp.kglob0 * kp.nx * kp.ny; n > 0; --n) (void)std::rand();
+  for (int k = gw; k < kp.ksize - gw; ++k) {
+    const T zPos = kp.zMin + kp.dz / 2 + (k + kp.kglob0 - gw) * kp.dz;
+    const bool outer = std::fabs(zPos - zCenter) > outerSize * zSize;
+    const T rho = outer ? rhoOut : rhoIn, vf = outer ? vOut : vIn;
+    for (int j = gw; j < kp.jsize - gw; ++j)
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        g.at(ID, i, j, k) = rho;
+        if (pRand) {
+          g.at(IU, i, j, k) = rho * (vf + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5));
+          g.at(IV, i, j, k) = rho * (0.0 + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5));
+          g.at(IW, i, j, k) = rho * (0.0 + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5));
+        } else {
+          const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+          g.at(IU, i, j, k) = rho * vf;
+          g.at(IV, i, j, k) = rho * T(0);
+          g.at(IW, i, j, k) = rho * (amplitude * std::sin(2.0 * M_PI * xPos / xSize));
+        }
+        g.at(IP, i, j, k) = pressure / (kp.gamma0 - 1.0f) +
+                            0.5 * (sqr(g.at(IU, i, j, k)) + sqr(g.at(IV, i, j, k)) + sqr(g.at(IW, i, j, k))) / g.at(ID, i, j, k);
+      }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
+}  // namespace
+
+template <typename T>
+bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, const std::string& problem,
+                 std::vector<T>& U, std::string* message) {
+  U.assign((size_t)kp.isize * kp.jsize * kp.ksize * kp.nvar, T(0));
+  if (rp.mhdEnabled) {  // reference MHDRunBase.cpp:1286-1342
+    if (problem == "Orszag-Tang" || problem == "OrszagTang") return initOrszagTang(cfg, rp, kp, U, message);
+    if (problem == "MRI" || problem == "Mri" || problem == "mri") return initMri(cfg, rp, kp, U, message);
+  } else {  // reference HydroRunBase.cpp:7023-7100
+    if (problem == "implode") return initImplode(cfg, rp, kp, U, message);
+    if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtz(cfg, rp, kp, U, message);
+  }
+  if (message) *message = "unknown problem name '" + problem + "' for this solver";
+  return false;
+}
+
+template bool initProblem<double>(const ConfigMap&, const RunParams&, const KParams<double>&, const std::string&,
+                                  std::vector<double>&, std::string*);
+template bool initProblem<float>(const ConfigMap&, const RunParams&, const KParams<float>&, const std::string&,
+                                 std::vector<float>&, std::string*);
+
+}  // namespace rg

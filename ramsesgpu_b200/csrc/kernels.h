@@ -1,0 +1,64 @@
+// Launch wrappers of the sm_100a kernels (definitions in kernels_*.cu).  Host-callable, templated on
+// the solver precision; explicit instantiations exist for double and float.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "params.h"
+
+namespace rg {
+
+// Number of components of the "traced state" W written by the trace kernel per cell
+// ("HBM layout"): 8 cell-centred + 6 face B (all advanced by dt/2) + 21 half
+// slopes of the cell-centred variables + 12 half slopes of the face fields.
+constexpr int NW_MHD = 47;
+
+// Scratch for one z-chunk of the 3D MHD step.  All arrays are SoA [component][kk][j][i] with
+// kk = k - kbase and `planes` allocated planes.
+template <typename T>
+struct MhdScratch {
+  T* Q = nullptr;     // 8 components, primitive variables
+  T* W = nullptr;     // NW_MHD components, traced state
+  T* F = nullptr;     // 15 components: flux_x[5], flux_y[5], flux_z[5] at the LOW faces
+  T* E = nullptr;     // 3 components: emf z, y, x at the LOW edges (reference order I_EMFZ=0..)
+  int planes = 0;     // allocated planes per component
+  int kbase = 0;      // k of scratch plane 0 for the chunk being processed
+};
+
+template <typename T>
+struct MhdKernels {
+  // ghost fill of one direction (0,1,2), both faces; reference make_boundary2
+  static void fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
+                           int kLo, int kHi, cudaStream_t s);
+  // max over inner cells of the inverse time step -> *dMaxInvDt (ordered-uint encoding)
+  static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* dMaxInvDt, cudaStream_t s);
+  // 3D MHD chunk pipeline on planes [ka, kb) of the update range
+  static void prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s);
+  static void trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s);
+  static void flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
+  static void emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
+  static void update(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
+                     unsigned long long* dMaxInvDt, cudaStream_t s);
+  // copy planes [k0,k1) of every variable (ghost planes that the update does not touch)
+  static void copyPlanes(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s);
+  // device probes for known-answer tests (n independent problems, arrays are [n][...])
+  static void probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s);
+  static void probeEmf(const KParams<T>& P, int n, int emfDir, const T* qEdge, const T* xPos, T* emf,
+                       cudaStream_t s);
+};
+
+// ordered encoding of a non-negative floating value for atomicMax
+inline double decodeMax(unsigned long long v) {
+  double d;
+  static_assert(sizeof(d) == sizeof(v), "size");
+  __builtin_memcpy(&d, &v, sizeof d);
+  return d;
+}
+
+// launch counter (bench.py's gpu_launches): every wrapper above bumps it once per kernel launch
+unsigned long long kernelLaunchCount();
+void resetKernelLaunchCount();
+
+}  // namespace rg

@@ -1,0 +1,670 @@
+// 3D ideal-MHD Godunov step for sm_100a: prim -> trace -> {fluxes, emfs} -> update(+CT, +next dt).
+//
+// What the reference does with 18 eight-component trace arrays in DRAM (reference
+// MHDRunGodunov.cpp:219-241, mhd_godunov_unsplit_cpu_v3.cpp:172-361) is done here with ONE
+// 47-component "traced state" W per cell from which every face/edge state is rebuilt with adds in
+// the consumer kernels; electric field and magnetic slopes are never materialised.  All arrays are
+// SoA with x fastest so that a warp reads/writes 32 consecutive reals per component.
+//
+// Index ranges follow the reference: prim 0..size-2, trace gw-1..size-gw,
+// flux/emf/update gw..size-gw (inclusive), with the reference's write guards.
+#include <cstdio>
+
+#include "kernels.h"
+#include "mhd_device.cuh"
+
+namespace rg {
+
+namespace {
+
+unsigned long long g_launches = 0;
+
+// W component ids
+enum {
+  W_R = 0, W_P, W_U, W_V, W_W, W_A, W_B, W_C,            // cell centred, advanced by dt/2
+  W_AL, W_AR, W_BL, W_BR, W_CL, W_CR,                    // face fields, advanced by dt/2
+  W_DRX, W_DPX, W_DUX, W_DVX, W_DWX, W_DBX, W_DCX,       // half slopes along x
+  W_DRY, W_DPY, W_DUY, W_DVY, W_DWY, W_DAY, W_DCY,       // half slopes along y
+  W_DRZ, W_DPZ, W_DUZ, W_DVZ, W_DWZ, W_DAZ, W_DBZ,       // half slopes along z
+  W_DALY, W_DALZ, W_DBLX, W_DBLZ, W_DCLX, W_DCLY,        // half slopes of the low-face fields
+  W_DARY, W_DARZ, W_DBRX, W_DBRZ, W_DCRX, W_DCRY         // half slopes of the high-face fields
+};
+static_assert(W_DCRY + 1 == NW_MHD, "W layout");
+
+template <typename T>
+struct View {  // [comp][kk][j][i] accessor of a scratch array
+  T* p;
+  size_t plane, comp;  // isize*jsize, planes*plane
+  int isize, kbase;
+  __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
+    return p[(size_t)c * comp + (size_t)(k - kbase) * plane + (size_t)j * isize + i];
+  }
+};
+template <typename T, typename PT>
+__host__ __device__ inline View<T> view(T* p, const PT& P, int planes, int kbase) {
+  View<T> v;
+  v.p = p;
+  v.plane = (size_t)P.isize * P.jsize;
+  v.comp = v.plane * planes;
+  v.isize = P.isize;
+  v.kbase = kbase;
+  return v;
+}
+template <typename T>
+struct UView {  // the state array [var][k][j][i]
+  const T* p;
+  size_t plane, comp;
+  int isize;
+  __device__ __forceinline__ T operator()(int v, int i, int j, int k) const {
+    return __ldg(p + (size_t)v * comp + (size_t)k * plane + (size_t)j * isize + i);
+  }
+};
+template <typename T>
+__host__ __device__ inline UView<T> uview(const T* p, const KParams<T>& P) {
+  UView<T> v;
+  v.p = p;
+  v.plane = (size_t)P.isize * P.jsize;
+  v.comp = v.plane * P.ksize;
+  v.isize = P.isize;
+  return v;
+}
+
+constexpr int BX = 128;  // threads along x
+
+inline dim3 gridFor(int ni, int nj, int nk) { return dim3((ni + BX - 1) / BX, nj, nk); }
+
+// ------------------------------------------------------------------------------------------------
+// K0: conservative -> primitive (reference MHDRunGodunov.cpp:538-560 + constoprim.h:137-199)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BX) k_prim(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                             T* __restrict__ Qp, int planes, int kbase, int k0, T dt) {
+  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
+  if (i >= P.isize - 1) return;
+  const UView<T> U = uview(Uin, P);
+  const View<T> Q = view(Qp, P, planes, kbase);
+  T u[8], q[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, k);
+  dev::cons_to_prim_mhd(P, u, U(IA, i + 1, j, k), U(IB, i, j + 1, k), U(IC, i, j, k + 1), dt, q);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) Q(v, i, j, k) = q[v];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: slopes + edge electric fields + face-B slopes + half-step trace -> W
+//     (reference cpu_v3.cpp:36-361, slope_mhd.h:436-502/598-704, trace_mhd.h:1854-2030)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BX) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                              const T* __restrict__ Qp, T* __restrict__ Wp, int planes, int kbase,
+                                              int k0, T dt) {
+  const int gw = P.gw;
+  const int i = gw - 1 + blockIdx.x * BX + threadIdx.x, j = gw - 1 + blockIdx.y, k = k0 + blockIdx.z;
+  if (i > P.isize - gw) return;
+  const UView<T> U = uview(Uin, P);
+  const View<const T> Q = view<const T>(Qp, P, planes, kbase);
+  const View<T> W = view(Wp, P, planes, kbase);
+  const T st = P.slope_type;
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  const T h = T(0.5);
+
+  // cell-centred state and its limited HALF slopes
+  T q[8], dx_[8], dy_[8], dz_[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    q[v] = Q(v, i, j, k);
+    if (st == T(0)) {
+      dx_[v] = dy_[v] = dz_[v] = T(0);
+    } else {
+      dx_[v] = h * dev::limited_slope(st, Q(v, i - 1, j, k), q[v], Q(v, i + 1, j, k));
+      dy_[v] = h * dev::limited_slope(st, Q(v, i, j - 1, k), q[v], Q(v, i, j + 1, k));
+      dz_[v] = h * dev::limited_slope(st, Q(v, i, j, k - 1), q[v], Q(v, i, j, k + 1));
+    }
+  }
+  // face fields and their transverse HALF slopes (slope type capped at 2, slope_mhd.h:636)
+  const T xst = dev::mn(st, T(2));
+  T AL = U(IA, i, j, k), AR = U(IA, i + 1, j, k);
+  T BL = U(IB, i, j, k), BR = U(IB, i, j + 1, k);
+  T CL = U(IC, i, j, k), CR = U(IC, i, j, k + 1);
+  const T dALy = h * dev::limited_slope(xst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
+  const T dALz = h * dev::limited_slope(xst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
+  const T dARy = h * dev::limited_slope(xst, U(IA, i + 1, j - 1, k), AR, U(IA, i + 1, j + 1, k));
+  const T dARz = h * dev::limited_slope(xst, U(IA, i + 1, j, k - 1), AR, U(IA, i + 1, j, k + 1));
+  const T dBLx = h * dev::limited_slope(xst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
+  const T dBLz = h * dev::limited_slope(xst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
+  const T dBRx = h * dev::limited_slope(xst, U(IB, i - 1, j + 1, k), BR, U(IB, i + 1, j + 1, k));
+  const T dBRz = h * dev::limited_slope(xst, U(IB, i, j + 1, k - 1), BR, U(IB, i, j + 1, k + 1));
+  const T dCLx = h * dev::limited_slope(xst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
+  const T dCLy = h * dev::limited_slope(xst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
+  const T dCRx = h * dev::limited_slope(xst, U(IC, i - 1, j, k + 1), CR, U(IC, i + 1, j, k + 1));
+  const T dCRy = h * dev::limited_slope(xst, U(IC, i, j - 1, k + 1), CR, U(IC, i, j + 1, k + 1));
+
+  // edge-centred electric fields E = v x B at the 12 edges of the cell (cpu_v3.cpp:36-101)
+  auto Ex = [&](int jj, int kk) {
+    T v = T(0.25) * (Q(IV, i, jj - 1, kk - 1) + Q(IV, i, jj - 1, kk) + Q(IV, i, jj, kk - 1) + Q(IV, i, jj, kk));
+    T w = T(0.25) * (Q(IW, i, jj - 1, kk - 1) + Q(IW, i, jj - 1, kk) + Q(IW, i, jj, kk - 1) + Q(IW, i, jj, kk));
+    T B = h * (U(IB, i, jj, kk - 1) + U(IB, i, jj, kk));
+    T C = h * (U(IC, i, jj - 1, kk) + U(IC, i, jj, kk));
+    return v * C - w * B;
+  };
+  auto Ey = [&](int ii, int kk) {
+    T u = T(0.25) * (Q(IU, ii - 1, j, kk - 1) + Q(IU, ii - 1, j, kk) + Q(IU, ii, j, kk - 1) + Q(IU, ii, j, kk));
+    T w = T(0.25) * (Q(IW, ii - 1, j, kk - 1) + Q(IW, ii - 1, j, kk) + Q(IW, ii, j, kk - 1) + Q(IW, ii, j, kk));
+    T A = h * (U(IA, ii, j, kk - 1) + U(IA, ii, j, kk));
+    T C = h * (U(IC, ii - 1, j, kk) + U(IC, ii, j, kk));
+    return w * A - u * C;
+  };
+  auto Ez = [&](int ii, int jj) {
+    T u = T(0.25) * (Q(IU, ii - 1, jj - 1, k) + Q(IU, ii - 1, jj, k) + Q(IU, ii, jj - 1, k) + Q(IU, ii, jj, k));
+    T v = T(0.25) * (Q(IV, ii - 1, jj - 1, k) + Q(IV, ii - 1, jj, k) + Q(IV, ii, jj - 1, k) + Q(IV, ii, jj, k));
+    T A = h * (U(IA, ii, jj - 1, k) + U(IA, ii, jj, k));
+    T B = h * (U(IB, ii - 1, jj, k) + U(IB, ii, jj, k));
+    return u * B - v * A;
+  };
+  const T ELL = Ex(j, k), ELR = Ex(j, k + 1), ERL = Ex(j + 1, k), ERR = Ex(j + 1, k + 1);
+  const T FLL = Ey(i, k), FLR = Ey(i, k + 1), FRL = Ey(i + 1, k), FRR = Ey(i + 1, k + 1);
+  const T GLL = Ez(i, j), GLR = Ez(i, j + 1), GRL = Ez(i + 1, j), GRR = Ez(i + 1, j + 1);
+
+  // half-step source terms (trace_mhd.h:1985-2011)
+  T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
+  const T drx = dx_[ID], dpx = dx_[IP], dux = dx_[IU], dvx = dx_[IV], dwx = dx_[IW], dBx = dx_[IB], dCx = dx_[IC];
+  const T dry = dy_[ID], dpy = dy_[IP], duy = dy_[IU], dvy = dy_[IV], dwy = dy_[IW], dAy = dy_[IA], dCy = dy_[IC];
+  const T drz = dz_[ID], dpz = dz_[IP], duz = dz_[IU], dvz = dz_[IV], dwz = dz_[IW], dAz = dz_[IA], dBz = dz_[IB];
+  const T dAx = h * (AR - AL), dBy = h * (BR - BL), dCz = h * (CR - CL);
+  const T ir = dev::rcp(r);
+  const T g = P.gamma0;
+
+  T sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
+  T su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx + (-v * duy + B * dAy * ir) * dtdy + (-w * duz + C * dAz * ir) * dtdz;
+  T sv0 = (-u * dvx + A * dBx * ir) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy + (-w * dvz + C * dBz * ir) * dtdz;
+  T sw0 = (-u * dwx + A * dCx * ir) * dtdx + (-v * dwy + B * dCy * ir) * dtdy + (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
+  T sp0 = (-u * dpx - dux * g * p) * dtdx + (-v * dpy - dvy * g * p) * dtdy + (-w * dpz - dwz * g * p) * dtdz;
+  T sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
+  T sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
+  T sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
+  if (P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003
+    const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
+    const T shear = T(-1.5) * P.Omega0 * xPos;
+    sr0 -= shear * dry * dtdy;
+    su0 -= shear * duy * dtdy;
+    sv0 -= shear * dvy * dtdy;
+    sw0 -= shear * dwy * dtdy;
+    sp0 -= shear * dpy * dtdy;
+    sA0 -= shear * dAy * dtdy;
+    sB0 += (shear * dAx - T(1.5) * P.Omega0 * A * P.dx) * dtdx + shear * dBz * dtdz;
+    sC0 -= shear * dCy * dtdy;
+  }
+  AL += (GLR - GLL) * dtdy * h - (FLR - FLL) * dtdz * h;
+  AR += (GRR - GRL) * dtdy * h - (FRR - FRL) * dtdz * h;
+  BL += -(GRL - GLL) * dtdx * h + (ELR - ELL) * dtdz * h;
+  BR += -(GRR - GLR) * dtdx * h + (ERR - ERL) * dtdz * h;
+  CL += (FRL - FLL) * dtdx * h - (ERL - ELL) * dtdy * h;
+  CR += (FRR - FLR) * dtdx * h - (ERR - ELR) * dtdy * h;
+
+  W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
+  W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
+  W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
+  W(W_AL, i, j, k) = AL; W(W_AR, i, j, k) = AR; W(W_BL, i, j, k) = BL;
+  W(W_BR, i, j, k) = BR; W(W_CL, i, j, k) = CL; W(W_CR, i, j, k) = CR;
+  W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
+  W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
+  W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
+  W(W_DWY, i, j, k) = dwy; W(W_DAY, i, j, k) = dAy; W(W_DCY, i, j, k) = dCy;
+  W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
+  W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
+  W(W_DALY, i, j, k) = dALy; W(W_DALZ, i, j, k) = dALz; W(W_DBLX, i, j, k) = dBLx; W(W_DBLZ, i, j, k) = dBLz;
+  W(W_DCLX, i, j, k) = dCLx; W(W_DCLY, i, j, k) = dCLy; W(W_DARY, i, j, k) = dARy; W(W_DARZ, i, j, k) = dARz;
+  W(W_DBRX, i, j, k) = dBRx; W(W_DBRZ, i, j, k) = dBRz; W(W_DCRX, i, j, k) = dCRx; W(W_DCRY, i, j, k) = dCRy;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: HLLD (or HLL/LLF) fluxes at the three low faces (reference cpu_v3.cpp:397-465, trace_mhd.h:2032-2102)
+//     face state = W cell-centred value +/- half slope along the normal, floors on rho and p
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DIR>
+__device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const View<const T>& W, int i, int j, int k,
+                                                    T sgn) {
+  // sgn = +1 : state at the HIGH face of cell (qm), -1 : at the LOW face (qp)
+  constexpr int S = (DIR == 0) ? W_DRX : (DIR == 1) ? W_DRY : W_DRZ;  // first slope component
+  dev::State<T> s;
+  s.r = dev::mx(P.smallr, W(W_R, i, j, k) + sgn * W(S + 0, i, j, k));
+  s.p = dev::mx(P.smallp, W(W_P, i, j, k) + sgn * W(S + 1, i, j, k));
+  const T u = W(W_U, i, j, k) + sgn * W(S + 2, i, j, k);
+  const T v = W(W_V, i, j, k) + sgn * W(S + 3, i, j, k);
+  const T w = W(W_W, i, j, k) + sgn * W(S + 4, i, j, k);
+  if (DIR == 0) {
+    s.u = u; s.v = v; s.w = w;
+    s.a = (sgn > T(0)) ? W(W_AR, i, j, k) : W(W_AL, i, j, k);
+    s.b = W(W_B, i, j, k) + sgn * W(W_DBX, i, j, k);
+    s.c = W(W_C, i, j, k) + sgn * W(W_DCX, i, j, k);
+  } else if (DIR == 1) {  // swap (u,v) and (a,b)
+    s.u = v; s.v = u; s.w = w;
+    s.a = (sgn > T(0)) ? W(W_BR, i, j, k) : W(W_BL, i, j, k);
+    s.b = W(W_A, i, j, k) + sgn * W(W_DAY, i, j, k);
+    s.c = W(W_C, i, j, k) + sgn * W(W_DCY, i, j, k);
+  } else {  // swap (u,w) and (a,c)
+    s.u = w; s.v = v; s.w = u;
+    s.a = (sgn > T(0)) ? W(W_CR, i, j, k) : W(W_CL, i, j, k);
+    s.b = W(W_B, i, j, k) + sgn * W(W_DBZ, i, j, k);
+    s.c = W(W_A, i, j, k) + sgn * W(W_DAZ, i, j, k);
+  }
+  return s;
+}
+
+template <typename T, int DIR>
+__global__ void __launch_bounds__(BX) k_flux(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
+                                             T* __restrict__ Fp, int planes, int kbase, int k0) {
+  const int gw = P.gw;
+  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
+  if (i > P.isize - gw) return;
+  // a face is only needed where both transverse indexes are inner
+  if (DIR != 0 && i >= P.isize - gw) return;
+  if (DIR != 1 && j >= P.jsize - gw) return;
+  if (DIR != 2 && k >= P.ksize - gw) return;
+  const View<const T> W = view<const T>(Wp, P, planes, kbase);
+  const View<T> F = view(Fp, P, planes, kbase);
+  const int il = i - (DIR == 0), jl = j - (DIR == 1), kl = k - (DIR == 2);
+  const dev::State<T> L = face_state<T, DIR>(P, W, il, jl, kl, T(1));
+  const dev::State<T> R = face_state<T, DIR>(P, W, i, j, k, T(-1));
+  T f[8];
+  dev::riemann_mhd(P, L, R, f);
+  // store in physical component order (undo the frame permutation)
+  const int c0 = 5 * DIR;
+  F(c0 + 0, i, j, k) = f[ID];
+  F(c0 + 1, i, j, k) = f[IP];
+  F(c0 + 2, i, j, k) = (DIR == 0) ? f[IU] : (DIR == 1) ? f[IV] : f[IW];
+  F(c0 + 3, i, j, k) = (DIR == 1) ? f[IU] : f[IV];
+  F(c0 + 4, i, j, k) = (DIR == 2) ? f[IU] : f[IW];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: corner emfs with the 2-D HLLD solver (reference cpu_v3.cpp:539-579, trace_mhd.h:2104-2246,
+//     riemann_mhd.h:1054-1193).  EDIR = 2: emf_z from Z-edge states of (i-1,j-1),(i-1,j),(i,j-1),(i,j)
+// ------------------------------------------------------------------------------------------------
+// edge state of cell (i,j,k) for edge direction EDIR, signs (s1, s2) along the two transverse
+// directions (d1,d2) = (x,y) for Z, (x,z) for Y, (y,z) for X; returned in the EDGE frame
+//   Z: u<-U v<-V w<-W a<-A b<-B c<-C ; Y: u<-W v<-U w<-V a<-C b<-A c<-B ; X: u<-V v<-W w<-U a<-B b<-C c<-A
+template <typename T, int EDIR>
+__device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const View<const T>& W, int i, int j, int k,
+                                                     T s1, T s2) {
+  constexpr int S1 = (EDIR == 0) ? W_DRY : W_DRX;  // slopes along d1
+  constexpr int S2 = (EDIR == 2) ? W_DRY : W_DRZ;  // slopes along d2
+  const T r = dev::mx(P.smallr, W(W_R, i, j, k) + (s1 * W(S1 + 0, i, j, k) + s2 * W(S2 + 0, i, j, k)));
+  const T p = dev::mx(P.smallp, W(W_P, i, j, k) + (s1 * W(S1 + 1, i, j, k) + s2 * W(S2 + 1, i, j, k)));
+  const T U = W(W_U, i, j, k) + (s1 * W(S1 + 2, i, j, k) + s2 * W(S2 + 2, i, j, k));
+  const T V = W(W_V, i, j, k) + (s1 * W(S1 + 3, i, j, k) + s2 * W(S2 + 3, i, j, k));
+  const T Wv = W(W_W, i, j, k) + (s1 * W(S1 + 4, i, j, k) + s2 * W(S2 + 4, i, j, k));
+  T A, B, C;
+  if (EDIR == 2) {  // (x,y): A from the x-face on side s1 with its y slope, B from the y-face on side s2 with its x slope
+    A = (s1 > T(0)) ? W(W_AR, i, j, k) + s2 * W(W_DARY, i, j, k) : W(W_AL, i, j, k) + s2 * W(W_DALY, i, j, k);
+    B = (s2 > T(0)) ? W(W_BR, i, j, k) + s1 * W(W_DBRX, i, j, k) : W(W_BL, i, j, k) + s1 * W(W_DBLX, i, j, k);
+    C = W(W_C, i, j, k) + (s1 * W(W_DCX, i, j, k) + s2 * W(W_DCY, i, j, k));
+  } else if (EDIR == 1) {  // (x,z)
+    A = (s1 > T(0)) ? W(W_AR, i, j, k) + s2 * W(W_DARZ, i, j, k) : W(W_AL, i, j, k) + s2 * W(W_DALZ, i, j, k);
+    B = W(W_B, i, j, k) + (s1 * W(W_DBX, i, j, k) + s2 * W(W_DBZ, i, j, k));
+    C = (s2 > T(0)) ? W(W_CR, i, j, k) + s1 * W(W_DCRX, i, j, k) : W(W_CL, i, j, k) + s1 * W(W_DCLX, i, j, k);
+  } else {  // (y,z)
+    A = W(W_A, i, j, k) + (s1 * W(W_DAY, i, j, k) + s2 * W(W_DAZ, i, j, k));
+    B = (s1 > T(0)) ? W(W_BR, i, j, k) + s2 * W(W_DBRZ, i, j, k) : W(W_BL, i, j, k) + s2 * W(W_DBLZ, i, j, k);
+    C = (s2 > T(0)) ? W(W_CR, i, j, k) + s1 * W(W_DCRY, i, j, k) : W(W_CL, i, j, k) + s1 * W(W_DCLY, i, j, k);
+  }
+  dev::Corner<T> c;
+  c.r = r; c.p = p;
+  if (EDIR == 2) { c.u = U; c.v = V; c.w = Wv; c.a = A; c.b = B; c.c = C; }
+  else if (EDIR == 1) { c.u = Wv; c.v = U; c.w = V; c.a = C; c.b = A; c.c = B; }
+  else { c.u = V; c.v = Wv; c.w = U; c.a = B; c.b = C; c.c = A; }
+  return c;
+}
+
+template <typename T, int EDIR>
+__global__ void __launch_bounds__(BX) k_emf(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
+                                            T* __restrict__ Ep, int planes, int kbase, int k0) {
+  const int gw = P.gw;
+  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
+  if (i > P.isize - gw) return;
+  const View<const T> W = view<const T>(Wp, P, planes, kbase);
+  const View<T> E = view(Ep, P, planes, kbase);
+  const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
+  dev::Corner<T> RT, RB, LT, LB;
+  if (EDIR == 2) {  // cpu_v3.cpp:550-557 : (s1,s2) = (x,y)
+    RT = edge_state<T, 2>(P, W, i - 1, j - 1, k, T(1), T(1));
+    RB = edge_state<T, 2>(P, W, i - 1, j, k, T(1), T(-1));
+    LT = edge_state<T, 2>(P, W, i, j - 1, k, T(-1), T(1));
+    LB = edge_state<T, 2>(P, W, i, j, k, T(-1), T(-1));
+  } else if (EDIR == 1) {  // cpu_v3.cpp:561-569 : (s1,s2) = (x,z); RB and LT swapped
+    RT = edge_state<T, 1>(P, W, i - 1, j, k - 1, T(1), T(1));
+    RB = edge_state<T, 1>(P, W, i, j, k - 1, T(-1), T(1));   // LT2(i,j,k-1)
+    LT = edge_state<T, 1>(P, W, i - 1, j, k, T(1), T(-1));   // RB2(i-1,j,k)
+    LB = edge_state<T, 1>(P, W, i, j, k, T(-1), T(-1));
+  } else {  // cpu_v3.cpp:572-579 : (s1,s2) = (y,z)
+    RT = edge_state<T, 0>(P, W, i, j - 1, k - 1, T(1), T(1));
+    RB = edge_state<T, 0>(P, W, i, j - 1, k, T(1), T(-1));
+    LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
+    LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
+  }
+  // reference component order: I_EMFZ = 0, I_EMFY = 1, I_EMFX = 2
+  E(2 - EDIR, i, j, k) = dev::compute_emf(P, RT, RB, LT, LB, EDIR, xPos);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: conservative update + constrained transport + inverse-dt reduction of the NEW state
+//     (reference cpu_v3.cpp:475-533 and :600-630; dt: MHDRunBase.cpp:141-250)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomicMaxOrdered(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BX) k_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                               T* __restrict__ Unew, const T* __restrict__ Fp,
+                                               const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
+                                               unsigned long long* __restrict__ dMaxInvDt) {
+  const int gw = P.gw;
+  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;  // first upper ghost index
+  T invDt = T(0);
+  if (i < P.isize) {
+    const UView<T> U = uview(Uold, P);
+    const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+    const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+    const bool inBox = i >= gw && i <= iN && j >= gw && j <= jN && k >= gw && k <= kN;
+    if (!inBox) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = U(v, i, j, k);
+    } else {
+      const View<const T> F = view<const T>(Fp, P, planes, kbase);
+      const View<const T> E = view<const T>(Ep, P, planes, kbase);
+      const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+      const bool inner = i < iN && j < jN && k < kN;
+      T un[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
+      if (inner) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          // same summation order as the reference's serial scatter
+          T s = un[v];
+          s += F(v, i, j, k) * dtdx;
+          s += F(5 + v, i, j, k) * dtdy;
+          s += F(10 + v, i, j, k) * dtdz;
+          s -= F(v, i + 1, j, k) * dtdx;
+          s -= F(5 + v, i, j + 1, k) * dtdy;
+          s -= F(10 + v, i, j, k + 1) * dtdz;
+          un[v] = s;
+        }
+      }
+      // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,
+      // exactly like the reference's zero-initialised h_emf
+      auto emf = [&](int c, int ii, int jj, int kk) -> T {
+        return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
+      };
+      auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
+        const T ez = emf(0, ii, jj, kk), ey = emf(1, ii, jj, kk), ex = emf(2, ii, jj, kk);
+        if (kk < kN) {
+          bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
+          by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
+        }
+        bx -= (emf(1, ii, jj, kk + 1) - ey) * dtdz;
+        by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
+        bz += (emf(1, ii + 1, jj, kk) - ey) * dtdx;
+        bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
+      };
+      ct(i, j, k, un[IA], un[IB], un[IC]);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
+
+      if (inner) {  // inverse dt of the new state: needs the new B on the three upper faces
+        T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
+        d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
+        d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
+        d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
+        T q[8];
+        dev::cons_to_prim_mhd(P, un, bxp, byp, bzp, T(0), q);
+        const T irho = dev::rcp(q[ID]);
+        const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+        const T bb = a2 + b2 + c2;
+        T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+        T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
+        T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+        if (P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+        invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+      }
+    }
+  }
+  // block max -> one atomic per block
+  if (dMaxInvDt != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) invDt = dev::mx(invDt, __shfl_xor_sync(0xffffffffu, invDt, o));
+    __shared__ T smax[BX / 32];
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = invDt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T m = smax[0];
+#pragma unroll
+      for (int w = 1; w < BX / 32; ++w) m = dev::mx(m, smax[w]);
+      if (m > T(0)) atomicMaxOrdered(dMaxInvDt, (double)m);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BX) k_copy_planes(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                                    T* __restrict__ Unew, int k0) {
+  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
+  if (i >= P.isize) return;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  for (int v = 0; v < P.nvar; ++v) Unew[v * comp + idx] = Uold[v * comp + idx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone inverse-dt reduction (reference MHDRunBase.cpp:141-250 / cmpdt_mhd.cuh:155)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BX) k_invdt(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                              unsigned long long* __restrict__ dMaxInvDt) {
+  const int gw = P.gw;
+  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y;
+  const int k = (P.dim == 3) ? gw + blockIdx.z : 0;
+  T invDt = T(0);
+  if (i < P.isize - gw) {
+    const UView<T> U = uview(Uin, P);
+    T u[8], q[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, k);
+    const T bzp = (P.dim == 3) ? U(IC, i, j, k + 1) : T(0);
+    dev::cons_to_prim_mhd(P, u, U(IA, i + 1, j, k), U(IB, i, j + 1, k), bzp, T(0), q);
+    // 2D: the reference passes magFieldNeighbors[IZ] = 0 (constoprim.h:409)
+    const T irho = dev::rcp(q[ID]);
+    const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+    const T bb = a2 + b2 + c2;
+    T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+    T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
+    if (P.dim == 3) {
+      T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+      if (P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+      invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+    } else {
+      invDt = vx / P.dx + vy / P.dy;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) invDt = dev::mx(invDt, __shfl_xor_sync(0xffffffffu, invDt, o));
+  __shared__ T smax[BX / 32];
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = invDt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T m = smax[0];
+#pragma unroll
+    for (int w = 1; w < BX / 32; ++w) m = dev::mx(m, smax[w]);
+    if (m > T(0)) atomicMaxOrdered(dMaxInvDt, (double)m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ghost fill (reference make_boundary_base.h:1040-1332): one launch per direction, both faces
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_boundary(const __grid_constant__ KParams<T> P, T* __restrict__ U, int dir, int bcLo, int bcHi,
+                           int skipLo, int skipHi, int kLo, int kHi) {
+  // thread = one (ghost slot g in [0, 2*gw), transverse a, transverse b) for all variables
+  const int gw = P.gw;
+  const int sizes[3] = {P.isize, P.jsize, P.ksize};
+  const int nn[3] = {P.nx, P.ny, P.nz};
+  const int n = nn[dir];
+  const int d1 = (dir == 0) ? 1 : 0, d2 = (dir == 2) ? 1 : 2;  // transverse dirs (d1 faster)
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y * blockDim.y + threadIdx.y;
+  const int g = blockIdx.z;
+  if (a >= sizes[d1] || b >= sizes[d2]) return;
+  const bool hi = g >= gw;
+  if (hi ? skipHi : skipLo) return;
+  const int bct = hi ? bcHi : bcLo;
+  if (bct != BC_DIRICHLET && bct != BC_NEUMANN && bct != BC_PERIODIC) return;
+  const int gi = hi ? n + g : g;  // ghost index along dir (hi: n+gw+(g-gw))
+  int src;
+  if (bct == BC_DIRICHLET) src = hi ? 2 * n + 2 * gw - 1 - gi : 2 * gw - 1 - gi;
+  else if (bct == BC_NEUMANN) src = hi ? n + gw - 1 : gw;
+  else src = hi ? gi - n : gi + n;
+  int c[3], s[3];
+  c[dir] = gi; c[d1] = a; c[d2] = b;
+  s[dir] = src; s[d1] = a; s[d2] = b;
+  if (c[2] < kLo || c[2] >= kHi) return;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t o = (size_t)c[2] * plane + (size_t)c[1] * P.isize + c[0];
+  const size_t in = (size_t)s[2] * plane + (size_t)s[1] * P.isize + s[0];
+  const int normalVar = IU + dir;
+  for (int v = 0; v < P.nvar; ++v) {
+    T val = U[v * comp + in];
+    if (bct == BC_DIRICHLET && v == normalVar) val = -val;
+    U[v * comp + o] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes for the known-answer tests
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_probe_riemann(const __grid_constant__ KParams<T> P, int n, const T* ql, const T* qr, T* flux) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const T* l = ql + 8 * t;
+  const T* r = qr + 8 * t;
+  dev::State<T> L{l[ID], l[IP], l[IU], l[IV], l[IW], l[IA], l[IB], l[IC]};
+  dev::State<T> R{r[ID], r[IP], r[IU], r[IV], r[IW], r[IA], r[IB], r[IC]};
+  T f[8];
+  dev::riemann_mhd(P, L, R, f);
+  for (int v = 0; v < 8; ++v) flux[8 * t + v] = f[v];
+}
+
+template <typename T>
+__global__ void k_probe_emf(const __grid_constant__ KParams<T> P, int n, int emfDir, const T* qEdge, const T* xPos,
+                            T* emf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  // qEdge[t][4][8] in the reference's (IRT, IRB, ILT, ILB) x (ID..IC) PHYSICAL layout
+  int iu, iv, iw, ia, ib, ic;
+  if (emfDir == 2) { iu = IU; iv = IV; iw = IW; ia = IA; ib = IB; ic = IC; }
+  else if (emfDir == 1) { iu = IW; iv = IU; iw = IV; ia = IC; ib = IA; ic = IB; }
+  else { iu = IV; iv = IW; iw = IU; ia = IB; ib = IC; ic = IA; }
+  dev::Corner<T> c[4];
+  for (int e = 0; e < 4; ++e) {
+    const T* q = qEdge + (size_t)t * 32 + e * 8;
+    c[e] = dev::Corner<T>{q[ID], q[IP], q[iu], q[iv], q[iw], q[ia], q[ib], q[ic]};
+  }
+  emf[t] = dev::compute_emf(P, c[0], c[1], c[2], c[3], emfDir, xPos ? xPos[t] : T(0));
+}
+
+}  // namespace
+
+unsigned long long kernelLaunchCount() { return g_launches; }
+void resetKernelLaunchCount() { g_launches = 0; }
+
+// ---- launch wrappers ---------------------------------------------------------------------------
+template <typename T>
+void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
+                                 int kLo, int kHi, cudaStream_t s) {
+  if (dir == 2 && P.dim == 2) return;
+  const int sizes[3] = {P.isize, P.jsize, P.ksize};
+  const int d1 = (dir == 0) ? 1 : 0, d2 = (dir == 2) ? 1 : 2;
+  dim3 block(32, 8, 1);
+  dim3 grid((sizes[d1] + 31) / 32, (sizes[d2] + 7) / 8, 2 * P.gw);
+  k_boundary<T><<<grid, block, 0, s>>>(P, U, dir, bcLo, bcHi, skipLo ? 1 : 0, skipHi ? 1 : 0, kLo, kHi);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::computeInvDt(const KParams<T>& P, const T* U, unsigned long long* d, cudaStream_t s) {
+  k_invdt<T><<<gridFor(P.nx, P.ny, P.dim == 3 ? P.nz : 1), BX, 0, s>>>(P, U, d);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_prim<T><<<gridFor(P.isize - 1, P.jsize - 1, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.planes, sc.kbase, k0, dt);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // gw-1 .. size-gw
+  k_trace<T><<<gridFor(n, m, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.W, sc.planes, sc.kbase, k0, dt);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
+  k_flux<T, 0><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
+  k_flux<T, 1><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
+  k_flux<T, 2><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
+  g_launches += 3;
+}
+
+template <typename T>
+void MhdKernels<T>::emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
+  k_emf<T, 2><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
+  k_emf<T, 1><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
+  k_emf<T, 0><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
+  g_launches += 3;
+}
+
+template <typename T>
+void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
+                           unsigned long long* d, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_update<T><<<gridFor(P.isize, P.jsize, k1 - k0), BX, 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0,
+                                                                dt, d);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::copyPlanes(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_copy_planes<T><<<gridFor(P.isize, P.jsize, k1 - k0), BX, 0, s>>>(P, Uold, Unew, k0);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s) {
+  k_probe_riemann<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, ql, qr, flux);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::probeEmf(const KParams<T>& P, int n, int emfDir, const T* qEdge, const T* xPos, T* emf,
+                             cudaStream_t s) {
+  k_probe_emf<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, emfDir, qEdge, xPos, emf);
+  ++g_launches;
+}
+
+template struct MhdKernels<double>;
+template struct MhdKernels<float>;
+
+}  // namespace rg

@@ -1,0 +1,110 @@
+#include "params.h"
+
+#include <algorithm>
+#include <cctype>
+
+namespace rg {
+
+namespace {
+std::string lower(std::string s) {
+  std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return std::tolower(c); });
+  return s;
+}
+}  // namespace
+
+// reference HydroParameters.h:196-271, 352-417, 464-485; MHDRunGodunov.cpp:161-164
+RunParams parseRunParams(const ConfigMap& cfg) {
+  RunParams rp;
+  rp.nStepmax = static_cast<int>(cfg.getInteger("run", "nstepmax", 1000));
+  rp.tEnd = cfg.getFloat("run", "tend", 0.0f);
+  rp.nOutput = static_cast<int>(cfg.getInteger("run", "noutput", 100));
+  rp.nLog = static_cast<int>(cfg.getInteger("run", "nlog", 0));
+  rp.nx = static_cast<int>(cfg.getInteger("mesh", "nx", 2));
+  rp.ny = static_cast<int>(cfg.getInteger("mesh", "ny", 2));
+  rp.nz = static_cast<int>(cfg.getInteger("mesh", "nz", 1));
+  rp.dim = (rp.nz == 1) ? 2 : 3;
+  rp.nbVar = (rp.nz == 1) ? NVAR_2D : NVAR_3D;
+  rp.mhdEnabled = cfg.getBool("MHD", "enable", false);
+  if (rp.mhdEnabled) rp.nbVar = NVAR_MHD;
+  static const char* names[6] = {"boundary_xmin", "boundary_xmax", "boundary_ymin",
+                                 "boundary_ymax", "boundary_zmin", "boundary_zmax"};
+  for (int f = 0; f < 6; ++f) rp.bc[f] = static_cast<int>(cfg.getInteger("mesh", names[f], BC_DIRICHLET));
+  rp.ghostWidth = static_cast<int>(cfg.getInteger("mesh", "ghostWidth", 2));
+  if (rp.ghostWidth != 2 && rp.ghostWidth != 3) rp.ghostWidth = 2;
+  if (rp.mhdEnabled) rp.ghostWidth = 3;
+  rp.problem = cfg.getString("hydro", "problem", "unknown");
+  rp.implementationVersion =
+      static_cast<int>(cfg.getInteger("MHD", "implementationVersion", rp.dim == 2 ? 1 : 4));
+  rp.unsplitVersion = static_cast<int>(cfg.getInteger("hydro", "unsplitVersion", 1));
+  rp.outputVtk = cfg.getBool("output", "outputVtk", true);
+  rp.outputVtkAscii = cfg.getBool("output", "outputVtkAscii", false);
+  rp.outputXsm = cfg.getBool("output", "outputXsm", false);
+  rp.ghostIncluded = cfg.getBool("output", "ghostIncluded", false);
+  rp.outputDir = cfg.getString("output", "outputDir", "./");
+  rp.outputPrefix = cfg.getString("output", "outputPrefix", "output");
+  return rp;
+}
+
+template <typename T>
+KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, int kglob0) {
+  KParams<T> k{};
+  k.nx = rp.nx;
+  k.ny = rp.ny;
+  k.nz = (rp.dim == 2) ? 1 : nzLocal;
+  k.nzGlobal = rp.nz;
+  k.kglob0 = kglob0;
+  k.gw = rp.ghostWidth;
+  k.nvar = rp.nbVar;
+  k.dim = rp.dim;
+  k.isize = k.nx + 2 * k.gw;
+  k.jsize = k.ny + 2 * k.gw;
+  k.ksize = (rp.dim == 2) ? 1 : k.nz + 2 * k.gw;
+  // geometry: float-parsed, arithmetic in T  (HydroParameters.h:238-247)
+  k.xMin = cfg.getFloat("mesh", "xmin", 0.0f);
+  k.xMax = cfg.getFloat("mesh", "xmax", 1.0f);
+  k.yMin = cfg.getFloat("mesh", "ymin", 0.0f);
+  k.yMax = cfg.getFloat("mesh", "ymax", 1.0f);
+  k.zMin = cfg.getFloat("mesh", "zmin", 0.0f);
+  k.zMax = cfg.getFloat("mesh", "zmax", 1.0f);
+  k.dx = (k.xMax - k.xMin) / rp.nx;
+  k.dy = (k.yMax - k.yMin) / rp.ny;
+  k.dz = (k.zMax - k.zMin) / rp.nz;
+  // hydro constants (HydroParameters.h:274-330)
+  k.cfl = cfg.getFloat("hydro", "cfl", 0.5f);
+  if (!k.cfl) k.cfl = T(0.5);
+  k.cIso = cfg.getFloat("hydro", "cIso", 0.0f);
+  k.gamma0 = cfg.getFloat("hydro", "gamma0", 1.4f);
+  k.smallr = cfg.getFloat("hydro", "smallr", 1e-10f);
+  k.smallc = cfg.getFloat("hydro", "smallc", 1e-10f);
+  k.niter_riemann = static_cast<int>(cfg.getInteger("hydro", "niter_riemann", 10));
+  k.smalle = T(1e-7);
+  k.smallp = k.smallc * k.smallc / k.gamma0;
+  if (k.cIso > 0) k.smallp = k.smallr * k.cIso * k.cIso;
+  k.smallpp = k.smallr * k.smallp;
+  k.gamma6 = (k.gamma0 + 1.0f) / (2.0f * k.gamma0);
+  k.Omega0 = cfg.getFloat("MHD", "omega0", 0.0f);
+  k.slope_type = cfg.getFloat("hydro", "slope_type", 1.0f);
+  if (cfg.getInteger("hydro", "traceVersion", 1) == 0) k.slope_type = T(0);
+  // Riemann solver selection (HydroParameters.h:352-417): hlld / llf only exist with MHD
+  std::string rs = lower(cfg.getString("hydro", "riemannSolver", "approx"));
+  k.riemannSolver = RS_APPROX;
+  if (rs == "hll") k.riemannSolver = RS_HLL;
+  else if (rs == "hllc") k.riemannSolver = RS_HLLC;
+  else if (rp.mhdEnabled && rs == "hlld") k.riemannSolver = RS_HLLD;
+  else if (rp.mhdEnabled && rs == "llf") k.riemannSolver = RS_LLF;
+  k.magRiemannSolver = MAG_HLLD;
+  if (rp.mhdEnabled) {
+    std::string ms = lower(cfg.getString("MHD", "magRiemannSolver", "hlld"));
+    if (ms == "hllf") k.magRiemannSolver = MAG_HLLF;
+    else if (ms == "hlla") k.magRiemannSolver = MAG_HLLA;
+    else if (ms == "roe") k.magRiemannSolver = MAG_ROE;
+    else if (ms == "llf") k.magRiemannSolver = MAG_LLF;
+    else if (ms == "upwind") k.magRiemannSolver = MAG_UPWIND;
+  }
+  return k;
+}
+
+template KParams<double> makeKParams<double>(const ConfigMap&, const RunParams&, int, int);
+template KParams<float> makeKParams<float>(const ConfigMap&, const RunParams&, int, int);
+
+}  // namespace rg

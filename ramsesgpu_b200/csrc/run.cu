@@ -1,0 +1,556 @@
+#include "run.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "init_conditions.h"
+#include "kernels.h"
+#include "nccl_dyn.h"
+#include "output.h"
+
+namespace rg {
+
+#define RG_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " +    \
+                               __FILE__ + ":" + std::to_string(__LINE__));                         \
+  } while (0)
+
+// ---- NCCL run-time binding ---------------------------------------------------------------------
+const NcclApi* NcclApi::get(const char** err) {
+  static NcclApi api;
+  static bool tried = false, ok = false;
+  static std::string msg;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // PyTorch's copy if mapped
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      msg = std::string("cannot load libnccl.so.2: ") + dlerror();
+    } else {
+#define RG_SYM(field, name)                                         \
+  *(void**)(&api.field) = dlsym(h, name);                           \
+  if (!api.field) msg += std::string(" missing symbol ") + name;
+      RG_SYM(GetUniqueId, "ncclGetUniqueId")
+      RG_SYM(CommInitRank, "ncclCommInitRank")
+      RG_SYM(CommDestroy, "ncclCommDestroy")
+      RG_SYM(Send, "ncclSend")
+      RG_SYM(Recv, "ncclRecv")
+      RG_SYM(GroupStart, "ncclGroupStart")
+      RG_SYM(GroupEnd, "ncclGroupEnd")
+      RG_SYM(AllReduce, "ncclAllReduce")
+      RG_SYM(GetErrorString, "ncclGetErrorString")
+#undef RG_SYM
+      ok = msg.empty();
+    }
+  }
+  if (!ok) {
+    if (err) *err = msg.c_str();
+    return nullptr;
+  }
+  return &api;
+}
+
+void slabExtent(int nzGlobal, int nranks, int rank, int* nzLocal, int* kOffset) {
+  // contiguous slabs, the first (nz % nranks) ranks get one extra plane
+  const int base = nzGlobal / nranks, rem = nzGlobal % nranks;
+  *nzLocal = base + (rank < rem ? 1 : 0);
+  *kOffset = rank * base + std::min(rank, rem);
+}
+
+namespace {
+
+template <typename T>
+class RunImpl final : public Run {
+ public:
+  RunImpl(const ConfigMap& cfg, const DistInit& dist) : cfg_(cfg), rank_(dist.rank), nranks_(dist.nranks) {
+    rp_ = parseRunParams(cfg_);
+    if (rp_.dim == 2 && nranks_ > 1) throw std::runtime_error("z-slab decomposition needs a 3D run");
+    if (dist.device >= 0) RG_CUDA(cudaSetDevice(dist.device));
+    int nzLocal = rp_.nz, kOff = 0;
+    if (rp_.dim == 3) slabExtent(rp_.nz, nranks_, rank_, &nzLocal, &kOff);
+    if (nranks_ > 1 && nzLocal < rp_.ghostWidth)
+      throw std::runtime_error("z-slab thinner than the ghost width");
+    kp_ = makeKParams<T>(cfg_, rp_, nzLocal, kOff);
+    cells_ = (size_t)kp_.isize * kp_.jsize * kp_.ksize;
+    elems_ = cells_ * kp_.nvar;
+    RG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    RG_CUDA(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+    RG_CUDA(cudaEventCreate(&ev0_));
+    RG_CUDA(cudaEventCreate(&ev1_));
+    RG_CUDA(cudaEventCreateWithFlags(&ev_sync_, cudaEventDisableTiming));
+    RG_CUDA(cudaEventCreate(&evProf0_));
+    RG_CUDA(cudaEventCreate(&evProf1_));
+    for (int b = 0; b < 2; ++b) {
+      RG_CUDA(cudaMalloc(&dU_[b], elems_ * sizeof(T)));
+      RG_CUDA(cudaMemset(dU_[b], 0, elems_ * sizeof(T)));
+    }
+    deviceBytes_ += 2 * elems_ * sizeof(T);
+    RG_CUDA(cudaMalloc(&dMax_, 2 * sizeof(unsigned long long)));
+    RG_CUDA(cudaMemset(dMax_, 0, 2 * sizeof(unsigned long long)));
+    RG_CUDA(cudaMallocHost(&hMax_, 2 * sizeof(unsigned long long)));
+    if (nranks_ > 1) initComm(dist);
+  }
+
+  ~RunImpl() override {
+    cudaDeviceSynchronize();
+    if (comm_ && nccl_) nccl_->CommDestroy(comm_);
+    freeScratch();
+    for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
+    cudaFree(dMax_);
+    cudaFreeHost(hMax_);
+    cudaEventDestroy(ev0_);
+    cudaEventDestroy(ev1_);
+    cudaEventDestroy(ev_sync_);
+    cudaEventDestroy(evProf0_);
+    cudaEventDestroy(evProf1_);
+    recycleEvents();
+    for (cudaEvent_t e : eventPool_) cudaEventDestroy(e);
+    cudaStreamDestroy(stream_);
+    cudaStreamDestroy(comm_stream_);
+  }
+
+  Layout layout() const override {
+    Layout l{};
+    l.nx = rp_.nx; l.ny = rp_.ny; l.nz = rp_.nz;
+    l.isize = kp_.isize; l.jsize = kp_.jsize; l.ksize = kp_.ksize;
+    l.nvar = kp_.nvar; l.ghostWidth = kp_.gw; l.dim = rp_.dim; l.mhd = rp_.mhdEnabled ? 1 : 0;
+    l.realBytes = (int)sizeof(T);
+    l.nzLocal = kp_.nz; l.kOffset = kp_.kglob0; l.rank = rank_; l.nranks = nranks_;
+    return l;
+  }
+  const ConfigMap& config() const override { return cfg_; }
+  const RunParams& runParams() const override { return rp_; }
+
+  double param(const std::string& n, bool* ok) const override {
+    if (ok) *ok = true;
+    if (n == "dx") return kp_.dx;
+    if (n == "dy") return kp_.dy;
+    if (n == "dz") return kp_.dz;
+    if (n == "xmin") return kp_.xMin;
+    if (n == "xmax") return kp_.xMax;
+    if (n == "ymin") return kp_.yMin;
+    if (n == "ymax") return kp_.yMax;
+    if (n == "zmin") return kp_.zMin;
+    if (n == "zmax") return kp_.zMax;
+    if (n == "gamma0") return kp_.gamma0;
+    if (n == "cfl") return kp_.cfl;
+    if (n == "smallr") return kp_.smallr;
+    if (n == "smallc") return kp_.smallc;
+    if (n == "smallp") return kp_.smallp;
+    if (n == "ciso") return kp_.cIso;
+    if (n == "omega0") return kp_.Omega0;
+    if (n == "slope_type") return kp_.slope_type;
+    if (n == "tend") return rp_.tEnd;
+    if (n == "nstepmax") return rp_.nStepmax;
+    if (n == "noutput") return rp_.nOutput;
+    if (n == "riemannsolver") return kp_.riemannSolver;
+    if (n == "magriemannsolver") return kp_.magRiemannSolver;
+    if (ok) *ok = false;
+    return 0.0;
+  }
+
+  // reference MHDRunBase::init_simulation (MHDRunBase.cpp:1231-1360): host IC -> device, U2 = U
+  int init_simulation(const std::string& problemIn) override {
+    const std::string problem = problemIn.empty() ? rp_.problem : problemIn;
+    std::vector<T> h;
+    std::string msg;
+    if (!initProblem<T>(cfg_, rp_, kp_, problem, h, &msg)) {
+      std::fprintf(stderr, "ramsesgpu_b200: %s\n", msg.c_str());
+      lastWarning_ = msg;
+    }
+    RG_CUDA(cudaMemcpyAsync(dU_[0], h.data(), elems_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    RG_CUDA(cudaMemcpyAsync(dU_[1], dU_[0], elems_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    invalidate(0);
+    invalidate(1);
+    totalTime = 0.0;
+    stepCount = 0;
+    return 0;
+  }
+
+  // reference HydroRunBase::make_all_boundaries (HydroRunBase.cpp:2322-2342): X, Y, then Z
+  void make_all_boundaries(int which) override {
+    fillGhosts(which, 0, kp_.ksize);
+    ghostsValid_[which] = true;
+  }
+
+  // reference MHDRunBase::compute_dt_mhd / HydroRunBase::compute_dt: cfl / max inverse dt
+  double compute_dt(int useU) override {
+    const int b = useU ? 1 : 0;
+    if (!dtCached_[b]) {
+      RG_CUDA(cudaMemsetAsync(dMax_ + b, 0, sizeof(unsigned long long), stream_));
+      if (!rp_.mhdEnabled) throw std::runtime_error("hydro compute_dt not available in this build");
+      phase(PH_DT, [&] { MhdKernels<T>::computeInvDt(kp_, dU_[b], dMax_ + b, stream_); });
+      dtCached_[b] = true;
+    }
+    if (nranks_ > 1) {
+      ncclCheck(nccl_->AllReduce(dMax_ + b, dMax_ + b, 1, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_),
+                "allreduce(dt)");
+    }
+    RG_CUDA(cudaMemcpyAsync(hMax_ + b, dMax_ + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    // seed of the running max, reference MHDRunBase.cpp:144
+    T invDt = kp_.smallc / std::min(kp_.dx, kp_.dy);
+    invDt = std::max(invDt, static_cast<T>(decodeMax(hMax_[b])));
+    return static_cast<double>(kp_.cfl / invDt);
+  }
+
+  // reference MHDRunGodunov::godunov_unsplit (MHDRunGodunov.cpp:572-594): even step U -> U2
+  void godunov_unsplit(int nStep, double dt) override {
+    const int src = (nStep % 2 == 0) ? 0 : 1, dst = 1 - src;
+    RG_CUDA(cudaEventRecord(ev0_, stream_));
+    if (!ghostsValid_[src]) make_all_boundaries(src);
+    if (rp_.mhdEnabled && rp_.dim == 3 && !(kp_.Omega0 > T(0))) {
+      stepMhd3d(src, dst, static_cast<T>(dt));
+    } else {
+      throw std::runtime_error("this solver variant is not available in this build");
+    }
+    RG_CUDA(cudaEventRecord(ev1_, stream_));
+    timed_ = true;
+  }
+
+  // reference MHDRunGodunov::oneStepIntegration (MHDRunGodunov.cpp:4077-4089)
+  void oneStepIntegration(int& nStep, double& t, double& dt) override {
+    dt = compute_dt(nStep % 2);
+    godunov_unsplit(nStep, dt);
+    nStep++;
+    // the reference accumulates time in real_t
+    t = static_cast<double>(static_cast<T>(t) + static_cast<T>(dt));
+  }
+
+  // reference MHDRunGodunov::start (MHDRunGodunov.cpp:3801-4070), outputs every nOutput steps
+  void start() override {
+    int nStep = init_simulation("");
+    make_all_boundaries(0);
+    RG_CUDA(cudaMemcpyAsync(dU_[1], dU_[0], elems_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    ghostsValid_[1] = true;
+    dtCached_[1] = false;
+    double t = 0.0, dt = compute_dt(0);
+    if (rank_ == 0) std::printf("Initial dt : %.12g\n", dt);
+    const auto t0 = std::chrono::steady_clock::now();
+    double ioSeconds = 0.0;
+    while (t < rp_.tEnd && nStep < rp_.nStepmax) {
+      if (rp_.nOutput > 0 && (nStep % rp_.nOutput) == 0) {
+        const auto a = std::chrono::steady_clock::now();
+        stepCount = nStep; totalTime = t;
+        output(nStep);
+        ioSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+        if (rank_ == 0) std::printf("step=%9d t=%.10g dt=%.12g\n", nStep, t, dt);
+      }
+      oneStepIntegration(nStep, t, dt);
+    }
+    synchronize();
+    stepCount = nStep; totalTime = t;
+    {
+      const auto a = std::chrono::steady_clock::now();
+      output(nStep);
+      ioSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+    }
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rank_ == 0) {
+      // the reference's metric line, MHDRunGodunov.cpp:4064-4068
+      std::printf("total time: %5.3f sec, output time: %5.3f sec\n", wall, ioSeconds);
+      std::printf("####################################\nGlobal performance                  \n%g cell updates per seconds (based on wall time)\n####################################\n",
+                  1.0 * nStep * rp_.nx * rp_.ny * rp_.nz / (wall - ioSeconds));
+    }
+  }
+
+  void output(int nStep) override {
+    std::vector<T> h(elems_);
+    copyToHost(nStep % 2, h.data(), elems_ * sizeof(T));
+    writeOutputs<T>(rp_, layout(), h.data(), nStep);
+  }
+
+  void copyToHost(int which, void* dst, size_t bytes) override {
+    checkBytes(bytes);
+    RG_CUDA(cudaMemcpyAsync(dst, dU_[which ? 1 : 0], bytes, cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+  }
+  void copyFromHost(int which, const void* src, size_t bytes) override {
+    checkBytes(bytes);
+    RG_CUDA(cudaMemcpyAsync(dU_[which ? 1 : 0], src, bytes, cudaMemcpyHostToDevice, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    invalidate(which ? 1 : 0);
+  }
+  void* deviceData(int which) override { return dU_[which ? 1 : 0]; }
+  void synchronize() override {
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    RG_CUDA(cudaStreamSynchronize(comm_stream_));
+  }
+
+  void stepsFromHost(const void* hostIn, void* hostOut, size_t bytes, int nSteps, double* tOut, double* dtLast) override {
+    checkBytes(bytes);
+    RG_CUDA(cudaMemcpyAsync(dU_[0], hostIn, bytes, cudaMemcpyHostToDevice, stream_));
+    invalidate(0);
+    invalidate(1);
+    int nStep = 0;
+    double t = 0.0, dt = 0.0;
+    for (int s = 0; s < nSteps; ++s) oneStepIntegration(nStep, t, dt);
+    RG_CUDA(cudaMemcpyAsync(hostOut, dU_[nStep % 2], bytes, cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    if (tOut) *tOut = t;
+    if (dtLast) *dtLast = dt;
+  }
+
+  Stats stats() const override {
+    Stats s{};
+    s.kernelLaunches = kernelLaunchCount();
+    s.lastStepMs = 0.0;
+    if (timed_) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(ev1_) == cudaSuccess && cudaEventElapsedTime(&ms, ev0_, ev1_) == cudaSuccess)
+        s.lastStepMs = ms;
+    }
+    s.haloBytesPerStep = haloBytesPerStep_;
+    s.deviceBytes = deviceBytes_;
+    s.chunkPlanes = chunkPlanes_;
+    return s;
+  }
+
+  void setChunkPlanes(int planes) override {
+    userChunk_ = planes;
+    freeScratch();
+  }
+
+  void probeRiemann(int n, const void* ql, const void* qr, void* flux) override {
+    T *dl, *dr, *df;
+    RG_CUDA(cudaMalloc(&dl, n * 8 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&dr, n * 8 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&df, n * 8 * sizeof(T)));
+    RG_CUDA(cudaMemcpy(dl, ql, n * 8 * sizeof(T), cudaMemcpyHostToDevice));
+    RG_CUDA(cudaMemcpy(dr, qr, n * 8 * sizeof(T), cudaMemcpyHostToDevice));
+    MhdKernels<T>::probeRiemann(kp_, n, dl, dr, df, stream_);
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    RG_CUDA(cudaMemcpy(flux, df, n * 8 * sizeof(T), cudaMemcpyDeviceToHost));
+    cudaFree(dl); cudaFree(dr); cudaFree(df);
+  }
+  void probeEmf(int n, int emfDir, const void* qEdge, const void* xPos, void* emf) override {
+    T *dq, *dx = nullptr, *de;
+    RG_CUDA(cudaMalloc(&dq, n * 32 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&de, n * sizeof(T)));
+    RG_CUDA(cudaMemcpy(dq, qEdge, n * 32 * sizeof(T), cudaMemcpyHostToDevice));
+    if (xPos) {
+      RG_CUDA(cudaMalloc(&dx, n * sizeof(T)));
+      RG_CUDA(cudaMemcpy(dx, xPos, n * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    MhdKernels<T>::probeEmf(kp_, n, emfDir, dq, dx, de, stream_);
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    RG_CUDA(cudaMemcpy(emf, de, n * sizeof(T), cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(de);
+    if (dx) cudaFree(dx);
+  }
+
+ public:
+  void profileBegin() override {
+    recycleEvents();
+    profiling_ = true;
+    RG_CUDA(cudaEventRecord(evProf0_, stream_));
+  }
+  void profileEnd(double* totalMs, double* phaseMs, unsigned long long* phaseLaunches) override {
+    RG_CUDA(cudaEventRecord(evProf1_, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    profiling_ = false;
+    float ms = 0.f;
+    RG_CUDA(cudaEventElapsedTime(&ms, evProf0_, evProf1_));
+    if (totalMs) *totalMs = ms;
+    double acc[PH_COUNT] = {0};
+    unsigned long long cnt[PH_COUNT] = {0};
+    for (const Span& sp : spans_) {
+      RG_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+      acc[sp.phase] += ms;
+      cnt[sp.phase] += sp.launches;
+    }
+    for (int p = 0; p < PH_COUNT; ++p) {
+      if (phaseMs) phaseMs[p] = acc[p];
+      if (phaseLaunches) phaseLaunches[p] = cnt[p];
+    }
+    recycleEvents();
+  }
+
+ private:
+  struct Span { int phase; cudaEvent_t a, b; unsigned long long launches; };
+  cudaEvent_t newEvent() {
+    if (!eventPool_.empty()) { cudaEvent_t e = eventPool_.back(); eventPool_.pop_back(); return e; }
+    cudaEvent_t e;
+    RG_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void recycleEvents() {
+    for (const Span& sp : spans_) { eventPool_.push_back(sp.a); eventPool_.push_back(sp.b); }
+    spans_.clear();
+  }
+  // runs `fn` (kernel launches on stream_) and, when profiling, brackets it with events
+  template <typename F>
+  void phase(int ph, F&& fn) {
+    if (!profiling_) { fn(); return; }
+    Span sp{ph, newEvent(), newEvent(), kernelLaunchCount()};
+    RG_CUDA(cudaEventRecord(sp.a, stream_));
+    fn();
+    RG_CUDA(cudaEventRecord(sp.b, stream_));
+    sp.launches = kernelLaunchCount() - sp.launches;
+    spans_.push_back(sp);
+  }
+
+  void checkBytes(size_t bytes) const {
+    if (bytes != elems_ * sizeof(T)) throw std::runtime_error("host buffer size does not match the state array");
+  }
+  void invalidate(int b) { ghostsValid_[b] = false; dtCached_[b] = false; }
+
+  void ncclCheck(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + nccl_->GetErrorString(rc));
+  }
+
+  void initComm(const DistInit& dist) {
+    const char* err = nullptr;
+    nccl_ = NcclApi::get(&err);
+    if (!nccl_) throw std::runtime_error(err ? err : "NCCL unavailable");
+    if (!dist.ncclUniqueId) throw std::runtime_error("nranks > 1 needs an NCCL unique id");
+    NcclApi::UniqueId id;
+    std::memcpy(&id, dist.ncclUniqueId, sizeof id);
+    ncclCheck(nccl_->CommInitRank(&comm_, nranks_, id, rank_), "ncclCommInitRank");
+  }
+
+  // ---- ghost cells -------------------------------------------------------------------------------
+  // x and y faces are always local; z faces are local for a single slab, otherwise the gw planes
+  // next to each slab interface travel over NCCL (reference: copy_boundaries + transfert_boundaries
+  // + make_boundary, HydroRunBaseMpi.cpp:3294-3389, without the host staging).
+  void fillGhosts(int b, int kLo, int kHi) {
+    T* U = dU_[b];
+    phase(PH_BOUNDARY, [&] {
+      MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
+      MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
+      if (rp_.dim == 3 && nranks_ == 1)
+        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
+    });
+    if (rp_.dim == 2 || nranks_ == 1) return;
+    const bool periodic = rp_.bc[4] == BC_PERIODIC && rp_.bc[5] == BC_PERIODIC;
+    const bool hasLo = rank_ > 0 || periodic, hasHi = rank_ < nranks_ - 1 || periodic;
+    // physical z faces of the outermost slabs
+    if (!hasLo || !hasHi)
+      phase(PH_BOUNDARY, [&] {
+        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
+      });
+    phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi); });
+  }
+
+  void exchangeZ(T* U, bool hasLo, bool hasHi) {
+    const int gw = kp_.gw, lo = (rank_ + nranks_ - 1) % nranks_, hi = (rank_ + 1) % nranks_;
+    const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
+    const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
+    ncclCheck(nccl_->GroupStart(), "group start");
+    for (int v = 0; v < kp_.nvar; ++v) {
+      T* base = U + (size_t)v * comp;
+      if (hasHi) ncclCheck(nccl_->Send(base + (size_t)(kp_.ksize - 2 * gw) * plane, n, dtype, hi, comm_, stream_), "send up");
+      if (hasLo) ncclCheck(nccl_->Send(base + (size_t)gw * plane, n, dtype, lo, comm_, stream_), "send down");
+      if (hasLo) ncclCheck(nccl_->Recv(base, n, dtype, lo, comm_, stream_), "recv from below");
+      if (hasHi) ncclCheck(nccl_->Recv(base + (size_t)(kp_.ksize - gw) * plane, n, dtype, hi, comm_, stream_), "recv from above");
+    }
+    ncclCheck(nccl_->GroupEnd(), "group end");
+    haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
+  }
+
+  // ---- scratch / chunking ------------------------------------------------------------------------
+  void freeScratch() {
+    if (sc_.Q) { cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); }
+    if (sc_.Q) deviceBytes_ -= scratchBytes_;
+    sc_ = MhdScratch<T>();
+    scratchBytes_ = 0;
+    chunkPlanes_ = 0;
+  }
+
+  void ensureScratchMhd3d() {
+    if (sc_.Q) return;
+    const size_t plane = (size_t)kp_.isize * kp_.jsize;
+    const size_t perPlane = plane * sizeof(T) * (8 + NW_MHD + 15 + 3);
+    const int updPlanes = kp_.ksize - 2 * kp_.gw + 1;  // gw .. ksize-gw inclusive
+    int chunk = updPlanes;
+    size_t freeB = 0, totalB = 0;
+    RG_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t budget = (size_t)(0.85 * (double)freeB);
+    const long fit = (long)(budget / perPlane) - 4;
+    if (fit < chunk) chunk = (int)std::max<long>(fit, 1);
+    if (userChunk_ > 0) chunk = std::min(userChunk_, updPlanes);
+    chunkPlanes_ = chunk;
+    sc_.planes = chunk + 4;
+    RG_CUDA(cudaMalloc(&sc_.Q, plane * sc_.planes * 8 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&sc_.W, plane * sc_.planes * NW_MHD * sizeof(T)));
+    RG_CUDA(cudaMalloc(&sc_.F, plane * sc_.planes * 15 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&sc_.E, plane * sc_.planes * 3 * sizeof(T)));
+    scratchBytes_ = perPlane * sc_.planes;
+    deviceBytes_ += scratchBytes_;
+  }
+
+  // ---- 3D MHD step: reference godunov_unsplit_cpu/gpu (MHDRunGodunov.cpp:623-672, 1447-1503) ------
+  void stepMhd3d(int src, int dst, T dt) {
+    ensureScratchMhd3d();
+    const T* Uold = dU_[src];
+    T* Unew = dU_[dst];
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    RG_CUDA(cudaMemsetAsync(dMax_ + dst, 0, sizeof(unsigned long long), stream_));
+    // ghost planes outside the update box keep the (ghost-filled) old values, like copyTo
+    phase(PH_COPY, [&] {
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN + 1, kp_.ksize, stream_);
+    });
+    for (int ka = gw; ka <= kN; ka += chunkPlanes_) {
+      const int kb = std::min(ka + chunkPlanes_, kN + 1);
+      const int fhi = std::min(kb, kN);
+      MhdScratch<T> sc = sc_;
+      sc.kbase = ka - 2;
+      phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
+      phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
+      phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
+      phase(PH_UPDATE, [&] { MhdKernels<T>::update(kp_, Uold, Unew, sc, ka, kb, dt, dMax_ + dst, stream_); });
+    }
+    ghostsValid_[dst] = false;
+    dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
+  }
+
+  ConfigMap cfg_;
+  RunParams rp_;
+  KParams<T> kp_;
+  int rank_, nranks_;
+  size_t cells_ = 0, elems_ = 0, deviceBytes_ = 0, scratchBytes_ = 0;
+  T* dU_[2] = {nullptr, nullptr};
+  MhdScratch<T> sc_;
+  int chunkPlanes_ = 0, userChunk_ = 0;
+  unsigned long long* dMax_ = nullptr;
+  unsigned long long* hMax_ = nullptr;
+  bool ghostsValid_[2] = {false, false}, dtCached_[2] = {false, false};
+  cudaStream_t stream_ = nullptr, comm_stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_sync_ = nullptr;
+  bool timed_ = false;
+  bool profiling_ = false;
+  cudaEvent_t evProf0_ = nullptr, evProf1_ = nullptr;
+  std::vector<Span> spans_;
+  std::vector<cudaEvent_t> eventPool_;
+  const NcclApi* nccl_ = nullptr;
+  NcclApi::comm_t comm_ = nullptr;
+  double haloBytesPerStep_ = 0.0;
+  std::string lastWarning_;
+};
+
+}  // namespace
+
+std::unique_ptr<Run> Run::create(const ConfigMap& cfg, bool fp32, const DistInit& dist) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw std::runtime_error("ramsesgpu_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+  if (fp32) return std::unique_ptr<Run>(new RunImpl<float>(cfg, dist));
+  return std::unique_ptr<Run>(new RunImpl<double>(cfg, dist));
+}
+
+}  // namespace rg

@@ -1,0 +1,169 @@
+"""GPU: parity of the CUDA 3D MHD path (through the C ABI) against
+  (1) golden vectors generated from the unmodified reference executable,
+  (2) the C oracle on the same seeded random inputs,
+  (3) size-independent properties at larger sizes (div B, conservation, chunk invariance)."""
+import numpy as np
+import pytest
+
+from conftest import TOL_F64, load_golden, ot3d_ini
+from ramsesgpu_b200.io import l2_relative
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4"]
+
+
+def run_gpu_steps(ini, nsteps, U0=None, chunk=0):
+    from ramsesgpu_b200 import MHDRunGodunov
+    with MHDRunGodunov(ini) as run:
+        if chunk:
+            run.set_chunk_planes(chunk)
+        run.init_simulation()
+        if U0 is not None:
+            run.setDataHost(U0, 0)
+        # start(): ghost fill of U, U2 = U (MHDRunGodunov.cpp:3827-3839)
+        run.make_all_boundaries(0)
+        run.setDataHost(run.getDataHost(0), 1)
+        n, t, dt, dts = 0, 0.0, 0.0, []
+        for _ in range(nsteps):
+            n, t, dt = run.oneStepIntegration(n, t, dt)
+            dts.append(dt)
+        return run.getDataHost(n), t, np.array(dts), run.layout.ghost_width
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_reference_run(native, name):
+    g = load_golden(name)
+    U, t, dts, gw = run_gpu_steps(str(g["ini"]), int(g["steps"]))
+    inner = U[:, gw:-gw, gw:-gw, gw:-gw]
+    for v, vname in enumerate(g["names"]):
+        err = l2_relative(g["final"][v], inner[v])
+        assert err < TOL_F64, (name, vname, err)
+    assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
+    assert abs(dts[-1] - g["dt_last"]) < 1e-10 * g["dt_last"]
+
+
+def test_initial_condition_and_dt(native, oracle64):
+    from ramsesgpu_b200 import MHDRunGodunov
+    ini = ot3d_ini((20, 16, 12), OrszagTang={"kt": 1.0})
+    p = oracle64.params(ini)
+    Uo = oracle64.init_problem(p)
+    with MHDRunGodunov(ini) as run:
+        run.init_simulation()
+        U = run.getDataHost(0)
+        g = p.ghostWidth
+        assert np.array_equal(U[:, g:-g, g:-g, g:-g], Uo[:, g:-g, g:-g, g:-g])
+        run.make_all_boundaries(0)
+        oracle64.make_all_boundaries(p, Uo)
+        assert np.array_equal(run.getDataHost(0), Uo)           # ghost fill is a pure copy: bitwise
+        dt = run.compute_dt(0)
+        assert abs(dt - oracle64.compute_dt(p, Uo)) < 1e-14 * dt
+
+
+def smooth_random_state(p, seed):
+    """A smooth, genuinely 3D, div-B-free-ish periodic state with all 8 variables active."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = p.ksize, p.jsize, p.isize
+    g = p.ghostWidth
+    z, y, x = np.meshgrid((np.arange(nz) - g) / p.nz, (np.arange(ny) - g) / p.ny, (np.arange(nx) - g) / p.nx, indexing="ij")
+    def field(amp):
+        f = np.zeros_like(x)
+        for _ in range(3):
+            kx, ky, kz = rng.integers(1, 3, size=3)
+            ph = rng.uniform(0, 2 * np.pi, size=3)
+            f += amp * np.sin(2 * np.pi * kx * x + ph[0]) * np.cos(2 * np.pi * ky * y + ph[1]) * np.sin(2 * np.pi * kz * z + ph[2])
+        return f
+    U = np.zeros((8, nz, ny, nx))
+    U[0] = 1.0 + field(0.1)
+    for v in (2, 3, 4):
+        U[v] = U[0] * field(0.3)
+    for v in (5, 6, 7):
+        U[v] = 0.3 + field(0.2)
+    ek = 0.5 * (U[2] ** 2 + U[3] ** 2 + U[4] ** 2) / U[0]
+    em = 0.5 * (U[5] ** 2 + U[6] ** 2 + U[7] ** 2)
+    U[1] = (1.0 + field(0.2)) / (p.gamma0 - 1.0) + ek + em * 1.5
+    return U
+
+
+@pytest.mark.parametrize("seed,n,over", [
+    (1, (16, 12, 20), {}),
+    (2, (12, 20, 16), {"hydro": {"slope_type": 1.0}}),
+    (3, (16, 16, 16), {"hydro": {"riemannSolver": "llf"}, "MHD": {"magRiemannSolver": "llf"}}),
+    (4, (16, 16, 16), {"hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hllf"}}),
+    (5, (14, 18, 10), {"hydro": {"cIso": 0.8}}),
+])
+def test_random_state_vs_oracle(native, oracle64, seed, n, over):
+    ini = ot3d_ini(n, **over)
+    p = oracle64.params(ini)
+    U0 = smooth_random_state(p, seed)
+    nsteps = 3
+    Ug, tg, dtg, gw = run_gpu_steps(ini, nsteps, U0=U0)
+    Uo, to, dto = oracle64.run_steps(p, U0.copy(), nsteps)
+    for v in range(8):
+        err = l2_relative(Uo[v, gw:-gw, gw:-gw, gw:-gw], Ug[v, gw:-gw, gw:-gw, gw:-gw])
+        assert err < TOL_F64, (v, err)
+    assert np.allclose(dtg, dto, rtol=1e-12)
+
+
+def test_chunked_pipeline_is_identical(native):
+    """z-chunking of the step pipeline (the single-GPU answer to grids whose scratch does not fit)
+    must not change a single bit."""
+    ini = ot3d_ini((16, 16, 24), OrszagTang={"kt": 1.0})
+    ref, _, _, _ = run_gpu_steps(ini, 3)
+    for chunk in (1, 5, 7):
+        got, _, _, _ = run_gpu_steps(ini, 3, chunk=chunk)
+        assert np.array_equal(ref, got), chunk
+
+
+def test_divb_and_conservation_full_size_properties(native):
+    """Properties that do not need the oracle: constrained transport keeps div B at round-off and the
+    periodic box conserves mass, momentum and energy to round-off (64^3, 20 steps)."""
+    ini = ot3d_ini((64, 64, 64), OrszagTang={"kt": 1.0})
+    from ramsesgpu_b200 import MHDRunGodunov
+    with MHDRunGodunov(ini) as run:
+        run.init_simulation()
+        run.make_all_boundaries(0)
+        run.setDataHost(run.getDataHost(0), 1)
+        g = run.layout.ghost_width
+        U0 = run.getDataHost(0)
+        n, t, dt = 0, 0.0, 0.0
+        for _ in range(20):
+            n, t, dt = run.oneStepIntegration(n, t, dt)
+        run.make_all_boundaries(n % 2)
+        U = run.getDataHost(n)
+        dx, dy, dz = run.param("dx"), run.param("dy"), run.param("dz")
+    def divb(A):
+        s = np.s_[g:-g]
+        return ((A[5, g:-g, g:-g, g + 1:A.shape[3] - g + 1] - A[5, s, s, s]) / dx +
+                (A[6, g:-g, g + 1:A.shape[2] - g + 1, g:-g] - A[6, s, s, s]) / dy +
+                (A[7, g + 1:A.shape[1] - g + 1, g:-g, g:-g] - A[7, s, s, s]) / dz)
+    assert np.abs(divb(U)).max() < 1e-11
+    for v in range(5):
+        a, b = U0[v, g:-g, g:-g, g:-g].sum(), U[v, g:-g, g:-g, g:-g].sum()
+        scale = np.abs(U0[v, g:-g, g:-g, g:-g]).sum() + 1.0
+        assert abs(a - b) / scale < 1e-12, (v, a, b)
+
+
+def test_device_probes_vs_oracle(native, oracle64):
+    """riemann_hlld and compute_emf<X,Y,Z> on 4096 random states, device vs oracle."""
+    from ramsesgpu_b200 import MHDRunGodunov
+    ini = ot3d_ini((8, 8, 8))
+    p = oracle64.params(ini)
+    rng = np.random.default_rng(7)
+    n = 4096
+    def states(m):
+        q = np.empty((m, 8))
+        q[:, 0] = rng.uniform(0.5, 2.0, m); q[:, 1] = rng.uniform(0.3, 2.0, m)
+        q[:, 2:5] = rng.uniform(-1, 1, (m, 3)); q[:, 5:8] = rng.uniform(-1, 1, (m, 3))
+        return q
+    ql, qr = states(n), states(n)
+    qe = states(4 * n).reshape(n, 4, 8)
+    qe += 0.0
+    with MHDRunGodunov(ini) as run:
+        f = run.probe_riemann_mhd(ql, qr)
+        fo = np.array([oracle64.riemann_mhd(p, ql[i], qr[i]) for i in range(n)])
+        assert np.allclose(f, fo, rtol=1e-11, atol=1e-12)
+        for d in range(3):
+            e = run.probe_compute_emf(d, qe)
+            eo = np.array([oracle64.compute_emf(p, d, qe[i]) for i in range(n)])
+            assert np.allclose(e, eo, rtol=1e-10, atol=1e-11), d

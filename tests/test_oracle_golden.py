@@ -1,0 +1,61 @@
+"""CPU: the C oracle against golden vectors generated from the unmodified reference executable
+(oracle/gen_golden.py) and against the reference's own known answers recorded in SURVEY.md 8(c)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from ramsesgpu_b200.io import l2_relative
+
+CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_run(oracle64, name):
+    g = load_golden(name)
+    p = oracle64.params(str(g["ini"]))
+    U = oracle64.init_problem(p)
+    gw = p.ghostWidth
+    # initial state (inner cells) is bit-identical
+    assert np.array_equal(U[:, gw:-gw, gw:-gw, gw:-gw], g["initial"])
+    Uf, t, dts = oracle64.run_steps(p, U, int(g["steps"]))
+    final = Uf[:, gw:-gw, gw:-gw, gw:-gw]
+    # same compiler family, same operation order: bitwise
+    assert np.array_equal(final, g["final"]), max(l2_relative(a, b) for a, b in zip(g["final"], final))
+    assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])       # stdout prints 12 digits
+    assert abs(dts[-1] - g["dt_last"]) <= 1e-11 * abs(g["dt_last"])
+    assert abs(dts[0] - g["dt0"]) <= 2e-6 * abs(g["dt0"])                 # "Initial dt" is printed with 6 digits
+
+
+def test_riemann_hlld_known_answer(oracle64):
+    """riemann_hlld on the states of the reference's data/testRiemannHLLD.ini ([BrioWu] block,
+    gamma0 = 1.4f), value recorded from the reference's src/testRiemannHLLD.cpp."""
+    ini = "[MHD]\nenable=true\n[hydro]\ngamma0=1.4\nriemannSolver=hlld\n[mesh]\nnx=4\nny=4\nnz=4\n"
+    p = oracle64.params(ini)
+    ql, qr = KAT_QL, KAT_QR
+    f = oracle64.riemann_mhd(p, ql, qr)
+    assert np.allclose(f, KAT_FLUX, rtol=5e-11, atol=1e-12), f  # recorded with 12 significant digits
+
+
+# qleft / qright of data/testRiemannHLLD.ini in (ID, IP, IU, IV, IW, IA, IB, IC) order; the reference
+# test reads them with ConfigMap::getFloat, i.e. rounded to float (src/testRiemannHLLD.cpp:77-92)
+_f32 = lambda v: np.array(v, dtype=np.float32).astype(np.float64)
+KAT_QL = _f32([1.08, 0.95, 1.2, 0.01, 0.5, 1.1283791670955126, 1.0155412503859613, 0.56418958354775628])
+KAT_QR = _f32([1.0, 1.0, 0.0, 0.0, 0.0, 1.1283791670955126, 1.1283791670955126, 0.56418958354775628])
+KAT_FLUX = np.array([0.797488380363, 4.68321393637, 3.51454807262, -1.36025984298, -0.222243381912, 0.0,
+                     0.676218159142, -0.0618583998892])
+
+
+def test_dt_seed_and_params(oracle64):
+    g = load_golden("ot3d_16_s10")
+    p = oracle64.params(str(g["ini"]))
+    # ConfigMap::getFloat parses as float: gamma0=1.66 -> (double)1.66f, cfl=0.4 -> (double)0.4f
+    assert p.gamma0 == float(np.float32(1.66)) and p.cfl == float(np.float32(0.4))
+    assert p.smallr == float(np.float32(1e-7))
+    assert p.ghostWidth == 3 and p.nbVar == 8 and p.isize == 22
+    assert p.smallp == p.smallc * p.smallc / p.gamma0
+
+
+def test_ot3d_density_is_float_parsed(oracle64):
+    # 3D OT initial density is (1.66f)^2/4pi = 0.21928367177348035
+    g = load_golden("ot3d_16_s10")
+    assert abs(g["initial"][0].mean() - 0.21928367177348035) < 1e-16
