@@ -109,6 +109,10 @@ int rg_reset_launch_count(void);
 /* z planes per pipeline chunk (0 = automatic: whole slab if the scratch fits in device memory) */
 int rg_set_chunk_planes(rg_handle h, int planes);
 
+/* occupancy knobs of the FP64 kernels (process-wide): key = "flux_minb" | "emf_minb" | "trace_minb" |
+ * "update_minb", value = 2..8 resident blocks per SM the kernel variant is compiled for */
+int rg_set_tuning(const char* key, int value);
+
 /* device timing of a region on the library's stream (CUDA events): total and per kernel family.
  * phase order: RG_PHASE_* below.  Events are recorded around every launch between begin and end;
  * rg_profile_end synchronises and returns milliseconds and launch counts summed over the region. */

@@ -178,6 +178,10 @@ int rg_get_stats(rg_handle h, rg_stats* out) {
 int rg_reset_launch_count(void) { rg::resetKernelLaunchCount(); return RG_OK; }
 int rg_set_chunk_planes(rg_handle h, int planes) { RG_TRY(h, h->run->setChunkPlanes(planes)) }
 
+int rg_set_tuning(const char* key, int value) {
+  return rg::setTuning(key, value) ? RG_OK : fail(RG_ERR_INVALID, "unknown tuning key or value out of range");
+}
+
 int rg_profile_begin(rg_handle h) { RG_TRY(h, h->run->profileBegin()) }
 int rg_profile_end(rg_handle h, double* total, double* phase, unsigned long long* launches) {
   RG_TRY(h, h->run->profileEnd(total, phase, launches))

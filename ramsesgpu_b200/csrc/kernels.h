@@ -23,6 +23,7 @@ struct MhdScratch {
   T* W = nullptr;     // NW_MHD components, traced state
   T* F = nullptr;     // 15 components: flux_x[5], flux_y[5], flux_z[5] at the LOW faces
   T* E = nullptr;     // 3 components: emf z, y, x at the LOW edges (reference order I_EMFZ=0..)
+  T* EL = nullptr;    // 3 components: v x B at the LOW edges (x, y, z), input of the trace
   int planes = 0;     // allocated planes per component
   int kbase = 0;      // k of scratch plane 0 for the chunk being processed
 };
@@ -36,6 +37,7 @@ struct MhdKernels {
   static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* dMaxInvDt, cudaStream_t s);
   // 3D MHD chunk pipeline on planes [ka, kb) of the update range
   static void prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s);
+  static void elec(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
   static void trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s);
   static void flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
   static void emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
@@ -49,6 +51,10 @@ struct MhdKernels {
                        cudaStream_t s);
 };
 
+// number of slots of the inverse-dt max reduction (power of two); every slot holds the bit pattern
+// of a non-negative double, so "max" works on the integer or on the floating view alike
+constexpr int MAX_SLOTS = 1024;
+
 // ordered encoding of a non-negative floating value for atomicMax
 inline double decodeMax(unsigned long long v) {
   double d;
@@ -59,6 +65,8 @@ inline double decodeMax(unsigned long long v) {
 
 // launch counter (bench.py's gpu_launches): every wrapper above bumps it once per kernel launch
 unsigned long long kernelLaunchCount();
+// occupancy knobs: "flux_minb" | "emf_minb" | "trace_minb" | "update_minb" = 2..8 resident blocks/SM
+bool setTuning(const char* key, int value);
 void resetKernelLaunchCount();
 
 }  // namespace rg

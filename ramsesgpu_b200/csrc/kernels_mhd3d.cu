@@ -9,6 +9,7 @@
 // Index ranges follow the reference: prim 0..size-2, trace gw-1..size-gw,
 // flux/emf/update gw..size-gw (inclusive), with the reference's write guards.
 #include <cstdio>
+#include <string>
 
 #include "kernels.h"
 #include "mhd_device.cuh"
@@ -18,6 +19,8 @@ namespace rg {
 namespace {
 
 unsigned long long g_launches = 0;
+// occupancy knobs (minimum resident blocks per SM the kernel is compiled for), see setTuning()
+int g_fluxMinB = 4, g_emfMinB = 4, g_traceMinB = 2, g_updateMinB = 6;
 
 // W component ids
 enum {
@@ -92,18 +95,56 @@ __global__ void __launch_bounds__(BX) k_prim(const __grid_constant__ KParams<T> 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0b: edge-centred electric field E = v x B at the LOW edges of every cell
+//      (reference cpu_v3.cpp:36-101, kernel_mhd_compute_elec_field): 4-cell average of the
+//      velocities, 2-face average of the face fields
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                             const T* __restrict__ Qp, T* __restrict__ ELp, int planes, int kbase,
+                                             int k0) {
+  const int i = 1 + blockIdx.x * BX + threadIdx.x, j = 1 + blockIdx.y, k = k0 + blockIdx.z;
+  if (i > P.isize - 2) return;
+  const UView<T> U = uview(Uin, P);
+  const View<const T> Q = view<const T>(Qp, P, planes, kbase);
+  const View<T> EL = view(ELp, P, planes, kbase);
+  const T h = T(0.5), f = T(0.25);
+  const T u00 = Q(IU, i, j, k), v00 = Q(IV, i, j, k), w00 = Q(IW, i, j, k);
+  const T A = U(IA, i, j, k), B = U(IB, i, j, k), C = U(IC, i, j, k);
+  {  // Ex: average over (j-1..j, k-1..k)
+    const T v = f * (Q(IV, i, j - 1, k - 1) + Q(IV, i, j - 1, k) + Q(IV, i, j, k - 1) + v00);
+    const T w = f * (Q(IW, i, j - 1, k - 1) + Q(IW, i, j - 1, k) + Q(IW, i, j, k - 1) + w00);
+    const T Bm = h * (U(IB, i, j, k - 1) + B), Cm = h * (U(IC, i, j - 1, k) + C);
+    EL(0, i, j, k) = v * Cm - w * Bm;
+  }
+  {  // Ey: average over (i-1..i, k-1..k)
+    const T u = f * (Q(IU, i - 1, j, k - 1) + Q(IU, i - 1, j, k) + Q(IU, i, j, k - 1) + u00);
+    const T w = f * (Q(IW, i - 1, j, k - 1) + Q(IW, i - 1, j, k) + Q(IW, i, j, k - 1) + w00);
+    const T Am = h * (U(IA, i, j, k - 1) + A), Cm = h * (U(IC, i - 1, j, k) + C);
+    EL(1, i, j, k) = w * Am - u * Cm;
+  }
+  {  // Ez: average over (i-1..i, j-1..j)
+    const T u = f * (Q(IU, i - 1, j - 1, k) + Q(IU, i - 1, j, k) + Q(IU, i, j - 1, k) + u00);
+    const T v = f * (Q(IV, i - 1, j - 1, k) + Q(IV, i - 1, j, k) + Q(IV, i, j - 1, k) + v00);
+    const T Am = h * (U(IA, i, j - 1, k) + A), Bm = h * (U(IB, i - 1, j, k) + B);
+    EL(2, i, j, k) = u * Bm - v * Am;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: slopes + edge electric fields + face-B slopes + half-step trace -> W
 //     (reference cpu_v3.cpp:36-361, slope_mhd.h:436-502/598-704, trace_mhd.h:1854-2030)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(BX) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
-                                              const T* __restrict__ Qp, T* __restrict__ Wp, int planes, int kbase,
-                                              int k0, T dt) {
+template <typename T, int MINB>
+__global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                                    const T* __restrict__ Qp, const T* __restrict__ ELp,
+                                                    T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
   const int gw = P.gw;
   const int i = gw - 1 + blockIdx.x * BX + threadIdx.x, j = gw - 1 + blockIdx.y, k = k0 + blockIdx.z;
   if (i > P.isize - gw) return;
   const UView<T> U = uview(Uin, P);
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
+  const View<const T> EL = view<const T>(ELp, P, planes, kbase);
   const View<T> W = view(Wp, P, planes, kbase);
   const T st = P.slope_type;
   const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
@@ -140,31 +181,10 @@ __global__ void __launch_bounds__(BX) k_trace(const __grid_constant__ KParams<T>
   const T dCRx = h * dev::limited_slope(xst, U(IC, i - 1, j, k + 1), CR, U(IC, i + 1, j, k + 1));
   const T dCRy = h * dev::limited_slope(xst, U(IC, i, j - 1, k + 1), CR, U(IC, i, j + 1, k + 1));
 
-  // edge-centred electric fields E = v x B at the 12 edges of the cell (cpu_v3.cpp:36-101)
-  auto Ex = [&](int jj, int kk) {
-    T v = T(0.25) * (Q(IV, i, jj - 1, kk - 1) + Q(IV, i, jj - 1, kk) + Q(IV, i, jj, kk - 1) + Q(IV, i, jj, kk));
-    T w = T(0.25) * (Q(IW, i, jj - 1, kk - 1) + Q(IW, i, jj - 1, kk) + Q(IW, i, jj, kk - 1) + Q(IW, i, jj, kk));
-    T B = h * (U(IB, i, jj, kk - 1) + U(IB, i, jj, kk));
-    T C = h * (U(IC, i, jj - 1, kk) + U(IC, i, jj, kk));
-    return v * C - w * B;
-  };
-  auto Ey = [&](int ii, int kk) {
-    T u = T(0.25) * (Q(IU, ii - 1, j, kk - 1) + Q(IU, ii - 1, j, kk) + Q(IU, ii, j, kk - 1) + Q(IU, ii, j, kk));
-    T w = T(0.25) * (Q(IW, ii - 1, j, kk - 1) + Q(IW, ii - 1, j, kk) + Q(IW, ii, j, kk - 1) + Q(IW, ii, j, kk));
-    T A = h * (U(IA, ii, j, kk - 1) + U(IA, ii, j, kk));
-    T C = h * (U(IC, ii - 1, j, kk) + U(IC, ii, j, kk));
-    return w * A - u * C;
-  };
-  auto Ez = [&](int ii, int jj) {
-    T u = T(0.25) * (Q(IU, ii - 1, jj - 1, k) + Q(IU, ii - 1, jj, k) + Q(IU, ii, jj - 1, k) + Q(IU, ii, jj, k));
-    T v = T(0.25) * (Q(IV, ii - 1, jj - 1, k) + Q(IV, ii - 1, jj, k) + Q(IV, ii, jj - 1, k) + Q(IV, ii, jj, k));
-    T A = h * (U(IA, ii, jj - 1, k) + U(IA, ii, jj, k));
-    T B = h * (U(IB, ii - 1, jj, k) + U(IB, ii, jj, k));
-    return u * B - v * A;
-  };
-  const T ELL = Ex(j, k), ELR = Ex(j, k + 1), ERL = Ex(j + 1, k), ERR = Ex(j + 1, k + 1);
-  const T FLL = Ey(i, k), FLR = Ey(i, k + 1), FRL = Ey(i + 1, k), FRR = Ey(i + 1, k + 1);
-  const T GLL = Ez(i, j), GLR = Ez(i, j + 1), GRL = Ez(i + 1, j), GRR = Ez(i + 1, j + 1);
+  // edge-centred electric fields at the 12 edges of the cell, from the elec kernel
+  const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k), ERR = EL(0, i, j + 1, k + 1);
+  const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k), FRR = EL(1, i + 1, j, k + 1);
+  const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k), GRR = EL(2, i + 1, j + 1, k);
 
   // half-step source terms (trace_mhd.h:1985-2011)
   T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
@@ -252,8 +272,8 @@ __device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const V
   return s;
 }
 
-template <typename T, int DIR>
-__global__ void __launch_bounds__(BX) k_flux(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
+template <typename T, int DIR, int MINB>
+__global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                              T* __restrict__ Fp, int planes, int kbase, int k0) {
   const int gw = P.gw;
   const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
@@ -317,8 +337,8 @@ __device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const 
   return c;
 }
 
-template <typename T, int EDIR>
-__global__ void __launch_bounds__(BX) k_emf(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
+template <typename T, int EDIR, int MINB>
+__global__ void __launch_bounds__(BX, MINB) k_emf(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                             T* __restrict__ Ep, int planes, int kbase, int k0) {
   const int gw = P.gw;
   const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
@@ -354,9 +374,20 @@ __global__ void __launch_bounds__(BX) k_emf(const __grid_constant__ KParams<T> P
 __device__ __forceinline__ void atomicMaxOrdered(unsigned long long* addr, double v) {
   atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
-
+// warp max -> one atomicMax per warp into one of MAX_SLOTS slots (spreads the atomics over many L2
+// addresses; the host or an NCCL all-reduce finishes the max).  No block barrier.
 template <typename T>
-__global__ void __launch_bounds__(BX) k_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+__device__ __forceinline__ void reduceMaxToSlots(T v, unsigned long long* slots) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dev::mx(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > T(0)) {
+    const unsigned slot = (blockIdx.x * 4u + (threadIdx.x >> 5) + blockIdx.y * 37u + blockIdx.z * 101u) & (MAX_SLOTS - 1);
+    atomicMaxOrdered(slots + slot, (double)v);
+  }
+}
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
                                                T* __restrict__ Unew, const T* __restrict__ Fp,
                                                const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
                                                unsigned long long* __restrict__ dMaxInvDt) {
@@ -432,20 +463,7 @@ __global__ void __launch_bounds__(BX) k_update(const __grid_constant__ KParams<T
       }
     }
   }
-  // block max -> one atomic per block
-  if (dMaxInvDt != nullptr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) invDt = dev::mx(invDt, __shfl_xor_sync(0xffffffffu, invDt, o));
-    __shared__ T smax[BX / 32];
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = invDt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      T m = smax[0];
-#pragma unroll
-      for (int w = 1; w < BX / 32; ++w) m = dev::mx(m, smax[w]);
-      if (m > T(0)) atomicMaxOrdered(dMaxInvDt, (double)m);
-    }
-  }
+  if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
 }
 
 template <typename T>
@@ -489,17 +507,7 @@ __global__ void __launch_bounds__(BX) k_invdt(const __grid_constant__ KParams<T>
       invDt = vx / P.dx + vy / P.dy;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) invDt = dev::mx(invDt, __shfl_xor_sync(0xffffffffu, invDt, o));
-  __shared__ T smax[BX / 32];
-  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = invDt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    T m = smax[0];
-#pragma unroll
-    for (int w = 1; w < BX / 32; ++w) m = dev::mx(m, smax[w]);
-    if (m > T(0)) atomicMaxOrdered(dMaxInvDt, (double)m);
-  }
+  reduceMaxToSlots(invDt, dMaxInvDt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,6 +587,16 @@ __global__ void k_probe_emf(const __grid_constant__ KParams<T> P, int n, int emf
 }  // namespace
 
 unsigned long long kernelLaunchCount() { return g_launches; }
+bool setTuning(const char* key, int value) {
+  const std::string k = key ? key : "";
+  if (value < 2 || value > 8) return false;
+  if (k == "flux_minb") g_fluxMinB = value;
+  else if (k == "emf_minb") g_emfMinB = value;
+  else if (k == "trace_minb") g_traceMinB = value;
+  else if (k == "update_minb") g_updateMinB = value;
+  else return false;
+  return true;
+}
 void resetKernelLaunchCount() { g_launches = 0; }
 
 // ---- launch wrappers ---------------------------------------------------------------------------
@@ -607,11 +625,34 @@ void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int 
   ++g_launches;
 }
 
+// MINB dispatch: FP64 kernels are compiled for several occupancy targets (register caps), picked at
+// run time by setTuning(); the FP32 flavour keeps one variant each.
+#define RG_MINB_SWITCH(T, minb, LAUNCH, DFLT)              \
+  if (sizeof(T) == 4) { LAUNCH(DFLT); }                    \
+  else switch (minb) {                                     \
+    case 2: LAUNCH(2); break;                              \
+    case 3: LAUNCH(3); break;                              \
+    case 4: LAUNCH(4); break;                              \
+    case 5: LAUNCH(5); break;                              \
+    case 6: LAUNCH(6); break;                              \
+    default: LAUNCH(8); break;                             \
+  }
+
+template <typename T>
+void MhdKernels<T>::elec(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_elec<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.EL, sc.planes, sc.kbase, k0);
+  ++g_launches;
+}
+
 template <typename T>
 void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
   const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // gw-1 .. size-gw
-  k_trace<T><<<gridFor(n, m, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.W, sc.planes, sc.kbase, k0, dt);
+  const dim3 g = gridFor(n, m, k1 - k0);
+#define RG_L(M) k_trace<T, M><<<g, BX, 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
+  RG_MINB_SWITCH(T, g_traceMinB, RG_L, 4)
+#undef RG_L
   ++g_launches;
 }
 
@@ -619,9 +660,12 @@ template <typename T>
 void MhdKernels<T>::flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
-  k_flux<T, 0><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
-  k_flux<T, 1><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
-  k_flux<T, 2><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);
+#define RG_L(M)                                                                   \
+  k_flux<T, 0, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 1, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 2, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
+  RG_MINB_SWITCH(T, g_fluxMinB, RG_L, 6)
+#undef RG_L
   g_launches += 3;
 }
 
@@ -629,9 +673,12 @@ template <typename T>
 void MhdKernels<T>::emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
-  k_emf<T, 2><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
-  k_emf<T, 1><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
-  k_emf<T, 0><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);
+#define RG_L(M)                                                                   \
+  k_emf<T, 2, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 1, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 0, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
+  RG_MINB_SWITCH(T, g_emfMinB, RG_L, 6)
+#undef RG_L
   g_launches += 3;
 }
 
@@ -639,8 +686,10 @@ template <typename T>
 void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
                            unsigned long long* d, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_update<T><<<gridFor(P.isize, P.jsize, k1 - k0), BX, 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0,
-                                                                dt, d);
+  const dim3 g = gridFor(P.isize, P.jsize, k1 - k0);
+#define RG_L(M) k_update<T, M><<<g, BX, 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
+  RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
+#undef RG_L
   ++g_launches;
 }
 

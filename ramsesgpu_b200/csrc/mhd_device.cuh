@@ -14,12 +14,43 @@ namespace rg {
 namespace dev {
 
 // ---- scalar helpers -------------------------------------------------------------------------
-__device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+// FP64 reciprocal / rsqrt / sqrt as MUFU seed + Newton steps WITHOUT the library's slow-path
+// branch (denormal / inf / zero handling): every denominator on this path is a normal number
+// (densities, wave-speed differences, positive radicands), and dropping the branch removes ~8
+// non-FP64 instructions + a BSSY/BSYNC pair per call.  Accuracy: rcp <= 1 ulp, rsqrt/sqrt <= 2 ulp.
+__device__ __forceinline__ double rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  r = fma(r, e, r);                                        // cubic step
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-__device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+__device__ __forceinline__ double rsq(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H
+  double e = fma(-x * y, y, 1.0);
+  y = fma(y * e, fma(e, 0.375, 0.5), y);
+  e = fma(-x * y, y, 1.0);
+  return fma(y * e, 0.5, y);
+}
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double sqr_t(double x) { return sqrt(x); }
+// sqrt for x > 0 (callers clamp radicands that can reach 0 to a tiny positive number)
+__device__ __forceinline__ double sqr_t(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(y * e, fma(e, 0.375, 0.5), y);
+  double s = x * y;
+  double r = fma(-s, s, x);
+  return fma(r, 0.5 * y, s);
+}
 __device__ __forceinline__ float sqr_t(float x) { return sqrtf(x); }
+template <typename T> __device__ __forceinline__ T tiny();
+template <> __device__ __forceinline__ double tiny<double>() { return 1e-300; }
+template <> __device__ __forceinline__ float tiny<float>() { return 1e-37f; }
 __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
@@ -80,7 +111,15 @@ template <typename T>
 __device__ __forceinline__ T fast_speed(T gamma, T p, T ir, T b2, T n2) {
   T c2 = gamma * p * ir;
   T d2 = T(0.5) * (b2 * ir + c2);
-  return sqr_t(d2 + sqr_t(mx(d2 * d2 - c2 * n2 * ir, T(0))));
+  return sqr_t(d2 + sqr_t(mx(d2 * d2 - c2 * n2 * ir, tiny<T>())));
+}
+
+// square of the fast speed (one sqrt less when only a max over states is needed)
+template <typename T>
+__device__ __forceinline__ T fast_speed2(T gamma, T p, T ir, T b2, T n2) {
+  T c2 = gamma * p * ir;
+  T d2 = T(0.5) * (b2 * ir + c2);
+  return d2 + sqr_t(mx(d2 * d2 - c2 * n2 * ir, tiny<T>()));
 }
 
 // 1-D physical flux + conservative vector, reference mhd_utils.h:106-156
@@ -140,7 +179,7 @@ __device__ void riemann_llf(const KParams<T>& P, State<T> l, State<T> r, T (&flu
     flux[n] = (ql[n] + qr[n]) * T(0.5) * zero_flux - vel * (ur[n] - ul[n]) * T(0.5);
 }
 
-// HLLD (Miyoshi & Kusano 2005) as in reference riemann_mhd.h:139-342.  8 reciprocals, 4 square
+// HLLD (Miyoshi & Kusano 2005) as in reference riemann_mhd.h:139-342.  8 reciprocals, 3 square
 // roots and 2 reciprocal square roots per interface instead of 29 divisions + 6 square roots.
 template <typename T>
 __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, State<T> Rr, T (&flux)[8]) {
@@ -164,9 +203,8 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
   const T ptotr = pr + emagr;
   const T vdotbr = ur * a + vr * br + wr * cr;
 
-  const T cfl_ = fast_speed(P.gamma0, pl, rcp(rl), T(2) * emagl, a2);
-  const T cfr_ = fast_speed(P.gamma0, pr, rcp(rr), T(2) * emagr, a2);
-  const T cmax = mx(cfl_, cfr_);
+  const T cmax = sqr_t(mx(fast_speed2(P.gamma0, pl, rcp(rl), T(2) * emagl, a2),
+                          fast_speed2(P.gamma0, pr, rcp(rr), T(2) * emagr, a2)));
   const T sl = mn(ul, ur) - cmax;
   const T sr = mx(ul, ur) + cmax;
 
@@ -279,7 +317,7 @@ struct Corner {
   T r, p, u, v, w, a, b, c;
 };
 
-// 2-D HLLD, reference riemann_mhd.h:615-821.  12 reciprocals + 16 sqrt + 16 rsqrt
+// 2-D HLLD, reference riemann_mhd.h:615-821.  12 reciprocals + 10 sqrt + 16 rsqrt
 // (reference: 82 divisions + 32 sqrt).
 template <typename T>
 __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corner<T>& LL, const Corner<T>& RL,
@@ -295,8 +333,8 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
     const T c2 = g * S.p * ir;                                      \
     const T d2 = T(0.5) * (bb * ir + c2);                           \
     const T dd = d2 * d2, ci = c2 * ir;                             \
-    cx = sqr_t(d2 + sqr_t(mx(dd - ci * a2, T(0))));                 \
-    cy = sqr_t(d2 + sqr_t(mx(dd - ci * b2_, T(0))));                \
+    cx = d2 + sqr_t(mx(dd - ci * a2, tiny<T>()));                        \
+    cy = d2 + sqr_t(mx(dd - ci * b2_, tiny<T>()));                       \
     Ptot = S.p + T(0.5) * bb;                                       \
   }
   RG_SPEEDS(LL, cxLL, cyLL, PtotLL)
@@ -304,7 +342,8 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
   RG_SPEEDS(RL, cxRL, cyRL, PtotRL)
   RG_SPEEDS(RR, cxRR, cyRR, PtotRR)
 #undef RG_SPEEDS
-  const T cxm = max4(cxLL, cxLR, cxRL, cxRR), cym = max4(cyLL, cyLR, cyRL, cyRR);
+  // sqrt is monotonic: max of the four fast speeds = sqrt of the max of their squares
+  const T cxm = sqr_t(max4(cxLL, cxLR, cxRL, cxRR)), cym = sqr_t(max4(cyLL, cyLR, cyRL, cyRR));
   const T SL = min4(LL.u, LR.u, RL.u, RR.u) - cxm;
   const T SR = max4(LL.u, LR.u, RL.u, RR.u) + cxm;
   const T SB = min4(LL.v, LR.v, RL.v, RR.v) - cym;
@@ -384,8 +423,8 @@ __device__ T mag_riemann2d_hll(const KParams<T>& P, const Corner<T> (&q)[4], boo
   for (int s = 0; s < 4; ++s) {
     const T ir = rcp(q[s].r);
     if (alfven) {
-      cx[s] = sqr_t(q[s].a * q[s].a * ir);
-      cy[s] = sqr_t(q[s].b * q[s].b * ir);
+      cx[s] = ab(q[s].a) * sqr_t(ir);
+      cy[s] = ab(q[s].b) * sqr_t(ir);
     } else {
       const T bb = q[s].a * q[s].a + q[s].b * q[s].b + q[s].c * q[s].c;
       cx[s] = fast_speed(P.gamma0, q[s].p, ir, bb, q[s].a * q[s].a);

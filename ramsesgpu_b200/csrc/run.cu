@@ -96,9 +96,9 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMemset(dU_[b], 0, elems_ * sizeof(T)));
     }
     deviceBytes_ += 2 * elems_ * sizeof(T);
-    RG_CUDA(cudaMalloc(&dMax_, 2 * sizeof(unsigned long long)));
-    RG_CUDA(cudaMemset(dMax_, 0, 2 * sizeof(unsigned long long)));
-    RG_CUDA(cudaMallocHost(&hMax_, 2 * sizeof(unsigned long long)));
+    RG_CUDA(cudaMalloc(&dMax_, 2 * MAX_SLOTS * sizeof(unsigned long long)));
+    RG_CUDA(cudaMemset(dMax_, 0, 2 * MAX_SLOTS * sizeof(unsigned long long)));
+    RG_CUDA(cudaMallocHost(&hMax_, MAX_SLOTS * sizeof(unsigned long long)));
     if (nranks_ > 1) initComm(dist);
   }
 
@@ -188,21 +188,24 @@ class RunImpl final : public Run {
   // reference MHDRunBase::compute_dt_mhd / HydroRunBase::compute_dt: cfl / max inverse dt
   double compute_dt(int useU) override {
     const int b = useU ? 1 : 0;
+    unsigned long long* slots = dMax_ + (size_t)b * MAX_SLOTS;
     if (!dtCached_[b]) {
-      RG_CUDA(cudaMemsetAsync(dMax_ + b, 0, sizeof(unsigned long long), stream_));
+      RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
       if (!rp_.mhdEnabled) throw std::runtime_error("hydro compute_dt not available in this build");
-      phase(PH_DT, [&] { MhdKernels<T>::computeInvDt(kp_, dU_[b], dMax_ + b, stream_); });
+      phase(PH_DT, [&] { MhdKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_); });
       dtCached_[b] = true;
     }
-    if (nranks_ > 1) {
-      ncclCheck(nccl_->AllReduce(dMax_ + b, dMax_ + b, 1, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_),
+    if (nranks_ > 1) {  // slots hold bit patterns of non-negative doubles: a floating max is exact
+      ncclCheck(nccl_->AllReduce(slots, slots, MAX_SLOTS, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_),
                 "allreduce(dt)");
     }
-    RG_CUDA(cudaMemcpyAsync(hMax_ + b, dMax_ + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaMemcpyAsync(hMax_, slots, MAX_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
     RG_CUDA(cudaStreamSynchronize(stream_));
+    unsigned long long best = 0;
+    for (int i = 0; i < MAX_SLOTS; ++i) best = std::max(best, hMax_[i]);
     // seed of the running max, reference MHDRunBase.cpp:144
     T invDt = kp_.smallc / std::min(kp_.dx, kp_.dy);
-    invDt = std::max(invDt, static_cast<T>(decodeMax(hMax_[b])));
+    invDt = std::max(invDt, static_cast<T>(decodeMax(best)));
     return static_cast<double>(kp_.cfl / invDt);
   }
 
@@ -462,7 +465,7 @@ class RunImpl final : public Run {
 
   // ---- scratch / chunking ------------------------------------------------------------------------
   void freeScratch() {
-    if (sc_.Q) { cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); }
+    if (sc_.Q) { cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL); }
     if (sc_.Q) deviceBytes_ -= scratchBytes_;
     sc_ = MhdScratch<T>();
     scratchBytes_ = 0;
@@ -472,7 +475,7 @@ class RunImpl final : public Run {
   void ensureScratchMhd3d() {
     if (sc_.Q) return;
     const size_t plane = (size_t)kp_.isize * kp_.jsize;
-    const size_t perPlane = plane * sizeof(T) * (8 + NW_MHD + 15 + 3);
+    const size_t perPlane = plane * sizeof(T) * (8 + NW_MHD + 15 + 3 + 3);
     const int updPlanes = kp_.ksize - 2 * kp_.gw + 1;  // gw .. ksize-gw inclusive
     int chunk = updPlanes;
     size_t freeB = 0, totalB = 0;
@@ -487,6 +490,7 @@ class RunImpl final : public Run {
     RG_CUDA(cudaMalloc(&sc_.W, plane * sc_.planes * NW_MHD * sizeof(T)));
     RG_CUDA(cudaMalloc(&sc_.F, plane * sc_.planes * 15 * sizeof(T)));
     RG_CUDA(cudaMalloc(&sc_.E, plane * sc_.planes * 3 * sizeof(T)));
+    RG_CUDA(cudaMalloc(&sc_.EL, plane * sc_.planes * 3 * sizeof(T)));
     scratchBytes_ = perPlane * sc_.planes;
     deviceBytes_ += scratchBytes_;
   }
@@ -497,7 +501,8 @@ class RunImpl final : public Run {
     const T* Uold = dU_[src];
     T* Unew = dU_[dst];
     const int gw = kp_.gw, kN = kp_.ksize - gw;
-    RG_CUDA(cudaMemsetAsync(dMax_ + dst, 0, sizeof(unsigned long long), stream_));
+    unsigned long long* slots = dMax_ + (size_t)dst * MAX_SLOTS;
+    RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
     // ghost planes outside the update box keep the (ghost-filled) old values, like copyTo
     phase(PH_COPY, [&] {
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
@@ -509,10 +514,11 @@ class RunImpl final : public Run {
       MhdScratch<T> sc = sc_;
       sc.kbase = ka - 2;
       phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
+      phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
       phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
-      phase(PH_UPDATE, [&] { MhdKernels<T>::update(kp_, Uold, Unew, sc, ka, kb, dt, dMax_ + dst, stream_); });
+      phase(PH_UPDATE, [&] { MhdKernels<T>::update(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_); });
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state

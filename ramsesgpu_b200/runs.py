@@ -164,6 +164,10 @@ class MHDRunGodunov(MHDRunBase):
     pass
 
 
+def set_tuning(key, value):
+    check(_lib.load().rg_set_tuning(key.encode(), int(value)))
+
+
 def reset_launch_count():
     _lib.load().rg_reset_launch_count()
 
