@@ -8,6 +8,7 @@
 //
 // Index ranges follow the reference: prim 0..size-2, trace gw-1..size-gw,
 // flux/emf/update gw..size-gw (inclusive), with the reference's write guards.
+#include <algorithm>
 #include <cstdio>
 #include <string>
 
@@ -20,7 +21,7 @@ namespace {
 
 unsigned long long g_launches = 0;
 // occupancy knobs (minimum resident blocks per SM the kernel is compiled for), see setTuning()
-int g_fluxMinB = 4, g_emfMinB = 4, g_traceMinB = 2, g_updateMinB = 6;
+int g_fluxMinB = 5, g_emfMinB = 4, g_traceMinB = 4, g_updateMinB = 4;
 
 // W component ids
 enum {
@@ -34,47 +35,80 @@ enum {
 };
 static_assert(W_DCRY + 1 == NW_MHD, "W layout");
 
+// Scratch arrays are indexed with 32-bit element offsets (one IMAD + one IMAD.WIDE per load instead
+// of a 64-bit add chain); the host keeps every scratch array below 2^31 elements by z-chunking.
 template <typename T>
 struct View {  // [comp][kk][j][i] accessor of a scratch array
   T* p;
-  size_t plane, comp;  // isize*jsize, planes*plane
+  int plane, comp;  // isize*jsize, planes*plane
   int isize, kbase;
   __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
-    return p[(size_t)c * comp + (size_t)(k - kbase) * plane + (size_t)j * isize + i];
+    return p[c * comp + ((k - kbase) * plane + j * isize + i)];
   }
 };
 template <typename T, typename PT>
 __host__ __device__ inline View<T> view(T* p, const PT& P, int planes, int kbase) {
   View<T> v;
   v.p = p;
-  v.plane = (size_t)P.isize * P.jsize;
+  v.plane = P.isize * P.jsize;
   v.comp = v.plane * planes;
   v.isize = P.isize;
   v.kbase = kbase;
   return v;
 }
 template <typename T>
-struct UView {  // the state array [var][k][j][i]
+struct UView {  // the state array [var][k][j][i]; cells < 2^31, variables offset in 64 bits
   const T* p;
-  size_t plane, comp;
-  int isize;
+  size_t comp;
+  int plane, isize;
   __device__ __forceinline__ T operator()(int v, int i, int j, int k) const {
-    return __ldg(p + (size_t)v * comp + (size_t)k * plane + (size_t)j * isize + i);
+    return __ldg(p + (size_t)v * comp + (k * plane + j * isize + i));
   }
 };
 template <typename T>
 __host__ __device__ inline UView<T> uview(const T* p, const KParams<T>& P) {
   UView<T> v;
   v.p = p;
-  v.plane = (size_t)P.isize * P.jsize;
-  v.comp = v.plane * P.ksize;
+  v.plane = P.isize * P.jsize;
+  v.comp = (size_t)v.plane * P.ksize;
   v.isize = P.isize;
   return v;
 }
 
-constexpr int BX = 128;  // threads along x
+constexpr int BX = 128;  // threads per block (tile shapes: 32x4, 64x2, 128x1)
+int g_tileX = 32;         // run-time knob "tile_x"; tile_y = BX / tile_x
+#define TX ((int)blockDim.x)
+#define TY ((int)blockDim.y)
 
-inline dim3 gridFor(int ni, int nj, int nk) { return dim3((ni + BX - 1) / BX, nj, nk); }
+// Index space [i0, i0+ni) x [j0, j0+nj) of one plane -> thread blocks.  Full TX-wide tiles first;
+// when the last tile would be mostly empty (ni % TX < 24, e.g. the nx+1 = 257 faces of a 256^3
+// grid), its columns are handled by "remainder" blocks (blockIdx.x == ni / TX) whose threads are
+// laid out transposed (r columns x BX/r rows), so that no warp runs with 1 active lane out of 32.
+constexpr int REM_MAX = 24;
+inline dim3 gridFor(int ni, int nj, int nk) {
+  const int tx = g_tileX, ty = BX / g_tileX;
+  const int nFull = ni / tx, r = ni % tx;
+  if (r > 0 && r < REM_MAX) {
+    const int R = BX / r;
+    return dim3(nFull + 1, std::max((nj + ty - 1) / ty, (nj + R - 1) / R), nk);
+  }
+  return dim3((ni + tx - 1) / tx, (nj + ty - 1) / ty, nk);
+}
+__device__ __forceinline__ bool tileCoords(int i0, int ni, int j0, int nj, int& i, int& j) {
+  const int nFull = ni / TX, r = ni - nFull * TX;
+  if (r > 0 && r < REM_MAX && (int)blockIdx.x == nFull) {
+    const int tid = threadIdx.y * TX + threadIdx.x, R = BX / r;
+    const int jj = blockIdx.y * R + tid / r;
+    i = i0 + nFull * TX + tid % r;
+    j = j0 + jj;
+    return tid < R * r && jj < nj;
+  }
+  const int ii = blockIdx.x * TX + threadIdx.x, jj = blockIdx.y * TY + threadIdx.y;
+  i = i0 + ii;
+  j = j0 + jj;
+  return ii < ni && jj < nj;
+}
+inline dim3 blockShape() { return dim3(g_tileX, BX / g_tileX, 1); }
 
 // ------------------------------------------------------------------------------------------------
 // K0: conservative -> primitive (reference MHDRunGodunov.cpp:538-560 + constoprim.h:137-199)
@@ -82,8 +116,9 @@ inline dim3 gridFor(int ni, int nj, int nk) { return dim3((ni + BX - 1) / BX, nj
 template <typename T>
 __global__ void __launch_bounds__(BX) k_prim(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                              T* __restrict__ Qp, int planes, int kbase, int k0, T dt) {
-  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
-  if (i >= P.isize - 1) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(0, P.isize - 1, 0, P.jsize - 1, i, j)) return;
   const UView<T> U = uview(Uin, P);
   const View<T> Q = view(Qp, P, planes, kbase);
   T u[8], q[8];
@@ -103,8 +138,9 @@ template <typename T>
 __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                              const T* __restrict__ Qp, T* __restrict__ ELp, int planes, int kbase,
                                              int k0) {
-  const int i = 1 + blockIdx.x * BX + threadIdx.x, j = 1 + blockIdx.y, k = k0 + blockIdx.z;
-  if (i > P.isize - 2) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(1, P.isize - 2, 1, P.jsize - 2, i, j)) return;
   const UView<T> U = uview(Uin, P);
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
   const View<T> EL = view(ELp, P, planes, kbase);
@@ -140,8 +176,9 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
                                                     const T* __restrict__ Qp, const T* __restrict__ ELp,
                                                     T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
   const int gw = P.gw;
-  const int i = gw - 1 + blockIdx.x * BX + threadIdx.x, j = gw - 1 + blockIdx.y, k = k0 + blockIdx.z;
-  if (i > P.isize - gw) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(gw - 1, P.isize - 2 * gw + 2, gw - 1, P.jsize - 2 * gw + 2, i, j)) return;
   const UView<T> U = uview(Uin, P);
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
   const View<const T> EL = view<const T>(ELp, P, planes, kbase);
@@ -276,8 +313,9 @@ template <typename T, int DIR, int MINB>
 __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                              T* __restrict__ Fp, int planes, int kbase, int k0) {
   const int gw = P.gw;
-  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
-  if (i > P.isize - gw) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(gw, P.nx + 1, gw, P.ny + 1, i, j)) return;
   // a face is only needed where both transverse indexes are inner
   if (DIR != 0 && i >= P.isize - gw) return;
   if (DIR != 1 && j >= P.jsize - gw) return;
@@ -341,8 +379,9 @@ template <typename T, int EDIR, int MINB>
 __global__ void __launch_bounds__(BX, MINB) k_emf(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                             T* __restrict__ Ep, int planes, int kbase, int k0) {
   const int gw = P.gw;
-  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y, k = k0 + blockIdx.z;
-  if (i > P.isize - gw) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(gw, P.nx + 1, gw, P.ny + 1, i, j)) return;
   const View<const T> W = view<const T>(Wp, P, planes, kbase);
   const View<T> E = view(Ep, P, planes, kbase);
   const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
@@ -381,7 +420,7 @@ __device__ __forceinline__ void reduceMaxToSlots(T v, unsigned long long* slots)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = dev::mx(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0 && v > T(0)) {
-    const unsigned slot = (blockIdx.x * 4u + (threadIdx.x >> 5) + blockIdx.y * 37u + blockIdx.z * 101u) & (MAX_SLOTS - 1);
+    const unsigned slot = (blockIdx.x * 29u + (threadIdx.x >> 5) + threadIdx.y * 7u + blockIdx.y * 37u + blockIdx.z * 101u) & (MAX_SLOTS - 1);
     atomicMaxOrdered(slots + slot, (double)v);
   }
 }
@@ -392,10 +431,12 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
                                                const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
                                                unsigned long long* __restrict__ dMaxInvDt) {
   const int gw = P.gw;
-  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  const bool valid = tileCoords(0, P.isize, 0, P.jsize, i, j);
   const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;  // first upper ghost index
   T invDt = T(0);
-  if (i < P.isize) {
+  if (valid) {
     const UView<T> U = uview(Uold, P);
     const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
     const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
@@ -469,8 +510,9 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
 template <typename T>
 __global__ void __launch_bounds__(BX) k_copy_planes(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
                                                     T* __restrict__ Unew, int k0) {
-  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y, k = k0 + blockIdx.z;
-  if (i >= P.isize) return;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(0, P.isize, 0, P.jsize, i, j)) return;
   const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
   const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
   for (int v = 0; v < P.nvar; ++v) Unew[v * comp + idx] = Uold[v * comp + idx];
@@ -483,10 +525,11 @@ template <typename T>
 __global__ void __launch_bounds__(BX) k_invdt(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                               unsigned long long* __restrict__ dMaxInvDt) {
   const int gw = P.gw;
-  const int i = gw + blockIdx.x * BX + threadIdx.x, j = gw + blockIdx.y;
+  int i, j;
+  const bool valid = tileCoords(gw, P.nx, gw, P.ny, i, j);
   const int k = (P.dim == 3) ? gw + blockIdx.z : 0;
   T invDt = T(0);
-  if (i < P.isize - gw) {
+  if (valid) {
     const UView<T> U = uview(Uin, P);
     T u[8], q[8];
 #pragma unroll
@@ -589,6 +632,11 @@ __global__ void k_probe_emf(const __grid_constant__ KParams<T> P, int n, int emf
 unsigned long long kernelLaunchCount() { return g_launches; }
 bool setTuning(const char* key, int value) {
   const std::string k = key ? key : "";
+  if (k == "tile_x") {
+    if (value != 32 && value != 64 && value != 128) return false;
+    g_tileX = value;
+    return true;
+  }
   if (value < 2 || value > 8) return false;
   if (k == "flux_minb") g_fluxMinB = value;
   else if (k == "emf_minb") g_emfMinB = value;
@@ -614,14 +662,14 @@ void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, i
 
 template <typename T>
 void MhdKernels<T>::computeInvDt(const KParams<T>& P, const T* U, unsigned long long* d, cudaStream_t s) {
-  k_invdt<T><<<gridFor(P.nx, P.ny, P.dim == 3 ? P.nz : 1), BX, 0, s>>>(P, U, d);
+  k_invdt<T><<<gridFor(P.nx, P.ny, P.dim == 3 ? P.nz : 1), blockShape(), 0, s>>>(P, U, d);
   ++g_launches;
 }
 
 template <typename T>
 void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_prim<T><<<gridFor(P.isize - 1, P.jsize - 1, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.planes, sc.kbase, k0, dt);
+  k_prim<T><<<gridFor(P.isize - 1, P.jsize - 1, k1 - k0), blockShape(), 0, s>>>(P, U, sc.Q, sc.planes, sc.kbase, k0, dt);
   ++g_launches;
 }
 
@@ -641,7 +689,7 @@ void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int 
 template <typename T>
 void MhdKernels<T>::elec(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_elec<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), BX, 0, s>>>(P, U, sc.Q, sc.EL, sc.planes, sc.kbase, k0);
+  k_elec<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.planes, sc.kbase, k0);
   ++g_launches;
 }
 
@@ -650,7 +698,7 @@ void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int
   if (k1 <= k0) return;
   const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // gw-1 .. size-gw
   const dim3 g = gridFor(n, m, k1 - k0);
-#define RG_L(M) k_trace<T, M><<<g, BX, 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
+#define RG_L(M) k_trace<T, M><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
   RG_MINB_SWITCH(T, g_traceMinB, RG_L, 4)
 #undef RG_L
   ++g_launches;
@@ -661,9 +709,9 @@ void MhdKernels<T>::flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, 
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
 #define RG_L(M)                                                                   \
-  k_flux<T, 0, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
-  k_flux<T, 1, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
-  k_flux<T, 2, M><<<g, BX, 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
+  k_flux<T, 0, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 1, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 2, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_fluxMinB, RG_L, 6)
 #undef RG_L
   g_launches += 3;
@@ -674,9 +722,9 @@ void MhdKernels<T>::emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, c
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
 #define RG_L(M)                                                                   \
-  k_emf<T, 2, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
-  k_emf<T, 1, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
-  k_emf<T, 0, M><<<g, BX, 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
+  k_emf<T, 2, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 1, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 0, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_emfMinB, RG_L, 6)
 #undef RG_L
   g_launches += 3;
@@ -687,7 +735,7 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
                            unsigned long long* d, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.isize, P.jsize, k1 - k0);
-#define RG_L(M) k_update<T, M><<<g, BX, 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
+#define RG_L(M) k_update<T, M><<<g, blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
   RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
 #undef RG_L
   ++g_launches;
@@ -696,7 +744,7 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
 template <typename T>
 void MhdKernels<T>::copyPlanes(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_copy_planes<T><<<gridFor(P.isize, P.jsize, k1 - k0), BX, 0, s>>>(P, Uold, Unew, k0);
+  k_copy_planes<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, k0);
   ++g_launches;
 }
 

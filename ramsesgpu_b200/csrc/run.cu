@@ -483,7 +483,10 @@ class RunImpl final : public Run {
     const size_t budget = (size_t)(0.85 * (double)freeB);
     const long fit = (long)(budget / perPlane) - 4;
     if (fit < chunk) chunk = (int)std::max<long>(fit, 1);
-    if (userChunk_ > 0) chunk = std::min(userChunk_, updPlanes);
+    // scratch arrays are indexed with 32-bit element offsets: keep the largest (W) below 2^31
+    const long idxFit = (long)(2147483647LL / ((long long)NW_MHD * (long long)plane)) - 4;
+    if (idxFit < chunk) chunk = (int)std::max<long>(idxFit, 1);
+    if (userChunk_ > 0) chunk = std::min(std::min(userChunk_, updPlanes), chunk);
     chunkPlanes_ = chunk;
     sc_.planes = chunk + 4;
     RG_CUDA(cudaMalloc(&sc_.Q, plane * sc_.planes * 8 * sizeof(T)));

@@ -28,12 +28,22 @@ def measure(label):
     return {k: v[0] / steps for k, v in ph.items()}
 
 
+# bring the GPU to its steady-state clocks first (the first second after idle runs at boost clocks)
+for _ in range(60):
+    state["nstep"], state["t"], state["dt"] = run.oneStepIntegration(state["nstep"], state["t"], state["dt"])
+measure("steady-state warm-up")
 best = {}
+res = {}
+for v in (128, 64, 32, 128, 64, 32):
+    set_tuning("tile_x", v)
+    res[v] = min(res.get(v, 1e9), sum(measure("tile_x=%d" % v).values()))
+best["tile_x"] = min(res, key=res.get)
+set_tuning("tile_x", best["tile_x"])
 for key, phase in (("emf_minb", "emf"), ("flux_minb", "flux"), ("trace_minb", "trace"), ("update_minb", "update")):
     res = {}
-    for v in (2, 3, 4, 5, 6, 8):
+    for v in (3, 4, 5, 6, 6, 5, 4, 3):
         set_tuning(key, v)
-        res[v] = measure("%s=%d" % (key, v))[phase]
+        res[v] = min(res.get(v, 1e9), measure("%s=%d" % (key, v))[phase])
     b = min(res, key=res.get)
     best[key] = b
     set_tuning(key, b)
