@@ -85,6 +85,7 @@ real_t orc_compute_dt(const orc_params *p, const real_t *U);
    MHDRunGodunov.cpp:1447 -> cpu_v3 (3D) / cpu_v1 (2D); HydroRunGodunov.cpp:1820 -> cpu_v1 */
 void orc_godunov_unsplit(const orc_params *p, real_t *Uold, real_t *Unew, real_t dt,
                          real_t totalTime);
+void orc_step_no_boundaries(const orc_params *p, const real_t *Uold, real_t *Unew, real_t dt);
 /* run n steps like start()/oneStepIntegration (MHDRunGodunov.cpp:3921,4077): returns
    final buffer index (0 -> U, 1 -> U2); dt_trace (may be NULL) receives every dt */
 int orc_run_steps(const orc_params *p, real_t *U, real_t *U2, int nsteps, real_t *t,

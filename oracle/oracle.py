@@ -62,6 +62,8 @@ class Oracle:
         L.orc_make_all_boundaries.argtypes = [P, RP]; L.orc_make_all_boundaries.restype = None
         L.orc_compute_dt.argtypes = [P, RP]; L.orc_compute_dt.restype = R
         L.orc_godunov_unsplit.argtypes = [P, RP, RP, R, R]; L.orc_godunov_unsplit.restype = None
+        L.orc_step_no_boundaries.argtypes = [P, RP, RP, R]; L.orc_step_no_boundaries.restype = None
+        L.orc_make_boundaries.argtypes = [P, RP, C.c_int]; L.orc_make_boundaries.restype = None
         L.orc_run_steps.argtypes = [P, RP, RP, C.c_int, RP, RP]; L.orc_run_steps.restype = C.c_int
         L.orc_riemann_mhd.argtypes = [P, RP, RP, RP]; L.orc_riemann_mhd.restype = None
         L.orc_compute_emf.argtypes = [P, C.c_int, RP, R]; L.orc_compute_emf.restype = R
@@ -94,6 +96,13 @@ class Oracle:
 
     def make_all_boundaries(self, p, U):
         self.lib.orc_make_all_boundaries(C.byref(p), self._p(U))
+
+    def make_boundaries(self, p, U, idim):
+        """idim = 1, 2, 3 (XDIR, YDIR, ZDIR)"""
+        self.lib.orc_make_boundaries(C.byref(p), self._p(U), idim)
+
+    def step_no_boundaries(self, p, Uold, Unew, dt):
+        self.lib.orc_step_no_boundaries(C.byref(p), self._p(Uold), self._p(Unew), dt)
 
     def compute_dt(self, p, U):
         return float(self.lib.orc_compute_dt(C.byref(p), self._p(U)))

@@ -87,6 +87,18 @@ void orc_godunov_unsplit(const orc_params *P, real_t *Uold, real_t *Unew, real_t
   }
 }
 
+/* the step WITHOUT its leading ghost fill (the caller has filled the ghosts of Uold, e.g. slab by
+ * slab with a z-halo exchange): copy + prim + step, MHDRunGodunov.cpp:1463-1497 */
+void orc_step_no_boundaries(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
+  memcpy(Unew, Uold, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->mhdEnabled) {
+    if (P->dim == 3) orc_mhd3d_step_v3(P, Uold, Unew, dt);
+    else orc_mhd2d_step_v1(P, Uold, Unew, dt);
+  } else {
+    orc_hydro_step_v1(P, Uold, Unew, dt);
+  }
+}
+
 /* start() prologue + hot loop: MHDRunGodunov.cpp:3801-3921, :4077-4089 ; the caller has
  * already run orc_init_problem.  Ghost fill of U, copy to U2, then nsteps of
  * { dt = compute_dt(U or U2 by parity); godunov_unsplit; ++nStep; t += dt }. */

@@ -1,0 +1,84 @@
+"""CPU, world_size 2 over gloo: the z-slab decomposition protocol of the multi-GPU path
+(slab extents from rg_slab_extent, local x/y ghost fill, z-halo exchange of gw planes with periodic
+wrap, dt = global max of the inverse dt) reproduces the mono-domain result BIT FOR BIT when every
+rank advances its slab with the oracle.  This is the host logic of run.cu::fillGhosts/exchangeZ/
+compute_dt, exercised without a GPU."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ot3d_ini
+from ramsesgpu_b200.io import ini_override
+
+NSTEPS = 3
+N = (12, 10, 16)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    from ramsesgpu_b200 import slab_extent
+    o = Oracle("f64")
+    ini = ot3d_ini(N, OrszagTang={"kt": 1.0})
+    pg = o.params(ini)
+    Ug = o.init_problem(pg)                      # every rank builds the GLOBAL initial state ...
+    gw = pg.ghostWidth
+    nzl, koff = slab_extent(pg.nz, world, rank)
+    # ... and keeps its slab (ghost planes included)
+    U = np.ascontiguousarray(Ug[:, koff:koff + nzl + 2 * gw])
+    # local parameters: same dz, nz = slab thickness (zmax chosen so that (zmax-zmin)/nz == dz exactly)
+    pl = o.params(ini_override(ini, {"mesh": {"nz": nzl, "zmin": 0.0, "zmax": nzl / pg.nz}}))
+    assert pl.dz == pg.dz and pl.ksize == nzl + 2 * gw
+    up, down = (rank + 1) % world, (rank - 1) % world
+
+    def fill_ghosts(A):
+        o.make_boundaries(pl, A, 1)
+        o.make_boundaries(pl, A, 2)
+        top = torch.from_numpy(np.ascontiguousarray(A[:, nzl:nzl + gw]))      # my top inner planes
+        bot = torch.from_numpy(np.ascontiguousarray(A[:, gw:2 * gw]))        # my bottom inner planes
+        from_below, from_above = torch.empty_like(top), torch.empty_like(bot)
+        reqs = [dist.isend(top, up, tag=1), dist.isend(bot, down, tag=2),
+                dist.irecv(from_below, down, tag=1), dist.irecv(from_above, up, tag=2)]
+        for r in reqs:
+            r.wait()
+        A[:, :gw] = from_below.numpy()
+        A[:, nzl + gw:] = from_above.numpy()
+
+    fill_ghosts(U)
+    U2 = U.copy()
+    a, b = U, U2
+    for _ in range(NSTEPS):
+        mn = torch.tensor([o.compute_dt(pl, a)], dtype=torch.float64)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)   # reference: allReduce(MIN) of dt, HydroRunBaseMpi.cpp:700
+        dt = float(mn.item())
+        fill_ghosts(a)
+        o.step_no_boundaries(pl, a, b, dt)
+        a, b = b, a
+    np.save(os.path.join(out_dir, "slab%d.npy" % rank), a[:, gw:gw + nzl])
+    dist.destroy_process_group()
+
+
+def test_two_slabs_equal_mono_domain(tmp_path, oracle64):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    ini = ot3d_ini(N, OrszagTang={"kt": 1.0})
+    p = oracle64.params(ini)
+    Uf, _, _ = oracle64.run_steps(p, oracle64.init_problem(p), NSTEPS)
+    gw = p.ghostWidth
+    got = np.concatenate([np.load(tmp_path / ("slab%d.npy" % r)) for r in range(world)], axis=1)
+    assert np.array_equal(got[:, :, gw:-gw, gw:-gw], Uf[:, gw:-gw, gw:-gw, gw:-gw])
