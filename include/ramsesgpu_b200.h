@@ -108,6 +108,9 @@ int rg_get_stats(rg_handle h, rg_stats* out);
 int rg_reset_launch_count(void);
 /* z planes per pipeline chunk (0 = automatic: whole slab if the scratch fits in device memory) */
 int rg_set_chunk_planes(rg_handle h, int planes);
+/* multi-GPU: exchange the z halo of the buffer being written as soon as the slab's boundary planes
+ * are final, on a second stream, overlapped with the interior update (default on) */
+int rg_set_halo_overlap(rg_handle h, int on);
 
 /* occupancy knobs of the FP64 kernels (process-wide): key = "flux_minb" | "emf_minb" | "trace_minb" |
  * "update_minb", value = 2..8 resident blocks per SM the kernel variant is compiled for */

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rg_get_stats": (C.c_int, [H, C.POINTER(RgStats)]),
     "rg_reset_launch_count": (C.c_int, []),
     "rg_set_chunk_planes": (C.c_int, [H, C.c_int]),
+    "rg_set_halo_overlap": (C.c_int, [H, C.c_int]),
     "rg_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "rg_profile_begin": (C.c_int, [H]),
     "rg_profile_end": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),

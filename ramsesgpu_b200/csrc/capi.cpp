@@ -177,6 +177,7 @@ int rg_get_stats(rg_handle h, rg_stats* out) {
 }
 int rg_reset_launch_count(void) { rg::resetKernelLaunchCount(); return RG_OK; }
 int rg_set_chunk_planes(rg_handle h, int planes) { RG_TRY(h, h->run->setChunkPlanes(planes)) }
+int rg_set_halo_overlap(rg_handle h, int on) { RG_TRY(h, h->run->setOverlap(on != 0)) }
 
 int rg_set_tuning(const char* key, int value) {
   return rg::setTuning(key, value) ? RG_OK : fail(RG_ERR_INVALID, "unknown tuning key or value out of range");

@@ -89,6 +89,8 @@ class RunImpl final : public Run {
     RG_CUDA(cudaEventCreate(&ev0_));
     RG_CUDA(cudaEventCreate(&ev1_));
     RG_CUDA(cudaEventCreateWithFlags(&ev_sync_, cudaEventDisableTiming));
+    RG_CUDA(cudaEventCreateWithFlags(&evEdge_, cudaEventDisableTiming));
+    RG_CUDA(cudaEventCreateWithFlags(&evHalo_, cudaEventDisableTiming));
     RG_CUDA(cudaEventCreate(&evProf0_));
     RG_CUDA(cudaEventCreate(&evProf1_));
     for (int b = 0; b < 2; ++b) {
@@ -112,6 +114,8 @@ class RunImpl final : public Run {
     cudaEventDestroy(ev0_);
     cudaEventDestroy(ev1_);
     cudaEventDestroy(ev_sync_);
+    cudaEventDestroy(evEdge_);
+    cudaEventDestroy(evHalo_);
     cudaEventDestroy(evProf0_);
     cudaEventDestroy(evProf1_);
     recycleEvents();
@@ -196,6 +200,7 @@ class RunImpl final : public Run {
       dtCached_[b] = true;
     }
     if (nranks_ > 1) {  // slots hold bit patterns of non-negative doubles: a floating max is exact
+      if (haloDone_[0] || haloDone_[1]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));  // one communicator: keep order
       ncclCheck(nccl_->AllReduce(slots, slots, MAX_SLOTS, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_),
                 "allreduce(dt)");
     }
@@ -277,6 +282,7 @@ class RunImpl final : public Run {
 
   void copyToHost(int which, void* dst, size_t bytes) override {
     checkBytes(bytes);
+    if (haloDone_[which ? 1 : 0]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
     RG_CUDA(cudaMemcpyAsync(dst, dU_[which ? 1 : 0], bytes, cudaMemcpyDeviceToHost, stream_));
     RG_CUDA(cudaStreamSynchronize(stream_));
   }
@@ -321,6 +327,7 @@ class RunImpl final : public Run {
     return s;
   }
 
+  void setOverlap(bool on) override { overlapHalo_ = on; }
   void setChunkPlanes(int planes) override {
     userChunk_ = planes;
     freeScratch();
@@ -408,7 +415,11 @@ class RunImpl final : public Run {
   void checkBytes(size_t bytes) const {
     if (bytes != elems_ * sizeof(T)) throw std::runtime_error("host buffer size does not match the state array");
   }
-  void invalidate(int b) { ghostsValid_[b] = false; dtCached_[b] = false; }
+  void invalidate(int b) {
+    if (haloDone_[b]) { cudaStreamSynchronize(comm_stream_); haloDone_[b] = false; }
+    ghostsValid_[b] = false;
+    dtCached_[b] = false;
+  }
 
   void ncclCheck(int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + nccl_->GetErrorString(rc));
@@ -428,8 +439,17 @@ class RunImpl final : public Run {
   // x and y faces are always local; z faces are local for a single slab, otherwise the gw planes
   // next to each slab interface travel over NCCL (reference: copy_boundaries + transfert_boundaries
   // + make_boundary, HydroRunBaseMpi.cpp:3294-3389, without the host staging).
+  void zNeighbours(bool* hasLo, bool* hasHi) const {
+    const bool periodic = rp_.bc[4] == BC_PERIODIC && rp_.bc[5] == BC_PERIODIC;
+    *hasLo = rank_ > 0 || periodic;
+    *hasHi = rank_ < nranks_ - 1 || periodic;
+  }
+
   void fillGhosts(int b, int kLo, int kHi) {
     T* U = dU_[b];
+    if (haloDone_[b]) {  // the z halo of this buffer was exchanged early (overlapped with the step)
+      RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
+    }
     phase(PH_BOUNDARY, [&] {
       MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
       MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
@@ -437,27 +457,50 @@ class RunImpl final : public Run {
         MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
     });
     if (rp_.dim == 2 || nranks_ == 1) return;
-    const bool periodic = rp_.bc[4] == BC_PERIODIC && rp_.bc[5] == BC_PERIODIC;
-    const bool hasLo = rank_ > 0 || periodic, hasHi = rank_ < nranks_ - 1 || periodic;
+    bool hasLo, hasHi;
+    zNeighbours(&hasLo, &hasHi);
     // physical z faces of the outermost slabs
     if (!hasLo || !hasHi)
       phase(PH_BOUNDARY, [&] {
         MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
       });
-    phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi); });
+    if (haloDone_[b]) {
+      haloDone_[b] = false;
+      return;
+    }
+    phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi, stream_); });
   }
 
-  void exchangeZ(T* U, bool hasLo, bool hasHi) {
+  // Early halo of the buffer being written by the current step: as soon as the gw inner planes next
+  // to each slab interface are final, fill their x/y ghosts and exchange them on the communication
+  // stream while the interior chunks are still being computed on the main stream.
+  void startEarlyHalo(int b) {
+    T* U = dU_[b];
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    bool hasLo, hasHi;
+    zNeighbours(&hasLo, &hasHi);
+    RG_CUDA(cudaEventRecord(evEdge_, stream_));
+    RG_CUDA(cudaStreamWaitEvent(comm_stream_, evEdge_, 0));
+    MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, gw, 2 * gw, comm_stream_);
+    MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, gw, 2 * gw, comm_stream_);
+    MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kN - gw, kN, comm_stream_);
+    MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kN - gw, kN, comm_stream_);
+    exchangeZ(U, hasLo, hasHi, comm_stream_);
+    RG_CUDA(cudaEventRecord(evHalo_, comm_stream_));
+    haloDone_[b] = true;
+  }
+
+  void exchangeZ(T* U, bool hasLo, bool hasHi, cudaStream_t st) {
     const int gw = kp_.gw, lo = (rank_ + nranks_ - 1) % nranks_, hi = (rank_ + 1) % nranks_;
     const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
     const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
     ncclCheck(nccl_->GroupStart(), "group start");
     for (int v = 0; v < kp_.nvar; ++v) {
       T* base = U + (size_t)v * comp;
-      if (hasHi) ncclCheck(nccl_->Send(base + (size_t)(kp_.ksize - 2 * gw) * plane, n, dtype, hi, comm_, stream_), "send up");
-      if (hasLo) ncclCheck(nccl_->Send(base + (size_t)gw * plane, n, dtype, lo, comm_, stream_), "send down");
-      if (hasLo) ncclCheck(nccl_->Recv(base, n, dtype, lo, comm_, stream_), "recv from below");
-      if (hasHi) ncclCheck(nccl_->Recv(base + (size_t)(kp_.ksize - gw) * plane, n, dtype, hi, comm_, stream_), "recv from above");
+      if (hasHi) ncclCheck(nccl_->Send(base + (size_t)(kp_.ksize - 2 * gw) * plane, n, dtype, hi, comm_, st), "send up");
+      if (hasLo) ncclCheck(nccl_->Send(base + (size_t)gw * plane, n, dtype, lo, comm_, st), "send down");
+      if (hasLo) ncclCheck(nccl_->Recv(base, n, dtype, lo, comm_, st), "recv from below");
+      if (hasHi) ncclCheck(nccl_->Recv(base + (size_t)(kp_.ksize - gw) * plane, n, dtype, hi, comm_, st), "recv from above");
     }
     ncclCheck(nccl_->GroupEnd(), "group end");
     haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
@@ -511,8 +554,7 @@ class RunImpl final : public Run {
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN + 1, kp_.ksize, stream_);
     });
-    for (int ka = gw; ka <= kN; ka += chunkPlanes_) {
-      const int kb = std::min(ka + chunkPlanes_, kN + 1);
+    auto runChunk = [&](int ka, int kb) {  // update planes [ka, kb)
       const int fhi = std::min(kb, kN);
       MhdScratch<T> sc = sc_;
       sc.kbase = ka - 2;
@@ -522,6 +564,20 @@ class RunImpl final : public Run {
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_UPDATE, [&] { MhdKernels<T>::update(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_); });
+    };
+    auto runRange = [&](int k0, int k1) {
+      for (int ka = k0; ka < k1; ka += chunkPlanes_) runChunk(ka, std::min(ka + chunkPlanes_, k1));
+    };
+    // overlap needs three disjoint plane ranges: bottom gw planes, top gw planes (+ the ghost-face
+    // plane kN), interior
+    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw;
+    if (overlap) {
+      runRange(gw, 2 * gw);
+      runRange(kN - gw, kN + 1);
+      startEarlyHalo(dst);
+      runRange(2 * gw, kN - gw);
+    } else {
+      runRange(gw, kN + 1);
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
@@ -538,6 +594,9 @@ class RunImpl final : public Run {
   unsigned long long* dMax_ = nullptr;
   unsigned long long* hMax_ = nullptr;
   bool ghostsValid_[2] = {false, false}, dtCached_[2] = {false, false};
+  bool haloDone_[2] = {false, false};  // z halo already exchanged by startEarlyHalo()
+  bool overlapHalo_ = true;
+  cudaEvent_t evEdge_ = nullptr, evHalo_ = nullptr;
   cudaStream_t stream_ = nullptr, comm_stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_sync_ = nullptr;
   bool timed_ = false;

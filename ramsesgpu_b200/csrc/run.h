@@ -72,6 +72,7 @@ class Run {
   virtual void profileBegin() = 0;
   virtual void profileEnd(double* totalMs, double* phaseMs, unsigned long long* phaseLaunches) = 0;
   virtual void setChunkPlanes(int planes) = 0;
+  virtual void setOverlap(bool on) = 0;  // early z-halo exchange overlapped with the interior update
 
   // device probes for known-answer tests
   virtual void probeRiemann(int n, const void* ql, const void* qr, void* flux) = 0;

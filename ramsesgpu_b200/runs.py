@@ -125,6 +125,9 @@ class HydroRunBase:
         check(self._L.rg_profile_end(self._h, C.byref(tot), ms, cnt))
         return tot.value, {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PHASES)}
 
+    def set_halo_overlap(self, on):
+        check(self._L.rg_set_halo_overlap(self._h, 1 if on else 0))
+
     def set_chunk_planes(self, planes):
         check(self._L.rg_set_chunk_planes(self._h, planes))
 

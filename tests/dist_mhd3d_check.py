@@ -24,6 +24,7 @@ def main():
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     nz = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     periodic_z = (sys.argv[3] == "periodic") if len(sys.argv) > 3 else True
+    overlap = (sys.argv[4] != "nooverlap") if len(sys.argv) > 4 else True
     mesh = {} if periodic_z else {"boundary_zmin": 2, "boundary_zmax": 1}
     ini = ot3d_ini((20, 16, nz), OrszagTang={"kt": 1.0}, mesh=mesh)
     buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -45,6 +46,7 @@ def main():
         return run.getDataHost(n), dts
 
     with MHDRunGodunov(ini, rank=rank, nranks=world, nccl_unique_id=uid, device=local) as run:
+        run.set_halo_overlap(overlap)
         U, dts = run_steps(run)
         g, nzl, koff = run.layout.ghost_width, run.layout.nz_local, run.layout.k_offset
         halo = run.stats().halo_bytes_per_step
@@ -63,8 +65,8 @@ def main():
             Um, dtm = run_steps(mono)
         want = Um[:, g:-g, g:-g, g:-g]
         ok = bool(np.array_equal(got, want)) and dts == dtm
-        print("dist check: world=%d nz=%d steps=%d periodic_z=%s halo_bytes=%d identical=%s maxdiff=%.3e" %
-              (world, nz, nsteps, periodic_z, halo, ok, float(np.abs(got - want).max())), flush=True)
+        print("dist check: world=%d nz=%d steps=%d periodic_z=%s overlap=%s halo_bytes=%d identical=%s maxdiff=%.3e" %
+              (world, nz, nsteps, periodic_z, overlap, halo, ok, float(np.abs(got - want).max())), flush=True)
     else:
         dist.send(inner, 0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
