@@ -31,9 +31,14 @@ def case(name, ini_file, overrides, steps, precision="f64"):
     prefix = re.search(r"outputPrefix=(\S+)", text).group(1)
     fields = read_vti(os.path.join(wd, "%s_%07d.vti" % (prefix, steps)))
     init = read_vti(os.path.join(wd, "%s_%07d.vti" % (prefix, 0)))
-    dt0 = float(re.search(r"Initial dt :\s*(\S+)", stdout).group(1))
-    ttot = float(re.search(r"DEBUG : totalTime\s*(\S+)", stdout).group(1))
-    dtl = float(re.search(r"DEBUG : dt\s*(\S+)", stdout).group(1))
+    def grab(pattern):
+        m = re.search(pattern, stdout)
+        return float(m.group(1)) if m else float("nan")
+    dt0 = grab(r"Initial dt :\s*(\S+)")
+    if dt0 != dt0:  # the hydro driver only prints dt in its step lines
+        dt0 = grab(r"step=\s*0 t=\s*\S+ dt=\s*(\S+)")
+    ttot = grab(r"DEBUG : totalTime\s*(\S+)")
+    dtl = grab(r"DEBUG : dt\s*(\S+)")
     names = list(fields.keys())
     np.savez_compressed(os.path.join(OUT, name + ".npz"), ini=np.array(text), steps=steps, names=np.array(names),
                         final=np.stack([fields[n] for n in names]), initial=np.stack([init[n] for n in names]),
@@ -55,6 +60,12 @@ if __name__ == "__main__":
             "mesh": {"nx": 16, "ny": 16, "nz": 16, "boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1,
                      "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1},
             "hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hlla"}}, 4, "f64"),
+        # hydro: BASELINE.json configs[4] (implode, approx Riemann solver, Dirichlet walls) and configs[2]
+        # (Kelvin-Helmholtz, HLLC, periodic; FP32 like the config, and FP64)
+        "implode3d_16_s8": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}}, 8, "f64"),
+        "implode3d_hll_20x12x16_s5": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 20, "ny": 12, "nz": 16}, "hydro": {"riemannSolver": "hll", "slope_type": 1.0}}, 5, "f64"),
+        "kh3d_16x8x16_f32_s10": ("kelvin_helmholtz_gpu_3d.ini", {"mesh": {"nx": 16, "ny": 8, "nz": 16}}, 10, "f32"),
+        "kh3d_16x8x16_f64_s10": ("kelvin_helmholtz_gpu_3d.ini", {"mesh": {"nx": 16, "ny": 8, "nz": 16}}, 10, "f64"),
     }
     for name, (ini, ov, steps, prec) in cases.items():
         if only and name not in only:

@@ -51,6 +51,19 @@ struct MhdKernels {
                        cudaStream_t s);
 };
 
+// hydro traced state: 5 cell-centred primitives advanced by dt/2 + 15 half slopes
+constexpr int NW_HYDRO = 20;
+
+template <typename T>
+struct HydroKernels {
+  // W is [NW_HYDRO][planes][j][i] with kk = k - kbase
+  static void trace(const KParams<T>& P, const T* U, T* W, int planes, int kbase, int k0, int k1, T dt, cudaStream_t s);
+  static void fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, const T* W, int planes, int kbase, int k0, int k1,
+                         T dt, unsigned long long* slots, cudaStream_t s);
+  static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* slots, cudaStream_t s);
+  static void probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s);
+};
+
 // number of slots of the inverse-dt max reduction (power of two); every slot holds the bit pattern
 // of a non-negative double, so "max" works on the integer or on the floating view alike
 constexpr int MAX_SLOTS = 1024;

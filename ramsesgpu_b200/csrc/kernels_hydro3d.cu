@@ -1,0 +1,195 @@
+// 3D Euler (hydro) Godunov step for sm_100a, FP32 and FP64: two kernels per z-chunk.
+//   trace      : U (7-point) -> cons->prim on the fly, TVD slopes, half-step predictor -> W (20 comps)
+//   fluxUpdate : per cell, the six face fluxes from W of the cell and its six neighbours (each face
+//                flux is evaluated by both adjacent cells with identical inputs and code, hence
+//                bitwise identical and conservative), conservative update, inverse dt of the new state
+// Reference: HydroRunGodunov.cpp:2658-2890 (godunov_unsplit_cpu_v1, 3D), trace.h:544-661,
+// slope.h:324-427, riemann.h, HydroRunBase.cpp:386-426.  Where the reference stores qm/qp x3
+// (30 reals per cell) plus Q, this keeps 20 reals of traced state and no primitive array.
+#include "hydro_device.cuh"
+#include "kernel_common.cuh"
+#include "kernels.h"
+
+namespace rg {
+
+namespace {
+
+enum { H_R = 0, H_P, H_U, H_V, H_W, H_DX = 5, H_DY = 10, H_DZ = 15 };  // slopes: (r, p, u, v, w) each
+static_assert(H_DZ + 5 == NW_HYDRO, "hydro W layout");
+
+template <typename T>
+__global__ void __launch_bounds__(BX) k_hydro_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                                    T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(1, P.isize - 2, 1, P.jsize - 2, i, j)) return;
+  const UView<T> U = uview(Uin, P);
+  const View<T> W = view(Wp, P, planes, kbase);
+  auto prim = [&](int ii, int jj, int kk, T(&q)[5]) {
+    dev::cons_to_prim_hydro(P, U(ID, ii, jj, kk), U(IP, ii, jj, kk), U(IU, ii, jj, kk), U(IV, ii, jj, kk),
+                            U(IW, ii, jj, kk), q);
+  };
+  T q[5], qxm[5], qxp[5], qym[5], qyp[5], qzm[5], qzp[5];
+  prim(i, j, k, q);
+  prim(i - 1, j, k, qxm); prim(i + 1, j, k, qxp);
+  prim(i, j - 1, k, qym); prim(i, j + 1, k, qyp);
+  prim(i, j, k - 1, qzm); prim(i, j, k + 1, qzp);
+  const T st = P.slope_type, h = T(0.5);
+  T dx_[5], dy_[5], dz_[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    dx_[v] = h * dev::hydro_slope(st, qxm[v], q[v], qxp[v]);
+    dy_[v] = h * dev::hydro_slope(st, qym[v], q[v], qyp[v]);
+    dz_[v] = h * dev::hydro_slope(st, qzm[v], q[v], qzp[v]);
+  }
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  const T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], g = P.gamma0;
+  const T ir = dev::rcp(r);
+  // half-step predictor, trace.h:585-600
+  const T sr0 = (-u * dx_[ID] - dx_[IU] * r) * dtdx + (-v * dy_[ID] - dy_[IV] * r) * dtdy + (-w * dz_[ID] - dz_[IW] * r) * dtdz;
+  const T su0 = (-u * dx_[IU] - dx_[IP] * ir) * dtdx + (-v * dy_[IU]) * dtdy + (-w * dz_[IU]) * dtdz;
+  const T sv0 = (-u * dx_[IV]) * dtdx + (-v * dy_[IV] - dy_[IP] * ir) * dtdy + (-w * dz_[IV]) * dtdz;
+  const T sw0 = (-u * dx_[IW]) * dtdx + (-v * dy_[IW]) * dtdy + (-w * dz_[IW] - dz_[IP] * ir) * dtdz;
+  const T sp0 = (-u * dx_[IP] - dx_[IU] * g * p) * dtdx + (-v * dy_[IP] - dy_[IV] * g * p) * dtdy + (-w * dz_[IP] - dz_[IW] * g * p) * dtdz;
+  W(H_R, i, j, k) = r + sr0; W(H_P, i, j, k) = p + sp0;
+  W(H_U, i, j, k) = u + su0; W(H_V, i, j, k) = v + sv0; W(H_W, i, j, k) = w + sw0;
+  // slope component order in W: r, p, u, v, w  (ID, IP, IU, IV, IW)
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    W(H_DX + c, i, j, k) = dx_[c];
+    W(H_DY + c, i, j, k) = dy_[c];
+    W(H_DZ + c, i, j, k) = dz_[c];
+  }
+}
+
+// state at a face of cell (i,j,k): W centre +/- half slope along DIR, floors (trace.h:603-660),
+// rotated so that .u is the velocity normal to the face
+template <typename T, int DIR>
+__device__ __forceinline__ dev::HState<T> hydro_face(const KParams<T>& P, const View<const T>& W, int i, int j, int k, T sgn) {
+  constexpr int S = (DIR == 0) ? H_DX : (DIR == 1) ? H_DY : H_DZ;
+  dev::HState<T> s;
+  s.r = dev::mx(P.smallr, W(H_R, i, j, k) + sgn * W(S + 0, i, j, k));
+  s.p = dev::mx(P.smallp * s.r, W(H_P, i, j, k) + sgn * W(S + 1, i, j, k));
+  const T u = W(H_U, i, j, k) + sgn * W(S + 2, i, j, k);
+  const T v = W(H_V, i, j, k) + sgn * W(S + 3, i, j, k);
+  const T w = W(H_W, i, j, k) + sgn * W(S + 4, i, j, k);
+  if (DIR == 0) { s.u = u; s.v = v; s.w = w; }
+  else if (DIR == 1) { s.u = v; s.v = u; s.w = w; }
+  else { s.u = w; s.v = v; s.w = u; }
+  return s;
+}
+
+// flux through the LOW face of cell (i,j,k) along DIR, in physical component order
+template <typename T, int DIR>
+__device__ __forceinline__ void hydro_low_flux(const KParams<T>& P, const View<const T>& W, int i, int j, int k, T (&f)[5]) {
+  const dev::HState<T> L = hydro_face<T, DIR>(P, W, i - (DIR == 0), j - (DIR == 1), k - (DIR == 2), T(1));
+  const dev::HState<T> R = hydro_face<T, DIR>(P, W, i, j, k, T(-1));
+  T fr[5];
+  dev::riemann_hydro(P, L, R, fr);
+  f[ID] = fr[ID]; f[IP] = fr[IP];
+  f[IU] = (DIR == 0) ? fr[IU] : (DIR == 1) ? fr[IV] : fr[IW];
+  f[IV] = (DIR == 1) ? fr[IU] : fr[IV];
+  f[IW] = (DIR == 2) ? fr[IU] : fr[IW];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BX) k_hydro_flux_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                                          T* __restrict__ Unew, const T* __restrict__ Wp, int planes,
+                                                          int kbase, int k0, T dt, unsigned long long* __restrict__ slots) {
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  const bool valid = tileCoords(0, P.isize, 0, P.jsize, i, j);
+  const int gw = P.gw;
+  T invDt = T(0);
+  if (valid) {
+    const UView<T> U = uview(Uold, P);
+    const size_t comp = (size_t)P.isize * P.jsize * P.ksize;
+    const size_t idx = (size_t)k * P.isize * P.jsize + (size_t)j * P.isize + i;
+    T un[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) un[v] = U(v, i, j, k);
+    const bool inner = i >= gw && i < P.isize - gw && j >= gw && j < P.jsize - gw && k >= gw && k < P.ksize - gw;
+    if (inner) {
+      const View<const T> W = view<const T>(Wp, P, planes, kbase);
+      const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+      T fxl[5], fyl[5], fzl[5], fxh[5], fyh[5], fzh[5];
+      hydro_low_flux<T, 0>(P, W, i, j, k, fxl);
+      hydro_low_flux<T, 1>(P, W, i, j, k, fyl);
+      hydro_low_flux<T, 2>(P, W, i, j, k, fzl);
+      hydro_low_flux<T, 0>(P, W, i + 1, j, k, fxh);
+      hydro_low_flux<T, 1>(P, W, i, j + 1, k, fyh);
+      hydro_low_flux<T, 2>(P, W, i, j, k + 1, fzh);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {  // summation order of the reference's serial scatter
+        T s = un[v];
+        s += fxl[v] * dtdx; s += fyl[v] * dtdy; s += fzl[v] * dtdz;
+        s -= fxh[v] * dtdx; s -= fyh[v] * dtdy; s -= fzh[v] * dtdz;
+        un[v] = s;
+      }
+      T q[5];
+      const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], un[IW], q);
+      invDt = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz;
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) Unew[v * comp + idx] = un[v];
+  }
+  if (slots != nullptr) reduceMaxToSlots(invDt, slots);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BX) k_hydro_invdt(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                                    unsigned long long* __restrict__ slots) {
+  int i, j;
+  const bool valid = tileCoords(P.gw, P.nx, P.gw, P.ny, i, j);
+  const int k = P.gw + blockIdx.z;
+  T invDt = T(0);
+  if (valid) {
+    const UView<T> U = uview(Uin, P);
+    T q[5];
+    const T c = dev::cons_to_prim_hydro(P, U(ID, i, j, k), U(IP, i, j, k), U(IU, i, j, k), U(IV, i, j, k), U(IW, i, j, k), q);
+    invDt = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz;
+  }
+  reduceMaxToSlots(invDt, slots);
+}
+
+template <typename T>
+__global__ void k_probe_riemann_hydro(const __grid_constant__ KParams<T> P, int n, const T* ql, const T* qr, T* flux) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const T *l = ql + 5 * t, *r = qr + 5 * t;
+  dev::HState<T> L{l[ID], l[IP], l[IU], l[IV], l[IW]}, R{r[ID], r[IP], r[IU], r[IV], r[IW]};
+  T f[5];
+  dev::riemann_hydro(P, L, R, f);
+  for (int v = 0; v < 5; ++v) flux[5 * t + v] = f[v];
+}
+
+}  // namespace
+
+template <typename T>
+void HydroKernels<T>::trace(const KParams<T>& P, const T* U, T* W, int planes, int kbase, int k0, int k1, T dt, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_hydro_trace<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), blockShape(), 0, s>>>(P, U, W, planes, kbase, k0, dt);
+  ++g_launches;
+}
+template <typename T>
+void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, const T* W, int planes, int kbase, int k0,
+                                 int k1, T dt, unsigned long long* slots, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_hydro_flux_update<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots);
+  ++g_launches;
+}
+template <typename T>
+void HydroKernels<T>::computeInvDt(const KParams<T>& P, const T* U, unsigned long long* slots, cudaStream_t s) {
+  k_hydro_invdt<T><<<gridFor(P.nx, P.ny, P.nz), blockShape(), 0, s>>>(P, U, slots);
+  ++g_launches;
+}
+template <typename T>
+void HydroKernels<T>::probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s) {
+  k_probe_riemann_hydro<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, ql, qr, flux);
+  ++g_launches;
+}
+
+template struct HydroKernels<double>;
+template struct HydroKernels<float>;
+
+}  // namespace rg

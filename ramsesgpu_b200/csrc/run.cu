@@ -195,8 +195,11 @@ class RunImpl final : public Run {
     unsigned long long* slots = dMax_ + (size_t)b * MAX_SLOTS;
     if (!dtCached_[b]) {
       RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
-      if (!rp_.mhdEnabled) throw std::runtime_error("hydro compute_dt not available in this build");
-      phase(PH_DT, [&] { MhdKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_); });
+      if (!rp_.mhdEnabled && rp_.dim != 3) throw std::runtime_error("2D hydro is not available in this build");
+      phase(PH_DT, [&] {
+        if (rp_.mhdEnabled) MhdKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
+        else HydroKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
+      });
       dtCached_[b] = true;
     }
     if (nranks_ > 1) {  // slots hold bit patterns of non-negative doubles: a floating max is exact
@@ -209,7 +212,8 @@ class RunImpl final : public Run {
     unsigned long long best = 0;
     for (int i = 0; i < MAX_SLOTS; ++i) best = std::max(best, hMax_[i]);
     // seed of the running max, reference MHDRunBase.cpp:144
-    T invDt = kp_.smallc / std::min(kp_.dx, kp_.dy);
+    // (the hydro driver starts from 0, HydroRunBase.cpp:386)
+    T invDt = rp_.mhdEnabled ? kp_.smallc / std::min(kp_.dx, kp_.dy) : T(0);
     invDt = std::max(invDt, static_cast<T>(decodeMax(best)));
     return static_cast<double>(kp_.cfl / invDt);
   }
@@ -221,6 +225,8 @@ class RunImpl final : public Run {
     if (!ghostsValid_[src]) make_all_boundaries(src);
     if (rp_.mhdEnabled && rp_.dim == 3 && !(kp_.Omega0 > T(0))) {
       stepMhd3d(src, dst, static_cast<T>(dt));
+    } else if (!rp_.mhdEnabled && rp_.dim == 3) {
+      stepHydro3d(src, dst, static_cast<T>(dt));
     } else {
       throw std::runtime_error("this solver variant is not available in this build");
     }
@@ -335,14 +341,16 @@ class RunImpl final : public Run {
 
   void probeRiemann(int n, const void* ql, const void* qr, void* flux) override {
     T *dl, *dr, *df;
-    RG_CUDA(cudaMalloc(&dl, n * 8 * sizeof(T)));
-    RG_CUDA(cudaMalloc(&dr, n * 8 * sizeof(T)));
-    RG_CUDA(cudaMalloc(&df, n * 8 * sizeof(T)));
-    RG_CUDA(cudaMemcpy(dl, ql, n * 8 * sizeof(T), cudaMemcpyHostToDevice));
-    RG_CUDA(cudaMemcpy(dr, qr, n * 8 * sizeof(T), cudaMemcpyHostToDevice));
-    MhdKernels<T>::probeRiemann(kp_, n, dl, dr, df, stream_);
+    const size_t nv = rp_.mhdEnabled ? 8 : 5;  // state size: MHD 8, hydro 5
+    RG_CUDA(cudaMalloc(&dl, n * nv * sizeof(T)));
+    RG_CUDA(cudaMalloc(&dr, n * nv * sizeof(T)));
+    RG_CUDA(cudaMalloc(&df, n * nv * sizeof(T)));
+    RG_CUDA(cudaMemcpy(dl, ql, n * nv * sizeof(T), cudaMemcpyHostToDevice));
+    RG_CUDA(cudaMemcpy(dr, qr, n * nv * sizeof(T), cudaMemcpyHostToDevice));
+    if (rp_.mhdEnabled) MhdKernels<T>::probeRiemann(kp_, n, dl, dr, df, stream_);
+    else HydroKernels<T>::probeRiemann(kp_, n, dl, dr, df, stream_);
     RG_CUDA(cudaStreamSynchronize(stream_));
-    RG_CUDA(cudaMemcpy(flux, df, n * 8 * sizeof(T), cudaMemcpyDeviceToHost));
+    RG_CUDA(cudaMemcpy(flux, df, n * nv * sizeof(T), cudaMemcpyDeviceToHost));
     cudaFree(dl); cudaFree(dr); cudaFree(df);
   }
   void probeEmf(int n, int emfDir, const void* qEdge, const void* xPos, void* emf) override {
@@ -508,8 +516,10 @@ class RunImpl final : public Run {
 
   // ---- scratch / chunking ------------------------------------------------------------------------
   void freeScratch() {
-    if (sc_.Q) { cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL); }
-    if (sc_.Q) deviceBytes_ -= scratchBytes_;
+    if (sc_.W) {  // cudaFree(nullptr) is a no-op for the arrays the hydro path does not use
+      cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL);
+      deviceBytes_ -= scratchBytes_;
+    }
     sc_ = MhdScratch<T>();
     scratchBytes_ = 0;
     chunkPlanes_ = 0;
@@ -581,6 +591,60 @@ class RunImpl final : public Run {
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
+  }
+
+  // ---- 3D hydro step: reference HydroRunGodunov::godunov_unsplit_cpu + _v1 (HydroRunGodunov.cpp:1820, 2658)
+  void ensureScratchHydro3d() {
+    if (sc_.W) return;
+    const size_t plane = (size_t)kp_.isize * kp_.jsize;
+    const size_t perPlane = plane * sizeof(T) * NW_HYDRO;
+    const int updPlanes = kp_.nz;
+    int chunk = updPlanes;
+    size_t freeB = 0, totalB = 0;
+    RG_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const long fit = (long)((size_t)(0.85 * (double)freeB) / perPlane) - 2;
+    if (fit < chunk) chunk = (int)std::max<long>(fit, 1);
+    const long idxFit = (long)(2147483647LL / ((long long)NW_HYDRO * (long long)plane)) - 2;
+    if (idxFit < chunk) chunk = (int)std::max<long>(idxFit, 1);
+    if (userChunk_ > 0) chunk = std::min(std::min(userChunk_, updPlanes), chunk);
+    chunkPlanes_ = chunk;
+    sc_.planes = chunk + 2;
+    RG_CUDA(cudaMalloc(&sc_.W, plane * sc_.planes * NW_HYDRO * sizeof(T)));
+    scratchBytes_ = perPlane * sc_.planes;
+    deviceBytes_ += scratchBytes_;
+  }
+
+  void stepHydro3d(int src, int dst, T dt) {
+    ensureScratchHydro3d();
+    const T* Uold = dU_[src];
+    T* Unew = dU_[dst];
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    unsigned long long* slots = dMax_ + (size_t)dst * MAX_SLOTS;
+    RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
+    phase(PH_COPY, [&] {
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN, kp_.ksize, stream_);
+    });
+    auto runRange = [&](int k0, int k1) {
+      for (int ka = k0; ka < k1; ka += chunkPlanes_) {
+        const int kb = std::min(ka + chunkPlanes_, k1);
+        phase(PH_TRACE, [&] { HydroKernels<T>::trace(kp_, Uold, sc_.W, sc_.planes, ka - 1, ka - 1, kb + 1, dt, stream_); });
+        phase(PH_UPDATE, [&] {
+          HydroKernels<T>::fluxUpdate(kp_, Uold, Unew, sc_.W, sc_.planes, ka - 1, ka, kb, dt, slots, stream_);
+        });
+      }
+    };
+    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw;
+    if (overlap) {
+      runRange(gw, 2 * gw);
+      runRange(kN - gw, kN);
+      startEarlyHalo(dst);
+      runRange(2 * gw, kN - gw);
+    } else {
+      runRange(gw, kN);
+    }
+    ghostsValid_[dst] = false;
+    dtCached_[dst] = true;
   }
 
   ConfigMap cfg_;

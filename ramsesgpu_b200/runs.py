@@ -139,8 +139,10 @@ class HydroRunBase:
 
     # -- device probes ---------------------------------------------------------------------------
     def probe_riemann_mhd(self, ql, qr):
-        ql = np.ascontiguousarray(ql, self.dtype).reshape(-1, 8)
-        qr = np.ascontiguousarray(qr, self.dtype).reshape(-1, 8)
+        """riemann_mhd (MHD handle, 8-component states) or riemann<NVAR_3D> (hydro handle, 5)."""
+        nv = 8 if self.layout.mhd else 5
+        ql = np.ascontiguousarray(ql, self.dtype).reshape(-1, nv)
+        qr = np.ascontiguousarray(qr, self.dtype).reshape(-1, nv)
         f = np.empty_like(ql)
         check(self._L.rg_probe_riemann_mhd(self._h, ql.shape[0], ql.ctypes.data, qr.ctypes.data, f.ctypes.data))
         return f
@@ -160,7 +162,8 @@ class MHDRunBase(HydroRunBase):
 
 
 class HydroRunGodunov(HydroRunBase):
-    pass
+    def probe_riemann(self, ql, qr):
+        return self.probe_riemann_mhd(ql, qr)
 
 
 class MHDRunGodunov(MHDRunBase):
