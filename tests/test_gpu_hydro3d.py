@@ -40,13 +40,15 @@ def test_golden_reference_run(native, name, tol):
     U, dts, gw = run_gpu(str(g["ini"]), int(g["steps"]), fp32=fp32)
     assert U.dtype == (np.float32 if fp32 else np.float64)
     inner = U[:, gw:-gw, gw:-gw, gw:-gw]
+    # momentum components are measured against the norm of the whole momentum field: a component
+    # that only carries the small seeded perturbation (KH "my") or stays ~0 by symmetry (implode)
+    # has no meaningful norm of its own at float / double round-off
+    mom_norm = np.sqrt(sum(float(np.sum(g["final"][v].astype(np.float64) ** 2)) for v in (2, 3, 4)))
     for v, vname in enumerate(g["names"]):
-        err = l2_relative(g["final"][v], inner[v])
-        scale = np.abs(g["final"][v]).max()
-        if scale < 1e-12:  # a momentum component that stays ~0 (implode symmetry): absolute check
-            assert np.abs(inner[v]).max() < 1e-10
-        else:
-            assert err < tol, (name, vname, err)
+        ref, got = g["final"][v].astype(np.float64), inner[v].astype(np.float64)
+        norm = np.sqrt(np.sum(ref ** 2)) if v < 2 else max(mom_norm, 1e-300)
+        err = np.sqrt(np.sum((ref - got) ** 2)) / norm
+        assert err < tol, (name, vname, err)
     assert abs(dts[0] - g["dt0"]) < 2e-6 * g["dt0"]
 
 
