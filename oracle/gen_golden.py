@@ -60,6 +60,9 @@ if __name__ == "__main__":
             "mesh": {"nx": 16, "ny": 16, "nz": 16, "boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1,
                      "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1},
             "hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hlla"}}, 4, "f64"),
+        # BASELINE.json configs[0]: 2D MHD Orszag-Tang (implementation 1) at a parity size
+        "ot2d_32_s12": ("orszag-tang.ini", {"mesh": {"nx": 32, "ny": 32}}, 12, "f64"),
+        "ot2d_40x24_hll_s6": ("orszag-tang.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemannSolver": "hll", "slope_type": 1.0}, "MHD": {"magRiemannSolver": "hllf"}}, 6, "f64"),
         # hydro: BASELINE.json configs[4] (implode, approx Riemann solver, Dirichlet walls) and configs[2]
         # (Kelvin-Helmholtz, HLLC, periodic; FP32 like the config, and FP64)
         "implode3d_16_s8": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}}, 8, "f64"),

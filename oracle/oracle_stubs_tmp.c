@@ -1,5 +1,4 @@
 #include "oracle.h"
 #include <stdio.h>
-void orc_mhd2d_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt){(void)P;(void)Uold;(void)Unew;(void)dt;}
 void orc_mhd3d_rotating_step(const orc_params *P, real_t *Uold, real_t *Unew, real_t dt, real_t t){(void)P;(void)Uold;(void)Unew;(void)dt;(void)t;}
 void orc_make_all_boundaries_shear(const orc_params *P, real_t *U, real_t dt, real_t t){(void)P;(void)U;(void)dt;(void)t;}

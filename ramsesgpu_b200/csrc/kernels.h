@@ -51,6 +51,16 @@ struct MhdKernels {
                        cudaStream_t s);
 };
 
+// 2D MHD traced state: 8 cell centred + 4 face B + 14 half slopes + 4 face-field half slopes
+constexpr int NW_MHD2D = 30;
+
+template <typename T>
+struct Mhd2dKernels {
+  // scratch: Q[8], W[NW_MHD2D], F[12], E[1], each [comp][j][i]
+  static void step(const KParams<T>& P, const T* Uold, T* Unew, T* Q, T* W, T* F, T* E, T dt,
+                   unsigned long long* slots, cudaStream_t s);
+};
+
 // hydro traced state: 5 cell-centred primitives advanced by dt/2 + 15 half slopes
 constexpr int NW_HYDRO = 20;
 

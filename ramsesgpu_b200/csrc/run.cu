@@ -227,6 +227,8 @@ class RunImpl final : public Run {
       stepMhd3d(src, dst, static_cast<T>(dt));
     } else if (!rp_.mhdEnabled && rp_.dim == 3) {
       stepHydro3d(src, dst, static_cast<T>(dt));
+    } else if (rp_.mhdEnabled && rp_.dim == 2) {
+      stepMhd2d(src, dst, static_cast<T>(dt));
     } else {
       throw std::runtime_error("this solver variant is not available in this build");
     }
@@ -591,6 +593,28 @@ class RunImpl final : public Run {
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
+  }
+
+  // ---- 2D MHD step: reference godunov_unsplit_cpu + _v1 (mhd_godunov_unsplit_cpu_v1.cpp:36-243)
+  void stepMhd2d(int src, int dst, T dt) {
+    if (!sc_.W) {
+      const size_t plane = (size_t)kp_.isize * kp_.jsize;
+      RG_CUDA(cudaMalloc(&sc_.Q, plane * 8 * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.W, plane * NW_MHD2D * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.F, plane * 12 * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.E, plane * sizeof(T)));
+      scratchBytes_ = plane * (8 + NW_MHD2D + 12 + 1) * sizeof(T);
+      deviceBytes_ += scratchBytes_;
+      sc_.planes = 1;
+      chunkPlanes_ = 1;
+    }
+    unsigned long long* slots = dMax_ + (size_t)dst * MAX_SLOTS;
+    RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
+    phase(PH_UPDATE, [&] {
+      Mhd2dKernels<T>::step(kp_, dU_[src], dU_[dst], sc_.Q, sc_.W, sc_.F, sc_.E, dt, slots, stream_);
+    });
+    ghostsValid_[dst] = false;
+    dtCached_[dst] = true;
   }
 
   // ---- 3D hydro step: reference HydroRunGodunov::godunov_unsplit_cpu + _v1 (HydroRunGodunov.cpp:1820, 2658)

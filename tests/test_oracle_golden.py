@@ -6,24 +6,29 @@ import pytest
 from conftest import load_golden
 from ramsesgpu_b200.io import l2_relative
 
-CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4"]
+CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4",
+         "ot2d_32_s12", "ot2d_40x24_hll_s6", "implode3d_16_s8", "implode3d_hll_20x12x16_s5",
+         "kh3d_16x8x16_f64_s10", "kh3d_16x8x16_f32_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_oracle_matches_reference_run(oracle64, name):
+def test_oracle_matches_reference_run(oracle64, oracle32, name):
     g = load_golden(name)
-    p = oracle64.params(str(g["ini"]))
-    U = oracle64.init_problem(p)
+    orc = oracle32 if str(g["precision"]) == "f32" else oracle64
+    p = orc.params(str(g["ini"]))
+    U = orc.init_problem(p)
     gw = p.ghostWidth
-    # initial state (inner cells) is bit-identical
-    assert np.array_equal(U[:, gw:-gw, gw:-gw, gw:-gw], g["initial"])
-    Uf, t, dts = oracle64.run_steps(p, U, int(g["steps"]))
-    final = Uf[:, gw:-gw, gw:-gw, gw:-gw]
-    # same compiler family, same operation order: bitwise
+    cut = (lambda A: A[:, 0, gw:-gw, gw:-gw]) if p.dim == 2 else (lambda A: A[:, gw:-gw, gw:-gw, gw:-gw])
+    # initial state (inner cells) is bit-identical (incl. the glibc rand()/drand48 streams)
+    assert np.array_equal(cut(U), g["initial"])
+    Uf, t, dts = orc.run_steps(p, U, int(g["steps"]))
+    final = cut(Uf)
+    # same compiler family, same operation order: bitwise, in double and in float
     assert np.array_equal(final, g["final"]), max(l2_relative(a, b) for a, b in zip(g["final"], final))
-    assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])       # stdout prints 12 digits
-    assert abs(dts[-1] - g["dt_last"]) <= 1e-11 * abs(g["dt_last"])
-    assert abs(dts[0] - g["dt0"]) <= 2e-6 * abs(g["dt0"])                 # "Initial dt" is printed with 6 digits
+    if g["total_time"] == g["total_time"]:  # the hydro driver does not print these
+        assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])   # stdout prints 12 digits
+        assert abs(dts[-1] - g["dt_last"]) <= 1e-11 * abs(g["dt_last"])
+    assert abs(dts[0] - g["dt0"]) <= 2e-6 * abs(g["dt0"])                 # printed with 6-7 digits
 
 
 def test_riemann_hlld_known_answer(oracle64):
