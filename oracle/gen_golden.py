@@ -63,6 +63,9 @@ if __name__ == "__main__":
         # BASELINE.json configs[0]: 2D MHD Orszag-Tang (implementation 1) at a parity size
         "ot2d_32_s12": ("orszag-tang.ini", {"mesh": {"nx": 32, "ny": 32}}, 12, "f64"),
         "ot2d_40x24_hll_s6": ("orszag-tang.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemannSolver": "hll", "slope_type": 1.0}, "MHD": {"magRiemannSolver": "hllf"}}, 6, "f64"),
+        # BASELINE.json configs[3]: MRI in the shearing box (rotating frame, isothermal), parity size
+        "mri3d_16x32x16_s12": ("mhd_mri_3d.ini", {"mesh": {"nx": 16, "ny": 32, "nz": 16}}, 12, "f64"),
+        "mri3d_12x20x8_s40": ("mhd_mri_3d.ini", {"mesh": {"nx": 12, "ny": 20, "nz": 8}}, 40, "f64"),
         # hydro: BASELINE.json configs[4] (implode, approx Riemann solver, Dirichlet walls) and configs[2]
         # (Kelvin-Helmholtz, HLLC, periodic; FP32 like the config, and FP64)
         "implode3d_16_s8": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}}, 8, "f64"),

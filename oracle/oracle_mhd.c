@@ -18,6 +18,7 @@
 #define SQRT_ sqrtf
 #define FABS_ fabsf
 #define COPYSIGN_ copysignf
+#define FMOD_ fmodf
 #else
 #define R(x) x
 #define FMAX_ fmax
@@ -25,11 +26,15 @@
 #define SQRT_ sqrt
 #define FABS_ fabs
 #define COPYSIGN_ copysign
+#define FMOD_ fmod
 #endif
 #define HALF R(0.5)
 #define ZERO R(0.0)
 #define ONE R(1.0)
 #define FOURTH R(0.25)
+#ifdef ORACLE_FLOAT
+#define fmodf_ fmodf
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * mhd_utils.h:28-52  find_speed_fast<dir>
@@ -602,8 +607,24 @@ real_t orc_compute_dt_mhd(const orc_params *P, const real_t *U) {
  * 3D MHD unsplit step, implementation 3/4 on the CPU: mhd_godunov_unsplit_cpu_v3.cpp:11-715
  * (the part of godunov_unsplit_cpu after boundaries + copy; Omega0 == 0 only)
  * ---------------------------------------------------------------------------------------- */
-void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
+static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt, real_t totalTime, int rot) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  const int nx = P->nx, ny = P->ny;
+  const real_t Omega0 = P->Omega0, dx = P->dx, dy = P->dy;
+  const int shearBox = rot && P->bc[0] == BC_SHEARINGBOX && P->bc[1] == BC_SHEARINGBOX && Omega0 > 0;
+  /* Crank-Nicolson Coriolis coefficients, MHDRunGodunov.cpp:2039-2053 */
+  real_t lambda = 0, ratio = 1, alpha1 = 1, alpha2 = 0;
+  if (rot) {
+    lambda = Omega0 * dt;
+    lambda = FOURTH * lambda * lambda;
+    ratio = (ONE - lambda) / (ONE + lambda);
+    alpha1 = ONE / (ONE + lambda);
+    alpha2 = Omega0 * dt / (ONE + lambda);
+  }
+  /* x-border density flux and emf_y strips [comp][k][j] (h_shear_flux_xmin/xmax) and their remaps */
+  real_t *sfmin = calloc((size_t)2 * jsz * ksz, sizeof(real_t)), *sfmax = calloc((size_t)2 * jsz * ksz, sizeof(real_t));
+  real_t *rmmin = calloc((size_t)jsz * ksz, sizeof(real_t)), *rmmax = calloc((size_t)jsz * ksz, sizeof(real_t));
+#define SF(arr, j, k, c) (arr)[(size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(c))]
   const size_t ncell = (size_t)isz * jsz * ksz;
   const real_t dtdx = dt / P->dx, dtdy = dt / P->dy, dtdz = dt / P->dz;
 
@@ -637,6 +658,11 @@ void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, re
         B = HALF * (AT(Uold, i, j, k - 1, IB) + AT(Uold, i, j, k, IB));
         C = HALF * (AT(Uold, i, j - 1, k, IC) + AT(Uold, i, j, k, IC));
         AT(elec, i, j, k, 0) = v * C - w * B;
+        if (rot) { /* MHDRunGodunov.cpp:2474-2478 */
+          real_t xPos = P->xMin + dx / 2 + (i - gw) * dx;
+          real_t shear = -1.5 * Omega0 * xPos;
+          AT(elec, i, j, k, 0) += shear * C;
+        }
         u = FOURTH * (AT(Q, i - 1, j, k - 1, IU) + AT(Q, i - 1, j, k, IU) + AT(Q, i, j, k - 1, IU) + AT(Q, i, j, k, IU));
         w = FOURTH * (AT(Q, i - 1, j, k - 1, IW) + AT(Q, i - 1, j, k, IW) + AT(Q, i, j, k - 1, IW) + AT(Q, i, j, k, IW));
         A = HALF * (AT(Uold, i, j, k - 1, IA) + AT(Uold, i, j, k, IA));
@@ -647,6 +673,11 @@ void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, re
         A = HALF * (AT(Uold, i, j - 1, k, IA) + AT(Uold, i, j, k, IA));
         B = HALF * (AT(Uold, i - 1, j, k, IB) + AT(Uold, i, j, k, IB));
         AT(elec, i, j, k, 2) = u * B - v * A;
+        if (rot) { /* :2517-2521 */
+          real_t xPos = P->xMin + dx / 2 + (i - gw) * dx;
+          real_t shear = -1.5 * Omega0 * (xPos - dx / 2);
+          AT(elec, i, j, k, 2) -= shear * A;
+        }
       }
 
   /* magnetic slopes: cpu_v3.cpp:115-163 + slope_mhd.h:636-700 */
@@ -709,49 +740,79 @@ void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, re
         }
       }
 
-  /* fluxes + emf + hydro update: cpu_v3.cpp:372-583 */
+  /* fluxes + emf + hydro update: cpu_v3.cpp:372-583 ; rotating frame: MHDRunGodunov.cpp:2786-3100 */
   for (int k = gw; k < ksz - gw + 1; ++k)
     for (int j = gw; j < jsz - gw + 1; ++j)
       for (int i = gw; i < isz - gw + 1; ++i) {
         real_t ql[8], qr[8], fx[8] = {0}, fy[8] = {0}, fz[8] = {0};
+        real_t xPos = P->xMin + dx / 2 + (i - gw) * dx;
         for (int v = 0; v < 8; ++v) { ql[v] = AT(qm_[0], i - 1, j, k, v); qr[v] = AT(qp_[0], i, j, k, v); }
         riemann_mhd_(P, ql, qr, fx);
         static const int swy[8] = {ID, IP, IV, IU, IW, IB, IA, IC};
         for (int v = 0; v < 8; ++v) { ql[v] = AT(qm_[1], i, j - 1, k, swy[v]); qr[v] = AT(qp_[1], i, j, k, swy[v]); }
         riemann_mhd_(P, ql, qr, fy);
+        if (rot) { /* shear correction of the y flux, :2860-2899 (ql/qr as modified by the solver) */
+          real_t shear_y = -1.5 * Omega0 * xPos;
+          real_t bn_mean = HALF * (ql[IA] + qr[IA]);
+          const real_t *s_ = (shear_y > 0) ? ql : qr;
+          real_t eMag = HALF * (s_[IA] * s_[IA] + s_[IB] * s_[IB] + s_[IC] * s_[IC]);
+          real_t eKin = HALF * (s_[IU] * s_[IU] + s_[IV] * s_[IV] + s_[IW] * s_[IW]);
+          real_t eTot = eKin + eMag + s_[IP] / (P->gamma0 - ONE);
+          fy[ID] = fy[ID] + shear_y * s_[ID];
+          fy[IP] = fy[IP] + shear_y * (eTot + eMag - bn_mean * bn_mean);
+          fy[IU] = fy[IU] + shear_y * s_[ID] * s_[IU];
+          fy[IV] = fy[IV] + shear_y * s_[ID] * s_[IV];
+          fy[IW] = fy[IW] + shear_y * s_[ID] * s_[IW];
+        }
         static const int swz[8] = {ID, IP, IW, IV, IU, IC, IB, IA};
         for (int v = 0; v < 8; ++v) { ql[v] = AT(qm_[2], i, j, k - 1, swz[v]); qr[v] = AT(qp_[2], i, j, k, swz[v]); }
         riemann_mhd_(P, ql, qr, fz);
 
         const int in_j = j < jsz - gw, in_k = k < ksz - gw, in_i = i < isz - gw;
+        if (rot && in_i && in_j && in_k) { /* :2966-2973 */
+          real_t dsx = R(2.0) * Omega0 * dt * AT(Unew, i, j, k, IV) / (ONE + lambda);
+          real_t dsy = -HALF * Omega0 * dt * AT(Unew, i, j, k, IU) / (ONE + lambda);
+          AT(Unew, i, j, k, IU) = AT(Unew, i, j, k, IU) * ratio + dsx;
+          AT(Unew, i, j, k, IV) = AT(Unew, i, j, k, IV) * ratio + dsy;
+        }
         if (i > gw && in_j && in_k) {
-          AT(Unew, i - 1, j, k, ID) -= fx[ID] * dtdx; AT(Unew, i - 1, j, k, IP) -= fx[IP] * dtdx;
-          AT(Unew, i - 1, j, k, IU) -= fx[IU] * dtdx; AT(Unew, i - 1, j, k, IV) -= fx[IV] * dtdx;
+          if (shearBox && i == nx + gw) SF(sfmax, j, k, 0) = fx[ID] * dtdx;
+          else AT(Unew, i - 1, j, k, ID) -= fx[ID] * dtdx;
+          AT(Unew, i - 1, j, k, IP) -= fx[IP] * dtdx;
+          AT(Unew, i - 1, j, k, IU) -= (alpha1 * fx[IU] + alpha2 * fx[IV]) * dtdx;
+          AT(Unew, i - 1, j, k, IV) -= (alpha1 * fx[IV] - 0.25 * alpha2 * fx[IU]) * dtdx;
           AT(Unew, i - 1, j, k, IW) -= fx[IW] * dtdx;
         }
         if (in_i && in_j && in_k) {
-          AT(Unew, i, j, k, ID) += fx[ID] * dtdx; AT(Unew, i, j, k, IP) += fx[IP] * dtdx;
-          AT(Unew, i, j, k, IU) += fx[IU] * dtdx; AT(Unew, i, j, k, IV) += fx[IV] * dtdx;
+          if (shearBox && i == gw) SF(sfmin, j, k, 0) = fx[ID] * dtdx;
+          else AT(Unew, i, j, k, ID) += fx[ID] * dtdx;
+          AT(Unew, i, j, k, IP) += fx[IP] * dtdx;
+          AT(Unew, i, j, k, IU) += (alpha1 * fx[IU] + alpha2 * fx[IV]) * dtdx;
+          AT(Unew, i, j, k, IV) += (alpha1 * fx[IV] - 0.25 * alpha2 * fx[IU]) * dtdx;
           AT(Unew, i, j, k, IW) += fx[IW] * dtdx;
         }
         if (in_i && j > gw && in_k) {
           AT(Unew, i, j - 1, k, ID) -= fy[ID] * dtdy; AT(Unew, i, j - 1, k, IP) -= fy[IP] * dtdy;
-          AT(Unew, i, j - 1, k, IU) -= fy[IV] * dtdy; AT(Unew, i, j - 1, k, IV) -= fy[IU] * dtdy;
+          AT(Unew, i, j - 1, k, IU) -= (alpha1 * fy[IV] + alpha2 * fy[IU]) * dtdy;
+          AT(Unew, i, j - 1, k, IV) -= (alpha1 * fy[IU] - 0.25 * alpha2 * fy[IV]) * dtdy;
           AT(Unew, i, j - 1, k, IW) -= fy[IW] * dtdy;
         }
         if (in_i && in_j && in_k) {
           AT(Unew, i, j, k, ID) += fy[ID] * dtdy; AT(Unew, i, j, k, IP) += fy[IP] * dtdy;
-          AT(Unew, i, j, k, IU) += fy[IV] * dtdy; AT(Unew, i, j, k, IV) += fy[IU] * dtdy;
+          AT(Unew, i, j, k, IU) += (alpha1 * fy[IV] + alpha2 * fy[IU]) * dtdy;
+          AT(Unew, i, j, k, IV) += (alpha1 * fy[IU] - 0.25 * alpha2 * fy[IV]) * dtdy;
           AT(Unew, i, j, k, IW) += fy[IW] * dtdy;
         }
         if (in_i && in_j && k > gw) {
           AT(Unew, i, j, k - 1, ID) -= fz[ID] * dtdz; AT(Unew, i, j, k - 1, IP) -= fz[IP] * dtdz;
-          AT(Unew, i, j, k - 1, IU) -= fz[IW] * dtdz; AT(Unew, i, j, k - 1, IV) -= fz[IV] * dtdz;
+          AT(Unew, i, j, k - 1, IU) -= (alpha1 * fz[IW] + alpha2 * fz[IV]) * dtdz;
+          AT(Unew, i, j, k - 1, IV) -= (alpha1 * fz[IV] - 0.25 * alpha2 * fz[IW]) * dtdz;
           AT(Unew, i, j, k - 1, IW) -= fz[IU] * dtdz;
         }
         if (in_i && in_j && in_k) {
           AT(Unew, i, j, k, ID) += fz[ID] * dtdz; AT(Unew, i, j, k, IP) += fz[IP] * dtdz;
-          AT(Unew, i, j, k, IU) += fz[IW] * dtdz; AT(Unew, i, j, k, IV) += fz[IV] * dtdz;
+          AT(Unew, i, j, k, IU) += (alpha1 * fz[IW] + alpha2 * fz[IV]) * dtdz;
+          AT(Unew, i, j, k, IV) += (alpha1 * fz[IV] - 0.25 * alpha2 * fz[IW]) * dtdz;
           AT(Unew, i, j, k, IW) += fz[IU] * dtdz;
         }
 
@@ -760,18 +821,64 @@ void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, re
           qe[IRT][v] = AT(qe_[IRT][2], i - 1, j - 1, k, v); qe[IRB][v] = AT(qe_[IRB][2], i - 1, j, k, v);
           qe[ILT][v] = AT(qe_[ILT][2], i, j - 1, k, v);     qe[ILB][v] = AT(qe_[ILB][2], i, j, k, v);
         }
-        AT(emf, i, j, k, 0) = orc_compute_emf(P, 2, (const real_t(*)[8])qe, ZERO);
+        real_t emfZ = orc_compute_emf(P, 2, (const real_t(*)[8])qe, xPos);
+        if (!rot || in_k) AT(emf, i, j, k, 0) = emfZ;
         for (int v = 0; v < 8; ++v) { /* emfY :561-569, RB and LT swapped */
           qe[IRT][v] = AT(qe_[IRT][1], i - 1, j, k - 1, v); qe[IRB][v] = AT(qe_[ILT][1], i, j, k - 1, v);
           qe[ILT][v] = AT(qe_[IRB][1], i - 1, j, k, v);     qe[ILB][v] = AT(qe_[ILB][1], i, j, k, v);
         }
-        AT(emf, i, j, k, 1) = orc_compute_emf(P, 1, (const real_t(*)[8])qe, ZERO);
+        real_t emfY = orc_compute_emf(P, 1, (const real_t(*)[8])qe, xPos);
+        if (!rot || in_j) {
+          AT(emf, i, j, k, 1) = emfY;
+          if (shearBox) { /* :3076-3084 */
+            if (i == gw) SF(sfmin, j, k, 1) = emfY;
+            if (i == nx + gw) SF(sfmax, j, k, 1) = emfY;
+          }
+        }
         for (int v = 0; v < 8; ++v) { /* emfX :572-579 */
           qe[IRT][v] = AT(qe_[IRT][0], i, j - 1, k - 1, v); qe[IRB][v] = AT(qe_[IRB][0], i, j - 1, k, v);
           qe[ILT][v] = AT(qe_[ILT][0], i, j, k - 1, v);     qe[ILB][v] = AT(qe_[ILB][0], i, j, k, v);
         }
-        AT(emf, i, j, k, 2) = orc_compute_emf(P, 0, (const real_t(*)[8])qe, ZERO);
+        real_t emfX = orc_compute_emf(P, 0, (const real_t(*)[8])qe, xPos);
+        if (!rot || in_i) AT(emf, i, j, k, 2) = emfX;
       }
+
+  if (shearBox) { /* flux / emf remap and border density update, MHDRunGodunov.cpp:3203-3305 */
+    real_t deltay = 1.5 * Omega0 * (dx * nx) * (totalTime + dt / 2);
+    deltay = FMOD_(deltay, (dy * ny));
+    int jplus = (int)(deltay / dy);
+    real_t epsi = FMOD_(deltay, dy);
+    for (int k = 0; k < ksz; ++k)
+      for (int j = 0; j < jsz; ++j) {
+        int jremap = j - jplus - 1, jremapp1 = jremap + 1;
+        real_t eps = 1.0 - epsi / dy;
+        if (jremap < gw) jremap += ny;
+        if (jremapp1 < gw) jremapp1 += ny;
+        if (j >= gw && j < jsz - gw + 1 && k >= gw && k < ksz - gw + 1) {
+          rmmin[j + (size_t)jsz * k] = SF(sfmin, j, k, 0) + (1.0 - eps) * SF(sfmax, jremap, k, 0) + eps * SF(sfmax, jremapp1, k, 0);
+          rmmin[j + (size_t)jsz * k] *= HALF;
+        }
+        AT(emf, gw, j, k, 1) += (1.0 - eps) * SF(sfmax, jremap, k, 1) + eps * SF(sfmax, jremapp1, k, 1);
+        AT(emf, gw, j, k, 1) *= HALF;
+        jremap = j + jplus; jremapp1 = jremap + 1;
+        eps = epsi / dy;
+        if (jremap > ny + gw - 1) jremap -= ny;
+        if (jremapp1 > ny + gw - 1) jremapp1 -= ny;
+        if (j >= gw && j < jsz - gw + 1 && k >= gw && k < ksz - gw + 1) {
+          rmmax[j + (size_t)jsz * k] = SF(sfmax, j, k, 0) + (1.0 - eps) * SF(sfmin, jremap, k, 0) + eps * SF(sfmin, jremapp1, k, 0);
+          rmmax[j + (size_t)jsz * k] *= HALF;
+        }
+        AT(emf, nx + gw, j, k, 1) += (1.0 - eps) * SF(sfmin, jremap, k, 1) + eps * SF(sfmin, jremapp1, k, 1);
+        AT(emf, nx + gw, j, k, 1) *= HALF;
+      }
+    for (int k = gw; k < ksz - gw + 1; ++k)
+      for (int j = gw; j < jsz - gw + 1; ++j) {
+        AT(Unew, gw, j, k, ID) += rmmin[j + (size_t)jsz * k];
+        AT(Unew, nx + gw - 1, j, k, ID) -= rmmax[j + (size_t)jsz * k];
+        AT(Unew, gw, j, k, ID) = FMAX_(AT(Unew, gw, j, k, ID), P->smallr);
+        AT(Unew, nx + gw - 1, j, k, ID) = FMAX_(AT(Unew, nx + gw - 1, j, k, ID), P->smallr);
+      }
+  }
 
   /* constrained transport: cpu_v3.cpp:600-630 (emf index: 0 = Z, 1 = Y, 2 = X) */
   for (int k = gw; k < ksz - gw + 1; ++k)
@@ -787,5 +894,108 @@ void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, re
         AT(Unew, i, j, k, IC) -= (AT(emf, i, j + 1, k, 2) - AT(emf, i, j, k, 2)) * dtdy;
       }
 #undef TR
+#undef SF
   free(Q); free(elec); free(dA); free(dB); free(dC); free(emf); free(tr);
+  free(sfmin); free(sfmax); free(rmmin); free(rmmax);
+}
+
+void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
+  mhd3d_core(P, Uold, Unew, dt, ZERO, 0);
+}
+
+/* shearing-box ghost remap in x, MHDRunGodunov.cpp:3539-3759 (time-dependent shift deltay) */
+static void make_boundaries_shear(const orc_params *P, real_t *U, real_t dt, real_t totalTime) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth, nx = P->nx, ny = P->ny, nv = P->nbVar;
+  const real_t dy = P->dy, st = P->slope_type;
+  real_t deltay = 1.5 * P->Omega0 * (P->dx * nx) * (totalTime + dt);
+  deltay = FMOD_(deltay, (dy * ny));
+  int jplus = (int)(deltay / dy);
+  real_t epsi = FMOD_(deltay, dy);
+  /* border copies [var][k][j][g] of the first / last gw inner columns (shearBorderUtils.h:46-97) */
+  const size_t nb = (size_t)gw * jsz * ksz * nv;
+  real_t *bmin = calloc(nb, sizeof(real_t)), *bmax = calloc(nb, sizeof(real_t));
+  real_t *smin = calloc(nb, sizeof(real_t)), *smax = calloc(nb, sizeof(real_t));
+#define BD(arr, g, j, k, v) (arr)[(size_t)(g) + (size_t)gw * ((size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(v)))]
+  for (int v = 0; v < nv; ++v)
+    for (int k = 0; k < ksz; ++k)
+      for (int j = 0; j < jsz; ++j)
+        for (int g = 0; g < gw; ++g) {
+          BD(bmin, g, j, k, v) = AT(U, gw + g, j, k, v);
+          BD(bmax, g, j, k, v) = AT(U, isz - 2 * gw + g, j, k, v);
+        }
+  if (st == 1 || st == 2) { /* :3583-3637 */
+    for (int k = 0; k < ksz; ++k)
+      for (int j = 1; j < jsz - 1; ++j)
+        for (int g = 0; g < gw; ++g)
+          for (int v = 0; v < nv; ++v) {
+            if (v == IB) {
+              BD(smin, g, j, k, IB) = BD(bmin, g, j + 1, k, IB) - BD(bmin, g, j, k, IB);
+              BD(smax, g, j, k, IB) = BD(bmax, g, j + 1, k, IB) - BD(bmax, g, j, k, IB);
+            } else {
+              for (int side = 0; side < 2; ++side) {
+                real_t *b = side ? bmax : bmin, *sl = side ? smax : smin;
+                real_t dlft = st * (BD(b, g, j, k, v) - BD(b, g, j - 1, k, v));
+                real_t drgt = st * (BD(b, g, j + 1, k, v) - BD(b, g, j, k, v));
+                real_t dcen = HALF * (dlft + drgt) / st;
+                real_t dsgn = (dcen >= ZERO) ? ONE : -ONE;
+                real_t slop = FMIN_(FABS_(dlft), FABS_(drgt));
+                real_t dlim = slop;
+                if ((dlft * drgt) <= ZERO) dlim = ZERO;
+                BD(sl, g, j, k, v) = dsgn * FMIN_(dlim, FABS_(dcen));
+              }
+            }
+          }
+  }
+  for (int k = 0; k < ksz; ++k)
+    for (int j = gw; j < jsz - gw; ++j) {
+      int jremap = j - jplus - 1, jremapp1 = jremap + 1;
+      real_t eps = 1.0 - epsi / dy;
+      if (jremap < gw) jremap += ny;
+      if (jremapp1 < gw) jremapp1 += ny;
+      real_t lam = HALF * eps * (eps - 1.0);
+      for (int v = 0; v < nv; ++v)
+        for (int g = 0; g < gw; ++g) {
+          if (v == IB) AT(U, g, j, k, IB) = BD(bmax, g, jremap, k, IB) + eps * BD(smax, g, jremap, k, IB);
+          else AT(U, g, j, k, v) = (1.0 - eps) * BD(bmax, g, jremap, k, v) + eps * BD(bmax, g, jremapp1, k, v) +
+                                   lam * (BD(smax, g, jremap, k, v) - BD(smax, g, jremapp1, k, v));
+        }
+      jremap = j + jplus; jremapp1 = jremap + 1;
+      eps = epsi / dy;
+      if (jremap > ny + gw - 1) jremap -= ny;
+      if (jremapp1 > ny + gw - 1) jremapp1 -= ny;
+      lam = HALF * eps * (eps - 1.0);
+      for (int v = 0; v < nv; ++v)
+        for (int g = 0; g < gw; ++g) {
+          const real_t interp = (1.0 - eps) * BD(bmin, g, jremap, k, v) + eps * BD(bmin, g, jremapp1, k, v) +
+                                lam * (BD(smin, g, jremapp1, k, v) - BD(smin, g, jremap, k, v));
+          if (v < 5) AT(U, nx + gw + g, j, k, v) = interp;
+          if (v == IA && g > 0) AT(U, nx + gw + g, j, k, IA) = interp; /* not the first outer ghost face */
+          if (v == IB) AT(U, nx + gw + g, j, k, IB) = BD(bmin, g, jremap, k, IB) + eps * BD(smin, g, jremap, k, IB);
+          if (v == IC) AT(U, nx + gw + g, j, k, IC) = interp;
+        }
+    }
+#undef BD
+  free(bmin); free(bmax); free(smin); free(smax);
+}
+
+void orc_make_boundaries(const orc_params *P, real_t *U, int idim);
+void orc_make_all_boundaries(const orc_params *P, real_t *U);
+
+/* MHDRunGodunov.cpp:3763-3793: Y, shear-X, Z, Y */
+void orc_make_all_boundaries_shear(const orc_params *P, real_t *U, real_t dt, real_t totalTime) {
+  orc_make_boundaries(P, U, 2);
+  make_boundaries_shear(P, U, dt, totalTime);
+  orc_make_boundaries(P, U, 3);
+  orc_make_boundaries(P, U, 2);
+}
+
+/* MHDRunGodunov.cpp:2031-3440 godunov_unsplit_rotating_cpu (3D): no leading ghost fill, ghosts of
+ * UNew are filled at the END of the step */
+void orc_mhd3d_rotating_step(const orc_params *P, real_t *Uold, real_t *Unew, real_t dt, real_t totalTime) {
+  memcpy(Unew, Uold, (size_t)orc_array_len(P) * sizeof(real_t));
+  mhd3d_core(P, Uold, Unew, dt, totalTime, 1);
+  if (P->bc[0] == BC_SHEARINGBOX && P->bc[1] == BC_SHEARINGBOX && P->Omega0 > 0)
+    orc_make_all_boundaries_shear(P, Unew, dt, totalTime);
+  else
+    orc_make_all_boundaries(P, Unew);
 }
