@@ -79,7 +79,12 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
     const T v = f * (Q(IV, i, j - 1, k - 1) + Q(IV, i, j - 1, k) + Q(IV, i, j, k - 1) + v00);
     const T w = f * (Q(IW, i, j - 1, k - 1) + Q(IW, i, j - 1, k) + Q(IW, i, j, k - 1) + w00);
     const T Bm = h * (U(IB, i, j, k - 1) + B), Cm = h * (U(IC, i, j - 1, k) + C);
-    EL(0, i, j, k) = v * Cm - w * Bm;
+    T ex = v * Cm - w * Bm;
+    if (P.Omega0 > T(0)) {  // rotating frame: advection by the background shear, MHDRunGodunov.cpp:2474-2478
+      const T xPos = P.xMin + P.dx * h + (i - P.gw) * P.dx;
+      ex += T(-1.5) * P.Omega0 * xPos * Cm;
+    }
+    EL(0, i, j, k) = ex;
   }
   {  // Ey: average over (i-1..i, k-1..k)
     const T u = f * (Q(IU, i - 1, j, k - 1) + Q(IU, i - 1, j, k) + Q(IU, i, j, k - 1) + u00);
@@ -91,7 +96,12 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
     const T u = f * (Q(IU, i - 1, j - 1, k) + Q(IU, i - 1, j, k) + Q(IU, i, j - 1, k) + u00);
     const T v = f * (Q(IV, i - 1, j - 1, k) + Q(IV, i - 1, j, k) + Q(IV, i, j - 1, k) + v00);
     const T Am = h * (U(IA, i, j - 1, k) + A), Bm = h * (U(IB, i - 1, j, k) + B);
-    EL(2, i, j, k) = u * Bm - v * Am;
+    T ez = u * Bm - v * Am;
+    if (P.Omega0 > T(0)) {  // MHDRunGodunov.cpp:2517-2521 (shear at the x face)
+      const T xFace = P.xMin + P.dx * h + (i - P.gw) * P.dx - P.dx * h;
+      ez -= T(-1.5) * P.Omega0 * xFace * Am;
+    }
+    EL(2, i, j, k) = ez;
   }
 }
 
@@ -255,6 +265,24 @@ __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KPara
   const dev::State<T> R = face_state<T, DIR>(P, W, i, j, k, T(-1));
   T f[8];
   dev::riemann_mhd(P, L, R, f);
+  if (DIR == 1 && P.Omega0 > T(0)) {
+    // rotating frame: upwind advection of the y flux by the background shear
+    // (MHDRunGodunov.cpp:2860-2899; the states are those the Riemann solver has seen: mean normal
+    // field, isothermal pressure when cIso > 0 and the solver is HLLD)
+    const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
+    const T shear_y = T(-1.5) * P.Omega0 * xPos;
+    const T bn = T(0.5) * (L.a + R.a);
+    const dev::State<T>& S = (shear_y > T(0)) ? L : R;
+    const T pS = (P.cIso > T(0) && P.riemannSolver == RS_HLLD) ? S.r * P.cIso * P.cIso : S.p;
+    const T eMag = T(0.5) * (bn * bn + S.b * S.b + S.c * S.c);
+    const T eKin = T(0.5) * (S.u * S.u + S.v * S.v + S.w * S.w);
+    const T eTot = eKin + eMag + pS / (P.gamma0 - T(1));
+    f[ID] += shear_y * S.r;
+    f[IP] += shear_y * (eTot + eMag - bn * bn);
+    f[IU] += shear_y * S.r * S.u;
+    f[IV] += shear_y * S.r * S.v;
+    f[IW] += shear_y * S.r * S.w;
+  }
   // store in physical component order (undo the frame permutation)
   const int c0 = 5 * DIR;
   F(c0 + 0, i, j, k) = f[ID];
@@ -418,6 +446,195 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
     }
   }
   if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4r: update in the rotating frame / shearing box (reference MHDRunGodunov.cpp:2938-3348):
+//   Crank-Nicolson Coriolis rotation of (rho u, rho v), alpha-mixed momentum fluxes, density flux
+//   and emf_y of the two x borders averaged with the y-remapped opposite border (gathered here
+//   instead of the reference's border strips), density floor on the border columns, CT, next dt
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct ShearShift {   // y shift of the opposite x border: deltay = 1.5 Omega0 Lx t, reference :3213-3216
+  int enabled;        // shearing-box boundaries in x
+  int jplus;          // whole cells
+  T frac;             // epsi / dy
+};
+
+template <typename T>
+__device__ __forceinline__ void remapRows(const KParams<T>& P, const ShearShift<T>& sh, int j, bool xmin, int& j0,
+                                          int& j1, T& eps) {
+  const int gw = P.gw, ny = P.ny;
+  if (xmin) {  // inner (xmin) border looks at the xmax border shifted by -jplus-1
+    j0 = j - sh.jplus - 1; j1 = j0 + 1; eps = T(1) - sh.frac;
+    if (j0 < gw) j0 += ny;
+    if (j1 < gw) j1 += ny;
+  } else {
+    j0 = j + sh.jplus; j1 = j0 + 1; eps = sh.frac;
+    if (j0 > ny + gw - 1) j0 -= ny;
+    if (j1 > ny + gw - 1) j1 -= ny;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BX, 3) k_update_rot(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                                      T* __restrict__ Unew, const T* __restrict__ Fp,
+                                                      const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
+                                                      const ShearShift<T> sh, unsigned long long* __restrict__ dMaxInvDt) {
+  const int gw = P.gw;
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  const bool valid = tileCoords(0, P.isize, 0, P.jsize, i, j);
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
+  T invDt = T(0);
+  if (valid) {
+    const UView<T> U = uview(Uold, P);
+    const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+    const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+    const bool inBox = i >= gw && i <= iN && j >= gw && j <= jN && k >= gw && k <= kN;
+    if (!inBox) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = U(v, i, j, k);
+    } else {
+      const View<const T> F = view<const T>(Fp, P, planes, kbase);
+      const View<const T> E = view<const T>(Ep, P, planes, kbase);
+      const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+      const bool inner = i < iN && j < jN && k < kN;
+      T lambda = P.Omega0 * dt;
+      lambda = T(0.25) * lambda * lambda;
+      const T il = dev::rcp(T(1) + lambda);
+      const T ratio = (T(1) - lambda) * il, alpha1 = il, alpha2 = P.Omega0 * dt * il;
+      T un[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
+      if (inner) {
+        const T dsx = T(2) * P.Omega0 * dt * un[IV] * il, dsy = T(-0.5) * P.Omega0 * dt * un[IU] * il;
+        T m[5];
+        m[ID] = un[ID]; m[IP] = un[IP]; m[IW] = un[IW];
+        m[IU] = un[IU] * ratio + dsx;
+        m[IV] = un[IV] * ratio + dsy;
+        const bool bLo = sh.enabled && i == gw, bHi = sh.enabled && i == P.nx + gw - 1;
+        // flux contributions in the reference's order: +x(i) +y(j) +z(k) -x(i+1) -y(j+1) -z(k+1)
+        auto add = [&](int c0, int ii, int jj, int kk, T s, T dtd, bool skipDensity) {
+          const T fd = F(c0 + 0, ii, jj, kk), fp = F(c0 + 1, ii, jj, kk), fu = F(c0 + 2, ii, jj, kk),
+                  fv = F(c0 + 3, ii, jj, kk), fw = F(c0 + 4, ii, jj, kk);
+          if (!skipDensity) m[ID] += s * fd * dtd;
+          m[IP] += s * fp * dtd;
+          m[IU] += s * (alpha1 * fu + alpha2 * fv) * dtd;
+          m[IV] += s * (alpha1 * fv - T(0.25) * alpha2 * fu) * dtd;
+          m[IW] += s * fw * dtd;
+        };
+        add(0, i, j, k, T(1), dtdx, bLo);
+        add(5, i, j, k, T(1), dtdy, false);
+        add(10, i, j, k, T(1), dtdz, false);
+        add(0, i + 1, j, k, T(-1), dtdx, bHi);
+        add(5, i, j + 1, k, T(-1), dtdy, false);
+        add(10, i, j, k + 1, T(-1), dtdz, false);
+        if (bLo || bHi) {  // remapped border density flux, :3237-3297
+          int j0, j1; T eps;
+          remapRows(P, sh, j, bLo, j0, j1, eps);
+          const int iOwn = bLo ? gw : P.nx + gw, iOpp = bLo ? P.nx + gw : gw;
+          const T own = F(0, iOwn, j, k) * dtdx;
+          const T rem = T(0.5) * (own + (T(1) - eps) * (F(0, iOpp, j0, k) * dtdx) + eps * (F(0, iOpp, j1, k) * dtdx));
+          m[ID] = bLo ? m[ID] + rem : m[ID] - rem;
+          m[ID] = dev::mx(m[ID], P.smallr);
+        }
+#pragma unroll
+        for (int v = 0; v < 5; ++v) un[v] = m[v];
+      }
+      // emf_y on the two x borders is the average with the remapped opposite border, :3251-3274
+      auto emfY = [&](int ii, int jj, int kk) -> T {
+        if (ii > iN || jj > jN || kk > kN) return T(0);
+        const T own = E(1, ii, jj, kk);
+        if (sh.enabled && (ii == gw || ii == P.nx + gw)) {
+          int j0, j1; T eps;
+          remapRows(P, sh, jj, ii == gw, j0, j1, eps);
+          const int iOpp = (ii == gw) ? P.nx + gw : gw;
+          return T(0.5) * (own + (T(1) - eps) * E(1, iOpp, j0, kk) + eps * E(1, iOpp, j1, kk));
+        }
+        return own;
+      };
+      auto emf = [&](int c, int ii, int jj, int kk) -> T {
+        return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
+      };
+      auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
+        const T ez = emf(0, ii, jj, kk), ey = emfY(ii, jj, kk), ex = emf(2, ii, jj, kk);
+        if (kk < kN) {
+          bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
+          by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
+        }
+        bx -= (emfY(ii, jj, kk + 1) - ey) * dtdz;
+        by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
+        bz += (emfY(ii + 1, jj, kk) - ey) * dtdx;
+        bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
+      };
+      ct(i, j, k, un[IA], un[IB], un[IC]);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
+      if (inner) {
+        T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
+        d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
+        d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
+        d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
+        T q[8];
+        dev::cons_to_prim_mhd(P, un, bxp, byp, bzp, T(0), q);
+        const T irho = dev::rcp(q[ID]);
+        const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+        const T bb = a2 + b2 + c2;
+        const T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+        const T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]) +
+                     T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+        const T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+        invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+      }
+    }
+  }
+  if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shearing-box ghost cells in x (reference MHDRunGodunov.cpp:3539-3759): every x-ghost cell of an
+// inner row is interpolated from the opposite border's inner columns, shifted along y by
+// deltay(t+dt), second order with limited y slopes (B_y: first-order difference slope)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_shear_ghosts(const __grid_constant__ KParams<T> P, T* __restrict__ U, const ShearShift<T> sh) {
+  const int gw = P.gw, nx = P.nx;
+  // thread = (ghost slot g in [0, 2gw), inner row j, plane k)
+  const int g = threadIdx.x % (2 * gw);
+  const int j = gw + blockIdx.x * (blockDim.x / (2 * gw)) + threadIdx.x / (2 * gw);
+  const int k = blockIdx.y;
+  if (threadIdx.x >= (blockDim.x / (2 * gw)) * 2 * gw || j >= P.jsize - gw) return;
+  const bool lo = g < gw;
+  const int gg = lo ? g : g - gw;
+  const int iDst = lo ? gg : nx + gw + gg;
+  const int iSrc = lo ? P.isize - 2 * gw + gg : gw + gg;   // opposite border's inner column
+  int j0, j1; T eps;
+  remapRows(P, sh, j, lo, j0, j1, eps);
+  const T lam = T(0.5) * eps * (eps - T(1));
+  const T st = P.slope_type;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  auto at = [&](int v, int ii, int jj) -> T& { return U[(size_t)v * comp + (size_t)k * plane + (size_t)jj * P.isize + ii]; };
+  auto slope = [&](int v, int jj) -> T {  // limited y slope of the border column, :3606-3616
+    if (st != T(1) && st != T(2)) return T(0);
+    const T dlft = st * (at(v, iSrc, jj) - at(v, iSrc, jj - 1)), drgt = st * (at(v, iSrc, jj + 1) - at(v, iSrc, jj));
+    const T dcen = T(0.5) * (dlft + drgt) / st;
+    const T dsgn = (dcen >= T(0)) ? T(1) : T(-1);
+    T dlim = dev::mn(dev::ab(dlft), dev::ab(drgt));
+    if (dlft * drgt <= T(0)) dlim = T(0);
+    return dsgn * dev::mn(dlim, dev::ab(dcen));
+  };
+  for (int v = 0; v < 8; ++v) {
+    if (v == IB) {
+      const T sl = (st == T(1) || st == T(2)) ? at(IB, iSrc, j0 + 1) - at(IB, iSrc, j0) : T(0);
+      at(IB, iDst, j) = at(IB, iSrc, j0) + eps * sl;
+      continue;
+    }
+    if (!lo && v == IA && gg == 0) continue;  // the first outer ghost face keeps its CT value
+    const T s0 = slope(v, j0), s1 = slope(v, j1);
+    const T d = lo ? (s0 - s1) : (s1 - s0);
+    at(v, iDst, j) = (T(1) - eps) * at(v, iSrc, j0) + eps * at(v, iSrc, j1) + lam * d;
+  }
 }
 
 template <typename T>
@@ -651,6 +868,25 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
 #define RG_L(M) k_update<T, M><<<g, blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
   RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
 #undef RG_L
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::updateRotating(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
+                                   int shearEnabled, int jplus, T frac, unsigned long long* d, cudaStream_t s) {
+  if (k1 <= k0) return;
+  ShearShift<T> sh{shearEnabled, jplus, frac};
+  k_update_rot<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes,
+                                                                              sc.kbase, k0, dt, sh, d);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, cudaStream_t s) {
+  ShearShift<T> sh{1, jplus, frac};
+  const int per = 2 * P.gw, rows = 128 / per;
+  dim3 grid((P.ny + rows - 1) / rows, P.ksize, 1);
+  k_shear_ghosts<T><<<grid, 128, 0, s>>>(P, U, sh);
   ++g_launches;
 }
 

@@ -185,7 +185,9 @@ class RunImpl final : public Run {
 
   // reference HydroRunBase::make_all_boundaries (HydroRunBase.cpp:2322-2342): X, Y, then Z
   void make_all_boundaries(int which) override {
-    fillGhosts(which, 0, kp_.ksize);
+    // reference start(): make_all_boundaries_shear(U, 0, 0) when the shearing box is enabled
+    if (shearingBox()) fillGhostsShear(which, T(0));
+    else fillGhosts(which, 0, kp_.ksize);
     ghostsValid_[which] = true;
   }
 
@@ -222,8 +224,12 @@ class RunImpl final : public Run {
   void godunov_unsplit(int nStep, double dt) override {
     const int src = (nStep % 2 == 0) ? 0 : 1, dst = 1 - src;
     RG_CUDA(cudaEventRecord(ev0_, stream_));
-    if (!ghostsValid_[src]) make_all_boundaries(src);
-    if (rp_.mhdEnabled && rp_.dim == 3 && !(kp_.Omega0 > T(0))) {
+    const bool rotating = rp_.mhdEnabled && kp_.Omega0 > T(0);
+    // the rotating-frame step fills the ghosts of UNew at its END (reference MHDRunGodunov.cpp:3429-3437)
+    if (!rotating && !ghostsValid_[src]) make_all_boundaries(src);
+    if (rotating && rp_.dim == 3) {
+      stepMhd3dRotating(src, dst, static_cast<T>(dt));
+    } else if (rp_.mhdEnabled && rp_.dim == 3) {
       stepMhd3d(src, dst, static_cast<T>(dt));
     } else if (!rp_.mhdEnabled && rp_.dim == 3) {
       stepHydro3d(src, dst, static_cast<T>(dt));
@@ -239,6 +245,7 @@ class RunImpl final : public Run {
   // reference MHDRunGodunov::oneStepIntegration (MHDRunGodunov.cpp:4077-4089)
   void oneStepIntegration(int& nStep, double& t, double& dt) override {
     dt = compute_dt(nStep % 2);
+    totalTime = t;  // the shearing-box remap depends on the time at the start of the step
     godunov_unsplit(nStep, dt);
     nStep++;
     // the reference accumulates time in real_t
@@ -593,6 +600,80 @@ class RunImpl final : public Run {
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
+  }
+
+  bool shearingBox() const {
+    return rp_.mhdEnabled && rp_.dim == 3 && rp_.bc[0] == BC_SHEARINGBOX && rp_.bc[1] == BC_SHEARINGBOX &&
+           kp_.Omega0 > T(0);
+  }
+  // y shift of the opposite x border at time t: whole cells and fraction of dy (MHDRunGodunov.cpp:3213-3216)
+  void shearShift(T t, int* jplus, T* frac) const {
+    T deltay = T(1.5) * kp_.Omega0 * (kp_.dx * rp_.nx) * t;
+    deltay = std::fmod(deltay, kp_.dy * rp_.ny);
+    *jplus = static_cast<int>(deltay / kp_.dy);
+    *frac = std::fmod(deltay, kp_.dy) / kp_.dy;
+  }
+  // reference make_all_boundaries_shear (MHDRunGodunov.cpp:3763-3793): Y, shear-X, Z, Y at time t + dt
+  void fillGhostsShear(int b, T dt) {
+    T* U = dU_[b];
+    int jplus; T frac;
+    shearShift(static_cast<T>(totalTime) + dt, &jplus, &frac);
+    phase(PH_BOUNDARY, [&] {
+      MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, kp_.ksize, stream_);
+      MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, stream_);
+    });
+    if (nranks_ == 1) {
+      phase(PH_BOUNDARY, [&] {
+        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
+      });
+    } else {
+      bool hasLo, hasHi;
+      zNeighbours(&hasLo, &hasHi);
+      if (!hasLo || !hasHi)
+        phase(PH_BOUNDARY, [&] {
+          MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
+        });
+      phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi, stream_); });
+    }
+    phase(PH_BOUNDARY, [&] {
+      MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, kp_.ksize, stream_);
+    });
+  }
+
+  // ---- 3D MHD step in the rotating frame (Omega0 > 0), with or without shearing-box boundaries:
+  //      reference godunov_unsplit_rotating_cpu / _gpu (MHDRunGodunov.cpp:1511, 2031)
+  void stepMhd3dRotating(int src, int dst, T dt) {
+    ensureScratchMhd3d();
+    const T* Uold = dU_[src];
+    T* Unew = dU_[dst];
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    unsigned long long* slots = dMax_ + (size_t)dst * MAX_SLOTS;
+    RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
+    const int shear = shearingBox() ? 1 : 0;
+    int jplus = 0; T frac = T(0);
+    if (shear) shearShift(static_cast<T>(totalTime) + dt / 2, &jplus, &frac);
+    phase(PH_COPY, [&] {
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
+      MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN + 1, kp_.ksize, stream_);
+    });
+    for (int ka = gw; ka <= kN; ka += chunkPlanes_) {
+      const int kb = std::min(ka + chunkPlanes_, kN + 1), fhi = std::min(kb, kN);
+      MhdScratch<T> sc = sc_;
+      sc.kbase = ka - 2;
+      phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
+      phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
+      phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
+      phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
+      phase(PH_UPDATE, [&] {
+        MhdKernels<T>::updateRotating(kp_, Uold, Unew, sc, ka, kb, dt, shear, jplus, frac, slots, stream_);
+      });
+    }
+    // ghosts of the NEW state, at the end of the step
+    if (shear) fillGhostsShear(dst, dt);
+    else fillGhosts(dst, 0, kp_.ksize);
+    ghostsValid_[dst] = true;
+    dtCached_[dst] = true;
   }
 
   // ---- 2D MHD step: reference godunov_unsplit_cpu + _v1 (mhd_godunov_unsplit_cpu_v1.cpp:36-243)
