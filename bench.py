@@ -30,8 +30,11 @@ METRIC = "Mcell-updates/s (FP64) on 3D MHD Godunov"
 UNIT = "Mcell-updates/s"
 B_ALG_CELL = 128.0        # compulsory bytes per MHD FP64 cell update: read U once, write U once
 # algorithmic bytes per launch unit of each kernel family (DESIGN.md "kernels"): reals read + written once
-B_ALG_KERNEL = {"prim": (8 + 8) * 8.0, "trace": (8 + 3 + 47) * 8.0, "flux": (16 + 5) * 8.0 * 3,
-                "emf": (26 + 1) * 8.0 * 3, "update": (8 + 15 + 3 + 8) * 8.0}
+# prim = k_prim (8r+8w) + k_elec (6r+3w); trace: Q 8 + face B 3 + E 3 read, W 38 written; flux: 15 W
+# components read + 5 written per direction; emf: 22 read + 1 written per direction; update: U 8 +
+# F 15 + E 3 read, U 8 written
+B_ALG_KERNEL = {"prim": (8 + 8 + 6 + 3) * 8.0, "trace": (8 + 3 + 3 + 38) * 8.0, "flux": (15 + 5) * 8.0 * 3,
+                "emf": (22 + 1) * 8.0 * 3, "update": (8 + 15 + 3 + 8) * 8.0}
 
 
 def base_ini():
@@ -173,7 +176,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--size", type=int, default=256, help="cells per direction per GPU")
-    ap.add_argument("--ref-size", type=int, default=48, help="grid of each CPU replica of the reference arm")
+    ap.add_argument("--ref-size", type=int, default=64, help="grid of each CPU replica of the reference arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -301,9 +304,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cv, kind, cwall = run_reference_cpu(args.ref_size, 6, cores)
+            cv, kind, cwall = run_reference_cpu(args.ref_size, 16, cores)
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": "%d single-thread replicas of the same problem at %d^3, 6 steps (%.0f s)" % (cores, args.ref_size, cwall)}
+                                    "sample": "%d single-thread replicas of the same problem at %d^3, 16 steps (%.0f s)" % (cores, args.ref_size, cwall)}
         print(json.dumps(line))
     run.close()
     if world > 1:

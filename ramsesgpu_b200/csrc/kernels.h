@@ -11,9 +11,10 @@
 namespace rg {
 
 // Number of components of the "traced state" W written by the trace kernel per cell
-// ("HBM layout"): 8 cell-centred + 6 face B (all advanced by dt/2) + 21 half
-// slopes of the cell-centred variables + 12 half slopes of the face fields.
-constexpr int NW_MHD = 47;
+// ("HBM layout"): 8 cell-centred + 3 low-face B (all advanced by dt/2) + 21 half
+// slopes of the cell-centred variables + 6 half slopes of the low-face fields (the high-face values
+// of a cell are the low-face values of its +1 neighbour, bit for bit).
+constexpr int NW_MHD = 38;
 
 // Scratch for one z-chunk of the 3D MHD step.  All arrays are SoA [component][kk][j][i] with
 // kk = k - kbase and `planes` allocated planes.

@@ -29,14 +29,16 @@ int g_fluxMinB = 5, g_emfMinB = 4, g_traceMinB = 4, g_updateMinB = 4;
 // W component ids
 enum {
   W_R = 0, W_P, W_U, W_V, W_W, W_A, W_B, W_C,            // cell centred, advanced by dt/2
-  W_AL, W_AR, W_BL, W_BR, W_CL, W_CR,                    // face fields, advanced by dt/2
+  W_AL, W_BL, W_CL,                                      // LOW-face fields, advanced by dt/2
   W_DRX, W_DPX, W_DUX, W_DVX, W_DWX, W_DBX, W_DCX,       // half slopes along x
   W_DRY, W_DPY, W_DUY, W_DVY, W_DWY, W_DAY, W_DCY,       // half slopes along y
   W_DRZ, W_DPZ, W_DUZ, W_DVZ, W_DWZ, W_DAZ, W_DBZ,       // half slopes along z
-  W_DALY, W_DALZ, W_DBLX, W_DBLZ, W_DCLX, W_DCLY,        // half slopes of the low-face fields
-  W_DARY, W_DARZ, W_DBRX, W_DBRZ, W_DCRX, W_DCRY         // half slopes of the high-face fields
+  W_DALY, W_DALZ, W_DBLX, W_DBLZ, W_DCLX, W_DCLY         // half slopes of the low-face fields
 };
-static_assert(W_DCRY + 1 == NW_MHD, "W layout");
+// The HIGH-face field of a cell and its slopes are, bit for bit, the LOW-face values of the +1
+// neighbour (same face, same edge electric fields, same limiter inputs), so consumers read them
+// there and W carries 38 components instead of 47.
+static_assert(W_DCLY + 1 == NW_MHD, "W layout");
 
 // ------------------------------------------------------------------------------------------------
 // K0: conservative -> primitive (reference MHDRunGodunov.cpp:538-560 + constoprim.h:137-199)
@@ -140,26 +142,19 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   }
   // face fields and their transverse HALF slopes (slope type capped at 2, slope_mhd.h:636)
   const T xst = dev::mn(st, T(2));
-  T AL = U(IA, i, j, k), AR = U(IA, i + 1, j, k);
-  T BL = U(IB, i, j, k), BR = U(IB, i, j + 1, k);
-  T CL = U(IC, i, j, k), CR = U(IC, i, j, k + 1);
+  T AL = U(IA, i, j, k), BL = U(IB, i, j, k), CL = U(IC, i, j, k);
+  const T AR = U(IA, i + 1, j, k), BR = U(IB, i, j + 1, k), CR = U(IC, i, j, k + 1);
   const T dALy = h * dev::limited_slope(xst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
   const T dALz = h * dev::limited_slope(xst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
-  const T dARy = h * dev::limited_slope(xst, U(IA, i + 1, j - 1, k), AR, U(IA, i + 1, j + 1, k));
-  const T dARz = h * dev::limited_slope(xst, U(IA, i + 1, j, k - 1), AR, U(IA, i + 1, j, k + 1));
   const T dBLx = h * dev::limited_slope(xst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
   const T dBLz = h * dev::limited_slope(xst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
-  const T dBRx = h * dev::limited_slope(xst, U(IB, i - 1, j + 1, k), BR, U(IB, i + 1, j + 1, k));
-  const T dBRz = h * dev::limited_slope(xst, U(IB, i, j + 1, k - 1), BR, U(IB, i, j + 1, k + 1));
   const T dCLx = h * dev::limited_slope(xst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
   const T dCLy = h * dev::limited_slope(xst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
-  const T dCRx = h * dev::limited_slope(xst, U(IC, i - 1, j, k + 1), CR, U(IC, i + 1, j, k + 1));
-  const T dCRy = h * dev::limited_slope(xst, U(IC, i, j - 1, k + 1), CR, U(IC, i, j + 1, k + 1));
 
   // edge-centred electric fields at the 12 edges of the cell, from the elec kernel
-  const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k), ERR = EL(0, i, j + 1, k + 1);
-  const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k), FRR = EL(1, i + 1, j, k + 1);
-  const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k), GRR = EL(2, i + 1, j + 1, k);
+  const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k);
+  const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k);
+  const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k);
 
   // half-step source terms (trace_mhd.h:1985-2011)
   T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
@@ -191,17 +186,13 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
     sC0 -= shear * dCy * dtdy;
   }
   AL += (GLR - GLL) * dtdy * h - (FLR - FLL) * dtdz * h;
-  AR += (GRR - GRL) * dtdy * h - (FRR - FRL) * dtdz * h;
   BL += -(GRL - GLL) * dtdx * h + (ELR - ELL) * dtdz * h;
-  BR += -(GRR - GLR) * dtdx * h + (ERR - ERL) * dtdz * h;
   CL += (FRL - FLL) * dtdx * h - (ERL - ELL) * dtdy * h;
-  CR += (FRR - FLR) * dtdx * h - (ERR - ELR) * dtdy * h;
 
   W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
   W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
   W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
-  W(W_AL, i, j, k) = AL; W(W_AR, i, j, k) = AR; W(W_BL, i, j, k) = BL;
-  W(W_BR, i, j, k) = BR; W(W_CL, i, j, k) = CL; W(W_CR, i, j, k) = CR;
+  W(W_AL, i, j, k) = AL; W(W_BL, i, j, k) = BL; W(W_CL, i, j, k) = CL;
   W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
   W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
   W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
@@ -209,8 +200,7 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
   W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
   W(W_DALY, i, j, k) = dALy; W(W_DALZ, i, j, k) = dALz; W(W_DBLX, i, j, k) = dBLx; W(W_DBLZ, i, j, k) = dBLz;
-  W(W_DCLX, i, j, k) = dCLx; W(W_DCLY, i, j, k) = dCLy; W(W_DARY, i, j, k) = dARy; W(W_DARZ, i, j, k) = dARz;
-  W(W_DBRX, i, j, k) = dBRx; W(W_DBRZ, i, j, k) = dBRz; W(W_DCRX, i, j, k) = dCRx; W(W_DCRY, i, j, k) = dCRy;
+  W(W_DCLX, i, j, k) = dCLx; W(W_DCLY, i, j, k) = dCLy;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,17 +220,17 @@ __device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const V
   const T w = W(W_W, i, j, k) + sgn * W(S + 4, i, j, k);
   if (DIR == 0) {
     s.u = u; s.v = v; s.w = w;
-    s.a = (sgn > T(0)) ? W(W_AR, i, j, k) : W(W_AL, i, j, k);
+    s.a = W(W_AL, (sgn > T(0)) ? i + 1 : i, j, k);
     s.b = W(W_B, i, j, k) + sgn * W(W_DBX, i, j, k);
     s.c = W(W_C, i, j, k) + sgn * W(W_DCX, i, j, k);
   } else if (DIR == 1) {  // swap (u,v) and (a,b)
     s.u = v; s.v = u; s.w = w;
-    s.a = (sgn > T(0)) ? W(W_BR, i, j, k) : W(W_BL, i, j, k);
+    s.a = W(W_BL, i, (sgn > T(0)) ? j + 1 : j, k);
     s.b = W(W_A, i, j, k) + sgn * W(W_DAY, i, j, k);
     s.c = W(W_C, i, j, k) + sgn * W(W_DCY, i, j, k);
   } else {  // swap (u,w) and (a,c)
     s.u = w; s.v = v; s.w = u;
-    s.a = (sgn > T(0)) ? W(W_CR, i, j, k) : W(W_CL, i, j, k);
+    s.a = W(W_CL, i, j, (sgn > T(0)) ? k + 1 : k);
     s.b = W(W_B, i, j, k) + sgn * W(W_DBZ, i, j, k);
     s.c = W(W_A, i, j, k) + sgn * W(W_DAZ, i, j, k);
   }
@@ -311,17 +301,17 @@ __device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const 
   const T Wv = W(W_W, i, j, k) + (s1 * W(S1 + 4, i, j, k) + s2 * W(S2 + 4, i, j, k));
   T A, B, C;
   if (EDIR == 2) {  // (x,y): A from the x-face on side s1 with its y slope, B from the y-face on side s2 with its x slope
-    A = (s1 > T(0)) ? W(W_AR, i, j, k) + s2 * W(W_DARY, i, j, k) : W(W_AL, i, j, k) + s2 * W(W_DALY, i, j, k);
-    B = (s2 > T(0)) ? W(W_BR, i, j, k) + s1 * W(W_DBRX, i, j, k) : W(W_BL, i, j, k) + s1 * W(W_DBLX, i, j, k);
+    { const int ia = (s1 > T(0)) ? i + 1 : i; A = W(W_AL, ia, j, k) + s2 * W(W_DALY, ia, j, k); }
+    { const int jb = (s2 > T(0)) ? j + 1 : j; B = W(W_BL, i, jb, k) + s1 * W(W_DBLX, i, jb, k); }
     C = W(W_C, i, j, k) + (s1 * W(W_DCX, i, j, k) + s2 * W(W_DCY, i, j, k));
   } else if (EDIR == 1) {  // (x,z)
-    A = (s1 > T(0)) ? W(W_AR, i, j, k) + s2 * W(W_DARZ, i, j, k) : W(W_AL, i, j, k) + s2 * W(W_DALZ, i, j, k);
+    { const int ia = (s1 > T(0)) ? i + 1 : i; A = W(W_AL, ia, j, k) + s2 * W(W_DALZ, ia, j, k); }
     B = W(W_B, i, j, k) + (s1 * W(W_DBX, i, j, k) + s2 * W(W_DBZ, i, j, k));
-    C = (s2 > T(0)) ? W(W_CR, i, j, k) + s1 * W(W_DCRX, i, j, k) : W(W_CL, i, j, k) + s1 * W(W_DCLX, i, j, k);
+    { const int kc = (s2 > T(0)) ? k + 1 : k; C = W(W_CL, i, j, kc) + s1 * W(W_DCLX, i, j, kc); }
   } else {  // (y,z)
     A = W(W_A, i, j, k) + (s1 * W(W_DAY, i, j, k) + s2 * W(W_DAZ, i, j, k));
-    B = (s1 > T(0)) ? W(W_BR, i, j, k) + s2 * W(W_DBRZ, i, j, k) : W(W_BL, i, j, k) + s2 * W(W_DBLZ, i, j, k);
-    C = (s2 > T(0)) ? W(W_CR, i, j, k) + s1 * W(W_DCRY, i, j, k) : W(W_CL, i, j, k) + s1 * W(W_DCLY, i, j, k);
+    { const int jb = (s1 > T(0)) ? j + 1 : j; B = W(W_BL, i, jb, k) + s2 * W(W_DBLZ, i, jb, k); }
+    { const int kc = (s2 > T(0)) ? k + 1 : k; C = W(W_CL, i, j, kc) + s1 * W(W_DCLY, i, j, kc); }
   }
   dev::Corner<T> c;
   c.r = r; c.p = p;
