@@ -24,7 +24,7 @@ int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 namespace {
 
 // occupancy knobs (minimum resident blocks per SM the kernel is compiled for), see setTuning()
-int g_fluxMinB = 5, g_emfMinB = 4, g_traceMinB = 4, g_updateMinB = 4;
+int g_fluxMinB = 5, g_emfMinB = 4, g_traceMinB = 3, g_updateMinB = 4;
 
 // W component ids
 enum {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
 // K1: slopes + edge electric fields + face-B slopes + half-step trace -> W
 //     (reference cpu_v3.cpp:36-361, slope_mhd.h:436-502/598-704, trace_mhd.h:1854-2030)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MINB>
+template <typename T, int MINB, bool FAST>
 __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                                     const T* __restrict__ Qp, const T* __restrict__ ELp,
                                                     T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
@@ -123,33 +123,29 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
   const View<const T> EL = view<const T>(ELp, P, planes, kbase);
   const View<T> W = view(Wp, P, planes, kbase);
-  const T st = P.slope_type;
-  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
   const T h = T(0.5);
+  const T hst = h * P.slope_type;  // slope_type 0 gives zero slopes through hst = 0
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
 
   // cell-centred state and its limited HALF slopes
   T q[8], dx_[8], dy_[8], dz_[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v) {
     q[v] = Q(v, i, j, k);
-    if (st == T(0)) {
-      dx_[v] = dy_[v] = dz_[v] = T(0);
-    } else {
-      dx_[v] = h * dev::limited_slope(st, Q(v, i - 1, j, k), q[v], Q(v, i + 1, j, k));
-      dy_[v] = h * dev::limited_slope(st, Q(v, i, j - 1, k), q[v], Q(v, i, j + 1, k));
-      dz_[v] = h * dev::limited_slope(st, Q(v, i, j, k - 1), q[v], Q(v, i, j, k + 1));
-    }
+    dx_[v] = dev::half_slope(hst, Q(v, i - 1, j, k), q[v], Q(v, i + 1, j, k));
+    dy_[v] = dev::half_slope(hst, Q(v, i, j - 1, k), q[v], Q(v, i, j + 1, k));
+    dz_[v] = dev::half_slope(hst, Q(v, i, j, k - 1), q[v], Q(v, i, j, k + 1));
   }
   // face fields and their transverse HALF slopes (slope type capped at 2, slope_mhd.h:636)
-  const T xst = dev::mn(st, T(2));
+  const T hxst = h * dev::mn(P.slope_type, T(2));
   T AL = U(IA, i, j, k), BL = U(IB, i, j, k), CL = U(IC, i, j, k);
   const T AR = U(IA, i + 1, j, k), BR = U(IB, i, j + 1, k), CR = U(IC, i, j, k + 1);
-  const T dALy = h * dev::limited_slope(xst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
-  const T dALz = h * dev::limited_slope(xst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
-  const T dBLx = h * dev::limited_slope(xst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
-  const T dBLz = h * dev::limited_slope(xst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
-  const T dCLx = h * dev::limited_slope(xst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
-  const T dCLy = h * dev::limited_slope(xst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
+  const T dALy = dev::half_slope(hxst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
+  const T dALz = dev::half_slope(hxst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
+  const T dBLx = dev::half_slope(hxst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
+  const T dBLz = dev::half_slope(hxst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
+  const T dCLx = dev::half_slope(hxst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
+  const T dCLy = dev::half_slope(hxst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
 
   // edge-centred electric fields at the 12 edges of the cell, from the elec kernel
   const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k);
@@ -173,7 +169,7 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   T sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
   T sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
   T sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
-  if (P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003
+  if (!FAST && P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003
     const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
     const T shear = T(-1.5) * P.Omega0 * xPos;
     sr0 -= shear * dry * dtdy;
@@ -207,9 +203,8 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
 // K2: HLLD (or HLL/LLF) fluxes at the three low faces (reference cpu_v3.cpp:397-465, trace_mhd.h:2032-2102)
 //     face state = W cell-centred value +/- half slope along the normal, floors on rho and p
 // ------------------------------------------------------------------------------------------------
-template <typename T, int DIR>
-__device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const View<const T>& W, int i, int j, int k,
-                                                    T sgn) {
+template <typename T, int DIR, typename WV>
+__device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const WV& W, int i, int j, int k, T sgn) {
   // sgn = +1 : state at the HIGH face of cell (qm), -1 : at the LOW face (qp)
   constexpr int S = (DIR == 0) ? W_DRX : (DIR == 1) ? W_DRY : W_DRZ;  // first slope component
   dev::State<T> s;
@@ -237,7 +232,7 @@ __device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const V
   return s;
 }
 
-template <typename T, int DIR, int MINB>
+template <typename T, int DIR, int MINB, bool FAST>
 __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                              T* __restrict__ Fp, int planes, int kbase, int k0) {
   const int gw = P.gw;
@@ -254,8 +249,8 @@ __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KPara
   const dev::State<T> L = face_state<T, DIR>(P, W, il, jl, kl, T(1));
   const dev::State<T> R = face_state<T, DIR>(P, W, i, j, k, T(-1));
   T f[8];
-  dev::riemann_mhd(P, L, R, f);
-  if (DIR == 1 && P.Omega0 > T(0)) {
+  dev::riemann_mhd<FAST>(P, L, R, f);
+  if (!FAST && DIR == 1 && P.Omega0 > T(0)) {
     // rotating frame: upwind advection of the y flux by the background shear
     // (MHDRunGodunov.cpp:2860-2899; the states are those the Riemann solver has seen: mean normal
     // field, isothermal pressure when cIso > 0 and the solver is HLLD)
@@ -289,9 +284,9 @@ __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KPara
 // edge state of cell (i,j,k) for edge direction EDIR, signs (s1, s2) along the two transverse
 // directions (d1,d2) = (x,y) for Z, (x,z) for Y, (y,z) for X; returned in the EDGE frame
 //   Z: u<-U v<-V w<-W a<-A b<-B c<-C ; Y: u<-W v<-U w<-V a<-C b<-A c<-B ; X: u<-V v<-W w<-U a<-B b<-C c<-A
-template <typename T, int EDIR>
-__device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const View<const T>& W, int i, int j, int k,
-                                                     T s1, T s2) {
+template <typename T, int EDIR, typename WV>
+__device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const WV& W, int i, int j, int k, T s1,
+                                                     T s2) {
   constexpr int S1 = (EDIR == 0) ? W_DRY : W_DRX;  // slopes along d1
   constexpr int S2 = (EDIR == 2) ? W_DRY : W_DRZ;  // slopes along d2
   const T r = dev::mx(P.smallr, W(W_R, i, j, k) + (s1 * W(S1 + 0, i, j, k) + s2 * W(S2 + 0, i, j, k)));
@@ -321,7 +316,7 @@ __device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const 
   return c;
 }
 
-template <typename T, int EDIR, int MINB>
+template <typename T, int EDIR, int MINB, bool FAST>
 __global__ void __launch_bounds__(BX, MINB) k_emf(const __grid_constant__ KParams<T> P, const T* __restrict__ Wp,
                                             T* __restrict__ Ep, int planes, int kbase, int k0) {
   const int gw = P.gw;
@@ -349,14 +344,83 @@ __global__ void __launch_bounds__(BX, MINB) k_emf(const __grid_constant__ KParam
     LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
   }
   // reference component order: I_EMFZ = 0, I_EMFY = 1, I_EMFX = 2
-  E(2 - EDIR, i, j, k) = dev::compute_emf(P, RT, RB, LT, LB, EDIR, xPos);
+  E(2 - EDIR, i, j, k) = dev::compute_emf<FAST>(P, RT, RB, LT, LB, EDIR, xPos);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K4: conservative update + constrained transport + inverse-dt reduction of the NEW state
 //     (reference cpu_v3.cpp:475-533 and :600-630; dt: MHDRunBase.cpp:141-250)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MINB>
+// One cell of the update box (gw <= i <= iN etc.).  FV(c, i, j, k) / EV(c, i, j, k) give the face
+// fluxes and corner emfs (global scratch arrays or the shared-memory tile of the fused kernel).
+// Returns the inverse time step of the NEW state (0 outside the inner cells).
+template <bool FAST, typename T, typename FV, typename EV>
+__device__ __forceinline__ T update_cell(const KParams<T>& P, const UView<T>& U, T* __restrict__ Unew, const FV& F,
+                                         const EV& E, int i, int j, int k, T dt) {
+  const int gw = P.gw;
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;  // first upper ghost index
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  const bool inner = i < iN && j < jN && k < kN;
+  T invDt = T(0);
+  T un[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
+  if (inner) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      // same summation order as the reference's serial scatter
+      T s = un[v];
+      s += F(v, i, j, k) * dtdx;
+      s += F(5 + v, i, j, k) * dtdy;
+      s += F(10 + v, i, j, k) * dtdz;
+      s -= F(v, i + 1, j, k) * dtdx;
+      s -= F(5 + v, i, j + 1, k) * dtdy;
+      s -= F(10 + v, i, j, k + 1) * dtdz;
+      un[v] = s;
+    }
+  }
+  // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,
+  // exactly like the reference's zero-initialised h_emf
+  auto emf = [&](int c, int ii, int jj, int kk) -> T {
+    return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
+  };
+  auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
+    const T ez = emf(0, ii, jj, kk), ey = emf(1, ii, jj, kk), ex = emf(2, ii, jj, kk);
+    if (kk < kN) {
+      bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
+      by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
+    }
+    bx -= (emf(1, ii, jj, kk + 1) - ey) * dtdz;
+    by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
+    bz += (emf(1, ii + 1, jj, kk) - ey) * dtdx;
+    bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
+  };
+  ct(i, j, k, un[IA], un[IB], un[IC]);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
+
+  if (inner) {  // inverse dt of the new state: needs the new B on the three upper faces
+    T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
+    d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
+    d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
+    d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
+    T q[8];
+    dev::cons_to_prim_mhd<FAST>(P, un, bxp, byp, bzp, T(0), q);
+    const T irho = dev::rcp(q[ID]);
+    const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+    const T bb = a2 + b2 + c2;
+    T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+    T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
+    T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+    if (!FAST && P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+    invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+  }
+  return invDt;
+}
+
+template <typename T, int MINB, bool FAST>
 __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
                                                T* __restrict__ Unew, const T* __restrict__ Fp,
                                                const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
@@ -369,70 +433,16 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
   T invDt = T(0);
   if (valid) {
     const UView<T> U = uview(Uold, P);
-    const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
-    const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
     const bool inBox = i >= gw && i <= iN && j >= gw && j <= jN && k >= gw && k <= kN;
     if (!inBox) {
+      const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+      const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
 #pragma unroll
       for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = U(v, i, j, k);
     } else {
       const View<const T> F = view<const T>(Fp, P, planes, kbase);
       const View<const T> E = view<const T>(Ep, P, planes, kbase);
-      const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
-      const bool inner = i < iN && j < jN && k < kN;
-      T un[8];
-#pragma unroll
-      for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
-      if (inner) {
-#pragma unroll
-        for (int v = 0; v < 5; ++v) {
-          // same summation order as the reference's serial scatter
-          T s = un[v];
-          s += F(v, i, j, k) * dtdx;
-          s += F(5 + v, i, j, k) * dtdy;
-          s += F(10 + v, i, j, k) * dtdz;
-          s -= F(v, i + 1, j, k) * dtdx;
-          s -= F(5 + v, i, j + 1, k) * dtdy;
-          s -= F(10 + v, i, j, k + 1) * dtdz;
-          un[v] = s;
-        }
-      }
-      // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,
-      // exactly like the reference's zero-initialised h_emf
-      auto emf = [&](int c, int ii, int jj, int kk) -> T {
-        return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
-      };
-      auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
-        const T ez = emf(0, ii, jj, kk), ey = emf(1, ii, jj, kk), ex = emf(2, ii, jj, kk);
-        if (kk < kN) {
-          bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
-          by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
-        }
-        bx -= (emf(1, ii, jj, kk + 1) - ey) * dtdz;
-        by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
-        bz += (emf(1, ii + 1, jj, kk) - ey) * dtdx;
-        bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
-      };
-      ct(i, j, k, un[IA], un[IB], un[IC]);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
-
-      if (inner) {  // inverse dt of the new state: needs the new B on the three upper faces
-        T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
-        d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
-        d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
-        d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
-        T q[8];
-        dev::cons_to_prim_mhd(P, un, bxp, byp, bzp, T(0), q);
-        const T irho = dev::rcp(q[ID]);
-        const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
-        const T bb = a2 + b2 + c2;
-        T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
-        T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
-        T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
-        if (P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
-        invDt = vx / P.dx + vy / P.dy + vz / P.dz;
-      }
+      invDt = update_cell<FAST>(P, U, Unew, F, E, i, j, k, dt);
     }
   }
   if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
@@ -796,15 +806,22 @@ void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int 
 // MINB dispatch: FP64 kernels are compiled for several occupancy targets (register caps), picked at
 // run time by setTuning(); the FP32 flavour keeps one variant each.
 #define RG_MINB_SWITCH(T, minb, LAUNCH, DFLT)              \
-  if (sizeof(T) == 4) { LAUNCH(DFLT); }                    \
+  if (sizeof(T) == 4) { LAUNCH(DFLT, false); }             \
+  else if (!fastPath(P)) { LAUNCH(4, false); }             \
   else switch (minb) {                                     \
-    case 2: LAUNCH(2); break;                              \
-    case 3: LAUNCH(3); break;                              \
-    case 4: LAUNCH(4); break;                              \
-    case 5: LAUNCH(5); break;                              \
-    case 6: LAUNCH(6); break;                              \
-    default: LAUNCH(8); break;                             \
+    case 2:                                                \
+    case 3: LAUNCH(3, true); break;                        \
+    case 4: LAUNCH(4, true); break;                        \
+    case 5: LAUNCH(5, true); break;                        \
+    case 6: LAUNCH(6, true); break;                        \
+    default: LAUNCH(8, true); break;                       \
   }
+// the FAST instantiations (see mhd_device.cuh) serve the headline configuration: adiabatic,
+// non-rotating, HLLD fluxes + 2-D HLLD emfs; everything else runs the generic kernels
+template <typename T>
+static bool fastPath(const KParams<T>& P) {
+  return P.cIso <= T(0) && P.Omega0 <= T(0) && P.riemannSolver == RS_HLLD && P.magRiemannSolver == MAG_HLLD;
+}
 
 template <typename T>
 void MhdKernels<T>::elec(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
@@ -818,7 +835,7 @@ void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int
   if (k1 <= k0) return;
   const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // gw-1 .. size-gw
   const dim3 g = gridFor(n, m, k1 - k0);
-#define RG_L(M) k_trace<T, M><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
+#define RG_L(M, FA) k_trace<T, M, FA><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
   RG_MINB_SWITCH(T, g_traceMinB, RG_L, 4)
 #undef RG_L
   ++g_launches;
@@ -828,10 +845,10 @@ template <typename T>
 void MhdKernels<T>::flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
-#define RG_L(M)                                                                   \
-  k_flux<T, 0, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
-  k_flux<T, 1, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
-  k_flux<T, 2, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
+#define RG_L(M, FA)                                                                   \
+  k_flux<T, 0, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 1, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0);       \
+  k_flux<T, 2, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_fluxMinB, RG_L, 6)
 #undef RG_L
   g_launches += 3;
@@ -841,10 +858,10 @@ template <typename T>
 void MhdKernels<T>::emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.nx + 1, P.ny + 1, k1 - k0);
-#define RG_L(M)                                                                   \
-  k_emf<T, 2, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
-  k_emf<T, 1, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
-  k_emf<T, 0, M><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
+#define RG_L(M, FA)                                                                   \
+  k_emf<T, 2, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 1, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0);        \
+  k_emf<T, 0, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_emfMinB, RG_L, 6)
 #undef RG_L
   g_launches += 3;
@@ -855,7 +872,7 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
                            unsigned long long* d, cudaStream_t s) {
   if (k1 <= k0) return;
   const dim3 g = gridFor(P.isize, P.jsize, k1 - k0);
-#define RG_L(M) k_update<T, M><<<g, blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
+#define RG_L(M, FA) k_update<T, M, FA><<<g, blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
   RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
 #undef RG_L
   ++g_launches;

@@ -17,43 +17,34 @@ namespace dev {
 // FP64 reciprocal / rsqrt / sqrt as MUFU seed + Newton steps WITHOUT the library's slow-path
 // branch (denormal / inf / zero handling): every denominator on this path is a normal number
 // (densities, wave-speed differences, positive radicands), and dropping the branch removes ~8
-// non-FP64 instructions + a BSSY/BSYNC pair per call.  Accuracy: rcp <= 1 ulp, rsqrt/sqrt <= 2 ulp.
+// non-FP64 instructions + a BSSY/BSYNC pair per call.  ONE cubic Newton step after the 2^-20 seed
+// (error 2^-60 before rounding): results are within ~2 ulp, far inside the 1e-12 parity tolerance.
 __device__ __forceinline__ double rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
   double e = fma(-x, r, 1.0);
   e = fma(e, e, e);
-  r = fma(r, e, r);                                        // cubic step
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  return fma(r, e, r);                                     // cubic step: 2^-20 -> 2^-60 + rounding
 }
 __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
 __device__ __forceinline__ double rsq(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H
-  double e = fma(-x * y, y, 1.0);
-  y = fma(y * e, fma(e, 0.375, 0.5), y);
-  e = fma(-x * y, y, 1.0);
-  return fma(y * e, 0.5, y);
+  const double e = fma(-x * y, y, 1.0);
+  return fma(y * e, fma(e, 0.375, 0.5), y);                // cubic step
 }
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
 // sqrt for x > 0 (callers clamp radicands that can reach 0 to a tiny positive number)
-__device__ __forceinline__ double sqr_t(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x * y, y, 1.0);
-  y = fma(y * e, fma(e, 0.375, 0.5), y);
-  double s = x * y;
-  double r = fma(-s, s, x);
-  return fma(r, 0.5 * y, s);
-}
+__device__ __forceinline__ double sqr_t(double x) { return x * rsq(x); }
 __device__ __forceinline__ float sqr_t(float x) { return sqrtf(x); }
 template <typename T> __device__ __forceinline__ T tiny();
 template <> __device__ __forceinline__ double tiny<double>() { return 1e-300; }
 template <> __device__ __forceinline__ float tiny<float>() { return 1e-37f; }
-__device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+// double max/min as compare + select (3 instructions); fmax/fmin cost 7 with their NaN handling,
+// and no NaN is ever an operand on this path
+__device__ __forceinline__ double mx(double a, double b) { return (a > b) ? a : b; }
 __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double mn(double a, double b) { return (a < b) ? a : b; }
 __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double ab(double a) { return fabs(a); }
 __device__ __forceinline__ float ab(float a) { return fabsf(a); }
@@ -77,10 +68,32 @@ __device__ __forceinline__ T limited_slope(T st, T qm, T q0, T qp) {
   if (dlft * drgt <= T(0)) dlim = T(0);
   return dsgn * mn(dlim, ab(dcen));
 }
+// the same limiter returning HALF the slope, arranged for the FP64 pipe: 3 adds, 2 multiplies and
+// 2 compares; the sign of dcen is copied with an integer op and "dlft*drgt <= 0" is the sign-bit
+// test of the two one-sided differences (a zero difference already gives min(|.|,|.|) = 0).
+// hst = st/2.  dcen is formed as (a+b)/2 instead of (qp-qm)/2: equal up to rounding.
+__device__ __forceinline__ double half_slope(double hst, double qm, double q0, double qp) {
+  const double a = q0 - qm, b = qp - q0;
+  const double s = a + b;
+  const double m = mn(ab(a), ab(b)) * hst;
+  const double c = ab(s) * 0.25;
+  double r = mn(m, c);
+  if ((__double2hiint(a) ^ __double2hiint(b)) < 0) r = 0.0;
+  return __hiloint2double((__double2hiint(r) & 0x7fffffff) | (__double2hiint(s) & 0x80000000), __double2loint(r));
+}
+__device__ __forceinline__ float half_slope(float hst, float qm, float q0, float qp) {
+  const float a = q0 - qm, b = qp - q0;
+  const float s = a + b;
+  float r = fminf(fminf(fabsf(a), fabsf(b)) * hst, fabsf(s) * 0.25f);
+  if ((__float_as_int(a) ^ __float_as_int(b)) < 0) r = 0.0f;
+  return copysignf(r, s);
+}
 
 // cons -> prim for one cell. reference constoprim.h:137-199 (constoprim_mhd).
 //   u[8] conservative (B = left faces), bn[3] = B faces of the +1 neighbours.
-template <typename T>
+// FAST = compile-time promise "adiabatic (cIso == 0), non-rotating (Omega0 == 0), HLLD + 2-D HLLD":
+// the launch wrappers pick the FAST instantiation of the kernels when the run parameters say so.
+template <bool FAST = false, typename T>
 __device__ __forceinline__ void cons_to_prim_mhd(const KParams<T>& P, const T (&u)[8], T bxp, T byp, T bzp,
                                                  T dt, T (&q)[8]) {
   T r = mx(u[ID], P.smallr);
@@ -88,7 +101,7 @@ __device__ __forceinline__ void cons_to_prim_mhd(const KParams<T>& P, const T (&
   T vx = u[IU] * ir, vy = u[IV] * ir, vz = u[IW] * ir;
   T A = T(0.5) * (u[IA] + bxp), B = T(0.5) * (u[IB] + byp), C = T(0.5) * (u[IC] + bzp);
   T p;
-  if (P.cIso > T(0)) {
+  if (!FAST && P.cIso > T(0)) {
     p = r * P.cIso * P.cIso;
   } else {
     T eken = T(0.5) * (vx * vx + vy * vy + vz * vz);
@@ -96,7 +109,7 @@ __device__ __forceinline__ void cons_to_prim_mhd(const KParams<T>& P, const T (&
     T eint = (u[IP] - emag) * ir - eken;
     p = mx((P.gamma0 - T(1)) * r * eint, r * P.smallp);
   }
-  if (P.Omega0 > T(0)) {  // Coriolis predictor, constoprim.h:189-195
+  if (!FAST && P.Omega0 > T(0)) {  // Coriolis predictor, constoprim.h:189-195
     T dvx = T(2.0) * P.Omega0 * vy;
     T dvy = T(-0.5) * P.Omega0 * vx;
     vx += dvx * dt * T(0.5);
@@ -181,13 +194,13 @@ __device__ void riemann_llf(const KParams<T>& P, State<T> l, State<T> r, T (&flu
 
 // HLLD (Miyoshi & Kusano 2005) as in reference riemann_mhd.h:139-342.  8 reciprocals, 3 square
 // roots and 2 reciprocal square roots per interface instead of 29 divisions + 6 square roots.
-template <typename T>
+template <bool FAST = false, typename T>
 __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, State<T> Rr, T (&flux)[8]) {
   const T entho = rcp(P.gamma0 - T(1));
   const T a = T(0.5) * (L.a + Rr.a);
   const T sgnm = (a >= T(0)) ? T(1) : T(-1);
   const T a2 = a * a;
-  if (P.cIso > T(0)) {
+  if (!FAST && P.cIso > T(0)) {
     L.p = L.r * P.cIso * P.cIso;
     Rr.p = Rr.r * P.cIso * P.cIso;
   }
@@ -295,10 +308,10 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
 }
 
 // dispatch, reference riemann_mhd.h:354-368
-template <typename T>
+template <bool FAST = false, typename T>
 __device__ __forceinline__ void riemann_mhd(const KParams<T>& P, const State<T>& l, const State<T>& r, T (&flux)[8]) {
-  if (P.riemannSolver == RS_HLLD) {
-    riemann_hlld(P, l, r, flux);
+  if (FAST || P.riemannSolver == RS_HLLD) {
+    riemann_hlld<FAST>(P, l, r, flux);
   } else if (P.riemannSolver == RS_HLL) {
     riemann_hll(P, l, r, flux);
   } else if (P.riemannSolver == RS_LLF) {
@@ -475,12 +488,12 @@ __device__ T mag_riemann2d_llf(const KParams<T>& P, const Corner<T> (&q)[4]) {
 //   s[0] = RT-state of cell (-1,-1), s[1] = RB of (-1,0), s[2] = LT of (0,-1), s[3] = LB of (0,0)
 // in the reference's (IRT, IRB, ILT, ILB) order, each as (r, p, u, v, w, a, b, c) edge-frame.
 // emfDir: 0 = X, 1 = Y, 2 = Z (shear terms only).
-template <typename T>
+template <bool FAST = false, typename T>
 __device__ __forceinline__ T compute_emf(const KParams<T>& P, const Corner<T>& RT, const Corner<T>& RB,
                                          const Corner<T>& LT, const Corner<T>& LB, int emfDir, T xPos) {
   Corner<T> q[4];  // LL <- RT, RL <- LT, LR <- RB, RR <- LB
   q[0] = RT; q[1] = LT; q[2] = RB; q[3] = LB;
-  if (P.cIso > T(0)) {
+  if (!FAST && P.cIso > T(0)) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) q[s].p = q[s].r * P.cIso * P.cIso;
   }
@@ -489,11 +502,11 @@ __device__ __forceinline__ T compute_emf(const KParams<T>& P, const Corner<T>& R
   q[0].a = aT; q[1].a = aT; q[2].a = aB; q[3].a = aB;
   q[0].b = bR; q[1].b = bL; q[2].b = bR; q[3].b = bL;
   T emf = T(0);
-  if (P.magRiemannSolver == MAG_HLLD) emf = mag_riemann2d_hlld(P, q[0], q[1], q[2], q[3]);
+  if (FAST || P.magRiemannSolver == MAG_HLLD) emf = mag_riemann2d_hlld(P, q[0], q[1], q[2], q[3]);
   else if (P.magRiemannSolver == MAG_HLLA) emf = mag_riemann2d_hll(P, q, true);
   else if (P.magRiemannSolver == MAG_HLLF) emf = mag_riemann2d_hll(P, q, false);
   else if (P.magRiemannSolver == MAG_LLF) emf = mag_riemann2d_llf(P, q);
-  if (P.Omega0 > T(0)) {  // shearing-box upwind terms, riemann_mhd.h:1171-1189
+  if (!FAST && P.Omega0 > T(0)) {  // shearing-box upwind terms, riemann_mhd.h:1171-1189
     if (emfDir == 0) {
       const T shear = T(-1.5) * P.Omega0 * xPos;
       emf += shear * (shear > T(0) ? q[0].b : q[3].b);
