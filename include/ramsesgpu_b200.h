@@ -113,14 +113,15 @@ int rg_set_chunk_planes(rg_handle h, int planes);
 int rg_set_halo_overlap(rg_handle h, int on);
 
 /* occupancy knobs of the FP64 kernels (process-wide): key = "flux_minb" | "emf_minb" | "trace_minb" |
- * "update_minb", value = 2..8 resident blocks per SM the kernel variant is compiled for */
+ * "update_minb", value = 2..8 resident blocks per SM the kernel variant is compiled for; "tile_x" = 32|64|128;
+ * "fused_b" = 0|1 selects the separate flux/emf/update kernels or the fused TMA kernel (default 1) */
 int rg_set_tuning(const char* key, int value);
 
 /* device timing of a region on the library's stream (CUDA events): total and per kernel family.
  * phase order: RG_PHASE_* below.  Events are recorded around every launch between begin and end;
  * rg_profile_end synchronises and returns milliseconds and launch counts summed over the region. */
 enum { RG_PHASE_BOUNDARY = 0, RG_PHASE_PRIM, RG_PHASE_TRACE, RG_PHASE_FLUX, RG_PHASE_EMF, RG_PHASE_UPDATE,
-       RG_PHASE_DT, RG_PHASE_COPY, RG_PHASE_HALO, RG_NPHASE };
+       RG_PHASE_DT, RG_PHASE_COPY, RG_PHASE_HALO, RG_PHASE_FUSED /* fused flux+emf+update */, RG_NPHASE };
 int rg_profile_begin(rg_handle h);
 int rg_profile_end(rg_handle h, double* total_ms, double* phase_ms, unsigned long long* phase_launches);
 

@@ -27,6 +27,9 @@ struct MhdScratch {
   T* EL = nullptr;    // 3 components: v x B at the LOW edges (x, y, z), input of the trace
   int planes = 0;     // allocated planes per component
   int kbase = 0;      // k of scratch plane 0 for the chunk being processed
+  // TMA descriptor (CUtensorMap) of W for the fused flux+emf+update kernel; valid when fused != 0
+  alignas(64) unsigned char mapW[128] = {0};
+  int fused = 0;
 };
 
 template <typename T>
@@ -44,6 +47,12 @@ struct MhdKernels {
   static void emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, cudaStream_t s);
   static void update(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
                      unsigned long long* dMaxInvDt, cudaStream_t s);
+  // fused flux + emf + update (TMA-staged W tiles, z-marching blocks) for the FAST configuration:
+  // fusedPrepare() encodes the tensor map of sc.W into sc.mapW and sets sc.fused when the run
+  // parameters and the array shapes qualify; fusedFluxEmfUpdate() replaces flux()+emf()+update()
+  static void fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc);
+  static void fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka, int kb,
+                                 T dt, unsigned long long* dMaxInvDt, cudaStream_t s);
   // rotating frame / shearing box variants (Omega0 > 0): update with Coriolis + border remap, and the
   // y-shifted x ghost cells; (jplus, frac) = whole cells and fraction of dy of the border shift
   static void updateRotating(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
@@ -96,6 +105,8 @@ inline double decodeMax(unsigned long long v) {
 unsigned long long kernelLaunchCount();
 // occupancy knobs: "flux_minb" | "emf_minb" | "trace_minb" | "update_minb" = 2..8 resident blocks/SM
 bool setTuning(const char* key, int value);
+// "fused_b" knob (default on): use the fused flux+emf+update kernel when MhdScratch::fused is set
+bool fusedRequested();
 void resetKernelLaunchCount();
 
 }  // namespace rg

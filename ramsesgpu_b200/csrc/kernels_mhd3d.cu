@@ -10,16 +10,20 @@
 // flux/emf/update gw..size-gw (inclusive), with the reference's write guards.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "kernels.h"
 #include "kernel_common.cuh"
 #include "mhd_device.cuh"
+#include "tma.cuh"
 
 namespace rg {
 
 unsigned long long g_launches = 0;
 int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
+int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
+bool fusedRequested() { return g_fusedB != 0; }
 
 namespace {
 
@@ -386,26 +390,30 @@ __device__ __forceinline__ T update_cell(const KParams<T>& P, const UView<T>& U,
   auto emf = [&](int c, int ii, int jj, int kk) -> T {
     return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
   };
-  auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
-    const T ez = emf(0, ii, jj, kk), ey = emf(1, ii, jj, kk), ex = emf(2, ii, jj, kk);
-    if (kk < kN) {
-      bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
-      by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
-    }
-    bx -= (emf(1, ii, jj, kk + 1) - ey) * dtdz;
-    by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
-    bz += (emf(1, ii + 1, jj, kk) - ey) * dtdx;
-    bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
+  // constrained transport of one face component (reference cpu_v3.cpp:600-630), per component so
+  // that the dt estimate below touches only the emfs it needs
+  auto ctx = [&](int ii, int jj, int kk, T bx) -> T {
+    if (kk < kN) bx += (emf(0, ii, jj + 1, kk) - emf(0, ii, jj, kk)) * dtdy;
+    return bx - (emf(1, ii, jj, kk + 1) - emf(1, ii, jj, kk)) * dtdz;
   };
-  ct(i, j, k, un[IA], un[IB], un[IC]);
+  auto cty = [&](int ii, int jj, int kk, T by) -> T {
+    if (kk < kN) by -= (emf(0, ii + 1, jj, kk) - emf(0, ii, jj, kk)) * dtdx;
+    return by + (emf(2, ii, jj, kk + 1) - emf(2, ii, jj, kk)) * dtdz;
+  };
+  auto ctz = [&](int ii, int jj, int kk, T bz) -> T {
+    bz += (emf(1, ii + 1, jj, kk) - emf(1, ii, jj, kk)) * dtdx;
+    return bz - (emf(2, ii, jj + 1, kk) - emf(2, ii, jj, kk)) * dtdy;
+  };
+  un[IA] = ctx(i, j, k, un[IA]);
+  un[IB] = cty(i, j, k, un[IB]);
+  un[IC] = ctz(i, j, k, un[IC]);
 #pragma unroll
   for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
 
   if (inner) {  // inverse dt of the new state: needs the new B on the three upper faces
-    T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
-    d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
-    d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
-    d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
+    const T bxp = ctx(i + 1, j, k, U(IA, i + 1, j, k));
+    const T byp = cty(i, j + 1, k, U(IB, i, j + 1, k));
+    const T bzp = ctz(i, j, k + 1, U(IC, i, j, k + 1));
     T q[8];
     dev::cons_to_prim_mhd<FAST>(P, un, bxp, byp, bzp, T(0), q);
     const T irho = dev::rcp(q[ID]);
@@ -446,6 +454,247 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
     }
   }
   if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KF: fluxes + corner emfs + conservative/CT update + next dt in ONE kernel (FAST configuration).
+//
+// A thread block (one per SM) owns a TW x TH column of cells and marches along z.  Per plane, ONE TMA
+// bulk-tensor copy brings the (TW+2) x (TH+2) tile of all 38 W components into shared memory (ring of
+// three plane buffers, the copy of plane p+1 is issued when plane p starts).  The 6 x (TW+1) x (TH+1)
+// face / edge Riemann problems of a plane and the update of the plane below are warp-sized TASKS
+// handed out in a fixed order by a ticket counter; a task waits (spinning on shared-memory counters
+// and on the TMA mbarrier of its plane) only for the earlier tasks it really depends on, so there is
+// no block-wide barrier in the march and warps flow from one plane into the next.  Face fluxes and
+// corner emfs live in a three-plane shared-memory ring and never go to HBM; W is read from HBM once
+// per step instead of once per kernel (3 flux + 3 emf kernels), and global-load latency is off the
+// critical path.
+//   task order of plane p: TMA(p+1) | emf_x emf_y flux_z (need W(p-1), W(p)) | emf_z flux_x flux_y
+//   (need W(p)) | update of plane p-1 (needs the z group of p and everything of p-1)
+//   run-ahead gate: a task of plane p starts only when plane p-2 is complete (ring safety)
+// The arithmetic is the one of k_flux / k_emf / k_update (same device functions).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TW_, int TH_, int THREADS_>
+struct FusedTile {
+  static constexpr int TW = TW_, TH = TH_, THREADS = THREADS_;
+  static constexpr int WX = TW + 2, WY = TH + 2, WCELLS = WX * WY;  // W tile with one halo cell on every side
+  static constexpr int PX = TW + 1, PY = TH + 1;                     // low faces/edges of the cells + the closing ones
+  // a warp task covers two rows of 16 positions: every half warp reads 16 consecutive reals of one
+  // tile row, which keeps the 64-bit shared-memory loads free of bank conflicts
+  static constexpr int PXP = 16, NCH = PY / 2, NPOSP = PXP * PY;
+  static_assert(WX == 16 && PY % 2 == 0, "tile shape");
+  static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
+  static constexpr int NT = 1 + 7 * NCH;                             // tasks per plane
+  static constexpr int LZMAX = 96;                                   // planes per block (counter arrays)
+  static constexpr unsigned W_BYTES = (unsigned)(NW_MHD * WCELLS * sizeof(T));
+  static constexpr unsigned W_STRIDE = (W_BYTES + 127u) / 128u * 128u;
+  static constexpr unsigned FE_SLOT = (unsigned)(NFE * NPOSP);       // reals per plane slot
+  static constexpr unsigned FE_BYTES = (unsigned)(3 * FE_SLOT * sizeof(T));
+  static constexpr unsigned NBAR = LZMAX + 2, NCNT = LZMAX + 4;
+  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 3u * NCNT * 4u + 16u;
+};
+
+template <typename T, typename C>
+struct WTileView {  // plane k of the W tile lives in ring buffer k % 3, laid out [comp][WY][WX]
+  const unsigned char* buf;
+  int ib, jb;  // cell index of tile element (0, 0)
+  __device__ __forceinline__ T operator()(int c, int i, int j, int k) const {
+    const T* b = reinterpret_cast<const T*>(buf + ((unsigned)k % 3u) * C::W_STRIDE);
+    return b[c * C::WCELLS + (j - jb) * C::WX + (i - ib)];
+  }
+};
+template <typename T, typename C>
+struct FETileView {  // fluxes (c0 = 0) or emfs (c0 = 15) of plane k (ring slot k % 3), [comp][PY][PXP]
+  T* buf;
+  int i0, j0, c0;
+  __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
+    return buf[((unsigned)k % 3u) * C::FE_SLOT + (c0 + c) * C::NPOSP + (j - j0) * C::PXP + (i - i0)];
+  }
+};
+
+template <typename T, typename C>
+__device__ __forceinline__ void fused_flux_task(const KParams<T>& P, const WTileView<T, C>& W,
+                                                const FETileView<T, C>& F, int dir, int i, int j, int k) {
+  dev::State<T> L, R;
+  if (dir == 0) {
+    L = face_state<T, 0>(P, W, i - 1, j, k, T(1));
+    R = face_state<T, 0>(P, W, i, j, k, T(-1));
+  } else if (dir == 1) {
+    L = face_state<T, 1>(P, W, i, j - 1, k, T(1));
+    R = face_state<T, 1>(P, W, i, j, k, T(-1));
+  } else {
+    L = face_state<T, 2>(P, W, i, j, k - 1, T(1));
+    R = face_state<T, 2>(P, W, i, j, k, T(-1));
+  }
+  T f[8];
+  dev::riemann_mhd<true>(P, L, R, f);
+  const int c0 = 5 * dir;
+  F(c0 + 0, i, j, k) = f[ID];
+  F(c0 + 1, i, j, k) = f[IP];
+  F(c0 + 2, i, j, k) = (dir == 0) ? f[IU] : (dir == 1) ? f[IV] : f[IW];
+  F(c0 + 3, i, j, k) = (dir == 1) ? f[IU] : f[IV];
+  F(c0 + 4, i, j, k) = (dir == 2) ? f[IU] : f[IW];
+}
+
+template <typename T, typename C>
+__device__ __forceinline__ void fused_emf_task(const KParams<T>& P, const WTileView<T, C>& W,
+                                               const FETileView<T, C>& E, int edir, int i, int j, int k) {
+  dev::Corner<T> RT, RB, LT, LB;
+  if (edir == 2) {
+    RT = edge_state<T, 2>(P, W, i - 1, j - 1, k, T(1), T(1));
+    RB = edge_state<T, 2>(P, W, i - 1, j, k, T(1), T(-1));
+    LT = edge_state<T, 2>(P, W, i, j - 1, k, T(-1), T(1));
+    LB = edge_state<T, 2>(P, W, i, j, k, T(-1), T(-1));
+  } else if (edir == 1) {
+    RT = edge_state<T, 1>(P, W, i - 1, j, k - 1, T(1), T(1));
+    RB = edge_state<T, 1>(P, W, i, j, k - 1, T(-1), T(1));
+    LT = edge_state<T, 1>(P, W, i - 1, j, k, T(1), T(-1));
+    LB = edge_state<T, 1>(P, W, i, j, k, T(-1), T(-1));
+  } else {
+    RT = edge_state<T, 0>(P, W, i, j - 1, k - 1, T(1), T(1));
+    RB = edge_state<T, 0>(P, W, i, j - 1, k, T(1), T(-1));
+    LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
+    LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
+  }
+  E(2 - edir, i, j, k) = dev::compute_emf<true>(P, RT, RB, LT, LB, edir, T(0));
+}
+
+// completion counters in shared memory: release-add by the finishing warp, acquire-poll by waiters
+__device__ __forceinline__ void signalCount(int* c) {
+  asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(tma::smemAddr(c)) : "memory");
+}
+__device__ __forceinline__ void waitCount(const int* c, int full) {
+  int v;
+  for (;;) {
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(tma::smemAddr(c)) : "memory");
+    if (v >= full) break;
+    __nanosleep(64);
+  }
+}
+
+template <typename T, typename C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapW,
+                        const T* __restrict__ Uold, T* __restrict__ Unew, int kbase, int ka, int kb, int lz, T dt,
+                        unsigned long long* __restrict__ dMaxInvDt) {
+  extern __shared__ unsigned char smemRaw[];
+  // 128-byte alignment for the TMA destination, computed on the shared-window address so that the
+  // compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+  unsigned char* sm = smemRaw + ((128u - (tma::smemAddr(smemRaw) & 127u)) & 127u);
+  unsigned char* wbuf = sm;
+  T* fe = reinterpret_cast<T*>(sm + 3 * C::W_STRIDE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 3 * C::W_STRIDE + C::FE_BYTES);  // bars[q - (za-1)]
+  int* cntAll = reinterpret_cast<int*>(bars + C::NBAR);  // cnt*[pl + 2], pl = plane - za
+  int* cntZ = cntAll + C::NCNT;
+  int* cntXY = cntZ + C::NCNT;
+  int* ticket = cntXY + C::NCNT;
+
+  const int gw = P.gw;
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
+  const int i0 = gw + blockIdx.x * C::TW, j0 = gw + blockIdx.y * C::TH;
+  const int za = ka + blockIdx.z * lz, zb = min(za + lz, kb);  // update planes [za, zb) of this block
+  if (za >= zb) return;
+  const int fhi = min(zb, kN);                       // last plane whose low faces / edges are needed
+  const int nPl = fhi - za + 1 + (zb > fhi ? 1 : 0);  // + the pseudo plane that only updates plane kN
+  const int tid = threadIdx.x, lane = tid & 31;
+
+  const WTileView<T, C> W{wbuf, i0 - 1, j0 - 1};
+  const FETileView<T, C> F{fe, i0, j0, 0}, E{fe, i0, j0, 15};
+  const UView<T> U = uview(Uold, P);
+
+  for (int n = tid; n < (int)C::NBAR; n += C::THREADS) tma::mbarInit(&bars[n], 1);
+  for (int n = tid; n < (int)C::NCNT; n += C::THREADS) {
+    cntAll[n] = (n < 2) ? C::NT : 0;      // planes za-2, za-1 count as complete
+    cntZ[n] = (n < 2) ? 3 * C::NCH : 0;
+    cntXY[n] = (n < 2) ? 3 * C::NCH : 0;
+  }
+  if (tid == 0) *ticket = 0;
+  tma::fenceBarrierInit();
+  __syncthreads();
+  auto loadPlane = [&](int q) {  // one thread
+    uint64_t* bar = &bars[q - (za - 1)];
+    tma::mbarExpectTx(bar, C::W_BYTES);
+    tma::loadTile4D(wbuf + ((unsigned)q % 3u) * C::W_STRIDE, &mapW, bar, i0 - 1, j0 - 1, q - kbase, 0);
+  };
+  if (tid == 0) {
+    loadPlane(za - 1);
+    loadPlane(za);
+  }
+
+  for (;;) {
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, 1);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= nPl * C::NT) break;
+    const int pl = tk / C::NT, t = tk - pl * C::NT, p = za + pl;
+    waitCount(&cntAll[pl], C::NT);  // plane p-2 complete: ring slots p % 3 of W and F/E are free
+    if (t == 0) {                   // producer task: W(p+1) -> ring buffer of plane p-2
+      waitCount(&cntZ[pl + 1], 3 * C::NCH);  // the z group of plane p-1 was the last reader of W(p-2)
+      if (lane == 0 && p + 1 <= fhi) {
+        tma::fenceProxyAsync();
+        loadPlane(p + 1);
+      }
+      __syncwarp();
+      if (lane == 0) signalCount(&cntAll[pl + 2]);
+      continue;
+    }
+    const int kind = (t - 1) / C::NCH, chunk = (t - 1) - kind * C::NCH;
+    const int pi = lane & 15, pj = chunk * 2 + (lane >> 4);
+    const int i = i0 + pi, j = j0 + pj;
+    const bool ok = pi < C::PX && i <= iN && j <= jN;
+    if (kind < 6) {
+      // kinds 0..2 = z group (emf_x, emf_y, flux_z), 3..5 = plane-local group (emf_z, flux_x, flux_y; not on
+      // the closing plane of a z range).  ONE call site per solver keeps a single copy of each in the
+      // instruction cache; the direction only selects which W components are gathered.
+      const bool zgrp = kind < 3;
+      const bool isEmf = kind == 0 || kind == 1 || kind == 3;
+      const int dir = isEmf ? (kind == 3 ? 2 : kind) : (kind == 2 ? 2 : kind - 4);
+      if (p <= fhi && (zgrp || p < zb)) {
+        if (zgrp) tma::mbarWait(&bars[pl], 0);
+        tma::mbarWait(&bars[pl + 1], 0);
+        if (isEmf) {
+          if (ok) fused_emf_task<T, C>(P, W, E, dir, i, j, p);
+        } else {
+          // a face is only needed where both transverse indexes are inner (k_flux)
+          const bool need = (dir == 0 || i < iN) && (dir == 1 || j < jN) && (dir == 2 || p < kN);
+          if (ok && need) fused_flux_task<T, C>(P, W, F, dir, i, j, p);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        signalCount(zgrp ? &cntZ[pl + 2] : &cntXY[pl + 2]);
+        signalCount(&cntAll[pl + 2]);
+      }
+    } else {  // update of plane p-1
+      if (p - 1 >= za) {
+        waitCount(&cntZ[pl + 2], 3 * C::NCH);
+        waitCount(&cntZ[pl + 1], 3 * C::NCH);
+        waitCount(&cntXY[pl + 1], 3 * C::NCH);
+        __syncwarp();
+        // a cell of the closing column/row belongs to this tile only when it is the ghost face (iN / jN)
+        const bool mine = ok && (i < i0 + C::TW || i == iN) && (j < j0 + C::TH || j == jN);
+        T invDt = T(0);
+        if (mine) invDt = update_cell<true>(P, U, Unew, F, E, i, j, p - 1, dt);
+        if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
+      }
+      __syncwarp();
+      if (lane == 0) signalCount(&cntAll[pl + 2]);
+    }
+  }
+}
+
+// ghost cells outside the update box keep the old values (the separate k_update does this itself)
+template <typename T>
+__global__ void __launch_bounds__(BX) k_copy_outside_box(const __grid_constant__ KParams<T> P,
+                                                         const T* __restrict__ Uold, T* __restrict__ Unew, int k0) {
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(0, P.isize, 0, P.jsize, i, j)) return;
+  const int gw = P.gw;
+  if (i >= gw && i <= P.isize - gw && j >= gw && j <= P.jsize - gw) return;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  for (int v = 0; v < P.nvar; ++v) Unew[v * comp + idx] = Uold[v * comp + idx];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -767,6 +1016,10 @@ bool setTuning(const char* key, int value) {
     g_tileX = value;
     return true;
   }
+  if (k == "fused_b") {
+    g_fusedB = value ? 1 : 0;
+    return true;
+  }
   if (value < 2 || value > 8) return false;
   if (k == "flux_minb") g_fluxMinB = value;
   else if (k == "emf_minb") g_emfMinB = value;
@@ -876,6 +1129,68 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
   RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
 #undef RG_L
   ++g_launches;
+}
+
+// ---- fused path ---------------------------------------------------------------------------------
+
+template <typename T>
+struct FusedSel { typedef FusedTile<T, 14, 7, 512> Cfg; };
+
+template <typename T>
+void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
+  typedef typename FusedSel<T>::Cfg C;
+  sc.fused = 0;
+  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3 || sc.W == nullptr) return;
+  CUtensorMap map;
+  if (!tma::encodeTile4D(&map, sc.W, (int)sizeof(T), P.isize, P.jsize, sc.planes, NW_MHD, C::WX, C::WY)) return;
+  static_assert(sizeof(CUtensorMap) <= sizeof(sc.mapW), "tensor map storage");
+  memcpy(sc.mapW, &map, sizeof(map));
+  static bool attrSet = false;
+  if (!attrSet) {
+    if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    attrSet = true;
+  }
+  sc.fused = 1;
+}
+
+template <typename T>
+void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka,
+                                       int kb, T dt, unsigned long long* d, cudaStream_t s) {
+  typedef typename FusedSel<T>::Cfg C;
+  if (kb <= ka) return;
+  static int nSM = 0;
+  if (nSM == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    if (nSM <= 0) nSM = 148;
+  }
+  // tiles of TW x TH cells over the (nx+1) x (ny+1) update box; the ghost-face column/row is folded
+  // into the last tile when it would otherwise open a tile of its own
+  const int ntx = std::max(1, (P.nx + C::TW - 1) / C::TW), nty = std::max(1, (P.ny + C::TH - 1) / C::TH);
+  // split z into ranges so that the grid fills the SMs in whole waves (one block per SM)
+  const int planes = kb - ka;
+  int bestNz = 1;
+  double bestCost = 1e300;
+  for (int nz = 1; nz <= planes; ++nz) {
+    const int lz = (planes + nz - 1) / nz;
+    if (lz > C::LZMAX) continue;
+    if (lz < 8 && nz > 1) break;
+    const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
+    const double cost = (double)((blocks + nSM - 1) / nSM) * (lz + 1.5);
+    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
+  }
+  const int lz = (planes + bestNz - 1) / bestNz;
+  const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
+  CUtensorMap map;
+  memcpy(&map, sc.mapW, sizeof(map));
+  k_fused_flux_emf_update<T, C><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d);
+  k_copy_outside_box<T><<<gridFor(P.isize, P.jsize, kb - ka), blockShape(), 0, s>>>(P, Uold, Unew, ka);
+  g_launches += 2;
 }
 
 template <typename T>

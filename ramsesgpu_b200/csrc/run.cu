@@ -558,6 +558,7 @@ class RunImpl final : public Run {
     RG_CUDA(cudaMalloc(&sc_.EL, plane * sc_.planes * 3 * sizeof(T)));
     scratchBytes_ = perPlane * sc_.planes;
     deviceBytes_ += scratchBytes_;
+    MhdKernels<T>::fusedPrepare(kp_, sc_);
   }
 
   // ---- 3D MHD step: reference godunov_unsplit_cpu/gpu (MHDRunGodunov.cpp:623-672, 1447-1503) ------
@@ -580,6 +581,10 @@ class RunImpl final : public Run {
       phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
       phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
       phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      if (sc.fused && fusedRequested()) {
+        phase(PH_FUSED, [&] { MhdKernels<T>::fusedFluxEmfUpdate(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_); });
+        return;
+      }
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_UPDATE, [&] { MhdKernels<T>::update(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_); });

@@ -167,3 +167,41 @@ def test_device_probes_vs_oracle(native, oracle64):
             e = run.probe_compute_emf(d, qe)
             eo = np.array([oracle64.compute_emf(p, d, qe[i]) for i in range(n)])
             assert np.allclose(e, eo, rtol=1e-10, atol=1e-11), d
+
+
+@pytest.mark.parametrize("n,over,chunk", [
+    ((40, 22, 12), {}, 0),                                   # several tiles in x and y, partial last tiles
+    ((28, 14, 10), {}, 0),                                   # nx, ny multiples of the tile: closing column/row folded
+    ((32, 16, 20), {"OrszagTang": {"kt": 1.0}}, 7),          # ghost-face column/row folded into the last tile, z chunks
+    ((18, 10, 9), {"mesh": {"boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1, "boundary_ymax": 1,
+                            "boundary_zmin": 2, "boundary_zmax": 1}}, 0),
+    ((17, 12, 8), {}, 0),                                    # odd row length: no TMA descriptor, separate kernels
+])
+def test_fused_kernel_equals_separate_kernels(native, n, over, chunk):
+    """The fused flux+emf+update kernel (TMA-staged W tiles, z-marching blocks, ticket-scheduled warp
+    tasks) runs the same device functions as k_flux/k_emf/k_update; the compiler contracts a few
+    multiply-adds differently in the two kernels, so agreement is to the last bits, not bitwise."""
+    from ramsesgpu_b200 import set_tuning
+    ini = ot3d_ini(n, **over)
+    try:
+        set_tuning("fused_b", 0)
+        ref, tr, dtr, gw = run_gpu_steps(ini, 4, chunk=chunk)
+        set_tuning("fused_b", 1)
+        got, tg, dtg, _ = run_gpu_steps(ini, 4, chunk=chunk)
+    finally:
+        set_tuning("fused_b", 1)
+    assert np.allclose(dtr, dtg, rtol=1e-14, atol=0)
+    assert (np.abs(ref - got) <= 1e-14 * np.abs(ref).max()).all()      # ghosts included
+    for v in range(8):
+        a, b = ref[v, gw:-gw, gw:-gw, gw:-gw], got[v, gw:-gw, gw:-gw, gw:-gw]
+        if np.abs(a).max() > 1e-10:     # B_z of the kt = 0 problem is rounding noise around zero
+            assert l2_relative(a, b) < 1e-14, v
+
+
+def test_fused_kernel_chunk_invariance_is_bitwise(native):
+    """z ranges / chunks of the fused kernel must not change a single bit (same kernel, same order)."""
+    ini = ot3d_ini((30, 16, 40), OrszagTang={"kt": 1.0})
+    ref, _, _, _ = run_gpu_steps(ini, 3)
+    for chunk in (3, 11):
+        got, _, _, _ = run_gpu_steps(ini, 3, chunk=chunk)
+        assert np.array_equal(ref, got), chunk
