@@ -32,9 +32,18 @@ B_ALG_CELL = 128.0        # compulsory bytes per MHD FP64 cell update: read U on
 # algorithmic bytes per launch unit of each kernel family (DESIGN.md "kernels"): reals read + written once
 # prim = k_prim (8r+8w) + k_elec (6r+3w); trace: Q 8 + face B 3 + E 3 read, W 38 written; flux: 15 W
 # components read + 5 written per direction; emf: 22 read + 1 written per direction; update: U 8 +
-# F 15 + E 3 read, U 8 written
+# F 15 + E 3 read, U 8 written; fused (flux+emf+update in one kernel): W 38 + U 8 read, U 8 written
 B_ALG_KERNEL = {"prim": (8 + 8 + 6 + 3) * 8.0, "trace": (8 + 3 + 3 + 38) * 8.0, "flux": (15 + 5) * 8.0 * 3,
-                "emf": (22 + 1) * 8.0 * 3, "update": (8 + 15 + 3 + 8) * 8.0}
+                "emf": (22 + 1) * 8.0 * 3, "update": (8 + 15 + 3 + 8) * 8.0, "fused": (38 + 8 + 8) * 8.0}
+
+
+def ncu_evidence(fam):
+    """Per-launch DRAM traffic and pipe utilisation of a kernel family from the committed ncu capture
+    (profiles/ncu_evidence.json, written from `ncu --set full` runs of this same workload)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_evidence.json"))).get(fam)
+    except Exception:
+        return None
 
 
 def base_ini():
@@ -283,6 +292,7 @@ def main():
         units = cells_per_gpu * args.steps            # cell updates processed by that family in the region
         achieved = B_ALG_KERNEL[fam] * units / (fam_ms * 1e-3) / 1e9
         step_achieved = B_ALG_CELL * cells_per_gpu / (ms_per_step * 1e-3) / 1e9
+        ev = ncu_evidence(fam)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -294,8 +304,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "launch_ms": fam_ms / max(fam_launches, 1), "share_of_step": fam_ms / total_ms},
+                         "frac": achieved / peak, "traffic": (ev or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "launch_ms": fam_ms / max(fam_launches, 1), "share_of_step": fam_ms / total_ms,
+                         "ncu": ev},
             "roofline_step": {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s",
                               "frac": step_achieved / peak, "bytes_per_cell": B_ALG_CELL,
                               "note": "whole fused-equivalent step at 128 B/cell; FP64-pipe bound, see DESIGN.md"},

@@ -53,6 +53,12 @@ struct MhdKernels {
   static void fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc);
   static void fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka, int kb,
                                  T dt, unsigned long long* dMaxInvDt, cudaStream_t s);
+  // fused cons->prim + edge electric field + trace (U -> W, shared-memory rings, z-marching blocks) for the
+  // FAST configuration; replaces prim() + elec() + trace() on traced planes [k0, k1)
+  static bool fusedTraceAvailable(const KParams<T>& P);
+  static void fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s);
+  // x/y ghost cells of planes [k0,k1) keep the old values (the fused kernel only writes the update box)
+  static void copyOutsideBox(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s);
   // rotating frame / shearing box variants (Omega0 > 0): update with Coriolis + border remap, and the
   // y-shifted x ghost cells; (jplus, frac) = whole cells and fraction of dy of the border shift
   static void updateRotating(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
@@ -107,6 +113,8 @@ unsigned long long kernelLaunchCount();
 bool setTuning(const char* key, int value);
 // "fused_b" knob (default on): use the fused flux+emf+update kernel when MhdScratch::fused is set
 bool fusedRequested();
+// "fused_a" knob (default on): fused prim+elec+trace kernel
+bool fusedTraceRequested();
 void resetKernelLaunchCount();
 
 }  // namespace rg

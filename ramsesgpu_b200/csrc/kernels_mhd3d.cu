@@ -24,6 +24,7 @@ unsigned long long g_launches = 0;
 int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
+extern int g_fusedA;
 
 namespace {
 
@@ -68,16 +69,10 @@ __global__ void __launch_bounds__(BX) k_prim(const __grid_constant__ KParams<T> 
 //      (reference cpu_v3.cpp:36-101, kernel_mhd_compute_elec_field): 4-cell average of the
 //      velocities, 2-face average of the face fields
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
-                                             const T* __restrict__ Qp, T* __restrict__ ELp, int planes, int kbase,
-                                             int k0) {
-  int i, j;
-  const int k = k0 + blockIdx.z;
-  if (!tileCoords(1, P.isize - 2, 1, P.jsize - 2, i, j)) return;
-  const UView<T> U = uview(Uin, P);
-  const View<const T> Q = view<const T>(Qp, P, planes, kbase);
-  const View<T> EL = view(ELp, P, planes, kbase);
+// edge electric fields of one cell (low edges); QV / UV / ELV as in trace_cell
+template <bool FAST, typename T, typename QV, typename UV, typename ELV>
+__device__ __forceinline__ void elec_cell(const KParams<T>& P, const QV& Q, const UV& U, const ELV& EL, int i, int j,
+                                          int k) {
   const T h = T(0.5), f = T(0.25);
   const T u00 = Q(IU, i, j, k), v00 = Q(IV, i, j, k), w00 = Q(IW, i, j, k);
   const T A = U(IA, i, j, k), B = U(IB, i, j, k), C = U(IC, i, j, k);
@@ -86,7 +81,7 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
     const T w = f * (Q(IW, i, j - 1, k - 1) + Q(IW, i, j - 1, k) + Q(IW, i, j, k - 1) + w00);
     const T Bm = h * (U(IB, i, j, k - 1) + B), Cm = h * (U(IC, i, j - 1, k) + C);
     T ex = v * Cm - w * Bm;
-    if (P.Omega0 > T(0)) {  // rotating frame: advection by the background shear, MHDRunGodunov.cpp:2474-2478
+    if (!FAST && P.Omega0 > T(0)) {  // rotating frame: advection by the background shear, MHDRunGodunov.cpp:2474-2478
       const T xPos = P.xMin + P.dx * h + (i - P.gw) * P.dx;
       ex += T(-1.5) * P.Omega0 * xPos * Cm;
     }
@@ -103,7 +98,7 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
     const T v = f * (Q(IV, i - 1, j - 1, k) + Q(IV, i - 1, j, k) + Q(IV, i, j - 1, k) + v00);
     const T Am = h * (U(IA, i, j - 1, k) + A), Bm = h * (U(IB, i - 1, j, k) + B);
     T ez = u * Bm - v * Am;
-    if (P.Omega0 > T(0)) {  // MHDRunGodunov.cpp:2517-2521 (shear at the x face)
+    if (!FAST && P.Omega0 > T(0)) {  // MHDRunGodunov.cpp:2517-2521 (shear at the x face)
       const T xFace = P.xMin + P.dx * h + (i - P.gw) * P.dx - P.dx * h;
       ez -= T(-1.5) * P.Omega0 * xFace * Am;
     }
@@ -111,10 +106,135 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
+                                             const T* __restrict__ Qp, T* __restrict__ ELp, int planes, int kbase,
+                                             int k0) {
+  int i, j;
+  const int k = k0 + blockIdx.z;
+  if (!tileCoords(1, P.isize - 2, 1, P.jsize - 2, i, j)) return;
+  const UView<T> U = uview(Uin, P);
+  const View<const T> Q = view<const T>(Qp, P, planes, kbase);
+  const View<T> EL = view(ELp, P, planes, kbase);
+  elec_cell<false>(P, Q, U, EL, i, j, k);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: slopes + edge electric fields + face-B slopes + half-step trace -> W
 //     (reference cpu_v3.cpp:36-361, slope_mhd.h:436-502/598-704, trace_mhd.h:1854-2030)
 // ------------------------------------------------------------------------------------------------
+// trace of one cell: QV(v,i,j,k) primitives, UV(v,i,j,k) conservative state (face fields), ELV(c,i,j,k)
+// edge electric fields, WV(c,i,j,k) the traced state (written).  Used by k_trace (global arrays) and by
+// the fused prim+elec+trace kernel (shared-memory tiles).
+template <bool FAST, typename T, typename QV, typename UV, typename ELV, typename WV>
+__device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, const UV& U, const ELV& EL, const WV& W,
+                                           int i, int j, int k, T dt) {
+  const int gw = P.gw;
+  const T h = T(0.5);
+  const T hst = h * P.slope_type;  // slope_type 0 gives zero slopes through hst = 0
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  // The work is arranged direction by direction (slopes of one direction -> stored -> their share of
+  // the half-step source terms accumulated) so that few values are live at any time.
+
+  // face fields: transverse HALF slopes (slope type capped at 2, slope_mhd.h:636), induction by the 12
+  // edge electric fields of the cell (trace_mhd.h:2006-2011)
+  const T hxst = h * dev::mn(P.slope_type, T(2));
+  const T AL = U(IA, i, j, k), BL = U(IB, i, j, k), CL = U(IC, i, j, k);
+  const T dAx = h * (U(IA, i + 1, j, k) - AL), dBy = h * (U(IB, i, j + 1, k) - BL), dCz = h * (U(IC, i, j, k + 1) - CL);
+  W(W_DALY, i, j, k) = dev::half_slope(hxst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
+  W(W_DALZ, i, j, k) = dev::half_slope(hxst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
+  W(W_DBLX, i, j, k) = dev::half_slope(hxst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
+  W(W_DBLZ, i, j, k) = dev::half_slope(hxst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
+  W(W_DCLX, i, j, k) = dev::half_slope(hxst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
+  W(W_DCLY, i, j, k) = dev::half_slope(hxst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
+  {
+    const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k);
+    const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k);
+    const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k);
+    W(W_AL, i, j, k) = AL + ((GLR - GLL) * dtdy * h - (FLR - FLL) * dtdz * h);
+    W(W_BL, i, j, k) = BL + (-(GRL - GLL) * dtdx * h + (ELR - ELL) * dtdz * h);
+    W(W_CL, i, j, k) = CL + ((FRL - FLL) * dtdx * h - (ERL - ELL) * dtdy * h);
+  }
+
+  // cell-centred state; half-step source terms (trace_mhd.h:1985-2011) accumulated per direction
+  const T r = Q(ID, i, j, k), p = Q(IP, i, j, k), u = Q(IU, i, j, k), v = Q(IV, i, j, k), w = Q(IW, i, j, k);
+  const T A = Q(IA, i, j, k), B = Q(IB, i, j, k), C = Q(IC, i, j, k);
+  const T ir = dev::rcp(r);
+  const T gp = P.gamma0 * p;
+  T sr0, su0, sv0, sw0, sp0, sA0, sB0, sC0;
+  {  // x
+    const T drx = dev::half_slope(hst, Q(ID, i - 1, j, k), r, Q(ID, i + 1, j, k));
+    const T dpx = dev::half_slope(hst, Q(IP, i - 1, j, k), p, Q(IP, i + 1, j, k));
+    const T dux = dev::half_slope(hst, Q(IU, i - 1, j, k), u, Q(IU, i + 1, j, k));
+    const T dvx = dev::half_slope(hst, Q(IV, i - 1, j, k), v, Q(IV, i + 1, j, k));
+    const T dwx = dev::half_slope(hst, Q(IW, i - 1, j, k), w, Q(IW, i + 1, j, k));
+    const T dBx = dev::half_slope(hst, Q(IB, i - 1, j, k), B, Q(IB, i + 1, j, k));
+    const T dCx = dev::half_slope(hst, Q(IC, i - 1, j, k), C, Q(IC, i + 1, j, k));
+    W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
+    W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
+    sr0 = (-u * drx - dux * r) * dtdx;
+    su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx;
+    sv0 = (-u * dvx + A * dBx * ir) * dtdx;
+    sw0 = (-u * dwx + A * dCx * ir) * dtdx;
+    sp0 = (-u * dpx - dux * gp) * dtdx;
+    sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx;
+    sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx;
+  }
+  T shr = T(0), shu = T(0), shv = T(0), shw = T(0), shp = T(0), shA = T(0), shC = T(0);  // shearing box only
+  {  // y
+    const T dry = dev::half_slope(hst, Q(ID, i, j - 1, k), r, Q(ID, i, j + 1, k));
+    const T dpy = dev::half_slope(hst, Q(IP, i, j - 1, k), p, Q(IP, i, j + 1, k));
+    const T duy = dev::half_slope(hst, Q(IU, i, j - 1, k), u, Q(IU, i, j + 1, k));
+    const T dvy = dev::half_slope(hst, Q(IV, i, j - 1, k), v, Q(IV, i, j + 1, k));
+    const T dwy = dev::half_slope(hst, Q(IW, i, j - 1, k), w, Q(IW, i, j + 1, k));
+    const T dAy = dev::half_slope(hst, Q(IA, i, j - 1, k), A, Q(IA, i, j + 1, k));
+    const T dCy = dev::half_slope(hst, Q(IC, i, j - 1, k), C, Q(IC, i, j + 1, k));
+    W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
+    W(W_DWY, i, j, k) = dwy; W(W_DAY, i, j, k) = dAy; W(W_DCY, i, j, k) = dCy;
+    sr0 += (-v * dry - dvy * r) * dtdy;
+    su0 += (-v * duy + B * dAy * ir) * dtdy;
+    sv0 += (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy;
+    sw0 += (-v * dwy + B * dCy * ir) * dtdy;
+    sp0 += (-v * dpy - dvy * gp) * dtdy;
+    sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy;
+    sC0 += (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
+    if (!FAST && P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003 (applied below)
+      const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
+      const T shear = T(-1.5) * P.Omega0 * xPos;
+      shr = shear * dry * dtdy; shu = shear * duy * dtdy; shv = shear * dvy * dtdy; shw = shear * dwy * dtdy;
+      shp = shear * dpy * dtdy; shA = shear * dAy * dtdy; shC = shear * dCy * dtdy;
+    }
+  }
+  {  // z
+    const T drz = dev::half_slope(hst, Q(ID, i, j, k - 1), r, Q(ID, i, j, k + 1));
+    const T dpz = dev::half_slope(hst, Q(IP, i, j, k - 1), p, Q(IP, i, j, k + 1));
+    const T duz = dev::half_slope(hst, Q(IU, i, j, k - 1), u, Q(IU, i, j, k + 1));
+    const T dvz = dev::half_slope(hst, Q(IV, i, j, k - 1), v, Q(IV, i, j, k + 1));
+    const T dwz = dev::half_slope(hst, Q(IW, i, j, k - 1), w, Q(IW, i, j, k + 1));
+    const T dAz = dev::half_slope(hst, Q(IA, i, j, k - 1), A, Q(IA, i, j, k + 1));
+    const T dBz = dev::half_slope(hst, Q(IB, i, j, k - 1), B, Q(IB, i, j, k + 1));
+    W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
+    W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
+    sr0 += (-w * drz - dwz * r) * dtdz;
+    su0 += (-w * duz + C * dAz * ir) * dtdz;
+    sv0 += (-w * dvz + C * dBz * ir) * dtdz;
+    sw0 += (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
+    sp0 += (-w * dpz - dwz * gp) * dtdz;
+    sA0 += (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
+    sB0 += (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
+    if (!FAST && P.Omega0 > T(0)) {
+      const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
+      const T shear = T(-1.5) * P.Omega0 * xPos;
+      sr0 -= shr; su0 -= shu; sv0 -= shv; sw0 -= shw; sp0 -= shp; sA0 -= shA;
+      sB0 += (shear * dAx - T(1.5) * P.Omega0 * A * P.dx) * dtdx + shear * dBz * dtdz;
+      sC0 -= shC;
+    }
+  }
+  W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
+  W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
+  W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
+}
+
 template <typename T, int MINB, bool FAST>
 __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                                     const T* __restrict__ Qp, const T* __restrict__ ELp,
@@ -127,80 +247,108 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
   const View<const T> EL = view<const T>(ELp, P, planes, kbase);
   const View<T> W = view(Wp, P, planes, kbase);
-  const T h = T(0.5);
-  const T hst = h * P.slope_type;  // slope_type 0 gives zero slopes through hst = 0
-  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  trace_cell<FAST>(P, Q, U, EL, W, i, j, k, dt);
+}
 
-  // cell-centred state and its limited HALF slopes
-  T q[8], dx_[8], dy_[8], dz_[8];
+// ------------------------------------------------------------------------------------------------
+// KA: cons->prim + edge electric fields + slopes + trace in ONE kernel (FAST configuration): U -> W.
+//
+// A block of 32 x 8 threads owns the 32 x 8 tile of PRIMITIVE cells around a 30 x 6 tile of traced
+// cells and marches along z.  Every thread converts one cell of the incoming plane (its conservative
+// state was prefetched into registers during the previous plane), the tile of primitives and face
+// fields lives in a 4-plane shared-memory ring, the edge electric fields in a 2-plane ring, and the
+// inner 30 x 6 threads evaluate the 36 limited slopes + the half-step predictor from shared memory.
+// Q and the edge electric field never go to HBM: per cell the kernel reads U once (x 1.4 tile halo)
+// and writes the 38 W components.
+// ------------------------------------------------------------------------------------------------
+struct TraceTile {
+  static constexpr int TW = 30, TH = 6, QX = 32, QY = 8, QCELLS = QX * QY, RING = 4;
+  static constexpr unsigned SMEM = (unsigned)((RING * 8 + RING * 3 + 2 * 3) * QCELLS * sizeof(double));
+};
+template <typename T>
+struct QTileView {  // primitives, ring of 4 planes, [plane][var][QY][QX]
+  T* buf;
+  int ib, jb;
+  __device__ __forceinline__ T& operator()(int v, int i, int j, int k) const {
+    return buf[((k & 3) * 8 + v) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+  }
+};
+template <typename T>
+struct BTileView {  // face fields U(IA..IC), ring of 4 planes
+  T* buf;
+  int ib, jb;
+  __device__ __forceinline__ T& operator()(int v, int i, int j, int k) const {
+    return buf[((k & 3) * 3 + (v - IA)) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+  }
+};
+template <typename T>
+struct ETileView {  // edge electric fields, ring of 2 planes
+  T* buf;
+  int ib, jb;
+  __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
+    return buf[((k & 1) * 3 + c) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T* __restrict__ Wp, int planes,
+              int kbase, int k0, int k1, int lz, T dt) {
+  extern __shared__ unsigned char smemRawA[];
+  T* sm = reinterpret_cast<T*>(smemRawA);
+  const int gw = P.gw;
+  const int ti = threadIdx.x, tj = threadIdx.y;
+  const int ib = gw - 2 + blockIdx.x * TraceTile::TW, jb = gw - 2 + blockIdx.y * TraceTile::TH;  // tile origin
+  const int i = ib + ti, j = jb + tj;
+  const int za = k0 + blockIdx.z * lz, zb = min(za + lz, k1);  // traced planes [za, zb)
+  if (za >= zb) return;
+  const QTileView<T> Q{sm, ib, jb};
+  const BTileView<T> B{sm + TraceTile::RING * 8 * TraceTile::QCELLS, ib, jb};
+  const ETileView<T> EL{sm + TraceTile::RING * 11 * TraceTile::QCELLS, ib, jb};
+  const UView<T> U = uview(Uin, P);
+  const View<T> W = view(Wp, P, planes, kbase);
+
+  // prim range of the reference: 0 .. size-2 (needs the +1 faces)
+  const bool primOK = i <= P.isize - 2 && j <= P.jsize - 2;
+  const bool elecOK = primOK && ti >= 1 && tj >= 1;
+  const bool traceOK = ti >= 1 && ti <= TraceTile::TW && tj >= 1 && tj <= TraceTile::TH && i <= P.isize - gw &&
+                       j <= P.jsize - gw;
+  T u[8], ap = T(0), bp = T(0), cp = T(0);
 #pragma unroll
-  for (int v = 0; v < 8; ++v) {
-    q[v] = Q(v, i, j, k);
-    dx_[v] = dev::half_slope(hst, Q(v, i - 1, j, k), q[v], Q(v, i + 1, j, k));
-    dy_[v] = dev::half_slope(hst, Q(v, i, j - 1, k), q[v], Q(v, i, j + 1, k));
-    dz_[v] = dev::half_slope(hst, Q(v, i, j, k - 1), q[v], Q(v, i, j, k + 1));
+  for (int v = 0; v < 8; ++v) u[v] = T(1);
+  auto load = [&](int q) {  // conservative state of plane q -> registers
+    if (primOK && q <= zb && q <= P.ksize - 2) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, q);
+      ap = U(IA, i + 1, j, q);
+      bp = U(IB, i, j + 1, q);
+      cp = U(IC, i, j, q + 1);
+    }
+  };
+  auto prim = [&](int q) {  // registers -> primitives + face fields of plane q in the rings
+    T qv[8];
+    dev::cons_to_prim_mhd<true>(P, u, ap, bp, cp, dt, qv);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) Q(v, i, j, q) = qv[v];
+    B(IA, i, j, q) = u[IA];
+    B(IB, i, j, q) = u[IB];
+    B(IC, i, j, q) = u[IC];
+  };
+  load(za - 1);
+  prim(za - 1);
+  load(za);
+  prim(za);
+  load(za + 1);
+  __syncthreads();
+  if (elecOK) elec_cell<true>(P, Q, B, EL, i, j, za);
+  for (int k = za; k < zb; ++k) {
+    prim(k + 1);
+    load(k + 2);  // prefetch: consumed by the next iteration, in flight during the trace below
+    __syncthreads();
+    if (elecOK) elec_cell<true>(P, Q, B, EL, i, j, k + 1);
+    __syncthreads();
+    if (traceOK) trace_cell<true>(P, Q, B, EL, W, i, j, k, dt);
   }
-  // face fields and their transverse HALF slopes (slope type capped at 2, slope_mhd.h:636)
-  const T hxst = h * dev::mn(P.slope_type, T(2));
-  T AL = U(IA, i, j, k), BL = U(IB, i, j, k), CL = U(IC, i, j, k);
-  const T AR = U(IA, i + 1, j, k), BR = U(IB, i, j + 1, k), CR = U(IC, i, j, k + 1);
-  const T dALy = dev::half_slope(hxst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
-  const T dALz = dev::half_slope(hxst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
-  const T dBLx = dev::half_slope(hxst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
-  const T dBLz = dev::half_slope(hxst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
-  const T dCLx = dev::half_slope(hxst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
-  const T dCLy = dev::half_slope(hxst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
-
-  // edge-centred electric fields at the 12 edges of the cell, from the elec kernel
-  const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k);
-  const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k);
-  const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k);
-
-  // half-step source terms (trace_mhd.h:1985-2011)
-  T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
-  const T drx = dx_[ID], dpx = dx_[IP], dux = dx_[IU], dvx = dx_[IV], dwx = dx_[IW], dBx = dx_[IB], dCx = dx_[IC];
-  const T dry = dy_[ID], dpy = dy_[IP], duy = dy_[IU], dvy = dy_[IV], dwy = dy_[IW], dAy = dy_[IA], dCy = dy_[IC];
-  const T drz = dz_[ID], dpz = dz_[IP], duz = dz_[IU], dvz = dz_[IV], dwz = dz_[IW], dAz = dz_[IA], dBz = dz_[IB];
-  const T dAx = h * (AR - AL), dBy = h * (BR - BL), dCz = h * (CR - CL);
-  const T ir = dev::rcp(r);
-  const T g = P.gamma0;
-
-  T sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
-  T su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx + (-v * duy + B * dAy * ir) * dtdy + (-w * duz + C * dAz * ir) * dtdz;
-  T sv0 = (-u * dvx + A * dBx * ir) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy + (-w * dvz + C * dBz * ir) * dtdz;
-  T sw0 = (-u * dwx + A * dCx * ir) * dtdx + (-v * dwy + B * dCy * ir) * dtdy + (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
-  T sp0 = (-u * dpx - dux * g * p) * dtdx + (-v * dpy - dvy * g * p) * dtdy + (-w * dpz - dwz * g * p) * dtdz;
-  T sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
-  T sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
-  T sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
-  if (!FAST && P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003
-    const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
-    const T shear = T(-1.5) * P.Omega0 * xPos;
-    sr0 -= shear * dry * dtdy;
-    su0 -= shear * duy * dtdy;
-    sv0 -= shear * dvy * dtdy;
-    sw0 -= shear * dwy * dtdy;
-    sp0 -= shear * dpy * dtdy;
-    sA0 -= shear * dAy * dtdy;
-    sB0 += (shear * dAx - T(1.5) * P.Omega0 * A * P.dx) * dtdx + shear * dBz * dtdz;
-    sC0 -= shear * dCy * dtdy;
-  }
-  AL += (GLR - GLL) * dtdy * h - (FLR - FLL) * dtdz * h;
-  BL += -(GRL - GLL) * dtdx * h + (ELR - ELL) * dtdz * h;
-  CL += (FRL - FLL) * dtdx * h - (ERL - ELL) * dtdy * h;
-
-  W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
-  W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
-  W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
-  W(W_AL, i, j, k) = AL; W(W_BL, i, j, k) = BL; W(W_CL, i, j, k) = CL;
-  W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
-  W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
-  W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
-  W(W_DWY, i, j, k) = dwy; W(W_DAY, i, j, k) = dAy; W(W_DCY, i, j, k) = dCy;
-  W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
-  W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
-  W(W_DALY, i, j, k) = dALy; W(W_DALZ, i, j, k) = dALz; W(W_DBLX, i, j, k) = dBLx; W(W_DBLZ, i, j, k) = dBLz;
-  W(W_DCLX, i, j, k) = dCLx; W(W_DCLY, i, j, k) = dCLy;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1020,6 +1168,10 @@ bool setTuning(const char* key, int value) {
     g_fusedB = value ? 1 : 0;
     return true;
   }
+  if (k == "fused_a") {
+    g_fusedA = value ? 1 : 0;
+    return true;
+  }
   if (value < 2 || value > 8) return false;
   if (k == "flux_minb") g_fluxMinB = value;
   else if (k == "emf_minb") g_emfMinB = value;
@@ -1132,6 +1284,51 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
 }
 
 // ---- fused path ---------------------------------------------------------------------------------
+int g_fusedA = 1;  // run-time knob "fused_a": fused prim+elec+trace kernel when available
+bool fusedTraceRequested() { return g_fusedA != 0; }
+
+template <typename T>
+bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
+  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3) return false;
+  static int ok = -1;
+  if (ok < 0)
+    ok = cudaFuncSetAttribute(k_fused_trace<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TraceTile::SMEM) ==
+                 cudaSuccess
+             ? 1
+             : 0;
+  if (!ok) cudaGetLastError();
+  return ok == 1;
+}
+
+template <typename T>
+void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
+  if (k1 <= k0) return;
+  static int nSM = 0;
+  if (nSM == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    if (nSM <= 0) nSM = 148;
+  }
+  const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // traced cells gw-1 .. size-gw
+  const int ntx = (n + TraceTile::TW - 1) / TraceTile::TW, nty = (m + TraceTile::TH - 1) / TraceTile::TH;
+  const int planes = k1 - k0, slots = 2 * nSM;  // two resident blocks per SM
+  int bestNz = 1;
+  double bestCost = 1e300;
+  for (int nz = 1; nz <= planes; ++nz) {
+    const int lz = (planes + nz - 1) / nz;
+    if (lz < 8 && nz > 1) break;
+    const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
+    const double cost = (double)((blocks + slots - 1) / slots) * (lz + 2.5);
+    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
+  }
+  const int lz = (planes + bestNz - 1) / bestNz;
+  const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
+  k_fused_trace<T><<<grid, dim3(TraceTile::QX, TraceTile::QY, 1), TraceTile::SMEM, s>>>(P, U, sc.W, sc.planes, sc.kbase,
+                                                                                         k0, k1, lz, dt);
+  ++g_launches;
+}
+
 
 template <typename T>
 struct FusedSel { typedef FusedTile<T, 14, 7, 512> Cfg; };
@@ -1189,8 +1386,14 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
   CUtensorMap map;
   memcpy(&map, sc.mapW, sizeof(map));
   k_fused_flux_emf_update<T, C><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d);
-  k_copy_outside_box<T><<<gridFor(P.isize, P.jsize, kb - ka), blockShape(), 0, s>>>(P, Uold, Unew, ka);
-  g_launches += 2;
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::copyOutsideBox(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  k_copy_outside_box<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, k0);
+  ++g_launches;
 }
 
 template <typename T>

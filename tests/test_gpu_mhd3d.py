@@ -178,17 +178,21 @@ def test_device_probes_vs_oracle(native, oracle64):
     ((17, 12, 8), {}, 0),                                    # odd row length: no TMA descriptor, separate kernels
 ])
 def test_fused_kernel_equals_separate_kernels(native, n, over, chunk):
-    """The fused flux+emf+update kernel (TMA-staged W tiles, z-marching blocks, ticket-scheduled warp
+    """Both fused kernels (prim+elec+trace: shared-memory rings; flux+emf+update: see below) against the
+    separate kernels.  The fused flux+emf+update kernel (TMA-staged W tiles, z-marching blocks, ticket-scheduled warp
     tasks) runs the same device functions as k_flux/k_emf/k_update; the compiler contracts a few
     multiply-adds differently in the two kernels, so agreement is to the last bits, not bitwise."""
     from ramsesgpu_b200 import set_tuning
     ini = ot3d_ini(n, **over)
     try:
+        set_tuning("fused_a", 0)
         set_tuning("fused_b", 0)
         ref, tr, dtr, gw = run_gpu_steps(ini, 4, chunk=chunk)
+        set_tuning("fused_a", 1)
         set_tuning("fused_b", 1)
         got, tg, dtg, _ = run_gpu_steps(ini, 4, chunk=chunk)
     finally:
+        set_tuning("fused_a", 1)
         set_tuning("fused_b", 1)
     assert np.allclose(dtr, dtg, rtol=1e-14, atol=0)
     assert (np.abs(ref - got) <= 1e-14 * np.abs(ref).max()).all()      # ghosts included
