@@ -25,6 +25,7 @@ int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
+int g_traceQY = 8;  // run-time knob "trace_qy": 8 (two 256-thread blocks per SM) or 16 (one 512-thread block)
 
 namespace {
 
@@ -261,11 +262,13 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
 // Q and the edge electric field never go to HBM: per cell the kernel reads U once (x 1.4 tile halo)
 // and writes the 38 W components.
 // ------------------------------------------------------------------------------------------------
-struct TraceTile {
-  static constexpr int TW = 30, TH = 6, QX = 32, QY = 8, QCELLS = QX * QY, RING = 4;
+template <int QY_>
+struct TraceTileT {
+  static constexpr int QX = 32, QY = QY_, TW = QX - 2, TH = QY - 2, QCELLS = QX * QY, RING = 4;
+  static constexpr int THREADS = QX * QY, MINB = 512 / THREADS;
   static constexpr unsigned SMEM = (unsigned)((RING * 8 + RING * 3 + 2 * 3) * QCELLS * sizeof(double));
 };
-template <typename T>
+template <typename T, typename TraceTile>
 struct QTileView {  // primitives, ring of 4 planes, [plane][var][QY][QX]
   T* buf;
   int ib, jb;
@@ -273,7 +276,7 @@ struct QTileView {  // primitives, ring of 4 planes, [plane][var][QY][QX]
     return buf[((k & 3) * 8 + v) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
   }
 };
-template <typename T>
+template <typename T, typename TraceTile>
 struct BTileView {  // face fields U(IA..IC), ring of 4 planes
   T* buf;
   int ib, jb;
@@ -281,7 +284,7 @@ struct BTileView {  // face fields U(IA..IC), ring of 4 planes
     return buf[((k & 3) * 3 + (v - IA)) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
   }
 };
-template <typename T>
+template <typename T, typename TraceTile>
 struct ETileView {  // edge electric fields, ring of 2 planes
   T* buf;
   int ib, jb;
@@ -290,8 +293,8 @@ struct ETileView {  // edge electric fields, ring of 2 planes
   }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, typename TraceTile>
+__global__ void __launch_bounds__(TraceTile::THREADS, TraceTile::MINB)
 k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T* __restrict__ Wp, int planes,
               int kbase, int k0, int k1, int lz, T dt) {
   extern __shared__ unsigned char smemRawA[];
@@ -302,9 +305,9 @@ k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T
   const int i = ib + ti, j = jb + tj;
   const int za = k0 + blockIdx.z * lz, zb = min(za + lz, k1);  // traced planes [za, zb)
   if (za >= zb) return;
-  const QTileView<T> Q{sm, ib, jb};
-  const BTileView<T> B{sm + TraceTile::RING * 8 * TraceTile::QCELLS, ib, jb};
-  const ETileView<T> EL{sm + TraceTile::RING * 11 * TraceTile::QCELLS, ib, jb};
+  const QTileView<T, TraceTile> Q{sm, ib, jb};
+  const BTileView<T, TraceTile> B{sm + TraceTile::RING * 8 * TraceTile::QCELLS, ib, jb};
+  const ETileView<T, TraceTile> EL{sm + TraceTile::RING * 11 * TraceTile::QCELLS, ib, jb};
   const UView<T> U = uview(Uin, P);
   const View<T> W = view(Wp, P, planes, kbase);
 
@@ -831,15 +834,27 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   }
 }
 
-// ghost cells outside the update box keep the old values (the separate k_update does this itself)
+// ghost cells outside the update box keep the old values (the separate k_update does this itself).
+// One thread per ghost cell of a plane: the gw lower and gw-1 upper ghost rows (full width), then the
+// gw lower and gw-1 upper ghost columns of the remaining rows.
 template <typename T>
-__global__ void __launch_bounds__(BX) k_copy_outside_box(const __grid_constant__ KParams<T> P,
-                                                         const T* __restrict__ Uold, T* __restrict__ Unew, int k0) {
+__global__ void __launch_bounds__(256) k_copy_outside_box(const __grid_constant__ KParams<T> P,
+                                                          const T* __restrict__ Uold, T* __restrict__ Unew, int k0) {
+  const int gw = P.gw, ng = 2 * gw - 1;  // ghost rows / columns outside the box per direction
+  const int nRowCells = ng * P.isize, nColCells = ng * (P.jsize - ng);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nRowCells + nColCells) return;
   int i, j;
-  const int k = k0 + blockIdx.z;
-  if (!tileCoords(0, P.isize, 0, P.jsize, i, j)) return;
-  const int gw = P.gw;
-  if (i >= gw && i <= P.isize - gw && j >= gw && j <= P.jsize - gw) return;
+  if (t < nRowCells) {
+    const int r = t / P.isize;
+    i = t - r * P.isize;
+    j = (r < gw) ? r : P.jsize - gw + 1 + (r - gw);
+  } else {
+    const int q = t - nRowCells, r = q / ng, c = q - r * ng;
+    j = gw + r;
+    i = (c < gw) ? c : P.isize - gw + 1 + (c - gw);
+  }
+  const int k = k0 + blockIdx.y;
   const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
   const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
   for (int v = 0; v < P.nvar; ++v) Unew[v * comp + idx] = Uold[v * comp + idx];
@@ -1172,6 +1187,11 @@ bool setTuning(const char* key, int value) {
     g_fusedA = value ? 1 : 0;
     return true;
   }
+  if (k == "trace_qy") {
+    if (value != 8 && value != 16) return false;
+    g_traceQY = value;
+    return true;
+  }
   if (value < 2 || value > 8) return false;
   if (k == "flux_minb") g_fluxMinB = value;
   else if (k == "emf_minb") g_emfMinB = value;
@@ -1292,12 +1312,34 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3) return false;
   static int ok = -1;
   if (ok < 0)
-    ok = cudaFuncSetAttribute(k_fused_trace<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TraceTile::SMEM) ==
-                 cudaSuccess
+    ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<8>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<16>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<16>::SMEM) == cudaSuccess)
              ? 1
              : 0;
   if (!ok) cudaGetLastError();
   return ok == 1;
+}
+
+template <typename T, typename TT>
+static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T>& sc, int k0, int k1, T dt, int nSM,
+                             cudaStream_t s) {
+  const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // traced cells gw-1 .. size-gw
+  const int ntx = (n + TT::TW - 1) / TT::TW, nty = (m + TT::TH - 1) / TT::TH;
+  const int planes = k1 - k0, slots = TT::MINB * nSM;  // resident blocks
+  int bestNz = 1;
+  double bestCost = 1e300;
+  for (int nz = 1; nz <= planes; ++nz) {
+    const int lz = (planes + nz - 1) / nz;
+    if (lz < 8 && nz > 1) break;
+    const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
+    const double cost = (double)((blocks + slots - 1) / slots) * (lz + 2.5);
+    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
+  }
+  const int lz = (planes + bestNz - 1) / bestNz;
+  const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
+  k_fused_trace<T, TT><<<grid, dim3(TT::QX, TT::QY, 1), TT::SMEM, s>>>(P, U, sc.W, sc.planes, sc.kbase, k0, k1, lz, dt);
 }
 
 template <typename T>
@@ -1310,25 +1352,10 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     if (nSM <= 0) nSM = 148;
   }
-  const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // traced cells gw-1 .. size-gw
-  const int ntx = (n + TraceTile::TW - 1) / TraceTile::TW, nty = (m + TraceTile::TH - 1) / TraceTile::TH;
-  const int planes = k1 - k0, slots = 2 * nSM;  // two resident blocks per SM
-  int bestNz = 1;
-  double bestCost = 1e300;
-  for (int nz = 1; nz <= planes; ++nz) {
-    const int lz = (planes + nz - 1) / nz;
-    if (lz < 8 && nz > 1) break;
-    const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
-    const double cost = (double)((blocks + slots - 1) / slots) * (lz + 2.5);
-    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
-  }
-  const int lz = (planes + bestNz - 1) / bestNz;
-  const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
-  k_fused_trace<T><<<grid, dim3(TraceTile::QX, TraceTile::QY, 1), TraceTile::SMEM, s>>>(P, U, sc.W, sc.planes, sc.kbase,
-                                                                                         k0, k1, lz, dt);
+  if (g_traceQY == 16) launchFusedTrace<T, TraceTileT<16>>(P, U, sc, k0, k1, dt, nSM, s);
+  else launchFusedTrace<T, TraceTileT<8>>(P, U, sc, k0, k1, dt, nSM, s);
   ++g_launches;
 }
-
 
 template <typename T>
 struct FusedSel { typedef FusedTile<T, 14, 7, 512> Cfg; };
@@ -1392,7 +1419,8 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
 template <typename T>
 void MhdKernels<T>::copyOutsideBox(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_copy_outside_box<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, k0);
+  const int ng = 2 * P.gw - 1, cells = ng * P.isize + ng * (P.jsize - ng);
+  k_copy_outside_box<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
   ++g_launches;
 }
 
