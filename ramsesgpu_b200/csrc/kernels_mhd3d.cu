@@ -628,12 +628,15 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
 template <typename T, int TW_, int TH_, int THREADS_>
 struct FusedTile {
   static constexpr int TW = TW_, TH = TH_, THREADS = THREADS_;
-  static constexpr int WX = TW + 2, WY = TH + 2, WCELLS = WX * WY;  // W tile with one halo cell on every side
+  // W tile with one halo cell on every side.  TMA wants the first element of a box row on a 16-byte
+  // boundary: the box starts at the even cell index at or below i0-1 and is TW+3 (rounded up to even)
+  // reals wide
+  static constexpr int WX = (TW + 3) / 2 * 2, WY = TH + 2, WCELLS = WX * WY;  // even TW: i0-1 is even (gw = 3)
   static constexpr int PX = TW + 1, PY = TH + 1;                     // low faces/edges of the cells + the closing ones
   // a warp task covers two rows of 16 positions: every half warp reads 16 consecutive reals of one
   // tile row, which keeps the 64-bit shared-memory loads free of bank conflicts
   static constexpr int PXP = 16, NCH = PY / 2, NPOSP = PXP * PY;
-  static_assert(WX == 16 && PY % 2 == 0, "tile shape");
+  static_assert(PX <= PXP && PY % 2 == 0, "tile shape");
   static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
   static constexpr int NT = 1 + 7 * NCH;                             // tasks per plane
   static constexpr int LZMAX = 96;                                   // planes per block (counter arrays)
@@ -749,7 +752,8 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   const int nPl = fhi - za + 1 + (zb > fhi ? 1 : 0);  // + the pseudo plane that only updates plane kN
   const int tid = threadIdx.x, lane = tid & 31;
 
-  const WTileView<T, C> W{wbuf, i0 - 1, j0 - 1};
+  const int ib = (i0 - 1) & ~1;  // even: 16-byte aligned box rows
+  const WTileView<T, C> W{wbuf, ib, j0 - 1};
   const FETileView<T, C> F{fe, i0, j0, 0}, E{fe, i0, j0, 15};
   const UView<T> U = uview(Uold, P);
 
@@ -765,7 +769,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   auto loadPlane = [&](int q) {  // one thread
     uint64_t* bar = &bars[q - (za - 1)];
     tma::mbarExpectTx(bar, C::W_BYTES);
-    tma::loadTile4D(wbuf + ((unsigned)q % 3u) * C::W_STRIDE, &mapW, bar, i0 - 1, j0 - 1, q - kbase, 0);
+    tma::loadTile4D(wbuf + ((unsigned)q % 3u) * C::W_STRIDE, &mapW, bar, ib, j0 - 1, q - kbase, 0);
   };
   if (tid == 0) {
     loadPlane(za - 1);
@@ -1358,13 +1362,14 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
 }
 
 template <typename T>
-struct FusedSel { typedef FusedTile<T, 14, 7, 512> Cfg; };
+struct FusedSel { typedef FusedTile<T, 15, 7, 512> Cfg; };
 
 template <typename T>
 void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   typedef typename FusedSel<T>::Cfg C;
   sc.fused = 0;
   if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3 || sc.W == nullptr) return;
+  if (C::TW % 2 == 0 && (P.gw - 1) % 2 != 0) return;  // box rows must start on an even cell index
   CUtensorMap map;
   if (!tma::encodeTile4D(&map, sc.W, (int)sizeof(T), P.isize, P.jsize, sc.planes, NW_MHD, C::WX, C::WY)) return;
   static_assert(sizeof(CUtensorMap) <= sizeof(sc.mapW), "tensor map storage");
