@@ -104,6 +104,19 @@ int rg_synchronize(rg_handle h);
 int rg_steps_from_host(rg_handle h, const void* host_in, void* host_out, size_t bytes, int n_steps,
                        double* t_out, double* dt_last);
 
+/* n_jobs INDEPENDENT one-step jobs (ensemble members, parameter scans sharing one .ini):
+ * host_out[j] = one rg_one_step of host_in[j] from (nStep, t) = (0, 0); dt_out[j] (optional) = the
+ * step's dt.  Same results, bit for bit, as n_jobs calls of rg_steps_from_host(.., 1, ..), but the H2D
+ * copy of job j+1, the step of job j and the D2H copy of job j-1 run concurrently on three streams
+ * (two device buffer pairs in rotation; pinned host buffers are needed for the overlap).  A host
+ * buffer may be reused by jobs j and j+2. */
+int rg_steps_from_host_batch(rg_handle h, int n_jobs, const void* const* host_in, void* const* host_out,
+                             size_t bytes, double* dt_out);
+
+/* page-locked host memory for the host-buffer calls above (cudaHostAlloc / cudaFreeHost) */
+int rg_alloc_pinned(size_t bytes, void** out);
+int rg_free_pinned(void* p);
+
 int rg_get_stats(rg_handle h, rg_stats* out);
 int rg_reset_launch_count(void);
 /* z planes per pipeline chunk (0 = automatic: whole slab if the scratch fits in device memory) */

@@ -47,6 +47,9 @@ SIGNATURES = {
     "rg_copy_from_host": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t]),
     "rg_synchronize": (C.c_int, [H]),
     "rg_steps_from_host": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rg_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rg_free_pinned": (C.c_int, [C.c_void_p]),
+    "rg_steps_from_host_batch": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_double)]),
     "rg_get_stats": (C.c_int, [H, C.POINTER(RgStats)]),
     "rg_reset_launch_count": (C.c_int, []),
     "rg_set_chunk_planes": (C.c_int, [H, C.c_int]),

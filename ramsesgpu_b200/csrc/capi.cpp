@@ -164,6 +164,26 @@ int rg_steps_from_host(rg_handle h, const void* in, void* outp, size_t bytes, in
   RG_TRY(h, h->run->stepsFromHost(in, outp, bytes, n, t, dt))
 }
 
+int rg_steps_from_host_batch(rg_handle h, int n_jobs, const void* const* in, void* const* outp, size_t bytes,
+                              double* dt_out) {
+  if (n_jobs < 0 || (n_jobs > 0 && (!in || !outp))) return fail(RG_ERR_INVALID, "null buffer list");
+  for (int j = 0; j < n_jobs; ++j)
+    if (!in[j] || !outp[j]) return fail(RG_ERR_INVALID, "null buffer");
+  RG_TRY(h, h->run->stepsFromHostBatch(n_jobs, in, outp, bytes, dt_out))
+}
+
+int rg_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return fail(RG_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(RG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return RG_OK;
+}
+int rg_free_pinned(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) return fail(RG_ERR_CUDA, "cudaFreeHost failed");
+  return RG_OK;
+}
+
 int rg_get_stats(rg_handle h, rg_stats* out) {
   if (!out) return fail(RG_ERR_INVALID, "null stats");
   RG_TRY(h, {

@@ -109,6 +109,14 @@ class RunImpl final : public Run {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     freeScratch();
     for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
+    for (int b = 0; b < 2; ++b) {
+      if (batchBuf_[b]) cudaFree(batchBuf_[b]);
+      if (evH2D_[b]) cudaEventDestroy(evH2D_[b]);
+      if (evD2H_[b]) cudaEventDestroy(evD2H_[b]);
+      if (evStepDone_[b]) cudaEventDestroy(evStepDone_[b]);
+    }
+    if (h2dStream_) cudaStreamDestroy(h2dStream_);
+    if (d2hStream_) cudaStreamDestroy(d2hStream_);
     cudaFree(dMax_);
     cudaFreeHost(hMax_);
     cudaEventDestroy(ev0_);
@@ -325,6 +333,75 @@ class RunImpl final : public Run {
     RG_CUDA(cudaStreamSynchronize(stream_));
     if (tOut) *tOut = t;
     if (dtLast) *dtLast = dt;
+  }
+
+  // n independent one-step jobs out[j] = step(in[j]) from HOST buffers.  The copy engines and the SMs
+  // work concurrently: H2D of job j+1 (copy stream), the step of job j (compute stream) and D2H of
+  // job j-1 (second copy stream) overlap, with two device buffer pairs in rotation (PCIe is full
+  // duplex, so the steady state costs max(H2D, D2H, step) per job instead of their sum).  Results
+  // are bitwise those of n calls of stepsFromHost(in[j], out[j], bytes, 1).
+  void stepsFromHostBatch(int nJobs, const void* const* in, void* const* out, size_t bytes, double* dtOut) override {
+    checkBytes(bytes);
+    if (nJobs <= 0) return;
+    ensureBatchResources();
+    T* saved[2] = {dU_[0], dU_[1]};
+    T* pairIn[2] = {saved[0], batchBuf_[0]};
+    T* pairOut[2] = {saved[1], batchBuf_[1]};
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    auto enqueueH2D = [&](int j) {
+      const int s = j & 1;
+      if (j >= 2) RG_CUDA(cudaStreamWaitEvent(h2dStream_, evStepDone_[s], 0));  // job j-2 no longer reads pairIn[s]
+      RG_CUDA(cudaMemcpyAsync(pairIn[s], in[j], bytes, cudaMemcpyHostToDevice, h2dStream_));
+      RG_CUDA(cudaEventRecord(evH2D_[s], h2dStream_));
+    };
+    try {
+      enqueueH2D(0);
+      for (int j = 0; j < nJobs; ++j) {
+        const int s = j & 1;
+        if (j + 1 < nJobs) enqueueH2D(j + 1);  // before the host blocks on this job's dt read-back
+        RG_CUDA(cudaStreamWaitEvent(stream_, evH2D_[s], 0));
+        if (j >= 2) RG_CUDA(cudaStreamWaitEvent(stream_, evD2H_[s], 0));  // job j-2 has left pairOut[s]
+        dU_[0] = pairIn[s];
+        dU_[1] = pairOut[s];
+        invalidate(0);
+        invalidate(1);
+        int nStep = 0;
+        double t = 0.0, dt = 0.0;
+        oneStepIntegration(nStep, t, dt);
+        if (haloDone_[1]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
+        RG_CUDA(cudaEventRecord(evStepDone_[s], stream_));
+        RG_CUDA(cudaStreamWaitEvent(d2hStream_, evStepDone_[s], 0));
+        RG_CUDA(cudaMemcpyAsync(out[j], pairOut[s], bytes, cudaMemcpyDeviceToHost, d2hStream_));
+        RG_CUDA(cudaEventRecord(evD2H_[s], d2hStream_));
+        if (dtOut) dtOut[j] = dt;
+      }
+      RG_CUDA(cudaStreamSynchronize(d2hStream_));
+      RG_CUDA(cudaStreamSynchronize(stream_));
+    } catch (...) {
+      cudaDeviceSynchronize();
+      dU_[0] = saved[0];
+      dU_[1] = saved[1];
+      invalidate(0);
+      invalidate(1);
+      throw;
+    }
+    dU_[0] = saved[0];
+    dU_[1] = saved[1];
+    invalidate(0);
+    invalidate(1);
+  }
+
+  void ensureBatchResources() {
+    if (batchBuf_[0]) return;
+    for (int b = 0; b < 2; ++b) {
+      RG_CUDA(cudaMalloc(&batchBuf_[b], elems_ * sizeof(T)));
+      RG_CUDA(cudaEventCreateWithFlags(&evH2D_[b], cudaEventDisableTiming));
+      RG_CUDA(cudaEventCreateWithFlags(&evD2H_[b], cudaEventDisableTiming));
+      RG_CUDA(cudaEventCreateWithFlags(&evStepDone_[b], cudaEventDisableTiming));
+    }
+    RG_CUDA(cudaStreamCreateWithFlags(&h2dStream_, cudaStreamNonBlocking));
+    RG_CUDA(cudaStreamCreateWithFlags(&d2hStream_, cudaStreamNonBlocking));
+    deviceBytes_ += 2 * elems_ * sizeof(T);
   }
 
   Stats stats() const override {
@@ -768,6 +845,10 @@ class RunImpl final : public Run {
   int rank_, nranks_;
   size_t cells_ = 0, elems_ = 0, deviceBytes_ = 0, scratchBytes_ = 0;
   T* dU_[2] = {nullptr, nullptr};
+  // stepsFromHostBatch: second device buffer pair, copy streams, events (created on first use)
+  T* batchBuf_[2] = {nullptr, nullptr};
+  cudaStream_t h2dStream_ = nullptr, d2hStream_ = nullptr;
+  cudaEvent_t evH2D_[2] = {nullptr, nullptr}, evD2H_[2] = {nullptr, nullptr}, evStepDone_[2] = {nullptr, nullptr};
   MhdScratch<T> sc_;
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;

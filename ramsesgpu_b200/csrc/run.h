@@ -67,6 +67,10 @@ class Run {
   virtual void stepsFromHost(const void* hostIn, void* hostOut, size_t bytes, int nSteps, double* tOut,
                              double* dtLast) = 0;
 
+  // n independent one-step jobs from host buffers with copy/compute overlap (see rg_steps_from_host_batch)
+  virtual void stepsFromHostBatch(int nJobs, const void* const* in, void* const* out, size_t bytes,
+                                  double* dtOut) = 0;
+
   virtual Stats stats() const = 0;
   // device timing of a region, total and per kernel family (see rg_profile_begin/end)
   virtual void profileBegin() = 0;

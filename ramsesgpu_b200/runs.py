@@ -102,6 +102,17 @@ class HydroRunBase:
                                          nsteps, C.byref(t), C.byref(dt)))
         return t.value, dt.value
 
+    def steps_from_host_batch(self, host_in, host_out):
+        """Independent one-step jobs host_out[j] = step(host_in[j]) with copy/compute overlap
+        (rg_steps_from_host_batch); returns the dt of every job."""
+        n = len(host_in)
+        assert len(host_out) == n
+        ins = (C.c_void_p * n)(*[a.ctypes.data for a in host_in])
+        outs = (C.c_void_p * n)(*[a.ctypes.data for a in host_out])
+        dts = (C.c_double * n)()
+        check(self._L.rg_steps_from_host_batch(self._h, n, ins, outs, host_in[0].nbytes, dts))
+        return list(dts)
+
     def synchronize(self):
         check(self._L.rg_synchronize(self._h))
 
@@ -168,6 +179,30 @@ class HydroRunGodunov(HydroRunBase):
 
 class MHDRunGodunov(MHDRunBase):
     pass
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (rg_alloc_pinned); free() or garbage collection releases it."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._L = _lib.load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(self._L.rg_alloc_pinned(n, C.byref(p)))
+        self._p = p
+        self.array = np.frombuffer((C.c_char * n).from_address(p.value), dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            self._L.rg_free_pinned(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def set_tuning(key, value):
