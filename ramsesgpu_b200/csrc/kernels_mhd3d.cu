@@ -293,7 +293,7 @@ struct ETileView {  // edge electric fields, ring of 2 planes
   }
 };
 
-template <typename T, typename TraceTile>
+template <typename T, typename TraceTile, bool FAST>
 __global__ void __launch_bounds__(TraceTile::THREADS, TraceTile::MINB)
 k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T* __restrict__ Wp, int planes,
               int kbase, int k0, int k1, int lz, T dt) {
@@ -330,7 +330,7 @@ k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T
   };
   auto prim = [&](int q) {  // registers -> primitives + face fields of plane q in the rings
     T qv[8];
-    dev::cons_to_prim_mhd<true>(P, u, ap, bp, cp, dt, qv);
+    dev::cons_to_prim_mhd<FAST>(P, u, ap, bp, cp, dt, qv);
 #pragma unroll
     for (int v = 0; v < 8; ++v) Q(v, i, j, q) = qv[v];
     B(IA, i, j, q) = u[IA];
@@ -343,14 +343,14 @@ k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T
   prim(za);
   load(za + 1);
   __syncthreads();
-  if (elecOK) elec_cell<true>(P, Q, B, EL, i, j, za);
+  if (elecOK) elec_cell<FAST>(P, Q, B, EL, i, j, za);
   for (int k = za; k < zb; ++k) {
     prim(k + 1);
     load(k + 2);  // prefetch: consumed by the next iteration, in flight during the trace below
     __syncthreads();
-    if (elecOK) elec_cell<true>(P, Q, B, EL, i, j, k + 1);
+    if (elecOK) elec_cell<FAST>(P, Q, B, EL, i, j, k + 1);
     __syncthreads();
-    if (traceOK) trace_cell<true>(P, Q, B, EL, W, i, j, k, dt);
+    if (traceOK) trace_cell<FAST>(P, Q, B, EL, W, i, j, k, dt);
   }
 }
 
@@ -1313,12 +1313,16 @@ bool fusedTraceRequested() { return g_fusedA != 0; }
 
 template <typename T>
 bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
-  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3) return false;
+  // every FP64 3D MHD configuration: the FAST instantiation for the headline one, the generic one
+  // (rotating frame, isothermal, other Riemann solvers) otherwise
+  if (sizeof(T) != 8 || P.dim != 3) return false;
   static int ok = -1;
   if (ok < 0)
-    ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<8>::SMEM) == cudaSuccess &&
-          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<16>>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<8>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<16>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<16>::SMEM) == cudaSuccess)
              ? 1
              : 0;
@@ -1326,7 +1330,7 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   return ok == 1;
 }
 
-template <typename T, typename TT>
+template <typename T, typename TT, bool FAST>
 static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T>& sc, int k0, int k1, T dt, int nSM,
                              cudaStream_t s) {
   const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // traced cells gw-1 .. size-gw
@@ -1343,7 +1347,8 @@ static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T
   }
   const int lz = (planes + bestNz - 1) / bestNz;
   const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
-  k_fused_trace<T, TT><<<grid, dim3(TT::QX, TT::QY, 1), TT::SMEM, s>>>(P, U, sc.W, sc.planes, sc.kbase, k0, k1, lz, dt);
+  k_fused_trace<T, TT, FAST><<<grid, dim3(TT::QX, TT::QY, 1), TT::SMEM, s>>>(P, U, sc.W, sc.planes, sc.kbase, k0, k1, lz,
+                                                                           dt);
 }
 
 template <typename T>
@@ -1356,8 +1361,9 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     if (nSM <= 0) nSM = 148;
   }
-  if (g_traceQY == 16) launchFusedTrace<T, TraceTileT<16>>(P, U, sc, k0, k1, dt, nSM, s);
-  else launchFusedTrace<T, TraceTileT<8>>(P, U, sc, k0, k1, dt, nSM, s);
+  if (!fastPath(P)) launchFusedTrace<T, TraceTileT<8>, false>(P, U, sc, k0, k1, dt, nSM, s);
+  else if (g_traceQY == 16) launchFusedTrace<T, TraceTileT<16>, true>(P, U, sc, k0, k1, dt, nSM, s);
+  else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
   ++g_launches;
 }
 

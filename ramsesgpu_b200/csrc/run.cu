@@ -747,9 +747,13 @@ class RunImpl final : public Run {
       const int kb = std::min(ka + chunkPlanes_, kN + 1), fhi = std::min(kb, kN);
       MhdScratch<T> sc = sc_;
       sc.kbase = ka - 2;
-      phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
-      phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
-      phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      if (fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_)) {
+        phase(PH_TRACE, [&] { MhdKernels<T>::fusedTrace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      } else {
+        phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
+        phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
+        phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      }
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_UPDATE, [&] {
