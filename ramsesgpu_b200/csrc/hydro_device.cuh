@@ -172,11 +172,13 @@ __device__ __forceinline__ void riemann_hllc(const KParams<T>& P, const HState<T
 }
 
 // dispatch, reference riemann.h:388-401
-template <typename T>
+// RS >= 0: solver fixed at compile time (one solver body per kernel instead of three per call site)
+template <int RS = -1, typename T>
 __device__ __forceinline__ void riemann_hydro(const KParams<T>& P, const HState<T>& L, const HState<T>& R, T (&flux)[5]) {
-  if (P.riemannSolver == RS_HLLC) riemann_hllc(P, L, R, flux);
-  else if (P.riemannSolver == RS_APPROX) riemann_approx(P, L, R, flux);
-  else if (P.riemannSolver == RS_HLL) riemann_hll_hydro(P, L, R, flux);
+  const int rs = (RS >= 0) ? RS : P.riemannSolver;
+  if (rs == RS_HLLC) riemann_hllc(P, L, R, flux);
+  else if (rs == RS_APPROX) riemann_approx(P, L, R, flux);
+  else if (rs == RS_HLL) riemann_hll_hydro(P, L, R, flux);
   else {
 #pragma unroll
     for (int n = 0; n < 5; ++n) flux[n] = T(0);

@@ -80,19 +80,19 @@ __device__ __forceinline__ dev::HState<T> hydro_face(const KParams<T>& P, const 
 }
 
 // flux through the LOW face of cell (i,j,k) along DIR, in physical component order
-template <typename T, int DIR>
+template <typename T, int DIR, int RS>
 __device__ __forceinline__ void hydro_low_flux(const KParams<T>& P, const View<const T>& W, int i, int j, int k, T (&f)[5]) {
   const dev::HState<T> L = hydro_face<T, DIR>(P, W, i - (DIR == 0), j - (DIR == 1), k - (DIR == 2), T(1));
   const dev::HState<T> R = hydro_face<T, DIR>(P, W, i, j, k, T(-1));
   T fr[5];
-  dev::riemann_hydro(P, L, R, fr);
+  dev::riemann_hydro<RS>(P, L, R, fr);
   f[ID] = fr[ID]; f[IP] = fr[IP];
   f[IU] = (DIR == 0) ? fr[IU] : (DIR == 1) ? fr[IV] : fr[IW];
   f[IV] = (DIR == 1) ? fr[IU] : fr[IV];
   f[IW] = (DIR == 2) ? fr[IU] : fr[IW];
 }
 
-template <typename T>
+template <typename T, int RS>
 __global__ void __launch_bounds__(BX) k_hydro_flux_update(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
                                                           T* __restrict__ Unew, const T* __restrict__ Wp, int planes,
                                                           int kbase, int k0, T dt, unsigned long long* __restrict__ slots) {
@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(BX) k_hydro_flux_update(const __grid_constant_
       const View<const T> W = view<const T>(Wp, P, planes, kbase);
       const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
       T fxl[5], fyl[5], fzl[5], fxh[5], fyh[5], fzh[5];
-      hydro_low_flux<T, 0>(P, W, i, j, k, fxl);
-      hydro_low_flux<T, 1>(P, W, i, j, k, fyl);
-      hydro_low_flux<T, 2>(P, W, i, j, k, fzl);
-      hydro_low_flux<T, 0>(P, W, i + 1, j, k, fxh);
-      hydro_low_flux<T, 1>(P, W, i, j + 1, k, fyh);
-      hydro_low_flux<T, 2>(P, W, i, j, k + 1, fzh);
+      hydro_low_flux<T, 0, RS>(P, W, i, j, k, fxl);
+      hydro_low_flux<T, 1, RS>(P, W, i, j, k, fyl);
+      hydro_low_flux<T, 2, RS>(P, W, i, j, k, fzl);
+      hydro_low_flux<T, 0, RS>(P, W, i + 1, j, k, fxh);
+      hydro_low_flux<T, 1, RS>(P, W, i, j + 1, k, fyh);
+      hydro_low_flux<T, 2, RS>(P, W, i, j, k + 1, fzh);
 #pragma unroll
       for (int v = 0; v < 5; ++v) {  // summation order of the reference's serial scatter
         T s = un[v];
@@ -175,7 +175,14 @@ template <typename T>
 void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, const T* W, int planes, int kbase, int k0,
                                  int k1, T dt, unsigned long long* slots, cudaStream_t s) {
   if (k1 <= k0) return;
-  k_hydro_flux_update<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots);
+  const dim3 g = gridFor(P.isize, P.jsize, k1 - k0);
+  // one instantiation per Riemann solver: a single solver body in the kernel instead of three per face
+  switch (P.riemannSolver) {
+    case RS_HLLC: k_hydro_flux_update<T, RS_HLLC><<<g, blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots); break;
+    case RS_HLL: k_hydro_flux_update<T, RS_HLL><<<g, blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots); break;
+    case RS_APPROX: k_hydro_flux_update<T, RS_APPROX><<<g, blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots); break;
+    default: k_hydro_flux_update<T, -1><<<g, blockShape(), 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, dt, slots); break;
+  }
   ++g_launches;
 }
 template <typename T>

@@ -26,7 +26,8 @@ __device__ __forceinline__ double rcp(double x) {
   e = fma(e, e, e);
   return fma(r, e, r);                                     // cubic step: 2^-20 -> 2^-60 + rounding
 }
-__device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+// FP32: the MUFU results (<= 2 ulp) without the IEEE slow-path branches of __frcp_rn / sqrtf
+__device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double rsq(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H
@@ -36,7 +37,7 @@ __device__ __forceinline__ double rsq(double x) {
 __device__ __forceinline__ float rsq(float x) { return rsqrtf(x); }
 // sqrt for x > 0 (callers clamp radicands that can reach 0 to a tiny positive number)
 __device__ __forceinline__ double sqr_t(double x) { return x * rsq(x); }
-__device__ __forceinline__ float sqr_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ float sqr_t(float x) { return x * rsqrtf(x); }
 template <typename T> __device__ __forceinline__ T tiny();
 template <> __device__ __forceinline__ double tiny<double>() { return 1e-300; }
 template <> __device__ __forceinline__ float tiny<float>() { return 1e-37f; }

@@ -236,3 +236,21 @@ def test_host_batch_pipeline_equals_single_calls(native):
         o = np.empty_like(jobs[0])
         run.steps_from_host(jobs[0], o, 1)
         assert np.array_equal(o, ref[0])
+
+
+def test_orszag_tang_3d_100_steps_vs_oracle(native, oracle64):
+    """BASELINE.json north star: L2-relative error < 1e-12 against the reference on Orszag-Tang after
+    100 steps (here 3D, 32 x 32 x 16 with kt = 1 so that all components are active; the oracle is the
+    bit-exact restatement of the reference CPU path)."""
+    ini = ot3d_ini((32, 32, 16), OrszagTang={"kt": 1.0})
+    p = oracle64.params(ini)
+    nsteps = 100
+    Ug, tg, dtg, gw = run_gpu_steps(ini, nsteps)
+    Uo, to, dto = oracle64.run_steps(p, oracle64.init_problem(p), nsteps)
+    worst = 0.0
+    for v in range(8):
+        err = l2_relative(Uo[v, gw:-gw, gw:-gw, gw:-gw], Ug[v, gw:-gw, gw:-gw, gw:-gw])
+        worst = max(worst, err)
+        assert err < TOL_F64, (v, err)
+    assert abs(tg - to) < 1e-12 * to
+    print("OT3D 100 steps: worst L2-relative error %.2e" % worst)
