@@ -177,6 +177,40 @@ def reference_arm(args, rank):
     print(json.dumps(line))
 
 
+def measure_e2e(run, args, nstep, cells_all, barrier, max_over_ranks):
+    """End to end through the C ABI with HOST buffers: H2D(state) + step + D2H(state) for every step."""
+    from ramsesgpu_b200 import PinnedArray
+    shape = run.shape
+    pins = [PinnedArray(shape) for _ in range(4)]   # page-locked host buffers (rg_alloc_pinned)
+    host_in, host_out, host_in2, host_out2 = [p.array for p in pins]
+    host_in[...] = run.getDataHost(nstep)
+    hin, hout = host_in, host_out
+    run.steps_from_host(hin, hout, 1)  # warm-up of the path
+    barrier()
+    e0 = time.time()
+    for _ in range(args.e2e_steps):
+        run.steps_from_host(hin, hout, 1)
+        hin, hout = hout, hin
+    barrier()
+    e2e_sync_s = (time.time() - e0) / args.e2e_steps
+    # the same work submitted as a batch of independent one-step jobs (rg_steps_from_host_batch): every
+    # job still pays its own H2D and D2H inside the timed region, the three engines overlap
+    host_in2[...] = host_in
+    ins = [host_in, host_in2]
+    outs = [host_out, host_out2]
+    njobs = max(args.e2e_steps, 2) * 2
+    run.steps_from_host_batch(ins, outs)  # warm-up (allocates the second buffer pair)
+    barrier()
+    e0 = time.time()
+    run.steps_from_host_batch([ins[j % 2] for j in range(njobs)], [outs[j % 2] for j in range(njobs)])
+    barrier()
+    e2e_s = (time.time() - e0) / njobs
+    e2e_s, e2e_sync_s = max_over_ranks([e2e_s, e2e_sync_s])
+    e2e_value = cells_all / e2e_s / 1e6
+    e2e_sync_value = cells_all / e2e_sync_s / 1e6
+    return e2e_value, e2e_sync_value, njobs, pins
+
+
 # -------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -187,6 +221,8 @@ def main():
     ap.add_argument("--size", type=int, default=256, help="cells per direction per GPU")
     ap.add_argument("--ref-size", type=int, default=64, help="grid of each CPU replica of the reference arm")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--global-nz", type=int, default=0,
+                    help="strong scaling: fixed global grid size x size x GLOBAL_NZ split into z slabs (default: weak, size^3 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -220,7 +256,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
 
     n = args.size
-    ini = workload_ini(n, n * world)
+    nz_total = args.global_nz if args.global_nz > 0 else n * world
+    if nz_total % world:
+        raise SystemExit("bench.py: --global-nz must be a multiple of the number of GPUs")
+    nz_local = nz_total // world
+    ini = workload_ini(n, nz_total)
     uid = None
     if world > 1:
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -269,41 +309,17 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = run.stats().kernel_launches - launches0
     total_ms = max_over_ranks([total_ms])[0]
-    cells_per_gpu = float(n) ** 3
+    cells_per_gpu = float(n) * n * nz_local
     cells_all = cells_per_gpu * world
     ms_per_step = total_ms / args.steps
     value = cells_all / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with HOST buffers: H2D(state) + step + D2H(state) every step
-    shape = run.shape
-    pins = [PinnedArray(shape) for _ in range(4)]   # page-locked host buffers (rg_alloc_pinned)
-    host_in, host_out, host_in2, host_out2 = [p.array for p in pins]
-    host_in[...] = run.getDataHost(nstep)
-    hin, hout = host_in, host_out
-    run.steps_from_host(hin, hout, 1)  # warm-up of the path
-    barrier()
-    e0 = time.time()
-    for _ in range(args.e2e_steps):
-        run.steps_from_host(hin, hout, 1)
-        hin, hout = hout, hin
-    barrier()
-    e2e_sync_s = (time.time() - e0) / args.e2e_steps
-    # the same work submitted as a batch of independent one-step jobs (rg_steps_from_host_batch): every
-    # job still pays its own H2D and D2H inside the timed region, the three engines overlap
-    host_in2[...] = host_in
-    ins = [host_in, host_in2]
-    outs = [host_out, host_out2]
-    njobs = max(args.e2e_steps, 2) * 2
-    run.steps_from_host_batch(ins, outs)  # warm-up (allocates the second buffer pair)
-    barrier()
-    e0 = time.time()
-    run.steps_from_host_batch([ins[j % 2] for j in range(njobs)], [outs[j % 2] for j in range(njobs)])
-    barrier()
-    e2e_s = (time.time() - e0) / njobs
-    e2e_s, e2e_sync_s = max_over_ranks([e2e_s, e2e_sync_s])
-    e2e_value = cells_all / e2e_s / 1e6
-    e2e_sync_value = cells_all / e2e_sync_s / 1e6
-    state_bytes = int(np.prod(shape)) * 8
+    state_bytes = int(np.prod(run.shape)) * 8
+    e2e_value = e2e_sync_value = None
+    njobs = 0
+    pins = []
+    if args.e2e_steps > 0:
+        e2e_value, e2e_sync_value, njobs, pins = measure_e2e(run, args, nstep, cells_all, barrier, max_over_ranks)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -316,15 +332,17 @@ def main():
         ev = ncu_evidence(fam)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_nz > 0 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "orszag-tang3d.ini 3D MHD %dx%dx%d per GPU (global nz=%d), HLLD + 2D-HLLD CT, periodic, FP64" % (n, n, n, n * world),
+            "config": {"workload": "orszag-tang3d.ini 3D MHD %dx%dx%d per GPU (global nz=%d), HLLD + 2D-HLLD CT, periodic, FP64" % (n, n, nz_local, nz_total),
                        "parallelism": "z-slab x%d" % world, "cache": "inputs larger than L2 (state %.2f GB per GPU)" % (state_bytes / 1e9),
                        "chunk_planes": run.stats().chunk_planes},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
-                    "call": "rg_steps_from_host_batch: %d independent one-step jobs, pinned host buffers, H2D(j+1) | step(j) | D2H(j-1) overlapped" % njobs,
-                    "single_call_value": e2e_sync_value,
-                    "single_call": "rg_steps_from_host: H2D, one step, D2H back to back (PCIe-bound: 2 x %.2f GB per step)" % (state_bytes / 1e9)},
+            "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
+                "call": "rg_steps_from_host_batch: %d independent one-step jobs, pinned host buffers, H2D(j+1) | step(j) | D2H(j-1) overlapped" % njobs,
+                "single_call_value": e2e_sync_value,
+                "single_call": "rg_steps_from_host: H2D, one step, D2H back to back (PCIe-bound: 2 x %.2f GB per step)" % (state_bytes / 1e9)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
