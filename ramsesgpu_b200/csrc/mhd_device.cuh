@@ -47,6 +47,13 @@ __device__ __forceinline__ double mx(double a, double b) { return (a > b) ? a : 
 __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double mn(double a, double b) { return (a < b) ? a : b; }
 __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+// forced select (the compiler otherwise turns long select ladders into divergent branches)
+__device__ __forceinline__ double pick(bool c, double a, double b) {
+  double r;
+  asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+  return r;
+}
+__device__ __forceinline__ float pick(bool c, float a, float b) { return c ? a : b; }
 __device__ __forceinline__ double ab(double a) { return fabs(a); }
 __device__ __forceinline__ float ab(float a) { return fabsf(a); }
 template <typename T> __device__ __forceinline__ T max4(T a, T b, T c, T d) { return mx(mx(a, b), mx(c, d)); }
@@ -233,15 +240,15 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
   const T rstarl = rl * dsl * idslu;
   const T estarl = rl * dsl * dslu - a2;
   const T el = rl * dsl * dsl - a2;
-  T vstarl = vl, bstarl = bl, wstarl = wl, cstarl = cl;
-  if (!(a2 > T(0) && ab(estarl - a2) <= T(1e-8) * a2)) {
-    const T ie = rcp(estarl);
-    const T k = a * (ustar - ul) * ie;
-    vstarl = vl - k * bl;
-    wstarl = wl - k * cl;
-    bstarl = bl * el * ie;
-    cstarl = cl * el * ie;
-  }
+  // degenerate case of the reference (riemann_mhd.h:205-219): the star values stay the outer ones;
+  // computed unconditionally and selected (a non-finite unselected value is harmless)
+  const bool degl = a2 > T(0) && ab(estarl - a2) <= T(1e-8) * a2;
+  const T iel = rcp(estarl);
+  const T kl = a * (ustar - ul) * iel;
+  const T vstarl = pick(degl, vl, vl - kl * bl);
+  const T wstarl = pick(degl, wl, wl - kl * cl);
+  const T bstarl = pick(degl, bl, bl * el * iel);
+  const T cstarl = pick(degl, cl, cl * el * iel);
   const T vdotbstarl = ustar * a + vstarl * bstarl + wstarl * cstarl;
   const T etotstarl = (dsl * etotl - ptotl * ul + ptotstar * ustar + a * (vdotbl - vdotbstarl)) * idslu;
   const T irsl = rsq(rstarl);
@@ -254,15 +261,13 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
   const T rstarr = rr * dsr * idsru;
   const T estarr = rr * dsr * dsru - a2;
   const T er = rr * dsr * dsr - a2;
-  T vstarr = vr, bstarr = br, wstarr = wr, cstarr = cr;
-  if (!(a2 > T(0) && ab(estarr - a2) <= T(1e-8) * a2)) {
-    const T ie = rcp(estarr);
-    const T k = a * (ustar - ur) * ie;
-    vstarr = vr - k * br;
-    wstarr = wr - k * cr;
-    bstarr = br * er * ie;
-    cstarr = cr * er * ie;
-  }
+  const bool degr = a2 > T(0) && ab(estarr - a2) <= T(1e-8) * a2;
+  const T ier = rcp(estarr);
+  const T kr = a * (ustar - ur) * ier;
+  const T vstarr = pick(degr, vr, vr - kr * br);
+  const T wstarr = pick(degr, wr, wr - kr * cr);
+  const T bstarr = pick(degr, br, br * er * ier);
+  const T cstarr = pick(degr, cr, cr * er * ier);
   const T vdotbstarr = ustar * a + vstarr * bstarr + wstarr * cstarr;
   const T etotstarr = (dsr * etotr - ptotr * ur + ptotstar * ustar + a * (vdotbr - vdotbstarr)) * idsru;
   const T irsr = rsq(rstarr);
@@ -279,25 +284,23 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
   const T etotssl = etotstarl - sgnm * sqrl * (vdotbstarl - vdotbss);
   const T etotssr = etotstarr + sgnm * sqrr * (vdotbstarr - vdotbss);
 
-  // sample at x/t = 0 (riemann_mhd.h:268-330) with selects
-  T ro, uo, vo, wo, bo, co, ptoto, etoto, vdotbo;
-  if (sl > T(0)) {
-    ro = rl; uo = ul; vo = vl; wo = wl; bo = bl; co = cl; ptoto = ptotl; etoto = etotl; vdotbo = vdotbl;
-  } else if (sal > T(0)) {
-    ro = rstarl; uo = ustar; vo = vstarl; wo = wstarl; bo = bstarl; co = cstarl;
-    ptoto = ptotstar; etoto = etotstarl; vdotbo = vdotbstarl;
-  } else if (ustar > T(0)) {
-    ro = rstarl; uo = ustar; vo = vss; wo = wss; bo = bss; co = css;
-    ptoto = ptotstar; etoto = etotssl; vdotbo = vdotbss;
-  } else if (sar > T(0)) {
-    ro = rstarr; uo = ustar; vo = vss; wo = wss; bo = bss; co = css;
-    ptoto = ptotstar; etoto = etotssr; vdotbo = vdotbss;
-  } else if (sr > T(0)) {
-    ro = rstarr; uo = ustar; vo = vstarr; wo = wstarr; bo = bstarr; co = cstarr;
-    ptoto = ptotstar; etoto = etotstarr; vdotbo = vdotbstarr;
-  } else {
-    ro = rr; uo = ur; vo = vr; wo = wr; bo = br; co = cr; ptoto = ptotr; etoto = etotr; vdotbo = vdotbr;
-  }
+  // sample at x/t = 0 (riemann_mhd.h:268-330).  The reference's ladder
+  //   sl > 0: L | sal > 0: L* | ustar > 0: L** | sar > 0: R** | sr > 0: R* | else: R
+  // is evaluated with explicit selects per output (32 selects; as an if/else ladder over nine
+  // variables the compiler emits divergent branches with ~18 register moves per level)
+  const bool c1 = sl > T(0), c2 = sal > T(0), c3 = ustar > T(0), c4 = sar > T(0), c5 = sr > T(0);
+  const bool cR = !(c1 || c2 || c3 || c4 || c5);  // region R
+  const bool c34 = c3 || c4;                        // (given !c1, !c2) one of the two double-star regions
+  const bool c23 = c2 || c3;                        // (given !c1) left of the contact
+  const T uo = pick(c1, ul, pick(cR, ur, ustar));
+  const T ptoto = pick(c1, ptotl, pick(cR, ptotr, ptotstar));
+  const T ro = pick(c1, rl, pick(cR, rr, pick(c23, rstarl, rstarr)));
+  const T vo = pick(c1, vl, pick(cR, vr, pick(c2, vstarl, pick(c34, vss, vstarr))));
+  const T wo = pick(c1, wl, pick(cR, wr, pick(c2, wstarl, pick(c34, wss, wstarr))));
+  const T bo = pick(c1, bl, pick(cR, br, pick(c2, bstarl, pick(c34, bss, bstarr))));
+  const T co = pick(c1, cl, pick(cR, cr, pick(c2, cstarl, pick(c34, css, cstarr))));
+  const T vdotbo = pick(c1, vdotbl, pick(cR, vdotbr, pick(c2, vdotbstarl, pick(c34, vdotbss, vdotbstarr))));
+  const T etoto = pick(c1, etotl, pick(cR, etotr, pick(c2, etotstarl, pick(c3, etotssl, pick(c4, etotssr, etotstarr)))));
   flux[ID] = ro * uo;
   flux[IP] = (etoto + ptoto) * uo - a * vdotbo;
   flux[IU] = ro * uo * uo - a2 + ptoto;
