@@ -25,7 +25,7 @@ int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
-int g_traceQY = 8;  // run-time knob "trace_qy": 8 (two 256-thread blocks per SM) or 16 (one 512-thread block)
+int g_traceQY = 12;  // run-time knob "trace_qy": 12 (one 384-thread block per SM, 168 registers) or 8 (two 256-thread blocks, 128)
 
 namespace {
 
@@ -1192,7 +1192,7 @@ bool setTuning(const char* key, int value) {
     return true;
   }
   if (k == "trace_qy") {
-    if (value != 8 && value != 16) return false;
+    if (value != 8 && value != 12) return false;
     g_traceQY = value;
     return true;
   }
@@ -1320,10 +1320,10 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   if (ok < 0)
     ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<8>::SMEM) == cudaSuccess &&
-          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<8>::SMEM) == cudaSuccess &&
-          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<16>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<16>::SMEM) == cudaSuccess)
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<12>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<12>::SMEM) == cudaSuccess)
              ? 1
              : 0;
   if (!ok) cudaGetLastError();
@@ -1361,13 +1361,14 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     if (nSM <= 0) nSM = 148;
   }
-  if (!fastPath(P)) launchFusedTrace<T, TraceTileT<8>, false>(P, U, sc, k0, k1, dt, nSM, s);
-  else if (g_traceQY == 16) launchFusedTrace<T, TraceTileT<16>, true>(P, U, sc, k0, k1, dt, nSM, s);
+  if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
+  else if (g_traceQY == 12) launchFusedTrace<T, TraceTileT<12>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
   ++g_launches;
 }
 
 template <typename T>
+// 512 threads / 124 registers: a 384-thread build (152 registers) measured 7 % slower, 640 threads spill
 struct FusedSel { typedef FusedTile<T, 15, 7, 512> Cfg; };
 
 template <typename T>
