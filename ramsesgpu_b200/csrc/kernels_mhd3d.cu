@@ -639,7 +639,7 @@ struct FusedTile {
   static_assert(PX <= PXP && PY % 2 == 0, "tile shape");
   static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
   static constexpr int NT = 1 + 7 * NCH;                             // tasks per plane
-  static constexpr int LZMAX = 96;                                   // planes per block (counter arrays)
+  static constexpr int LZMAX = 160;                                  // planes per block (counter arrays)
   static constexpr unsigned W_BYTES = (unsigned)(NW_MHD * WCELLS * sizeof(T));
   static constexpr unsigned W_STRIDE = (W_BYTES + 127u) / 128u * 128u;
   static constexpr unsigned FE_SLOT = (unsigned)(NFE * NPOSP);       // reals per plane slot
