@@ -72,6 +72,24 @@ if __name__ == "__main__":
         "implode3d_hll_20x12x16_s5": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 20, "ny": 12, "nz": 16}, "hydro": {"riemannSolver": "hll", "slope_type": 1.0}}, 5, "f64"),
         "kh3d_16x8x16_f32_s10": ("kelvin_helmholtz_gpu_3d.ini", {"mesh": {"nx": 16, "ny": 8, "nz": 16}}, 10, "f32"),
         "kh3d_16x8x16_f64_s10": ("kelvin_helmholtz_gpu_3d.ini", {"mesh": {"nx": 16, "ny": 8, "nz": 16}}, 10, "f64"),
+        # SURVEY 8(f).2 -- dissipative terms: Ohmic resistivity + viscosity on the adiabatic 3D MHD step,
+        # on the isothermal shearing box (no resistive energy flux) and viscosity on the hydro step
+        "ot3d_diss_16x12x20_s6": ("orszag-tang3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 20}, "OrszagTang": {"kt": 1.0},
+                                                        "hydro": {"nu": 0.004}, "MHD": {"eta": 0.003}}, 6, "f64"),
+        "ot3d_eta_walls_16_s4": ("orszag-tang3d.ini", {
+            "mesh": {"nx": 16, "ny": 16, "nz": 16, "boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1,
+                     "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1}, "MHD": {"eta": 0.005}}, 4, "f64"),
+        "mri3d_diss_12x20x8_s10": ("mhd_mri_3d.ini", {"mesh": {"nx": 12, "ny": 20, "nz": 8},
+                                                      "hydro": {"nu": 2e-6}, "MHD": {"eta": 1e-6}}, 10, "f64"),
+        "implode3d_visc_16_s6": ("implode3d_mpi_zslab.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}, "hydro": {"nu": 0.002}}, 6, "f64"),
+        "kh3d_visc_16x8x16_f32_s6": ("kelvin_helmholtz_gpu_3d.ini", {"mesh": {"nx": 16, "ny": 8, "nz": 16}, "hydro": {"nu": 0.001}}, 6, "f32"),
+        # SURVEY 8(f).2 -- static gravity: Rayleigh-Taylor, hydro (approx solver) and MHD (HLLD), z walls
+        "rt3d_hydro_10x8x24_s8": ("rayleigh_taylor_gpu_3d.ini", {"mesh": {"nx": 10, "ny": 8, "nz": 24}}, 8, "f64"),
+        "rt3d_mhd_10x8x24_s8": ("rayleigh_taylor_gpu_3d_mhd.ini", {"mesh": {"nx": 10, "ny": 8, "nz": 24}}, 8, "f64"),
+        "rt3d_mhd_visc_rand_8x10x16_s5": ("rayleigh_taylor_gpu_3d_mhd.ini", {
+            "mesh": {"nx": 8, "ny": 10, "nz": 16}, "hydro": {"nu": 0.001}, "MHD": {"eta": 0.002},
+            "gravity": {"static_field_x": 0.05, "static_field_z": -0.3},
+            "rayleigh-taylor": {"randomEnabled": "yes", "random_seed": 7, "bx": 0.05, "bz": 0.02}}, 5, "f64"),
     }
     for name, (ini, ov, steps, prec) in cases.items():
         if only and name not in only:

@@ -68,6 +68,13 @@ typedef struct orc_params {
   int kh_seed, kh_p_rand, kh_p_sine, kh_p_sine_robertson;
   real_t kh_amp, kh_rho_in, kh_rho_out, kh_pressure, kh_inner, kh_outer, kh_vin, kh_vout;
   real_t kh_mode, kh_w0, kh_delta;
+  /* [gravity] static field (HydroRunBase.cpp:253-260, HydroParameters.h:322-324): the reference's h_gravity
+     array is uniform for the one shipped problem that fills it (Rayleigh-Taylor, :6400-6408) */
+  int gravityEnabled;
+  real_t gravity_x, gravity_y, gravity_z;
+  /* [rayleigh-taylor] HydroRunBase.cpp:6269-6277, MHDRunBase.cpp:2999-3001 */
+  int rt_random, rt_seed;
+  real_t rt_amp, rt_d0, rt_d1, rt_bx, rt_by, rt_bz;
 } orc_params;
 
 /* parse ini TEXT with the reference's inih + ConfigMap semantics (float parse!) */

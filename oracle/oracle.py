@@ -39,6 +39,9 @@ def _params_struct(real):
             ("kh_amp", real), ("kh_rho_in", real), ("kh_rho_out", real), ("kh_pressure", real),
             ("kh_inner", real), ("kh_outer", real), ("kh_vin", real), ("kh_vout", real),
             ("kh_mode", real), ("kh_w0", real), ("kh_delta", real),
+            ("gravityEnabled", C.c_int), ("gravity_x", real), ("gravity_y", real), ("gravity_z", real),
+            ("rt_random", C.c_int), ("rt_seed", C.c_int),
+            ("rt_amp", real), ("rt_d0", real), ("rt_d1", real), ("rt_bx", real), ("rt_by", real), ("rt_bz", real),
         ]
     return OrcParams
 

@@ -219,5 +219,24 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->kh_mode = get_float(&c, "kelvin-helmholtz", "mode", 2.0f);
   p->kh_w0 = get_float(&c, "kelvin-helmholtz", "w0", 0.1f);
   p->kh_delta = get_float(&c, "kelvin-helmholtz", "delta", 0.03f);
+  /* static gravity: HydroRunBase.cpp:253-260 (forced on for Rayleigh-Taylor), HydroParameters.h:322-324.
+     Only init_hydro_Rayleigh_Taylor fills h_gravity with the static field (HydroRunBase.cpp:6400-6408);
+     with any other problem the allocated array stays zero. */
+  p->gravityEnabled = get_bool(&c, "gravity", "static", 0) || get_bool(&c, "gravity", "self", 0);
+  if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityEnabled = 1;
+  p->gravity_x = p->gravity_y = p->gravity_z = 0;
+  if (!strcmp(p->problem, "Rayleigh-Taylor")) {
+    p->gravity_x = get_float(&c, "gravity", "static_field_x", 0.0f);
+    p->gravity_y = get_float(&c, "gravity", "static_field_y", 0.0f);
+    p->gravity_z = get_float(&c, "gravity", "static_field_z", 0.0f);
+  }
+  p->rt_amp = get_float(&c, "rayleigh-taylor", "amplitude", 0.01f);
+  p->rt_d0 = get_float(&c, "rayleigh-taylor", "d0", 1.0f);
+  p->rt_d1 = get_float(&c, "rayleigh-taylor", "d1", 2.0f);
+  p->rt_random = get_bool(&c, "rayleigh-taylor", "randomEnabled", 0);
+  p->rt_seed = (int)get_int(&c, "rayleigh-taylor", "random_seed", 33);
+  p->rt_bx = get_float(&c, "rayleigh-taylor", "bx", 1e-8f);
+  p->rt_by = get_float(&c, "rayleigh-taylor", "by", 1e-8f);
+  p->rt_bz = get_float(&c, "rayleigh-taylor", "bz", 1e-8f);
   return 0;
 }

@@ -220,6 +220,8 @@ real_t orc_compute_dt_hydro(const orc_params *P, const real_t *U) {
   return P->cfl / invDt;
 }
 
+void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear);
+
 /* HydroRunGodunov.cpp:2658-2890 + convertToPrimitives :4210-4250 */
 void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
@@ -259,6 +261,10 @@ void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, re
         real_t sw0 = (-u * dwx) * dtdx + (-v_ * dwy) * dtdy + (-w * dwz - dpz / r) * dtdz;
         real_t sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v_ * dpy - dvy * gamma * p) * dtdy + (-w * dpz - dwz * gamma * p) * dtdz;
         r = r + sr0; u = u + su0; v_ = v_ + sv0; w = w + sw0; p = p + sp0;
+        /* gravity predictor, added to qm/qp AFTER the trace (HydroRunGodunov.cpp:2705-2734) */
+        const real_t gpx = P->gravityEnabled ? HALF * dt * P->gravity_x : 0;
+        const real_t gpy = P->gravityEnabled ? HALF * dt * P->gravity_y : 0;
+        const real_t gpz = P->gravityEnabled ? HALF * dt * P->gravity_z : 0;
         for (int dd = 0; dd < 3; ++dd) {
           real_t s[2] = {-ONE, ONE};
           for (int side = 0; side < 2; ++side) { /* side 0: qp (low face), 1: qm (high face) */
@@ -272,6 +278,7 @@ void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, re
             rr = FMAX_(P->smallr, rr);
             pp = FMAX_(P->smallp * rr, pp);
             AT(dst, i, j, k, ID) = rr; AT(dst, i, j, k, IP) = pp;
+            if (P->gravityEnabled) { uu += gpx; vv += gpy; ww += gpz; }
             AT(dst, i, j, k, IU) = uu; AT(dst, i, j, k, IV) = vv; AT(dst, i, j, k, IW) = ww;
           }
         }
@@ -297,5 +304,16 @@ void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, re
         if (in_i && in_j && k > gw) for (int v = 0; v < 5; ++v) AT(Unew, i, j, k - 1, v) -= fz[swz[v]] * dtdz;
         if (in_i && in_j && in_k) for (int v = 0; v < 5; ++v) AT(Unew, i, j, k, v) += fz[swz[v]] * dtdz;
       }
+  /* gravity source term, HydroRunGodunov.cpp:2900-2903 -> HydroRunBase.cpp:1962-1976 */
+  if (P->gravityEnabled)
+    for (int k = gw; k < ksz - gw; ++k)
+      for (int j = gw; j < jsz - gw; ++j)
+        for (int i = gw; i < isz - gw; ++i) {
+          real_t rhoOld = AT(Uold, i, j, k, ID), rhoNew = AT(Unew, i, j, k, ID);
+          AT(Unew, i, j, k, IU) += HALF * dt * P->gravity_x * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IV) += HALF * dt * P->gravity_y * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IW) += HALF * dt * P->gravity_z * (rhoOld + rhoNew);
+        }
   free(Q); free(tr);
+  orc_dissipative_3d(P, Unew, dt, 0, 0); /* viscosity, HydroRunGodunov.cpp:2908-2927 */
 }

@@ -223,13 +223,61 @@ static int init_kelvin_helmholtz(const orc_params *P, real_t *U) {
   return 0;
 }
 
+/* Rayleigh-Taylor, 3D: HydroRunBase.cpp:6262-6434 (hydro part, whole array incl. ghosts) and
+ * MHDRunBase.cpp:2995-3040 (uniform seed field added to the energy).  Heavy fluid d1 above the
+ * mid-plane in z, hydrostatic pressure P0 + rho g.x, single-mode or rand() velocity perturbation. */
+static int init_rayleigh_taylor(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->dim != 3) {
+    fprintf(stderr, "oracle: Rayleigh-Taylor is restated in 3D only\n");
+    return -1;
+  }
+  if (P->rt_random) srand(P->rt_seed);
+  const real_t P0 = 1.0f / (P->gamma0 - 1.0f);
+  const real_t Lx = P->xMax - P->xMin, Ly = P->yMax - P->yMin, Lz = P->zMax - P->zMin;
+  for (int k = 0; k < ksz; ++k) {
+    real_t z = P->zMin + P->dz / 2 + (k - gw) * P->dz;
+    for (int j = 0; j < jsz; ++j) {
+      real_t y = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+      for (int i = 0; i < isz; ++i) {
+        real_t x = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+        real_t d = (z > (P->zMin + P->zMax) / 2) ? P->rt_d1 : P->rt_d0;
+        AT(U, i, j, k, ID) = d;
+        AT(U, i, j, k, IP) = P0 + d * (P->gravity_x * x + P->gravity_y * y + P->gravity_z * z);
+        AT(U, i, j, k, IU) = 0.0f;
+        AT(U, i, j, k, IV) = 0.0f;
+        if (P->rt_random)
+          AT(U, i, j, k, IW) = P->rt_amp * (rand() * 1.0 / RAND_MAX - 0.5);
+        else
+          AT(U, i, j, k, IW) = P->rt_amp * (1 + cos(2 * M_PI * x / Lx)) * (1 + cos(2 * M_PI * y / Ly)) * (1 + cos(2 * M_PI * z / Lz)) / 8;
+      }
+    }
+  }
+  fill_corners_gw2(P, U);
+  if (P->mhdEnabled) {
+    const real_t Bx0 = P->rt_bx, By0 = P->rt_by, Bz0 = P->rt_bz;
+    for (int k = 0; k < ksz; ++k)
+      for (int j = 0; j < jsz; ++j)
+        for (int i = 0; i < isz; ++i) {
+          AT(U, i, j, k, IA) = Bx0;
+          AT(U, i, j, k, IB) = By0;
+          AT(U, i, j, k, IC) = Bz0;
+          AT(U, i, j, k, IP) += 0.5 * (Bx0 * Bx0 + By0 * By0 + Bz0 * Bz0);
+        }
+  }
+  return 0;
+}
+
 /* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
 int orc_init_problem(const orc_params *P, real_t *U) {
   const char *n = P->problem;
   if (P->mhdEnabled) {
     if (!strcmp(n, "Orszag-Tang") || !strcmp(n, "OrszagTang")) { init_orszag_tang(P, U); return 0; }
     if (!strcmp(n, "MRI") || !strcmp(n, "Mri") || !strcmp(n, "mri")) { init_mri(P, U); return 0; }
+    if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
   } else {
+    if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
     if (!strcmp(n, "implode")) { init_implode(P, U); return 0; }
     if (!strcmp(n, "Kelvin-Helmholtz")) return init_kelvin_helmholtz(P, U);
   }

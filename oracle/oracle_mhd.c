@@ -731,6 +731,15 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
         E[2][0][0] = AT(elec, i, j, k, 2); E[2][0][1] = AT(elec, i, j + 1, k, 2);
         E[2][1][0] = AT(elec, i + 1, j, k, 2); E[2][1][1] = AT(elec, i + 1, j + 1, k, 2);
         orc_trace_mhd_3d(P, q, (const real_t(*)[8])dq, bfNb, dbf, (const real_t(*)[2][2])E, dtdx, dtdy, dtdz, xPos, qm, qp, qEdge);
+        if (P->gravityEnabled) { /* gravity predictor on every traced velocity, cpu_v3.cpp:277-332 */
+          const real_t g[3] = {HALF * dt * P->gravity_x, HALF * dt * P->gravity_y, HALF * dt * P->gravity_z};
+          for (int d = 0; d < 3; ++d)
+            for (int c = 0; c < 3; ++c) {
+              qm[d][IU + c] += g[c];
+              qp[d][IU + c] += g[c];
+              for (int e = 0; e < 4; ++e) qEdge[e][d][IU + c] += g[c];
+            }
+        }
         for (int v = 0; v < 8; ++v) {
           for (int d = 0; d < 3; ++d) {
             AT(qm_[d], i, j, k, v) = qm[d][v];
@@ -880,6 +889,17 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
       }
   }
 
+  /* gravity source term on the momenta of the inner cells, cpu_v3.cpp:585-588 -> HydroRunBase.cpp:1962-1976 */
+  if (P->gravityEnabled)
+    for (int k = gw; k < ksz - gw; ++k)
+      for (int j = gw; j < jsz - gw; ++j)
+        for (int i = gw; i < isz - gw; ++i) {
+          real_t rhoOld = AT(Uold, i, j, k, ID), rhoNew = AT(Unew, i, j, k, ID);
+          AT(Unew, i, j, k, IU) += HALF * dt * P->gravity_x * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IV) += HALF * dt * P->gravity_y * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IW) += HALF * dt * P->gravity_z * (rhoOld + rhoNew);
+        }
+
   /* constrained transport: cpu_v3.cpp:600-630 (emf index: 0 = Z, 1 = Y, 2 = X) */
   for (int k = gw; k < ksz - gw + 1; ++k)
     for (int j = gw; j < jsz - gw + 1; ++j)
@@ -899,8 +919,11 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
   free(sfmin); free(sfmax); free(rmmin); free(rmmax);
 }
 
+void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear);
+
 void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
   mhd3d_core(P, Uold, Unew, dt, ZERO, 0);
+  orc_dissipative_3d(P, Unew, dt, ZERO, 0); /* cpu_v3.cpp:661-693 */
 }
 
 /* shearing-box ghost remap in x, MHDRunGodunov.cpp:3539-3759 (time-dependent shift deltay) */
@@ -994,7 +1017,9 @@ void orc_make_all_boundaries_shear(const orc_params *P, real_t *U, real_t dt, re
 void orc_mhd3d_rotating_step(const orc_params *P, real_t *Uold, real_t *Unew, real_t dt, real_t totalTime) {
   memcpy(Unew, Uold, (size_t)orc_array_len(P) * sizeof(real_t));
   mhd3d_core(P, Uold, Unew, dt, totalTime, 1);
-  if (P->bc[0] == BC_SHEARINGBOX && P->bc[1] == BC_SHEARINGBOX && P->Omega0 > 0)
+  const int shearBox = P->bc[0] == BC_SHEARINGBOX && P->bc[1] == BC_SHEARINGBOX && P->Omega0 > 0;
+  orc_dissipative_3d(P, Unew, dt, totalTime, shearBox); /* MHDRunGodunov.cpp:3379-3419 */
+  if (shearBox)
     orc_make_all_boundaries_shear(P, Unew, dt, totalTime);
   else
     orc_make_all_boundaries(P, Unew);

@@ -8,7 +8,10 @@ from ramsesgpu_b200.io import l2_relative
 
 CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4",
          "ot2d_32_s12", "ot2d_40x24_hll_s6", "implode3d_16_s8", "implode3d_hll_20x12x16_s5",
-         "kh3d_16x8x16_f64_s10", "kh3d_16x8x16_f32_s10", "mri3d_16x32x16_s12", "mri3d_12x20x8_s40"]
+         "kh3d_16x8x16_f64_s10", "kh3d_16x8x16_f32_s10", "mri3d_16x32x16_s12", "mri3d_12x20x8_s40",
+         # resistivity / viscosity / static gravity
+         "ot3d_diss_16x12x20_s6", "ot3d_eta_walls_16_s4", "mri3d_diss_12x20x8_s10", "implode3d_visc_16_s6",
+         "kh3d_visc_16x8x16_f32_s6", "rt3d_hydro_10x8x24_s8", "rt3d_mhd_10x8x24_s8", "rt3d_mhd_visc_rand_8x10x16_s5"]
 
 
 @pytest.mark.parametrize("name", CASES)
