@@ -134,7 +134,8 @@ int rg_set_tuning(const char* key, int value);
  * phase order: RG_PHASE_* below.  Events are recorded around every launch between begin and end;
  * rg_profile_end synchronises and returns milliseconds and launch counts summed over the region. */
 enum { RG_PHASE_BOUNDARY = 0, RG_PHASE_PRIM, RG_PHASE_TRACE, RG_PHASE_FLUX, RG_PHASE_EMF, RG_PHASE_UPDATE,
-       RG_PHASE_DT, RG_PHASE_COPY, RG_PHASE_HALO, RG_PHASE_FUSED /* fused flux+emf+update */, RG_NPHASE };
+       RG_PHASE_DT, RG_PHASE_COPY, RG_PHASE_HALO, RG_PHASE_FUSED /* fused flux+emf+update */,
+       RG_PHASE_DISS /* resistivity + viscosity */, RG_NPHASE };
 int rg_profile_begin(rg_handle h);
 int rg_profile_end(rg_handle h, double* total_ms, double* phase_ms, unsigned long long* phase_launches);
 

@@ -19,7 +19,7 @@ class RgStats(C.Structure):
 
 
 RG_FLAG_FP32 = 1
-PHASES = ["boundary", "prim", "trace", "flux", "emf", "update", "dt", "copy", "halo", "fused"]
+PHASES = ["boundary", "prim", "trace", "flux", "emf", "update", "dt", "copy", "halo", "fused", "diss"]
 RG_ERR_NO_DEVICE = 2
 
 # name -> (restype, argtypes); also the list the symbol-export test checks against the header

@@ -278,6 +278,63 @@ bool initKelvinHelmholtz(const ConfigMap& cfg, const RunParams& rp, const KParam
   return true;
 }
 
+// Rayleigh-Taylor instability in 3D (hydro and MHD): heavy fluid d1 above the mid-plane in z,
+// hydrostatic pressure P0 + rho g.x, single-mode or rand() perturbation of the vertical momentum,
+// uniform seed field for MHD.  Reference HydroRunBase.cpp:6262-6434 (every cell incl. ghosts, glibc
+// rand() in (k,j,i) order over the WHOLE array) and MHDRunBase.cpp:2995-3040.
+template <typename T>
+bool initRayleighTaylor(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                        std::string* msg) {
+  if (rp.dim != 3) {
+    if (msg) *msg = "Rayleigh-Taylor: only the 3D variants are implemented";
+    return false;
+  }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const char* S = "rayleigh-taylor";
+  const T amplitude = cfg.getFloat(S, "amplitude", 0.01f);
+  const T d0 = cfg.getFloat(S, "d0", 1.0f), d1 = cfg.getFloat(S, "d1", 2.0f);
+  const bool randomEnabled = cfg.getBool(S, "randomEnabled", false);
+  if (randomEnabled) {
+    std::srand((unsigned)cfg.getInteger(S, "random_seed", 33));
+    // draws of the slabs below: the reference draws for every cell of the (global) array, ghosts included;
+    // local plane k is global plane k + kglob0
+    for (long n = (long)kp.kglob0 * kp.isize * kp.jsize; n > 0; --n) (void)std::rand();
+  }
+  const T P0 = 1.0f / (kp.gamma0 - 1.0f);
+  const T Lx = kp.xMax - kp.xMin, Ly = kp.yMax - kp.yMin, Lz = kp.zMax - kp.zMin;
+  for (int k = 0; k < kp.ksize; ++k) {
+    const T z = kp.zMin + kp.dz / 2 + (k + kp.kglob0 - gw) * kp.dz;
+    for (int j = 0; j < kp.jsize; ++j) {
+      const T y = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+      for (int i = 0; i < kp.isize; ++i) {
+        const T x = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+        const T d = (z > (kp.zMin + kp.zMax) / 2) ? d1 : d0;
+        g.at(ID, i, j, k) = d;
+        g.at(IP, i, j, k) = P0 + d * (kp.gx * x + kp.gy * y + kp.gz * z);
+        if (randomEnabled)
+          g.at(IW, i, j, k) = amplitude * (std::rand() * 1.0 / RAND_MAX - 0.5);
+        else
+          g.at(IW, i, j, k) = amplitude * (1 + std::cos(2 * M_PI * x / Lx)) * (1 + std::cos(2 * M_PI * y / Ly)) *
+                              (1 + std::cos(2 * M_PI * z / Lz)) / 8;
+      }
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  if (rp.mhdEnabled) {
+    const T bx = cfg.getFloat(S, "bx", 1e-8f), by = cfg.getFloat(S, "by", 1e-8f), bz = cfg.getFloat(S, "bz", 1e-8f);
+    for (int k = 0; k < kp.ksize; ++k)
+      for (int j = 0; j < kp.jsize; ++j)
+        for (int i = 0; i < kp.isize; ++i) {
+          g.at(IA, i, j, k) = bx;
+          g.at(IB, i, j, k) = by;
+          g.at(IC, i, j, k) = bz;
+          g.at(IP, i, j, k) += 0.5 * (bx * bx + by * by + bz * bz);
+        }
+  }
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -287,9 +344,11 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
   if (rp.mhdEnabled) {  // reference MHDRunBase.cpp:1286-1342
     if (problem == "Orszag-Tang" || problem == "OrszagTang") return initOrszagTang(cfg, rp, kp, U, message);
     if (problem == "MRI" || problem == "Mri" || problem == "mri") return initMri(cfg, rp, kp, U, message);
+    if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
   } else {  // reference HydroRunBase.cpp:7023-7100
     if (problem == "implode") return initImplode(cfg, rp, kp, U, message);
     if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtz(cfg, rp, kp, U, message);
+    if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

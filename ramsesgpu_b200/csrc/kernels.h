@@ -95,6 +95,17 @@ struct HydroKernels {
   static void probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s);
 };
 
+// dissipative terms on the NEW state after the Godunov update (kernels_dissipative.cu).
+// D is a scratch array of 12 components over the whole local array [c][k][j][i].
+template <typename T>
+struct DissKernels {
+  static void resistEmf(const KParams<T>& P, const T* U, T* D, cudaStream_t s);     // D[0..2] = -eta curl B
+  static void ctUpdate(const KParams<T>& P, T* U, const T* D, T dt, cudaStream_t s);  // U.B += dt curl-difference of D[0..2]
+  static void resistEnergy(const KParams<T>& P, T* U, T dt, cudaStream_t s);         // U.E -= div(eta J x B) dt
+  static void viscFlux(const KParams<T>& P, const T* U, T* D, T dt, cudaStream_t s);  // D[dir*4 + (mx,my,mz,E)]
+  static void viscUpdate(const KParams<T>& P, T* U, const T* D, cudaStream_t s);
+};
+
 // number of slots of the inverse-dt max reduction (power of two); every slot holds the bit pattern
 // of a non-negative double, so "max" works on the integer or on the floating view alike
 constexpr int MAX_SLOTS = 1024;

@@ -51,8 +51,12 @@ __global__ void __launch_bounds__(BX) k_hydro_trace(const __grid_constant__ KPar
   const T sv0 = (-u * dx_[IV]) * dtdx + (-v * dy_[IV] - dy_[IP] * ir) * dtdy + (-w * dz_[IV]) * dtdz;
   const T sw0 = (-u * dx_[IW]) * dtdx + (-v * dy_[IW]) * dtdy + (-w * dz_[IW] - dz_[IP] * ir) * dtdz;
   const T sp0 = (-u * dx_[IP] - dx_[IU] * g * p) * dtdx + (-v * dy_[IP] - dy_[IV] * g * p) * dtdy + (-w * dz_[IP] - dz_[IW] * g * p) * dtdz;
+  T gpx = T(0), gpy = T(0), gpz = T(0);
+  if (P.gravity) {  // gravity predictor on the traced velocities, reference HydroRunGodunov.cpp:2705-2734
+    gpx = h * dt * P.gx; gpy = h * dt * P.gy; gpz = h * dt * P.gz;
+  }
   W(H_R, i, j, k) = r + sr0; W(H_P, i, j, k) = p + sp0;
-  W(H_U, i, j, k) = u + su0; W(H_V, i, j, k) = v + sv0; W(H_W, i, j, k) = w + sw0;
+  W(H_U, i, j, k) = u + su0 + gpx; W(H_V, i, j, k) = v + sv0 + gpy; W(H_W, i, j, k) = w + sw0 + gpz;
   // slope component order in W: r, p, u, v, w  (ID, IP, IU, IV, IW)
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
@@ -159,6 +163,10 @@ __global__ void __launch_bounds__(128) k_hydro_flux_update(const __grid_constant
           s += fxl[v] * dtdx; s += fyl[v] * dtdy; s += fzl[v] * dtdz;
           s -= fxh[v] * dtdx; s -= fyh[v] * dtdy; s -= fzh[v] * dtdz;
           un[v] = s;
+        }
+        if (P.gravity) {  // static gravity source term, reference HydroRunBase.cpp:1962-1976
+          const T hdt = T(0.5) * dt, rs = U(ID, i, j, k) + un[ID];
+          un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * P.gz * rs;
         }
         T q[5];
         const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], un[IW], q);

@@ -231,6 +231,10 @@ __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, con
       sC0 -= shC;
     }
   }
+  if (P.gravity) {  // gravity predictor on every traced velocity of the cell (reference cpu_v3.cpp:277-332):
+    const T hdt = h * dt;  // face / edge states are centre +/- slopes, so it goes into the centre value
+    su0 += hdt * P.gx; sv0 += hdt * P.gy; sw0 += hdt * P.gz;
+  }
   W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
   W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
   W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
@@ -534,6 +538,10 @@ __device__ __forceinline__ T update_cell(const KParams<T>& P, const UView<T>& U,
       s -= F(5 + v, i, j + 1, k) * dtdy;
       s -= F(10 + v, i, j, k + 1) * dtdz;
       un[v] = s;
+    }
+    if (P.gravity) {  // static gravity source term on the momenta, reference HydroRunBase.cpp:1962-1976
+      const T hdt = T(0.5) * dt, rs = U(ID, i, j, k) + un[ID];
+      un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * P.gz * rs;
     }
   }
   // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,

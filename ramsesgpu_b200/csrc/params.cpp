@@ -101,6 +101,18 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
     else if (ms == "llf") k.magRiemannSolver = MAG_LLF;
     else if (ms == "upwind") k.magRiemannSolver = MAG_UPWIND;
   }
+  // dissipative terms (HydroParameters.h nu / eta) and static gravity (HydroRunBase.cpp:253-260,
+  // HydroParameters.h:322-324): only the Rayleigh-Taylor problem fills the reference's gravity array
+  k.nu = cfg.getFloat("hydro", "nu", 0.0f);
+  k.eta = rp.mhdEnabled ? T(cfg.getFloat("MHD", "eta", 0.0f)) : T(0);
+  k.gravity = (cfg.getBool("gravity", "static", false) || cfg.getBool("gravity", "self", false)) ? 1 : 0;
+  k.gx = k.gy = k.gz = T(0);
+  if (rp.problem == "Rayleigh-Taylor") {
+    k.gravity = 1;
+    k.gx = cfg.getFloat("gravity", "static_field_x", 0.0f);
+    k.gy = cfg.getFloat("gravity", "static_field_y", 0.0f);
+    k.gz = cfg.getFloat("gravity", "static_field_z", 0.0f);
+  }
   return k;
 }
 

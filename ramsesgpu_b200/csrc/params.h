@@ -32,6 +32,12 @@ struct KParams {
   T gamma0, smallr, smallc, smallp, smallpp, smalle, gamma6, cIso, Omega0, slope_type, cfl;
   int niter_riemann;
   int riemannSolver, magRiemannSolver;
+  // dissipative terms and static gravity: kinematic viscosity [hydro] nu, Ohmic
+  // resistivity [MHD] eta, uniform field [gravity] static_field_x/y/z (reference h_gravity array,
+  // uniform for the problem that fills it: HydroRunBase.cpp:6400-6408)
+  T nu, eta;
+  int gravity;
+  T gx, gy, gz;
 };
 
 struct RunParams {

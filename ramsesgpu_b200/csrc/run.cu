@@ -109,6 +109,7 @@ class RunImpl final : public Run {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     freeScratch();
     for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
+    cudaFree(dDiss_);
     for (int b = 0; b < 2; ++b) {
       if (batchBuf_[b]) cudaFree(batchBuf_[b]);
       if (evH2D_[b]) cudaEventDestroy(evH2D_[b]);
@@ -235,6 +236,10 @@ class RunImpl final : public Run {
     const bool rotating = rp_.mhdEnabled && kp_.Omega0 > T(0);
     // the rotating-frame step fills the ghosts of UNew at its END (reference MHDRunGodunov.cpp:3429-3437)
     if (!rotating && !ghostsValid_[src]) make_all_boundaries(src);
+    if (kp_.gravity && (rotating || rp_.dim != 3))
+      throw std::runtime_error("static gravity is available for the non-rotating 3D solvers only");
+    if ((kp_.nu > T(0) || kp_.eta > T(0)) && rp_.dim != 3)
+      throw std::runtime_error("viscosity / resistivity are available for the 3D solvers only");
     if (rotating && rp_.dim == 3) {
       stepMhd3dRotating(src, dst, static_cast<T>(dt));
     } else if (rp_.mhdEnabled && rp_.dim == 3) {
@@ -676,7 +681,7 @@ class RunImpl final : public Run {
     };
     // overlap needs three disjoint plane ranges: bottom gw planes, top gw planes (+ the ghost-face
     // plane kN), interior
-    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw;
+    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative();
     if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN + 1);
@@ -687,6 +692,34 @@ class RunImpl final : public Run {
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;  // the update kernel reduced the inverse dt of the new state
+    if (dissipative()) {    // reference mhd_godunov_unsplit_cpu_v3.cpp:661-693
+      fillGhosts(dst, 0, kp_.ksize);
+      dissipativeTerms(dst, dt);
+    }
+  }
+
+  // ---- dissipative terms on the new state (its ghosts have just been refreshed) -------------------
+  bool dissipative() const { return rp_.dim == 3 && (kp_.nu > T(0) || kp_.eta > T(0)); }
+  void dissipativeTerms(int b, T dt) {
+    T* U = dU_[b];
+    if (!dDiss_) {
+      const size_t bytes = cells_ * 12 * sizeof(T);
+      RG_CUDA(cudaMalloc(&dDiss_, bytes));
+      deviceBytes_ += bytes;
+    }
+    phase(PH_DISS, [&] {
+      if (kp_.eta > T(0)) {
+        DissKernels<T>::resistEmf(kp_, U, dDiss_, stream_);
+        DissKernels<T>::ctUpdate(kp_, U, dDiss_, dt, stream_);
+        if (!(kp_.cIso > T(0))) DissKernels<T>::resistEnergy(kp_, U, dt, stream_);
+      }
+      if (kp_.nu > T(0)) {
+        DissKernels<T>::viscFlux(kp_, U, dDiss_, dt, stream_);
+        DissKernels<T>::viscUpdate(kp_, U, dDiss_, stream_);
+      }
+    });
+    ghostsValid_[b] = false;
+    dtCached_[b] = false;  // the state changed after the update kernel reduced its inverse dt
   }
 
   bool shearingBox() const {
@@ -760,11 +793,16 @@ class RunImpl final : public Run {
         MhdKernels<T>::updateRotating(kp_, Uold, Unew, sc, ka, kb, dt, shear, jplus, frac, slots, stream_);
       });
     }
+    dtCached_[dst] = true;
+    if (dissipative()) {  // reference MHDRunGodunov.cpp:3379-3419: ghost refresh, then the dissipative terms
+      if (shear) fillGhostsShear(dst, dt);
+      else fillGhosts(dst, 0, kp_.ksize);
+      dissipativeTerms(dst, dt);
+    }
     // ghosts of the NEW state, at the end of the step
     if (shear) fillGhostsShear(dst, dt);
     else fillGhosts(dst, 0, kp_.ksize);
     ghostsValid_[dst] = true;
-    dtCached_[dst] = true;
   }
 
   // ---- 2D MHD step: reference godunov_unsplit_cpu + _v1 (mhd_godunov_unsplit_cpu_v1.cpp:36-243)
@@ -830,7 +868,7 @@ class RunImpl final : public Run {
         });
       }
     };
-    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw;
+    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative();
     if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN);
@@ -841,6 +879,10 @@ class RunImpl final : public Run {
     }
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;
+    if (dissipative()) {  // viscosity, reference HydroRunGodunov.cpp:2908-2927
+      fillGhosts(dst, 0, kp_.ksize);
+      dissipativeTerms(dst, dt);
+    }
   }
 
   ConfigMap cfg_;
@@ -854,6 +896,7 @@ class RunImpl final : public Run {
   cudaStream_t h2dStream_ = nullptr, d2hStream_ = nullptr;
   cudaEvent_t evH2D_[2] = {nullptr, nullptr}, evD2H_[2] = {nullptr, nullptr}, evStepDone_[2] = {nullptr, nullptr};
   MhdScratch<T> sc_;
+  T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;
   unsigned long long* hMax_ = nullptr;

@@ -29,7 +29,7 @@ struct Stats {
   int chunkPlanes;          // z planes per chunk of the step pipeline
 };
 
-enum Phase { PH_BOUNDARY = 0, PH_PRIM, PH_TRACE, PH_FLUX, PH_EMF, PH_UPDATE, PH_DT, PH_COPY, PH_HALO, PH_FUSED, PH_COUNT };
+enum Phase { PH_BOUNDARY = 0, PH_PRIM, PH_TRACE, PH_FLUX, PH_EMF, PH_UPDATE, PH_DT, PH_COPY, PH_HALO, PH_FUSED, PH_DISS, PH_COUNT };
 
 struct DistInit {
   int rank = 0, nranks = 1;

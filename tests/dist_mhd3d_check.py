@@ -34,6 +34,12 @@ def main():
         ini = ot3d_ini((20, 16, nz), OrszagTang={"kt": 1.0}, mesh=mesh)
     elif problem == "mri":      # BASELINE.json configs[3]: shearing box, z-slabs
         ini = ini_override(str(load_golden("mri3d_12x20x8_s40")["ini"]), {"mesh": {"nx": 12, "ny": 20, "nz": nz}})
+    elif problem == "ot3d_diss":  # resistivity + viscosity: ghost refresh (z halo) of the new state inside the step
+        ini = ot3d_ini((20, 16, nz), OrszagTang={"kt": 1.0}, mesh=mesh, hydro={"nu": 0.004}, MHD={"eta": 0.003})
+    elif problem == "mri_diss":
+        ini = ini_override(str(load_golden("mri3d_diss_12x20x8_s10")["ini"]), {"mesh": {"nx": 12, "ny": 20, "nz": nz}})
+    elif problem == "rt_mhd":     # static gravity, rand() stream over every cell of the global array (ghosts included)
+        ini = ini_override(str(load_golden("rt3d_mhd_visc_rand_8x10x16_s5")["ini"]), {"mesh": {"nx": 8, "ny": 10, "nz": nz}})
     elif problem == "implode":  # configs[4]: hydro, Dirichlet walls (physical z faces on the outer slabs)
         ini = ini_override(str(load_golden("implode3d_16_s8")["ini"]), {"mesh": {"nx": 16, "ny": 12, "nz": nz}})
         Run = HydroRunGodunov

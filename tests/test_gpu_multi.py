@@ -16,7 +16,8 @@ def _ngpu():
 
 @pytest.mark.parametrize("bc,overlap,problem", [
     ("periodic", "overlap", "ot3d"), ("open", "overlap", "ot3d"), ("periodic", "nooverlap", "ot3d"),
-    ("periodic", "overlap", "mri"), ("periodic", "overlap", "implode"), ("periodic", "overlap", "kh32")])
+    ("periodic", "overlap", "mri"), ("periodic", "overlap", "implode"), ("periodic", "overlap", "kh32"),
+    ("periodic", "overlap", "ot3d_diss"), ("periodic", "overlap", "mri_diss"), ("periodic", "overlap", "rt_mhd")])
 def test_slabs_over_nccl_match_single_gpu(native, bc, overlap, problem):
     n = _ngpu()
     if n < 2:
