@@ -12,6 +12,8 @@
 
 namespace rg {
 
+int g_hydroTile = 1;  // run-time knob "hydro_tile": register-tiled flux+update kernel (default) or the gather variant
+
 namespace {
 
 enum { H_R = 0, H_P, H_U, H_V, H_W, H_DX = 5, H_DY = 10, H_DZ = 15 };  // slopes: (r, p, u, v, w) each
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(BX) k_hydro_trace(const __grid_constant__ KPar
     W(H_DZ + c, i, j, k) = dz_[c];
   }
 }
+
 
 // state at a face of cell (i,j,k): W centre +/- half slope along DIR, floors (trace.h:603-660),
 // rotated so that .u is the velocity normal to the face
@@ -187,6 +190,163 @@ __global__ void __launch_bounds__(128) k_hydro_flux_update(const __grid_constant
   if (slots != nullptr) reduceMaxToSlots(invDt, slots);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// flux + conservative update + next dt, register-tiled ("tile" variant, default): a 32 x HR thread
+// block marches along z over a (32-2) x (HR-2) column of updated cells surrounded by a one-cell halo.
+// Every thread loads the 20 W components of ITS OWN cell once per plane (coalesced, each W value is
+// read from HBM once per tile instead of six times through L1) and builds its six face states in
+// registers.  The left state of a face comes from the neighbour: lane-1 by warp shuffle (x), row-1
+// through shared memory (y), the thread's own high-z state of the previous plane by register carry
+// (z).  Every face flux of the tile is solved exactly once (no serial closing-face solves); the high
+// z flux of a cell is the low z flux of the next plane, so the update of plane p is finished one
+// iteration later.  Faces on tile seams are solved by both tiles with identical inputs and code,
+// hence bitwise identical and conservative.  3.4 Riemann problems per updated cell.
+// ------------------------------------------------------------------------------------------------
+constexpr int HR = 8;  // rows of the thread block
+
+template <typename T, int DIR>
+__device__ __forceinline__ dev::HState<T> face_from_regs(const KParams<T>& P, const T (&w)[NW_HYDRO], T sgn) {
+  constexpr int S = (DIR == 0) ? H_DX : (DIR == 1) ? H_DY : H_DZ;
+  dev::HState<T> s;
+  s.r = dev::mx(P.smallr, w[H_R] + sgn * w[S + 0]);
+  s.p = dev::mx(P.smallp * s.r, w[H_P] + sgn * w[S + 1]);
+  const T u = w[H_U] + sgn * w[S + 2], v = w[H_V] + sgn * w[S + 3], ww = w[H_W] + sgn * w[S + 4];
+  if (DIR == 0) { s.u = u; s.v = v; s.w = ww; }
+  else if (DIR == 1) { s.u = v; s.v = u; s.w = ww; }
+  else { s.u = ww; s.v = v; s.w = u; }
+  return s;
+}
+
+// Riemann flux of a face normal to DIR from its rotated left/right states, in physical component order
+template <typename T, int DIR, int RS>
+__device__ __forceinline__ void face_flux(const KParams<T>& P, const dev::HState<T>& L, const dev::HState<T>& R, T (&f)[5]) {
+  T fr[5];
+  dev::riemann_hydro<RS>(P, L, R, fr);
+  f[ID] = fr[ID]; f[IP] = fr[IP];
+  f[IU] = (DIR == 0) ? fr[IU] : (DIR == 1) ? fr[IV] : fr[IW];
+  f[IV] = (DIR == 1) ? fr[IU] : fr[IV];
+  f[IW] = (DIR == 2) ? fr[IU] : fr[IW];
+}
+
+template <typename T, int RS>
+__global__ void __launch_bounds__(32 * HR) k_hydro_flux_update_tile(const __grid_constant__ KParams<T> P,
+                                                                    const T* __restrict__ Uold, T* __restrict__ Unew,
+                                                                    const T* __restrict__ Wp, int planes, int kbase,
+                                                                    int k0, int k1, int lzc, T dt,
+                                                                    unsigned long long* __restrict__ slots) {
+  __shared__ T sy[HR][5][32];  // high-y face states, then low-y fluxes, of the current plane
+  const int tx = threadIdx.x, ty = threadIdx.y, gw = P.gw;
+  const int i = gw + blockIdx.x * 30 - 1 + tx, j = gw + blockIdx.y * (HR - 2) - 1 + ty;
+  const int za = k0 + blockIdx.z * lzc, zb = min(za + lzc, k1);  // updated planes [za, zb)
+  const int iN = P.isize - gw, jN = P.jsize - gw;
+  const bool cellOK = i <= P.isize - 2 && j <= P.jsize - 2;  // W exists (i, j >= 1 by construction)
+  const bool rowUpd = ty >= 1 && ty <= HR - 2 && j < jN, colUpd = tx >= 1 && tx <= 30 && i < iN;
+  const bool upd = rowUpd && colUpd;
+  const bool solveX = tx >= 1 && i <= iN && rowUpd;  // low x face of the cell is a face of an updated cell of this tile
+  const bool solveY = ty >= 1 && j <= jN && colUpd;
+  const View<const T> W = view<const T>(Wp, P, planes, kbase);
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  T invDt = T(0);
+  dev::HState<T> zPrev{T(1), T(1), T(0), T(0), T(0)};  // high-z face state of the previous plane
+  T acc[5] = {T(0), T(0), T(0), T(0), T(0)};            // update of the previous plane, all terms but the high z flux
+  for (int p = za - 1; p <= zb; ++p) {
+    T w[NW_HYDRO];
+#pragma unroll
+    for (int c = 0; c < NW_HYDRO; ++c) w[c] = cellOK ? W(c, i, j, p) : T(1);
+    const bool mid = p >= za && p < zb;  // block-uniform
+    T un[5];
+    if (mid && upd) {
+      const size_t idx = (size_t)p * plane + (size_t)j * P.isize + i;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
+    }
+    T fz[5] = {T(0), T(0), T(0), T(0), T(0)};
+    if (p >= za && upd) face_flux<T, 2, RS>(P, zPrev, face_from_regs<T, 2>(P, w, T(-1)), fz);
+    if (p > za && upd) {  // the low z flux of this plane closes the update of the plane below
+      const size_t idx = (size_t)(p - 1) * plane + (size_t)j * P.isize + i;
+      T r5[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) r5[v] = acc[v] - fz[v] * dtdz;
+      if (P.gravity) {  // static gravity source term, reference HydroRunBase.cpp:1962-1976
+        const T hdt = T(0.5) * dt, rs = __ldg(Uold + idx) + r5[ID];
+        r5[IU] += hdt * P.gx * rs; r5[IV] += hdt * P.gy * rs; r5[IW] += hdt * P.gz * rs;
+      }
+#pragma unroll
+      for (int v = 0; v < 5; ++v) Unew[v * comp + idx] = r5[v];
+      T q[5];
+      const T c = dev::cons_to_prim_hydro(P, r5[ID], r5[IP], r5[IU], r5[IV], r5[IW], q);
+      invDt = dev::mx(invDt, (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz);
+    }
+    zPrev = face_from_regs<T, 2>(P, w, T(1));
+    if (!mid) continue;  // block-uniform: first (za-1) and last (zb) planes only feed the z faces
+    // x faces: left state from lane-1, high flux from lane+1
+    T fxl[5] = {T(0), T(0), T(0), T(0), T(0)}, fxh[5];
+    {
+      const dev::HState<T> hi = face_from_regs<T, 0>(P, w, T(1));
+      dev::HState<T> L;
+      L.r = __shfl_up_sync(0xffffffffu, hi.r, 1); L.p = __shfl_up_sync(0xffffffffu, hi.p, 1);
+      L.u = __shfl_up_sync(0xffffffffu, hi.u, 1); L.v = __shfl_up_sync(0xffffffffu, hi.v, 1);
+      L.w = __shfl_up_sync(0xffffffffu, hi.w, 1);
+      if (solveX) face_flux<T, 0, RS>(P, L, face_from_regs<T, 0>(P, w, T(-1)), fxl);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) fxh[v] = __shfl_down_sync(0xffffffffu, fxl[v], 1);
+    }
+    // y faces: left state from row-1, high flux from row+1, both through shared memory
+    T fyl[5] = {T(0), T(0), T(0), T(0), T(0)}, fyh[5];
+    {
+      const dev::HState<T> hi = face_from_regs<T, 1>(P, w, T(1));
+      sy[ty][0][tx] = hi.r; sy[ty][1][tx] = hi.p; sy[ty][2][tx] = hi.u; sy[ty][3][tx] = hi.v; sy[ty][4][tx] = hi.w;
+      __syncthreads();
+      if (solveY) {
+        const dev::HState<T> L{sy[ty - 1][0][tx], sy[ty - 1][1][tx], sy[ty - 1][2][tx], sy[ty - 1][3][tx], sy[ty - 1][4][tx]};
+        face_flux<T, 1, RS>(P, L, face_from_regs<T, 1>(P, w, T(-1)), fyl);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < 5; ++v) sy[ty][v][tx] = fyl[v];
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < 5; ++v) fyh[v] = (ty < HR - 1) ? sy[ty + 1][v][tx] : T(0);
+      __syncthreads();  // sy is rewritten by the next plane
+    }
+    if (upd) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {  // summation order of the reference's serial scatter
+        T s = un[v];
+        s += fxl[v] * dtdx; s += fyl[v] * dtdy; s += fz[v] * dtdz;
+        s -= fxh[v] * dtdx; s -= fyh[v] * dtdy;
+        acc[v] = s;
+      }
+    }
+  }
+  if (slots != nullptr) reduceMaxToSlots(invDt, slots);
+}
+
+// x/y ghost cells of planes [k0, k1) keep the old values (the tile kernel only writes inner cells)
+template <typename T>
+__global__ void __launch_bounds__(256) k_hydro_copy_ghosts(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                                           T* __restrict__ Unew, int k0) {
+  const int gw = P.gw, ng = 2 * gw;
+  const int nRowCells = ng * P.isize, nColCells = ng * (P.jsize - ng);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nRowCells + nColCells) return;
+  int i, j;
+  if (t < nRowCells) {
+    const int r = t / P.isize;
+    i = t - r * P.isize;
+    j = (r < gw) ? r : P.jsize - ng + r;
+  } else {
+    const int q = t - nRowCells, r = q / ng, c = q - r * ng;
+    j = gw + r;
+    i = (c < gw) ? c : P.isize - ng + c;
+  }
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)(k0 + blockIdx.y) * plane + (size_t)j * P.isize + i;
+  for (int v = 0; v < P.nvar; ++v) Unew[v * comp + idx] = Uold[v * comp + idx];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BX) k_hydro_invdt(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                                     unsigned long long* __restrict__ slots) {
@@ -226,6 +386,20 @@ template <typename T>
 void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, const T* W, int planes, int kbase, int k0,
                                  int k1, T dt, unsigned long long* slots, cudaStream_t s) {
   if (k1 <= k0) return;
+  if (g_hydroTile) {  // register-tiled variant (default): z ranges of up to 64 planes
+    const int lzc = std::min(k1 - k0, 64);
+    const dim3 g((P.nx + 29) / 30, (P.ny + HR - 3) / (HR - 2), (k1 - k0 + lzc - 1) / lzc), b(32, HR, 1);
+    switch (P.riemannSolver) {
+      case RS_HLLC: k_hydro_flux_update_tile<T, RS_HLLC><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
+      case RS_HLL: k_hydro_flux_update_tile<T, RS_HLL><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
+      case RS_APPROX: k_hydro_flux_update_tile<T, RS_APPROX><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
+      default: k_hydro_flux_update_tile<T, -1><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
+    }
+    const int ng = 2 * P.gw, cells = ng * P.isize + ng * (P.jsize - ng);
+    k_hydro_copy_ghosts<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
+    g_launches += 2;
+    return;
+  }
   // z ranges of about 32 planes (one redundant z face per range), at least a few waves of blocks
   const int lzc = std::min(k1 - k0, 32);
   const dim3 g((P.isize + 31) / 32, (P.jsize + 3) / 4, (k1 - k0 + lzc - 1) / lzc), b(32, 4, 1);

@@ -1199,6 +1199,10 @@ bool setTuning(const char* key, int value) {
     g_fusedA = value ? 1 : 0;
     return true;
   }
+  if (k == "hydro_tile") {
+    g_hydroTile = value ? 1 : 0;
+    return true;
+  }
   if (k == "trace_qy") {
     if (value != 8 && value != 12) return false;
     g_traceQY = value;

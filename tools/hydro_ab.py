@@ -1,0 +1,22 @@
+"""A/B timing of the hydro flux+update kernel variants at 512^3 FP32 (BASELINE.json configs[2]) on the GPU box:
+   python tools/hydro_ab.py"""
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np
+from ramsesgpu_b200 import HydroRunGodunov, set_tuning
+from ramsesgpu_b200.io import ini_override
+G = "tests/golden/"
+ini = ini_override(str(np.load(G + "kh3d_16x8x16_f32_s10.npz")["ini"]), {"mesh": {"nx": 512, "ny": 512, "nz": 512},
+      "run": {"nstepmax": 1000000, "tend": 1e9, "noutput": -1}, "output": {"outputVtk": "no", "outputXsm": "no", "outputHdf5": "no"}})
+with HydroRunGodunov(ini, fp32=True) as run:
+    run.init_simulation(); run.make_all_boundaries(0)
+    s = (0, 0.0, 0.0)
+    for _ in range(3): s = run.oneStepIntegration(*s)
+    for rep in range(2):
+        for tile in (0, 1):
+            set_tuning("hydro_tile", tile)
+            for _ in range(2): s = run.oneStepIntegration(*s)
+            run.profile_begin()
+            for _ in range(5): s = run.oneStepIntegration(*s)
+            tot, ph = run.profile_end()
+            print("hydro_tile=%d total %.3f ms/step %.0f Mcell/s |" % (tile, tot / 5, 512**3 * 5 / tot / 1e3), " ".join("%s %.3f" % (k, v[0] / 5) for k, v in ph.items() if v[0] > 0), flush=True)
