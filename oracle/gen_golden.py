@@ -46,6 +46,25 @@ def case(name, ini_file, overrides, steps, precision="f64"):
     print(name, "steps", steps, "dt0", dt0, "t", ttot, "last dt", dtl, "vars", names)
 
 
+def history_case(name, ini_file, overrides, steps, dt_hist):
+    """History diagnostics (MHDRunBase.cpp:3311 / :3476) written by the reference into <prefix>_history.txt:
+    the table is frozen together with the ini (values are printed with 6 significant digits)."""
+    text = open(os.path.join(REF_DATA, ini_file)).read()
+    ov = {k: dict(v) for k, v in overrides.items()}
+    ov.setdefault("run", {}).update({"nstepmax": steps, "noutput": steps, "tend": 1.0e6})
+    ov.setdefault("output", {}).update(VTK_ON)
+    ov.setdefault("history", {}).update({"enabled": "yes", "dtHist": dt_hist, "filename": "history.txt"})
+    text = ini_override(text, ov)
+    stdout, wd = run_reference(text)
+    prefix = re.search(r"outputPrefix=(\S+)", text).group(1)
+    lines = open(os.path.join(wd, prefix + "_history.txt")).read().splitlines()
+    header = [l for l in lines if l.startswith("# totalTime")][0][2:].split()
+    table = np.array([[float(x) for x in l.split()] for l in lines if l and not l.startswith("#")])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ini=np.array(text), steps=steps, columns=np.array(header), table=table)
+    print(name, header, table.shape)
+    print(table)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
@@ -95,3 +114,12 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         case(name, ini, ov, steps, prec)
+    hist = {
+        # SURVEY 8(f).3 -- history files of the reference: MRI stresses, and mass / div B of Orszag-Tang
+        "mri3d_history_12x20x8_s10": ("mhd_mri_3d.ini", {"mesh": {"nx": 12, "ny": 20, "nz": 8}}, 10, 24.0),
+        "ot3d_history_16_s8": ("orszag-tang3d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 16}, "OrszagTang": {"kt": 1.0}}, 8, 0.0045),
+    }
+    for name, (ini, ov, steps, dth) in hist.items():
+        if only and name not in only:
+            continue
+        history_case(name, ini, ov, steps, dth)

@@ -107,6 +107,14 @@ void   orc_trace_mhd_3d(const orc_params *p, const real_t q[8], const real_t dq[
                         real_t qm[3][8], real_t qp[3][8], real_t qEdge[4][3][8]);
 void   orc_riemann_hydro(const orc_params *p, const real_t ql[5], const real_t qr[5], real_t flux[5]);
 
+/* history diagnostics of a 3D MHD state, MHDRunBase.cpp:3311-3410 / :3476-3620:
+   out = mass, maxwell, reynolds, magp, mean_Bx, mean_By, mean_Bz, divB */
+void orc_history_mhd3d(const orc_params *p, const real_t *U, double out[8]);
+
+/* dissipative block in two stages + switch that removes it from the step drivers (slab protocol test) */
+void orc_set_skip_dissipative(int on);
+void orc_dissipative_stage(const orc_params *p, real_t *Unew, real_t dt, int stage);
+
 int orc_sizeof_real(void);
 
 #ifdef __cplusplus

@@ -73,6 +73,9 @@ class Oracle:
         L.orc_trace_mhd_3d.argtypes = [P, RP, RP, RP, RP, RP, R, R, R, R, RP, RP, RP]
         L.orc_trace_mhd_3d.restype = None
         L.orc_riemann_hydro.argtypes = [P, RP, RP, RP]; L.orc_riemann_hydro.restype = None
+        L.orc_set_skip_dissipative.argtypes = [C.c_int]; L.orc_set_skip_dissipative.restype = None
+        L.orc_dissipative_stage.argtypes = [P, RP, R, C.c_int]; L.orc_dissipative_stage.restype = None
+        L.orc_history_mhd3d.argtypes = [P, RP, C.POINTER(C.c_double)]; L.orc_history_mhd3d.restype = None
 
     # -- helpers ---------------------------------------------------------------------------
     def _p(self, a):
@@ -120,6 +123,19 @@ class Oracle:
         dts = np.zeros(max(nsteps, 1), dtype=self.dtype)
         which = self.lib.orc_run_steps(C.byref(p), self._p(U), self._p(U2), nsteps, C.byref(t), self._p(dts))
         return (U2 if which else U), float(t.value), dts[:nsteps]
+
+    def set_skip_dissipative(self, on):
+        self.lib.orc_set_skip_dissipative(1 if on else 0)
+
+    def dissipative_stage(self, p, U, dt, stage):
+        self.lib.orc_dissipative_stage(C.byref(p), self._p(U), dt, stage)
+
+    HISTORY_NAMES = ("mass", "maxwell", "reynolds", "magp", "mean_Bx", "mean_By", "mean_Bz", "divB")
+
+    def history_mhd3d(self, p, U):
+        out = (C.c_double * 8)()
+        self.lib.orc_history_mhd3d(C.byref(p), self._p(U), out)
+        return dict(zip(self.HISTORY_NAMES, [float(v) for v in out]))
 
     def riemann_mhd(self, p, ql, qr):
         ql = np.ascontiguousarray(ql, self.dtype); qr = np.ascontiguousarray(qr, self.dtype)

@@ -191,28 +191,102 @@ void orc_hydro_update_3d(const orc_params *P, real_t *U, const real_t *fx, const
 
 /* the dissipative block at the end of the 3D step: ghost refresh of UNew, resistivity, viscosity.
  * mhd_godunov_unsplit_cpu_v3.cpp:661-693 ; MHDRunGodunov.cpp:3379-3419 (rotating) ;
- * HydroRunGodunov.cpp:2908-2927 (hydro: viscosity only) */
-void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear) {
+ * HydroRunGodunov.cpp:2908-2927 (hydro: viscosity only).
+ * Split in two stages for the z-slab protocol test (tests/test_slab_protocol_gloo.py): stage 0 = resistive
+ * emf + constrained transport, stage 1 = resistive energy flux + viscosity; the caller fills the ghosts
+ * before stage 0.  orc_dissipative_3d = ghost fill + stage 0 + stage 1. */
+static int g_skip_dissipative = 0;
+void orc_set_skip_dissipative(int on) { g_skip_dissipative = on; }
+
+void orc_dissipative_stage(const orc_params *P, real_t *Unew, real_t dt, int stage) {
   const real_t nu = P->nu, eta = P->mhdEnabled ? P->eta : 0;
-  if (!(nu > 0) && !(eta > 0)) return;
-  if (P->dim != 3) return;
+  if ((!(nu > 0) && !(eta > 0)) || P->dim != 3) return;
   const size_t ncell = (size_t)P->isize * P->jsize * P->ksize;
-  if (shear) orc_make_all_boundaries_shear(P, Unew, dt, totalTime);
-  else orc_make_all_boundaries(P, Unew);
-  real_t *fx = calloc(ncell * 5, sizeof(real_t)), *fy = calloc(ncell * 5, sizeof(real_t)), *fz = calloc(ncell * 5, sizeof(real_t));
-  if (eta > 0) {
-    real_t *emf = calloc(ncell * 3, sizeof(real_t));
-    orc_resistivity_emf_3d(P, Unew, emf);
-    orc_ct_update_3d(P, Unew, emf, dt);
-    if (P->cIso <= 0) {
-      orc_resistivity_energy_flux_3d(P, Unew, fx, fy, fz, dt);
-      orc_hydro_update_3d(P, Unew, fx, fy, fz, 1);
+  if (stage == 0) {
+    if (eta > 0) {
+      real_t *emf = calloc(ncell * 3, sizeof(real_t));
+      orc_resistivity_emf_3d(P, Unew, emf);
+      orc_ct_update_3d(P, Unew, emf, dt);
+      free(emf);
     }
-    free(emf);
+    return;
+  }
+  real_t *fx = calloc(ncell * 5, sizeof(real_t)), *fy = calloc(ncell * 5, sizeof(real_t)), *fz = calloc(ncell * 5, sizeof(real_t));
+  if (eta > 0 && P->cIso <= 0) {
+    orc_resistivity_energy_flux_3d(P, Unew, fx, fy, fz, dt);
+    orc_hydro_update_3d(P, Unew, fx, fy, fz, 1);
   }
   if (nu > 0) {
     orc_viscosity_flux_3d(P, Unew, fx, fy, fz, dt);
     orc_hydro_update_3d(P, Unew, fx, fy, fz, 0);
   }
   free(fx); free(fy); free(fz);
+}
+
+void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear) {
+  const real_t nu = P->nu, eta = P->mhdEnabled ? P->eta : 0;
+  if (g_skip_dissipative) return;
+  if (!(nu > 0) && !(eta > 0)) return;
+  if (P->dim != 3) return;
+  if (shear) orc_make_all_boundaries_shear(P, Unew, dt, totalTime);
+  else orc_make_all_boundaries(P, Unew);
+  orc_dissipative_stage(P, Unew, dt, 0);
+  orc_dissipative_stage(P, Unew, dt, 1);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * History diagnostics, 3D MHD: MHDRunBase.cpp:3311-3410 (history_default: mass, divB)
+ * and :3476-3620 (history_mri: + Maxwell / Reynolds stresses, magnetic pressure, mean field).
+ * Accumulation in double in the reference's loop order.  out[8] = mass, maxwell, reynolds, magp,
+ * mean_Bx, mean_By, mean_Bz, divB  (history_default prints mass and divB only).
+ * ---------------------------------------------------------------------------------------- */
+void orc_history_mhd3d(const orc_params *P, const real_t *U, double out[8]) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  const real_t dx = P->dx, dy = P->dy, dz = P->dz;
+  double mass = 0.0, magp = 0.0, maxwell = 0.0, mbx = 0.0, mby = 0.0, mbz = 0.0;
+#define SQR_(x) ((x) * (x))
+  for (int k = gw; k < ksz - gw; ++k)
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        mass += AT(U, i, j, k, ID);
+        magp += 0.25 * SQR_(AT(U, i, j, k, IA) + AT(U, i + 1, j, k, IA));
+        magp += 0.25 * SQR_(AT(U, i, j, k, IB) + AT(U, i, j + 1, k, IB));
+        magp += 0.25 * SQR_(AT(U, i, j, k, IC) + AT(U, i, j, k + 1, IC));
+        maxwell -= 0.25 * (AT(U, i, j, k, IA) + AT(U, i + 1, j, k, IA)) * (AT(U, i, j, k, IB) + AT(U, i, j + 1, k, IB));
+        mbx += AT(U, i, j, k, IA);
+        mby += AT(U, i, j, k, IB);
+        mbz += AT(U, i, j, k, IC);
+      }
+  double dTau = dx * dy * dz / (P->xMax - P->xMin) / (P->yMax - P->yMin) / (P->zMax - P->zMin);
+  magp = magp * dTau / 2.;
+  mass = mass * dTau;
+  maxwell = maxwell * dTau;
+  mbx *= dTau; mby *= dTau; mbz *= dTau;
+  /* y-z averages of rho, u, v per x column (ghost columns included), :3565-3586 */
+  real_t *mean = calloc((size_t)isz * 3, sizeof(real_t));
+  for (int k = gw; k < ksz - gw; ++k)
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = 0; i < isz; ++i) {
+        mean[i] += AT(U, i, j, k, ID);
+        mean[isz + i] += AT(U, i, j, k, IU) / AT(U, i, j, k, ID);
+        mean[2 * isz + i] += AT(U, i, j, k, IV) / AT(U, i, j, k, ID);
+      }
+  for (int i = 0; i < isz; ++i) {
+    mean[i] /= (P->ny * P->nz);
+    mean[isz + i] /= (P->ny * P->nz);
+    mean[2 * isz + i] /= (P->ny * P->nz);
+  }
+  double reynolds = 0.0, divB = 0.0;
+  for (int k = gw; k < ksz - gw; ++k)
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        reynolds += AT(U, i, j, k, ID) * dTau * (AT(U, i, j, k, IU) / AT(U, i, j, k, ID) - mean[isz + i]) *
+                    (AT(U, i, j, k, IV) / AT(U, i, j, k, ID) - mean[2 * isz + i]);
+        divB += (AT(U, i + 1, j, k, IA) - AT(U, i, j, k, IA)) / dx + (AT(U, i, j + 1, k, IB) - AT(U, i, j, k, IB)) / dy +
+                (AT(U, i, j, k + 1, IC) - AT(U, i, j, k, IC)) / dz;
+      }
+  free(mean);
+#undef SQR_
+  out[0] = mass; out[1] = maxwell; out[2] = reynolds; out[3] = magp;
+  out[4] = mbx; out[5] = mby; out[6] = mbz; out[7] = divB;
 }

@@ -2,6 +2,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <vector>
@@ -74,17 +76,97 @@ void writeXsm(const std::string& path, const Layout& L, const T* U, int iVar) {
     }
 }
 
-template <typename T>
-void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep) {
+namespace {
+std::string outputBase(const RunParams& rp, const Layout& L, std::string* rankTag) {
   std::string base = rp.outputDir;
   if (!base.empty() && base.back() != '/') base += "/";
   base += rp.outputPrefix;
-  std::string rankTag;
+  rankTag->clear();
   if (L.nranks > 1) {
     char buf[32];
     std::snprintf(buf, sizeof buf, "_rank%04d", L.rank);
-    rankTag = buf;
+    *rankTag = buf;
   }
+  return base;
+}
+}  // namespace
+
+std::string vtiPath(const RunParams& rp, const Layout& L, int nStep) {
+  std::string rankTag;
+  const std::string base = outputBase(rp, L, &rankTag);
+  return base + rankTag + "_" + stepString(nStep) + ".vti";
+}
+
+void writeRestartMeta(const std::string& vti, const RestartMeta& m) {
+  std::FILE* f = std::fopen((vti + ".meta").c_str(), "w");
+  if (!f) return;
+  // %a: exact hexadecimal floats, the decimal values are for the reader's eyes only
+  std::fprintf(f, "nStep %d\ntotalTime %a\ndt %a\n# totalTime = %.17g, dt = %.17g\n", m.nStep, m.totalTime, m.dt,
+               m.totalTime, m.dt);
+  std::fclose(f);
+}
+
+bool readRestartMeta(const std::string& vti, RestartMeta* m) {
+  std::FILE* f = std::fopen((vti + ".meta").c_str(), "r");
+  if (!f) return false;
+  char key[64], val[128];
+  int got = 0;
+  while (std::fscanf(f, "%63s %127[^\n]", key, val) == 2) {
+    if (!std::strcmp(key, "nStep")) { m->nStep = std::atoi(val); ++got; }
+    else if (!std::strcmp(key, "totalTime")) { m->totalTime = std::strtod(val, nullptr); ++got; }
+    else if (!std::strcmp(key, "dt")) { m->dt = std::strtod(val, nullptr); ++got; }
+  }
+  std::fclose(f);
+  return got == 3;
+}
+
+template <typename T>
+bool readVti(const std::string& path, const Layout& L, T* U, bool* ghostIncluded, std::string* msg) {
+  std::ifstream in(path.c_str(), std::ios::in | std::ios::binary);
+  if (!in) { if (msg) *msg = "cannot open restart file '" + path + "'"; return false; }
+  std::string header, line;
+  const std::string marker = "<AppendedData encoding=\"raw\">";
+  bool found = false;
+  while (std::getline(in, line)) {
+    header += line + "\n";
+    if (line.find(marker) != std::string::npos) { found = true; break; }
+  }
+  if (!found || in.get() != '_') { if (msg) *msg = "'" + path + "' is not a raw-appended .vti"; return false; }
+  int e[6] = {0, 0, 0, 0, 0, 0};
+  const size_t w = header.find("WholeExtent=\"");
+  if (w == std::string::npos || std::sscanf(header.c_str() + w + 13, "%d %d %d %d %d %d", e, e + 1, e + 2, e + 3, e + 4, e + 5) != 6) {
+    if (msg) *msg = "'" + path + "': no WholeExtent";
+    return false;
+  }
+  const char* type = sizeof(T) == 8 ? "Float64" : "Float32";
+  if (header.find(type) == std::string::npos) { if (msg) *msg = "'" + path + "': precision does not match the run"; return false; }
+  const int nx = e[1] + 1, ny = e[3] + 1, nz = e[5] + 1;
+  const int gw = L.ghostWidth, kd = (L.dim == 2) ? 1 : L.ksize;
+  int g;
+  if (nx == L.isize && ny == L.jsize && nz == kd) g = 0;
+  else if (nx == L.isize - 2 * gw && ny == L.jsize - 2 * gw && nz == ((L.dim == 2) ? 1 : L.ksize - 2 * gw)) g = gw;
+  else { if (msg) *msg = "'" + path + "': grid size does not match the run"; return false; }
+  if (ghostIncluded) *ghostIncluded = (g == 0);
+  const int k0 = (L.dim == 2) ? 0 : g;
+  const size_t plane = (size_t)L.isize * L.jsize, comp = plane * L.ksize, n = (size_t)nx * ny * nz;
+  for (int v = 0; v < L.nvar; ++v) {
+    uint32_t nbytes = 0;
+    in.read(reinterpret_cast<char*>(&nbytes), sizeof nbytes);
+    if (!in || nbytes != (uint32_t)(n * sizeof(T))) { if (msg) *msg = "'" + path + "': truncated or wrong variable count"; return false; }
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j) {
+        T* dst = U + (size_t)v * comp + (size_t)(k + k0) * plane + (size_t)(j + g) * L.isize + g;
+        in.read(reinterpret_cast<char*>(dst), (std::streamsize)nx * sizeof(T));
+      }
+    if (!in) { if (msg) *msg = "'" + path + "': truncated"; return false; }
+  }
+  return true;
+}
+
+template <typename T>
+void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep) {
+  std::string rankTag;
+  const std::string base = outputBase(rp, L, &rankTag);
   if (rp.outputVtk && !rp.outputVtkAscii)
     writeVti<T>(base + rankTag + "_" + stepString(nStep) + ".vti", L, U, rp.ghostIncluded);
   if (rp.outputXsm)
@@ -93,6 +175,8 @@ void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep) {
 
 template void writeVti<double>(const std::string&, const Layout&, const double*, bool);
 template void writeVti<float>(const std::string&, const Layout&, const float*, bool);
+template bool readVti<double>(const std::string&, const Layout&, double*, bool*, std::string*);
+template bool readVti<float>(const std::string&, const Layout&, float*, bool*, std::string*);
 template void writeXsm<double>(const std::string&, const Layout&, const double*, int);
 template void writeXsm<float>(const std::string&, const Layout&, const float*, int);
 template void writeOutputs<double>(const RunParams&, const Layout&, const double*, int);

@@ -17,4 +17,22 @@ void writeXsm(const std::string& path, const Layout& L, const T* U, int iVar);
 template <typename T>
 void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep);
 
+
+// Checkpoint / resume.  The reference restarts from its HDF5 output ("total time" and
+// "time step" attributes, HydroRunBase.cpp:5100-5110, MHDRunBase.cpp:1234-1282); HDF5 is not available
+// here, so the restart input is the raw-appended .vti written by writeOutputs plus a small text sidecar
+// `<same name>.meta` holding what the .vti cannot: time step, total time and dt as exact hex floats.
+struct RestartMeta {
+  int nStep = 0;
+  double totalTime = 0.0, dt = 0.0;
+};
+void writeRestartMeta(const std::string& vtiPath, const RestartMeta& m);
+bool readRestartMeta(const std::string& vtiPath, RestartMeta* m);
+// path of the .vti of step nStep for this rank (same naming as writeOutputs)
+std::string vtiPath(const RunParams& rp, const Layout& L, int nStep);
+// reads a .vti written by writeVti into the local array U ([var][k][j][i], ghosts included; cells outside
+// the file's extent are left untouched).  Returns false with a message when the file does not match.
+template <typename T>
+bool readVti(const std::string& path, const Layout& L, T* U, bool* ghostIncluded, std::string* msg);
+
 }  // namespace rg

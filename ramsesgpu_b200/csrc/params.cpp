@@ -19,6 +19,10 @@ RunParams parseRunParams(const ConfigMap& cfg) {
   rp.tEnd = cfg.getFloat("run", "tend", 0.0f);
   rp.nOutput = static_cast<int>(cfg.getInteger("run", "noutput", 100));
   rp.nLog = static_cast<int>(cfg.getInteger("run", "nlog", 0));
+  rp.restart = cfg.getBool("run", "restart", false);
+  rp.restartFilename = cfg.getString("run", "restart_filename", "");
+  rp.historyEnabled = cfg.getBool("history", "enabled", false);
+  rp.historyFilename = cfg.getString("history", "filename", "history.txt");
   rp.nx = static_cast<int>(cfg.getInteger("mesh", "nx", 2));
   rp.ny = static_cast<int>(cfg.getInteger("mesh", "ny", 2));
   rp.nz = static_cast<int>(cfg.getInteger("mesh", "nz", 1));

@@ -53,6 +53,11 @@ struct RunParams {
   // outputs
   bool outputVtk = true, outputVtkAscii = false, outputXsm = false, ghostIncluded = false;
   std::string outputDir = "./", outputPrefix = "output";
+  // [run] restart / restart_filename (reference MHDRunBase.cpp:1234-1244); [history] (MHDRunBase.cpp:3234-3283)
+  bool restart = false;
+  std::string restartFilename;
+  bool historyEnabled = false;
+  std::string historyFilename = "history.txt";
 };
 
 RunParams parseRunParams(const ConfigMap& cfg);

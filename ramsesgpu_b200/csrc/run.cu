@@ -178,7 +178,21 @@ class RunImpl final : public Run {
     const std::string problem = problemIn.empty() ? rp_.problem : problemIn;
     std::vector<T> h;
     std::string msg;
-    if (!initProblem<T>(cfg_, rp_, kp_, problem, h, &msg)) {
+    int startStep = 0;
+    double startTime = 0.0;
+    if (rp_.restart) {  // reference MHDRunBase.cpp:1234-1282: reload a dump instead of the problem's initial condition
+      std::string path = rp_.outputDir;
+      if (!path.empty() && path.back() != '/') path += "/";
+      path += rp_.restartFilename;
+      h.assign(elems_, T(0));
+      RestartMeta meta;
+      bool ghosts = false;
+      if (!readVti<T>(path, layout(), h.data(), &ghosts, &msg)) throw std::runtime_error(msg);
+      if (!readRestartMeta(path, &meta)) throw std::runtime_error("restart: no readable '" + path + ".meta' (time step / total time)");
+      startStep = meta.nStep;
+      startTime = meta.totalTime;
+      lastDt_ = meta.dt;
+    } else if (!initProblem<T>(cfg_, rp_, kp_, problem, h, &msg)) {
       std::fprintf(stderr, "ramsesgpu_b200: %s\n", msg.c_str());
       lastWarning_ = msg;
     }
@@ -187,9 +201,9 @@ class RunImpl final : public Run {
     RG_CUDA(cudaStreamSynchronize(stream_));
     invalidate(0);
     invalidate(1);
-    totalTime = 0.0;
-    stepCount = 0;
-    return 0;
+    totalTime = startTime;
+    stepCount = startStep;
+    return startStep;
   }
 
   // reference HydroRunBase::make_all_boundaries (HydroRunBase.cpp:2322-2342): X, Y, then Z
@@ -263,6 +277,9 @@ class RunImpl final : public Run {
     nStep++;
     // the reference accumulates time in real_t
     t = static_cast<double>(static_cast<T>(t) + static_cast<T>(dt));
+    totalTime = t;
+    stepCount = nStep;
+    lastDt_ = dt;
   }
 
   // reference MHDRunGodunov::start (MHDRunGodunov.cpp:3801-4070), outputs every nOutput steps
@@ -272,14 +289,15 @@ class RunImpl final : public Run {
     RG_CUDA(cudaMemcpyAsync(dU_[1], dU_[0], elems_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
     ghostsValid_[1] = true;
     dtCached_[1] = false;
-    double t = 0.0, dt = compute_dt(0);
+    double t = totalTime, dt = compute_dt(nStep % 2);  // t > 0, nStep > 0 only when restarting from a dump
     if (rank_ == 0) std::printf("Initial dt : %.12g\n", dt);
+    const int firstStep = nStep;
     const auto t0 = std::chrono::steady_clock::now();
     double ioSeconds = 0.0;
     while (t < rp_.tEnd && nStep < rp_.nStepmax) {
-      if (rp_.nOutput > 0 && (nStep % rp_.nOutput) == 0) {
+      if (rp_.nOutput > 0 && (nStep % rp_.nOutput) == 0 && !(rp_.restart && nStep == firstStep)) {
         const auto a = std::chrono::steady_clock::now();
-        stepCount = nStep; totalTime = t;
+        stepCount = nStep; totalTime = t; lastDt_ = dt;
         output(nStep);
         ioSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
         if (rank_ == 0) std::printf("step=%9d t=%.10g dt=%.12g\n", nStep, t, dt);
@@ -306,6 +324,8 @@ class RunImpl final : public Run {
     std::vector<T> h(elems_);
     copyToHost(nStep % 2, h.data(), elems_ * sizeof(T));
     writeOutputs<T>(rp_, layout(), h.data(), nStep);
+    if (rp_.outputVtk && !rp_.outputVtkAscii)  // what a restart needs besides the fields (see output.h)
+      writeRestartMeta(vtiPath(rp_, layout(), nStep), RestartMeta{nStep, totalTime, lastDt_});
   }
 
   void copyToHost(int which, void* dst, size_t bytes) override {
@@ -605,6 +625,26 @@ class RunImpl final : public Run {
     haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
   }
 
+  // B of the ghost planes next to INTERIOR slab interfaces only (no periodic wrap): used between the
+  // resistive CT update and the resistive energy flux, where the mono-domain run sees updated inner
+  // cells across an interface but stale ghosts across the global z boundary (a property of the
+  // reference's sequence, mhd_godunov_unsplit_cpu_v3.cpp:666-680; tests/test_slab_protocol_gloo.py)
+  void exchangeZInteriorB(T* U, cudaStream_t st) {
+    const bool hasLo = rank_ > 0, hasHi = rank_ < nranks_ - 1;
+    const int gw = kp_.gw, lo = rank_ - 1, hi = rank_ + 1;
+    const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
+    const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
+    ncclCheck(nccl_->GroupStart(), "group start");
+    for (int v = IA; v <= IC; ++v) {
+      T* base = U + (size_t)v * comp;
+      if (hasHi) ncclCheck(nccl_->Send(base + (size_t)(kp_.ksize - 2 * gw) * plane, n, dtype, hi, comm_, st), "send up");
+      if (hasLo) ncclCheck(nccl_->Send(base + (size_t)gw * plane, n, dtype, lo, comm_, st), "send down");
+      if (hasLo) ncclCheck(nccl_->Recv(base, n, dtype, lo, comm_, st), "recv from below");
+      if (hasHi) ncclCheck(nccl_->Recv(base + (size_t)(kp_.ksize - gw) * plane, n, dtype, hi, comm_, st), "recv from above");
+    }
+    ncclCheck(nccl_->GroupEnd(), "group end");
+  }
+
   // ---- scratch / chunking ------------------------------------------------------------------------
   void freeScratch() {
     if (sc_.W) {  // cudaFree(nullptr) is a no-op for the arrays the hydro path does not use
@@ -707,12 +747,15 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMalloc(&dDiss_, bytes));
       deviceBytes_ += bytes;
     }
-    phase(PH_DISS, [&] {
-      if (kp_.eta > T(0)) {
+    const bool resistiveEnergy = kp_.eta > T(0) && !(kp_.cIso > T(0));
+    if (kp_.eta > T(0))
+      phase(PH_DISS, [&] {
         DissKernels<T>::resistEmf(kp_, U, dDiss_, stream_);
         DissKernels<T>::ctUpdate(kp_, U, dDiss_, dt, stream_);
-        if (!(kp_.cIso > T(0))) DissKernels<T>::resistEnergy(kp_, U, dt, stream_);
-      }
+      });
+    if (resistiveEnergy && nranks_ > 1) phase(PH_HALO, [&] { exchangeZInteriorB(U, stream_); });
+    phase(PH_DISS, [&] {
+      if (resistiveEnergy) DissKernels<T>::resistEnergy(kp_, U, dt, stream_);
       if (kp_.nu > T(0)) {
         DissKernels<T>::viscFlux(kp_, U, dDiss_, dt, stream_);
         DissKernels<T>::viscUpdate(kp_, U, dDiss_, stream_);
@@ -896,6 +939,7 @@ class RunImpl final : public Run {
   cudaStream_t h2dStream_ = nullptr, d2hStream_ = nullptr;
   cudaEvent_t evH2D_[2] = {nullptr, nullptr}, evD2H_[2] = {nullptr, nullptr}, evStepDone_[2] = {nullptr, nullptr};
   MhdScratch<T> sc_;
+  double lastDt_ = 0.0;  // dt of the last step (restart sidecar, history)
   T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;

@@ -26,14 +26,18 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+DISS = {"hydro": {"nu": 0.004}, "MHD": {"eta": 0.003}}
+
+
+def _worker(rank, world, port, out_dir, diss=False, refresh=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.oracle import Oracle
     from ramsesgpu_b200 import slab_extent
     o = Oracle("f64")
-    ini = ot3d_ini(N, OrszagTang={"kt": 1.0})
+    ini = ot3d_ini(N, OrszagTang={"kt": 1.0}, **(DISS if diss else {}))
+    o.set_skip_dissipative(diss)                 # the dissipative block is driven by the slab protocol below
     pg = o.params(ini)
     Ug = o.init_problem(pg)                      # every rank builds the GLOBAL initial state ...
     gw = pg.ghostWidth
@@ -58,6 +62,26 @@ def _worker(rank, world, port, out_dir):
         A[:, :gw] = from_below.numpy()
         A[:, nzl + gw:] = from_above.numpy()
 
+    def refresh_interior_B(A):
+        """B of the ghost planes next to INTERIOR slab interfaces, after the resistive CT update: in the
+        mono-domain run those planes are inner cells and carry the updated field, while the ghosts of
+        the global (here periodic) boundary keep their pre-CT values (run.cu::exchangeZInterior)."""
+        reqs, bufs = [], {}
+        if rank < world - 1:
+            top = torch.from_numpy(np.ascontiguousarray(A[5:8, nzl:nzl + gw]))
+            bufs["above"] = torch.empty_like(top)
+            reqs += [dist.isend(top, rank + 1, tag=3), dist.irecv(bufs["above"], rank + 1, tag=4)]
+        if rank > 0:
+            bot = torch.from_numpy(np.ascontiguousarray(A[5:8, gw:2 * gw]))
+            bufs["below"] = torch.empty_like(bot)
+            reqs += [dist.isend(bot, rank - 1, tag=4), dist.irecv(bufs["below"], rank - 1, tag=3)]
+        for r in reqs:
+            r.wait()
+        if "above" in bufs:
+            A[5:8, nzl + gw:] = bufs["above"].numpy()
+        if "below" in bufs:
+            A[5:8, :gw] = bufs["below"].numpy()
+
     fill_ghosts(U)
     U2 = U.copy()
     a, b = U, U2
@@ -67,18 +91,42 @@ def _worker(rank, world, port, out_dir):
         dt = float(mn.item())
         fill_ghosts(a)
         o.step_no_boundaries(pl, a, b, dt)
+        if diss:                                   # run.cu::stepMhd3d: ghost refresh, then the dissipative terms
+            fill_ghosts(b)
+            o.dissipative_stage(pl, b, dt, 0)
+            if refresh:
+                refresh_interior_B(b)
+            o.dissipative_stage(pl, b, dt, 1)
         a, b = b, a
     np.save(os.path.join(out_dir, "slab%d.npy" % rank), a[:, gw:gw + nzl])
     dist.destroy_process_group()
 
 
-def test_two_slabs_equal_mono_domain(tmp_path, oracle64):
+def _run(tmp_path, oracle64, diss, refresh=True):
     world = 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    ini = ot3d_ini(N, OrszagTang={"kt": 1.0})
+    mp.spawn(_worker, args=(world, port, str(tmp_path), diss, refresh), nprocs=world, join=True)
+    ini = ot3d_ini(N, OrszagTang={"kt": 1.0}, **(DISS if diss else {}))
     p = oracle64.params(ini)
     Uf, _, _ = oracle64.run_steps(p, oracle64.init_problem(p), NSTEPS)
     gw = p.ghostWidth
     got = np.concatenate([np.load(tmp_path / ("slab%d.npy" % r)) for r in range(world)], axis=1)
-    assert np.array_equal(got[:, :, gw:-gw, gw:-gw], Uf[:, gw:-gw, gw:-gw, gw:-gw])
+    return got[:, :, gw:-gw, gw:-gw], Uf[:, gw:-gw, gw:-gw, gw:-gw]
+
+
+def test_two_slabs_equal_mono_domain(tmp_path, oracle64):
+    got, want = _run(tmp_path, oracle64, diss=False)
+    assert np.array_equal(got, want)
+
+
+def test_two_slabs_with_dissipative_terms_equal_mono_domain(tmp_path, oracle64):
+    """resistivity + viscosity: a second ghost refresh inside the step, and the field of the interior
+    interfaces refreshed once more between the resistive CT update and the resistive energy flux"""
+    got, want = _run(tmp_path, oracle64, diss=True)
+    assert np.array_equal(got, want)
+
+
+def test_interior_field_refresh_is_needed(tmp_path, oracle64):
+    """without that refresh the energy next to the slab interface differs from the mono-domain run"""
+    got, want = _run(tmp_path, oracle64, diss=True, refresh=False)
+    assert not np.array_equal(got[1], want[1])
