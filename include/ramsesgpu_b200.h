@@ -93,6 +93,11 @@ int rg_run(rg_handle h);
 /* output(U, nStep) (HydroRunBase.cpp:4348): raw .vti and/or .xsm as the [output] section asks */
 int rg_output(rg_handle h, int nStep);
 
+/* history(nStep, dt) diagnostics (MHDRunBase.cpp:3311 history_default, :3476 history_mri), reduced on the device and
+ * summed over all slabs; 3D MHD only.  out[8] = mass, maxwell, reynolds, magp, mean_Bx, mean_By, mean_Bz, divB.
+ * rg_run writes the reference's history file when [history] enabled=yes. */
+int rg_history(rg_handle h, int nStep, double* out8);
+
 /* getData(nStep) / copyGpuToCpu(nStep) / getDataHost (HydroRunBase.h:437,456,512) */
 int rg_get_data_device(rg_handle h, int which, void** device_ptr);
 int rg_copy_to_host(rg_handle h, int which, void* dst, size_t bytes);

@@ -86,6 +86,8 @@ int  orc_init_problem(const orc_params *p, real_t *U);
 /* ghost fill, HydroRunBase.cpp:2322 + make_boundary_base.h:1040 */
 void orc_make_all_boundaries(const orc_params *p, real_t *U);
 void orc_make_boundaries(const orc_params *p, real_t *U, int idim /*1,2,3*/);
+/* shearing-box variant at time totalTime + dt, MHDRunGodunov.cpp:3763-3793 */
+void orc_make_all_boundaries_shear(const orc_params *p, real_t *U, real_t dt, real_t totalTime);
 /* CFL time step, MHDRunBase.cpp:141-250 (MHD), HydroRunBase.cpp:314-426 (hydro) */
 real_t orc_compute_dt(const orc_params *p, const real_t *U);
 /* one godunov_unsplit call (boundaries of Uold, copy, prim, step):

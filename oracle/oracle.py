@@ -73,6 +73,7 @@ class Oracle:
         L.orc_trace_mhd_3d.argtypes = [P, RP, RP, RP, RP, RP, R, R, R, R, RP, RP, RP]
         L.orc_trace_mhd_3d.restype = None
         L.orc_riemann_hydro.argtypes = [P, RP, RP, RP]; L.orc_riemann_hydro.restype = None
+        L.orc_make_all_boundaries_shear.argtypes = [P, RP, R, R]; L.orc_make_all_boundaries_shear.restype = None
         L.orc_set_skip_dissipative.argtypes = [C.c_int]; L.orc_set_skip_dissipative.restype = None
         L.orc_dissipative_stage.argtypes = [P, RP, R, C.c_int]; L.orc_dissipative_stage.restype = None
         L.orc_history_mhd3d.argtypes = [P, RP, C.POINTER(C.c_double)]; L.orc_history_mhd3d.restype = None
@@ -102,6 +103,10 @@ class Oracle:
 
     def make_all_boundaries(self, p, U):
         self.lib.orc_make_all_boundaries(C.byref(p), self._p(U))
+
+    def make_all_boundaries_shear(self, p, U, dt=0.0, t=0.0):
+        """shearing-box ghost fill at time t + dt (MHDRunGodunov.cpp:3763-3793)"""
+        self.lib.orc_make_all_boundaries_shear(C.byref(p), self._p(U), dt, t)
 
     def make_boundaries(self, p, U, idim):
         """idim = 1, 2, 3 (XDIR, YDIR, ZDIR)"""

@@ -204,6 +204,10 @@ int rg_set_tuning(const char* key, int value) {
 }
 
 int rg_profile_begin(rg_handle h) { RG_TRY(h, h->run->profileBegin()) }
+int rg_history(rg_handle h, int nStep, double* out8) {
+  RG_TRY(h, h->run->history(nStep, out8))
+}
+
 int rg_profile_end(rg_handle h, double* total, double* phase, unsigned long long* launches) {
   RG_TRY(h, h->run->profileEnd(total, phase, launches))
 }

@@ -106,6 +106,14 @@ struct DissKernels {
   static void viscUpdate(const KParams<T>& P, T* U, const T* D, cudaStream_t s);
 };
 
+// history diagnostics of a 3D MHD state (kernels_history.cu): two reduction passes with a fixed order
+template <typename T>
+struct HistoryKernels {
+  static void columnSums(const KParams<T>& P, const T* U, double* partial /*[nBlocks][3][isize]*/, int nBlocks, cudaStream_t s);
+  static void sums(const KParams<T>& P, const T* U, const double* meanUV /*[2][isize]*/, double* partial /*[nBlocks][8]*/,
+                   int nBlocks, cudaStream_t s);
+};
+
 // number of slots of the inverse-dt max reduction (power of two); every slot holds the bit pattern
 // of a non-negative double, so "max" works on the integer or on the floating view alike
 constexpr int MAX_SLOTS = 1024;

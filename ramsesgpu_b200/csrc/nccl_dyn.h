@@ -10,7 +10,7 @@ namespace rg {
 struct NcclApi {
   typedef struct ncclComm* comm_t;
   struct UniqueId { char internal[128]; };
-  enum { kFloat32 = 7, kFloat64 = 8, kMax = 2 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+  enum { kFloat32 = 7, kFloat64 = 8, kSum = 0, kMax = 2 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
   int (*GetUniqueId)(UniqueId*) = nullptr;
   int (*CommInitRank)(comm_t*, int, UniqueId, int) = nullptr;

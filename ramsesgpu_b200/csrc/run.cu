@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <fstream>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -110,6 +111,7 @@ class RunImpl final : public Run {
     freeScratch();
     for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
     cudaFree(dDiss_);
+    cudaFree(dHist_);
     for (int b = 0; b < 2; ++b) {
       if (batchBuf_[b]) cudaFree(batchBuf_[b]);
       if (evH2D_[b]) cudaEventDestroy(evH2D_[b]);
@@ -292,6 +294,9 @@ class RunImpl final : public Run {
     double t = totalTime, dt = compute_dt(nStep % 2);  // t > 0, nStep > 0 only when restarting from a dump
     if (rank_ == 0) std::printf("Initial dt : %.12g\n", dt);
     const int firstStep = nStep;
+    // history cadence of the reference, MHDRunGodunov.cpp:3915-3916 / :3975-3983 (arithmetic in real_t)
+    const T dtHist = cfg_.getFloat("history", "dtHist", static_cast<float>(10 * dt));
+    T tHist = static_cast<T>(t);
     const auto t0 = std::chrono::steady_clock::now();
     double ioSeconds = 0.0;
     while (t < rp_.tEnd && nStep < rp_.nStepmax) {
@@ -301,6 +306,13 @@ class RunImpl final : public Run {
         output(nStep);
         ioSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
         if (rank_ == 0) std::printf("step=%9d t=%.10g dt=%.12g\n", nStep, t, dt);
+      }
+      if (rp_.historyEnabled) {
+        const T tt = static_cast<T>(t), dd = static_cast<T>(dt);
+        if (tHist == T(0) || ((tt - dd <= tHist + dtHist) && (tt > tHist + dtHist))) {
+          writeHistoryLine(nStep, t, dt);
+          tHist += dtHist;
+        }
       }
       oneStepIntegration(nStep, t, dt);
     }
@@ -326,6 +338,75 @@ class RunImpl final : public Run {
     writeOutputs<T>(rp_, layout(), h.data(), nStep);
     if (rp_.outputVtk && !rp_.outputVtkAscii)  // what a restart needs besides the fields (see output.h)
       writeRestartMeta(vtiPath(rp_, layout(), nStep), RestartMeta{nStep, totalTime, lastDt_});
+  }
+
+  // reference MHDRunBase::history_default / history_mri (MHDRunBase.cpp:3311-3410, :3476-3620), reduced on the
+  // device (kernels_history.cu); sums over slabs with ncclAllReduce
+  void history(int nStep, double* out) override {
+    if (!(rp_.mhdEnabled && rp_.dim == 3)) throw std::runtime_error("history diagnostics are available for 3D MHD only");
+    const T* U = dU_[nStep % 2];
+    const int nB = 296, is = kp_.isize;
+    const size_t n1 = (size_t)nB * 3 * is, nMean = (size_t)3 * is, n2 = (size_t)nB * 8;
+    if (!dHist_) {
+      RG_CUDA(cudaMalloc(&dHist_, (n1 + nMean + n2 + 8) * sizeof(double)));
+      deviceBytes_ += (n1 + nMean + n2 + 8) * sizeof(double);
+      hHist_.resize(n1 + nMean + n2 + 8);
+    }
+    double *dPart1 = dHist_, *dMean = dHist_ + n1, *dPart2 = dMean + nMean, *dTot = dPart2 + n2;
+    auto allSum = [&](double* dBuf, double* hBuf, size_t n) {  // sum over ranks of a small host array
+      if (nranks_ == 1) return;
+      RG_CUDA(cudaMemcpyAsync(dBuf, hBuf, n * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      if (haloDone_[0] || haloDone_[1]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
+      ncclCheck(nccl_->AllReduce(dBuf, dBuf, n, NcclApi::kFloat64, NcclApi::kSum, comm_, stream_), "allreduce(history)");
+      RG_CUDA(cudaMemcpyAsync(hBuf, dBuf, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      RG_CUDA(cudaStreamSynchronize(stream_));
+    };
+    HistoryKernels<T>::columnSums(kp_, U, dPart1, nB, stream_);
+    RG_CUDA(cudaMemcpyAsync(hHist_.data(), dPart1, n1 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<double> col(nMean, 0.0);
+    for (int b = 0; b < nB; ++b)
+      for (size_t q = 0; q < nMean; ++q) col[q] += hHist_[(size_t)b * nMean + q];
+    allSum(dMean, col.data(), nMean);
+    const double cells = (double)rp_.ny * (double)rp_.nz;  // GLOBAL y-z plane
+    for (int i = 0; i < is; ++i) { col[i] = col[is + i] / cells; col[is + i] = col[2 * is + i] / cells; }  // mean u, mean v
+    RG_CUDA(cudaMemcpyAsync(dMean, col.data(), 2 * is * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    HistoryKernels<T>::sums(kp_, U, dMean, dPart2, nB, stream_);
+    RG_CUDA(cudaMemcpyAsync(hHist_.data(), dPart2, n2 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < nB; ++b)
+      for (int q = 0; q < 8; ++q) s[q] += hHist_[(size_t)b * 8 + q];
+    allSum(dTot, s, 8);
+    const double dTau = (double)kp_.dx * (double)kp_.dy * (double)kp_.dz / (double)(kp_.xMax - kp_.xMin) /
+                        (double)(kp_.yMax - kp_.yMin) / (double)(kp_.zMax - kp_.zMin);
+    out[0] = s[0] * dTau; out[1] = s[1] * dTau; out[2] = s[2] * dTau; out[3] = s[3] * dTau / 2.;
+    out[4] = s[4] * dTau; out[5] = s[5] * dTau; out[6] = s[6] * dTau; out[7] = s[7];
+  }
+
+  // one line of the reference's history file (<outputDir>/<outputPrefix>_<[history] filename>), rank 0 only
+  void writeHistoryLine(int nStep, double t, double dt) {
+    const bool mri = rp_.problem == "MRI" || rp_.problem == "Mri" || rp_.problem == "mri";
+    const bool ot = rp_.problem == "Orszag-Tang" || rp_.problem == "OrszagTang";
+    if (!(mri || ot) || !(rp_.mhdEnabled && rp_.dim == 3)) return;  // the reference's history_empty
+    double h[8];
+    history(nStep, h);
+    if (rank_ != 0) return;
+    std::string path = rp_.outputDir;
+    if (!path.empty() && path.back() != '/') path += "/";
+    path += rp_.outputPrefix + "_" + rp_.historyFilename;
+    std::ofstream histo(path.c_str(), std::ios::out | std::ios::app | std::ios::ate);
+    if (t <= 0) {
+      histo << "# history\n";
+      if (rp_.restart) histo << "# history : this is a restart run\n";
+      histo << (mri ? "# totalTime dt mass maxwell reynolds maxwell+reynolds magp mean_Bx mean_By mean_Bz divB\n"
+                    : "# totalTime dt mass divB\n");
+    }
+    histo << t << "\t" << dt << "\t" << h[0] << "\t";
+    if (mri)
+      histo << h[1] << "\t" << h[2] << "\t" << h[1] + h[2] << "\t" << h[3] << "\t" << h[4] << "\t" << h[5] << "\t"
+            << h[6] << "\t";
+    histo << h[7] << "\n";
   }
 
   void copyToHost(int which, void* dst, size_t bytes) override {
@@ -940,6 +1021,8 @@ class RunImpl final : public Run {
   cudaEvent_t evH2D_[2] = {nullptr, nullptr}, evD2H_[2] = {nullptr, nullptr}, evStepDone_[2] = {nullptr, nullptr};
   MhdScratch<T> sc_;
   double lastDt_ = 0.0;  // dt of the last step (restart sidecar, history)
+  double* dHist_ = nullptr;  // partial sums of the history kernels
+  std::vector<double> hHist_;
   T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;

@@ -56,6 +56,9 @@ class Run {
   virtual void oneStepIntegration(int& nStep, double& t, double& dt) = 0;
   virtual void start() = 0;                                                // full run loop
   virtual void output(int nStep) = 0;
+  // history diagnostics of buffer nStep % 2 (reference MHDRunBase::history_default / history_mri), global over all
+  // slabs: out[8] = mass, maxwell, reynolds, magp, mean_Bx, mean_By, mean_Bz, divB
+  virtual void history(int nStep, double* out) = 0;
 
   // data access; host arrays are [var][k][j][i] of the LOCAL slab, ghosts included
   virtual void copyToHost(int which, void* dst, size_t bytes) = 0;

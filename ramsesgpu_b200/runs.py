@@ -77,6 +77,15 @@ class HydroRunBase:
     def output(self, nStep):
         check(self._L.rg_output(self._h, nStep))
 
+    HISTORY_NAMES = ("mass", "maxwell", "reynolds", "magp", "mean_Bx", "mean_By", "mean_Bz", "divB")
+
+    def history(self, nStep):
+        """History diagnostics of the state of step nStep (reference MHDRunBase::history_default / history_mri),
+        reduced on the device, global over all slabs."""
+        out = (C.c_double * 8)()
+        check(self._L.rg_history(self._h, nStep, out))
+        return dict(zip(self.HISTORY_NAMES, [float(v) for v in out]))
+
     # -- data ------------------------------------------------------------------------------------
     def getData(self, nStep=0):
         """Device pointer (int) of the buffer holding step nStep."""
