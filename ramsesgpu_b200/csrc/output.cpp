@@ -101,8 +101,8 @@ void writeRestartMeta(const std::string& vti, const RestartMeta& m) {
   std::FILE* f = std::fopen((vti + ".meta").c_str(), "w");
   if (!f) return;
   // %a: exact hexadecimal floats, the decimal values are for the reader's eyes only
-  std::fprintf(f, "nStep %d\ntotalTime %a\ndt %a\n# totalTime = %.17g, dt = %.17g\n", m.nStep, m.totalTime, m.dt,
-               m.totalTime, m.dt);
+  std::fprintf(f, "nStep %d\ntotalTime %a\ndt %a\ndtNext %a\n# totalTime = %.17g, dt = %.17g, dtNext = %.17g\n", m.nStep,
+               m.totalTime, m.dt, m.dtNext, m.totalTime, m.dt, m.dtNext);
   std::fclose(f);
 }
 
@@ -115,6 +115,7 @@ bool readRestartMeta(const std::string& vti, RestartMeta* m) {
     if (!std::strcmp(key, "nStep")) { m->nStep = std::atoi(val); ++got; }
     else if (!std::strcmp(key, "totalTime")) { m->totalTime = std::strtod(val, nullptr); ++got; }
     else if (!std::strcmp(key, "dt")) { m->dt = std::strtod(val, nullptr); ++got; }
+    else if (!std::strcmp(key, "dtNext")) { m->dtNext = std::strtod(val, nullptr); }
   }
   std::fclose(f);
   return got == 3;

@@ -21,10 +21,12 @@ void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep);
 // Checkpoint / resume.  The reference restarts from its HDF5 output ("total time" and
 // "time step" attributes, HydroRunBase.cpp:5100-5110, MHDRunBase.cpp:1234-1282); HDF5 is not available
 // here, so the restart input is the raw-appended .vti written by writeOutputs plus a small text sidecar
-// `<same name>.meta` holding what the .vti cannot: time step, total time and dt as exact hex floats.
+// `<same name>.meta` holding what the .vti cannot: time step, total time, dt and the next dt as exact hex floats (the next dt
+// so that a resumed run repeats the uninterrupted one bit for bit whichever kernel reduced it).
 struct RestartMeta {
   int nStep = 0;
   double totalTime = 0.0, dt = 0.0;
+  double dtNext = 0.0;  // CFL step of the dumped state as the uninterrupted run will use it (0 = recompute)
 };
 void writeRestartMeta(const std::string& vtiPath, const RestartMeta& m);
 bool readRestartMeta(const std::string& vtiPath, RestartMeta* m);

@@ -194,6 +194,7 @@ class RunImpl final : public Run {
       startStep = meta.nStep;
       startTime = meta.totalTime;
       lastDt_ = meta.dt;
+      resumeDt_ = meta.dtNext;  // used for the first step after the restart (cleared by godunov_unsplit)
     } else if (!initProblem<T>(cfg_, rp_, kp_, problem, h, &msg)) {
       std::fprintf(stderr, "ramsesgpu_b200: %s\n", msg.c_str());
       lastWarning_ = msg;
@@ -218,6 +219,7 @@ class RunImpl final : public Run {
 
   // reference MHDRunBase::compute_dt_mhd / HydroRunBase::compute_dt: cfl / max inverse dt
   double compute_dt(int useU) override {
+    if (resumeDt_ > 0.0) return resumeDt_;
     const int b = useU ? 1 : 0;
     unsigned long long* slots = dMax_ + (size_t)b * MAX_SLOTS;
     if (!dtCached_[b]) {
@@ -248,6 +250,7 @@ class RunImpl final : public Run {
   // reference MHDRunGodunov::godunov_unsplit (MHDRunGodunov.cpp:572-594): even step U -> U2
   void godunov_unsplit(int nStep, double dt) override {
     const int src = (nStep % 2 == 0) ? 0 : 1, dst = 1 - src;
+    resumeDt_ = 0.0;
     RG_CUDA(cudaEventRecord(ev0_, stream_));
     const bool rotating = rp_.mhdEnabled && kp_.Omega0 > T(0);
     // the rotating-frame step fills the ghosts of UNew at its END (reference MHDRunGodunov.cpp:3429-3437)
@@ -337,7 +340,7 @@ class RunImpl final : public Run {
     copyToHost(nStep % 2, h.data(), elems_ * sizeof(T));
     writeOutputs<T>(rp_, layout(), h.data(), nStep);
     if (rp_.outputVtk && !rp_.outputVtkAscii)  // what a restart needs besides the fields (see output.h)
-      writeRestartMeta(vtiPath(rp_, layout(), nStep), RestartMeta{nStep, totalTime, lastDt_});
+      writeRestartMeta(vtiPath(rp_, layout(), nStep), RestartMeta{nStep, totalTime, lastDt_, compute_dt(nStep % 2)});
   }
 
   // reference MHDRunBase::history_default / history_mri (MHDRunBase.cpp:3311-3410, :3476-3620), reduced on the
@@ -1021,6 +1024,7 @@ class RunImpl final : public Run {
   cudaEvent_t evH2D_[2] = {nullptr, nullptr}, evD2H_[2] = {nullptr, nullptr}, evStepDone_[2] = {nullptr, nullptr};
   MhdScratch<T> sc_;
   double lastDt_ = 0.0;  // dt of the last step (restart sidecar, history)
+  double resumeDt_ = 0.0;  // next dt read from a restart sidecar
   double* dHist_ = nullptr;  // partial sums of the history kernels
   std::vector<double> hHist_;
   T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
