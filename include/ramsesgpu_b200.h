@@ -80,6 +80,11 @@ int rg_get_param(rg_handle h, const char* name, double* value);
 
 /* init_simulation(problem) (MHDRunBase.cpp:1231, HydroRunBase.cpp:7023); problem NULL/"" = [hydro] problem */
 int rg_init_simulation(rg_handle h, const char* problem, int* nStep);
+/* The host half of init_simulation alone: initial condition of z-slab `rank` of `nranks` written into a caller
+ * buffer ([var][k][j][i] of the local slab, ghosts included), no device involved (a coupler that builds its own
+ * state, or a check of the problem setup on a machine without a GPU).  dst == NULL only fills *layout_out. */
+int rg_initial_condition_host(const char* ini_text, int flags, int rank, int nranks, void* dst, size_t bytes,
+                              rg_layout* layout_out);
 /* make_all_boundaries(U) (HydroRunBase.h:422): which = 0 -> U, 1 -> U2 */
 int rg_make_all_boundaries(rg_handle h, int which);
 /* compute_dt(int useU) / compute_dt_mhd(int useU) (HydroRunBase.h:80, MHDRunBase.h:49); global over all slabs */

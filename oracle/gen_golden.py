@@ -109,6 +109,17 @@ if __name__ == "__main__":
             "mesh": {"nx": 8, "ny": 10, "nz": 16}, "hydro": {"nu": 0.001}, "MHD": {"eta": 0.002},
             "gravity": {"static_field_x": 0.05, "static_field_z": -0.3},
             "rayleigh-taylor": {"randomEnabled": "yes", "random_seed": 7, "bx": 0.05, "bz": 0.02}}, 5, "f64"),
+        # SURVEY 8(f).4 -- further MHD test problems of the reference on the same step kernels
+        "briowu2d_32x24_s8": ("mhd_BrioWu.ini", {"mesh": {"nx": 32, "ny": 24}}, 8, "f64"),
+        "briowu2d_diag_24_s6": ("mhd_BrioWu.ini", {"mesh": {"nx": 24, "ny": 24}, "BrioWu": {"direction": 3}}, 6, "f64"),
+        "briowu3d_z_10x8x16_s5": ("mhd_BrioWu.ini", {"mesh": {"nx": 10, "ny": 8, "nz": 16}, "BrioWu": {"direction": 2}}, 5, "f64"),
+        "briowu3d_xyz_12_s5": ("mhd_BrioWu.ini", {"mesh": {"nx": 12, "ny": 12, "nz": 12}, "BrioWu": {"direction": 3}}, 5, "f64"),
+        # (the reference run of this problem blows up after ~5 steps at any resolution, incl. the shipped 128^2: 3 steps)
+        "rotor2d_48_s1": ("mhd_rotor.ini", {"mesh": {"nx": 48, "ny": 48}, "MHD": {"implementationVersion": 1}}, 1, "f64"),
+        "fieldloop2d_32x20_s8": ("mhd_fieldloop2d.ini", {"mesh": {"nx": 32, "ny": 20}}, 8, "f64"),
+        "fieldloop3d_16x12x10_s6": ("mhd_fieldloop3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 10}}, 6, "f64"),
+        "currentsheet2d_24_s8": ("mhd_currentSheet_2d.ini", {"mesh": {"nx": 24, "ny": 24}}, 8, "f64"),
+        "currentsheet3d_16x16x8_s5": ("mhd_currentSheet_3d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 8}}, 5, "f64"),
     }
     for name, (ini, ov, steps, prec) in cases.items():
         if only and name not in only:

@@ -5,7 +5,7 @@ from .io import ini_override, l2_relative, read_vti, read_xsm  # noqa: F401
 
 def __getattr__(name):
     # the compute API needs the native library; keep `import ramsesgpu_b200` itself light
-    if name in ("HydroRunBase", "MHDRunBase", "HydroRunGodunov", "MHDRunGodunov", "reset_launch_count", "slab_extent", "set_tuning", "PinnedArray"):
+    if name in ("HydroRunBase", "MHDRunBase", "HydroRunGodunov", "MHDRunGodunov", "reset_launch_count", "slab_extent", "set_tuning", "PinnedArray", "initial_condition_host"):
         from . import runs
         return getattr(runs, name)
     raise AttributeError(name)

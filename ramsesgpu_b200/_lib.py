@@ -56,6 +56,7 @@ SIGNATURES = {
     "rg_set_halo_overlap": (C.c_int, [H, C.c_int]),
     "rg_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "rg_history": (C.c_int, [H, C.c_int, C.POINTER(C.c_double)]),
+    "rg_initial_condition_host": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(RgLayout)]),
     "rg_profile_begin": (C.c_int, [H]),
     "rg_profile_end": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "rg_probe_riemann_mhd": (C.c_int, [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

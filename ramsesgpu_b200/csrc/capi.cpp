@@ -5,8 +5,10 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/ramsesgpu_b200.h"
+#include "init_conditions.h"
 #include "kernels.h"
 #include "nccl_dyn.h"
 #include "run.h"
@@ -40,6 +42,27 @@ int classify(const std::exception& e) {
   } catch (const std::exception& e) {                     \
     return fail(classify(e), e.what());                   \
   }
+
+// Host-only initial condition of z-slab `rank` of `nranks` (the host half of init_simulation: no device is touched).
+template <typename T>
+static int initialConditionHost(const rg::ConfigMap& cfg, int rank, int nranks, void* dst, size_t bytes, rg_layout* lay) {
+  const rg::RunParams rp = rg::parseRunParams(cfg);
+  int nzLocal = rp.nz, kOff = 0;
+  if (rp.dim == 3) rg::slabExtent(rp.nz, nranks, rank, &nzLocal, &kOff);
+  const rg::KParams<T> kp = rg::makeKParams<T>(cfg, rp, nzLocal, kOff);
+  const size_t n = (size_t)kp.isize * kp.jsize * kp.ksize * kp.nvar;
+  if (lay) {
+    *lay = rg_layout{rp.nx, rp.ny, rp.nz, kp.isize, kp.jsize, kp.ksize, kp.nvar, kp.gw, rp.dim, rp.mhdEnabled ? 1 : 0,
+                     (int)sizeof(T), nzLocal, kOff, rank, nranks};
+  }
+  if (!dst) return RG_OK;  // layout query
+  if (bytes != n * sizeof(T)) return fail(RG_ERR_INVALID, "buffer size does not match the local array");
+  std::vector<T> U;
+  std::string msg;
+  const bool ok = rg::initProblem<T>(cfg, rp, kp, rp.problem, U, &msg);
+  std::memcpy(dst, U.data(), n * sizeof(T));
+  return ok ? RG_OK : fail(RG_ERR_UNSUPPORTED, msg);
+}
 
 extern "C" {
 
@@ -219,6 +242,19 @@ int rg_probe_riemann_mhd(rg_handle h, int n, const void* ql, const void* qr, voi
 int rg_probe_compute_emf(rg_handle h, int n, int dir, const void* q, const void* x, void* emf) {
   if (!q || !emf || n <= 0 || dir < 0 || dir > 2) return fail(RG_ERR_INVALID, "bad probe arguments");
   RG_TRY(h, h->run->probeEmf(n, dir, q, x, emf))
+}
+
+int rg_initial_condition_host(const char* ini_text, int flags, int rank, int nranks, void* dst, size_t bytes,
+                              rg_layout* layout_out) {
+  if (!ini_text) return fail(RG_ERR_INVALID, "null ini text");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(RG_ERR_INVALID, "bad rank / nranks");
+  try {
+    const rg::ConfigMap cfg = rg::ConfigMap::fromText(ini_text);
+    return (flags & RG_FLAG_FP32) ? initialConditionHost<float>(cfg, rank, nranks, dst, bytes, layout_out)
+                                  : initialConditionHost<double>(cfg, rank, nranks, dst, bytes, layout_out);
+  } catch (const std::exception& e) {
+    return fail(classify(e), e.what());
+  }
 }
 
 int rg_slab_extent(int nzGlobal, int nranks, int rank, int* nzLocal, int* kOffset) {

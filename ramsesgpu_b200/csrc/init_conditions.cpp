@@ -335,6 +335,209 @@ bool initRayleighTaylor(const ConfigMap& cfg, const RunParams& rp, const KParams
   return true;
 }
 
+// Brio-Wu shock tube in 2D / 3D; reference MHDRunBase.cpp:1870-2100.  Inner cells only; the interface is
+// at half of the (ghosted, GLOBAL) index range, the ghosts come from the boundary conditions.
+template <typename T>
+bool initBrioWu(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "Brio-Wu needs MHD"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const T B0 = cfg.getFloat("BrioWu", "B0", 1.0f), B1 = cfg.getFloat("BrioWu", "B1", 0.75f);
+  const T d0 = cfg.getFloat("BrioWu", "d0", 1.0f), d1 = cfg.getFloat("BrioWu", "d1", 0.125f);
+  const T p0 = 1.0, p1 = 0.1;
+  int direction = (int)cfg.getInteger("BrioWu", "direction", 0);
+  if (direction < 0 || direction > 4) direction = 0;
+  const int isize = kp.isize, jsize = kp.jsize, ksizeG = kp.nzGlobal + 2 * gw;
+  const T gm1 = kp.gamma0 - 1.0f;
+  if (rp.dim == 2) {
+    for (int j = gw; j < jsize - gw; ++j)
+      for (int i = gw; i < isize - gw; ++i) {
+        bool left;
+        T a, b, e;
+        if (direction == 0 || direction == 2) {  // direction 2 does not exist in 2D: the reference leaves zeros
+          if (direction == 2) continue;
+          left = i < isize / 2;
+          a = B1; b = left ? B0 : -B0;
+          e = (left ? p0 : p1) / gm1 + 0.5 * (B0 * B0 + B1 * B1);
+        } else if (direction == 1) {
+          left = j < jsize / 2;
+          a = left ? B0 : -B0; b = B1;
+          e = (left ? p0 : p1) / gm1 + 0.5 * (B0 * B0 + B1 * B1);
+        } else if (direction == 3) {
+          left = 1.0 * i / isize + 1.0 * j / jsize < 1;
+          const T s2 = std::sqrt(T(2.));
+          a = left ? -B0 / s2 + B1 / s2 : B0 / s2 + B1 / s2;
+          b = left ? B0 / s2 + B1 / s2 : -B0 / s2 + B1 / s2;
+          e = (left ? p0 : p1) / gm1 + 0.5 * ((-B0 + B1) * (-B0 + B1) / 2 + (B0 + B1) * (B0 + B1) / 2);
+        } else {  // 4: quarter circle in the lower-left corner
+          const T phi = std::atan2(1.0 * j, 1.0 * i);
+          left = 1.0 * i * i / (isize * isize) + 1.0 * j * j / (jsize * jsize) < 1.0 / 4;
+          a = left ? T(-B0 * std::sin(phi) + B1 * std::cos(phi)) : T(B0 * std::sin(phi) + B1 * std::cos(phi));
+          b = left ? T(B0 * std::cos(phi) + B1 * std::sin(phi)) : T(-B0 * std::cos(phi) + B1 * std::sin(phi));
+          e = (left ? p0 : p1) / gm1 + 0.5 * (a * a + b * b);
+        }
+        g.at(ID, i, j, 0) = left ? d0 : d1;
+        g.at(IP, i, j, 0) = e;
+        g.at(IA, i, j, 0) = a;
+        g.at(IB, i, j, 0) = b;
+      }
+    return true;
+  }
+  for (int k = gw; k < kp.ksize - gw; ++k) {
+    const int kg = k + kp.kglob0;
+    for (int j = gw; j < jsize - gw; ++j)
+      for (int i = gw; i < isize - gw; ++i) {
+        bool left;
+        T a, b, c, e;
+        if (direction == 3) {
+          left = 1.0 * i / isize + 1.0 * j / jsize + 1.0 * kg / ksizeG < 1;
+          const T s3 = std::sqrt(T(3.));
+          a = B1 / s3;
+          b = left ? B1 / s3 + B0 * std::sqrt(T(2.0 / 3)) : B1 / s3 - B0 * std::sqrt(T(2.0 / 3));
+          c = left ? B1 / s3 - 2 * B0 / std::sqrt(T(6.0)) : B1 / s3 + 2 * B0 / std::sqrt(T(6.0));
+          e = (left ? p0 : p1) / gm1 + 0.5 * (a * a + b * b + c * c);
+        } else if (direction == 4) {
+          continue;  // not defined in 3D
+        } else {
+          left = direction == 0 ? i < isize / 2 : direction == 1 ? j < jsize / 2 : kg < ksizeG / 2;
+          const T s = left ? B0 : -B0;
+          a = direction == 0 ? B1 : s;
+          b = direction == 1 ? B1 : s;
+          c = direction == 2 ? B1 : s;
+          e = (left ? p0 : p1) / gm1 + 0.5 * (B0 * B0 + B0 * B0 + B1 * B1);
+        }
+        g.at(ID, i, j, k) = left ? d0 : d1;
+        g.at(IP, i, j, k) = e;
+        g.at(IA, i, j, k) = a;
+        g.at(IB, i, j, k) = b;
+        g.at(IC, i, j, k) = c;
+      }
+  }
+  return true;
+}
+
+// MHD rotor (Balsara & Spicer 1999, Toth 2000), 2D; reference MHDRunBase.cpp:2117-2190
+template <typename T>
+bool initRotor(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "rotor needs MHD"; return false; }
+  if (rp.dim != 2) return true;  // the reference's 3D branch is empty: zero state
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const T FourPi = (T)(8.0 * std::asin(1.0));
+  const T r0 = cfg.getFloat("rotor", "r0", 0.1f), r1 = cfg.getFloat("rotor", "r1", 0.115f);
+  const T u0 = cfg.getFloat("rotor", "u0", 2.0f), p0 = cfg.getFloat("rotor", "p0", 1.0f);
+  const T b0 = cfg.getFloat("rotor", "b0", (float)(5.0 / std::sqrt(FourPi)));
+  const T xMax = cfg.getFloat("mesh", "xmax", 1.0f), yMax = cfg.getFloat("mesh", "ymax", 1.0f);
+  const T xC = (xMax + kp.xMin) / 2, yC = (yMax + kp.yMin) / 2;
+  for (int j = gw; j < kp.jsize - gw; ++j) {
+    const T yPos = kp.yMin + kp.dx / 2 + (j - gw) * kp.dy;  // dx/2: as written in the reference
+    for (int i = gw; i < kp.isize - gw; ++i) {
+      const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+      const T r = std::sqrt((xPos - xC) * (xPos - xC) + (yPos - yC) * (yPos - yC));
+      const T f_r = (r1 - r) / (r1 - r0);
+      T d, mx, my;
+      if (r <= r0) { d = 10.0; mx = -u0 * (yPos - yC) / r0; my = u0 * (xPos - xC) / r0; }
+      else if (r <= r1) { d = 1 + 9 * f_r; mx = -f_r * u0 * (yPos - yC) / r; my = f_r * u0 * (xPos - xC) / r; }
+      else { d = 1.0; mx = 0.0; my = 0.0; }
+      g.at(ID, i, j, 0) = d; g.at(IU, i, j, 0) = mx; g.at(IV, i, j, 0) = my;
+      g.at(IA, i, j, 0) = b0;
+      const T mz = 0.0;
+      g.at(IP, i, j, 0) = p0 / (kp.gamma0 - 1.0) + (mx * mx + my * my + mz * mz) / 2 / d + (b0 * b0) / 2;
+    }
+  }
+  return true;
+}
+
+// field-loop advection (Gardiner & Stone 2005), 2D and 3D (loop in the x-y plane); reference
+// MHDRunBase.cpp:2214-2400.  B = curl A on the staggered grid; in 3D the reference adds drand48 noise to
+// A_z over the WHOLE (ghosted) array in (k,j,i) order: one global stream, jump-ahead per slab.
+template <typename T>
+bool initFieldLoop(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "field loop needs MHD"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw, isize = kp.isize, jsize = kp.jsize;
+  const T radius = cfg.getFloat("FieldLoop", "radius", 1.0f), density_in = cfg.getFloat("FieldLoop", "density_in", 1.0f);
+  const T amplitude = cfg.getFloat("FieldLoop", "amplitude", 1.0f), vflow = cfg.getFloat("FieldLoop", "vflow", 1.0f);
+  const T cos_theta = 2.0 / std::sqrt(5.0);
+  const T sin_theta = std::sqrt(1 - cos_theta * cos_theta);
+  const T dx = kp.dx, dy = kp.dy, dz = kp.dz;
+  auto xOf = [&](int i) { return kp.xMin + dx / 2 + (i - gw) * dx; };
+  auto yOf = [&](int j) { return kp.yMin + dy / 2 + (j - gw) * dy; };
+  if (rp.dim == 2) {
+    std::vector<T> Az((size_t)isize * jsize, T(0));
+    for (int j = gw; j < jsize - gw + 1; ++j)
+      for (int i = gw; i < isize - gw + 1; ++i) {
+        const T xPos = xOf(i), yPos = yOf(j), r = std::sqrt(xPos * xPos + yPos * yPos);
+        Az[(size_t)j * isize + i] = r < radius ? amplitude * (radius - r) : T(0);
+      }
+    for (int j = gw; j < jsize - gw; ++j)
+      for (int i = gw; i < isize - gw; ++i) {
+        const T xPos = xOf(i), yPos = yOf(j);
+        const T diag = std::sqrt(1.0 * (rp.nx * rp.nx + rp.ny * rp.ny + rp.nz * rp.nz));
+        const T r = std::sqrt(xPos * xPos + yPos * yPos);
+        const T d = r < radius ? density_in : T(1.0f);
+        const T mx = d * vflow * cos_theta, my = d * vflow * sin_theta, mz = d * vflow * rp.nz / diag;
+        const T a = (Az[(size_t)(j + 1) * isize + i] - Az[(size_t)j * isize + i]) / dy;
+        const T b = -(Az[(size_t)j * isize + i + 1] - Az[(size_t)j * isize + i]) / dx;
+        g.at(ID, i, j, 0) = d; g.at(IU, i, j, 0) = mx; g.at(IV, i, j, 0) = my; g.at(IW, i, j, 0) = mz;
+        g.at(IA, i, j, 0) = a; g.at(IB, i, j, 0) = b;
+        g.at(IP, i, j, 0) = 1.0f / (kp.gamma0 - 1.0f) + 0.5 * (a * a + b * b) + 0.5 * (mx * mx + my * my) / d;
+      }
+    return true;
+  }
+  // 3D: only A_z is non-zero
+  const double amp = cfg.getFloat("FieldLoop", "amp", 0.01f);
+  Rand48 rng(cfg.getInteger("FieldLoop", "seed", 0));
+  rng.skip((uint64_t)isize * jsize * (uint64_t)kp.kglob0);
+  const size_t plane = (size_t)isize * jsize;
+  std::vector<T> Az(plane * kp.ksize, T(0));
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < jsize; ++j)
+      for (int i = 0; i < isize; ++i) {
+        const T xPos = xOf(i), yPos = yOf(j);
+        T a = T(0) + amp * (rng.next() - 0.5);
+        const T r = std::sqrt(xPos * xPos + yPos * yPos);
+        if (r < radius) a = amplitude * (radius - r);
+        Az[(size_t)k * plane + (size_t)j * isize + i] = a;
+      }
+  for (int k = gw; k < kp.ksize - gw; ++k)
+    for (int j = gw; j < jsize - gw; ++j)
+      for (int i = gw; i < isize - gw; ++i) {
+        const T xPos = xOf(i), yPos = yOf(j), r = std::sqrt(xPos * xPos + yPos * yPos);
+        const T d = r < radius ? density_in : T(1.0f);
+        const T mx = d * vflow * cos_theta, my = d * vflow * sin_theta, mz = T(0);
+        const size_t c = (size_t)k * plane + (size_t)j * isize + i;
+        const T zero = T(0);
+        const T a = (Az[c + isize] - Az[c]) / dy - (zero - zero) / dz;
+        const T b = (zero - zero) / dz - (Az[c + 1] - Az[c]) / dx;
+        const T cz = (zero - zero) / dx - (zero - zero) / dy;
+        g.at(ID, i, j, k) = d; g.at(IU, i, j, k) = mx; g.at(IV, i, j, k) = my; g.at(IW, i, j, k) = mz;
+        g.at(IA, i, j, k) = a; g.at(IB, i, j, k) = b; g.at(IC, i, j, k) = cz;
+        if (kp.cIso > 0) g.at(IP, i, j, k) = T(0);
+        else g.at(IP, i, j, k) = 1.0f / (kp.gamma0 - 1.0f) + 0.5 * (a * a + b * b + cz * cz) + 0.5 * (mx * mx + my * my + mz * mz) / d;
+      }
+  return true;
+}
+
+// current sheet, 2D and 3D, every cell (ghosts included); reference MHDRunBase.cpp:2424-2490
+template <typename T>
+bool initCurrentSheet(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "current sheet needs MHD"; return false; }
+  Grid<T> g(kp, U);
+  const T A = cfg.getFloat("CurrentSheet", "A", 0.1f), B0 = cfg.getFloat("CurrentSheet", "B0", 1.0f);
+  const T beta = cfg.getFloat("CurrentSheet", "beta", 0.1f);
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < kp.jsize; ++j)
+      for (int i = 0; i < kp.isize; ++i) {
+        const T xPos = kp.xMin + kp.dx / 2 + (i - kp.gw) * kp.dx, yPos = kp.yMin + kp.dy / 2 + (j - kp.gw) * kp.dy;
+        g.at(ID, i, j, k) = T(1);
+        g.at(IP, i, j, k) = beta;
+        g.at(IU, i, j, k) = T(1) * A * std::sin(M_PI * yPos);
+        g.at(IB, i, j, k) = (xPos < 0.5 || xPos > 1.5) ? B0 : -B0;
+      }
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -345,6 +548,12 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Orszag-Tang" || problem == "OrszagTang") return initOrszagTang(cfg, rp, kp, U, message);
     if (problem == "MRI" || problem == "Mri" || problem == "mri") return initMri(cfg, rp, kp, U, message);
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
+    if (problem == "Brio-Wu" || problem == "BrioWu" || problem == "brio-wu" || problem == "briowu") return initBrioWu(cfg, rp, kp, U, message);
+    if (problem == "Rotor" || problem == "rotor") return initRotor(cfg, rp, kp, U, message);
+    if (problem == "FieldLoop" || problem == "fieldloop" || problem == "Fieldloop" || problem == "field-loop" || problem == "Field-Loop")
+      return initFieldLoop(cfg, rp, kp, U, message);
+    if (problem == "CurrentSheet" || problem == "currentsheet" || problem == "Current-Sheet" || problem == "current-sheet" || problem == "Currentsheet")
+      return initCurrentSheet(cfg, rp, kp, U, message);
   } else {  // reference HydroRunBase.cpp:7023-7100
     if (problem == "implode") return initImplode(cfg, rp, kp, U, message);
     if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtz(cfg, rp, kp, U, message);

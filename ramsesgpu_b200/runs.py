@@ -222,6 +222,19 @@ def reset_launch_count():
     _lib.load().rg_reset_launch_count()
 
 
+def initial_condition_host(ini_text, fp32=False, rank=0, nranks=1):
+    """Initial condition of a z-slab computed on the HOST only (rg_initial_condition_host): ndarray [var, k, j, i]
+    with ghosts, and the layout.  Works without a GPU."""
+    import numpy as np
+    L = _lib.load()
+    lay = _lib.RgLayout()
+    flags = 1 if fp32 else 0
+    check(L.rg_initial_condition_host(ini_text.encode(), flags, rank, nranks, None, 0, C.byref(lay)))
+    U = np.zeros((lay.nvar, lay.ksize, lay.jsize, lay.isize), dtype=np.float32 if fp32 else np.float64)
+    check(L.rg_initial_condition_host(ini_text.encode(), flags, rank, nranks, U.ctypes.data_as(C.c_void_p), U.nbytes, C.byref(lay)))
+    return U, lay
+
+
 def slab_extent(nz_global, nranks, rank):
     a, b = C.c_int(0), C.c_int(0)
     check(_lib.load().rg_slab_extent(nz_global, nranks, rank, C.byref(a), C.byref(b)))

@@ -1,0 +1,67 @@
+"""CPU: the host half of init_simulation (rg_initial_condition_host, no device needed) against the initial
+states written by the unmodified reference executable, its independence of the z-slab decomposition (single
+global pseudo-random stream), and the oracle's step on the further MHD test problems of SURVEY 8(f).4 started
+from the reference's initial state."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from ramsesgpu_b200.io import l2_relative
+
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "_history_" not in f)
+NEW_PROBLEMS = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
+                "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5"]
+
+
+def inner(U, lay):
+    g = lay.ghost_width
+    return U[:, 0, g:-g, g:-g] if lay.dim == 2 else U[:, g:-g, g:-g, g:-g]
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_initial_condition_matches_reference_bitwise(native, name):
+    from ramsesgpu_b200 import initial_condition_host
+    g = load_golden(name)
+    U, lay = initial_condition_host(str(g["ini"]), fp32=str(g["precision"]) == "f32")
+    assert np.array_equal(inner(U, lay), g["initial"]), name
+
+
+@pytest.mark.parametrize("name", ["fieldloop3d_16x12x10_s6", "rt3d_mhd_visc_rand_8x10x16_s5", "mri3d_12x20x8_s40",
+                                  "kh3d_16x8x16_f32_s10", "implode3d_16_s8", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
+                                  "currentsheet3d_16x16x8_s5"])
+def test_initial_condition_is_slab_independent(native, name):
+    """every slab generates its part of ONE global state: drand48 jump-ahead / rand() skip, global indices"""
+    from ramsesgpu_b200 import initial_condition_host
+    g = load_golden(name)
+    fp32 = str(g["precision"]) == "f32"
+    mono, lay = initial_condition_host(str(g["ini"]), fp32=fp32)
+    gw = lay.ghost_width
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            U, l = initial_condition_host(str(g["ini"]), fp32=fp32, rank=r, nranks=world)
+            assert l.nz_local == U.shape[1] - 2 * gw
+            parts.append(U[:, gw:gw + l.nz_local])
+        assert np.array_equal(np.concatenate(parts, axis=1), mono[:, gw:-gw])
+
+
+@pytest.mark.parametrize("name", NEW_PROBLEMS)
+def test_oracle_step_on_further_problems(oracle64, name):
+    """the oracle does not restate these initial conditions: it starts from the reference's initial state (inner
+    cells; the ghosts come from the boundary conditions, like the reference's start()) and must reproduce the
+    reference's final state bit for bit"""
+    g = load_golden(name)
+    p = oracle64.params(str(g["ini"]))
+    U = oracle64.alloc(p)
+    gw = p.ghostWidth
+    if p.dim == 2:
+        U[:, 0, gw:-gw, gw:-gw] = g["initial"]
+    else:
+        U[:, gw:-gw, gw:-gw, gw:-gw] = g["initial"]
+    Uf, t, dts = oracle64.run_steps(p, U, int(g["steps"]))
+    final = Uf[:, 0, gw:-gw, gw:-gw] if p.dim == 2 else Uf[:, gw:-gw, gw:-gw, gw:-gw]
+    assert np.array_equal(final, g["final"]), max(l2_relative(a, b) for a, b in zip(g["final"], final))
+    assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])
