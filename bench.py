@@ -157,11 +157,16 @@ def _oracle_rate(args):
     return steps * p.nx * p.ny * p.nz / (time.time() - t0)
 
 
+def workload_name(n, nz_local, nz_total):
+    return "orszag-tang3d.ini 3D MHD %dx%dx%d per GPU (global nz=%d), HLLD + 2D-HLLD CT, periodic, FP64" % (n, n, nz_local, nz_total)
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n = args.ref_size
+    nz_total = args.global_nz if args.global_nz > 0 else args.size * args.gpus
     steps = args.steps + args.warmup
     value, kind, wall = run_reference_cpu(n, steps, cores)
     sample = "%d single-thread replicas of Orszag-Tang 3D %d^3, %d steps each (reference prints nStep*cells/(wall-io))" % (cores, n, steps)
@@ -169,7 +174,9 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "orszag-tang3d.ini 3D MHD HLLD FP64 (reference CPU path euler_cpu, sample %d^3 per core)" % n},
+        # the same workload as the native arm; every step is a bounded sample of it (one 64^3 box per host core)
+        "config": {"workload": workload_name(args.size, nz_total // max(args.gpus, 1), nz_total),
+                   "sample": "reference CPU path euler_cpu, %d^3 cells of the same problem per core, %d cores" % (n, cores)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -335,7 +342,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.global_nz > 0 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "orszag-tang3d.ini 3D MHD %dx%dx%d per GPU (global nz=%d), HLLD + 2D-HLLD CT, periodic, FP64" % (n, n, nz_local, nz_total),
+            "config": {"workload": workload_name(n, nz_local, nz_total),
                        "parallelism": "z-slab x%d" % world, "cache": "inputs larger than L2 (state %.2f GB per GPU)" % (state_bytes / 1e9),
                        "chunk_planes": run.stats().chunk_planes},
             "e2e": None if e2e_value is None else {
