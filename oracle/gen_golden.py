@@ -120,6 +120,9 @@ if __name__ == "__main__":
         "fieldloop3d_16x12x10_s6": ("mhd_fieldloop3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 10}}, 6, "f64"),
         "currentsheet2d_24_s8": ("mhd_currentSheet_2d.ini", {"mesh": {"nx": 24, "ny": 24}}, 8, "f64"),
         "currentsheet3d_16x16x8_s5": ("mhd_currentSheet_3d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 8}}, 5, "f64"),
+        "khmhd2d_24x32_s8": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 24, "ny": 32}}, 8, "f64"),
+        "khmhd3d_12x16x8_s5": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8}, "MHD": {"implementationVersion": 4}}, 5, "f64"),
+        "shearwave3d_16x12x8_s10": ("mhd_shearWave_3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 8}}, 10, "f64"),
     }
     for name, (ini, ov, steps, prec) in cases.items():
         if only and name not in only:

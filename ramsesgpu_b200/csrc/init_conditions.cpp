@@ -538,6 +538,78 @@ bool initCurrentSheet(const ConfigMap& cfg, const RunParams& rp, const KParams<T
   return true;
 }
 
+// shear wave in the shearing box (test of the rotating-frame terms); reference MHDRunBase.cpp:2574-2660
+template <typename T>
+bool initShearWave(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "shear wave needs MHD"; return false; }
+  if (rp.bc[0] != BC_SHEARINGBOX || rp.bc[1] != BC_SHEARINGBOX) {
+    if (msg) *msg = "shear wave needs shearing-box boundaries along x";
+    return false;
+  }
+  Grid<T> g(kp, U);
+  const double TwoPi = 4.0 * std::asin(1.0), d0 = 1.0;
+  const double Lx = kp.dx * rp.nx, Ly = kp.dy * rp.ny;
+  const double energy = cfg.getFloat("ShearWave", "energy", 1.0f);
+  const double delta_vx = (-4.0e-4) * kp.cIso, delta_vy = (1.0e-4) * kp.cIso;
+  const double kx0 = -4 * TwoPi / Lx, ky0 = TwoPi / Ly;
+  const double xi0 = 0.5 * kp.Omega0 / d0;
+  const double delta_rho = (kx0 * delta_vy - ky0 * delta_vx) / xi0;
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < kp.jsize; ++j) {
+      const double yPos = kp.yMin + kp.dy / 2 + (j - kp.gw) * kp.dy;
+      for (int i = 0; i < kp.isize; ++i) {
+        const double xPos = kp.xMin + kp.dx / 2 + (i - kp.gw) * kp.dx;
+        const T d = d0 * (1.0 - delta_rho * std::sin(kx0 * xPos + ky0 * yPos));
+        g.at(ID, i, j, k) = d;
+        g.at(IP, i, j, k) = energy;
+        g.at(IU, i, j, k) = d * delta_vx * std::cos(kx0 * xPos + ky0 * yPos);
+        g.at(IV, i, j, k) = d * delta_vy * std::cos(kx0 * xPos + ky0 * yPos);
+      }
+    }
+  return true;
+}
+
+// magnetised Kelvin-Helmholtz (shear layers normal to y, uniform B_x), 2D and 3D; reference
+// MHDRunBase.cpp:2814-2990 with its quirks: the two perturbation switches are read with getFloat (so only a
+// NUMERIC value overrides the default), `pressure` is read from a section spelt "kelvin_helmholtz", and the 2D
+// branch derives both positions from j.  glibc rand() over the inner cells in (k,j,i) order, 2 (2D) or 3 (3D)
+// draws per cell, consumed whether or not the random perturbation is switched on.
+template <typename T>
+bool initKelvinHelmholtzMhd(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                            std::string* msg) {
+  (void)msg;
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const char* S = "kelvin-helmholtz";
+  std::srand((unsigned)cfg.getInteger(S, "seed", 1));
+  const T amplitude = cfg.getFloat(S, "amplitude", 0.01f);
+  const bool p_sine = cfg.getFloat(S, "perturbation_sine", 0.0f) != 0.0f;
+  const bool p_rand = cfg.getFloat(S, "perturbation_rand", 1.0f) != 0.0f;
+  const T rho_inner = cfg.getFloat(S, "rho_inner", 2.0f), rho_outer = cfg.getFloat(S, "rho_outer", 1.0f);
+  const T pressure = cfg.getFloat("kelvin_helmholtz", "pressure", 2.5f);
+  const T v0 = cfg.getFloat(S, "v0", 1.0f), b0 = cfg.getFloat(S, "b0", 1.0f);
+  const T xMin = kp.xMin, yMin = kp.yMin, xMax = kp.xMax, yMax = kp.yMax;
+  auto pert = [&](T xPos) { return p_rand * amplitude * (1.0 * std::rand() / RAND_MAX - 0.5) + p_sine * amplitude * std::sin(2 * M_PI * xPos); };
+  if (rp.dim == 3)
+    for (long n = 3L * kp.kglob0 * kp.nx * kp.ny; n > 0; --n) (void)std::rand();  // draws of the slabs below
+  for (int k = (rp.dim == 3 ? gw : 0); k < (rp.dim == 3 ? kp.ksize - gw : 1); ++k)
+    for (int j = gw; j < kp.jsize - gw; ++j) {
+      const T yPos = rp.dim == 2 ? T(yMin + (yMax - yMin) * j / kp.jsize) : T(yMin + kp.dy / 2 + (j - gw) * kp.dy);
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        const T xPos = rp.dim == 2 ? T(xMin + (xMax - xMin) * j / kp.jsize) : T(xMin + kp.dx / 2 + (i - gw) * kp.dx);
+        const bool outer = yPos < yMin + 0.25 * (yMax - yMin) || yPos > yMin + 0.75 * (yMax - yMin);
+        const T rho = outer ? rho_outer : rho_inner, vs = outer ? v0 : -v0;
+        const T mx = rho * (vs + pert(xPos));
+        const T my = rho * (pert(xPos));
+        const T mz = rp.dim == 3 ? T(rho * (pert(xPos))) : T(0);
+        g.at(ID, i, j, k) = rho; g.at(IU, i, j, k) = mx; g.at(IV, i, j, k) = my; g.at(IW, i, j, k) = mz;
+        g.at(IA, i, j, k) = b0;
+        g.at(IP, i, j, k) = pressure / (kp.gamma0 - 1.0f) + 0.5 * (mx * mx + my * my + mz * mz) / rho + 0.5 * b0 * b0;
+      }
+    }
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -548,6 +620,9 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Orszag-Tang" || problem == "OrszagTang") return initOrszagTang(cfg, rp, kp, U, message);
     if (problem == "MRI" || problem == "Mri" || problem == "mri") return initMri(cfg, rp, kp, U, message);
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
+    if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtzMhd(cfg, rp, kp, U, message);
+    if (problem == "ShearWave" || problem == "shearwave" || problem == "Shear-Wave" || problem == "shear-wave" || problem == "Shearwave")
+      return initShearWave(cfg, rp, kp, U, message);
     if (problem == "Brio-Wu" || problem == "BrioWu" || problem == "brio-wu" || problem == "briowu") return initBrioWu(cfg, rp, kp, U, message);
     if (problem == "Rotor" || problem == "rotor") return initRotor(cfg, rp, kp, U, message);
     if (problem == "FieldLoop" || problem == "fieldloop" || problem == "Fieldloop" || problem == "field-loop" || problem == "Field-Loop")

@@ -13,7 +13,8 @@ from ramsesgpu_b200.io import l2_relative
 
 ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "_history_" not in f)
 NEW_PROBLEMS = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
-                "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5"]
+                "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5",
+                "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10"]
 
 
 def inner(U, lay):
@@ -31,7 +32,7 @@ def test_initial_condition_matches_reference_bitwise(native, name):
 
 @pytest.mark.parametrize("name", ["fieldloop3d_16x12x10_s6", "rt3d_mhd_visc_rand_8x10x16_s5", "mri3d_12x20x8_s40",
                                   "kh3d_16x8x16_f32_s10", "implode3d_16_s8", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
-                                  "currentsheet3d_16x16x8_s5"])
+                                  "currentsheet3d_16x16x8_s5", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10"])
 def test_initial_condition_is_slab_independent(native, name):
     """every slab generates its part of ONE global state: drand48 jump-ahead / rand() skip, global indices"""
     from ramsesgpu_b200 import initial_condition_host
