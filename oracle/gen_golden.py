@@ -120,6 +120,11 @@ if __name__ == "__main__":
         "fieldloop3d_16x12x10_s6": ("mhd_fieldloop3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 10}}, 6, "f64"),
         "currentsheet2d_24_s8": ("mhd_currentSheet_2d.ini", {"mesh": {"nx": 24, "ny": 24}}, 8, "f64"),
         "currentsheet3d_16x16x8_s5": ("mhd_currentSheet_3d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 8}}, 5, "f64"),
+        # jet inflow through the lower z (3D) / y (2D) ghost cells: boundary patch + dt limit
+        "jet3d_hydro_14x14x20_s8": ("jet3d_gpu.ini", {"mesh": {"nx": 14, "ny": 14, "nz": 20}, "jet": {"ijet": 4, "offsetJet": 5}}, 8, "f64"),
+        "jet3d_mhd_15x15x20_s8": ("mhd_jet3d.ini", {"mesh": {"nx": 15, "ny": 15, "nz": 20}, "MHD": {"implementationVersion": 4},
+                                                     "jet": {"BStatic_z": 0.5, "BStatic_x": 0.1}}, 8, "f64"),
+        "jet2d_mhd_24x32_s10": ("mhd_jet2d.ini", {"mesh": {"nx": 24, "ny": 32}, "MHD": {"implementationVersion": 1}, "jet": {"ijet": 4, "offsetJet": 10}}, 10, "f64"),
         "khmhd2d_24x32_s8": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 24, "ny": 32}}, 8, "f64"),
         "khmhd3d_12x16x8_s5": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8}, "MHD": {"implementationVersion": 4}}, 5, "f64"),
         "shearwave3d_16x12x8_s10": ("mhd_shearWave_3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 8}}, 10, "f64"),

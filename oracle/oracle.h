@@ -75,6 +75,9 @@ typedef struct orc_params {
   /* [rayleigh-taylor] HydroRunBase.cpp:6269-6277, MHDRunBase.cpp:2999-3001 */
   int rt_random, rt_seed;
   real_t rt_amp, rt_d0, rt_d1, rt_bx, rt_by, rt_bz;
+  /* [jet] inflow patch in the lower ghost rows/planes (HydroParameters.h:434-444, HydroRunBase.cpp:2374-2408) */
+  int enableJet, ijet, offsetJet;
+  real_t djet, ujet, pjet, cjet, jet_bx, jet_by, jet_bz;
 } orc_params;
 
 /* parse ini TEXT with the reference's inih + ConfigMap semantics (float parse!) */

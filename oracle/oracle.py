@@ -42,6 +42,8 @@ def _params_struct(real):
             ("gravityEnabled", C.c_int), ("gravity_x", real), ("gravity_y", real), ("gravity_z", real),
             ("rt_random", C.c_int), ("rt_seed", C.c_int),
             ("rt_amp", real), ("rt_d0", real), ("rt_d1", real), ("rt_bx", real), ("rt_by", real), ("rt_bz", real),
+            ("enableJet", C.c_int), ("ijet", C.c_int), ("offsetJet", C.c_int),
+            ("djet", real), ("ujet", real), ("pjet", real), ("cjet", real), ("jet_bx", real), ("jet_by", real), ("jet_bz", real),
         ]
     return OrcParams
 

@@ -238,5 +238,20 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->rt_bx = get_float(&c, "rayleigh-taylor", "bx", 1e-8f);
   p->rt_by = get_float(&c, "rayleigh-taylor", "by", 1e-8f);
   p->rt_bz = get_float(&c, "rayleigh-taylor", "bz", 1e-8f);
+  /* jet: HydroParameters.h:434-444 (enabled by the problem name only), MHDRunBase.cpp:1756-1758 */
+  p->enableJet = !strcmp(p->problem, "jet");
+  p->ijet = (int)get_int(&c, "jet", "ijet", 0);
+  p->djet = get_float(&c, "jet", "djet", 1.0f);
+  p->ujet = get_float(&c, "jet", "ujet", 0.0f);
+  p->pjet = get_float(&c, "jet", "pjet", 0.0f);
+#ifdef ORACLE_FLOAT
+  p->cjet = sqrtf(p->gamma0 * p->pjet / p->djet);
+#else
+  p->cjet = sqrt(p->gamma0 * p->pjet / p->djet);
+#endif
+  p->offsetJet = (int)get_int(&c, "jet", "offsetJet", 0);
+  p->jet_bx = get_float(&c, "jet", "BStatic_x", 0.0f);
+  p->jet_by = get_float(&c, "jet", "BStatic_y", 0.0f);
+  p->jet_bz = get_float(&c, "jet", "BStatic_z", 0.0f);
   return 0;
 }

@@ -269,6 +269,27 @@ static int init_rayleigh_taylor(const orc_params *P, real_t *U) {
   return 0;
 }
 
+/* jet: uniform medium at rest (HydroRunBase.cpp:5282-5350; MHD: + static field, MHDRunBase.cpp:1747-1800),
+ * inner cells only; the jet itself enters through the boundary patch of make_jet */
+static int init_jet(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  const real_t Bx = P->jet_bx, By = P->jet_by, Bz = P->jet_bz;
+  for (int k = (P->dim == 3 ? gw : 0); k < (P->dim == 3 ? ksz - gw : 1); ++k)
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        AT(U, i, j, k, ID) = 1.0f;
+        if (P->mhdEnabled) {
+          AT(U, i, j, k, IP) = 1.0f / (P->gamma0 - 1.0f) + 0.5 * (P->dim == 3 ? (Bx * Bx + By * By + Bz * Bz) : (Bx * Bx + By * By));
+          AT(U, i, j, k, IA) = Bx; AT(U, i, j, k, IB) = By; AT(U, i, j, k, IC) = Bz;
+        } else {
+          AT(U, i, j, k, IP) = 1.0f / (P->gamma0 - 1.0f);
+        }
+      }
+  if (!P->mhdEnabled) fill_corners_gw2(P, U);
+  return 0;
+}
+
 /* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
 int orc_init_problem(const orc_params *P, real_t *U) {
   const char *n = P->problem;
@@ -276,7 +297,9 @@ int orc_init_problem(const orc_params *P, real_t *U) {
     if (!strcmp(n, "Orszag-Tang") || !strcmp(n, "OrszagTang")) { init_orszag_tang(P, U); return 0; }
     if (!strcmp(n, "MRI") || !strcmp(n, "Mri") || !strcmp(n, "mri")) { init_mri(P, U); return 0; }
     if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
+    if (!strcmp(n, "jet") || !strcmp(n, "Jet")) return init_jet(P, U);
   } else {
+    if (!strcmp(n, "jet")) return init_jet(P, U);
     if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
     if (!strcmp(n, "implode")) { init_implode(P, U); return 0; }
     if (!strcmp(n, "Kelvin-Helmholtz")) return init_kelvin_helmholtz(P, U);

@@ -600,6 +600,8 @@ real_t orc_compute_dt_mhd(const orc_params *P, const real_t *U) {
           invDt = FMAX_(invDt, vx / P->dx + vy / P->dy);
         }
       }
+  /* the inflow speed of the jet limits the step too: HydroRunBase.cpp:420-422, MHDRunBase.cpp:184-186,228-230 */
+  if (P->enableJet) invDt = FMAX_(invDt, (P->ujet + P->cjet) / P->dx);
   return P->cfl / invDt;
 }
 

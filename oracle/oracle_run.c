@@ -52,12 +52,35 @@ static void fill_face(const orc_params *P, real_t *U, int face, int bct) {
     }
 }
 
+/* HydroRunBase.cpp:2374-2408 make_jet: matter injected through a square patch of the LOWER ghost rows (2D: y) or
+ * planes (3D: z); hydro variables only, the magnetic field of the patch keeps the boundary values */
+static void make_jet(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  const int a = gw + P->offsetJet, b = gw + P->offsetJet + P->ijet;
+  const real_t e = P->pjet / (P->gamma0 - 1.) + 0.5 * P->djet * P->ujet * P->ujet;
+  if (P->dim == 2) {
+    for (int j = 0; j < gw; ++j)
+      for (int i = a; i < b; ++i) {
+        AT(U, i, j, 0, ID) = P->djet; AT(U, i, j, 0, IP) = e;
+        AT(U, i, j, 0, IU) = 0.0f; AT(U, i, j, 0, IV) = P->djet * P->ujet;
+      }
+  } else {
+    for (int k = 0; k < gw; ++k)
+      for (int j = a; j < b; ++j)
+        for (int i = a; i < b; ++i) {
+          AT(U, i, j, k, ID) = P->djet; AT(U, i, j, k, IP) = e;
+          AT(U, i, j, k, IU) = 0.0f; AT(U, i, j, k, IV) = 0.0f; AT(U, i, j, k, IW) = P->djet * P->ujet;
+        }
+  }
+}
+
 /* HydroRunBase.cpp:2280-2316 */
 void orc_make_boundaries(const orc_params *P, real_t *U, int idim) {
   int d = idim - 1;
   if (d == 2 && P->dim == 2) return;
   fill_face(P, U, 2 * d, P->bc[2 * d]);
   fill_face(P, U, 2 * d + 1, P->bc[2 * d + 1]);
+  if (P->enableJet && d == P->dim - 1) make_jet(P, U); /* after the last direction, :2290-2291, :2310-2311 */
 }
 
 /* HydroRunBase.cpp:2333-2342: X, then Y, then Z */

@@ -11,7 +11,9 @@ CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neu
          "kh3d_16x8x16_f64_s10", "kh3d_16x8x16_f32_s10", "mri3d_16x32x16_s12", "mri3d_12x20x8_s40",
          # resistivity / viscosity / static gravity
          "ot3d_diss_16x12x20_s6", "ot3d_eta_walls_16_s4", "mri3d_diss_12x20x8_s10", "implode3d_visc_16_s6",
-         "kh3d_visc_16x8x16_f32_s6", "rt3d_hydro_10x8x24_s8", "rt3d_mhd_10x8x24_s8", "rt3d_mhd_visc_rand_8x10x16_s5"]
+         "kh3d_visc_16x8x16_f32_s6", "rt3d_hydro_10x8x24_s8", "rt3d_mhd_10x8x24_s8", "rt3d_mhd_visc_rand_8x10x16_s5",
+         # jet inflow boundary
+         "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -31,7 +33,7 @@ def test_oracle_matches_reference_run(oracle64, oracle32, name):
     if g["total_time"] == g["total_time"]:  # the hydro driver does not print these
         assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])   # stdout prints 12 digits
         assert abs(dts[-1] - g["dt_last"]) <= 1e-11 * abs(g["dt_last"])
-    assert abs(dts[0] - g["dt0"]) <= 2e-6 * abs(g["dt0"])                 # printed with 6-7 digits
+    assert abs(dts[0] - g["dt0"]) <= max(2e-6 * abs(g["dt0"]), 5.1e-9)    # printed with 6-7 digits / 8 decimals
 
 
 def test_riemann_hlld_known_answer(oracle64):
