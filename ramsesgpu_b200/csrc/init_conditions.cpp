@@ -610,6 +610,29 @@ bool initKelvinHelmholtzMhd(const ConfigMap& cfg, const RunParams& rp, const KPa
   return true;
 }
 
+// jet: uniform medium at rest (+ static field for MHD), inner cells; the jet enters through the boundary patch.
+// Reference HydroRunBase.cpp:5282-5350, MHDRunBase.cpp:1747-1800.
+template <typename T>
+bool initJet(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  (void)msg;
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const T Bx = cfg.getFloat("jet", "BStatic_x", 0.0f), By = cfg.getFloat("jet", "BStatic_y", 0.0f), Bz = cfg.getFloat("jet", "BStatic_z", 0.0f);
+  for (int k = (rp.dim == 3 ? gw : 0); k < (rp.dim == 3 ? kp.ksize - gw : 1); ++k)
+    for (int j = gw; j < kp.jsize - gw; ++j)
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        g.at(ID, i, j, k) = 1.0f;
+        if (rp.mhdEnabled) {
+          g.at(IP, i, j, k) = 1.0f / (kp.gamma0 - 1.0f) + 0.5 * (rp.dim == 3 ? (Bx * Bx + By * By + Bz * Bz) : (Bx * Bx + By * By));
+          g.at(IA, i, j, k) = Bx; g.at(IB, i, j, k) = By; g.at(IC, i, j, k) = Bz;
+        } else {
+          g.at(IP, i, j, k) = 1.0f / (kp.gamma0 - 1.0f);
+        }
+      }
+  if (!rp.mhdEnabled) fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -621,6 +644,7 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "MRI" || problem == "Mri" || problem == "mri") return initMri(cfg, rp, kp, U, message);
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
     if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtzMhd(cfg, rp, kp, U, message);
+    if (problem == "jet" || problem == "Jet") return initJet(cfg, rp, kp, U, message);
     if (problem == "ShearWave" || problem == "shearwave" || problem == "Shear-Wave" || problem == "shear-wave" || problem == "Shearwave")
       return initShearWave(cfg, rp, kp, U, message);
     if (problem == "Brio-Wu" || problem == "BrioWu" || problem == "brio-wu" || problem == "briowu") return initBrioWu(cfg, rp, kp, U, message);
@@ -633,6 +657,7 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "implode") return initImplode(cfg, rp, kp, U, message);
     if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtz(cfg, rp, kp, U, message);
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
+    if (problem == "jet") return initJet(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

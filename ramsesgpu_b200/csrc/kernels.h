@@ -37,6 +37,9 @@ struct MhdKernels {
   // ghost fill of one direction (0,1,2), both faces; reference make_boundary2
   static void fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
                            int kLo, int kHi, cudaStream_t s);
+  // jet inflow patch in the lower ghost rows (2D) / planes (3D), after the ghost fill of the last direction;
+  // reference make_jet, HydroRunBase.cpp:2374-2408 (hydro variables only)
+  static void jetInflow(const KParams<T>& P, T* U, cudaStream_t s);
   // max over inner cells of the inverse time step -> *dMaxInvDt (ordered-uint encoding)
   static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* dMaxInvDt, cudaStream_t s);
   // 3D MHD chunk pipeline on planes [ka, kb) of the update range

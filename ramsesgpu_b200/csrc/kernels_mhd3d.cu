@@ -1218,6 +1218,33 @@ bool setTuning(const char* key, int value) {
 }
 void resetKernelLaunchCount() { g_launches = 0; }
 
+// jet inflow patch: (ijet x ijet x gw) cells in 3D, (ijet x gw) in 2D (reference make_jet)
+template <typename T>
+__global__ void k_jet(const __grid_constant__ KParams<T> P, T* __restrict__ U) {
+  const int a = P.gw + P.offsetJet;
+  const int i = a + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a + P.ijet || i >= P.isize) return;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const T e = P.pjet / (P.gamma0 - T(1)) + T(0.5) * P.djet * P.ujet * P.ujet;
+  size_t idx;
+  if (P.dim == 2) {
+    idx = (size_t)blockIdx.y * P.isize + i;              // j = blockIdx.y < gw
+  } else {
+    const int j = a + blockIdx.y, k = blockIdx.z;      // k < gw
+    if (j >= P.jsize) return;
+    idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  }
+  U[ID * comp + idx] = P.djet;
+  U[IP * comp + idx] = e;
+  U[IU * comp + idx] = T(0);
+  if (P.dim == 2) {
+    U[IV * comp + idx] = P.djet * P.ujet;
+  } else {
+    U[IV * comp + idx] = T(0);
+    U[IW * comp + idx] = P.djet * P.ujet;
+  }
+}
+
 // ---- launch wrappers ---------------------------------------------------------------------------
 template <typename T>
 void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
@@ -1228,6 +1255,14 @@ void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, i
   dim3 block(32, 8, 1);
   dim3 grid((sizes[d1] + 31) / 32, (sizes[d2] + 7) / 8, 2 * P.gw);
   k_boundary<T><<<grid, block, 0, s>>>(P, U, dir, bcLo, bcHi, skipLo ? 1 : 0, skipHi ? 1 : 0, kLo, kHi);
+  ++g_launches;
+}
+
+template <typename T>
+void MhdKernels<T>::jetInflow(const KParams<T>& P, T* U, cudaStream_t s) {
+  if (!P.jet || P.ijet <= 0) return;
+  const dim3 grid((P.ijet + 31) / 32, P.dim == 2 ? P.gw : P.ijet, P.dim == 2 ? 1 : P.gw);
+  k_jet<T><<<grid, 32, 0, s>>>(P, U);
   ++g_launches;
 }
 

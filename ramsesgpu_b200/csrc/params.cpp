@@ -1,5 +1,7 @@
 #include "params.h"
 
+#include <cmath>
+
 #include <algorithm>
 #include <cctype>
 
@@ -117,6 +119,13 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
     k.gy = cfg.getFloat("gravity", "static_field_y", 0.0f);
     k.gz = cfg.getFloat("gravity", "static_field_z", 0.0f);
   }
+  k.jet = rp.problem == "jet" ? 1 : 0;
+  k.ijet = static_cast<int>(cfg.getInteger("jet", "ijet", 0));
+  k.offsetJet = static_cast<int>(cfg.getInteger("jet", "offsetJet", 0));
+  k.djet = cfg.getFloat("jet", "djet", 1.0f);
+  k.ujet = cfg.getFloat("jet", "ujet", 0.0f);
+  k.pjet = cfg.getFloat("jet", "pjet", 0.0f);
+  k.cjet = std::sqrt(k.gamma0 * k.pjet / k.djet);
   return k;
 }
 

@@ -38,6 +38,10 @@ struct KParams {
   T nu, eta;
   int gravity;
   T gx, gy, gz;
+  // jet inflow through a square patch of the lower ghost rows (2D: y) / planes (3D: z), problem "jet"
+  // (reference HydroParameters.h:434-444, HydroRunBase.cpp:2374-2408)
+  int jet, ijet, offsetJet;
+  T djet, ujet, pjet, cjet;
 };
 
 struct RunParams {

@@ -244,6 +244,8 @@ class RunImpl final : public Run {
     // (the hydro driver starts from 0, HydroRunBase.cpp:386)
     T invDt = rp_.mhdEnabled ? kp_.smallc / std::min(kp_.dx, kp_.dy) : T(0);
     invDt = std::max(invDt, static_cast<T>(decodeMax(best)));
+    // the inflow speed of the jet limits the step too (reference HydroRunBase.cpp:420-422, MHDRunBase.cpp:228-230)
+    if (kp_.jet) invDt = std::max(invDt, (kp_.ujet + kp_.cjet) / kp_.dx);
     return static_cast<double>(kp_.cfl / invDt);
   }
 
@@ -658,6 +660,8 @@ class RunImpl final : public Run {
       MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
       if (rp_.dim == 3 && nranks_ == 1)
         MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
+      // jet inflow patch after the last direction (reference HydroRunBase.cpp:2290, :2310); with slabs below
+      if (kp_.jet && (rp_.dim == 2 || nranks_ == 1)) MhdKernels<T>::jetInflow(kp_, U, stream_);
     });
     if (rp_.dim == 2 || nranks_ == 1) return;
     bool hasLo, hasHi;
@@ -666,6 +670,7 @@ class RunImpl final : public Run {
     if (!hasLo || !hasHi)
       phase(PH_BOUNDARY, [&] {
         MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
+        if (kp_.jet && !hasLo) MhdKernels<T>::jetInflow(kp_, U, stream_);  // the slab that owns the lower z face
       });
     if (haloDone_[b]) {
       haloDone_[b] = false;

@@ -1,5 +1,6 @@
 """GPU: the further MHD test problems of the reference (Brio-Wu shock tube, field-loop advection,
-current sheet; 2D and 3D, outflow and periodic boundaries) on the same CUDA step kernels, through the C ABI,
+current sheet, magnetised Kelvin-Helmholtz, shear wave in the shearing box, jets; 2D and 3D, outflow, wall and
+periodic boundaries) on the same CUDA step kernels, through the C ABI,
 against golden vectors from the unmodified reference executable."""
 import numpy as np
 import pytest
@@ -10,14 +11,17 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
          "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5",
-         "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10"]
+         "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10",
+         # jet inflow boundary patch + dt limit (hydro 3D, MHD 3D, MHD 2D)
+         "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_golden_reference_run(native, name):
-    from ramsesgpu_b200 import MHDRunGodunov
+    from ramsesgpu_b200 import HydroRunGodunov, MHDRunGodunov
     g = load_golden(name)
-    with MHDRunGodunov(str(g["ini"])) as run:
+    Run = MHDRunGodunov if len(g["names"]) == 8 else HydroRunGodunov
+    with Run(str(g["ini"])) as run:
         run.init_simulation()
         run.make_all_boundaries(0)
         run.setDataHost(run.getDataHost(0), 1)
@@ -29,11 +33,12 @@ def test_golden_reference_run(native, name):
     got = U[:, 0, gw:-gw, gw:-gw] if dim == 2 else U[:, gw:-gw, gw:-gw, gw:-gw]
     ref = g["final"]
     mom = np.sqrt(sum(float(np.sum(ref[v] ** 2)) for v in (2, 3, 4)))
-    mag = np.sqrt(sum(float(np.sum(ref[v] ** 2)) for v in (5, 6, 7)))
+    mag = np.sqrt(sum(float(np.sum(ref[v] ** 2)) for v in (5, 6, 7))) if len(ref) == 8 else 1.0
     for v, vname in enumerate(g["names"]):
         # vector components against the norm of their vector field (components that stay ~0 by symmetry)
         norm = np.sqrt(np.sum(ref[v] ** 2)) if v < 2 else (mom if v < 5 else mag)
         err = np.sqrt(np.sum((ref[v] - got[v]) ** 2)) / max(norm, 1e-300)
         assert err < TOL_F64, (name, vname, err)
-    assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
-    assert abs(dt - g["dt_last"]) < 1e-10 * g["dt_last"]
+    if g["total_time"] == g["total_time"]:   # the hydro driver of the reference does not print these
+        assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
+        assert abs(dt - g["dt_last"]) < 1e-10 * g["dt_last"]
