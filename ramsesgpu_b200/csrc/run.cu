@@ -83,6 +83,11 @@ class RunImpl final : public Run {
     if (nranks_ > 1 && nzLocal < rp_.ghostWidth)
       throw std::runtime_error("z-slab thinner than the ghost width");
     kp_ = makeKParams<T>(cfg_, rp_, nzLocal, kOff);
+    // variants of the reference that are not built must fail loudly, not run with silently different numerics
+    for (int f = 0; f < 2 * rp_.dim; ++f)
+      if (rp_.bc[f] == BC_COPY || rp_.bc[f] == BC_Z_STRATIFIED)
+        throw std::runtime_error("boundary type " + std::to_string(rp_.bc[f]) + " (copy / z-stratified) is not available in this build");
+    if (kp_.slope_type == T(3)) throw std::runtime_error("slope_type 3 (27-point positivity-preserving slopes) is not available in this build");
     cells_ = (size_t)kp_.isize * kp_.jsize * kp_.ksize;
     elems_ = cells_ * kp_.nvar;
     RG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
