@@ -227,7 +227,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--size", type=int, default=256, help="cells per direction per GPU")
     ap.add_argument("--ref-size", type=int, default=64, help="grid of each CPU replica of the reference arm")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8,
+                    help="host-buffer steps of the e2e leg (the batch leg submits twice as many one-step jobs)")
     ap.add_argument("--global-nz", type=int, default=0,
                     help="strong scaling: fixed global grid size x size x GLOBAL_NZ split into z slabs (default: weak, size^3 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
