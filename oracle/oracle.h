@@ -78,7 +78,13 @@ typedef struct orc_params {
   /* [jet] inflow patch in the lower ghost rows/planes (HydroParameters.h:434-444, HydroRunBase.cpp:2374-2408) */
   int enableJet, ijet, offsetJet;
   real_t djet, ujet, pjet, cjet, jet_bx, jet_by, jet_bz;
+  /* stratified shearing box (MHDRunBase.cpp:2763-2800, :3163-3211; make_boundary_base.h:1357-1647):
+     gravityMode 0 = none, 1 = uniform static field (Rayleigh-Taylor), 2 = vertical field of the MRI problem */
+  int gravityMode, mri_smoothGravity, mri_bcFloor;
+  real_t mri_zFloor;
 } orc_params;
+/* gravity field of cell plane k (reference h_gravity(i,j,k,0..2)) */
+void orc_gravity_at(const orc_params *p, int k, real_t g[3]);
 
 /* parse ini TEXT with the reference's inih + ConfigMap semantics (float parse!) */
 int  orc_params_from_ini(const char *ini_text, orc_params *p);

@@ -253,5 +253,15 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->jet_bx = get_float(&c, "jet", "BStatic_x", 0.0f);
   p->jet_by = get_float(&c, "jet", "BStatic_y", 0.0f);
   p->jet_bz = get_float(&c, "jet", "BStatic_z", 0.0f);
+  /* gravity field: uniform for Rayleigh-Taylor, the vertical field of init_mhd_mri_grav_field for MRI with
+     [gravity] static=yes (MHDRunBase.cpp:2763-2766), zero otherwise */
+  p->mri_smoothGravity = get_bool(&c, "MRI", "smoothGravity", 0);
+  p->mri_zFloor = get_float(&c, "MRI", "zFloor", 5.0f);
+  p->mri_bcFloor = get_bool(&c, "MRI", "floor", 0);
+  p->gravityMode = 0;
+  if (p->gravityEnabled) {
+    if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityMode = 1;
+    else if (p->mhdEnabled && (!strcmp(p->problem, "MRI") || !strcmp(p->problem, "Mri") || !strcmp(p->problem, "mri"))) p->gravityMode = 2;
+  }
   return 0;
 }

@@ -264,9 +264,11 @@ void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, re
         real_t sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v_ * dpy - dvy * gamma * p) * dtdy + (-w * dpz - dwz * gamma * p) * dtdz;
         r = r + sr0; u = u + su0; v_ = v_ + sv0; w = w + sw0; p = p + sp0;
         /* gravity predictor, added to qm/qp AFTER the trace (HydroRunGodunov.cpp:2705-2734) */
-        const real_t gpx = P->gravityEnabled ? HALF * dt * P->gravity_x : 0;
-        const real_t gpy = P->gravityEnabled ? HALF * dt * P->gravity_y : 0;
-        const real_t gpz = P->gravityEnabled ? HALF * dt * P->gravity_z : 0;
+        real_t gf[3];
+        orc_gravity_at(P, k, gf);
+        const real_t gpx = P->gravityEnabled ? HALF * dt * gf[0] : 0;
+        const real_t gpy = P->gravityEnabled ? HALF * dt * gf[1] : 0;
+        const real_t gpz = P->gravityEnabled ? HALF * dt * gf[2] : 0;
         for (int dd = 0; dd < 3; ++dd) {
           real_t s[2] = {-ONE, ONE};
           for (int side = 0; side < 2; ++side) { /* side 0: qp (low face), 1: qm (high face) */
@@ -312,9 +314,11 @@ void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, re
       for (int j = gw; j < jsz - gw; ++j)
         for (int i = gw; i < isz - gw; ++i) {
           real_t rhoOld = AT(Uold, i, j, k, ID), rhoNew = AT(Unew, i, j, k, ID);
-          AT(Unew, i, j, k, IU) += HALF * dt * P->gravity_x * (rhoOld + rhoNew);
-          AT(Unew, i, j, k, IV) += HALF * dt * P->gravity_y * (rhoOld + rhoNew);
-          AT(Unew, i, j, k, IW) += HALF * dt * P->gravity_z * (rhoOld + rhoNew);
+          real_t gf[3];
+          orc_gravity_at(P, k, gf);
+          AT(Unew, i, j, k, IU) += HALF * dt * gf[0] * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IV) += HALF * dt * gf[1] * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IW) += HALF * dt * gf[2] * (rhoOld + rhoNew);
         }
   free(Q); free(tr);
   orc_dissipative_3d(P, Unew, dt, 0, 0); /* viscosity, HydroRunGodunov.cpp:2908-2927 */

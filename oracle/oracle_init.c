@@ -124,6 +124,18 @@ static void init_mri(const orc_params *P, real_t *U) {
         else if (!strcmp(P->mri_type, "pyl") || !strcmp(P->mri_type, "fluxZ")) AT(U, i, j, k, IC) = B0;
         else AT(U, i, j, k, IC) = 0;
       }
+  if (P->gravityEnabled) { /* stratified disc: MHDRunBase.cpp:2763-2800 */
+    const double zFloor = P->mri_zFloor, H = P->cIso / P->Omega0;
+    for (int k = 0; k < ksz; ++k) {
+      real_t zPos = P->zMin + P->dz / 2 + (k - gw) * P->dz;
+      for (int j = 0; j < jsz; ++j)
+        for (int i = 0; i < isz; ++i) {
+          AT(U, i, j, k, ID) = d0 * fmax(exp(-(zPos * zPos) / 2.0 / (H * H)), exp(-zFloor * zFloor / 2.0));
+          AT(U, i, j, k, IA) = 0; AT(U, i, j, k, IB) = 0; AT(U, i, j, k, IC) = 0;
+          if (zPos < H && zPos > -H) AT(U, i, j, k, IB) = B0;
+        }
+    }
+  }
 }
 
 static void fill_corners_gw2(const orc_params *P, real_t *U) {

@@ -734,7 +734,9 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
         E[2][1][0] = AT(elec, i + 1, j, k, 2); E[2][1][1] = AT(elec, i + 1, j + 1, k, 2);
         orc_trace_mhd_3d(P, q, (const real_t(*)[8])dq, bfNb, dbf, (const real_t(*)[2][2])E, dtdx, dtdy, dtdz, xPos, qm, qp, qEdge);
         if (P->gravityEnabled) { /* gravity predictor on every traced velocity, cpu_v3.cpp:277-332 */
-          const real_t g[3] = {HALF * dt * P->gravity_x, HALF * dt * P->gravity_y, HALF * dt * P->gravity_z};
+          real_t gf[3];
+          orc_gravity_at(P, k, gf);
+          const real_t g[3] = {HALF * dt * gf[0], HALF * dt * gf[1], HALF * dt * gf[2]};
           for (int d = 0; d < 3; ++d)
             for (int c = 0; c < 3; ++c) {
               qm[d][IU + c] += g[c];
@@ -854,6 +856,20 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
         if (!rot || in_i) AT(emf, i, j, k, 2) = emfX;
       }
 
+  /* gravity source term on the momenta of the inner cells, cpu_v3.cpp:585-588 -> HydroRunBase.cpp:1962-1976;
+   * in the rotating step it comes BEFORE the border remap of the density (MHDRunGodunov.cpp:3188-3192 vs :3203) */
+  if (P->gravityEnabled)
+    for (int k = gw; k < ksz - gw; ++k)
+      for (int j = gw; j < jsz - gw; ++j)
+        for (int i = gw; i < isz - gw; ++i) {
+          real_t rhoOld = AT(Uold, i, j, k, ID), rhoNew = AT(Unew, i, j, k, ID);
+          real_t gf[3];
+          orc_gravity_at(P, k, gf);
+          AT(Unew, i, j, k, IU) += HALF * dt * gf[0] * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IV) += HALF * dt * gf[1] * (rhoOld + rhoNew);
+          AT(Unew, i, j, k, IW) += HALF * dt * gf[2] * (rhoOld + rhoNew);
+        }
+
   if (shearBox) { /* flux / emf remap and border density update, MHDRunGodunov.cpp:3203-3305 */
     real_t deltay = 1.5 * Omega0 * (dx * nx) * (totalTime + dt / 2);
     deltay = FMOD_(deltay, (dy * ny));
@@ -890,17 +906,6 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
         AT(Unew, nx + gw - 1, j, k, ID) = FMAX_(AT(Unew, nx + gw - 1, j, k, ID), P->smallr);
       }
   }
-
-  /* gravity source term on the momenta of the inner cells, cpu_v3.cpp:585-588 -> HydroRunBase.cpp:1962-1976 */
-  if (P->gravityEnabled)
-    for (int k = gw; k < ksz - gw; ++k)
-      for (int j = gw; j < jsz - gw; ++j)
-        for (int i = gw; i < isz - gw; ++i) {
-          real_t rhoOld = AT(Uold, i, j, k, ID), rhoNew = AT(Unew, i, j, k, ID);
-          AT(Unew, i, j, k, IU) += HALF * dt * P->gravity_x * (rhoOld + rhoNew);
-          AT(Unew, i, j, k, IV) += HALF * dt * P->gravity_y * (rhoOld + rhoNew);
-          AT(Unew, i, j, k, IW) += HALF * dt * P->gravity_z * (rhoOld + rhoNew);
-        }
 
   /* constrained transport: cpu_v3.cpp:600-630 (emf index: 0 = Z, 1 = Y, 2 = X) */
   for (int k = gw; k < ksz - gw + 1; ++k)

@@ -52,6 +52,90 @@ static void fill_face(const orc_params *P, real_t *U, int face, int bct) {
     }
 }
 
+/* reference h_gravity(i,j,k,:): uniform static field (HydroRunBase.cpp:6400-6408) or the vertical field of the
+ * stratified shearing box, g_z = -(phi(z+dz) - phi(z-dz)) / (2 dz) with phi = Omega0^2 z^2 / 2, optionally
+ * flattened above zFloor (MHDRunBase.cpp:3163-3211; phi is held in double) */
+void orc_gravity_at(const orc_params *P, int k, real_t g[3]) {
+  g[0] = g[1] = g[2] = 0;
+  if (P->gravityMode == 1) {
+    g[0] = P->gravity_x; g[1] = P->gravity_y; g[2] = P->gravity_z;
+  } else if (P->gravityMode == 2) {
+    const real_t Omega0 = P->Omega0, dz = P->dz, HALF = (real_t)0.5;
+    real_t zPos = P->zMin + dz / 2 + (k - P->ghostWidth) * dz;
+    double phi0 = HALF * Omega0 * Omega0 * (zPos - dz) * (zPos - dz);
+    double phi1 = HALF * Omega0 * Omega0 * (zPos + dz) * (zPos + dz);
+    if (P->mri_smoothGravity) {
+      double zFloor = P->mri_zFloor;
+      if ((zPos - dz) > zFloor) phi0 = HALF * Omega0 * Omega0 * zFloor * zFloor;
+      if ((zPos + dz) > zFloor) phi1 = HALF * Omega0 * Omega0 * zFloor * zFloor;
+    }
+    const double zero = 0.0;
+    g[0] = -HALF * (zero - zero) / P->dx;
+    g[1] = -HALF * (zero - zero) / P->dy;
+    g[2] = -HALF * (phi1 - phi0) / dz;
+  }
+}
+
+/* make_boundary_base.h:1357-1647 make_boundary2_z_stratified_cpu (ghost width 3): hydrostatic extrapolation of
+ * the density, velocities copied (outflow only for w), zero horizontal field, B_z from div B = 0.  The reference's
+ * ZMAX branch differences B_y with itself (dbydy = 0, :1611-1612, :1623-1624); kept. */
+static void fill_z_stratified(const orc_params *P, real_t *U, int hi) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize;
+  const real_t dx = P->dx, dy = P->dy, dz = P->dz, HALF = (real_t)0.5;
+  const real_t H = P->cIso / P->Omega0;
+  const real_t factor = -dz / 2.0 / H / H;
+  real_t r1 = 1, r2 = 1, r3 = 1;
+  if (!P->mri_bcFloor) {
+    if (!hi) {
+      r1 = exp(factor * (-2 * (P->zMin + HALF * dz) + dz));
+      r2 = exp(factor * (-2 * (P->zMin + HALF * dz) + 3.0 * dz));
+      r3 = exp(factor * (-2 * (P->zMin + HALF * dz) + 5.0 * dz));
+    } else {
+      r1 = exp(factor * (2 * (P->zMax - HALF * dz) + dz));
+      r2 = exp(factor * (2 * (P->zMax - HALF * dz) + 3.0 * dz));
+      r3 = exp(factor * (2 * (P->zMax - HALF * dz) + 5.0 * dz));
+    }
+  }
+  /* planes: e = first inner plane next to the face, g1..g3 = ghost planes going outwards */
+  const int e = hi ? ksz - 4 : 3, s = hi ? 1 : -1;
+  const int g1 = e + s, g2 = e + 2 * s, g3 = e + 3 * s;
+  for (int j = 0; j < jsz; ++j)
+    for (int i = 0; i < isz; ++i) {
+      real_t rho_e = AT(U, i, j, e, ID);
+      real_t rho1 = rho_e * r1, rho2 = rho_e * r1 * r2, rho3 = rho_e * r1 * r2 * r3;
+      AT(U, i, j, g1, ID) = rho1; AT(U, i, j, g2, ID) = rho2; AT(U, i, j, g3, ID) = rho3;
+      for (int v = IU; v <= IV; ++v) {
+        real_t m = AT(U, i, j, e, v);
+        AT(U, i, j, g3, v) = m / rho_e * rho3;
+        AT(U, i, j, g2, v) = m / rho_e * rho2;
+        AT(U, i, j, g1, v) = m / rho_e * rho1;
+      }
+      real_t w = hi ? fmax(AT(U, i, j, e, IW), 0) : fmin(AT(U, i, j, e, IW), 0);
+      AT(U, i, j, g1, IW) = w; AT(U, i, j, g2, IW) = w; AT(U, i, j, g3, IW) = w;
+      for (int v = IA; v <= IB; ++v) { AT(U, i, j, g1, v) = 0; AT(U, i, j, g2, v) = 0; AT(U, i, j, g3, v) = 0; }
+    }
+  for (int j = 0; j < jsz - 1; ++j)
+    for (int i = 0; i < isz - 1; ++i) {
+      if (!hi) { /* lower face: B_z on the low faces of the ghost planes 2, 1, 0 from the one of plane 3 */
+        real_t bz = AT(U, i, j, 3, IC), acc = bz;
+        for (int k = 2; k >= 0; --k) {
+          real_t dbxdx = (AT(U, i + 1, j, k, IA) - AT(U, i, j, k, IA)) / dx;
+          real_t dbydy = (AT(U, i, j + 1, k, IB) - AT(U, i, j, k, IB)) / dy;
+          acc = acc + dz * (dbxdx + dbydy);
+          AT(U, i, j, k, IC) = acc;
+        }
+      } else {   /* upper face: planes ksz-2, ksz-1 from the low-face B_z of plane ksz-3 */
+        real_t bz = AT(U, i, j, ksz - 3, IC), acc = bz;
+        for (int k = ksz - 3; k <= ksz - 2; ++k) {
+          real_t dbxdx = (AT(U, i + 1, j, k, IA) - AT(U, i, j, k, IA)) / dx;
+          real_t dbydy = (AT(U, i, j, k, IB) - AT(U, i, j, k, IB)) / dy;
+          acc = acc - dz * (dbxdx + dbydy);
+          AT(U, i, j, k + 1, IC) = acc;
+        }
+      }
+    }
+}
+
 /* HydroRunBase.cpp:2374-2408 make_jet: matter injected through a square patch of the LOWER ghost rows (2D: y) or
  * planes (3D: z); hydro variables only, the magnetic field of the patch keeps the boundary values */
 static void make_jet(const orc_params *P, real_t *U) {
@@ -78,8 +162,8 @@ static void make_jet(const orc_params *P, real_t *U) {
 void orc_make_boundaries(const orc_params *P, real_t *U, int idim) {
   int d = idim - 1;
   if (d == 2 && P->dim == 2) return;
-  fill_face(P, U, 2 * d, P->bc[2 * d]);
-  fill_face(P, U, 2 * d + 1, P->bc[2 * d + 1]);
+  if (d == 2 && P->bc[4] == BC_Z_STRATIFIED) fill_z_stratified(P, U, 0); else fill_face(P, U, 2 * d, P->bc[2 * d]);
+  if (d == 2 && P->bc[5] == BC_Z_STRATIFIED) fill_z_stratified(P, U, 1); else fill_face(P, U, 2 * d + 1, P->bc[2 * d + 1]);
   if (P->enableJet && d == P->dim - 1) make_jet(P, U); /* after the last direction, :2290-2291, :2310-2311 */
 }
 

@@ -146,6 +146,20 @@ bool initMri(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, st
         else if (type == "pyl" || type == "fluxZ") g.at(IC, i, j, k) = B0;
         else g.at(IC, i, j, k) = T(0);
       }
+  if (kp.gravity) {  // stratified disc (reference MHDRunBase.cpp:2763-2800): Gaussian density profile with a floor,
+                     // toroidal field within one scale height; the velocity perturbation above is kept
+    const double zFloor = cfg.getFloat("MRI", "zFloor", 5.0f), H = kp.cIso / kp.Omega0;
+    for (int k = 0; k < kp.ksize; ++k) {
+      const T zPos = kp.zMin + kp.dz / 2 + (k + kp.kglob0 - kp.gw) * kp.dz;
+      for (int j = 0; j < kp.jsize; ++j)
+        for (int i = 0; i < kp.isize; ++i) {
+          g.at(ID, i, j, k) = d0 * std::fmax(std::exp(-(zPos * zPos) / 2.0 / (H * H)), std::exp(-zFloor * zFloor / 2.0));
+          g.at(IA, i, j, k) = T(0);
+          g.at(IB, i, j, k) = (zPos < H && zPos > -H) ? T(B0) : T(0);
+          g.at(IC, i, j, k) = T(0);
+        }
+    }
+  }
   return true;
 }
 

@@ -13,7 +13,10 @@ CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neu
          "ot3d_diss_16x12x20_s6", "ot3d_eta_walls_16_s4", "mri3d_diss_12x20x8_s10", "implode3d_visc_16_s6",
          "kh3d_visc_16x8x16_f32_s6", "rt3d_hydro_10x8x24_s8", "rt3d_mhd_10x8x24_s8", "rt3d_mhd_visc_rand_8x10x16_s5",
          # jet inflow boundary
-         "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10"]
+         "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10",
+         # oracle ahead of the CUDA path (next round): stratified shearing box = vertical gravity field + z-stratified
+         # boundaries in the rotating frame
+         "mri3d_strat_8x12x24_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)
