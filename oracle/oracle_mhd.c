@@ -454,6 +454,30 @@ static real_t lim_slope(real_t st, real_t qm, real_t q0, real_t qp) {
   return dsgn * FMIN_(dlim, FABS_(dcen));
 }
 
+#define AT(arr, i, j, k, v) (arr)[(size_t)(i) + (size_t)isz * ((size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(v)))]
+
+/* slope_mhd.h:352-409  slope_type 3: central differences scaled by one positivity-preserving factor taken over the
+ * 27-cell neighbourhood.  nb(di,dj,dk) returns the neighbour value of the variable. */
+static void slope27(const real_t *Q, const orc_params *P, int i, int j, int k, int v, real_t *dx_, real_t *dy_, real_t *dz_) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize;
+  const real_t q0 = AT(Q, i, j, k, v);
+  real_t vmin = ZERO, vmax = ZERO; /* the centre difference (0) takes part in both */
+  for (int di = -1; di <= 1; ++di)
+    for (int dj = -1; dj <= 1; ++dj)
+      for (int dk = -1; dk <= 1; ++dk) {
+        real_t d = AT(Q, i + di, j + dj, k + dk, v) - q0;
+        vmin = FMIN_(vmin, d);
+        vmax = FMAX_(vmax, d);
+      }
+  real_t dfx = HALF * (AT(Q, i + 1, j, k, v) - AT(Q, i - 1, j, k, v));
+  real_t dfy = HALF * (AT(Q, i, j + 1, k, v) - AT(Q, i, j - 1, k, v));
+  real_t dfz = HALF * (AT(Q, i, j, k + 1, v) - AT(Q, i, j, k - 1, v));
+  real_t dff = HALF * (FABS_(dfx) + FABS_(dfy) + FABS_(dfz));
+  real_t slop = ONE;
+  if (dff > ZERO) slop = FMIN_(ONE, FMIN_(FABS_(vmin), FABS_(vmax)) / dff);
+  *dx_ = slop * dfx; *dy_ = slop * dfy; *dz_ = slop * dfz;
+}
+
 /* trace_mhd.h:1853-2248  trace_unsplit_mhd_3d_simpler (dq is consumed: halved in place) */
 void orc_trace_mhd_3d(const orc_params *P, const real_t q[8], const real_t dq_[3][8],
                       const real_t bfNb[6], const real_t dbf[12], const real_t E[3][2][2],
@@ -543,7 +567,6 @@ void orc_trace_mhd_3d(const orc_params *P, const real_t q[8], const real_t dq_[3
 /* ------------------------------------------------------------------------------------------
  * constoprim.h:137-199 constoprim_mhd + :438-463 computePrimitives_MHD_3D / :389-420 (2D)
  * ---------------------------------------------------------------------------------------- */
-#define AT(arr, i, j, k, v) (arr)[(size_t)(i) + (size_t)isz * ((size_t)(j) + (size_t)jsz * ((size_t)(k) + (size_t)ksz * (size_t)(v)))]
 
 void orc_constoprim_mhd(const orc_params *P, const real_t u[8], const real_t bn[3], real_t q[8], real_t dt) {
   q[ID] = FMAX_(u[ID], P->smallr);
@@ -711,6 +734,9 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
           q[v] = AT(Q, i, j, k, v);
           if (P->slope_type == 0) {
             dq[0][v] = dq[1][v] = dq[2][v] = ZERO;
+          } else if (P->slope_type == 3 && !rot) { /* cpu_v3.cpp:197-210; the rotating CPU step of the reference
+                                                      never fills dq for this type (MHDRunGodunov.cpp:2620-2636) */
+            slope27(Q, P, i, j, k, v, &dq[0][v], &dq[1][v], &dq[2][v]);
           } else { /* slope_mhd.h:459-500 */
             dq[0][v] = lim_slope(P->slope_type, AT(Q, i - 1, j, k, v), q[v], AT(Q, i + 1, j, k, v));
             dq[1][v] = lim_slope(P->slope_type, AT(Q, i, j - 1, k, v), q[v], AT(Q, i, j + 1, k, v));
