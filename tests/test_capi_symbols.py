@@ -55,3 +55,51 @@ def test_sass_is_sm100(native):
         pytest.skip("no cuobjdump")
     out = subprocess.run([exe, "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE).stdout.decode()
     assert "sm_100a" in out
+
+
+def test_header_is_plain_c_and_links(native, tmp_path):
+    """the boundary is a C ABI: the public header compiles as C99 (no C++/torch types) and a C caller links
+    against the shared library; without a device the program gets RG_ERR_NO_DEVICE, computes the initial
+    condition on the host and exits cleanly"""
+    import shutil
+    import subprocess
+    from ramsesgpu_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "ramsesgpu_b200.h"
+int main(void) {
+  const char* ini = "[mesh]\nnx=8\nny=6\nnz=4\nboundary_xmin=3\nboundary_xmax=3\nboundary_ymin=3\nboundary_ymax=3\n"
+                    "boundary_zmin=3\nboundary_zmax=3\n[hydro]\nproblem=Orszag-Tang\ngamma0=1.66\n[MHD]\nenable=true\n";
+  rg_layout L;
+  if (rg_initial_condition_host(ini, 0, 0, 1, NULL, 0, &L) != RG_OK) { puts(rg_last_error()); return 2; }
+  size_t n = (size_t)L.isize * L.jsize * L.ksize * L.nvar;
+  double* U = (double*)malloc(n * sizeof(double));
+  if (rg_initial_condition_host(ini, 0, 0, 1, U, n * sizeof(double), &L) != RG_OK) { puts(rg_last_error()); return 3; }
+  printf("layout %d %d %d nvar %d gw %d rho %.17g\n", L.isize, L.jsize, L.ksize, L.nvar, L.ghost_width,
+         U[(size_t)L.ghost_width * L.isize * L.jsize + (size_t)L.ghost_width * L.isize + L.ghost_width]);
+  rg_handle h = NULL;
+  int rc = rg_create(ini, 0, &h);
+  printf("rg_create -> %d (%s)\n", rc, rc ? rg_last_error() : "ok");
+  if (rc == RG_OK) rg_destroy(h);
+  free(U);
+  return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lramsesgpu_b200", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=120)
+    text = out.stdout.decode()
+    assert out.returncode == 0, text
+    assert "layout 14 12 10 nvar 8 gw 3" in text
+    assert "rho 0.21928367177348035" in text          # (1.66f)^2 / 4 pi, SURVEY 8(c)
+    import torch
+    if not torch.cuda.is_available():
+        assert "rg_create -> 2" in text               # RG_ERR_NO_DEVICE, no CPU fallback
