@@ -21,7 +21,11 @@ namespace dev {
 // (error 2^-60 before rounding): results are within ~2 ulp, far inside the 1e-12 parity tolerance.
 __device__ __forceinline__ double rcp(double x) {
   double r;
+#ifdef RG_HOST_EMULATION  // tests/host_emul: the same Newton steps on a 20-bit seed, compiled for the host (CPU test suite)
+  r = rg_host_seed20(1.0 / x);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // MUFU.RCP64H, ~20 bits
+#endif
   double e = fma(-x, r, 1.0);
   e = fma(e, e, e);
   return fma(r, e, r);                                     // cubic step: 2^-20 -> 2^-60 + rounding
@@ -30,7 +34,11 @@ __device__ __forceinline__ double rcp(double x) {
 __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ double rsq(double x) {
   double y;
+#ifdef RG_HOST_EMULATION
+  y = rg_host_seed20(1.0 / sqrt(x));
+#else
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H
+#endif
   const double e = fma(-x * y, y, 1.0);
   return fma(y * e, fma(e, 0.375, 0.5), y);                // cubic step
 }
@@ -49,9 +57,13 @@ __device__ __forceinline__ double mn(double a, double b) { return (a < b) ? a : 
 __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
 // forced select (the compiler otherwise turns long select ladders into divergent branches)
 __device__ __forceinline__ double pick(bool c, double a, double b) {
+#ifdef RG_HOST_EMULATION
+  return c ? a : b;
+#else
   double r;
   asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
   return r;
+#endif
 }
 __device__ __forceinline__ float pick(bool c, float a, float b) { return c ? a : b; }
 __device__ __forceinline__ double ab(double a) { return fabs(a); }

@@ -1,0 +1,171 @@
+"""CPU: the product's point-wise device functions (ramsesgpu_b200/csrc/mhd_device.cuh, hydro_device.cuh) compiled
+for the HOST (tests/host_emul: CUDA intrinsics shimmed, the MUFU seeds emulated as 20-bit values) against the
+oracle on random states.  This is the same SOURCE as the sm_100a kernels run: every solver (HLLD / HLL / LLF,
+2-D HLLD / HLLA / HLLF / LLF with and without the shearing-box terms, hydro approx / HLL / HLLC in FP64 and
+FP32), the two limiter formulations, the branch-free reciprocal / rsqrt / sqrt, cons -> prim.  The GPU tests
+check the same functions on the device (tests/test_gpu_mhd3d.py::test_device_probes_vs_oracle)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, ot3d_ini
+from ramsesgpu_b200.io import ini_override
+
+HERE = os.path.join(ROOT, "tests", "host_emul")
+D = C.POINTER(C.c_double)
+F = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(HERE, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libdevice_math_host.so")
+    csrc = os.path.join(ROOT, "ramsesgpu_b200", "csrc")
+    srcs = [os.path.join(HERE, "device_math_host.cpp"), os.path.join(csrc, "config_map.cpp"), os.path.join(csrc, "params.cpp")]
+    deps = srcs + [os.path.join(HERE, "cuda_host_shim.h"), os.path.join(csrc, "mhd_device.cuh"), os.path.join(csrc, "hydro_device.cuh")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        # -ffp-contract=fast: let the host compiler fuse multiply-adds like nvcc does
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-shared", "-ffp-contract=fast", "-I", csrc, "-I", HERE,
+                               "-I", cuda_inc] + srcs + ["-o", lib])
+    L = C.CDLL(lib)
+    L.emu_riemann_mhd.argtypes = [C.c_char_p, C.c_int, D, D, D]
+    L.emu_compute_emf.argtypes = [C.c_char_p, C.c_int, C.c_int, D, D, D]
+    L.emu_riemann_hydro.argtypes = [C.c_char_p, C.c_int, D, D, D]
+    L.emu_riemann_hydro_f32.argtypes = [C.c_char_p, C.c_int, F, F, F]
+    L.emu_slopes.argtypes = [C.c_double, C.c_int, D, D, D, D, D]
+    L.emu_rcp_rsq.argtypes = [C.c_int, D, D, D, D]
+    L.emu_cons_to_prim_mhd.argtypes = [C.c_char_p, C.c_int, D, D, C.c_double, D]
+    return L
+
+
+def p64(a):
+    return a.ctypes.data_as(D)
+
+
+def states(rng, m):
+    q = np.empty((m, 8))
+    q[:, 0] = rng.uniform(0.5, 2.0, m); q[:, 1] = rng.uniform(0.3, 2.0, m)
+    q[:, 2:5] = rng.uniform(-1, 1, (m, 3)); q[:, 5:8] = rng.uniform(-1, 1, (m, 3))
+    return q
+
+
+@pytest.mark.parametrize("solver", ["hlld", "hll", "llf"])
+def test_mhd_riemann_solvers(emu, oracle64, solver):
+    ini = ot3d_ini((8, 8, 8), hydro={"riemannSolver": solver})
+    p = oracle64.params(ini)
+    rng = np.random.default_rng(11)
+    n = 2048
+    ql, qr = states(rng, n), states(rng, n)
+    qr[: n // 8] = ql[: n // 8] * (1 + 1e-9)            # nearly equal states: the degenerate branches of HLLD
+    ql[n // 8: n // 4, 5] = qr[n // 8: n // 4, 5] = 0.0   # vanishing normal field
+    f = np.zeros((n, 8))
+    emu.emu_riemann_mhd(ini.encode(), n, p64(ql), p64(qr), p64(f))
+    fo = np.array([oracle64.riemann_mhd(p, ql[i], qr[i]) for i in range(n)])
+    assert np.allclose(f, fo, rtol=1e-11, atol=1e-12), np.abs(f - fo).max()
+
+
+@pytest.mark.parametrize("mag,omega", [("hlld", 0.0), ("hlla", 0.0), ("hllf", 0.0), ("llf", 0.0), ("hlld", 0.7)])
+def test_corner_emf_solvers(emu, oracle64, mag, omega):
+    over = {"MHD": {"magRiemannSolver": mag}}
+    if omega:
+        over["MHD"]["omega0"] = omega
+    ini = ot3d_ini((8, 8, 8), **over)
+    p = oracle64.params(ini)
+    rng = np.random.default_rng(13)
+    n = 1024
+    qe = states(rng, 4 * n).reshape(n, 4, 8).copy()
+    xpos = rng.uniform(-0.5, 0.5, n)
+    for d in range(3):
+        e = np.zeros(n)
+        emu.emu_compute_emf(ini.encode(), n, d, p64(qe), p64(xpos), p64(e))
+        eo = np.array([oracle64.compute_emf(p, d, qe[i], xpos[i]) for i in range(n)])
+        assert np.allclose(e, eo, rtol=1e-10, atol=1e-11), (d, np.abs(e - eo).max())
+
+
+@pytest.mark.parametrize("solver", ["approx", "hll", "hllc"])
+def test_hydro_riemann_solvers(emu, oracle64, oracle32, solver):
+    base = str(load_golden("implode3d_16_s8")["ini"])
+    ini = ini_override(base, {"hydro": {"riemannSolver": solver}})
+    rng = np.random.default_rng(17)
+    n = 2048
+    def hs(m):
+        q = np.empty((m, 5))
+        q[:, 0] = rng.uniform(0.1, 2.0, m); q[:, 1] = rng.uniform(0.1, 2.0, m); q[:, 2:5] = rng.uniform(-1.5, 1.5, (m, 3))
+        return q
+    ql, qr = hs(n), hs(n)
+    p = oracle64.params(ini)
+    f = np.zeros((n, 5))
+    emu.emu_riemann_hydro(ini.encode(), n, p64(ql), p64(qr), p64(f))
+    fo = np.array([oracle64.riemann_hydro(p, ql[i], qr[i]) for i in range(n)])
+    assert np.allclose(f, fo, rtol=1e-10, atol=1e-12), np.abs(f - fo).max()
+    # FP32 (BASELINE.json configs[2] runs in float): a few float ulps, like the GPU test tolerance
+    p32 = oracle32.params(ini)
+    l32, r32 = ql.astype(np.float32), qr.astype(np.float32)
+    f32 = np.zeros((n, 5), np.float32)
+    emu.emu_riemann_hydro_f32(ini.encode(), n, l32.ctypes.data_as(F), r32.ctypes.data_as(F), f32.ctypes.data_as(F))
+    fo32 = np.array([oracle32.riemann_hydro(p32, l32[i], r32[i]) for i in range(n)])
+    scale = np.abs(fo32).max(axis=1, keepdims=True) + 1.0
+    assert (np.abs(f32 - fo32) / scale).max() < 2e-5
+
+
+def test_limiters(emu):
+    rng = np.random.default_rng(19)
+    n = 20000
+    qm, q0, qp = rng.normal(size=n), rng.normal(size=n), rng.normal(size=n)
+    q0[:200] = qm[:200]                      # zero one-sided difference
+    qp[200:400] = q0[200:400]
+    qm[400:500] = q0[400:500] = qp[400:500]  # flat
+    for st in (1.0, 2.0):
+        dlft, drgt, dcen = st * (q0 - qm), st * (qp - q0), 0.5 * (qp - qm)
+        ref = np.where(dlft * drgt <= 0, 0.0, np.where(dcen >= 0, 1.0, -1.0) * np.minimum(np.minimum(np.abs(dlft), np.abs(drgt)), np.abs(dcen)))
+        full, half = np.zeros(n), np.zeros(n)
+        emu.emu_slopes(st, n, p64(qm), p64(q0), p64(qp), p64(full), p64(half))
+        assert np.array_equal(full, ref)                                   # reference formulation: bitwise
+        assert np.allclose(2 * half, ref, rtol=4e-16, atol=1e-300)         # FP64-pipe formulation: dcen as (a+b)/2
+
+
+def test_reciprocal_and_rsqrt_two_ulp(emu):
+    rng = np.random.default_rng(23)
+    x = np.concatenate([10.0 ** rng.uniform(-200, 200, 20000), rng.uniform(0.5, 2.0, 20000), [1e-300, 1.0, 4.0]])
+    n = len(x)
+    r, s, q = np.zeros(n), np.zeros(n), np.zeros(n)
+    emu.emu_rcp_rsq(n, p64(x), p64(r), p64(s), p64(q))
+    ulp = np.finfo(np.float64).eps
+    assert (np.abs(r * x - 1.0)).max() < 3 * ulp
+    assert (np.abs(s * s * x - 1.0)).max() < 6 * ulp
+    assert (np.abs(q / np.sqrt(x) - 1.0)).max() < 4 * ulp
+
+
+@pytest.mark.parametrize("over", [{}, {"hydro": {"cIso": 0.3}}, {"MHD": {"omega0": 0.5}}])
+def test_cons_to_prim_mhd(emu, oracle64, over):
+    ini = ot3d_ini((8, 8, 8), **over)
+    p = oracle64.params(ini)
+    rng = np.random.default_rng(29)
+    n = 4096
+    u = np.empty((n, 8))
+    u[:, 0] = rng.uniform(0.2, 2.0, n); u[:, 2:5] = rng.uniform(-1, 1, (n, 3)) * u[:, :1]; u[:, 5:8] = rng.uniform(-1, 1, (n, 3))
+    bn = u[:, 5:8] + rng.uniform(-0.1, 0.1, (n, 3))
+    u[:, 1] = rng.uniform(0.5, 3.0, n) + 0.5 * (u[:, 2:5] ** 2).sum(1) / u[:, 0] + 0.5 * (0.25 * (u[:, 5:8] + bn) ** 2).sum(1)
+    u[:16, 0] = 1e-12                                                   # density floor
+    dt = 0.01
+    q = np.zeros((n, 8))
+    emu.emu_cons_to_prim_mhd(ini.encode(), n, p64(u), p64(np.ascontiguousarray(bn)), dt, p64(q))
+    r = np.maximum(u[:, 0], p.smallr)
+    v = u[:, 2:5] / r[:, None]
+    B = 0.5 * (u[:, 5:8] + bn)
+    if p.cIso > 0:
+        pr = r * p.cIso * p.cIso
+    else:
+        eint = (u[:, 1] - 0.5 * (B ** 2).sum(1)) / r - 0.5 * (v ** 2).sum(1)
+        pr = np.maximum((p.gamma0 - 1.0) * r * eint, r * p.smallp)
+    if p.Omega0 > 0:   # Coriolis predictor, constoprim.h:189-195
+        v = v.copy()
+        dvx, dvy = 2.0 * p.Omega0 * v[:, 1], -0.5 * p.Omega0 * v[:, 0]
+        v[:, 0] += dvx * dt * 0.5; v[:, 1] += dvy * dt * 0.5
+    want = np.column_stack([r, pr, v, B])
+    assert np.allclose(q, want, rtol=1e-12, atol=1e-13), np.abs(q - want).max()
