@@ -1,6 +1,7 @@
 """Opcode counts of tools/microbench/select_variants.cu per kernel (static SASS, no GPU):
    python tools/microbench/select_variants.py"""
 import collections
+import sys
 import os
 import re
 import subprocess
@@ -9,7 +10,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 cubin = os.path.join(tempfile.mkdtemp(), "sel.cubin")
 subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-cubin", "-o", cubin,
-                       os.path.join(HERE, "select_variants.cu")])
+                       (sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "select_variants.cu"))])
 sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", cubin], stdout=subprocess.PIPE).stdout.decode()
 kern, ops = None, collections.OrderedDict()
 for line in sass.splitlines():
