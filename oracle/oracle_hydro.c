@@ -56,6 +56,21 @@ static void constoprim_3d(const orc_params *P, const real_t u[5], real_t q[5], r
   }
 }
 
+/* constoprim.h:43-71 constoprim_2D */
+static void constoprim_2d(const orc_params *P, const real_t u[4], real_t q[4], real_t *c) {
+  q[ID] = FMAX_(u[ID], P->smallr);
+  q[IU] = u[IU] / q[ID]; q[IV] = u[IV] / q[ID];
+  real_t eken = 0.5f * (q[IU] * q[IU] + q[IV] * q[IV]);
+  if (P->cIso > 0) {
+    q[IP] = q[ID] * (P->cIso) * (P->cIso);
+    *c = P->cIso;
+  } else {
+    real_t eint = u[IP] / q[ID] - eken;
+    q[IP] = FMAX_((P->gamma0 - 1.0f) * q[ID] * eint, q[ID] * P->smallp);
+    *c = SQRT_(P->gamma0 * q[IP] / q[ID]);
+  }
+}
+
 /* cmpflx.h:23-49 */
 static void cmpflx3(const orc_params *P, const real_t g[5], real_t f[5]) {
   f[ID] = g[ID] * g[IU];
@@ -203,11 +218,38 @@ static real_t slope1(const orc_params *P, real_t qm, real_t q0, real_t qp) {
   return ZERO; /* other slope types leave dq untouched (zero-initialised stack in practice) */
 }
 
+/* slope.h slope_unsplit_hydro_2d: slope types 1 and 2 share one formula */
+static real_t slope2d(const orc_params *P, real_t qm, real_t q0, real_t qp) {
+  if (P->slope_type == 0) return ZERO;
+  if (P->slope_type == 1 || P->slope_type == 2) {
+    real_t dlft = P->slope_type * (q0 - qm);
+    real_t drgt = P->slope_type * (qp - q0);
+    real_t dcen = HALF * (qp - qm);
+    real_t dsgn = (dcen >= ZERO) ? ONE : -ONE;
+    real_t slop = FMIN_(FABS_(dlft), FABS_(drgt));
+    real_t dlim = slop;
+    if ((dlft * drgt) <= ZERO) dlim = ZERO;
+    return dsgn * FMIN_(dlim, FABS_(dcen));
+  }
+  return ZERO;
+}
+
 /* HydroRunBase.cpp:386-426 (3D and 2D branches) */
 real_t orc_compute_dt_hydro(const orc_params *P, const real_t *U) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
   real_t invDt = 0;
-  if (P->dim != 3) { fprintf(stderr, "oracle: 2D hydro not restated\n"); return 0; }
+  if (P->dim != 3) { /* HydroRunBase.cpp:386-399 */
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        real_t u[4], q[4], c;
+        for (int v = 0; v < 4; ++v) u[v] = AT(U, i, j, 0, v);
+        constoprim_2d(P, u, q, &c);
+        real_t vx = c + FABS_(q[IU]), vy = c + FABS_(q[IV]);
+        invDt = FMAX_(invDt, vx / P->dx + vy / P->dy);
+      }
+    if (P->enableJet) invDt = FMAX_(invDt, (P->ujet + P->cjet) / P->dx);
+    return P->cfl / invDt;
+  }
   for (int k = gw; k < ksz - gw; ++k)
     for (int j = gw; j < jsz - gw; ++j)
       for (int i = gw; i < isz - gw; ++i) {
@@ -225,9 +267,86 @@ real_t orc_compute_dt_hydro(const orc_params *P, const real_t *U) {
 void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear);
 
 /* HydroRunGodunov.cpp:2658-2890 + convertToPrimitives :4210-4250 */
+/* 2D: HydroRunGodunov.cpp:2446-2655 (godunov_unsplit_cpu_v1, TWO_D) + trace.h:332-414; the Riemann solvers are the
+ * 3D ones with w = 0 (riemann<NVAR_2D> performs the same operations without the third velocity) */
+static void hydro2d_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
+  const int isz = P->isize, jsz = P->jsize, ksz = 1, gw = P->ghostWidth;
+  const size_t ncell = (size_t)isz * jsz;
+  const real_t dtdx = dt / P->dx, dtdy = dt / P->dy;
+  real_t *Q = calloc(ncell * 4, sizeof(real_t));
+  real_t *tr = calloc(ncell * 4 * 4, sizeof(real_t));
+  real_t *qm_[2] = {tr, tr + ncell * 4}, *qp_[2] = {tr + ncell * 8, tr + ncell * 12};
+  for (int j = 0; j < jsz; ++j)
+    for (int i = 0; i < isz; ++i) {
+      real_t u[4], q[4], c;
+      for (int v = 0; v < 4; ++v) u[v] = AT(Uold, i, j, 0, v);
+      constoprim_2d(P, u, q, &c);
+      for (int v = 0; v < 4; ++v) AT(Q, i, j, 0, v) = q[v];
+    }
+  for (int j = 1; j < jsz - 1; ++j)
+    for (int i = 1; i < isz - 1; ++i) {
+      real_t q[4], d[2][4];
+      for (int v = 0; v < 4; ++v) {
+        q[v] = AT(Q, i, j, 0, v);
+        d[0][v] = HALF * slope2d(P, AT(Q, i - 1, j, 0, v), q[v], AT(Q, i + 1, j, 0, v));
+        d[1][v] = HALF * slope2d(P, AT(Q, i, j - 1, 0, v), q[v], AT(Q, i, j + 1, 0, v));
+      }
+      real_t r = q[ID], p = q[IP], u = q[IU], v_ = q[IV];
+      const real_t drx = d[0][ID], dpx = d[0][IP], dux = d[0][IU], dvx = d[0][IV];
+      const real_t dry = d[1][ID], dpy = d[1][IP], duy = d[1][IU], dvy = d[1][IV];
+      const real_t gamma = P->gamma0;
+      real_t sr0 = (-u * drx - dux * r) * dtdx + (-v_ * dry - dvy * r) * dtdy;
+      real_t su0 = (-u * dux - dpx / r) * dtdx + (-v_ * duy) * dtdy;
+      real_t sv0 = (-u * dvx) * dtdx + (-v_ * dvy - dpy / r) * dtdy;
+      real_t sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v_ * dpy - dvy * gamma * p) * dtdy;
+      r = r + sr0; u = u + su0; v_ = v_ + sv0; p = p + sp0;
+      real_t gf[3];
+      orc_gravity_at(P, 0, gf);
+      for (int dd = 0; dd < 2; ++dd)
+        for (int side = 0; side < 2; ++side) { /* side 0: qp (low face), 1: qm (high face) */
+          real_t *dst = side ? qm_[dd] : qp_[dd];
+          real_t rr = side ? r + d[dd][ID] : r - d[dd][ID];
+          real_t uu = side ? u + d[dd][IU] : u - d[dd][IU];
+          real_t vv = side ? v_ + d[dd][IV] : v_ - d[dd][IV];
+          real_t pp = side ? p + d[dd][IP] : p - d[dd][IP];
+          rr = FMAX_(P->smallr, rr);
+          pp = FMAX_(P->smallp * rr, pp);
+          if (P->gravityEnabled) { uu += HALF * dt * gf[0]; vv += HALF * dt * gf[1]; }
+          AT(dst, i, j, 0, ID) = rr; AT(dst, i, j, 0, IP) = pp; AT(dst, i, j, 0, IU) = uu; AT(dst, i, j, 0, IV) = vv;
+        }
+    }
+  for (int j = gw; j < jsz - gw + 1; ++j)
+    for (int i = gw; i < isz - gw + 1; ++i) {
+      real_t ql[5], qr[5], fx[5], fy[5];
+      ql[ID] = AT(qm_[0], i - 1, j, 0, ID); ql[IP] = AT(qm_[0], i - 1, j, 0, IP); ql[IU] = AT(qm_[0], i - 1, j, 0, IU); ql[IV] = AT(qm_[0], i - 1, j, 0, IV); ql[IW] = 0;
+      qr[ID] = AT(qp_[0], i, j, 0, ID); qr[IP] = AT(qp_[0], i, j, 0, IP); qr[IU] = AT(qp_[0], i, j, 0, IU); qr[IV] = AT(qp_[0], i, j, 0, IV); qr[IW] = 0;
+      orc_riemann_hydro(P, ql, qr, fx);
+      ql[ID] = AT(qm_[1], i, j - 1, 0, ID); ql[IP] = AT(qm_[1], i, j - 1, 0, IP); ql[IU] = AT(qm_[1], i, j - 1, 0, IV); ql[IV] = AT(qm_[1], i, j - 1, 0, IU); ql[IW] = 0;
+      qr[ID] = AT(qp_[1], i, j, 0, ID); qr[IP] = AT(qp_[1], i, j, 0, IP); qr[IU] = AT(qp_[1], i, j, 0, IV); qr[IV] = AT(qp_[1], i, j, 0, IU); qr[IW] = 0;
+      orc_riemann_hydro(P, ql, qr, fy);
+      const int in_i = i < isz - gw, in_j = j < jsz - gw;
+      static const int sw[4] = {ID, IP, IV, IU};
+      if (i > gw && in_j) for (int v = 0; v < 4; ++v) AT(Unew, i - 1, j, 0, v) -= fx[v] * dtdx;
+      if (in_i && in_j) for (int v = 0; v < 4; ++v) AT(Unew, i, j, 0, v) += fx[v] * dtdx;
+      if (in_i && j > gw) for (int v = 0; v < 4; ++v) AT(Unew, i, j - 1, 0, v) -= fy[sw[v]] * dtdy;
+      if (in_i && in_j) for (int v = 0; v < 4; ++v) AT(Unew, i, j, 0, v) += fy[sw[v]] * dtdy;
+    }
+  if (P->gravityEnabled) { /* HydroRunBase.cpp:1946-1958 */
+    real_t gf[3];
+    orc_gravity_at(P, 0, gf);
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        real_t rhoOld = AT(Uold, i, j, 0, ID), rhoNew = AT(Unew, i, j, 0, ID);
+        AT(Unew, i, j, 0, IU) += HALF * dt * gf[0] * (rhoOld + rhoNew);
+        AT(Unew, i, j, 0, IV) += HALF * dt * gf[1] * (rhoOld + rhoNew);
+      }
+  }
+  free(Q); free(tr);
+}
+
 void orc_hydro_step_v1(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
-  if (P->dim != 3) { fprintf(stderr, "oracle: 2D hydro not restated\n"); return; }
+  if (P->dim != 3) { hydro2d_step_v1(P, Uold, Unew, dt); return; }
   const size_t ncell = (size_t)isz * jsz * ksz;
   const real_t dtdx = dt / P->dx, dtdy = dt / P->dy, dtdz = dt / P->dz;
   real_t *Q = calloc(ncell * 5, sizeof(real_t));

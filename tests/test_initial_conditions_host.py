@@ -11,10 +11,12 @@ import pytest
 from conftest import GOLDEN, load_golden
 from ramsesgpu_b200.io import l2_relative
 
-ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if "_history_" not in f)
+NOT_BUILT = {"blast2d_hllc_32_s8"}   # initial conditions the product does not implement (the oracle starts from the golden state)
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+             if "_history_" not in f and os.path.basename(f)[:-4] not in NOT_BUILT)
 NEW_PROBLEMS = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
                 "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5",
-                "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10"]
+                "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10", "blast2d_hllc_32_s8"]
 # (the jet problems need the oracle's own boundary patch from step 0: they are in tests/test_oracle_golden.py)
 
 
@@ -66,4 +68,5 @@ def test_oracle_step_on_further_problems(oracle64, name):
     Uf, t, dts = oracle64.run_steps(p, U, int(g["steps"]))
     final = Uf[:, 0, gw:-gw, gw:-gw] if p.dim == 2 else Uf[:, gw:-gw, gw:-gw, gw:-gw]
     assert np.array_equal(final, g["final"]), max(l2_relative(a, b) for a, b in zip(g["final"], final))
-    assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])
+    if g["total_time"] == g["total_time"]:   # the hydro driver of the reference does not print it
+        assert abs(t - g["total_time"]) <= 1e-11 * abs(g["total_time"])
