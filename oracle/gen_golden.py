@@ -133,6 +133,7 @@ if __name__ == "__main__":
         "implode2d_32_s10": ("implode2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 10, "f64"),
         "jet2d_hydro_24x32_s10": ("jet2d_cpu.ini", {"mesh": {"nx": 24, "ny": 32}, "jet": {"ijet": 4, "offsetJet": 10}}, 10, "f64"),
         "blast2d_hllc_32_s8": ("blast2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 8, "f64"),
+        "blast3d_hllc_16x12x20_s8": ("blast2d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 20}, "blast": {"center_z": 0.4}}, 8, "f64"),
         "khmhd2d_24x32_s8": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 24, "ny": 32}}, 8, "f64"),
         "khmhd3d_12x16x8_s5": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8}, "MHD": {"implementationVersion": 4}}, 5, "f64"),
         "shearwave3d_16x12x8_s10": ("mhd_shearWave_3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 8}}, 10, "f64"),

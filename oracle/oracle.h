@@ -82,6 +82,7 @@ typedef struct orc_params {
      gravityMode 0 = none, 1 = uniform static field (Rayleigh-Taylor), 2 = vertical field of the MRI problem */
   int gravityMode, mri_smoothGravity, mri_bcFloor;
   real_t mri_zFloor;
+  real_t blast[8]; /* [blast] radius, center_x/y/z, density_in/out, pressure_in/out (HydroRunBase.cpp:5570-5577) */
 } orc_params;
 /* gravity field of cell plane k (reference h_gravity(i,j,k,0..2)) */
 void orc_gravity_at(const orc_params *p, int k, real_t g[3]);

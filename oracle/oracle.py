@@ -45,6 +45,7 @@ def _params_struct(real):
             ("enableJet", C.c_int), ("ijet", C.c_int), ("offsetJet", C.c_int),
             ("djet", real), ("ujet", real), ("pjet", real), ("cjet", real), ("jet_bx", real), ("jet_by", real), ("jet_bz", real),
             ("gravityMode", C.c_int), ("mri_smoothGravity", C.c_int), ("mri_bcFloor", C.c_int), ("mri_zFloor", real),
+            ("blast", real * 8),
         ]
     return OrcParams
 

@@ -258,6 +258,14 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->mri_smoothGravity = get_bool(&c, "MRI", "smoothGravity", 0);
   p->mri_zFloor = get_float(&c, "MRI", "zFloor", 5.0f);
   p->mri_bcFloor = get_bool(&c, "MRI", "floor", 0);
+  p->blast[0] = get_float(&c, "blast", "radius", (float)(0.25 * (p->xMax - p->xMin)));
+  p->blast[1] = get_float(&c, "blast", "center_x", (float)((p->xMax + p->xMin) / 2));
+  p->blast[2] = get_float(&c, "blast", "center_y", (float)((p->yMax + p->yMin) / 2));
+  p->blast[3] = get_float(&c, "blast", "center_z", (float)((p->zMax + p->zMin) / 2));
+  p->blast[4] = get_float(&c, "blast", "density_in", 1.0f);
+  p->blast[5] = get_float(&c, "blast", "density_out", 1.0f);
+  p->blast[6] = get_float(&c, "blast", "pressure_in", 10.0f);
+  p->blast[7] = get_float(&c, "blast", "pressure_out", 0.1f);
   p->gravityMode = 0;
   if (p->gravityEnabled) {
     if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityMode = 1;

@@ -302,6 +302,31 @@ static int init_jet(const orc_params *P, real_t *U) {
   return 0;
 }
 
+/* spherical blast wave (hydro 2D/3D), HydroRunBase.cpp:5551-5680; the ini defaults go through getFloat (float) */
+static int init_blast(const orc_params *P, real_t *U, const real_t par[8]) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  real_t radius = par[0];
+  const real_t cx = par[1], cy = par[2], cz = par[3], dIn = par[4], dOut = par[5], pIn = par[6], pOut = par[7];
+  radius *= radius;
+  for (int k = (P->dim == 3 ? gw : 0); k < (P->dim == 3 ? ksz - gw : 1); ++k) {
+    real_t zPos = P->zMin + P->dz / 2 + (k - gw) * P->dz;
+    for (int j = gw; j < jsz - gw; ++j) {
+      real_t yPos = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+      for (int i = gw; i < isz - gw; ++i) {
+        real_t xPos = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+        real_t d2 = (xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy);
+        if (P->dim == 3) d2 = (xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy) + (zPos - cz) * (zPos - cz);
+        int in = d2 < radius;
+        AT(U, i, j, k, ID) = in ? dIn : dOut;
+        AT(U, i, j, k, IP) = (in ? pIn : pOut) / (P->gamma0 - 1.0f);
+      }
+    }
+  }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
 /* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
 int orc_init_problem(const orc_params *P, real_t *U) {
   const char *n = P->problem;
@@ -312,6 +337,7 @@ int orc_init_problem(const orc_params *P, real_t *U) {
     if (!strcmp(n, "jet") || !strcmp(n, "Jet")) return init_jet(P, U);
   } else {
     if (!strcmp(n, "jet")) return init_jet(P, U);
+    if (!strcmp(n, "blast")) return init_blast(P, U, P->blast);
     if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
     if (!strcmp(n, "implode")) { init_implode(P, U); return 0; }
     if (!strcmp(n, "Kelvin-Helmholtz")) return init_kelvin_helmholtz(P, U);

@@ -647,6 +647,38 @@ bool initJet(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, st
   return true;
 }
 
+// spherical blast wave, 2D and 3D hydro; reference HydroRunBase.cpp:5551-5680 (inner cells, defaults passed through
+// getFloat, i.e. rounded to float)
+template <typename T>
+bool initBlast(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled) { if (msg) *msg = "blast is a hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  T radius = cfg.getFloat("blast", "radius", (float)(0.25 * (kp.xMax - kp.xMin)));
+  const T cx = cfg.getFloat("blast", "center_x", (float)((kp.xMax + kp.xMin) / 2));
+  const T cy = cfg.getFloat("blast", "center_y", (float)((kp.yMax + kp.yMin) / 2));
+  const T cz = cfg.getFloat("blast", "center_z", (float)((kp.zMax + kp.zMin) / 2));
+  const T dIn = cfg.getFloat("blast", "density_in", 1.0f), dOut = cfg.getFloat("blast", "density_out", 1.0f);
+  const T pIn = cfg.getFloat("blast", "pressure_in", 10.0f), pOut = cfg.getFloat("blast", "pressure_out", 0.1f);
+  radius *= radius;
+  for (int k = (rp.dim == 3 ? gw : 0); k < (rp.dim == 3 ? kp.ksize - gw : 1); ++k) {
+    const T zPos = kp.zMin + kp.dz / 2 + (k + kp.kglob0 - gw) * kp.dz;
+    for (int j = gw; j < kp.jsize - gw; ++j) {
+      const T yPos = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+        T d2 = (xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy);
+        if (rp.dim == 3) d2 = (xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy) + (zPos - cz) * (zPos - cz);
+        const bool in = d2 < radius;
+        g.at(ID, i, j, k) = in ? dIn : dOut;
+        g.at(IP, i, j, k) = (in ? pIn : pOut) / (kp.gamma0 - 1.0f);
+      }
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -672,6 +704,7 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Kelvin-Helmholtz") return initKelvinHelmholtz(cfg, rp, kp, U, message);
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
     if (problem == "jet") return initJet(cfg, rp, kp, U, message);
+    if (problem == "blast") return initBlast(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

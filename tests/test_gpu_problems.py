@@ -14,6 +14,8 @@ CASES = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "b
          "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10",
          # jet inflow boundary patch + dt limit (hydro 3D, MHD 3D, MHD 2D)
          "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10"]
+# blast3d_hllc_16x12x20_s8 (spherical blast, 3D hydro HLLC): initial condition bitwise on the host and oracle pinned
+# (CPU suite); its GPU run joins this list once it has been run on a B200 (the round's GPU budget was spent).
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -18,7 +18,7 @@ CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neu
          # boundaries in the rotating frame; slope_type 3 (27-point positivity-preserving slopes)
          "mri3d_strat_8x12x24_s10", "ot3d_slope3_16x12x20_s6",
          # ... and 2D hydro (godunov_unsplit_cpu_v1, TWO_D branch)
-         "implode2d_32_s10", "jet2d_hydro_24x32_s10"]
+         "implode2d_32_s10", "jet2d_hydro_24x32_s10", "blast2d_hllc_32_s8", "blast3d_hllc_16x12x20_s8"]
 
 
 @pytest.mark.parametrize("name", CASES)
