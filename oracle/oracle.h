@@ -127,6 +127,9 @@ void orc_history_mhd3d(const orc_params *p, const real_t *U, double out[8]);
 void orc_set_skip_dissipative(int on);
 void orc_dissipative_stage(const orc_params *p, real_t *Unew, real_t dt, int stage);
 
+/* test hook: the 18 trace arrays (qm[3], qp[3], qEdge[4][3]) of one 3D MHD step from a ghost-filled state */
+void orc_mhd3d_trace_arrays(const orc_params *p, const real_t *Uold, real_t dt, real_t *out);
+
 int orc_sizeof_real(void);
 
 #ifdef __cplusplus

@@ -80,6 +80,7 @@ class Oracle:
         L.orc_make_all_boundaries_shear.argtypes = [P, RP, R, R]; L.orc_make_all_boundaries_shear.restype = None
         L.orc_set_skip_dissipative.argtypes = [C.c_int]; L.orc_set_skip_dissipative.restype = None
         L.orc_dissipative_stage.argtypes = [P, RP, R, C.c_int]; L.orc_dissipative_stage.restype = None
+        L.orc_mhd3d_trace_arrays.argtypes = [P, RP, R, RP]; L.orc_mhd3d_trace_arrays.restype = None
         L.orc_history_mhd3d.argtypes = [P, RP, C.POINTER(C.c_double)]; L.orc_history_mhd3d.restype = None
 
     # -- helpers ---------------------------------------------------------------------------
@@ -138,6 +139,12 @@ class Oracle:
 
     def dissipative_stage(self, p, U, dt, stage):
         self.lib.orc_dissipative_stage(C.byref(p), self._p(U), dt, stage)
+
+    def mhd3d_trace_arrays(self, p, U, dt):
+        """qm[3], qp[3], qEdge[4][3] of one step: array [18, 8, k, j, i] (see orc_mhd3d_trace_arrays)"""
+        out = np.zeros((18, 8, p.ksize, p.jsize, p.isize), dtype=self.dtype)
+        self.lib.orc_mhd3d_trace_arrays(C.byref(p), self._p(U), dt, self._p(out))
+        return out
 
     HISTORY_NAMES = ("mass", "maxwell", "reynolds", "magp", "mean_Bx", "mean_By", "mean_Bz", "divB")
 

@@ -632,6 +632,9 @@ real_t orc_compute_dt_mhd(const orc_params *P, const real_t *U) {
  * 3D MHD unsplit step, implementation 3/4 on the CPU: mhd_godunov_unsplit_cpu_v3.cpp:11-715
  * (the part of godunov_unsplit_cpu after boundaries + copy; Omega0 == 0 only)
  * ---------------------------------------------------------------------------------------- */
+/* test hook: when set, mhd3d_core copies its 18 trace arrays (qm[3], qp[3], qEdge[4][3]; each [var][k][j][i]) here */
+static real_t *g_trace_dump = NULL;
+
 static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt, real_t totalTime, int rot) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
   const int nx = P->nx, ny = P->ny;
@@ -778,6 +781,8 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
           }
         }
       }
+
+  if (g_trace_dump) memcpy(g_trace_dump, tr, ncell * 8 * 18 * sizeof(real_t));
 
   /* fluxes + emf + hydro update: cpu_v3.cpp:372-583 ; rotating frame: MHDRunGodunov.cpp:2786-3100 */
   for (int k = gw; k < ksz - gw + 1; ++k)
@@ -953,6 +958,17 @@ static void mhd3d_core(const orc_params *P, const real_t *Uold, real_t *Unew, re
 }
 
 void orc_dissipative_3d(const orc_params *P, real_t *Unew, real_t dt, real_t totalTime, int shear);
+
+/* the trace arrays of one step from Uold (ghosts filled by the caller): out[18][8][ksize][jsize][isize] in the order
+ * qm_x, qm_y, qm_z, qp_x, qp_y, qp_z, then qEdge[e][d] at 6 + 3 e + d (e: RT, RB, LT, LB; d: edge direction x, y, z) */
+void orc_mhd3d_trace_arrays(const orc_params *P, const real_t *Uold, real_t dt, real_t *out) {
+  real_t *tmp = malloc((size_t)orc_array_len(P) * sizeof(real_t));
+  memcpy(tmp, Uold, (size_t)orc_array_len(P) * sizeof(real_t));
+  g_trace_dump = out;
+  mhd3d_core(P, Uold, tmp, dt, ZERO, P->Omega0 > 0);
+  g_trace_dump = NULL;
+  free(tmp);
+}
 
 void orc_mhd3d_step_v3(const orc_params *P, const real_t *Uold, real_t *Unew, real_t dt) {
   mhd3d_core(P, Uold, Unew, dt, ZERO, 0);

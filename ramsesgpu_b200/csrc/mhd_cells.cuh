@@ -1,0 +1,258 @@
+// Per-cell building blocks of the 3D MHD step, generic in the way the arrays are reached: Q(v,i,j,k) primitives,
+// U(v,i,j,k) conservative state (face fields), EL(c,i,j,k) edge electric fields, W(c,i,j,k) the traced state.
+// The kernels of kernels_mhd3d.cu instantiate them on global-memory views and on shared-memory tiles; the CPU test
+// suite instantiates the same source on host arrays (tests/host_emul) and compares it with the oracle.
+#pragma once
+#include "kernels.h"
+#include "mhd_device.cuh"
+
+namespace rg {
+
+namespace {
+
+// W component ids
+enum {
+  W_R = 0, W_P, W_U, W_V, W_W, W_A, W_B, W_C,            // cell centred, advanced by dt/2
+  W_AL, W_BL, W_CL,                                      // LOW-face fields, advanced by dt/2
+  W_DRX, W_DPX, W_DUX, W_DVX, W_DWX, W_DBX, W_DCX,       // half slopes along x
+  W_DRY, W_DPY, W_DUY, W_DVY, W_DWY, W_DAY, W_DCY,       // half slopes along y
+  W_DRZ, W_DPZ, W_DUZ, W_DVZ, W_DWZ, W_DAZ, W_DBZ,       // half slopes along z
+  W_DALY, W_DALZ, W_DBLX, W_DBLZ, W_DCLX, W_DCLY         // half slopes of the low-face fields
+};
+// The HIGH-face field of a cell and its slopes are, bit for bit, the LOW-face values of the +1
+// neighbour (same face, same edge electric fields, same limiter inputs), so consumers read them
+// there and W carries 38 components instead of 47.
+static_assert(W_DCLY + 1 == NW_MHD, "W layout");
+
+// ------------------------------------------------------------------------------------------------
+// edge-centred electric field E = v x B at the LOW edges of a cell (reference cpu_v3.cpp:36-101)
+// ------------------------------------------------------------------------------------------------
+// edge electric fields of one cell (low edges); QV / UV / ELV as in trace_cell
+template <bool FAST, typename T, typename QV, typename UV, typename ELV>
+__device__ __forceinline__ void elec_cell(const KParams<T>& P, const QV& Q, const UV& U, const ELV& EL, int i, int j,
+                                          int k) {
+  const T h = T(0.5), f = T(0.25);
+  const T u00 = Q(IU, i, j, k), v00 = Q(IV, i, j, k), w00 = Q(IW, i, j, k);
+  const T A = U(IA, i, j, k), B = U(IB, i, j, k), C = U(IC, i, j, k);
+  {  // Ex: average over (j-1..j, k-1..k)
+    const T v = f * (Q(IV, i, j - 1, k - 1) + Q(IV, i, j - 1, k) + Q(IV, i, j, k - 1) + v00);
+    const T w = f * (Q(IW, i, j - 1, k - 1) + Q(IW, i, j - 1, k) + Q(IW, i, j, k - 1) + w00);
+    const T Bm = h * (U(IB, i, j, k - 1) + B), Cm = h * (U(IC, i, j - 1, k) + C);
+    T ex = v * Cm - w * Bm;
+    if (!FAST && P.Omega0 > T(0)) {  // rotating frame: advection by the background shear, MHDRunGodunov.cpp:2474-2478
+      const T xPos = P.xMin + P.dx * h + (i - P.gw) * P.dx;
+      ex += T(-1.5) * P.Omega0 * xPos * Cm;
+    }
+    EL(0, i, j, k) = ex;
+  }
+  {  // Ey: average over (i-1..i, k-1..k)
+    const T u = f * (Q(IU, i - 1, j, k - 1) + Q(IU, i - 1, j, k) + Q(IU, i, j, k - 1) + u00);
+    const T w = f * (Q(IW, i - 1, j, k - 1) + Q(IW, i - 1, j, k) + Q(IW, i, j, k - 1) + w00);
+    const T Am = h * (U(IA, i, j, k - 1) + A), Cm = h * (U(IC, i - 1, j, k) + C);
+    EL(1, i, j, k) = w * Am - u * Cm;
+  }
+  {  // Ez: average over (i-1..i, j-1..j)
+    const T u = f * (Q(IU, i - 1, j - 1, k) + Q(IU, i - 1, j, k) + Q(IU, i, j - 1, k) + u00);
+    const T v = f * (Q(IV, i - 1, j - 1, k) + Q(IV, i - 1, j, k) + Q(IV, i, j - 1, k) + v00);
+    const T Am = h * (U(IA, i, j - 1, k) + A), Bm = h * (U(IB, i - 1, j, k) + B);
+    T ez = u * Bm - v * Am;
+    if (!FAST && P.Omega0 > T(0)) {  // MHDRunGodunov.cpp:2517-2521 (shear at the x face)
+      const T xFace = P.xMin + P.dx * h + (i - P.gw) * P.dx - P.dx * h;
+      ez -= T(-1.5) * P.Omega0 * xFace * Am;
+    }
+    EL(2, i, j, k) = ez;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// slopes + face-B slopes + half-step trace of one cell -> W (reference cpu_v3.cpp:36-361, slope_mhd.h, trace_mhd.h)
+// ------------------------------------------------------------------------------------------------
+// trace of one cell: QV(v,i,j,k) primitives, UV(v,i,j,k) conservative state (face fields), ELV(c,i,j,k)
+// edge electric fields, WV(c,i,j,k) the traced state (written).  Used by k_trace (global arrays) and by
+// the fused prim+elec+trace kernel (shared-memory tiles).
+template <bool FAST, typename T, typename QV, typename UV, typename ELV, typename WV>
+__device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, const UV& U, const ELV& EL, const WV& W,
+                                           int i, int j, int k, T dt) {
+  const int gw = P.gw;
+  const T h = T(0.5);
+  const T hst = h * P.slope_type;  // slope_type 0 gives zero slopes through hst = 0
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  // The work is arranged direction by direction (slopes of one direction -> stored -> their share of
+  // the half-step source terms accumulated) so that few values are live at any time.
+
+  // face fields: transverse HALF slopes (slope type capped at 2, slope_mhd.h:636), induction by the 12
+  // edge electric fields of the cell (trace_mhd.h:2006-2011)
+  const T hxst = h * dev::mn(P.slope_type, T(2));
+  const T AL = U(IA, i, j, k), BL = U(IB, i, j, k), CL = U(IC, i, j, k);
+  const T dAx = h * (U(IA, i + 1, j, k) - AL), dBy = h * (U(IB, i, j + 1, k) - BL), dCz = h * (U(IC, i, j, k + 1) - CL);
+  W(W_DALY, i, j, k) = dev::half_slope(hxst, U(IA, i, j - 1, k), AL, U(IA, i, j + 1, k));
+  W(W_DALZ, i, j, k) = dev::half_slope(hxst, U(IA, i, j, k - 1), AL, U(IA, i, j, k + 1));
+  W(W_DBLX, i, j, k) = dev::half_slope(hxst, U(IB, i - 1, j, k), BL, U(IB, i + 1, j, k));
+  W(W_DBLZ, i, j, k) = dev::half_slope(hxst, U(IB, i, j, k - 1), BL, U(IB, i, j, k + 1));
+  W(W_DCLX, i, j, k) = dev::half_slope(hxst, U(IC, i - 1, j, k), CL, U(IC, i + 1, j, k));
+  W(W_DCLY, i, j, k) = dev::half_slope(hxst, U(IC, i, j - 1, k), CL, U(IC, i, j + 1, k));
+  {
+    const T ELL = EL(0, i, j, k), ELR = EL(0, i, j, k + 1), ERL = EL(0, i, j + 1, k);
+    const T FLL = EL(1, i, j, k), FLR = EL(1, i, j, k + 1), FRL = EL(1, i + 1, j, k);
+    const T GLL = EL(2, i, j, k), GLR = EL(2, i, j + 1, k), GRL = EL(2, i + 1, j, k);
+    W(W_AL, i, j, k) = AL + ((GLR - GLL) * dtdy * h - (FLR - FLL) * dtdz * h);
+    W(W_BL, i, j, k) = BL + (-(GRL - GLL) * dtdx * h + (ELR - ELL) * dtdz * h);
+    W(W_CL, i, j, k) = CL + ((FRL - FLL) * dtdx * h - (ERL - ELL) * dtdy * h);
+  }
+
+  // cell-centred state; half-step source terms (trace_mhd.h:1985-2011) accumulated per direction
+  const T r = Q(ID, i, j, k), p = Q(IP, i, j, k), u = Q(IU, i, j, k), v = Q(IV, i, j, k), w = Q(IW, i, j, k);
+  const T A = Q(IA, i, j, k), B = Q(IB, i, j, k), C = Q(IC, i, j, k);
+  const T ir = dev::rcp(r);
+  const T gp = P.gamma0 * p;
+  T sr0, su0, sv0, sw0, sp0, sA0, sB0, sC0;
+  {  // x
+    const T drx = dev::half_slope(hst, Q(ID, i - 1, j, k), r, Q(ID, i + 1, j, k));
+    const T dpx = dev::half_slope(hst, Q(IP, i - 1, j, k), p, Q(IP, i + 1, j, k));
+    const T dux = dev::half_slope(hst, Q(IU, i - 1, j, k), u, Q(IU, i + 1, j, k));
+    const T dvx = dev::half_slope(hst, Q(IV, i - 1, j, k), v, Q(IV, i + 1, j, k));
+    const T dwx = dev::half_slope(hst, Q(IW, i - 1, j, k), w, Q(IW, i + 1, j, k));
+    const T dBx = dev::half_slope(hst, Q(IB, i - 1, j, k), B, Q(IB, i + 1, j, k));
+    const T dCx = dev::half_slope(hst, Q(IC, i - 1, j, k), C, Q(IC, i + 1, j, k));
+    W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
+    W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
+    sr0 = (-u * drx - dux * r) * dtdx;
+    su0 = (-u * dux - (dpx + B * dBx + C * dCx) * ir) * dtdx;
+    sv0 = (-u * dvx + A * dBx * ir) * dtdx;
+    sw0 = (-u * dwx + A * dCx * ir) * dtdx;
+    sp0 = (-u * dpx - dux * gp) * dtdx;
+    sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx;
+    sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx;
+  }
+  T shr = T(0), shu = T(0), shv = T(0), shw = T(0), shp = T(0), shA = T(0), shC = T(0);  // shearing box only
+  {  // y
+    const T dry = dev::half_slope(hst, Q(ID, i, j - 1, k), r, Q(ID, i, j + 1, k));
+    const T dpy = dev::half_slope(hst, Q(IP, i, j - 1, k), p, Q(IP, i, j + 1, k));
+    const T duy = dev::half_slope(hst, Q(IU, i, j - 1, k), u, Q(IU, i, j + 1, k));
+    const T dvy = dev::half_slope(hst, Q(IV, i, j - 1, k), v, Q(IV, i, j + 1, k));
+    const T dwy = dev::half_slope(hst, Q(IW, i, j - 1, k), w, Q(IW, i, j + 1, k));
+    const T dAy = dev::half_slope(hst, Q(IA, i, j - 1, k), A, Q(IA, i, j + 1, k));
+    const T dCy = dev::half_slope(hst, Q(IC, i, j - 1, k), C, Q(IC, i, j + 1, k));
+    W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
+    W(W_DWY, i, j, k) = dwy; W(W_DAY, i, j, k) = dAy; W(W_DCY, i, j, k) = dCy;
+    sr0 += (-v * dry - dvy * r) * dtdy;
+    su0 += (-v * duy + B * dAy * ir) * dtdy;
+    sv0 += (-v * dvy - (dpy + A * dAy + C * dCy) * ir) * dtdy;
+    sw0 += (-v * dwy + B * dCy * ir) * dtdy;
+    sp0 += (-v * dpy - dvy * gp) * dtdy;
+    sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy;
+    sC0 += (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
+    if (!FAST && P.Omega0 > T(0)) {  // shearing-box terms, trace_mhd.h:1993-2003 (applied below)
+      const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
+      const T shear = T(-1.5) * P.Omega0 * xPos;
+      shr = shear * dry * dtdy; shu = shear * duy * dtdy; shv = shear * dvy * dtdy; shw = shear * dwy * dtdy;
+      shp = shear * dpy * dtdy; shA = shear * dAy * dtdy; shC = shear * dCy * dtdy;
+    }
+  }
+  {  // z
+    const T drz = dev::half_slope(hst, Q(ID, i, j, k - 1), r, Q(ID, i, j, k + 1));
+    const T dpz = dev::half_slope(hst, Q(IP, i, j, k - 1), p, Q(IP, i, j, k + 1));
+    const T duz = dev::half_slope(hst, Q(IU, i, j, k - 1), u, Q(IU, i, j, k + 1));
+    const T dvz = dev::half_slope(hst, Q(IV, i, j, k - 1), v, Q(IV, i, j, k + 1));
+    const T dwz = dev::half_slope(hst, Q(IW, i, j, k - 1), w, Q(IW, i, j, k + 1));
+    const T dAz = dev::half_slope(hst, Q(IA, i, j, k - 1), A, Q(IA, i, j, k + 1));
+    const T dBz = dev::half_slope(hst, Q(IB, i, j, k - 1), B, Q(IB, i, j, k + 1));
+    W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
+    W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
+    sr0 += (-w * drz - dwz * r) * dtdz;
+    su0 += (-w * duz + C * dAz * ir) * dtdz;
+    sv0 += (-w * dvz + C * dBz * ir) * dtdz;
+    sw0 += (-w * dwz - (dpz + A * dAz + B * dBz) * ir) * dtdz;
+    sp0 += (-w * dpz - dwz * gp) * dtdz;
+    sA0 += (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
+    sB0 += (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
+    if (!FAST && P.Omega0 > T(0)) {
+      const T xPos = P.xMin + P.dx * h + (i - gw) * P.dx;
+      const T shear = T(-1.5) * P.Omega0 * xPos;
+      sr0 -= shr; su0 -= shu; sv0 -= shv; sw0 -= shw; sp0 -= shp; sA0 -= shA;
+      sB0 += (shear * dAx - T(1.5) * P.Omega0 * A * P.dx) * dtdx + shear * dBz * dtdz;
+      sC0 -= shC;
+    }
+  }
+  if (P.gravity) {  // gravity predictor on every traced velocity of the cell (reference cpu_v3.cpp:277-332):
+    const T hdt = h * dt;  // face / edge states are centre +/- slopes, so it goes into the centre value
+    su0 += hdt * P.gx; sv0 += hdt * P.gy; sw0 += hdt * P.gz;
+  }
+  W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
+  W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
+  W(W_A, i, j, k) = A + sA0;  W(W_B, i, j, k) = B + sB0;  W(W_C, i, j, k) = C + sC0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// face state = W cell-centred value +/- half slope along the normal, floors on rho and p (trace_mhd.h:2032-2102)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DIR, typename WV>
+__device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const WV& W, int i, int j, int k, T sgn) {
+  // sgn = +1 : state at the HIGH face of cell (qm), -1 : at the LOW face (qp)
+  constexpr int S = (DIR == 0) ? W_DRX : (DIR == 1) ? W_DRY : W_DRZ;  // first slope component
+  dev::State<T> s;
+  s.r = dev::mx(P.smallr, W(W_R, i, j, k) + sgn * W(S + 0, i, j, k));
+  s.p = dev::mx(P.smallp, W(W_P, i, j, k) + sgn * W(S + 1, i, j, k));
+  const T u = W(W_U, i, j, k) + sgn * W(S + 2, i, j, k);
+  const T v = W(W_V, i, j, k) + sgn * W(S + 3, i, j, k);
+  const T w = W(W_W, i, j, k) + sgn * W(S + 4, i, j, k);
+  if (DIR == 0) {
+    s.u = u; s.v = v; s.w = w;
+    s.a = W(W_AL, (sgn > T(0)) ? i + 1 : i, j, k);
+    s.b = W(W_B, i, j, k) + sgn * W(W_DBX, i, j, k);
+    s.c = W(W_C, i, j, k) + sgn * W(W_DCX, i, j, k);
+  } else if (DIR == 1) {  // swap (u,v) and (a,b)
+    s.u = v; s.v = u; s.w = w;
+    s.a = W(W_BL, i, (sgn > T(0)) ? j + 1 : j, k);
+    s.b = W(W_A, i, j, k) + sgn * W(W_DAY, i, j, k);
+    s.c = W(W_C, i, j, k) + sgn * W(W_DCY, i, j, k);
+  } else {  // swap (u,w) and (a,c)
+    s.u = w; s.v = v; s.w = u;
+    s.a = W(W_CL, i, j, (sgn > T(0)) ? k + 1 : k);
+    s.b = W(W_B, i, j, k) + sgn * W(W_DBZ, i, j, k);
+    s.c = W(W_A, i, j, k) + sgn * W(W_DAZ, i, j, k);
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge states for the corner emfs (trace_mhd.h:2104-2246)
+// ------------------------------------------------------------------------------------------------
+// edge state of cell (i,j,k) for edge direction EDIR, signs (s1, s2) along the two transverse
+// directions (d1,d2) = (x,y) for Z, (x,z) for Y, (y,z) for X; returned in the EDGE frame
+//   Z: u<-U v<-V w<-W a<-A b<-B c<-C ; Y: u<-W v<-U w<-V a<-C b<-A c<-B ; X: u<-V v<-W w<-U a<-B b<-C c<-A
+template <typename T, int EDIR, typename WV>
+__device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const WV& W, int i, int j, int k, T s1,
+                                                     T s2) {
+  constexpr int S1 = (EDIR == 0) ? W_DRY : W_DRX;  // slopes along d1
+  constexpr int S2 = (EDIR == 2) ? W_DRY : W_DRZ;  // slopes along d2
+  const T r = dev::mx(P.smallr, W(W_R, i, j, k) + (s1 * W(S1 + 0, i, j, k) + s2 * W(S2 + 0, i, j, k)));
+  const T p = dev::mx(P.smallp, W(W_P, i, j, k) + (s1 * W(S1 + 1, i, j, k) + s2 * W(S2 + 1, i, j, k)));
+  const T U = W(W_U, i, j, k) + (s1 * W(S1 + 2, i, j, k) + s2 * W(S2 + 2, i, j, k));
+  const T V = W(W_V, i, j, k) + (s1 * W(S1 + 3, i, j, k) + s2 * W(S2 + 3, i, j, k));
+  const T Wv = W(W_W, i, j, k) + (s1 * W(S1 + 4, i, j, k) + s2 * W(S2 + 4, i, j, k));
+  T A, B, C;
+  if (EDIR == 2) {  // (x,y): A from the x-face on side s1 with its y slope, B from the y-face on side s2 with its x slope
+    { const int ia = (s1 > T(0)) ? i + 1 : i; A = W(W_AL, ia, j, k) + s2 * W(W_DALY, ia, j, k); }
+    { const int jb = (s2 > T(0)) ? j + 1 : j; B = W(W_BL, i, jb, k) + s1 * W(W_DBLX, i, jb, k); }
+    C = W(W_C, i, j, k) + (s1 * W(W_DCX, i, j, k) + s2 * W(W_DCY, i, j, k));
+  } else if (EDIR == 1) {  // (x,z)
+    { const int ia = (s1 > T(0)) ? i + 1 : i; A = W(W_AL, ia, j, k) + s2 * W(W_DALZ, ia, j, k); }
+    B = W(W_B, i, j, k) + (s1 * W(W_DBX, i, j, k) + s2 * W(W_DBZ, i, j, k));
+    { const int kc = (s2 > T(0)) ? k + 1 : k; C = W(W_CL, i, j, kc) + s1 * W(W_DCLX, i, j, kc); }
+  } else {  // (y,z)
+    A = W(W_A, i, j, k) + (s1 * W(W_DAY, i, j, k) + s2 * W(W_DAZ, i, j, k));
+    { const int jb = (s1 > T(0)) ? j + 1 : j; B = W(W_BL, i, jb, k) + s2 * W(W_DBLZ, i, jb, k); }
+    { const int kc = (s2 > T(0)) ? k + 1 : k; C = W(W_CL, i, j, kc) + s1 * W(W_DCLY, i, j, kc); }
+  }
+  dev::Corner<T> c;
+  c.r = r; c.p = p;
+  if (EDIR == 2) { c.u = U; c.v = V; c.w = Wv; c.a = A; c.b = B; c.c = C; }
+  else if (EDIR == 1) { c.u = Wv; c.v = U; c.w = V; c.a = C; c.b = A; c.c = B; }
+  else { c.u = V; c.v = Wv; c.w = U; c.a = B; c.b = C; c.c = A; }
+  return c;
+}
+
+}  // namespace
+
+}  // namespace rg

@@ -6,6 +6,9 @@
 #include "params.h"
 #include "mhd_device.cuh"
 #include "hydro_device.cuh"
+#include "mhd_cells.cuh"
+
+#include <vector>
 
 using namespace rg;
 
@@ -15,6 +18,13 @@ static KParams<T> paramsOf(const char* ini) {
   const RunParams rp = parseRunParams(cfg);
   return makeKParams<T>(cfg, rp, rp.nz, 0);
 }
+
+template <typename T>
+struct HostView {  // [comp][k][j][i]
+  T* p;
+  int isize, jsize, ksize;
+  T& operator()(int c, int i, int j, int k) const { return p[(((size_t)c * ksize + k) * jsize + j) * isize + i]; }
+};
 
 extern "C" {
 
@@ -90,6 +100,71 @@ void emu_cons_to_prim_mhd(const char* ini, int n, const double* u, const double*
     dev::cons_to_prim_mhd(P, uu, bnext[3 * t], bnext[3 * t + 1], bnext[3 * t + 2], dt, qq);
     for (int v = 0; v < 8; ++v) q[8 * t + v] = qq[v];
   }
+}
+
+// The trace stage of one 3D MHD step with the product's per-cell functions (mhd_cells.cuh) on host arrays:
+// cons -> prim, edge electric fields, trace -> W, then the face / edge states the flux and emf stages rebuild from W,
+// un-rotated to physical component order and laid out like the oracle's 18 trace arrays
+// (orc_mhd3d_trace_arrays: qm[3], qp[3], qEdge[4][3], each [var][k][j][i]).  Cells outside the range the product
+// traces (gw-1 .. size-gw) and states that would need W of a cell beyond it are left at 0.
+void emu_mhd3d_trace_arrays(const char* ini, const double* Uin, double dt, double* out) {
+  const KParams<double> P = paramsOf<double>(ini);
+  const int is = P.isize, js = P.jsize, ks = P.ksize, gw = P.gw;
+  const size_t ncell = (size_t)is * js * ks;
+  std::vector<double> Qs(ncell * 8, 0.0), ELs(ncell * 3, 0.0), Ws(ncell * NW_MHD, 0.0);
+  const HostView<const double> U{Uin, is, js, ks};
+  const HostView<double> Q{Qs.data(), is, js, ks}, EL{ELs.data(), is, js, ks}, W{Ws.data(), is, js, ks};
+  for (int k = 0; k < ks - 1; ++k)      // k_prim: 0 .. size-2
+    for (int j = 0; j < js - 1; ++j)
+      for (int i = 0; i < is - 1; ++i) {
+        double u[8], q[8];
+        for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, k);
+        dev::cons_to_prim_mhd(P, u, U(IA, i + 1, j, k), U(IB, i, j + 1, k), U(IC, i, j, k + 1), dt, q);
+        for (int v = 0; v < 8; ++v) Q(v, i, j, k) = q[v];
+      }
+  for (int k = 1; k < ks - 1; ++k)      // k_elec: 1 .. size-2
+    for (int j = 1; j < js - 1; ++j)
+      for (int i = 1; i < is - 1; ++i) elec_cell<false>(P, Q, U, EL, i, j, k);
+  for (int k = gw - 1; k <= ks - gw; ++k)   // k_trace: gw-1 .. size-gw
+    for (int j = gw - 1; j <= js - gw; ++j)
+      for (int i = gw - 1; i <= is - gw; ++i) trace_cell<false>(P, Q, U, EL, W, i, j, k, dt);
+  auto arr = [&](int s) { return HostView<double>{out + (size_t)s * ncell * 8, is, js, ks}; };
+  auto putState = [&](const HostView<double>& A, int i, int j, int k, int dir, const dev::State<double>& s) {
+    A(ID, i, j, k) = s.r; A(IP, i, j, k) = s.p;
+    if (dir == 0) { A(IU, i, j, k) = s.u; A(IV, i, j, k) = s.v; A(IW, i, j, k) = s.w; A(IA, i, j, k) = s.a; A(IB, i, j, k) = s.b; A(IC, i, j, k) = s.c; }
+    else if (dir == 1) { A(IU, i, j, k) = s.v; A(IV, i, j, k) = s.u; A(IW, i, j, k) = s.w; A(IA, i, j, k) = s.b; A(IB, i, j, k) = s.a; A(IC, i, j, k) = s.c; }
+    else { A(IU, i, j, k) = s.w; A(IV, i, j, k) = s.v; A(IW, i, j, k) = s.u; A(IA, i, j, k) = s.c; A(IB, i, j, k) = s.b; A(IC, i, j, k) = s.a; }
+  };
+  auto putCorner = [&](const HostView<double>& A, int i, int j, int k, int edir, const dev::Corner<double>& c) {
+    A(ID, i, j, k) = c.r; A(IP, i, j, k) = c.p;
+    if (edir == 2) { A(IU, i, j, k) = c.u; A(IV, i, j, k) = c.v; A(IW, i, j, k) = c.w; A(IA, i, j, k) = c.a; A(IB, i, j, k) = c.b; A(IC, i, j, k) = c.c; }
+    else if (edir == 1) { A(IW, i, j, k) = c.u; A(IU, i, j, k) = c.v; A(IV, i, j, k) = c.w; A(IC, i, j, k) = c.a; A(IA, i, j, k) = c.b; A(IB, i, j, k) = c.c; }
+    else { A(IV, i, j, k) = c.u; A(IW, i, j, k) = c.v; A(IU, i, j, k) = c.w; A(IB, i, j, k) = c.a; A(IC, i, j, k) = c.b; A(IA, i, j, k) = c.c; }
+  };
+  const int hi[3] = {is - gw, js - gw, ks - gw};  // last traced cell per direction
+  for (int k = gw - 1; k <= hi[2]; ++k)
+    for (int j = gw - 1; j <= hi[1]; ++j)
+      for (int i = gw - 1; i <= hi[0]; ++i) {
+        const int c[3] = {i, j, k};
+        // face states: qp (low face) always; qm (high face) reads the low-face field of the +1 neighbour
+        putState(arr(3), i, j, k, 0, face_state<double, 0>(P, W, i, j, k, -1.0));
+        putState(arr(4), i, j, k, 1, face_state<double, 1>(P, W, i, j, k, -1.0));
+        putState(arr(5), i, j, k, 2, face_state<double, 2>(P, W, i, j, k, -1.0));
+        if (c[0] < hi[0]) putState(arr(0), i, j, k, 0, face_state<double, 0>(P, W, i, j, k, 1.0));
+        if (c[1] < hi[1]) putState(arr(1), i, j, k, 1, face_state<double, 1>(P, W, i, j, k, 1.0));
+        if (c[2] < hi[2]) putState(arr(2), i, j, k, 2, face_state<double, 2>(P, W, i, j, k, 1.0));
+        // edge states: e = RT (+,+), RB (+,-), LT (-,+), LB (-,-) along (d1, d2) = (y,z) for x edges, (x,z) for y, (x,y) for z
+        const double sg[4][2] = {{1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+        for (int e = 0; e < 4; ++e) {
+          const double s1 = sg[e][0], s2 = sg[e][1];
+          { const bool ok = (s1 < 0 || c[1] < hi[1]) && (s2 < 0 || c[2] < hi[2]);
+            if (ok) putCorner(arr(6 + 3 * e + 0), i, j, k, 0, edge_state<double, 0>(P, W, i, j, k, s1, s2)); }
+          { const bool ok = (s1 < 0 || c[0] < hi[0]) && (s2 < 0 || c[2] < hi[2]);
+            if (ok) putCorner(arr(6 + 3 * e + 1), i, j, k, 1, edge_state<double, 1>(P, W, i, j, k, s1, s2)); }
+          { const bool ok = (s1 < 0 || c[0] < hi[0]) && (s2 < 0 || c[1] < hi[1]);
+            if (ok) putCorner(arr(6 + 3 * e + 2), i, j, k, 2, edge_state<double, 2>(P, W, i, j, k, s1, s2)); }
+        }
+      }
 }
 
 }  // extern "C"
