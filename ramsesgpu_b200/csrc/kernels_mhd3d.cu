@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BX) k_elec(const __grid_constant__ KParams<T> 
 // K1: slopes + edge electric fields + face-B slopes + half-step trace -> W
 //     (reference cpu_v3.cpp:36-361, slope_mhd.h:436-502/598-704, trace_mhd.h:1854-2030)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MINB, bool FAST>
+template <typename T, int MINB, bool FAST, bool S3 = false>
 __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                                     const T* __restrict__ Qp, const T* __restrict__ ELp,
                                                     T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
   const View<const T> Q = view<const T>(Qp, P, planes, kbase);
   const View<const T> EL = view<const T>(ELp, P, planes, kbase);
   const View<T> W = view(Wp, P, planes, kbase);
-  trace_cell<FAST>(P, Q, U, EL, W, i, j, k, dt);
+  trace_cell<FAST, S3>(P, Q, U, EL, W, i, j, k, dt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1066,7 +1066,8 @@ void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int 
 // non-rotating, HLLD fluxes + 2-D HLLD emfs; everything else runs the generic kernels
 template <typename T>
 static bool fastPath(const KParams<T>& P) {
-  return P.cIso <= T(0) && P.Omega0 <= T(0) && P.riemannSolver == RS_HLLD && P.magRiemannSolver == MAG_HLLD;
+  return P.cIso <= T(0) && P.Omega0 <= T(0) && P.riemannSolver == RS_HLLD && P.magRiemannSolver == MAG_HLLD &&
+         P.slope_type != T(3);  // the 27-point slopes run on the separate kernels (k_trace<.., S3 = true>)
 }
 
 template <typename T>
@@ -1081,6 +1082,11 @@ void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int
   if (k1 <= k0) return;
   const int n = P.isize - 2 * P.gw + 2, m = P.jsize - 2 * P.gw + 2;  // gw-1 .. size-gw
   const dim3 g = gridFor(n, m, k1 - k0);
+  if (P.slope_type == T(3)) {  // 27-point slopes: their own instantiation of the generic kernel
+    k_trace<T, 4, false, true><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt);
+    ++g_launches;
+    return;
+  }
 #define RG_L(M, FA) k_trace<T, M, FA><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
   RG_MINB_SWITCH(T, g_traceMinB, RG_L, 4)
 #undef RG_L
@@ -1133,6 +1139,7 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   // every FP64 3D MHD configuration: the FAST instantiation for the headline one, the generic one
   // (rotating frame, isothermal, other Riemann solvers) otherwise
   if (sizeof(T) != 8 || P.dim != 3) return false;
+  if (P.slope_type == T(3)) return false;  // 27-point slopes: separate prim / elec / trace kernels
   static int ok = -1;
   if (ok < 0)
     ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

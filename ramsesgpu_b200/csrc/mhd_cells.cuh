@@ -67,16 +67,47 @@ __device__ __forceinline__ void elec_cell(const KParams<T>& P, const QV& Q, cons
 // ------------------------------------------------------------------------------------------------
 // slopes + face-B slopes + half-step trace of one cell -> W (reference cpu_v3.cpp:36-361, slope_mhd.h, trace_mhd.h)
 // ------------------------------------------------------------------------------------------------
+// slope_type 3 (reference slope_mhd.h:352-409): the central differences of a variable along x, y, z are scaled by ONE
+// positivity-preserving factor, min(1, min(|vmin|, |vmax|) / (|dfx| + |dfy| + |dfz|) * 2), taken over the 27-cell
+// neighbourhood.  Returns that factor for variable v of cell (i,j,k).
+template <typename T, typename QV>
+__device__ __forceinline__ T slope27_factor(const QV& Q, int v, int i, int j, int k) {
+  const T q0 = Q(v, i, j, k);
+  T vmin = T(0), vmax = T(0);  // the centre difference (0) takes part in both
+#pragma unroll
+  for (int dk = -1; dk <= 1; ++dk)
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+      for (int di = -1; di <= 1; ++di) {
+        const T d = Q(v, i + di, j + dj, k + dk) - q0;
+        vmin = dev::mn(vmin, d);
+        vmax = dev::mx(vmax, d);
+      }
+  const T dfx = T(0.5) * (Q(v, i + 1, j, k) - Q(v, i - 1, j, k));
+  const T dfy = T(0.5) * (Q(v, i, j + 1, k) - Q(v, i, j - 1, k));
+  const T dfz = T(0.5) * (Q(v, i, j, k + 1) - Q(v, i, j, k - 1));
+  const T dff = T(0.5) * (dev::ab(dfx) + dev::ab(dfy) + dev::ab(dfz));
+  return (dff > T(0)) ? dev::mn(T(1), dev::mn(dev::ab(vmin), dev::ab(vmax)) / dff) : T(1);
+}
+
 // trace of one cell: QV(v,i,j,k) primitives, UV(v,i,j,k) conservative state (face fields), ELV(c,i,j,k)
 // edge electric fields, WV(c,i,j,k) the traced state (written).  Used by k_trace (global arrays) and by
 // the fused prim+elec+trace kernel (shared-memory tiles).
-template <bool FAST, typename T, typename QV, typename UV, typename ELV, typename WV>
+template <bool FAST, bool S3 = false, typename T, typename QV, typename UV, typename ELV, typename WV>
 __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, const UV& U, const ELV& EL, const WV& W,
                                            int i, int j, int k, T dt) {
   const int gw = P.gw;
   const T h = T(0.5);
   const T hst = h * P.slope_type;  // slope_type 0 gives zero slopes through hst = 0
   const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  // HALF slope of primitive variable v between its -1 / +1 neighbours along one direction: TVD limiter (types 1, 2),
+  // or the centred difference times the 27-point factor (S3 = slope_type 3: its own instantiation, so that the
+  // kernels of the other slope types are untouched)
+  auto hslope = [&](int v, T qm, T q0, T qp) -> T {
+    if (S3) return h * (slope27_factor<T>(Q, v, i, j, k) * (h * (qp - qm)));
+    return dev::half_slope(hst, qm, q0, qp);
+  };
   // The work is arranged direction by direction (slopes of one direction -> stored -> their share of
   // the half-step source terms accumulated) so that few values are live at any time.
 
@@ -107,13 +138,13 @@ __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, con
   const T gp = P.gamma0 * p;
   T sr0, su0, sv0, sw0, sp0, sA0, sB0, sC0;
   {  // x
-    const T drx = dev::half_slope(hst, Q(ID, i - 1, j, k), r, Q(ID, i + 1, j, k));
-    const T dpx = dev::half_slope(hst, Q(IP, i - 1, j, k), p, Q(IP, i + 1, j, k));
-    const T dux = dev::half_slope(hst, Q(IU, i - 1, j, k), u, Q(IU, i + 1, j, k));
-    const T dvx = dev::half_slope(hst, Q(IV, i - 1, j, k), v, Q(IV, i + 1, j, k));
-    const T dwx = dev::half_slope(hst, Q(IW, i - 1, j, k), w, Q(IW, i + 1, j, k));
-    const T dBx = dev::half_slope(hst, Q(IB, i - 1, j, k), B, Q(IB, i + 1, j, k));
-    const T dCx = dev::half_slope(hst, Q(IC, i - 1, j, k), C, Q(IC, i + 1, j, k));
+    const T drx = hslope(ID, Q(ID, i - 1, j, k), r, Q(ID, i + 1, j, k));
+    const T dpx = hslope(IP, Q(IP, i - 1, j, k), p, Q(IP, i + 1, j, k));
+    const T dux = hslope(IU, Q(IU, i - 1, j, k), u, Q(IU, i + 1, j, k));
+    const T dvx = hslope(IV, Q(IV, i - 1, j, k), v, Q(IV, i + 1, j, k));
+    const T dwx = hslope(IW, Q(IW, i - 1, j, k), w, Q(IW, i + 1, j, k));
+    const T dBx = hslope(IB, Q(IB, i - 1, j, k), B, Q(IB, i + 1, j, k));
+    const T dCx = hslope(IC, Q(IC, i - 1, j, k), C, Q(IC, i + 1, j, k));
     W(W_DRX, i, j, k) = drx; W(W_DPX, i, j, k) = dpx; W(W_DUX, i, j, k) = dux; W(W_DVX, i, j, k) = dvx;
     W(W_DWX, i, j, k) = dwx; W(W_DBX, i, j, k) = dBx; W(W_DCX, i, j, k) = dCx;
     sr0 = (-u * drx - dux * r) * dtdx;
@@ -126,13 +157,13 @@ __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, con
   }
   T shr = T(0), shu = T(0), shv = T(0), shw = T(0), shp = T(0), shA = T(0), shC = T(0);  // shearing box only
   {  // y
-    const T dry = dev::half_slope(hst, Q(ID, i, j - 1, k), r, Q(ID, i, j + 1, k));
-    const T dpy = dev::half_slope(hst, Q(IP, i, j - 1, k), p, Q(IP, i, j + 1, k));
-    const T duy = dev::half_slope(hst, Q(IU, i, j - 1, k), u, Q(IU, i, j + 1, k));
-    const T dvy = dev::half_slope(hst, Q(IV, i, j - 1, k), v, Q(IV, i, j + 1, k));
-    const T dwy = dev::half_slope(hst, Q(IW, i, j - 1, k), w, Q(IW, i, j + 1, k));
-    const T dAy = dev::half_slope(hst, Q(IA, i, j - 1, k), A, Q(IA, i, j + 1, k));
-    const T dCy = dev::half_slope(hst, Q(IC, i, j - 1, k), C, Q(IC, i, j + 1, k));
+    const T dry = hslope(ID, Q(ID, i, j - 1, k), r, Q(ID, i, j + 1, k));
+    const T dpy = hslope(IP, Q(IP, i, j - 1, k), p, Q(IP, i, j + 1, k));
+    const T duy = hslope(IU, Q(IU, i, j - 1, k), u, Q(IU, i, j + 1, k));
+    const T dvy = hslope(IV, Q(IV, i, j - 1, k), v, Q(IV, i, j + 1, k));
+    const T dwy = hslope(IW, Q(IW, i, j - 1, k), w, Q(IW, i, j + 1, k));
+    const T dAy = hslope(IA, Q(IA, i, j - 1, k), A, Q(IA, i, j + 1, k));
+    const T dCy = hslope(IC, Q(IC, i, j - 1, k), C, Q(IC, i, j + 1, k));
     W(W_DRY, i, j, k) = dry; W(W_DPY, i, j, k) = dpy; W(W_DUY, i, j, k) = duy; W(W_DVY, i, j, k) = dvy;
     W(W_DWY, i, j, k) = dwy; W(W_DAY, i, j, k) = dAy; W(W_DCY, i, j, k) = dCy;
     sr0 += (-v * dry - dvy * r) * dtdy;
@@ -150,13 +181,13 @@ __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, con
     }
   }
   {  // z
-    const T drz = dev::half_slope(hst, Q(ID, i, j, k - 1), r, Q(ID, i, j, k + 1));
-    const T dpz = dev::half_slope(hst, Q(IP, i, j, k - 1), p, Q(IP, i, j, k + 1));
-    const T duz = dev::half_slope(hst, Q(IU, i, j, k - 1), u, Q(IU, i, j, k + 1));
-    const T dvz = dev::half_slope(hst, Q(IV, i, j, k - 1), v, Q(IV, i, j, k + 1));
-    const T dwz = dev::half_slope(hst, Q(IW, i, j, k - 1), w, Q(IW, i, j, k + 1));
-    const T dAz = dev::half_slope(hst, Q(IA, i, j, k - 1), A, Q(IA, i, j, k + 1));
-    const T dBz = dev::half_slope(hst, Q(IB, i, j, k - 1), B, Q(IB, i, j, k + 1));
+    const T drz = hslope(ID, Q(ID, i, j, k - 1), r, Q(ID, i, j, k + 1));
+    const T dpz = hslope(IP, Q(IP, i, j, k - 1), p, Q(IP, i, j, k + 1));
+    const T duz = hslope(IU, Q(IU, i, j, k - 1), u, Q(IU, i, j, k + 1));
+    const T dvz = hslope(IV, Q(IV, i, j, k - 1), v, Q(IV, i, j, k + 1));
+    const T dwz = hslope(IW, Q(IW, i, j, k - 1), w, Q(IW, i, j, k + 1));
+    const T dAz = hslope(IA, Q(IA, i, j, k - 1), A, Q(IA, i, j, k + 1));
+    const T dBz = hslope(IB, Q(IB, i, j, k - 1), B, Q(IB, i, j, k + 1));
     W(W_DRZ, i, j, k) = drz; W(W_DPZ, i, j, k) = dpz; W(W_DUZ, i, j, k) = duz; W(W_DVZ, i, j, k) = dvz;
     W(W_DWZ, i, j, k) = dwz; W(W_DAZ, i, j, k) = dAz; W(W_DBZ, i, j, k) = dBz;
     sr0 += (-w * drz - dwz * r) * dtdz;

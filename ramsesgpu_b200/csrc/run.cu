@@ -87,7 +87,10 @@ class RunImpl final : public Run {
     for (int f = 0; f < 2 * rp_.dim; ++f)
       if (rp_.bc[f] == BC_COPY || rp_.bc[f] == BC_Z_STRATIFIED)
         throw std::runtime_error("boundary type " + std::to_string(rp_.bc[f]) + " (copy / z-stratified) is not available in this build");
-    if (kp_.slope_type == T(3)) throw std::runtime_error("slope_type 3 (27-point positivity-preserving slopes) is not available in this build");
+    // slope_type 3 (27-point slopes, slope_mhd.h:352-409) exists for the non-rotating 3D MHD step, like in the
+    // reference (its rotating CPU step never fills the slopes for that type, its 2D and hydro steps ignore it)
+    if (kp_.slope_type == T(3) && !(rp_.mhdEnabled && rp_.dim == 3 && !(kp_.Omega0 > T(0))))
+      throw std::runtime_error("slope_type 3 is available for the non-rotating 3D MHD solver only");
     cells_ = (size_t)kp_.isize * kp_.jsize * kp_.ksize;
     elems_ = cells_ * kp_.nvar;
     RG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));

@@ -127,7 +127,10 @@ void emu_mhd3d_trace_arrays(const char* ini, const double* Uin, double dt, doubl
       for (int i = 1; i < is - 1; ++i) elec_cell<false>(P, Q, U, EL, i, j, k);
   for (int k = gw - 1; k <= ks - gw; ++k)   // k_trace: gw-1 .. size-gw
     for (int j = gw - 1; j <= js - gw; ++j)
-      for (int i = gw - 1; i <= is - gw; ++i) trace_cell<false>(P, Q, U, EL, W, i, j, k, dt);
+      for (int i = gw - 1; i <= is - gw; ++i) {
+        if (P.slope_type == 3.0) trace_cell<false, true>(P, Q, U, EL, W, i, j, k, dt);   // k_trace<.., S3 = true>
+        else trace_cell<false>(P, Q, U, EL, W, i, j, k, dt);
+      }
   auto arr = [&](int s) { return HostView<double>{out + (size_t)s * ncell * 8, is, js, ks}; };
   auto putState = [&](const HostView<double>& A, int i, int j, int k, int dir, const dev::State<double>& s) {
     A(ID, i, j, k) = s.r; A(IP, i, j, k) = s.p;

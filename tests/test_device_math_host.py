@@ -196,6 +196,7 @@ def smooth_state(p, seed):
 @pytest.mark.parametrize("over,name", [
     ({}, "adiabatic"),
     ({"hydro": {"slope_type": 1.0}}, "minmod"),
+    ({"hydro": {"slope_type": 3.0}}, "27-point slopes"),
     ({"hydro": {"cIso": 0.4}}, "isothermal"),
     ({"MHD": {"omega0": 0.3}, "hydro": {"cIso": 0.4}}, "rotating frame, isothermal"),
     ({"hydro": {"problem": "Rayleigh-Taylor"}, "gravity": {"static_field_x": 0.3, "static_field_z": -0.7}}, "static gravity"),

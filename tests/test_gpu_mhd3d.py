@@ -10,7 +10,8 @@ from ramsesgpu_b200.io import l2_relative
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN_CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4"]
+GOLDEN_CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neumann_hll_s4",
+                "ot3d_slope3_16x12x20_s6"]   # slope_type 3: 27-point slopes (k_trace<.., S3 = true>, separate kernels)
 
 
 def run_gpu_steps(ini, nsteps, U0=None, chunk=0):
