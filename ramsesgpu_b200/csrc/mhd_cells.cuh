@@ -284,6 +284,138 @@ __device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const 
   return c;
 }
 
+// ------------------------------------------------------------------------------------------------
+// conservative update + constrained transport + inverse dt of the NEW state for one cell of the update box
+// (reference cpu_v3.cpp:475-533, :600-630; dt: MHDRunBase.cpp:141-250)
+// ------------------------------------------------------------------------------------------------
+// One cell of the update box (gw <= i <= iN etc.).  FV(c, i, j, k) / EV(c, i, j, k) give the face
+// fluxes and corner emfs (global scratch arrays or the shared-memory tile of the fused kernel).
+// Returns the inverse time step of the NEW state (0 outside the inner cells).
+template <bool FAST, typename T, typename UV, typename FV, typename EV>
+__device__ __forceinline__ T update_cell(const KParams<T>& P, const UV& U, T* __restrict__ Unew, const FV& F,
+                                         const EV& E, int i, int j, int k, T dt) {
+  const int gw = P.gw;
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;  // first upper ghost index
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  const bool inner = i < iN && j < jN && k < kN;
+  T invDt = T(0);
+  T un[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
+  if (inner) {
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      // same summation order as the reference's serial scatter
+      T s = un[v];
+      s += F(v, i, j, k) * dtdx;
+      s += F(5 + v, i, j, k) * dtdy;
+      s += F(10 + v, i, j, k) * dtdz;
+      s -= F(v, i + 1, j, k) * dtdx;
+      s -= F(5 + v, i, j + 1, k) * dtdy;
+      s -= F(10 + v, i, j, k + 1) * dtdz;
+      un[v] = s;
+    }
+    if (P.gravity) {  // static gravity source term on the momenta, reference HydroRunBase.cpp:1962-1976
+      const T hdt = T(0.5) * dt, rs = U(ID, i, j, k) + un[ID];
+      un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * P.gz * rs;
+    }
+  }
+  // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,
+  // exactly like the reference's zero-initialised h_emf
+  auto emf = [&](int c, int ii, int jj, int kk) -> T {
+    return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
+  };
+  // constrained transport of one face component (reference cpu_v3.cpp:600-630), per component so
+  // that the dt estimate below touches only the emfs it needs
+  auto ctx = [&](int ii, int jj, int kk, T bx) -> T {
+    if (kk < kN) bx += (emf(0, ii, jj + 1, kk) - emf(0, ii, jj, kk)) * dtdy;
+    return bx - (emf(1, ii, jj, kk + 1) - emf(1, ii, jj, kk)) * dtdz;
+  };
+  auto cty = [&](int ii, int jj, int kk, T by) -> T {
+    if (kk < kN) by -= (emf(0, ii + 1, jj, kk) - emf(0, ii, jj, kk)) * dtdx;
+    return by + (emf(2, ii, jj, kk + 1) - emf(2, ii, jj, kk)) * dtdz;
+  };
+  auto ctz = [&](int ii, int jj, int kk, T bz) -> T {
+    bz += (emf(1, ii + 1, jj, kk) - emf(1, ii, jj, kk)) * dtdx;
+    return bz - (emf(2, ii, jj + 1, kk) - emf(2, ii, jj, kk)) * dtdy;
+  };
+  un[IA] = ctx(i, j, k, un[IA]);
+  un[IB] = cty(i, j, k, un[IB]);
+  un[IC] = ctz(i, j, k, un[IC]);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
+
+  if (inner) {  // inverse dt of the new state: needs the new B on the three upper faces
+    const T bxp = ctx(i + 1, j, k, U(IA, i + 1, j, k));
+    const T byp = cty(i, j + 1, k, U(IB, i, j + 1, k));
+    const T bzp = ctz(i, j, k + 1, U(IC, i, j, k + 1));
+    T q[8];
+    dev::cons_to_prim_mhd<FAST>(P, un, bxp, byp, bzp, T(0), q);
+    const T irho = dev::rcp(q[ID]);
+    const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+    const T bb = a2 + b2 + c2;
+    T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+    T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
+    T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+    if (!FAST && P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+    invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+  }
+  return invDt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one face flux / one corner emf of the FAST configuration (adiabatic, non-rotating, HLLD + 2-D HLLD) from W;
+// W, F, E are any accessors: shared-memory tiles in the fused kernel, host arrays in the CPU test suite
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename WV, typename FV>
+__device__ __forceinline__ void fused_flux_task(const KParams<T>& P, const WV& W,
+                                                const FV& F, int dir, int i, int j, int k) {
+  dev::State<T> L, R;
+  if (dir == 0) {
+    L = face_state<T, 0>(P, W, i - 1, j, k, T(1));
+    R = face_state<T, 0>(P, W, i, j, k, T(-1));
+  } else if (dir == 1) {
+    L = face_state<T, 1>(P, W, i, j - 1, k, T(1));
+    R = face_state<T, 1>(P, W, i, j, k, T(-1));
+  } else {
+    L = face_state<T, 2>(P, W, i, j, k - 1, T(1));
+    R = face_state<T, 2>(P, W, i, j, k, T(-1));
+  }
+  T f[8];
+  dev::riemann_mhd<true>(P, L, R, f);
+  const int c0 = 5 * dir;
+  F(c0 + 0, i, j, k) = f[ID];
+  F(c0 + 1, i, j, k) = f[IP];
+  F(c0 + 2, i, j, k) = (dir == 0) ? f[IU] : (dir == 1) ? f[IV] : f[IW];
+  F(c0 + 3, i, j, k) = (dir == 1) ? f[IU] : f[IV];
+  F(c0 + 4, i, j, k) = (dir == 2) ? f[IU] : f[IW];
+}
+
+template <typename T, typename WV, typename EV>
+__device__ __forceinline__ void fused_emf_task(const KParams<T>& P, const WV& W,
+                                               const EV& E, int edir, int i, int j, int k) {
+  dev::Corner<T> RT, RB, LT, LB;
+  if (edir == 2) {
+    RT = edge_state<T, 2>(P, W, i - 1, j - 1, k, T(1), T(1));
+    RB = edge_state<T, 2>(P, W, i - 1, j, k, T(1), T(-1));
+    LT = edge_state<T, 2>(P, W, i, j - 1, k, T(-1), T(1));
+    LB = edge_state<T, 2>(P, W, i, j, k, T(-1), T(-1));
+  } else if (edir == 1) {
+    RT = edge_state<T, 1>(P, W, i - 1, j, k - 1, T(1), T(1));
+    RB = edge_state<T, 1>(P, W, i, j, k - 1, T(-1), T(1));
+    LT = edge_state<T, 1>(P, W, i - 1, j, k, T(1), T(-1));
+    LB = edge_state<T, 1>(P, W, i, j, k, T(-1), T(-1));
+  } else {
+    RT = edge_state<T, 0>(P, W, i, j - 1, k - 1, T(1), T(1));
+    RB = edge_state<T, 0>(P, W, i, j - 1, k, T(1), T(-1));
+    LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
+    LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
+  }
+  E(2 - edir, i, j, k) = dev::compute_emf<true>(P, RT, RB, LT, LB, edir, T(0));
+}
+
 }  // namespace
 
 }  // namespace rg

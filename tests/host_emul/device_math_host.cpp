@@ -170,4 +170,53 @@ void emu_mhd3d_trace_arrays(const char* ini, const double* Uin, double dt, doubl
       }
 }
 
+// One whole step of the FAST configuration (adiabatic, non-rotating, HLLD + 2-D HLLD: the headline workload) from a
+// ghost-filled state, with the product's per-cell functions in the order and over the index ranges of its kernels
+// (k_prim, k_elec, k_trace, flux / emf tasks, update_cell with the constrained-transport update and the next
+// inverse dt).  Unew must hold a copy of Uold on entry (the kernels leave the cells outside the update box alone).
+// Returns the maximum inverse dt of the new state.
+double emu_mhd3d_step_fast(const char* ini, const double* Uin, double dt, double* Unew) {
+  const KParams<double> P = paramsOf<double>(ini);
+  const int is = P.isize, js = P.jsize, ks = P.ksize, gw = P.gw;
+  const int iN = is - gw, jN = js - gw, kN = ks - gw;
+  const size_t ncell = (size_t)is * js * ks;
+  std::vector<double> Qs(ncell * 8, 0.0), ELs(ncell * 3, 0.0), Ws(ncell * NW_MHD, 0.0), Fs(ncell * 15, 0.0), Es(ncell * 3, 0.0);
+  const HostView<const double> U{Uin, is, js, ks};
+  const HostView<double> Q{Qs.data(), is, js, ks}, EL{ELs.data(), is, js, ks}, W{Ws.data(), is, js, ks};
+  const HostView<double> F{Fs.data(), is, js, ks}, E{Es.data(), is, js, ks};
+  for (int k = 0; k < ks - 1; ++k)
+    for (int j = 0; j < js - 1; ++j)
+      for (int i = 0; i < is - 1; ++i) {
+        double u[8], q[8];
+        for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, k);
+        dev::cons_to_prim_mhd<true>(P, u, U(IA, i + 1, j, k), U(IB, i, j + 1, k), U(IC, i, j, k + 1), dt, q);
+        for (int v = 0; v < 8; ++v) Q(v, i, j, k) = q[v];
+      }
+  for (int k = 1; k < ks - 1; ++k)
+    for (int j = 1; j < js - 1; ++j)
+      for (int i = 1; i < is - 1; ++i) elec_cell<true>(P, Q, U, EL, i, j, k);
+  for (int k = gw - 1; k <= kN; ++k)
+    for (int j = gw - 1; j <= jN; ++j)
+      for (int i = gw - 1; i <= iN; ++i) trace_cell<true>(P, Q, U, EL, W, i, j, k, dt);
+  for (int k = gw; k <= kN; ++k)
+    for (int j = gw; j <= jN; ++j)
+      for (int i = gw; i <= iN; ++i) {
+        for (int dir = 0; dir < 3; ++dir) {  // a face is only needed where both transverse indexes are inner (k_flux)
+          if (dir != 0 && i >= iN) continue;
+          if (dir != 1 && j >= jN) continue;
+          if (dir != 2 && k >= kN) continue;
+          fused_flux_task(P, W, F, dir, i, j, k);
+        }
+        for (int edir = 0; edir < 3; ++edir) fused_emf_task(P, W, E, edir, i, j, k);
+      }
+  double invDt = 0.0;
+  for (int k = gw; k <= kN; ++k)
+    for (int j = gw; j <= jN; ++j)
+      for (int i = gw; i <= iN; ++i) {
+        const double v = update_cell<true>(P, U, Unew, F, E, i, j, k, dt);
+        if (v > invDt) invDt = v;
+      }
+  return invDt;
+}
+
 }  // extern "C"

@@ -235,3 +235,35 @@ def test_trace_stage_of_the_product_vs_oracle(emu, oracle64, over, name):
         assert err < 1e-13, (name, s, err)
         checked += a.size
     assert checked > 18 * 8 * 200
+
+
+@pytest.mark.parametrize("n,kt,seed", [((10, 8, 9), 1.0, 3), ((14, 6, 7), 0.0, 4)])
+def test_whole_step_of_the_headline_configuration_vs_oracle(emu, oracle64, n, kt, seed):
+    """One whole step of the FAST configuration (adiabatic HLLD + 2-D HLLD, the bench workload) assembled on the host from
+    the product's per-cell functions (mhd_cells.cuh: the same source the fused TMA kernels and the separate kernels
+    instantiate) over the kernels' index ranges, against the oracle's step: conservative update, constrained transport
+    (incl. the first upper ghost faces) and the dt of the new state."""
+    emu.emu_mhd3d_step_fast.argtypes = [C.c_char_p, D, C.c_double, D]
+    emu.emu_mhd3d_step_fast.restype = C.c_double
+    ini = ot3d_ini(n, OrszagTang={"kt": kt})
+    p = oracle64.params(ini)
+    U = smooth_state(p, seed)
+    oracle64.make_all_boundaries(p, U)
+    dt = oracle64.compute_dt(p, U)
+    want = np.zeros_like(U)
+    oracle64.step_no_boundaries(p, U, want, dt)
+    got = U.copy()
+    inv_dt = emu.emu_mhd3d_step_fast(ini.encode(), p64(U), dt, p64(got))
+    gw = p.ghostWidth
+    box = (slice(None), slice(gw, p.ksize - gw + 1), slice(gw, p.jsize - gw + 1), slice(gw, p.isize - gw + 1))
+    inner = (slice(None), slice(gw, -gw), slice(gw, -gw), slice(gw, -gw))
+    for v in range(8):
+        scale = np.abs(want[v][inner[1:]]).max() + 1e-3
+        sl = inner if v < 5 else box          # face fields: the update box includes the first upper ghost faces
+        assert (np.abs(got[v][sl[1:]] - want[v][sl[1:]]) / scale).max() < 1e-13, v
+    # cells outside the update box are untouched, like the reference's copy of UOld
+    mask = np.ones(U.shape[1:], bool); mask[box[1:]] = False
+    assert np.array_equal(got[:, mask], U[:, mask])
+    # next dt from the inverse dt reduced inside the update (seed of the running max: MHDRunBase.cpp:144)
+    dt_next = p.cfl / max(inv_dt, p.smallc / min(p.dx, p.dy))
+    assert abs(dt_next - oracle64.compute_dt(p, want)) < 1e-13 * dt_next
