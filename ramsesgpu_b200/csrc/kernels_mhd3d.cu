@@ -209,36 +209,7 @@ __global__ void __launch_bounds__(BX, MINB) k_flux(const __grid_constant__ KPara
   if (DIR != 2 && k >= P.ksize - gw) return;
   const View<const T> W = view<const T>(Wp, P, planes, kbase);
   const View<T> F = view(Fp, P, planes, kbase);
-  const int il = i - (DIR == 0), jl = j - (DIR == 1), kl = k - (DIR == 2);
-  const dev::State<T> L = face_state<T, DIR>(P, W, il, jl, kl, T(1));
-  const dev::State<T> R = face_state<T, DIR>(P, W, i, j, k, T(-1));
-  T f[8];
-  dev::riemann_mhd<FAST>(P, L, R, f);
-  if (!FAST && DIR == 1 && P.Omega0 > T(0)) {
-    // rotating frame: upwind advection of the y flux by the background shear
-    // (MHDRunGodunov.cpp:2860-2899; the states are those the Riemann solver has seen: mean normal
-    // field, isothermal pressure when cIso > 0 and the solver is HLLD)
-    const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
-    const T shear_y = T(-1.5) * P.Omega0 * xPos;
-    const T bn = T(0.5) * (L.a + R.a);
-    const dev::State<T>& S = (shear_y > T(0)) ? L : R;
-    const T pS = (P.cIso > T(0) && P.riemannSolver == RS_HLLD) ? S.r * P.cIso * P.cIso : S.p;
-    const T eMag = T(0.5) * (bn * bn + S.b * S.b + S.c * S.c);
-    const T eKin = T(0.5) * (S.u * S.u + S.v * S.v + S.w * S.w);
-    const T eTot = eKin + eMag + pS / (P.gamma0 - T(1));
-    f[ID] += shear_y * S.r;
-    f[IP] += shear_y * (eTot + eMag - bn * bn);
-    f[IU] += shear_y * S.r * S.u;
-    f[IV] += shear_y * S.r * S.v;
-    f[IW] += shear_y * S.r * S.w;
-  }
-  // store in physical component order (undo the frame permutation)
-  const int c0 = 5 * DIR;
-  F(c0 + 0, i, j, k) = f[ID];
-  F(c0 + 1, i, j, k) = f[IP];
-  F(c0 + 2, i, j, k) = (DIR == 0) ? f[IU] : (DIR == 1) ? f[IV] : f[IW];
-  F(c0 + 3, i, j, k) = (DIR == 1) ? f[IU] : f[IV];
-  F(c0 + 4, i, j, k) = (DIR == 2) ? f[IU] : f[IW];
+  flux_cell<T, DIR, FAST>(P, W, F, i, j, k);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -254,26 +225,7 @@ __global__ void __launch_bounds__(BX, MINB) k_emf(const __grid_constant__ KParam
   if (!tileCoords(gw, P.nx + 1, gw, P.ny + 1, i, j)) return;
   const View<const T> W = view<const T>(Wp, P, planes, kbase);
   const View<T> E = view(Ep, P, planes, kbase);
-  const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
-  dev::Corner<T> RT, RB, LT, LB;
-  if (EDIR == 2) {  // cpu_v3.cpp:550-557 : (s1,s2) = (x,y)
-    RT = edge_state<T, 2>(P, W, i - 1, j - 1, k, T(1), T(1));
-    RB = edge_state<T, 2>(P, W, i - 1, j, k, T(1), T(-1));
-    LT = edge_state<T, 2>(P, W, i, j - 1, k, T(-1), T(1));
-    LB = edge_state<T, 2>(P, W, i, j, k, T(-1), T(-1));
-  } else if (EDIR == 1) {  // cpu_v3.cpp:561-569 : (s1,s2) = (x,z); RB and LT swapped
-    RT = edge_state<T, 1>(P, W, i - 1, j, k - 1, T(1), T(1));
-    RB = edge_state<T, 1>(P, W, i, j, k - 1, T(-1), T(1));   // LT2(i,j,k-1)
-    LT = edge_state<T, 1>(P, W, i - 1, j, k, T(1), T(-1));   // RB2(i-1,j,k)
-    LB = edge_state<T, 1>(P, W, i, j, k, T(-1), T(-1));
-  } else {  // cpu_v3.cpp:572-579 : (s1,s2) = (y,z)
-    RT = edge_state<T, 0>(P, W, i, j - 1, k - 1, T(1), T(1));
-    RB = edge_state<T, 0>(P, W, i, j - 1, k, T(1), T(-1));
-    LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
-    LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
-  }
-  // reference component order: I_EMFZ = 0, I_EMFY = 1, I_EMFX = 2
-  E(2 - EDIR, i, j, k) = dev::compute_emf<FAST>(P, RT, RB, LT, LB, EDIR, xPos);
+  emf_cell<T, EDIR, FAST>(P, W, E, i, j, k);
 }
 
 // ------------------------------------------------------------------------------------------------

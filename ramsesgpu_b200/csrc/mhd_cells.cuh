@@ -416,6 +416,73 @@ __device__ __forceinline__ void fused_emf_task(const KParams<T>& P, const WV& W,
   E(2 - edir, i, j, k) = dev::compute_emf<true>(P, RT, RB, LT, LB, edir, T(0));
 }
 
+// ------------------------------------------------------------------------------------------------
+// generic path: Riemann flux through the LOW face normal to DIR of cell (i,j,k) (any solver; rotating-frame shear
+// advection of the y flux), stored in physical component order (reference cpu_v3.cpp:397-465)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DIR, bool FAST, typename WV, typename FV>
+__device__ __forceinline__ void flux_cell(const KParams<T>& P, const WV& W, const FV& F, int i, int j, int k) {
+  const int gw = P.gw;
+  const int il = i - (DIR == 0), jl = j - (DIR == 1), kl = k - (DIR == 2);
+  const dev::State<T> L = face_state<T, DIR>(P, W, il, jl, kl, T(1));
+  const dev::State<T> R = face_state<T, DIR>(P, W, i, j, k, T(-1));
+  T f[8];
+  dev::riemann_mhd<FAST>(P, L, R, f);
+  if (!FAST && DIR == 1 && P.Omega0 > T(0)) {
+    // rotating frame: upwind advection of the y flux by the background shear
+    // (MHDRunGodunov.cpp:2860-2899; the states are those the Riemann solver has seen: mean normal
+    // field, isothermal pressure when cIso > 0 and the solver is HLLD)
+    const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
+    const T shear_y = T(-1.5) * P.Omega0 * xPos;
+    const T bn = T(0.5) * (L.a + R.a);
+    const dev::State<T>& S = (shear_y > T(0)) ? L : R;
+    const T pS = (P.cIso > T(0) && P.riemannSolver == RS_HLLD) ? S.r * P.cIso * P.cIso : S.p;
+    const T eMag = T(0.5) * (bn * bn + S.b * S.b + S.c * S.c);
+    const T eKin = T(0.5) * (S.u * S.u + S.v * S.v + S.w * S.w);
+    const T eTot = eKin + eMag + pS / (P.gamma0 - T(1));
+    f[ID] += shear_y * S.r;
+    f[IP] += shear_y * (eTot + eMag - bn * bn);
+    f[IU] += shear_y * S.r * S.u;
+    f[IV] += shear_y * S.r * S.v;
+    f[IW] += shear_y * S.r * S.w;
+  }
+  // store in physical component order (undo the frame permutation)
+  const int c0 = 5 * DIR;
+  F(c0 + 0, i, j, k) = f[ID];
+  F(c0 + 1, i, j, k) = f[IP];
+  F(c0 + 2, i, j, k) = (DIR == 0) ? f[IU] : (DIR == 1) ? f[IV] : f[IW];
+  F(c0 + 3, i, j, k) = (DIR == 1) ? f[IU] : f[IV];
+  F(c0 + 4, i, j, k) = (DIR == 2) ? f[IU] : f[IW];
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path: corner emf along EDIR at the low edge of cell (i,j,k) (reference cpu_v3.cpp:539-579)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int EDIR, bool FAST, typename WV, typename EV>
+__device__ __forceinline__ void emf_cell(const KParams<T>& P, const WV& W, const EV& E, int i, int j, int k) {
+  const int gw = P.gw;
+  const T xPos = P.xMin + P.dx * T(0.5) + (i - gw) * P.dx;
+  dev::Corner<T> RT, RB, LT, LB;
+  if (EDIR == 2) {  // cpu_v3.cpp:550-557 : (s1,s2) = (x,y)
+    RT = edge_state<T, 2>(P, W, i - 1, j - 1, k, T(1), T(1));
+    RB = edge_state<T, 2>(P, W, i - 1, j, k, T(1), T(-1));
+    LT = edge_state<T, 2>(P, W, i, j - 1, k, T(-1), T(1));
+    LB = edge_state<T, 2>(P, W, i, j, k, T(-1), T(-1));
+  } else if (EDIR == 1) {  // cpu_v3.cpp:561-569 : (s1,s2) = (x,z); RB and LT swapped
+    RT = edge_state<T, 1>(P, W, i - 1, j, k - 1, T(1), T(1));
+    RB = edge_state<T, 1>(P, W, i, j, k - 1, T(-1), T(1));   // LT2(i,j,k-1)
+    LT = edge_state<T, 1>(P, W, i - 1, j, k, T(1), T(-1));   // RB2(i-1,j,k)
+    LB = edge_state<T, 1>(P, W, i, j, k, T(-1), T(-1));
+  } else {  // cpu_v3.cpp:572-579 : (s1,s2) = (y,z)
+    RT = edge_state<T, 0>(P, W, i, j - 1, k - 1, T(1), T(1));
+    RB = edge_state<T, 0>(P, W, i, j - 1, k, T(1), T(-1));
+    LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
+    LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
+  }
+  // reference component order: I_EMFZ = 0, I_EMFY = 1, I_EMFX = 2
+  E(2 - EDIR, i, j, k) = dev::compute_emf<FAST>(P, RT, RB, LT, LB, EDIR, xPos);
+}
+
 }  // namespace
 
 }  // namespace rg

@@ -220,3 +220,68 @@ double emu_mhd3d_step_fast(const char* ini, const double* Uin, double dt, double
 }
 
 }  // extern "C"
+
+// The same for the GENERIC path (any Riemann / emf solver, isothermal, 27-point slopes, static gravity; Omega0 = 0):
+// k_prim, k_elec, k_trace<false>, k_flux<false> x3, k_emf<false> x3, k_update<false>.
+template <int DIR>
+static void fluxAll(const KParams<double>& P, const HostView<double>& W, const HostView<double>& F) {
+  const int gw = P.gw, iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
+  for (int k = gw; k <= kN; ++k)
+    for (int j = gw; j <= jN; ++j)
+      for (int i = gw; i <= iN; ++i) {
+        if (DIR != 0 && i >= iN) continue;
+        if (DIR != 1 && j >= jN) continue;
+        if (DIR != 2 && k >= kN) continue;
+        flux_cell<double, DIR, false>(P, W, F, i, j, k);
+      }
+}
+template <int EDIR>
+static void emfAll(const KParams<double>& P, const HostView<double>& W, const HostView<double>& E) {
+  const int gw = P.gw, iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
+  for (int k = gw; k <= kN; ++k)
+    for (int j = gw; j <= jN; ++j)
+      for (int i = gw; i <= iN; ++i) emf_cell<double, EDIR, false>(P, W, E, i, j, k);
+}
+
+double emu_mhd3d_step_generic_impl(const char* ini, const double* Uin, double dt, double* Unew) {
+  const KParams<double> P = paramsOf<double>(ini);
+  const int is = P.isize, js = P.jsize, ks = P.ksize, gw = P.gw;
+  const int iN = is - gw, jN = js - gw, kN = ks - gw;
+  const size_t ncell = (size_t)is * js * ks;
+  std::vector<double> Qs(ncell * 8, 0.0), ELs(ncell * 3, 0.0), Ws(ncell * NW_MHD, 0.0), Fs(ncell * 15, 0.0), Es(ncell * 3, 0.0);
+  const HostView<const double> U{Uin, is, js, ks};
+  const HostView<double> Q{Qs.data(), is, js, ks}, EL{ELs.data(), is, js, ks}, W{Ws.data(), is, js, ks};
+  const HostView<double> F{Fs.data(), is, js, ks}, E{Es.data(), is, js, ks};
+  for (int k = 0; k < ks - 1; ++k)
+    for (int j = 0; j < js - 1; ++j)
+      for (int i = 0; i < is - 1; ++i) {
+        double u[8], q[8];
+        for (int v = 0; v < 8; ++v) u[v] = U(v, i, j, k);
+        dev::cons_to_prim_mhd(P, u, U(IA, i + 1, j, k), U(IB, i, j + 1, k), U(IC, i, j, k + 1), dt, q);
+        for (int v = 0; v < 8; ++v) Q(v, i, j, k) = q[v];
+      }
+  for (int k = 1; k < ks - 1; ++k)
+    for (int j = 1; j < js - 1; ++j)
+      for (int i = 1; i < is - 1; ++i) elec_cell<false>(P, Q, U, EL, i, j, k);
+  for (int k = gw - 1; k <= kN; ++k)
+    for (int j = gw - 1; j <= jN; ++j)
+      for (int i = gw - 1; i <= iN; ++i) {
+        if (P.slope_type == 3.0) trace_cell<false, true>(P, Q, U, EL, W, i, j, k, dt);
+        else trace_cell<false>(P, Q, U, EL, W, i, j, k, dt);
+      }
+  fluxAll<0>(P, W, F); fluxAll<1>(P, W, F); fluxAll<2>(P, W, F);
+  emfAll<0>(P, W, E); emfAll<1>(P, W, E); emfAll<2>(P, W, E);
+  double invDt = 0.0;
+  for (int k = gw; k <= kN; ++k)
+    for (int j = gw; j <= jN; ++j)
+      for (int i = gw; i <= iN; ++i) {
+        const double v = update_cell<false>(P, U, Unew, F, E, i, j, k, dt);
+        if (v > invDt) invDt = v;
+      }
+  return invDt;
+}
+
+
+extern "C" double emu_mhd3d_step_generic(const char* ini, const double* Uin, double dt, double* Unew) {
+  return emu_mhd3d_step_generic_impl(ini, Uin, dt, Unew);
+}

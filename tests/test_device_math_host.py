@@ -267,3 +267,37 @@ def test_whole_step_of_the_headline_configuration_vs_oracle(emu, oracle64, n, kt
     # next dt from the inverse dt reduced inside the update (seed of the running max: MHDRunBase.cpp:144)
     dt_next = p.cfl / max(inv_dt, p.smallc / min(p.dx, p.dy))
     assert abs(dt_next - oracle64.compute_dt(p, want)) < 1e-13 * dt_next
+
+
+@pytest.mark.parametrize("over,name", [
+    ({"hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hlla"}}, "HLL + HLLA"),
+    ({"hydro": {"riemannSolver": "llf"}, "MHD": {"magRiemannSolver": "llf"}}, "LLF"),
+    ({"MHD": {"magRiemannSolver": "hllf"}}, "HLLD + HLLF"),
+    ({"hydro": {"cIso": 0.4}}, "isothermal"),
+    ({"hydro": {"slope_type": 3.0}}, "27-point slopes"),
+    ({"hydro": {"slope_type": 1.0, "problem": "Rayleigh-Taylor"}, "gravity": {"static_field_y": 0.2, "static_field_z": -0.6}}, "minmod + gravity"),
+    ({"mesh": {"boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1, "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1}}, "walls"),
+])
+def test_whole_step_of_the_generic_path_vs_oracle(emu, oracle64, over, name):
+    """the separate-kernel path (k_prim, k_elec, k_trace, k_flux, k_emf, k_update instantiated with FAST = false) assembled
+    on the host from the same per-cell functions, for the solver / equation-of-state / slope / gravity / boundary variants"""
+    emu.emu_mhd3d_step_generic.argtypes = [C.c_char_p, D, C.c_double, D]
+    emu.emu_mhd3d_step_generic.restype = C.c_double
+    ini = ot3d_ini((9, 10, 8), OrszagTang={"kt": 1.0}, **over)
+    p = oracle64.params(ini)
+    U = smooth_state(p, 8)
+    oracle64.make_all_boundaries(p, U)
+    dt = oracle64.compute_dt(p, U)
+    want = np.zeros_like(U)
+    oracle64.step_no_boundaries(p, U, want, dt)
+    got = U.copy()
+    inv_dt = emu.emu_mhd3d_step_generic(ini.encode(), p64(U), dt, p64(got))
+    gw = p.ghostWidth
+    box = (slice(gw, p.ksize - gw + 1), slice(gw, p.jsize - gw + 1), slice(gw, p.isize - gw + 1))
+    inner = (slice(gw, -gw), slice(gw, -gw), slice(gw, -gw))
+    for v in range(8):
+        scale = np.abs(want[v][inner]).max() + 1e-3
+        sl = inner if v < 5 else box
+        assert (np.abs(got[v][sl] - want[v][sl]) / scale).max() < 1e-13, (name, v)
+    dt_next = p.cfl / max(inv_dt, p.smallc / min(p.dx, p.dy))
+    assert abs(dt_next - oracle64.compute_dt(p, want)) < 1e-13 * dt_next
