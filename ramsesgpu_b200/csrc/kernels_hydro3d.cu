@@ -6,6 +6,7 @@
 // Reference: HydroRunGodunov.cpp:2658-2890 (godunov_unsplit_cpu_v1, 3D), trace.h:544-661,
 // slope.h:324-427, riemann.h, HydroRunBase.cpp:386-426.  Where the reference stores qm/qp x3
 // (30 reals per cell) plus Q, this keeps 20 reals of traced state and no primitive array.
+#include "hydro_cells.cuh"
 #include "hydro_device.cuh"
 #include "kernel_common.cuh"
 #include "kernels.h"
@@ -16,9 +17,6 @@ int g_hydroTile = 1;  // run-time knob "hydro_tile": register-tiled flux+update 
 
 namespace {
 
-enum { H_R = 0, H_P, H_U, H_V, H_W, H_DX = 5, H_DY = 10, H_DZ = 15 };  // slopes: (r, p, u, v, w) each
-static_assert(H_DZ + 5 == NW_HYDRO, "hydro W layout");
-
 template <typename T>
 __global__ void __launch_bounds__(BX) k_hydro_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin,
                                                     T* __restrict__ Wp, int planes, int kbase, int k0, T dt) {
@@ -27,77 +25,9 @@ __global__ void __launch_bounds__(BX) k_hydro_trace(const __grid_constant__ KPar
   if (!tileCoords(1, P.isize - 2, 1, P.jsize - 2, i, j)) return;
   const UView<T> U = uview(Uin, P);
   const View<T> W = view(Wp, P, planes, kbase);
-  auto prim = [&](int ii, int jj, int kk, T(&q)[5]) {
-    dev::cons_to_prim_hydro(P, U(ID, ii, jj, kk), U(IP, ii, jj, kk), U(IU, ii, jj, kk), U(IV, ii, jj, kk),
-                            U(IW, ii, jj, kk), q);
-  };
-  T q[5], qxm[5], qxp[5], qym[5], qyp[5], qzm[5], qzp[5];
-  prim(i, j, k, q);
-  prim(i - 1, j, k, qxm); prim(i + 1, j, k, qxp);
-  prim(i, j - 1, k, qym); prim(i, j + 1, k, qyp);
-  prim(i, j, k - 1, qzm); prim(i, j, k + 1, qzp);
-  const T st = P.slope_type, h = T(0.5);
-  T dx_[5], dy_[5], dz_[5];
-#pragma unroll
-  for (int v = 0; v < 5; ++v) {
-    dx_[v] = h * dev::hydro_slope(st, qxm[v], q[v], qxp[v]);
-    dy_[v] = h * dev::hydro_slope(st, qym[v], q[v], qyp[v]);
-    dz_[v] = h * dev::hydro_slope(st, qzm[v], q[v], qzp[v]);
-  }
-  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
-  const T r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], g = P.gamma0;
-  const T ir = dev::rcp(r);
-  // half-step predictor, trace.h:585-600
-  const T sr0 = (-u * dx_[ID] - dx_[IU] * r) * dtdx + (-v * dy_[ID] - dy_[IV] * r) * dtdy + (-w * dz_[ID] - dz_[IW] * r) * dtdz;
-  const T su0 = (-u * dx_[IU] - dx_[IP] * ir) * dtdx + (-v * dy_[IU]) * dtdy + (-w * dz_[IU]) * dtdz;
-  const T sv0 = (-u * dx_[IV]) * dtdx + (-v * dy_[IV] - dy_[IP] * ir) * dtdy + (-w * dz_[IV]) * dtdz;
-  const T sw0 = (-u * dx_[IW]) * dtdx + (-v * dy_[IW]) * dtdy + (-w * dz_[IW] - dz_[IP] * ir) * dtdz;
-  const T sp0 = (-u * dx_[IP] - dx_[IU] * g * p) * dtdx + (-v * dy_[IP] - dy_[IV] * g * p) * dtdy + (-w * dz_[IP] - dz_[IW] * g * p) * dtdz;
-  T gpx = T(0), gpy = T(0), gpz = T(0);
-  if (P.gravity) {  // gravity predictor on the traced velocities, reference HydroRunGodunov.cpp:2705-2734
-    gpx = h * dt * P.gx; gpy = h * dt * P.gy; gpz = h * dt * P.gz;
-  }
-  W(H_R, i, j, k) = r + sr0; W(H_P, i, j, k) = p + sp0;
-  W(H_U, i, j, k) = u + su0 + gpx; W(H_V, i, j, k) = v + sv0 + gpy; W(H_W, i, j, k) = w + sw0 + gpz;
-  // slope component order in W: r, p, u, v, w  (ID, IP, IU, IV, IW)
-#pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    W(H_DX + c, i, j, k) = dx_[c];
-    W(H_DY + c, i, j, k) = dy_[c];
-    W(H_DZ + c, i, j, k) = dz_[c];
-  }
+  hydro_trace_cell(P, U, W, i, j, k, dt);
 }
 
-
-// state at a face of cell (i,j,k): W centre +/- half slope along DIR, floors (trace.h:603-660),
-// rotated so that .u is the velocity normal to the face
-template <typename T, int DIR>
-__device__ __forceinline__ dev::HState<T> hydro_face(const KParams<T>& P, const View<const T>& W, int i, int j, int k, T sgn) {
-  constexpr int S = (DIR == 0) ? H_DX : (DIR == 1) ? H_DY : H_DZ;
-  dev::HState<T> s;
-  s.r = dev::mx(P.smallr, W(H_R, i, j, k) + sgn * W(S + 0, i, j, k));
-  s.p = dev::mx(P.smallp * s.r, W(H_P, i, j, k) + sgn * W(S + 1, i, j, k));
-  const T u = W(H_U, i, j, k) + sgn * W(S + 2, i, j, k);
-  const T v = W(H_V, i, j, k) + sgn * W(S + 3, i, j, k);
-  const T w = W(H_W, i, j, k) + sgn * W(S + 4, i, j, k);
-  if (DIR == 0) { s.u = u; s.v = v; s.w = w; }
-  else if (DIR == 1) { s.u = v; s.v = u; s.w = w; }
-  else { s.u = w; s.v = v; s.w = u; }
-  return s;
-}
-
-// flux through the LOW face of cell (i,j,k) along DIR, in physical component order
-template <typename T, int DIR, int RS>
-__device__ __forceinline__ void hydro_low_flux(const KParams<T>& P, const View<const T>& W, int i, int j, int k, T (&f)[5]) {
-  const dev::HState<T> L = hydro_face<T, DIR>(P, W, i - (DIR == 0), j - (DIR == 1), k - (DIR == 2), T(1));
-  const dev::HState<T> R = hydro_face<T, DIR>(P, W, i, j, k, T(-1));
-  T fr[5];
-  dev::riemann_hydro<RS>(P, L, R, fr);
-  f[ID] = fr[ID]; f[IP] = fr[IP];
-  f[IU] = (DIR == 0) ? fr[IU] : (DIR == 1) ? fr[IV] : fr[IW];
-  f[IV] = (DIR == 1) ? fr[IU] : fr[IV];
-  f[IW] = (DIR == 2) ? fr[IU] : fr[IW];
-}
 
 // flux + conservative update + next dt, z-marching: a 32 x 4 thread block owns a column of cells and
 // walks a range of planes.  Every face flux is evaluated ONCE per tile: a thread solves the Riemann
@@ -204,30 +134,6 @@ __global__ void __launch_bounds__(128) k_hydro_flux_update(const __grid_constant
 // hence bitwise identical and conservative.  3.4 Riemann problems per updated cell.
 // ------------------------------------------------------------------------------------------------
 constexpr int HR = 8;  // rows of the thread block
-
-template <typename T, int DIR>
-__device__ __forceinline__ dev::HState<T> face_from_regs(const KParams<T>& P, const T (&w)[NW_HYDRO], T sgn) {
-  constexpr int S = (DIR == 0) ? H_DX : (DIR == 1) ? H_DY : H_DZ;
-  dev::HState<T> s;
-  s.r = dev::mx(P.smallr, w[H_R] + sgn * w[S + 0]);
-  s.p = dev::mx(P.smallp * s.r, w[H_P] + sgn * w[S + 1]);
-  const T u = w[H_U] + sgn * w[S + 2], v = w[H_V] + sgn * w[S + 3], ww = w[H_W] + sgn * w[S + 4];
-  if (DIR == 0) { s.u = u; s.v = v; s.w = ww; }
-  else if (DIR == 1) { s.u = v; s.v = u; s.w = ww; }
-  else { s.u = ww; s.v = v; s.w = u; }
-  return s;
-}
-
-// Riemann flux of a face normal to DIR from its rotated left/right states, in physical component order
-template <typename T, int DIR, int RS>
-__device__ __forceinline__ void face_flux(const KParams<T>& P, const dev::HState<T>& L, const dev::HState<T>& R, T (&f)[5]) {
-  T fr[5];
-  dev::riemann_hydro<RS>(P, L, R, fr);
-  f[ID] = fr[ID]; f[IP] = fr[IP];
-  f[IU] = (DIR == 0) ? fr[IU] : (DIR == 1) ? fr[IV] : fr[IW];
-  f[IV] = (DIR == 1) ? fr[IU] : fr[IV];
-  f[IW] = (DIR == 2) ? fr[IU] : fr[IW];
-}
 
 template <typename T, int RS>
 __global__ void __launch_bounds__(32 * HR) k_hydro_flux_update_tile(const __grid_constant__ KParams<T> P,

@@ -7,6 +7,7 @@
 #include "mhd_device.cuh"
 #include "hydro_device.cuh"
 #include "mhd_cells.cuh"
+#include "hydro_cells.cuh"
 
 #include <vector>
 
@@ -285,3 +286,47 @@ double emu_mhd3d_step_generic_impl(const char* ini, const double* Uin, double dt
 extern "C" double emu_mhd3d_step_generic(const char* ini, const double* Uin, double dt, double* Unew) {
   return emu_mhd3d_step_generic_impl(ini, Uin, dt, Unew);
 }
+
+// One whole 3D hydro step (FP64 or FP32) from a ghost-filled state with the product's per-cell functions
+// (hydro_cells.cuh: trace -> W, face states, Riemann fluxes) and the update of k_hydro_flux_update (reference
+// summation order, gravity source term, inverse dt of the new state).  Unew holds a copy of Uold on entry.
+template <typename T>
+static double hydroStep(const char* ini, const T* Uin, T dt, T* Unew) {
+  const KParams<T> P = paramsOf<T>(ini);
+  const int is = P.isize, js = P.jsize, ks = P.ksize, gw = P.gw;
+  const size_t ncell = (size_t)is * js * ks;
+  std::vector<T> Ws(ncell * NW_HYDRO, T(0));
+  const HostView<const T> U{Uin, is, js, ks};
+  const HostView<T> W{Ws.data(), is, js, ks};
+  for (int k = 1; k < ks - 1; ++k)
+    for (int j = 1; j < js - 1; ++j)
+      for (int i = 1; i < is - 1; ++i) hydro_trace_cell(P, U, W, i, j, k, dt);
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  double invDt = 0.0;
+  for (int k = gw; k < ks - gw; ++k)
+    for (int j = gw; j < js - gw; ++j)
+      for (int i = gw; i < is - gw; ++i) {
+        T fxl[5], fyl[5], fzl[5], fxh[5], fyh[5], fzh[5], un[5];
+        hydro_low_flux<T, 0, -1>(P, W, i, j, k, fxl); hydro_low_flux<T, 0, -1>(P, W, i + 1, j, k, fxh);
+        hydro_low_flux<T, 1, -1>(P, W, i, j, k, fyl); hydro_low_flux<T, 1, -1>(P, W, i, j + 1, k, fyh);
+        hydro_low_flux<T, 2, -1>(P, W, i, j, k, fzl); hydro_low_flux<T, 2, -1>(P, W, i, j, k + 1, fzh);
+        for (int v = 0; v < 5; ++v) {
+          T s = U(v, i, j, k);
+          s += fxl[v] * dtdx; s += fyl[v] * dtdy; s += fzl[v] * dtdz;
+          s -= fxh[v] * dtdx; s -= fyh[v] * dtdy; s -= fzh[v] * dtdz;
+          un[v] = s;
+        }
+        if (P.gravity) {
+          const T hdt = T(0.5) * dt, rs = U(ID, i, j, k) + un[ID];
+          un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * P.gz * rs;
+        }
+        for (int v = 0; v < 5; ++v) Unew[((size_t)v * ks + k) * js * is + (size_t)j * is + i] = un[v];
+        T q[5];
+        const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], un[IW], q);
+        const double d = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz;
+        if (d > invDt) invDt = d;
+      }
+  return invDt;
+}
+extern "C" double emu_hydro3d_step(const char* ini, const double* U, double dt, double* Unew) { return hydroStep<double>(ini, U, dt, Unew); }
+extern "C" double emu_hydro3d_step_f32(const char* ini, const float* U, float dt, float* Unew) { return hydroStep<float>(ini, U, dt, Unew); }

@@ -301,3 +301,35 @@ def test_whole_step_of_the_generic_path_vs_oracle(emu, oracle64, over, name):
         assert (np.abs(got[v][sl] - want[v][sl]) / scale).max() < 1e-13, (name, v)
     dt_next = p.cfl / max(inv_dt, p.smallc / min(p.dx, p.dy))
     assert abs(dt_next - oracle64.compute_dt(p, want)) < 1e-13 * dt_next
+
+
+@pytest.mark.parametrize("solver,over,name", [
+    ("approx", {}, "two-shock solver"), ("hll", {"hydro": {"slope_type": 1.0}}, "HLL minmod"), ("hllc", {}, "HLLC"),
+    ("hllc", {"hydro": {"problem": "Rayleigh-Taylor"}, "gravity": {"static_field_x": 0.1, "static_field_z": -0.4}}, "HLLC + gravity"),
+])
+def test_whole_hydro_step_vs_oracle(emu, oracle64, oracle32, solver, over, name):
+    """3D hydro (BASELINE.json configs[2] and [4]): one step assembled on the host from hydro_cells.cuh in FP64 and FP32"""
+    emu.emu_hydro3d_step.argtypes = [C.c_char_p, D, C.c_double, D]; emu.emu_hydro3d_step.restype = C.c_double
+    emu.emu_hydro3d_step_f32.argtypes = [C.c_char_p, F, C.c_float, F]; emu.emu_hydro3d_step_f32.restype = C.c_double
+    ov = {"mesh": {"nx": 9, "ny": 7, "nz": 8, "boundary_xmin": 3, "boundary_xmax": 3, "boundary_ymin": 3, "boundary_ymax": 3,
+                   "boundary_zmin": 3, "boundary_zmax": 3}, "hydro": {"riemannSolver": solver}}
+    for k, v in over.items():
+        ov.setdefault(k, {}).update(v)
+    ini = ini_override(str(load_golden("implode3d_16_s8")["ini"]), ov)
+    for orc, dtype, fn, tol in ((oracle64, np.float64, emu.emu_hydro3d_step, 1e-13), (oracle32, np.float32, emu.emu_hydro3d_step_f32, 2e-6)):
+        p = orc.params(ini)
+        g = p.ghostWidth
+        U8 = smooth_state(type("P", (), dict(ksize=p.ksize, jsize=p.jsize, isize=p.isize, ghostWidth=g, nx=p.nx, ny=p.ny, nz=p.nz)), 9)
+        U = np.ascontiguousarray(U8[:5]).astype(dtype)
+        U[1] = (2.0 + 0.5 * (U8[2] ** 2 + U8[3] ** 2 + U8[4] ** 2) / U8[0]).astype(dtype)
+        orc.make_all_boundaries(p, U)
+        dt = orc.compute_dt(p, U)
+        want = np.zeros_like(U)
+        orc.step_no_boundaries(p, U, want, dt)
+        got = U.copy()
+        ptr = (lambda a: a.ctypes.data_as(D if dtype == np.float64 else F))
+        inv_dt = fn(ini.encode(), ptr(U), dt, ptr(got))
+        inner = (slice(None), slice(g, -g), slice(g, -g), slice(g, -g))
+        scale = np.abs(want[inner]).max(axis=(1, 2, 3), keepdims=True) + 1e-3
+        assert (np.abs(got[inner].astype(np.float64) - want[inner]) / scale).max() < tol, (name, dtype)
+        assert abs(p.cfl / inv_dt - orc.compute_dt(p, want)) < 10 * tol * dt
