@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libramsesgpu_b200.so")
+# RG_LIB_PATH: an experimental flavour built with RG_VARIANT (see build.py), for A/B timing only
+LIB_PATH = os.environ.get("RG_LIB_PATH") or os.path.join(PKG, "lib", "libramsesgpu_b200.so")
 
 
 class RgLayout(C.Structure):

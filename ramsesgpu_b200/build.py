@@ -12,8 +12,12 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-LIBDIR = os.path.join(PKG, "lib")
-OBJDIR = os.path.join(PKG, "build")
+# RG_VARIANT=<tag> builds an experimental flavour next to the product (lib_<tag>/, build_<tag>/) with the extra
+# preprocessor defines of RG_VARIANT_DEFINES (e.g. "-DRG_EXP_INT_CLAMP -DRG_EXP_LIMITER_V1"); load it with
+# RG_LIB_PATH=ramsesgpu_b200/lib_<tag>/libramsesgpu_b200.so for A/B timing.  Unset: the product, as always.
+VARIANT = os.environ.get("RG_VARIANT", "")
+LIBDIR = os.path.join(PKG, "lib" + ("_" + VARIANT if VARIANT else ""))
+OBJDIR = os.path.join(PKG, "build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(LIBDIR, "libramsesgpu_b200.so")
 MAIN = os.path.join(LIBDIR, "ramsesgpu_b200_main")
 
@@ -21,6 +25,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 CUFLAGS = ["--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if VARIANT:
+    COMMON = COMMON + os.environ.get("RG_VARIANT_DEFINES", "").split()
 
 
 def _sources():

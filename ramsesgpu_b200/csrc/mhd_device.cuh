@@ -70,6 +70,32 @@ __device__ __forceinline__ double ab(double a) { return fabs(a); }
 __device__ __forceinline__ float ab(float a) { return fabsf(a); }
 template <typename T> __device__ __forceinline__ T max4(T a, T b, T c, T d) { return mx(mx(a, b), mx(c, d)); }
 template <typename T> __device__ __forceinline__ T min4(T a, T b, T c, T d) { return mn(mn(a, b), mn(c, d)); }
+// clamps at zero and the guard in front of a square root.  Default: compare-select on the FP64 pipe (DSETP + 2 FSEL).
+// RG_EXP_INT_CLAMP (experiment, off by default; tools/microbench/select_variants.cu, profiles/r01_select_variants_sass.txt):
+// the same decisions on the integer pipe -- a sign-bit mask for the clamps (min0 keeps a -0.0), one integer compare of
+// the high words for the guard (threshold 2^-996 instead of 1e-300: both only keep rsq() away from 0 and negatives).
+#if defined(RG_EXP_INT_CLAMP)
+__device__ __forceinline__ double min0(double x) {
+  const int hi = __double2hiint(x), m = hi >> 31;
+  return __hiloint2double(hi & m, __double2loint(x) & m);
+}
+__device__ __forceinline__ double max0(double x) {
+  const int hi = __double2hiint(x), m = ~(hi >> 31);
+  return __hiloint2double(hi & m, __double2loint(x) & m);
+}
+__device__ __forceinline__ double guard_tiny(double x) {
+  const int hi = __double2hiint(x);
+  const bool small = hi < 0x01b00000;  // also negative values and +0
+  return __hiloint2double(small ? 0x01b00000 : hi, small ? 0 : __double2loint(x));
+}
+#else
+__device__ __forceinline__ double min0(double x) { return mn(x, 0.0); }
+__device__ __forceinline__ double max0(double x) { return mx(x, 0.0); }
+__device__ __forceinline__ double guard_tiny(double x) { return mx(x, tiny<double>()); }
+#endif
+__device__ __forceinline__ float min0(float x) { return mn(x, 0.0f); }
+__device__ __forceinline__ float max0(float x) { return mx(x, 0.0f); }
+__device__ __forceinline__ float guard_tiny(float x) { return mx(x, tiny<float>()); }
 
 // A primitive state in the frame of the interface normal: (r, p, u=normal v, v, w, a=normal B, b, c)
 template <typename T>
@@ -95,11 +121,22 @@ __device__ __forceinline__ T limited_slope(T st, T qm, T q0, T qp) {
 __device__ __forceinline__ double half_slope(double hst, double qm, double q0, double qp) {
   const double a = q0 - qm, b = qp - q0;
   const double s = a + b;
+#if defined(RG_EXP_LIMITER_V1)
+  // experiment (off by default; tools/microbench/limiter_variants.cu): one three-way minimum of the sign-flipped terms,
+  // clamped at zero with a sign mask -- opposite signs give a negative minimum.  Same value, bit for bit.
+  const int sg = __double2hiint(s) & 0x80000000;
+  const double fa = __hiloint2double(__double2hiint(a) ^ sg, __double2loint(a)) * hst;
+  const double fb = __hiloint2double(__double2hiint(b) ^ sg, __double2loint(b)) * hst;
+  const double rr = mn(mn(fa, fb), ab(s) * 0.25);
+  const int hi = __double2hiint(rr), m = ~(hi >> 31);
+  return __hiloint2double((hi & m) | sg, __double2loint(rr) & m);
+#else
   const double m = mn(ab(a), ab(b)) * hst;
   const double c = ab(s) * 0.25;
   double r = mn(m, c);
   if ((__double2hiint(a) ^ __double2hiint(b)) < 0) r = 0.0;
   return __hiloint2double((__double2hiint(r) & 0x7fffffff) | (__double2hiint(s) & 0x80000000), __double2loint(r));
+#endif
 }
 __device__ __forceinline__ float half_slope(float hst, float qm, float q0, float qp) {
   const float a = q0 - qm, b = qp - q0;
@@ -144,7 +181,7 @@ template <typename T>
 __device__ __forceinline__ T fast_speed(T gamma, T p, T ir, T b2, T n2) {
   T c2 = gamma * p * ir;
   T d2 = T(0.5) * (b2 * ir + c2);
-  return sqr_t(d2 + sqr_t(mx(d2 * d2 - c2 * n2 * ir, tiny<T>())));
+  return sqr_t(d2 + sqr_t(guard_tiny(d2 * d2 - c2 * n2 * ir)));
 }
 
 // square of the fast speed (one sqrt less when only a max over states is needed)
@@ -152,7 +189,7 @@ template <typename T>
 __device__ __forceinline__ T fast_speed2(T gamma, T p, T ir, T b2, T n2) {
   T c2 = gamma * p * ir;
   T d2 = T(0.5) * (b2 * ir + c2);
-  return d2 + sqr_t(mx(d2 * d2 - c2 * n2 * ir, tiny<T>()));
+  return d2 + sqr_t(guard_tiny(d2 * d2 - c2 * n2 * ir));
 }
 
 // 1-D physical flux + conservative vector, reference mhd_utils.h:106-156
@@ -187,8 +224,8 @@ __device__ void riemann_hll(const KParams<T>& P, State<T> l, State<T> r, T (&flu
   T cl = fast_speed(P.gamma0, l.p, rcp(l.r), l.a * l.a + l.b * l.b + l.c * l.c, l.a * l.a);
   T cr = fast_speed(P.gamma0, r.p, rcp(r.r), r.a * r.a + r.b * r.b + r.c * r.c, r.a * r.a);
   T cm = mx(cl, cr);
-  T sl = mn(mn(l.u, r.u) - cm, T(0));
-  T sr = mx(mx(l.u, r.u) + cm, T(0));
+  T sl = min0(mn(l.u, r.u) - cm);
+  T sr = max0(mx(l.u, r.u) + cm);
   T inv = rcp(sr - sl);
 #pragma unroll
   for (int n = 0; n < 8; ++n) flux[n] = (sr * fl[n] - sl * fr[n] + sr * sl * (ur[n] - ul[n])) * inv;
@@ -362,8 +399,8 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
     const T c2 = g * S.p * ir;                                      \
     const T d2 = T(0.5) * (bb * ir + c2);                           \
     const T dd = d2 * d2, ci = c2 * ir;                             \
-    cx = d2 + sqr_t(mx(dd - ci * a2, tiny<T>()));                        \
-    cy = d2 + sqr_t(mx(dd - ci * b2_, tiny<T>()));                       \
+    cx = d2 + sqr_t(guard_tiny(dd - ci * a2));                        \
+    cy = d2 + sqr_t(guard_tiny(dd - ci * b2_));                       \
     Ptot = S.p + T(0.5) * bb;                                       \
   }
   RG_SPEEDS(LL, cxLL, cyLL, PtotLL)
@@ -417,8 +454,8 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
   const T calfB = mx(max4(cbLLy, cbLL, cbRLy, cbRL), P.smallc);
   const T calfT = mx(max4(cbLRy, cbLR, cbRRy, cbRR), P.smallc);
 
-  const T SAL = mn(ustar - calfL, T(0)), SAR = mx(ustar + calfR, T(0));
-  const T SAB = mn(vstar - calfB, T(0)), SAT = mx(vstar + calfT, T(0));
+  const T SAL = min0(ustar - calfL), SAR = max0(ustar + calfR);
+  const T SAB = min0(vstar - calfB), SAT = max0(vstar + calfT);
   const T iA = rcp(SAR - SAL), iB = rcp(SAT - SAB);
 
   // region selection: the reference's integer masks (riemann_mhd.h:759-787) are equivalent to this
@@ -462,10 +499,10 @@ __device__ T mag_riemann2d_hll(const KParams<T>& P, const Corner<T> (&q)[4], boo
   }
   T cxm = max4(cx[0], cx[1], cx[2], cx[3]), cym = max4(cy[0], cy[1], cy[2], cy[3]);
   if (alfven) { cxm = mx(cxm, P.smallc); cym = mx(cym, P.smallc); }
-  const T SL = mn(min4(q[0].u, q[1].u, q[2].u, q[3].u) - cxm, T(0));
-  const T SR = mx(max4(q[0].u, q[1].u, q[2].u, q[3].u) + cxm, T(0));
-  const T SB = mn(min4(q[0].v, q[1].v, q[2].v, q[3].v) - cym, T(0));
-  const T ST = mx(max4(q[0].v, q[1].v, q[2].v, q[3].v) + cym, T(0));
+  const T SL = min0(min4(q[0].u, q[1].u, q[2].u, q[3].u) - cxm);
+  const T SR = max0(max4(q[0].u, q[1].u, q[2].u, q[3].u) + cxm);
+  const T SB = min0(min4(q[0].v, q[1].v, q[2].v, q[3].v) - cym);
+  const T ST = max0(max4(q[0].v, q[1].v, q[2].v, q[3].v) + cym);
   T e[4];
 #pragma unroll
   for (int s = 0; s < 4; ++s) e[s] = q[s].u * q[s].b - q[s].v * q[s].a;

@@ -19,11 +19,16 @@ D = C.POINTER(C.c_double)
 F = C.POINTER(C.c_float)
 
 
-@pytest.fixture(scope="module")
-def emu():
+# the product as built, and the experimental formulations kept behind macros for the next A/B on the GPU
+# (RG_EXP_INT_CLAMP: clamps / sqrt guards on the integer pipe; RG_EXP_LIMITER_V1: sign-flipped three-way minimum)
+FLAVOURS = {"product": [], "experiments": ["-DRG_EXP_INT_CLAMP", "-DRG_EXP_LIMITER_V1"]}
+
+
+@pytest.fixture(scope="module", params=list(FLAVOURS))
+def emu(request):
     out = os.path.join(HERE, "_build")
     os.makedirs(out, exist_ok=True)
-    lib = os.path.join(out, "libdevice_math_host.so")
+    lib = os.path.join(out, "libdevice_math_host_%s.so" % request.param)
     csrc = os.path.join(ROOT, "ramsesgpu_b200", "csrc")
     srcs = [os.path.join(HERE, "device_math_host.cpp"), os.path.join(csrc, "config_map.cpp"), os.path.join(csrc, "params.cpp")]
     deps = srcs + [os.path.join(HERE, "cuda_host_shim.h"), os.path.join(csrc, "mhd_device.cuh"), os.path.join(csrc, "hydro_device.cuh")]
@@ -31,7 +36,7 @@ def emu():
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         # -ffp-contract=fast: let the host compiler fuse multiply-adds like nvcc does
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-fPIC", "-shared", "-ffp-contract=fast", "-I", csrc, "-I", HERE,
-                               "-I", cuda_inc] + srcs + ["-o", lib])
+                               "-I", cuda_inc] + FLAVOURS[request.param] + srcs + ["-o", lib])
     L = C.CDLL(lib)
     L.emu_riemann_mhd.argtypes = [C.c_char_p, C.c_int, D, D, D]
     L.emu_compute_emf.argtypes = [C.c_char_p, C.c_int, C.c_int, D, D, D]

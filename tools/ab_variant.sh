@@ -1,0 +1,23 @@
+#!/bin/bash
+# A/B of an experimental flavour of the library against the product on the bench workload.
+#   here (CPU box, cross-compile):   bash tools/ab_variant.sh build
+#   on the GPU box:                  gpurun --timeout 300 -- 'bash tools/ab_variant.sh run > gpurun_out/ab_variant.log 2>&1'
+# The flavour is the product source with RG_VARIANT_DEFINES (default: the two formulations validated against the
+# oracle on the host by tests/test_device_math_host.py[experiments]: clamps / sqrt guards on the integer pipe and the
+# sign-flipped three-way limiter).  Static SASS, r01: fused update 2992 -> 2904 instructions (DSETP 117 -> 100),
+# fused trace 2120 -> 2088 (FP64-pipe 580 -> 552), registers unchanged (125 / 168), no spills.
+set -eu
+cd "$(dirname "$0")/.."
+DEFS=${RG_VARIANT_DEFINES:-"-DRG_EXP_INT_CLAMP -DRG_EXP_LIMITER_V1"}
+case "${1:-run}" in
+  build)
+    RG_VARIANT=exp RG_VARIANT_DEFINES="$DEFS" python -m ramsesgpu_b200.build
+    ;;
+  run)
+    for rep in 1 2; do
+      echo "== product"; python bench.py --no-cpu-baseline --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
+      echo "== variant"; RG_LIB_PATH=ramsesgpu_b200/lib_exp/libramsesgpu_b200.so python bench.py --no-cpu-baseline --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
+    done
+    echo "== parity of the variant"; RG_LIB_PATH=ramsesgpu_b200/lib_exp/libramsesgpu_b200.so python -m pytest tests/test_gpu_mhd3d.py tests/test_gpu_mri.py -q -m gpu 2>&1 | tail -3
+    ;;
+esac
