@@ -27,7 +27,7 @@ int fail(int code, const std::string& msg) {
 int classify(const std::exception& e) {
   const std::string m = e.what();
   if (m.find("no CPU fallback") != std::string::npos) return RG_ERR_NO_DEVICE;
-  if (m.find("CUDA error") != std::string::npos) return RG_ERR_CUDA;
+  if (m.find("CUDA error") != std::string::npos || m.find("CUDA kernel launch") != std::string::npos) return RG_ERR_CUDA;
   if (m.find("NCCL") != std::string::npos) return RG_ERR_NCCL;
   if (m.find("not available") != std::string::npos) return RG_ERR_UNSUPPORTED;
   return RG_ERR_INVALID;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <stdexcept>
+#include <string>
 
 #include "kernels.h"
 #include "mhd_device.cuh"
@@ -13,6 +15,34 @@ namespace rg {
 extern unsigned long long g_launches;  // kernels launched by this library
 extern int g_hydroTile;                // run-time knob "hydro_tile" (kernels_hydro3d.cu)
 extern int g_tileX;                    // run-time knob "tile_x" (32 | 64 | 128); tile_y = BX / tile_x
+
+// Every launch wrapper calls this right after its <<<>>>: counts the launch(es) and turns a failed launch
+// (no kernel image for the device, too much dynamic shared memory, a bad grid) into an exception instead
+// of stale results behind an RG_OK (cudaGetLastError does not synchronise).
+inline void launched(int n = 1) {
+  g_launches += (unsigned long long)n;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string("CUDA kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// Per-device state (function attributes, SM count) is cached per device id: a process may hold handles on several
+// devices (rg_create_distributed takes a device argument)
+constexpr int MAX_DEVICES = 64;
+inline int currentDevice() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < MAX_DEVICES) ? d : 0;
+}
+inline int smCount() {
+  static int n[MAX_DEVICES] = {0};
+  const int d = currentDevice();
+  if (n[d] == 0) {
+    cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+    if (n[d] <= 0) n[d] = 148;
+  }
+  return n[d];
+}
 
 namespace {
 

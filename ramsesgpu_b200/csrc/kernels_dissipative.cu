@@ -235,27 +235,27 @@ __global__ void __launch_bounds__(BX) k_visc_update(const __grid_constant__ KPar
 template <typename T>
 void DissKernels<T>::resistEmf(const KParams<T>& P, const T* U, T* D, cudaStream_t s) {
   k_res_emf<T><<<gridFor(P.nx + 1, P.ny + 1, P.nz + 1), blockShape(), 0, s>>>(P, U, D);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void DissKernels<T>::ctUpdate(const KParams<T>& P, T* U, const T* D, T dt, cudaStream_t s) {
   k_res_ct<T><<<gridFor(P.nx + 1, P.ny + 1, P.nz + 1), blockShape(), 0, s>>>(P, U, D, dt);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void DissKernels<T>::resistEnergy(const KParams<T>& P, T* U, T dt, cudaStream_t s) {
   k_res_energy<T><<<gridFor(P.nx, P.ny, P.nz), blockShape(), 0, s>>>(P, U, dt);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void DissKernels<T>::viscFlux(const KParams<T>& P, const T* U, T* D, T dt, cudaStream_t s) {
   k_visc_flux<T><<<gridFor(P.nx + 1, P.ny + 1, P.nz + 1), blockShape(), 0, s>>>(P, U, D, dt);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void DissKernels<T>::viscUpdate(const KParams<T>& P, T* U, const T* D, cudaStream_t s) {
   k_visc_update<T><<<gridFor(P.nx, P.ny, P.nz), blockShape(), 0, s>>>(P, U, D);
-  ++g_launches;
+  launched();
 }
 
 template struct DissKernels<double>;

@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(HB) k_history_sums(const __grid_constant__ KPa
 template <typename T>
 void HistoryKernels<T>::columnSums(const KParams<T>& P, const T* U, double* partial, int nBlocks, cudaStream_t s) {
   k_history_columns<T><<<nBlocks, HB, 0, s>>>(P, U, partial);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void HistoryKernels<T>::sums(const KParams<T>& P, const T* U, const double* meanUV, double* partial, int nBlocks,
                              cudaStream_t s) {
   k_history_sums<T><<<nBlocks, HB, 0, s>>>(P, U, meanUV, partial);
-  ++g_launches;
+  launched();
 }
 
 template struct HistoryKernels<double>;

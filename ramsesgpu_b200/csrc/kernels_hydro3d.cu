@@ -286,7 +286,7 @@ template <typename T>
 void HydroKernels<T>::trace(const KParams<T>& P, const T* U, T* W, int planes, int kbase, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
   k_hydro_trace<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), blockShape(), 0, s>>>(P, U, W, planes, kbase, k0, dt);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, const T* W, int planes, int kbase, int k0,
@@ -303,7 +303,7 @@ void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, co
     }
     const int ng = 2 * P.gw, cells = ng * P.isize + ng * (P.jsize - ng);
     k_hydro_copy_ghosts<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
-    g_launches += 2;
+    launched(2);
     return;
   }
   // z ranges of about 32 planes (one redundant z face per range), at least a few waves of blocks
@@ -316,17 +316,17 @@ void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, co
     case RS_APPROX: k_hydro_flux_update<T, RS_APPROX><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
     default: k_hydro_flux_update<T, -1><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
   }
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void HydroKernels<T>::computeInvDt(const KParams<T>& P, const T* U, unsigned long long* slots, cudaStream_t s) {
   k_hydro_invdt<T><<<gridFor(P.nx, P.ny, P.nz), blockShape(), 0, s>>>(P, U, slots);
-  ++g_launches;
+  launched();
 }
 template <typename T>
 void HydroKernels<T>::probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s) {
   k_probe_riemann_hydro<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, ql, qr, flux);
-  ++g_launches;
+  launched();
 }
 
 template struct HydroKernels<double>;

@@ -229,7 +229,7 @@ void Mhd2dKernels<T>::step(const KParams<T>& P, const T* Uold, T* Unew, T* Q, T*
   k2_trace<T><<<gridFor(n, m, 1), blockShape(), 0, s>>>(P, Uold, Q, W, dt);
   k2_flux_emf<T><<<gridFor(P.nx + 1, P.ny + 1, 1), blockShape(), 0, s>>>(P, W, F, E);
   k2_update<T><<<gridFor(P.isize, P.jsize, 1), blockShape(), 0, s>>>(P, Uold, Unew, F, E, dt, slots);
-  g_launches += 4;
+  launched(4);
 }
 
 template struct Mhd2dKernels<double>;

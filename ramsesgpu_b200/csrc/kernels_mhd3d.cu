@@ -853,7 +853,7 @@ void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, i
   dim3 block(32, 8, 1);
   dim3 grid((sizes[d1] + 31) / 32, (sizes[d2] + 7) / 8, 2 * P.gw);
   k_boundary<T><<<grid, block, 0, s>>>(P, U, dir, bcLo, bcHi, skipLo ? 1 : 0, skipHi ? 1 : 0, kLo, kHi);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -861,20 +861,20 @@ void MhdKernels<T>::jetInflow(const KParams<T>& P, T* U, cudaStream_t s) {
   if (!P.jet || P.ijet <= 0) return;
   const dim3 grid((P.ijet + 31) / 32, P.dim == 2 ? P.gw : P.ijet, P.dim == 2 ? 1 : P.gw);
   k_jet<T><<<grid, 32, 0, s>>>(P, U);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
 void MhdKernels<T>::computeInvDt(const KParams<T>& P, const T* U, unsigned long long* d, cudaStream_t s) {
   k_invdt<T><<<gridFor(P.nx, P.ny, P.dim == 3 ? P.nz : 1), blockShape(), 0, s>>>(P, U, d);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
 void MhdKernels<T>::prim(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
   k_prim<T><<<gridFor(P.isize - 1, P.jsize - 1, k1 - k0), blockShape(), 0, s>>>(P, U, sc.Q, sc.planes, sc.kbase, k0, dt);
-  ++g_launches;
+  launched();
 }
 
 // MINB dispatch: FP64 kernels are compiled for several occupancy targets (register caps), picked at
@@ -902,7 +902,7 @@ template <typename T>
 void MhdKernels<T>::elec(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   k_elec<T><<<gridFor(P.isize - 2, P.jsize - 2, k1 - k0), blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.planes, sc.kbase, k0);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -912,13 +912,13 @@ void MhdKernels<T>::trace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int
   const dim3 g = gridFor(n, m, k1 - k0);
   if (P.slope_type == T(3)) {  // 27-point slopes: their own instantiation of the generic kernel
     k_trace<T, 4, false, true><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt);
-    ++g_launches;
+    launched();
     return;
   }
 #define RG_L(M, FA) k_trace<T, M, FA><<<g, blockShape(), 0, s>>>(P, U, sc.Q, sc.EL, sc.W, sc.planes, sc.kbase, k0, dt)
   RG_MINB_SWITCH(T, g_traceMinB, RG_L, 4)
 #undef RG_L
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -931,7 +931,7 @@ void MhdKernels<T>::flux(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, 
   k_flux<T, 2, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.F, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_fluxMinB, RG_L, 6)
 #undef RG_L
-  g_launches += 3;
+  launched(3);
 }
 
 template <typename T>
@@ -944,7 +944,7 @@ void MhdKernels<T>::emf(const KParams<T>& P, MhdScratch<T> sc, int k0, int k1, c
   k_emf<T, 0, M, FA><<<g, blockShape(), 0, s>>>(P, sc.W, sc.E, sc.planes, sc.kbase, k0)
   RG_MINB_SWITCH(T, g_emfMinB, RG_L, 6)
 #undef RG_L
-  g_launches += 3;
+  launched(3);
 }
 
 template <typename T>
@@ -955,7 +955,7 @@ void MhdKernels<T>::update(const KParams<T>& P, const T* Uold, T* Unew, MhdScrat
 #define RG_L(M, FA) k_update<T, M, FA><<<g, blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes, sc.kbase, k0, dt, d)
   RG_MINB_SWITCH(T, g_updateMinB, RG_L, 8)
 #undef RG_L
-  ++g_launches;
+  launched();
 }
 
 // ---- fused path ---------------------------------------------------------------------------------
@@ -968,7 +968,10 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   // (rotating frame, isothermal, other Riemann solvers) otherwise
   if (sizeof(T) != 8 || P.dim != 3) return false;
   if (P.slope_type == T(3)) return false;  // 27-point slopes: separate prim / elec / trace kernels
-  static int ok = -1;
+  static int okDev[MAX_DEVICES];
+  static bool init = false;
+  if (!init) { for (int d = 0; d < MAX_DEVICES; ++d) okDev[d] = -1; init = true; }
+  int& ok = okDev[currentDevice()];
   if (ok < 0)
     ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<8>::SMEM) == cudaSuccess &&
@@ -1006,17 +1009,11 @@ static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T
 template <typename T>
 void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
-  static int nSM = 0;
-  if (nSM == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
-    if (nSM <= 0) nSM = 148;
-  }
+  const int nSM = smCount();
   if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
   else if (g_traceQY == 12) launchFusedTrace<T, TraceTileT<12>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -1033,7 +1030,8 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   if (!tma::encodeTile4D(&map, sc.W, (int)sizeof(T), P.isize, P.jsize, sc.planes, NW_MHD, C::WX, C::WY)) return;
   static_assert(sizeof(CUtensorMap) <= sizeof(sc.mapW), "tensor map storage");
   memcpy(sc.mapW, &map, sizeof(map));
-  static bool attrSet = false;
+  static bool attrSetDev[MAX_DEVICES] = {false};
+  bool& attrSet = attrSetDev[currentDevice()];
   if (!attrSet) {
     if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
         cudaSuccess) {
@@ -1050,13 +1048,7 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
                                        int kb, T dt, unsigned long long* d, cudaStream_t s) {
   typedef typename FusedSel<T>::Cfg C;
   if (kb <= ka) return;
-  static int nSM = 0;
-  if (nSM == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
-    if (nSM <= 0) nSM = 148;
-  }
+  const int nSM = smCount();
   // tiles of TW x TH cells over the (nx+1) x (ny+1) update box; the ghost-face column/row is folded
   // into the last tile when it would otherwise open a tile of its own
   const int ntx = std::max(1, (P.nx + C::TW - 1) / C::TW), nty = std::max(1, (P.ny + C::TH - 1) / C::TH);
@@ -1077,7 +1069,7 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
   CUtensorMap map;
   memcpy(&map, sc.mapW, sizeof(map));
   k_fused_flux_emf_update<T, C><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -1085,7 +1077,7 @@ void MhdKernels<T>::copyOutsideBox(const KParams<T>& P, const T* Uold, T* Unew, 
   if (k1 <= k0) return;
   const int ng = 2 * P.gw - 1, cells = ng * P.isize + ng * (P.jsize - ng);
   k_copy_outside_box<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -1095,7 +1087,7 @@ void MhdKernels<T>::updateRotating(const KParams<T>& P, const T* Uold, T* Unew, 
   ShearShift<T> sh{shearEnabled, jplus, frac};
   k_update_rot<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, sc.F, sc.E, sc.planes,
                                                                               sc.kbase, k0, dt, sh, d);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
@@ -1104,27 +1096,27 @@ void MhdKernels<T>::shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, cu
   const int per = 2 * P.gw, rows = 128 / per;
   dim3 grid((P.ny + rows - 1) / rows, P.ksize, 1);
   k_shear_ghosts<T><<<grid, 128, 0, s>>>(P, U, sh);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
 void MhdKernels<T>::copyPlanes(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   k_copy_planes<T><<<gridFor(P.isize, P.jsize, k1 - k0), blockShape(), 0, s>>>(P, Uold, Unew, k0);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
 void MhdKernels<T>::probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s) {
   k_probe_riemann<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, ql, qr, flux);
-  ++g_launches;
+  launched();
 }
 
 template <typename T>
 void MhdKernels<T>::probeEmf(const KParams<T>& P, int n, int emfDir, const T* qEdge, const T* xPos, T* emf,
                              cudaStream_t s) {
   k_probe_emf<T><<<(n + 127) / 128, 128, 0, s>>>(P, n, emfDir, qEdge, xPos, emf);
-  ++g_launches;
+  launched();
 }
 
 template struct MhdKernels<double>;

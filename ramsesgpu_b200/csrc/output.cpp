@@ -101,8 +101,8 @@ void writeRestartMeta(const std::string& vti, const RestartMeta& m) {
   std::FILE* f = std::fopen((vti + ".meta").c_str(), "w");
   if (!f) return;
   // %a: exact hexadecimal floats, the decimal values are for the reader's eyes only
-  std::fprintf(f, "nStep %d\ntotalTime %a\ndt %a\ndtNext %a\n# totalTime = %.17g, dt = %.17g, dtNext = %.17g\n", m.nStep,
-               m.totalTime, m.dt, m.dtNext, m.totalTime, m.dt, m.dtNext);
+  std::fprintf(f, "nStep %d\ntotalTime %a\ndt %a\ndtNext %a\nrank %d\nnranks %d\nkOffset %d\n# totalTime = %.17g, dt = %.17g, dtNext = %.17g\n",
+               m.nStep, m.totalTime, m.dt, m.dtNext, m.rank, m.nranks, m.kOffset, m.totalTime, m.dt, m.dtNext);
   std::fclose(f);
 }
 
@@ -116,13 +116,33 @@ bool readRestartMeta(const std::string& vti, RestartMeta* m) {
     else if (!std::strcmp(key, "totalTime")) { m->totalTime = std::strtod(val, nullptr); ++got; }
     else if (!std::strcmp(key, "dt")) { m->dt = std::strtod(val, nullptr); ++got; }
     else if (!std::strcmp(key, "dtNext")) { m->dtNext = std::strtod(val, nullptr); }
+    else if (!std::strcmp(key, "rank")) { m->rank = std::atoi(val); }
+    else if (!std::strcmp(key, "nranks")) { m->nranks = std::atoi(val); }
+    else if (!std::strcmp(key, "kOffset")) { m->kOffset = std::atoi(val); }
   }
   std::fclose(f);
   return got == 3;
 }
 
+std::string restartSlabName(const std::string& name, int rank, int nranks) {
+  if (nranks <= 1) return name;
+  char tag[32];
+  std::snprintf(tag, sizeof tag, "_rank%04d", rank);
+  const size_t r = name.find("_rank");
+  if (r != std::string::npos && r + 9 <= name.size()) {
+    bool digits = true;
+    for (size_t q = r + 5; q < r + 9; ++q) digits = digits && name[q] >= '0' && name[q] <= '9';
+    if (digits) return name.substr(0, r) + tag + name.substr(r + 9);
+  }
+  // mono-domain name <prefix>_<step>.vti: the tag goes in front of the step suffix
+  const size_t dot = name.rfind(".vti");
+  size_t us = (dot == std::string::npos) ? std::string::npos : name.rfind('_', dot);
+  if (us == std::string::npos) return name + tag;
+  return name.substr(0, us) + tag + name.substr(us);
+}
+
 template <typename T>
-bool readVti(const std::string& path, const Layout& L, T* U, bool* ghostIncluded, std::string* msg) {
+bool readVti(const std::string& path, const Layout& L, T* U, bool* ghostIncluded, std::string* msg, bool* global) {
   std::ifstream in(path.c_str(), std::ios::in | std::ios::binary);
   if (!in) { if (msg) *msg = "cannot open restart file '" + path + "'"; return false; }
   std::string header, line;
@@ -144,21 +164,27 @@ bool readVti(const std::string& path, const Layout& L, T* U, bool* ghostIncluded
   const int nx = e[1] + 1, ny = e[3] + 1, nz = e[5] + 1;
   const int gw = L.ghostWidth, kd = (L.dim == 2) ? 1 : L.ksize;
   int g;
+  bool wholeGrid = false;  // inner cells of the global grid: this rank takes its planes
   if (nx == L.isize && ny == L.jsize && nz == kd) g = 0;
   else if (nx == L.isize - 2 * gw && ny == L.jsize - 2 * gw && nz == ((L.dim == 2) ? 1 : L.ksize - 2 * gw)) g = gw;
+  else if (L.nranks > 1 && nx == L.isize - 2 * gw && ny == L.jsize - 2 * gw && nz == L.nz) { g = gw; wholeGrid = true; }
   else { if (msg) *msg = "'" + path + "': grid size does not match the run"; return false; }
   if (ghostIncluded) *ghostIncluded = (g == 0);
+  if (global) *global = wholeGrid;
   const int k0 = (L.dim == 2) ? 0 : g;
+  const int kFirst = wholeGrid ? L.kOffset : 0, kCount = wholeGrid ? L.nzLocal : nz;
   const size_t plane = (size_t)L.isize * L.jsize, comp = plane * L.ksize, n = (size_t)nx * ny * nz;
   for (int v = 0; v < L.nvar; ++v) {
     uint32_t nbytes = 0;
     in.read(reinterpret_cast<char*>(&nbytes), sizeof nbytes);
     if (!in || nbytes != (uint32_t)(n * sizeof(T))) { if (msg) *msg = "'" + path + "': truncated or wrong variable count"; return false; }
-    for (int k = 0; k < nz; ++k)
+    if (kFirst > 0) in.seekg((std::streamoff)kFirst * ny * nx * (std::streamoff)sizeof(T), std::ios::cur);
+    for (int k = 0; k < kCount; ++k)
       for (int j = 0; j < ny; ++j) {
         T* dst = U + (size_t)v * comp + (size_t)(k + k0) * plane + (size_t)(j + g) * L.isize + g;
         in.read(reinterpret_cast<char*>(dst), (std::streamsize)nx * sizeof(T));
       }
+    if (nz - kFirst - kCount > 0) in.seekg((std::streamoff)(nz - kFirst - kCount) * ny * nx * (std::streamoff)sizeof(T), std::ios::cur);
     if (!in) { if (msg) *msg = "'" + path + "': truncated"; return false; }
   }
   return true;
@@ -176,8 +202,8 @@ void writeOutputs(const RunParams& rp, const Layout& L, const T* U, int nStep) {
 
 template void writeVti<double>(const std::string&, const Layout&, const double*, bool);
 template void writeVti<float>(const std::string&, const Layout&, const float*, bool);
-template bool readVti<double>(const std::string&, const Layout&, double*, bool*, std::string*);
-template bool readVti<float>(const std::string&, const Layout&, float*, bool*, std::string*);
+template bool readVti<double>(const std::string&, const Layout&, double*, bool*, std::string*, bool*);
+template bool readVti<float>(const std::string&, const Layout&, float*, bool*, std::string*, bool*);
 template void writeXsm<double>(const std::string&, const Layout&, const double*, int);
 template void writeXsm<float>(const std::string&, const Layout&, const float*, int);
 template void writeOutputs<double>(const RunParams&, const Layout&, const double*, int);

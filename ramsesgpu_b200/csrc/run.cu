@@ -191,17 +191,30 @@ class RunImpl final : public Run {
     int startStep = 0;
     double startTime = 0.0;
     if (rp_.restart) {  // reference MHDRunBase.cpp:1234-1282: reload a dump instead of the problem's initial condition
-      std::string path = rp_.outputDir;
-      if (!path.empty() && path.back() != '/') path += "/";
-      path += rp_.restartFilename;
+      // variants of the reference's restart that are not built fail loudly
+      if (cfg_.getBool("run", "restart_upscale", false))
+        throw std::runtime_error("restart_upscale (restart from a half-resolution dump) is not available in this build");
+      std::string dir = rp_.outputDir;
+      if (!dir.empty() && dir.back() != '/') dir += "/";
+      // every rank resumes from ITS slab's dump (<prefix>_rankNNNN_<step>.vti, the naming of output()); when that
+      // file does not exist the name is taken as a dump of the global grid, of which the rank reads its planes
+      std::string path = dir + restartSlabName(rp_.restartFilename, rank_, nranks_);
+      if (nranks_ > 1 && !std::ifstream(path.c_str()).good()) path = dir + rp_.restartFilename;
       h.assign(elems_, T(0));
       RestartMeta meta;
-      bool ghosts = false;
-      if (!readVti<T>(path, layout(), h.data(), &ghosts, &msg)) throw std::runtime_error(msg);
+      bool ghosts = false, global = false;
+      if (!readVti<T>(path, layout(), h.data(), &ghosts, &msg, &global)) throw std::runtime_error(msg);
       if (!readRestartMeta(path, &meta)) throw std::runtime_error("restart: no readable '" + path + ".meta' (time step / total time)");
-      startStep = meta.nStep;
-      startTime = meta.totalTime;
+      if (!global && (meta.nranks != nranks_ || meta.rank != rank_ || meta.kOffset != kp_.kglob0))
+        throw std::runtime_error("restart: '" + path + "' was written by rank " + std::to_string(meta.rank) + " of " +
+                                 std::to_string(meta.nranks) + " (first plane " + std::to_string(meta.kOffset) +
+                                 "), not by this rank's slab");
+      if (global && meta.nranks != 1) throw std::runtime_error("restart: '" + path + "' is not a dump of the global grid");
+      // reference MHDRunBase.cpp:1358-1360 / MHDRunGodunov.cpp:3875-3877
+      startStep = cfg_.getBool("run", "restart_reset_timestep", false) ? 0 : meta.nStep;
+      startTime = cfg_.getBool("run", "restart_reset_totaltime", false) ? 0.0 : meta.totalTime;
       lastDt_ = meta.dt;
+      // next dt of the uninterrupted run: valid only when the resumed run sees the same decomposition-independent state
       resumeDt_ = meta.dtNext;  // used for the first step after the restart (cleared by godunov_unsplit)
     } else if (!initProblem<T>(cfg_, rp_, kp_, problem, h, &msg)) {
       std::fprintf(stderr, "ramsesgpu_b200: %s\n", msg.c_str());
@@ -350,7 +363,8 @@ class RunImpl final : public Run {
     copyToHost(nStep % 2, h.data(), elems_ * sizeof(T));
     writeOutputs<T>(rp_, layout(), h.data(), nStep);
     if (rp_.outputVtk && !rp_.outputVtkAscii)  // what a restart needs besides the fields (see output.h)
-      writeRestartMeta(vtiPath(rp_, layout(), nStep), RestartMeta{nStep, totalTime, lastDt_, compute_dt(nStep % 2)});
+      writeRestartMeta(vtiPath(rp_, layout(), nStep),
+                       RestartMeta{nStep, totalTime, lastDt_, compute_dt(nStep % 2), rank_, nranks_, kp_.kglob0});
   }
 
   // reference MHDRunBase::history_default / history_mri (MHDRunBase.cpp:3311-3410, :3476-3620), reduced on the
@@ -374,6 +388,8 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMemcpyAsync(hBuf, dBuf, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
       RG_CUDA(cudaStreamSynchronize(stream_));
     };
+    // an overlapped step may still be filling the ghosts of this buffer on the communication stream
+    if (haloDone_[nStep % 2]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
     HistoryKernels<T>::columnSums(kp_, U, dPart1, nB, stream_);
     RG_CUDA(cudaMemcpyAsync(hHist_.data(), dPart1, n1 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     RG_CUDA(cudaStreamSynchronize(stream_));
@@ -1068,6 +1084,13 @@ std::unique_ptr<Run> Run::create(const ConfigMap& cfg, bool fp32, const DistInit
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
     throw std::runtime_error("ramsesgpu_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+  // the library ships sm_100a SASS only: any other device would fail every launch
+  int dev = dist.device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  int major = 0;
+  if (dev >= count || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10)
+    throw std::runtime_error("ramsesgpu_b200 is not available on device " + std::to_string(dev) + " (compute capability major " +
+                             std::to_string(major) + "): the library holds sm_100a (B200) code only");
   if (fp32) return std::unique_ptr<Run>(new RunImpl<float>(cfg, dist));
   return std::unique_ptr<Run>(new RunImpl<double>(cfg, dist));
 }
