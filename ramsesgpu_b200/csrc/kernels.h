@@ -54,6 +54,8 @@ struct MhdKernels {
   // fusedPrepare() encodes the tensor map of sc.W into sc.mapW and sets sc.fused when the run
   // parameters and the array shapes qualify; fusedFluxEmfUpdate() replaces flux()+emf()+update()
   static void fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc);
+  // what fusedPrepare() will decide from the run parameters alone (before any scratch exists)
+  static bool fusedUpdateEligible(const KParams<T>& P);
   static void fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka, int kb,
                                  T dt, unsigned long long* dMaxInvDt, cudaStream_t s);
   // fused cons->prim + edge electric field + trace (U -> W, shared-memory rings, z-marching blocks) for the

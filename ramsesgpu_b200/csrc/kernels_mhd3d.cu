@@ -27,6 +27,7 @@ int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when av
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
 int g_traceQY = 12;  // run-time knob "trace_qy": 12 (one 384-thread block per SM, 168 registers) or 8 (two 256-thread blocks, 128)
+int g_traceRing = 4;  // run-time knob "trace_ring": 4 = two barriers per plane, 5 = one barrier per plane (5-plane ring; trace_qy 12 only)
 
 namespace {
 
@@ -100,37 +101,43 @@ __global__ void __launch_bounds__(BX, MINB) k_trace(const __grid_constant__ KPar
 // Q and the edge electric field never go to HBM: per cell the kernel reads U once (x 1.4 tile halo)
 // and writes the 38 W components.
 // ------------------------------------------------------------------------------------------------
-template <int QY_>
+template <int QY_, int RINGQ_ = 4, int RINGE_ = 2>
 struct TraceTileT {
-  static constexpr int QX = 32, QY = QY_, TW = QX - 2, TH = QY - 2, QCELLS = QX * QY, RING = 4;
-  static constexpr int THREADS = QX * QY, MINB = 512 / THREADS;
-  static constexpr unsigned SMEM = (unsigned)((RING * 8 + RING * 3 + 2 * 3) * QCELLS * sizeof(double));
+  static constexpr int QX = 32, QY = QY_, TW = QX - 2, TH = QY - 2, QCELLS = QX * QY, RING = RINGQ_, RINGE = RINGE_;
+  static constexpr int THREADS = QX * QY;
+  static constexpr unsigned SMEM = (unsigned)((RING * 8 + RING * 3 + RINGE * 3) * QCELLS * sizeof(double));
+  static constexpr int MINB = (512 / THREADS) * SMEM <= 227u * 1024u ? 512 / THREADS : 1;
 };
 template <typename T, typename TraceTile>
-struct QTileView {  // primitives, ring of 4 planes, [plane][var][QY][QX]
+struct QTileView {  // primitives, ring of RING planes, [plane][var][QY][QX]
   T* buf;
   int ib, jb;
   __device__ __forceinline__ T& operator()(int v, int i, int j, int k) const {
-    return buf[((k & 3) * 8 + v) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+    return buf[(((unsigned)k % (unsigned)TraceTile::RING) * 8 + v) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
   }
 };
 template <typename T, typename TraceTile>
-struct BTileView {  // face fields U(IA..IC), ring of 4 planes
+struct BTileView {  // face fields U(IA..IC), ring of RING planes
   T* buf;
   int ib, jb;
   __device__ __forceinline__ T& operator()(int v, int i, int j, int k) const {
-    return buf[((k & 3) * 3 + (v - IA)) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+    return buf[(((unsigned)k % (unsigned)TraceTile::RING) * 3 + (v - IA)) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
   }
 };
 template <typename T, typename TraceTile>
-struct ETileView {  // edge electric fields, ring of 2 planes
+struct ETileView {  // edge electric fields, ring of RINGE planes
   T* buf;
   int ib, jb;
   __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
-    return buf[((k & 1) * 3 + c) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
+    return buf[(((unsigned)k % (unsigned)TraceTile::RINGE) * 3 + c) * TraceTile::QCELLS + (j - jb) * TraceTile::QX + (i - ib)];
   }
 };
 
+// Two pipelines over the same rings (TraceTile::RING picks one):
+//   RING = 4 (edge ring 2): plane k = { prim(k+1) | barrier | elec(k+1) | barrier | trace(k) }
+//   RING = 5 (edge ring 3): plane k = { prim(k+3), elec(k+2), trace(k) | barrier } -- the three stages of an
+//   iteration touch disjoint ring slots (prim writes the slot plane k-2 left, elec the slot edge plane k-1 left), so
+//   ONE block barrier per plane orders everything and the stages give the scheduler independent work to interleave.
 template <typename T, typename TraceTile, bool FAST>
 __global__ void __launch_bounds__(TraceTile::THREADS, TraceTile::MINB)
 k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T* __restrict__ Wp, int planes,
@@ -175,6 +182,27 @@ k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T
     B(IB, i, j, q) = u[IB];
     B(IC, i, j, q) = u[IC];
   };
+  if (TraceTile::RING >= 5) {
+    load(za - 1); prim(za - 1);
+    load(za);     prim(za);
+    load(za + 1); prim(za + 1);
+    load(za + 2); prim(za + 2);
+    load(za + 3);
+    __syncthreads();
+    if (elecOK) {
+      elec_cell<FAST>(P, Q, B, EL, i, j, za);
+      elec_cell<FAST>(P, Q, B, EL, i, j, za + 1);
+    }
+    __syncthreads();
+    for (int k = za; k < zb; ++k) {
+      if (k + 3 <= zb) prim(k + 3);
+      load(k + 4);  // prefetch: consumed by the next iteration
+      if (elecOK && k + 2 <= zb) elec_cell<FAST>(P, Q, B, EL, i, j, k + 2);
+      if (traceOK) trace_cell<FAST>(P, Q, B, EL, W, i, j, k, dt);
+      __syncthreads();
+    }
+    return;
+  }
   load(za - 1);
   prim(za - 1);
   load(za);
@@ -801,6 +829,11 @@ bool setTuning(const char* key, int value) {
     g_hydroTile = value ? 1 : 0;
     return true;
   }
+  if (k == "trace_ring") {
+    if (value != 4 && value != 5) return false;
+    g_traceRing = value;
+    return true;
+  }
   if (k == "trace_qy") {
     if (value != 8 && value != 12) return false;
     g_traceQY = value;
@@ -978,7 +1011,11 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<12>::SMEM) == cudaSuccess &&
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<12>::SMEM) == cudaSuccess)
+                               (int)TraceTileT<12>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12, 5, 3>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<12, 5, 3>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12, 5, 3>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<12, 5, 3>::SMEM) == cudaSuccess)
              ? 1
              : 0;
   if (!ok) cudaGetLastError();
@@ -997,7 +1034,7 @@ static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T
     const int lz = (planes + nz - 1) / nz;
     if (lz < 8 && nz > 1) break;
     const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
-    const double cost = (double)((blocks + slots - 1) / slots) * (lz + 2.5);
+    const double cost = (double)((blocks + slots - 1) / slots) * (lz + (TT::RING >= 5 ? 4.5 : 2.5));
     if (cost < bestCost) { bestCost = cost; bestNz = nz; }
   }
   const int lz = (planes + bestNz - 1) / bestNz;
@@ -1010,7 +1047,9 @@ template <typename T>
 void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
   const int nSM = smCount();
-  if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
+  if (!fastPath(P) && g_traceRing == 5) launchFusedTrace<T, TraceTileT<12, 5, 3>, false>(P, U, sc, k0, k1, dt, nSM, s);
+  else if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
+  else if (g_traceQY == 12 && g_traceRing == 5) launchFusedTrace<T, TraceTileT<12, 5, 3>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else if (g_traceQY == 12) launchFusedTrace<T, TraceTileT<12>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
   launched();
@@ -1021,11 +1060,18 @@ template <typename T>
 struct FusedSel { typedef FusedTile<T, 15, 7, 512> Cfg; };
 
 template <typename T>
+bool MhdKernels<T>::fusedUpdateEligible(const KParams<T>& P) {
+  typedef typename FusedSel<T>::Cfg C;
+  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3) return false;
+  if (C::TW % 2 == 0 && (P.gw - 1) % 2 != 0) return false;  // box rows must start on an even cell index
+  return ((size_t)P.isize * sizeof(T)) % 16 == 0;           // TMA: row pitch a multiple of 16 bytes
+}
+
+template <typename T>
 void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   typedef typename FusedSel<T>::Cfg C;
   sc.fused = 0;
-  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3 || sc.W == nullptr) return;
-  if (C::TW % 2 == 0 && (P.gw - 1) % 2 != 0) return;  // box rows must start on an even cell index
+  if (!fusedUpdateEligible(P) || sc.W == nullptr) return;
   CUtensorMap map;
   if (!tma::encodeTile4D(&map, sc.W, (int)sizeof(T), P.isize, P.jsize, sc.planes, NW_MHD, C::WX, C::WY)) return;
   static_assert(sizeof(CUtensorMap) <= sizeof(sc.mapW), "tensor map storage");

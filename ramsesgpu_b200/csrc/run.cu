@@ -769,10 +769,17 @@ class RunImpl final : public Run {
     chunkPlanes_ = 0;
   }
 
-  void ensureScratchMhd3d() {
-    if (sc_.Q) return;
+  // The headline configuration runs on the two fused kernels and needs W only; the separate-kernel path (rotating
+  // frame fluxes/emfs, other solvers, slope_type 3, or a knob turned off) also needs Q, F, E, EL.
+  bool fusedPairUsable() {
+    return fusedTraceRequested() && fusedRequested() && MhdKernels<T>::fusedTraceAvailable(kp_) &&
+           MhdKernels<T>::fusedUpdateEligible(kp_);
+  }
+  void ensureScratchMhd3d(bool generic) {
+    if (sc_.W && generic && !sc_.F) freeScratch();  // a knob asked for the separate kernels after a W-only allocation
+    if (sc_.W) return;
     const size_t plane = (size_t)kp_.isize * kp_.jsize;
-    const size_t perPlane = plane * sizeof(T) * (8 + NW_MHD + 15 + 3 + 3);
+    const size_t perPlane = plane * sizeof(T) * (generic ? (8 + NW_MHD + 15 + 3 + 3) : NW_MHD);
     const int updPlanes = kp_.ksize - 2 * kp_.gw + 1;  // gw .. ksize-gw inclusive
     int chunk = updPlanes;
     size_t freeB = 0, totalB = 0;
@@ -786,11 +793,13 @@ class RunImpl final : public Run {
     if (userChunk_ > 0) chunk = std::min(std::min(userChunk_, updPlanes), chunk);
     chunkPlanes_ = chunk;
     sc_.planes = chunk + 4;
-    RG_CUDA(cudaMalloc(&sc_.Q, plane * sc_.planes * 8 * sizeof(T)));
     RG_CUDA(cudaMalloc(&sc_.W, plane * sc_.planes * NW_MHD * sizeof(T)));
-    RG_CUDA(cudaMalloc(&sc_.F, plane * sc_.planes * 15 * sizeof(T)));
-    RG_CUDA(cudaMalloc(&sc_.E, plane * sc_.planes * 3 * sizeof(T)));
-    RG_CUDA(cudaMalloc(&sc_.EL, plane * sc_.planes * 3 * sizeof(T)));
+    if (generic) {
+      RG_CUDA(cudaMalloc(&sc_.Q, plane * sc_.planes * 8 * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.F, plane * sc_.planes * 15 * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.E, plane * sc_.planes * 3 * sizeof(T)));
+      RG_CUDA(cudaMalloc(&sc_.EL, plane * sc_.planes * 3 * sizeof(T)));
+    }
     scratchBytes_ = perPlane * sc_.planes;
     deviceBytes_ += scratchBytes_;
     MhdKernels<T>::fusedPrepare(kp_, sc_);
@@ -798,7 +807,11 @@ class RunImpl final : public Run {
 
   // ---- 3D MHD step: reference godunov_unsplit_cpu/gpu (MHDRunGodunov.cpp:623-672, 1447-1503) ------
   void stepMhd3d(int src, int dst, T dt) {
-    ensureScratchMhd3d();
+    ensureScratchMhd3d(!fusedPairUsable());
+    if (!sc_.fused && !sc_.F) {  // the tensor map / kernel attribute could not be set up: separate kernels after all
+      freeScratch();
+      ensureScratchMhd3d(true);
+    }
     const T* Uold = dU_[src];
     T* Unew = dU_[dst];
     const int gw = kp_.gw, kN = kp_.ksize - gw;
@@ -919,7 +932,7 @@ class RunImpl final : public Run {
   // ---- 3D MHD step in the rotating frame (Omega0 > 0), with or without shearing-box boundaries:
   //      reference godunov_unsplit_rotating_cpu / _gpu (MHDRunGodunov.cpp:1511, 2031)
   void stepMhd3dRotating(int src, int dst, T dt) {
-    ensureScratchMhd3d();
+    ensureScratchMhd3d(true);
     const T* Uold = dU_[src];
     T* Unew = dU_[dst];
     const int gw = kp_.gw, kN = kp_.ksize - gw;

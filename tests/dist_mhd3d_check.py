@@ -47,52 +47,13 @@ def main():
         ini = ini_override(str(load_golden("kh3d_16x8x16_f32_s10")["ini"]), {"mesh": {"nx": 16, "ny": 8, "nz": nz}})
         Run = HydroRunGodunov
         fp32 = True
-    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    from ramsesgpu_b200.distcheck import slabs_match_single_gpu
+    ok, info = slabs_match_single_gpu(torch, dist, Run, ini, nsteps, rank, world, local, fp32=fp32, overlap=overlap)
     if rank == 0:
-        raw = C.create_string_buffer(128)
-        _lib.check(L.rg_nccl_unique_id(raw))
-        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-    dist.broadcast(buf, 0)
-    uid = bytes(buf.cpu().numpy().tobytes())
-
-    def run_steps(run):
-        run.init_simulation()
-        run.make_all_boundaries(0)
-        run.setDataHost(run.getDataHost(0), 1)
-        n, t, dt, dts = 0, 0.0, 0.0, []
-        for _ in range(nsteps):
-            n, t, dt = run.oneStepIntegration(n, t, dt)
-            dts.append(dt)
-        return run.getDataHost(n), dts
-
-    with Run(ini, fp32=fp32, rank=rank, nranks=world, nccl_unique_id=uid, device=local) as run:
-        run.set_halo_overlap(overlap)
-        U, dts = run_steps(run)
-        g, nzl, koff = run.layout.ghost_width, run.layout.nz_local, run.layout.k_offset
-        halo = run.stats().halo_bytes_per_step
-    inner = torch.from_numpy(np.ascontiguousarray(U[:, g:g + nzl, g:-g, g:-g])).cuda()
-    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([nzl], dtype=torch.int64, device="cuda"))
-    ok = True
-    if rank == 0:
-        parts = [inner.cpu().numpy()]
-        for r in range(1, world):
-            t = torch.empty((inner.shape[0], int(sizes[r].item()), inner.shape[2], inner.shape[3]), dtype=inner.dtype, device="cuda")
-            dist.recv(t, r)
-            parts.append(t.cpu().numpy())
-        got = np.concatenate(parts, axis=1)
-        with Run(ini, fp32=fp32) as mono:
-            Um, dtm = run_steps(mono)
-        want = Um[:, g:-g, g:-g, g:-g]
-        ok = bool(np.array_equal(got, want)) and dts == dtm
         print("dist check: problem=" + problem + " world=%d nz=%d steps=%d periodic_z=%s overlap=%s halo_bytes=%d identical=%s maxdiff=%.3e" %
-              (world, nz, nsteps, periodic_z, overlap, halo, ok, float(np.abs(got - want).max())), flush=True)
-    else:
-        dist.send(inner, 0)
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+              (world, nz, nsteps, periodic_z, overlap, info["halo_bytes_per_step"], ok, info["max_abs_diff"]), flush=True)
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1 else 1)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -24,6 +24,7 @@ static inline double __hiloint2double(int hi, int lo) {
   std::memcpy(&v, &b, 8);
   return v;
 }
+static inline long long __double_as_longlong(double v) { long long b; std::memcpy(&b, &v, 8); return b; }
 static inline int __float_as_int(float v) { int b; std::memcpy(&b, &v, 4); return b; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }

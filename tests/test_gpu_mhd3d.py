@@ -255,3 +255,80 @@ def test_orszag_tang_3d_100_steps_vs_oracle(native, oracle64):
         assert err < TOL_F64, (v, err)
     assert abs(tg - to) < 1e-12 * to
     print("OT3D 100 steps: worst L2-relative error %.2e" % worst)
+
+
+def test_orszag_tang_3d_64cubed_100_steps_vs_reference(native):
+    """BASELINE.json north star at the survey's parity size: data/orszag-tang3d.ini at 64^3, 100 steps, against the final
+    state written by the UNMODIFIED reference executable (tests/golden/ot3d_64_s100.npz, oracle/gen_golden.py),
+    L2-relative error of every variable (test/computeL2relatif.py.in:43-50) < 1e-12."""
+    g = load_golden("ot3d_64_s100")
+    U, t, dts, gw = run_gpu_steps(str(g["ini"]), int(g["steps"]))
+    inner = U[:, gw:-gw, gw:-gw, gw:-gw]
+    # the reference's result is invariant along z, bit for bit: the fixture keeps ONE plane, every CUDA plane is compared
+    final = np.broadcast_to(g["final"], inner.shape) if g.get("z_invariant", False) else g["final"]
+    worst = 0.0
+    for v, vname in enumerate(g["names"]):
+        if np.abs(final[v]).max() < 1e-10:   # w and B_z of the kt = 0 problem stay at rounding noise around zero
+            assert np.abs(inner[v]).max() < 1e-10, vname
+            continue
+        err = l2_relative(final[v], inner[v])
+        worst = max(worst, err)
+        assert err < TOL_F64, (vname, err)
+    assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
+    assert abs(dts[-1] - g["dt_last"]) < 1e-10 * g["dt_last"]
+    print("OT3D 64^3, 100 steps vs the reference executable: worst L2-relative error %.2e" % worst)
+
+
+@pytest.mark.parametrize("n,chunk", [((96, 80, 200), 0), ((96, 80, 200), 70)])
+def test_many_tiles_z_ranges_and_chunks_vs_oracle(native, oracle64, n, chunk):
+    """A grid that exercises the launch geometry of the fused kernels the small cases do not: 7 x 12 update tiles with
+    partial last tiles, several z ranges per tile column, (second case) three z chunks of the step pipeline -- against
+    the oracle restatement on the genuinely 3D kt = 1 problem, 2 steps (about 12 s of CPU)."""
+    ini = ot3d_ini(n, OrszagTang={"kt": 1.0})
+    p = oracle64.params(ini)
+    nsteps = 2
+    Ug, tg, dtg, gw = run_gpu_steps(ini, nsteps, chunk=chunk)
+    Uo, to, dto = oracle64.run_steps(p, oracle64.init_problem(p), nsteps)
+    for v in range(8):
+        err = l2_relative(Uo[v, gw:-gw, gw:-gw, gw:-gw], Ug[v, gw:-gw, gw:-gw, gw:-gw])
+        assert err < TOL_F64, (v, err)
+    assert np.allclose(dtg, dto, rtol=1e-12)
+
+
+@pytest.mark.parametrize("chunk", [0, 100])
+def test_bench_size_256cubed_every_plane_vs_oracle(native, oracle64, chunk):
+    """The bench workload itself (BASELINE.json configs[1]: orszag-tang3d.ini at 256^3, kt = 0) is invariant along z, so
+    every z plane of the 256^3 CUDA result must equal the oracle's result on the same problem with 8 planes (periodic
+    in z): 18 x 37 tiles x 2 z ranges (x 3 chunks in the second case) checked against the oracle, 2 steps."""
+    nsteps = 2
+    Ug, tg, dtg, gw = run_gpu_steps(ot3d_ini((256, 256, 256)), nsteps, chunk=chunk)
+    ini_thin = ot3d_ini((256, 256, 8), mesh={"zmax": 8.0 / 256.0})   # same dz
+    p = oracle64.params(ini_thin)
+    Uo, to, dto = oracle64.run_steps(p, oracle64.init_problem(p), nsteps)
+    assert np.allclose(dtg, dto, rtol=1e-12)
+    want = Uo[:, gw, gw:-gw, gw:-gw]                                 # one inner plane of the oracle (all are equal)
+    assert np.array_equal(Uo[:, gw + 3, gw:-gw, gw:-gw], want)
+    got = Ug[:, gw:-gw, gw:-gw, gw:-gw]
+    for v in range(8):
+        if np.abs(want[v]).max() < 1e-10:
+            assert np.abs(got[v]).max() < 1e-10, v
+            continue
+        den = np.sqrt(np.sum(want[v] ** 2))
+        errs = np.sqrt(np.sum((got[v] - want[v][None]) ** 2, axis=(1, 2))) / den   # L2-relative error of every plane
+        assert errs.max() < TOL_F64, (v, int(errs.argmax()), float(errs.max()))
+
+
+def test_trace_pipelines_are_bitwise_equal(native):
+    """The one-barrier-per-plane trace pipeline (5-plane primitive ring, knob trace_ring = 5) runs the same per-cell
+    functions on the same inputs as the two-barrier one: bitwise equal results, headline and rotating configuration."""
+    from ramsesgpu_b200 import set_tuning
+    mri = str(load_golden("mri3d_16x32x16_s12")["ini"])
+    try:
+        for ini in (ot3d_ini((40, 22, 30), OrszagTang={"kt": 1.0}), mri):
+            set_tuning("trace_ring", 4)
+            a, _, dta, _ = run_gpu_steps(ini, 3)
+            set_tuning("trace_ring", 5)
+            b, _, dtb, _ = run_gpu_steps(ini, 3)
+            assert np.array_equal(a, b) and np.array_equal(dta, dtb)
+    finally:
+        set_tuning("trace_ring", 4)

@@ -15,8 +15,8 @@ case "${1:-run}" in
     ;;
   run)
     for rep in 1 2; do
-      echo "== product"; python bench.py --no-cpu-baseline --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
-      echo "== variant"; RG_LIB_PATH=ramsesgpu_b200/lib_exp/libramsesgpu_b200.so python bench.py --no-cpu-baseline --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
+      echo "== product"; python bench.py --no-cpu-baseline --no-configs --no-strong --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
+      echo "== variant"; RG_LIB_PATH=ramsesgpu_b200/lib_exp/libramsesgpu_b200.so python bench.py --no-cpu-baseline --no-configs --no-strong --e2e-steps 0 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step'])"
     done
     echo "== parity of the variant"; RG_LIB_PATH=ramsesgpu_b200/lib_exp/libramsesgpu_b200.so python -m pytest tests/test_gpu_mhd3d.py tests/test_gpu_mri.py -q -m gpu 2>&1 | tail -3
     ;;

@@ -22,6 +22,14 @@ def scale(v, unit):
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit, 1.0)
 
 
+# python tools/ncu_evidence.py [--cells-per-launch N] [--head SHA] rep...: the launch shape the capture describes
+# (bench.py attaches the DRAM bytes per launch only to launches of the same shape)
+argv = sys.argv[1:]
+meta = {}
+while argv and argv[0].startswith("--"):
+    meta[argv[0][2:].replace("-", "_")] = argv[1]
+    argv = argv[2:]
+sys.argv = [sys.argv[0]] + argv
 out = {}
 for rep in sys.argv[1:]:
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
@@ -52,5 +60,9 @@ for fam, e in out.items():
                 "ncu_ms_per_step": e["ms"] / steps, "fp64_pipe_pct": e["fp64w"] / e["ms"], "issue_pct": e["issuew"] / e["ms"],
                 "warp_inst_per_step": e["inst"] / steps, "kernels": e["kernels"],
                 "source": [os.path.basename(r) for r in sys.argv[1:]]}
+    if "cells_per_launch" in meta:
+        res[fam]["cells_per_launch"] = float(meta["cells_per_launch"])
+    if "head" in meta:
+        res[fam]["head"] = meta["head"]
 json.dump(res, open(os.path.join(ROOT, "profiles", "ncu_evidence.json"), "w"), indent=1)
 print(json.dumps(res, indent=1))
