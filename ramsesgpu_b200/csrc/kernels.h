@@ -100,6 +100,16 @@ struct HydroKernels {
   static void probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s);
 };
 
+// 2D hydro traced state: 4 cell-centred primitives advanced by dt/2 + 8 half slopes
+constexpr int NW_HYDRO2D = 12;
+
+template <typename T>
+struct Hydro2dKernels {
+  // one step U -> Unew of the 2D Euler solver (kernels_hydro2d.cu); W is [NW_HYDRO2D][j][i]
+  static void step(const KParams<T>& P, const T* Uold, T* Unew, T* W, T dt, unsigned long long* slots, cudaStream_t s);
+  static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* slots, cudaStream_t s);
+};
+
 // dissipative terms on the NEW state after the Godunov update (kernels_dissipative.cu).
 // D is a scratch array of 12 components over the whole local array [c][k][j][i].
 template <typename T>

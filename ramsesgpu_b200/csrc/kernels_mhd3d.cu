@@ -27,7 +27,6 @@ int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when av
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
 int g_traceQY = 12;  // run-time knob "trace_qy": 12 (one 384-thread block per SM, 168 registers) or 8 (two 256-thread blocks, 128)
-int g_traceRing = 4;  // run-time knob "trace_ring": 4 = two barriers per plane, 5 = one barrier per plane (5-plane ring; trace_qy 12 only)
 
 namespace {
 
@@ -133,11 +132,9 @@ struct ETileView {  // edge electric fields, ring of RINGE planes
   }
 };
 
-// Two pipelines over the same rings (TraceTile::RING picks one):
-//   RING = 4 (edge ring 2): plane k = { prim(k+1) | barrier | elec(k+1) | barrier | trace(k) }
-//   RING = 5 (edge ring 3): plane k = { prim(k+3), elec(k+2), trace(k) | barrier } -- the three stages of an
-//   iteration touch disjoint ring slots (prim writes the slot plane k-2 left, elec the slot edge plane k-1 left), so
-//   ONE block barrier per plane orders everything and the stages give the scheduler independent work to interleave.
+// (A one-barrier-per-plane variant -- 5-plane primitive ring, prim(k+3) | elec(k+2) | trace(k) per iteration -- was built
+// and measured in round 2: 1.58 ms against 1.52 ms for this two-barrier pipeline at 256^3, profiles/r02_a_ab_trace_ring.txt;
+// the modulo-5 ring indexing and the larger shared-memory footprint cost more than the second barrier.)
 template <typename T, typename TraceTile, bool FAST>
 __global__ void __launch_bounds__(TraceTile::THREADS, TraceTile::MINB)
 k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T* __restrict__ Wp, int planes,
@@ -182,27 +179,6 @@ k_fused_trace(const __grid_constant__ KParams<T> P, const T* __restrict__ Uin, T
     B(IB, i, j, q) = u[IB];
     B(IC, i, j, q) = u[IC];
   };
-  if (TraceTile::RING >= 5) {
-    load(za - 1); prim(za - 1);
-    load(za);     prim(za);
-    load(za + 1); prim(za + 1);
-    load(za + 2); prim(za + 2);
-    load(za + 3);
-    __syncthreads();
-    if (elecOK) {
-      elec_cell<FAST>(P, Q, B, EL, i, j, za);
-      elec_cell<FAST>(P, Q, B, EL, i, j, za + 1);
-    }
-    __syncthreads();
-    for (int k = za; k < zb; ++k) {
-      if (k + 3 <= zb) prim(k + 3);
-      load(k + 4);  // prefetch: consumed by the next iteration
-      if (elecOK && k + 2 <= zb) elec_cell<FAST>(P, Q, B, EL, i, j, k + 2);
-      if (traceOK) trace_cell<FAST>(P, Q, B, EL, W, i, j, k, dt);
-      __syncthreads();
-    }
-    return;
-  }
   load(za - 1);
   prim(za - 1);
   load(za);
@@ -829,11 +805,6 @@ bool setTuning(const char* key, int value) {
     g_hydroTile = value ? 1 : 0;
     return true;
   }
-  if (k == "trace_ring") {
-    if (value != 4 && value != 5) return false;
-    g_traceRing = value;
-    return true;
-  }
   if (k == "trace_qy") {
     if (value != 8 && value != 12) return false;
     g_traceQY = value;
@@ -1011,11 +982,7 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<12>::SMEM) == cudaSuccess &&
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<12>::SMEM) == cudaSuccess &&
-          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12, 5, 3>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<12, 5, 3>::SMEM) == cudaSuccess &&
-          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12, 5, 3>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)TraceTileT<12, 5, 3>::SMEM) == cudaSuccess)
+                               (int)TraceTileT<12>::SMEM) == cudaSuccess)
              ? 1
              : 0;
   if (!ok) cudaGetLastError();
@@ -1034,7 +1001,7 @@ static void launchFusedTrace(const KParams<T>& P, const T* U, const MhdScratch<T
     const int lz = (planes + nz - 1) / nz;
     if (lz < 8 && nz > 1) break;
     const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
-    const double cost = (double)((blocks + slots - 1) / slots) * (lz + (TT::RING >= 5 ? 4.5 : 2.5));
+    const double cost = (double)((blocks + slots - 1) / slots) * (lz + 2.5);
     if (cost < bestCost) { bestCost = cost; bestNz = nz; }
   }
   const int lz = (planes + bestNz - 1) / bestNz;
@@ -1047,9 +1014,7 @@ template <typename T>
 void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc, int k0, int k1, T dt, cudaStream_t s) {
   if (k1 <= k0) return;
   const int nSM = smCount();
-  if (!fastPath(P) && g_traceRing == 5) launchFusedTrace<T, TraceTileT<12, 5, 3>, false>(P, U, sc, k0, k1, dt, nSM, s);
-  else if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
-  else if (g_traceQY == 12 && g_traceRing == 5) launchFusedTrace<T, TraceTileT<12, 5, 3>, true>(P, U, sc, k0, k1, dt, nSM, s);
+  if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
   else if (g_traceQY == 12) launchFusedTrace<T, TraceTileT<12>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
   launched();

@@ -222,8 +222,8 @@ __device__ __forceinline__ dev::State<T> face_state(const KParams<T>& P, const W
   // sgn = +1 : state at the HIGH face of cell (qm), -1 : at the LOW face (qp)
   constexpr int S = (DIR == 0) ? W_DRX : (DIR == 1) ? W_DRY : W_DRZ;  // first slope component
   dev::State<T> s;
-  s.r = dev::mxp(P.smallr, W(W_R, i, j, k) + sgn * W(S + 0, i, j, k));
-  s.p = dev::mxp(P.smallp, W(W_P, i, j, k) + sgn * W(S + 1, i, j, k));
+  s.r = dev::mx(P.smallr, W(W_R, i, j, k) + sgn * W(S + 0, i, j, k));
+  s.p = dev::mx(P.smallp, W(W_P, i, j, k) + sgn * W(S + 1, i, j, k));
   const T u = W(W_U, i, j, k) + sgn * W(S + 2, i, j, k);
   const T v = W(W_V, i, j, k) + sgn * W(S + 3, i, j, k);
   const T w = W(W_W, i, j, k) + sgn * W(S + 4, i, j, k);
@@ -257,8 +257,8 @@ __device__ __forceinline__ dev::Corner<T> edge_state(const KParams<T>& P, const 
                                                      T s2) {
   constexpr int S1 = (EDIR == 0) ? W_DRY : W_DRX;  // slopes along d1
   constexpr int S2 = (EDIR == 2) ? W_DRY : W_DRZ;  // slopes along d2
-  const T r = dev::mxp(P.smallr, W(W_R, i, j, k) + (s1 * W(S1 + 0, i, j, k) + s2 * W(S2 + 0, i, j, k)));
-  const T p = dev::mxp(P.smallp, W(W_P, i, j, k) + (s1 * W(S1 + 1, i, j, k) + s2 * W(S2 + 1, i, j, k)));
+  const T r = dev::mx(P.smallr, W(W_R, i, j, k) + (s1 * W(S1 + 0, i, j, k) + s2 * W(S2 + 0, i, j, k)));
+  const T p = dev::mx(P.smallp, W(W_P, i, j, k) + (s1 * W(S1 + 1, i, j, k) + s2 * W(S2 + 1, i, j, k)));
   const T U = W(W_U, i, j, k) + (s1 * W(S1 + 2, i, j, k) + s2 * W(S2 + 2, i, j, k));
   const T V = W(W_V, i, j, k) + (s1 * W(S1 + 3, i, j, k) + s2 * W(S2 + 3, i, j, k));
   const T Wv = W(W_W, i, j, k) + (s1 * W(S1 + 4, i, j, k) + s2 * W(S2 + 4, i, j, k));

@@ -55,19 +55,6 @@ __device__ __forceinline__ double mx(double a, double b) { return (a > b) ? a : 
 __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double mn(double a, double b) { return (a < b) ? a : b; }
 __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
-// max / min when at least ONE operand is known to be non-negative (floors, squared wave speeds, |x|).  Default: the
-// compare-select above.  RG_EXP_INT_MAX (experiment, off by default): a signed 64-bit integer compare of the bit patterns
-// (non-negative doubles order like their patterns, a negative double is a negative integer) -- the compare leaves the
-// FP64 pipe (DSETP -> 2 ISETP) at the price of one more issue slot.
-#if defined(RG_EXP_INT_MAX) && !defined(RG_HOST_EMULATION_NO_INT_MAX)
-__device__ __forceinline__ double mxp(double a, double b) { return (__double_as_longlong(a) > __double_as_longlong(b)) ? a : b; }
-__device__ __forceinline__ double mnp(double a, double b) { return (__double_as_longlong(a) < __double_as_longlong(b)) ? a : b; }
-#else
-__device__ __forceinline__ double mxp(double a, double b) { return mx(a, b); }
-__device__ __forceinline__ double mnp(double a, double b) { return mn(a, b); }
-#endif
-__device__ __forceinline__ float mxp(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ float mnp(float a, float b) { return fminf(a, b); }
 // forced select (the compiler otherwise turns long select ladders into divergent branches)
 __device__ __forceinline__ double pick(bool c, double a, double b) {
 #ifdef RG_HOST_EMULATION
@@ -82,13 +69,12 @@ __device__ __forceinline__ float pick(bool c, float a, float b) { return c ? a :
 __device__ __forceinline__ double ab(double a) { return fabs(a); }
 __device__ __forceinline__ float ab(float a) { return fabsf(a); }
 template <typename T> __device__ __forceinline__ T max4(T a, T b, T c, T d) { return mx(mx(a, b), mx(c, d)); }
-template <typename T> __device__ __forceinline__ T max4p(T a, T b, T c, T d) { return mxp(mxp(a, b), mxp(c, d)); }  // all >= 0
 template <typename T> __device__ __forceinline__ T min4(T a, T b, T c, T d) { return mn(mn(a, b), mn(c, d)); }
-// clamps at zero and the guard in front of a square root.  Default: compare-select on the FP64 pipe (DSETP + 2 FSEL).
-// RG_EXP_INT_CLAMP (experiment, off by default; tools/microbench/select_variants.cu, profiles/r01_select_variants_sass.txt):
-// the same decisions on the integer pipe -- a sign-bit mask for the clamps (min0 keeps a -0.0), one integer compare of
-// the high words for the guard (threshold 2^-996 instead of 1e-300: both only keep rsq() away from 0 and negatives).
-#if defined(RG_EXP_INT_CLAMP)
+// clamps at zero and the guard in front of a square root, on the INTEGER pipe: a sign-bit mask for the clamps (min0 keeps
+// a -0.0), one integer compare of the high words for the guard (threshold 2^-996 instead of 1e-300: both only keep rsq()
+// away from 0 and negatives).  No DSETP on the FP64 pipe: measured -3.2 % on the fused update kernel against the
+// compare-select forms (profiles/r02_a_ab_variants.txt).  RG_FP64_CLAMP restores the compare-select forms.
+#if !defined(RG_FP64_CLAMP)
 __device__ __forceinline__ double min0(double x) {
   const int hi = __double2hiint(x), m = hi >> 31;
   return __hiloint2double(hi & m, __double2loint(x) & m);
@@ -103,9 +89,9 @@ __device__ __forceinline__ double guard_tiny(double x) {
   return __hiloint2double(small ? 0x01b00000 : hi, small ? 0 : __double2loint(x));
 }
 #else
-__device__ __forceinline__ double min0(double x) { return mnp(x, 0.0); }
-__device__ __forceinline__ double max0(double x) { return mxp(x, 0.0); }
-__device__ __forceinline__ double guard_tiny(double x) { return mxp(x, tiny<double>()); }
+__device__ __forceinline__ double min0(double x) { return mn(x, 0.0); }
+__device__ __forceinline__ double max0(double x) { return mx(x, 0.0); }
+__device__ __forceinline__ double guard_tiny(double x) { return mx(x, tiny<double>()); }
 #endif
 __device__ __forceinline__ float min0(float x) { return mn(x, 0.0f); }
 __device__ __forceinline__ float max0(float x) { return mx(x, 0.0f); }
@@ -135,9 +121,9 @@ __device__ __forceinline__ T limited_slope(T st, T qm, T q0, T qp) {
 __device__ __forceinline__ double half_slope(double hst, double qm, double q0, double qp) {
   const double a = q0 - qm, b = qp - q0;
   const double s = a + b;
-#if defined(RG_EXP_LIMITER_V1)
-  // experiment (off by default; tools/microbench/limiter_variants.cu): one three-way minimum of the sign-flipped terms,
-  // clamped at zero with a sign mask -- opposite signs give a negative minimum.  Same value, bit for bit.
+#if !defined(RG_LIMITER_V0)
+  // one three-way minimum of the sign-flipped terms, clamped at zero with a sign mask -- opposite signs give a negative
+  // minimum (tools/microbench/limiter_variants.cu: 19 -> 16 instructions, 9 -> 6 on the FP64 pipe per slope)
   const int sg = __double2hiint(s) & 0x80000000;
   const double fa = __hiloint2double(__double2hiint(a) ^ sg, __double2loint(a)) * hst;
   const double fb = __hiloint2double(__double2hiint(b) ^ sg, __double2loint(b)) * hst;
@@ -145,9 +131,9 @@ __device__ __forceinline__ double half_slope(double hst, double qm, double q0, d
   const int hi = __double2hiint(rr), m = ~(hi >> 31);
   return __hiloint2double((hi & m) | sg, __double2loint(rr) & m);
 #else
-  const double m = mnp(ab(a), ab(b)) * hst;
+  const double m = mn(ab(a), ab(b)) * hst;
   const double c = ab(s) * 0.25;
-  double r = mnp(m, c);
+  double r = mn(m, c);
   if ((__double2hiint(a) ^ __double2hiint(b)) < 0) r = 0.0;
   return __hiloint2double((__double2hiint(r) & 0x7fffffff) | (__double2hiint(s) & 0x80000000), __double2loint(r));
 #endif
@@ -167,7 +153,7 @@ __device__ __forceinline__ float half_slope(float hst, float qm, float q0, float
 template <bool FAST = false, typename T>
 __device__ __forceinline__ void cons_to_prim_mhd(const KParams<T>& P, const T (&u)[8], T bxp, T byp, T bzp,
                                                  T dt, T (&q)[8]) {
-  T r = mxp(u[ID], P.smallr);
+  T r = mx(u[ID], P.smallr);
   T ir = rcp(r);
   T vx = u[IU] * ir, vy = u[IV] * ir, vz = u[IW] * ir;
   T A = T(0.5) * (u[IA] + bxp), B = T(0.5) * (u[IB] + byp), C = T(0.5) * (u[IC] + bzp);
@@ -178,7 +164,7 @@ __device__ __forceinline__ void cons_to_prim_mhd(const KParams<T>& P, const T (&
     T eken = T(0.5) * (vx * vx + vy * vy + vz * vz);
     T emag = T(0.5) * (A * A + B * B + C * C);
     T eint = (u[IP] - emag) * ir - eken;
-    p = mxp((P.gamma0 - T(1)) * r * eint, r * P.smallp);
+    p = mx((P.gamma0 - T(1)) * r * eint, r * P.smallp);
   }
   if (!FAST && P.Omega0 > T(0)) {  // Coriolis predictor, constoprim.h:189-195
     T dvx = T(2.0) * P.Omega0 * vy;
@@ -287,7 +273,7 @@ __device__ __forceinline__ void riemann_hlld(const KParams<T>& P, State<T> L, St
   const T ptotr = pr + emagr;
   const T vdotbr = ur * a + vr * br + wr * cr;
 
-  const T cmax = sqr_t(mxp(fast_speed2(P.gamma0, pl, rcp(rl), T(2) * emagl, a2),
+  const T cmax = sqr_t(mx(fast_speed2(P.gamma0, pl, rcp(rl), T(2) * emagl, a2),
                            fast_speed2(P.gamma0, pr, rcp(rr), T(2) * emagr, a2)));
   const T sl = mn(ul, ur) - cmax;
   const T sr = mx(ul, ur) + cmax;
@@ -423,7 +409,7 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
   RG_SPEEDS(RR, cxRR, cyRR, PtotRR)
 #undef RG_SPEEDS
   // sqrt is monotonic: max of the four fast speeds = sqrt of the max of their squares
-  const T cxm = sqr_t(max4p(cxLL, cxLR, cxRL, cxRR)), cym = sqr_t(max4p(cyLL, cyLR, cyRL, cyRR));
+  const T cxm = sqr_t(max4(cxLL, cxLR, cxRL, cxRR)), cym = sqr_t(max4(cyLL, cyLR, cyRL, cyRR));
   const T SL = min4(LL.u, LR.u, RL.u, RR.u) - cxm;
   const T SR = max4(LL.u, LR.u, RL.u, RR.u) + cxm;
   const T SB = min4(LL.v, LR.v, RL.v, RR.v) - cym;
@@ -463,10 +449,10 @@ __device__ __forceinline__ T mag_riemann2d_hlld(const KParams<T>& P, const Corne
   RG_CORNER(RL, SR, iSR, SB, iSB, BsRL, AsRL, ExRL, EyRL, EsRL, caRLx, caRL, cbRLy, cbRL)
   RG_CORNER(RR, SR, iSR, ST, iST, BsRR, AsRR, ExRR, EyRR, EsRR, caRRx, caRR, cbRRy, cbRR)
 #undef RG_CORNER
-  const T calfL = mxp(max4p(caLRx, caLR, caLLx, caLL), P.smallc);
-  const T calfR = mxp(max4p(caRRx, caRR, caRLx, caRL), P.smallc);
-  const T calfB = mxp(max4p(cbLLy, cbLL, cbRLy, cbRL), P.smallc);
-  const T calfT = mxp(max4p(cbLRy, cbLR, cbRRy, cbRR), P.smallc);
+  const T calfL = mx(max4(caLRx, caLR, caLLx, caLL), P.smallc);
+  const T calfR = mx(max4(caRRx, caRR, caRLx, caRL), P.smallc);
+  const T calfB = mx(max4(cbLLy, cbLL, cbRLy, cbRL), P.smallc);
+  const T calfT = mx(max4(cbLRy, cbLR, cbRRy, cbRR), P.smallc);
 
   const T SAL = min0(ustar - calfL), SAR = max0(ustar + calfR);
   const T SAB = min0(vstar - calfB), SAT = max0(vstar + calfT);

@@ -245,10 +245,10 @@ class RunImpl final : public Run {
     unsigned long long* slots = dMax_ + (size_t)b * MAX_SLOTS;
     if (!dtCached_[b]) {
       RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
-      if (!rp_.mhdEnabled && rp_.dim != 3) throw std::runtime_error("2D hydro is not available in this build");
       phase(PH_DT, [&] {
         if (rp_.mhdEnabled) MhdKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
-        else HydroKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
+        else if (rp_.dim == 3) HydroKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
+        else Hydro2dKernels<T>::computeInvDt(kp_, dU_[b], slots, stream_);
       });
       dtCached_[b] = true;
     }
@@ -291,7 +291,7 @@ class RunImpl final : public Run {
     } else if (rp_.mhdEnabled && rp_.dim == 2) {
       stepMhd2d(src, dst, static_cast<T>(dt));
     } else {
-      throw std::runtime_error("this solver variant is not available in this build");
+      stepHydro2d(src, dst, static_cast<T>(dt));
     }
     RG_CUDA(cudaEventRecord(ev1_, stream_));
     timed_ = true;
@@ -992,6 +992,23 @@ class RunImpl final : public Run {
     phase(PH_UPDATE, [&] {
       Mhd2dKernels<T>::step(kp_, dU_[src], dU_[dst], sc_.Q, sc_.W, sc_.F, sc_.E, dt, slots, stream_);
     });
+    ghostsValid_[dst] = false;
+    dtCached_[dst] = true;
+  }
+
+  // ---- 2D hydro step: reference HydroRunGodunov::godunov_unsplit_cpu + _v1, TWO_D branch (HydroRunGodunov.cpp:2437-2655)
+  void stepHydro2d(int src, int dst, T dt) {
+    if (!sc_.W) {
+      const size_t plane = (size_t)kp_.isize * kp_.jsize;
+      RG_CUDA(cudaMalloc(&sc_.W, plane * NW_HYDRO2D * sizeof(T)));
+      scratchBytes_ = plane * NW_HYDRO2D * sizeof(T);
+      deviceBytes_ += scratchBytes_;
+      sc_.planes = 1;
+      chunkPlanes_ = 1;
+    }
+    unsigned long long* slots = dMax_ + (size_t)dst * MAX_SLOTS;
+    RG_CUDA(cudaMemsetAsync(slots, 0, MAX_SLOTS * sizeof(unsigned long long), stream_));
+    phase(PH_UPDATE, [&] { Hydro2dKernels<T>::step(kp_, dU_[src], dU_[dst], sc_.W, dt, slots, stream_); });
     ghostsValid_[dst] = false;
     dtCached_[dst] = true;
   }

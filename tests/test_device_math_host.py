@@ -20,9 +20,9 @@ F = C.POINTER(C.c_float)
 
 
 # the product as built, and the experimental formulations kept behind macros for the next A/B on the GPU
-# (RG_EXP_INT_CLAMP: clamps / sqrt guards on the integer pipe; RG_EXP_LIMITER_V1: sign-flipped three-way minimum;
-# RG_EXP_INT_MAX: max / min with a non-negative operand as signed 64-bit integer compares)
-FLAVOURS = {"product": [], "experiments": ["-DRG_EXP_INT_CLAMP", "-DRG_EXP_LIMITER_V1"], "intmax": ["-DRG_EXP_INT_MAX"]}
+# (product: clamps / sqrt guards on the integer pipe, sign-flipped three-way limiter; "fp64forms": the compare-select
+# formulations they replaced in round 2, kept behind RG_FP64_CLAMP / RG_LIMITER_V0)
+FLAVOURS = {"product": [], "fp64forms": ["-DRG_FP64_CLAMP", "-DRG_LIMITER_V0"]}
 
 
 @pytest.fixture(scope="module", params=list(FLAVOURS))

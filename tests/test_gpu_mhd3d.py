@@ -316,19 +316,3 @@ def test_bench_size_256cubed_every_plane_vs_oracle(native, oracle64, chunk):
         den = np.sqrt(np.sum(want[v] ** 2))
         errs = np.sqrt(np.sum((got[v] - want[v][None]) ** 2, axis=(1, 2))) / den   # L2-relative error of every plane
         assert errs.max() < TOL_F64, (v, int(errs.argmax()), float(errs.max()))
-
-
-def test_trace_pipelines_are_bitwise_equal(native):
-    """The one-barrier-per-plane trace pipeline (5-plane primitive ring, knob trace_ring = 5) runs the same per-cell
-    functions on the same inputs as the two-barrier one: bitwise equal results, headline and rotating configuration."""
-    from ramsesgpu_b200 import set_tuning
-    mri = str(load_golden("mri3d_16x32x16_s12")["ini"])
-    try:
-        for ini in (ot3d_ini((40, 22, 30), OrszagTang={"kt": 1.0}), mri):
-            set_tuning("trace_ring", 4)
-            a, _, dta, _ = run_gpu_steps(ini, 3)
-            set_tuning("trace_ring", 5)
-            b, _, dtb, _ = run_gpu_steps(ini, 3)
-            assert np.array_equal(a, b) and np.array_equal(dta, dtb)
-    finally:
-        set_tuning("trace_ring", 4)

@@ -2,13 +2,12 @@
 # A/B of an experimental flavour of the library against the product on the bench workload.
 #   here (CPU box, cross-compile):   bash tools/ab_variant.sh build
 #   on the GPU box:                  gpurun --timeout 300 -- 'bash tools/ab_variant.sh run > gpurun_out/ab_variant.log 2>&1'
-# The flavour is the product source with RG_VARIANT_DEFINES (default: the two formulations validated against the
-# oracle on the host by tests/test_device_math_host.py[experiments]: clamps / sqrt guards on the integer pipe and the
-# sign-flipped three-way limiter).  Static SASS, r01: fused update 2992 -> 2904 instructions (DSETP 117 -> 100),
-# fused trace 2120 -> 2088 (FP64-pipe 580 -> 552), registers unchanged (125 / 168), no spills.
+# The flavour is the product source with RG_VARIANT_DEFINES (default: the compare-select formulations of round 1, which
+# the integer-pipe clamps / guards and the three-way limiter replaced in round 2 after this A/B: fused update 4.887 ->
+# 4.732 ms, trace 1.504 -> 1.491 ms at 256^3, profiles/r02_a_ab_variants.txt).
 set -eu
 cd "$(dirname "$0")/.."
-DEFS=${RG_VARIANT_DEFINES:-"-DRG_EXP_INT_CLAMP -DRG_EXP_LIMITER_V1"}
+DEFS=${RG_VARIANT_DEFINES:-"-DRG_FP64_CLAMP -DRG_LIMITER_V0"}
 case "${1:-run}" in
   build)
     RG_VARIANT=exp RG_VARIANT_DEFINES="$DEFS" python -m ramsesgpu_b200.build
