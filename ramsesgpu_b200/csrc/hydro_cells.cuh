@@ -12,18 +12,13 @@ namespace {
 enum { H_R = 0, H_P, H_U, H_V, H_W, H_DX = 5, H_DY = 10, H_DZ = 15 };  // slopes: (r, p, u, v, w) each
 static_assert(H_DZ + 5 == NW_HYDRO, "hydro W layout");
 
-// slopes + half-step predictor of one cell -> W (reference HydroRunGodunov.cpp:2663-2740, trace.h:544-661)
-template <typename T, typename UV, typename WV>
-__device__ __forceinline__ void hydro_trace_cell(const KParams<T>& P, const UV& U, const WV& W, int i, int j, int k, T dt) {
-  auto prim = [&](int ii, int jj, int kk, T(&q)[5]) {
-    dev::cons_to_prim_hydro(P, U(ID, ii, jj, kk), U(IP, ii, jj, kk), U(IU, ii, jj, kk), U(IV, ii, jj, kk),
-                            U(IW, ii, jj, kk), q);
-  };
-  T q[5], qxm[5], qxp[5], qym[5], qyp[5], qzm[5], qzp[5];
-  prim(i, j, k, q);
-  prim(i - 1, j, k, qxm); prim(i + 1, j, k, qxp);
-  prim(i, j - 1, k, qym); prim(i, j + 1, k, qyp);
-  prim(i, j, k - 1, qzm); prim(i, j, k + 1, qzp);
+// slopes + half-step predictor of one cell from its primitive state and the six neighbours' -> w[NW_HYDRO]
+// (reference HydroRunGodunov.cpp:2663-2740, trace.h:544-661).  Shared by the separate trace kernel (hydro_trace_cell
+// below) and by the fused hydro kernel, which keeps the primitives in registers / shared memory.
+template <typename T>
+__device__ __forceinline__ void hydro_trace_from_prims(const KParams<T>& P, const T (&q)[5], const T (&qxm)[5],
+                                                       const T (&qxp)[5], const T (&qym)[5], const T (&qyp)[5],
+                                                       const T (&qzm)[5], const T (&qzp)[5], T dt, T (&wv)[NW_HYDRO]) {
   const T st = P.slope_type, h = T(0.5);
   T dx_[5], dy_[5], dz_[5];
 #pragma unroll
@@ -45,15 +40,32 @@ __device__ __forceinline__ void hydro_trace_cell(const KParams<T>& P, const UV& 
   if (P.gravity) {  // gravity predictor on the traced velocities, reference HydroRunGodunov.cpp:2705-2734
     gpx = h * dt * P.gx; gpy = h * dt * P.gy; gpz = h * dt * P.gz;
   }
-  W(H_R, i, j, k) = r + sr0; W(H_P, i, j, k) = p + sp0;
-  W(H_U, i, j, k) = u + su0 + gpx; W(H_V, i, j, k) = v + sv0 + gpy; W(H_W, i, j, k) = w + sw0 + gpz;
+  wv[H_R] = r + sr0; wv[H_P] = p + sp0;
+  wv[H_U] = u + su0 + gpx; wv[H_V] = v + sv0 + gpy; wv[H_W] = w + sw0 + gpz;
   // slope component order in W: r, p, u, v, w  (ID, IP, IU, IV, IW)
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
-    W(H_DX + c, i, j, k) = dx_[c];
-    W(H_DY + c, i, j, k) = dy_[c];
-    W(H_DZ + c, i, j, k) = dz_[c];
+    wv[H_DX + c] = dx_[c];
+    wv[H_DY + c] = dy_[c];
+    wv[H_DZ + c] = dz_[c];
   }
+}
+
+template <typename T, typename UV, typename WV>
+__device__ __forceinline__ void hydro_trace_cell(const KParams<T>& P, const UV& U, const WV& W, int i, int j, int k, T dt) {
+  auto prim = [&](int ii, int jj, int kk, T(&q)[5]) {
+    dev::cons_to_prim_hydro(P, U(ID, ii, jj, kk), U(IP, ii, jj, kk), U(IU, ii, jj, kk), U(IV, ii, jj, kk),
+                            U(IW, ii, jj, kk), q);
+  };
+  T q[5], qxm[5], qxp[5], qym[5], qyp[5], qzm[5], qzp[5];
+  prim(i, j, k, q);
+  prim(i - 1, j, k, qxm); prim(i + 1, j, k, qxp);
+  prim(i, j - 1, k, qym); prim(i, j + 1, k, qyp);
+  prim(i, j, k - 1, qzm); prim(i, j, k + 1, qzp);
+  T wv[NW_HYDRO];
+  hydro_trace_from_prims(P, q, qxm, qxp, qym, qyp, qzm, qzp, dt, wv);
+#pragma unroll
+  for (int c = 0; c < NW_HYDRO; ++c) W(c, i, j, k) = wv[c];
 }
 
 // state at a face of cell (i,j,k): W centre +/- half slope along DIR, floors (trace.h:603-660),

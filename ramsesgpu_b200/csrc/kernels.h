@@ -98,7 +98,14 @@ struct HydroKernels {
                          T dt, unsigned long long* slots, cudaStream_t s);
   static void computeInvDt(const KParams<T>& P, const T* U, unsigned long long* slots, cudaStream_t s);
   static void probeRiemann(const KParams<T>& P, int n, const T* ql, const T* qr, T* flux, cudaStream_t s);
+  // the whole step of planes [k0, k1) in ONE kernel (kernels_hydro3d_fused.cu): U -> Unew, no W scratch
+  static void fusedStep(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, T dt, unsigned long long* slots,
+                        cudaStream_t s);
+  // x/y ghost cells of planes [k0, k1) keep the old values (the tiled kernels only write inner cells)
+  static void copyGhosts(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s);
 };
+// "hydro_fused" knob (default on): one-kernel hydro step
+bool hydroFusedRequested();
 
 // 2D hydro traced state: 4 cell-centred primitives advanced by dt/2 + 8 half slopes
 constexpr int NW_HYDRO2D = 12;

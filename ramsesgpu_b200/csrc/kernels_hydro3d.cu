@@ -301,9 +301,8 @@ void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, co
       case RS_APPROX: k_hydro_flux_update_tile<T, RS_APPROX><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
       default: k_hydro_flux_update_tile<T, -1><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
     }
-    const int ng = 2 * P.gw, cells = ng * P.isize + ng * (P.jsize - ng);
-    k_hydro_copy_ghosts<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
-    launched(2);
+    launched();
+    copyGhosts(P, Uold, Unew, k0, k1, s);
     return;
   }
   // z ranges of about 32 planes (one redundant z face per range), at least a few waves of blocks
@@ -316,6 +315,13 @@ void HydroKernels<T>::fluxUpdate(const KParams<T>& P, const T* Uold, T* Unew, co
     case RS_APPROX: k_hydro_flux_update<T, RS_APPROX><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
     default: k_hydro_flux_update<T, -1><<<g, b, 0, s>>>(P, Uold, Unew, W, planes, kbase, k0, k1, lzc, dt, slots); break;
   }
+  launched();
+}
+template <typename T>
+void HydroKernels<T>::copyGhosts(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const int ng = 2 * P.gw, cells = ng * P.isize + ng * (P.jsize - ng);
+  k_hydro_copy_ghosts<T><<<dim3((cells + 255) / 256, k1 - k0, 1), 256, 0, s>>>(P, Uold, Unew, k0);
   launched();
 }
 template <typename T>

@@ -801,6 +801,10 @@ bool setTuning(const char* key, int value) {
     g_fusedA = value ? 1 : 0;
     return true;
   }
+  if (k == "hydro_fused") {
+    g_hydroFused = value ? 1 : 0;
+    return true;
+  }
   if (k == "hydro_tile") {
     g_hydroTile = value ? 1 : 0;
     return true;

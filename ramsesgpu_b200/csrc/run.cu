@@ -1035,7 +1035,9 @@ class RunImpl final : public Run {
   }
 
   void stepHydro3d(int src, int dst, T dt) {
-    ensureScratchHydro3d();
+    const bool fused = hydroFusedRequested();  // one kernel, no traced-state scratch
+    if (!fused) ensureScratchHydro3d();
+    else if (chunkPlanes_ == 0) chunkPlanes_ = kp_.nz;
     const T* Uold = dU_[src];
     T* Unew = dU_[dst];
     const int gw = kp_.gw, kN = kp_.ksize - gw;
@@ -1046,6 +1048,10 @@ class RunImpl final : public Run {
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN, kp_.ksize, stream_);
     });
     auto runRange = [&](int k0, int k1) {
+      if (fused) {
+        phase(PH_FUSED, [&] { HydroKernels<T>::fusedStep(kp_, Uold, Unew, k0, k1, dt, slots, stream_); });
+        return;
+      }
       for (int ka = k0; ka < k1; ka += chunkPlanes_) {
         const int kb = std::min(ka + chunkPlanes_, k1);
         phase(PH_TRACE, [&] { HydroKernels<T>::trace(kp_, Uold, sc_.W, sc_.planes, ka - 1, ka - 1, kb + 1, dt, stream_); });

@@ -90,11 +90,17 @@ def test_random_state_vs_oracle(native, oracle64, solver, slope):
 
 
 def test_chunked_pipeline_is_identical(native):
+    """z chunks of the two-kernel path (trace + flux/update through W; the fused one-kernel step has no scratch to chunk)"""
+    from ramsesgpu_b200 import set_tuning
     g = load_golden("implode3d_16_s8")
-    ref, _, _ = run_gpu(str(g["ini"]), 4)
-    for chunk in (1, 3, 5):
-        got, _, _ = run_gpu(str(g["ini"]), 4, chunk=chunk)
-        assert np.array_equal(ref, got), chunk
+    try:
+        set_tuning("hydro_fused", 0)
+        ref, _, _ = run_gpu(str(g["ini"]), 4)
+        for chunk in (1, 3, 5):
+            got, _, _ = run_gpu(str(g["ini"]), 4, chunk=chunk)
+            assert np.array_equal(ref, got), chunk
+    finally:
+        set_tuning("hydro_fused", 1)
 
 
 def test_conservation_periodic_fp32_full_size(native):
@@ -130,12 +136,61 @@ def test_tile_and_gather_kernels_bitwise_identical(native):
         fp32 = str(g["precision"]) == "f32"
         ini = ini_override(str(g["ini"]), {"mesh": mesh})
         try:
+            set_tuning("hydro_fused", 0)
             set_tuning("hydro_tile", 0)
             Ua, dta, gw = run_gpu(ini, 6, fp32=fp32)
             set_tuning("hydro_tile", 1)
             Ub, dtb, _ = run_gpu(ini, 6, fp32=fp32)
         finally:
             set_tuning("hydro_tile", 1)
+            set_tuning("hydro_fused", 1)
         inner = (slice(None), slice(gw, -gw), slice(gw, -gw), slice(gw, -gw))
         assert np.array_equal(Ua[inner], Ub[inner]), name
         assert np.array_equal(dta, dtb), name
+
+
+@pytest.mark.parametrize("name,mesh,over", [
+    ("kh3d_16x8x16_f32_s10", {"nx": 67, "ny": 19, "nz": 23}, {}),            # partial tiles in x and y
+    ("kh3d_16x8x16_f64_s10", {"nx": 56, "ny": 16, "nz": 40}, {}),            # exact multiples of the 28 x 8 FP64 tile
+    ("implode3d_16_s8", {"nx": 35, "ny": 31, "nz": 70}, {}),                 # walls, approx solver, several z ranges
+    ("implode3d_hll_20x12x16_s5", {"nx": 29, "ny": 13, "nz": 9}, {}),        # HLL, minmod
+    ("rt3d_hydro_10x8x24_s8", {"nx": 30, "ny": 12, "nz": 24}, {}),           # static gravity (predictor + source term)
+])
+def test_fused_step_equals_two_kernel_path(native, name, mesh, over):
+    """The one-kernel hydro step (kernels_hydro3d_fused.cu: primitives in registers / shared memory, no W scratch)
+    against trace + flux/update through W: the same per-cell functions on the same inputs.  The compiler may contract
+    multiply-adds differently in the two kernels, so agreement is to the last bits (a few ulp), not bitwise."""
+    from ramsesgpu_b200 import set_tuning
+    g = load_golden(name)
+    fp32 = str(g["precision"]) == "f32"
+    ini = ini_override(str(g["ini"]), dict({"mesh": mesh}, **over))
+    try:
+        set_tuning("hydro_fused", 0)
+        Ua, dta, gw = run_gpu(ini, 6, fp32=fp32)
+        set_tuning("hydro_fused", 1)
+        Ub, dtb, _ = run_gpu(ini, 6, fp32=fp32)
+    finally:
+        set_tuning("hydro_fused", 1)
+    eps = 2e-6 if fp32 else 1e-14
+    assert np.allclose(dta, dtb, rtol=10 * eps, atol=0)
+    scale = np.abs(Ua.astype(np.float64)).max(axis=(1, 2, 3), keepdims=True)
+    scale[2:5] = scale[2:5].max()   # momentum components against the largest of them
+    assert (np.abs(Ua.astype(np.float64) - Ub.astype(np.float64)) <= 20 * eps * scale).all()      # ghosts included
+    print(name, "fused vs two-kernel: bitwise" if np.array_equal(Ua, Ub) else "fused vs two-kernel: max diff %.2e" %
+          float(np.abs(Ua.astype(np.float64) - Ub.astype(np.float64)).max()))
+
+
+def test_fused_step_full_size_fp32_vs_oracle_slab(native, oracle32):
+    """configs[2] geometry at a size the oracle finishes in seconds: 120 x 100 x 48 FP32 Kelvin-Helmholtz (HLLC, rand()
+    perturbation), 3 steps, 5 x 9 tiles x several z ranges of the fused kernel against the FP32 oracle restatement."""
+    g = load_golden("kh3d_16x8x16_f32_s10")
+    ini = ini_override(str(g["ini"]), {"mesh": {"nx": 120, "ny": 100, "nz": 48}})
+    p = oracle32.params(ini)
+    Ug, dtg, gw = run_gpu(ini, 3, fp32=True)
+    Uo, _, dto = oracle32.run_steps(p, oracle32.init_problem(p), 3)
+    mom = np.sqrt(sum(float(np.sum(Uo[v, gw:-gw, gw:-gw, gw:-gw].astype(np.float64) ** 2)) for v in (2, 3, 4)))
+    for v in range(5):
+        ref, got = Uo[v, gw:-gw, gw:-gw, gw:-gw].astype(np.float64), Ug[v, gw:-gw, gw:-gw, gw:-gw].astype(np.float64)
+        norm = np.sqrt(np.sum(ref ** 2)) if v < 2 else mom
+        assert np.sqrt(np.sum((ref - got) ** 2)) / norm < TOL_F32, v
+    assert np.allclose(dtg, dto, rtol=1e-5)
