@@ -70,8 +70,20 @@ def _compile(src, stamp, verbose):
 
 
 def build(force=False, verbose=False):
+    """Builds what is out of date.  Safe to call from several processes at once (pytest-xdist workers, the ranks of a
+    torchrun launch): an exclusive file lock serialises them, the late comers find everything up to date."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
+    with open(os.path.join(OBJDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp = _headers_digest() + ("force%d" % os.getpid() if force else "")
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
@@ -83,11 +95,13 @@ def build(force=False, verbose=False):
             fh.write(logs)
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
+        subprocess.check_call([NVCC] + ARCH + ["-shared", "-o", LIB + ".tmp"] + objs + ["-lcudart", "-ldl"])
+        os.replace(LIB + ".tmp", LIB)
     main_src = os.path.join(CSRC, "main.cpp")
     if os.path.exists(main_src) and (force or not os.path.exists(MAIN) or os.path.getmtime(MAIN) < max(newest, os.path.getmtime(main_src))):
-        subprocess.check_call([NVCC] + ARCH + COMMON + [main_src, "-o", MAIN, "-L", LIBDIR, "-lramsesgpu_b200",
+        subprocess.check_call([NVCC] + ARCH + COMMON + [main_src, "-o", MAIN + ".tmp", "-L", LIBDIR, "-lramsesgpu_b200",
                                                          "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
+        os.replace(MAIN + ".tmp", MAIN)
     return LIB
 
 

@@ -25,6 +25,7 @@ struct MhdScratch {
   T* F = nullptr;     // 15 components: flux_x[5], flux_y[5], flux_z[5] at the LOW faces
   T* E = nullptr;     // 3 components: emf z, y, x at the LOW edges (reference order I_EMFZ=0..)
   T* EL = nullptr;    // 3 components: v x B at the LOW edges (x, y, z), input of the trace
+  T* strips = nullptr;  // shearing box on the fused kernels: F[15] + E[3] of the 4 x-border position columns, [18][kk][j][4]
   int planes = 0;     // allocated planes per component
   int kbase = 0;      // k of scratch plane 0 for the chunk being processed
   // TMA descriptor (CUtensorMap) of W for the fused flux+emf+update kernel; valid when fused != 0
@@ -56,8 +57,12 @@ struct MhdKernels {
   static void fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc);
   // what fusedPrepare() will decide from the run parameters alone (before any scratch exists)
   static bool fusedUpdateEligible(const KParams<T>& P);
+  // rotating frame (Omega0 > 0, HLLD + 2-D HLLD): the FAST = false instantiation with update_cell_rot; with shearing-box
+  // boundaries (shearEnabled; jplus, frac = y shift of the opposite border) the cells next to the x borders are updated
+  // by a small second kernel from the border strips (sc.strips)
   static void fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka, int kb,
-                                 T dt, unsigned long long* dMaxInvDt, cudaStream_t s);
+                                 T dt, unsigned long long* dMaxInvDt, cudaStream_t s, int shearEnabled = 0, int jplus = 0,
+                                 T frac = T(0));
   // fused cons->prim + edge electric field + trace (U -> W, shared-memory rings, z-marching blocks) for the
   // FAST configuration; replaces prim() + elec() + trace() on traced planes [k0, k1)
   static bool fusedTraceAvailable(const KParams<T>& P);

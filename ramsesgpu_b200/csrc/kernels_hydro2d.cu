@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(BX) k_hydro2d_flux_update(const __grid_constan
       }
       T q[5];
       const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], T(0), q);
-      invDt = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy;
+      invDt = (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy;
     }
 #pragma unroll
     for (int v = 0; v < 4; ++v) Unew[v * plane + idx] = un[v];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(BX) k_hydro2d_invdt(const __grid_constant__ KP
     T q[5];
     const T c = dev::cons_to_prim_hydro(P, __ldg(Uin + idx), __ldg(Uin + plane + idx), __ldg(Uin + 2 * plane + idx),
                                         __ldg(Uin + 3 * plane + idx), T(0), q);
-    invDt = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy;
+    invDt = (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy;
   }
   reduceMaxToSlots(invDt, slots);
 }

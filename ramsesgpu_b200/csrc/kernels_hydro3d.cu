@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) k_hydro_flux_update(const __grid_constant
         }
         T q[5];
         const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], un[IW], q);
-        invDt = dev::mx(invDt, (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz);
+        invDt = dev::mx(invDt, (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy + (c + dev::ab(q[IW])) * P.rdz);
 #pragma unroll
         for (int v = 0; v < 5; ++v) fzl[v] = fzh[v];  // the high z face is the low face of the next plane
       }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(32 * HR) k_hydro_flux_update_tile(const __grid
       for (int v = 0; v < 5; ++v) Unew[v * comp + idx] = r5[v];
       T q[5];
       const T c = dev::cons_to_prim_hydro(P, r5[ID], r5[IP], r5[IU], r5[IV], r5[IW], q);
-      invDt = dev::mx(invDt, (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz);
+      invDt = dev::mx(invDt, (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy + (c + dev::ab(q[IW])) * P.rdz);
     }
     zPrev = face_from_regs<T, 2>(P, w, T(1));
     if (!mid) continue;  // block-uniform: first (za-1) and last (zb) planes only feed the z faces
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BX) k_hydro_invdt(const __grid_constant__ KPar
     const UView<T> U = uview(Uin, P);
     T q[5];
     const T c = dev::cons_to_prim_hydro(P, U(ID, i, j, k), U(IP, i, j, k), U(IU, i, j, k), U(IV, i, j, k), U(IW, i, j, k), q);
-    invDt = (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz;
+    invDt = (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy + (c + dev::ab(q[IW])) * P.rdz;
   }
   reduceMaxToSlots(invDt, slots);
 }

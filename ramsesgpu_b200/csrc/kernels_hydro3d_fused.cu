@@ -25,6 +25,7 @@
 namespace rg {
 
 int g_hydroFused = 1;  // run-time knob "hydro_fused": the one-kernel step (default) or trace + flux/update through W
+int g_hydroRows = 0;   // run-time knob "hydro_rows": rows of the thread block (0 = default: 16 in FP32, 12 in FP64)
 
 namespace {
 
@@ -120,10 +121,16 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
       for (int v = 0; v < 5; ++v) Unew[v * comp + idx] = r5[v];
       T q[5];
       const T c = dev::cons_to_prim_hydro(P, r5[ID], r5[IP], r5[IU], r5[IV], r5[IW], q);
-      invDt = dev::mx(invDt, (c + dev::ab(q[IU])) / P.dx + (c + dev::ab(q[IV])) / P.dy + (c + dev::ab(q[IW])) / P.dz);
+      invDt = dev::mx(invDt, (c + dev::ab(q[IU])) * P.rdx + (c + dev::ab(q[IV])) * P.rdy + (c + dev::ab(q[IW])) * P.rdz);
     }
     zPrev = face_from_regs<T, 2>(P, w, T(1));
     T fxl[5] = {T(0), T(0), T(0), T(0), T(0)}, fxh[5], fyl[5] = {T(0), T(0), T(0), T(0), T(0)};
+    T un[5] = {T(0), T(0), T(0), T(0), T(0)};
+    if (mid && upd) {  // old state of the cell: requested here, consumed after the two barriers below
+      const size_t idx = (size_t)p * plane + col;
+#pragma unroll
+      for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
+    }
     if (mid) {
       // x faces: left state from lane-1, high flux from lane+1
       const dev::HState<T> hi = face_from_regs<T, 0>(P, w, T(1));
@@ -153,10 +160,9 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
     }
     __syncthreads();  // B: sF and the new sQ complete; every read of sY is done
     if (mid && upd) {
-      const size_t idx = (size_t)p * plane + col;
 #pragma unroll
       for (int v = 0; v < 5; ++v) {  // summation order of the reference's serial scatter
-        T s = __ldg(Uold + v * comp + idx);
+        T s = un[v];
         s += fxl[v] * dtdx; s += fyl[v] * dtdy; s += fz[v] * dtdz;
         s -= fxh[v] * dtdx; s -= sF[v * SV + sidx + C::CX] * dtdy;
         acc[v] = s;
@@ -211,7 +217,11 @@ template <typename T>
 void HydroKernels<T>::fusedStep(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, T dt, unsigned long long* slots,
                                 cudaStream_t s) {
   if (k1 <= k0) return;
-  launchHydroFused<T, HydroFusedTile<T, (sizeof(T) == 4 ? 16 : 12)>>(P, Uold, Unew, k0, k1, dt, slots, s);
+  const int rows = g_hydroRows ? g_hydroRows : (sizeof(T) == 4 ? 16 : 12);
+  if (rows == 24) launchHydroFused<T, HydroFusedTile<T, 24>>(P, Uold, Unew, k0, k1, dt, slots, s);
+  else if (rows == 20) launchHydroFused<T, HydroFusedTile<T, 20>>(P, Uold, Unew, k0, k1, dt, slots, s);
+  else if (rows == 16) launchHydroFused<T, HydroFusedTile<T, 16>>(P, Uold, Unew, k0, k1, dt, slots, s);
+  else launchHydroFused<T, HydroFusedTile<T, 12>>(P, Uold, Unew, k0, k1, dt, slots, s);
   copyGhosts(P, Uold, Unew, k0, k1, s);
 }
 

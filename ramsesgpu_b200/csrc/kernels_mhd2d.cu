@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(BX) k2_update(const __grid_constant__ KParams<
         dev::cons_to_prim_mhd(P, un, bxp, byp, T(0), T(0), q);
         const T irho = dev::rcp(q[ID]);
         const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], bb = a2 + b2 + q[IC] * q[IC];
-        invDt = (dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU])) / P.dx +
-                (dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV])) / P.dy;
+        invDt = (dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU])) * P.rdx +
+                (dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV])) * P.rdy;
       }
     }
 #pragma unroll

@@ -336,11 +336,16 @@ __device__ __forceinline__ void waitCount(const int* c, int full) {
   }
 }
 
-template <typename T, typename C>
+// FAST = false: the rotating frame / shearing box with the isothermal closure (BASELINE.json configs[3]): same tasks with
+// the shear terms of the y flux and of the emfs, update_cell_rot for the cells of the tile, and -- with shearing-box
+// boundaries -- the fluxes / emfs of the four x-border position columns copied to compact strips in HBM, from which
+// k_update_rot_border updates the three cell columns that read the y-remapped OPPOSITE border (other tiles' data).
+template <typename T, typename C, bool FAST>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapW,
                         const T* __restrict__ Uold, T* __restrict__ Unew, int kbase, int ka, int kb, int lz, T dt,
-                        unsigned long long* __restrict__ dMaxInvDt) {
+                        unsigned long long* __restrict__ dMaxInvDt, const ShearShift<T> sh, T* __restrict__ strips,
+                        int stripPlanes) {
   extern __shared__ unsigned char smemRaw[];
   // 128-byte alignment for the TMA destination, computed on the shared-window address so that the
   // compiler keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -417,12 +422,26 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       if (p <= fhi && (zgrp || p < zb)) {
         if (zgrp) tma::mbarWait(&bars[pl], 0);
         tma::mbarWait(&bars[pl + 1], 0);
+        const bool strip = !FAST && sh.enabled && BorderView<T>::holds(i, gw, P.nx);
         if (isEmf) {
-          if (ok) fused_emf_task(P, W, E, dir, i, j, p);
+          if (ok) {
+            fused_emf_task<FAST>(P, W, E, dir, i, j, p);
+            if (strip) {
+              const BorderView<T> Eb{strips, P.jsize, stripPlanes, kbase, gw, P.nx, 15};
+              Eb(2 - dir, i, j, p) = E(2 - dir, i, j, p);
+            }
+          }
         } else {
           // a face is only needed where both transverse indexes are inner (k_flux)
           const bool need = (dir == 0 || i < iN) && (dir == 1 || j < jN) && (dir == 2 || p < kN);
-          if (ok && need) fused_flux_task(P, W, F, dir, i, j, p);
+          if (ok && need) {
+            fused_flux_task<FAST>(P, W, F, dir, i, j, p);
+            if (strip) {
+              const BorderView<T> Fb{strips, P.jsize, stripPlanes, kbase, gw, P.nx, 0};
+#pragma unroll
+              for (int c = 0; c < 5; ++c) Fb(5 * dir + c, i, j, p) = F(5 * dir + c, i, j, p);
+            }
+          }
         }
       }
       __syncwarp();
@@ -439,7 +458,14 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
         // a cell of the closing column/row belongs to this tile only when it is the ghost face (iN / jN)
         const bool mine = ok && (i < i0 + C::TW || i == iN) && (j < j0 + C::TH || j == jN);
         T invDt = T(0);
-        if (mine) invDt = update_cell<true>(P, U, Unew, F, E, i, j, p - 1, dt);
+        if (mine) {
+          if (FAST) {
+            invDt = update_cell<true>(P, U, Unew, F, E, i, j, p - 1, dt);
+          } else if (!(sh.enabled && (i == gw || i == P.nx + gw - 1 || i == P.nx + gw))) {
+            // (the three cell columns next to a shearing x border are updated by k_update_rot_border)
+            invDt = update_cell_rot(P, U, Unew, F, E, F, E, i, j, p - 1, dt, sh);
+          }
+        }
         if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
       }
       __syncwarp();
@@ -481,28 +507,6 @@ __global__ void __launch_bounds__(256) k_copy_outside_box(const __grid_constant_
 //   instead of the reference's border strips), density floor on the border columns, CT, next dt
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-struct ShearShift {   // y shift of the opposite x border: deltay = 1.5 Omega0 Lx t, reference :3213-3216
-  int enabled;        // shearing-box boundaries in x
-  int jplus;          // whole cells
-  T frac;             // epsi / dy
-};
-
-template <typename T>
-__device__ __forceinline__ void remapRows(const KParams<T>& P, const ShearShift<T>& sh, int j, bool xmin, int& j0,
-                                          int& j1, T& eps) {
-  const int gw = P.gw, ny = P.ny;
-  if (xmin) {  // inner (xmin) border looks at the xmax border shifted by -jplus-1
-    j0 = j - sh.jplus - 1; j1 = j0 + 1; eps = T(1) - sh.frac;
-    if (j0 < gw) j0 += ny;
-    if (j1 < gw) j1 += ny;
-  } else {
-    j0 = j + sh.jplus; j1 = j0 + 1; eps = sh.frac;
-    if (j0 > ny + gw - 1) j0 -= ny;
-    if (j1 > ny + gw - 1) j1 -= ny;
-  }
-}
-
-template <typename T>
 __global__ void __launch_bounds__(BX, 3) k_update_rot(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
                                                       T* __restrict__ Unew, const T* __restrict__ Fp,
                                                       const T* __restrict__ Ep, int planes, int kbase, int k0, T dt,
@@ -515,105 +519,40 @@ __global__ void __launch_bounds__(BX, 3) k_update_rot(const __grid_constant__ KP
   T invDt = T(0);
   if (valid) {
     const UView<T> U = uview(Uold, P);
-    const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
-    const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
     const bool inBox = i >= gw && i <= iN && j >= gw && j <= jN && k >= gw && k <= kN;
     if (!inBox) {
+      const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+      const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
 #pragma unroll
       for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = U(v, i, j, k);
     } else {
       const View<const T> F = view<const T>(Fp, P, planes, kbase);
       const View<const T> E = view<const T>(Ep, P, planes, kbase);
-      const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
-      const bool inner = i < iN && j < jN && k < kN;
-      T lambda = P.Omega0 * dt;
-      lambda = T(0.25) * lambda * lambda;
-      const T il = dev::rcp(T(1) + lambda);
-      const T ratio = (T(1) - lambda) * il, alpha1 = il, alpha2 = P.Omega0 * dt * il;
-      T un[8];
-#pragma unroll
-      for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
-      if (inner) {
-        const T dsx = T(2) * P.Omega0 * dt * un[IV] * il, dsy = T(-0.5) * P.Omega0 * dt * un[IU] * il;
-        T m[5];
-        m[ID] = un[ID]; m[IP] = un[IP]; m[IW] = un[IW];
-        m[IU] = un[IU] * ratio + dsx;
-        m[IV] = un[IV] * ratio + dsy;
-        const bool bLo = sh.enabled && i == gw, bHi = sh.enabled && i == P.nx + gw - 1;
-        // flux contributions in the reference's order: +x(i) +y(j) +z(k) -x(i+1) -y(j+1) -z(k+1)
-        auto add = [&](int c0, int ii, int jj, int kk, T s, T dtd, bool skipDensity) {
-          const T fd = F(c0 + 0, ii, jj, kk), fp = F(c0 + 1, ii, jj, kk), fu = F(c0 + 2, ii, jj, kk),
-                  fv = F(c0 + 3, ii, jj, kk), fw = F(c0 + 4, ii, jj, kk);
-          if (!skipDensity) m[ID] += s * fd * dtd;
-          m[IP] += s * fp * dtd;
-          m[IU] += s * (alpha1 * fu + alpha2 * fv) * dtd;
-          m[IV] += s * (alpha1 * fv - T(0.25) * alpha2 * fu) * dtd;
-          m[IW] += s * fw * dtd;
-        };
-        add(0, i, j, k, T(1), dtdx, bLo);
-        add(5, i, j, k, T(1), dtdy, false);
-        add(10, i, j, k, T(1), dtdz, false);
-        add(0, i + 1, j, k, T(-1), dtdx, bHi);
-        add(5, i, j + 1, k, T(-1), dtdy, false);
-        add(10, i, j, k + 1, T(-1), dtdz, false);
-        if (bLo || bHi) {  // remapped border density flux, :3237-3297
-          int j0, j1; T eps;
-          remapRows(P, sh, j, bLo, j0, j1, eps);
-          const int iOwn = bLo ? gw : P.nx + gw, iOpp = bLo ? P.nx + gw : gw;
-          const T own = F(0, iOwn, j, k) * dtdx;
-          const T rem = T(0.5) * (own + (T(1) - eps) * (F(0, iOpp, j0, k) * dtdx) + eps * (F(0, iOpp, j1, k) * dtdx));
-          m[ID] = bLo ? m[ID] + rem : m[ID] - rem;
-          m[ID] = dev::mx(m[ID], P.smallr);
-        }
-#pragma unroll
-        for (int v = 0; v < 5; ++v) un[v] = m[v];
-      }
-      // emf_y on the two x borders is the average with the remapped opposite border, :3251-3274
-      auto emfY = [&](int ii, int jj, int kk) -> T {
-        if (ii > iN || jj > jN || kk > kN) return T(0);
-        const T own = E(1, ii, jj, kk);
-        if (sh.enabled && (ii == gw || ii == P.nx + gw)) {
-          int j0, j1; T eps;
-          remapRows(P, sh, jj, ii == gw, j0, j1, eps);
-          const int iOpp = (ii == gw) ? P.nx + gw : gw;
-          return T(0.5) * (own + (T(1) - eps) * E(1, iOpp, j0, kk) + eps * E(1, iOpp, j1, kk));
-        }
-        return own;
-      };
-      auto emf = [&](int c, int ii, int jj, int kk) -> T {
-        return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
-      };
-      auto ct = [&](int ii, int jj, int kk, T& bx, T& by, T& bz) {
-        const T ez = emf(0, ii, jj, kk), ey = emfY(ii, jj, kk), ex = emf(2, ii, jj, kk);
-        if (kk < kN) {
-          bx += (emf(0, ii, jj + 1, kk) - ez) * dtdy;
-          by -= (emf(0, ii + 1, jj, kk) - ez) * dtdx;
-        }
-        bx -= (emfY(ii, jj, kk + 1) - ey) * dtdz;
-        by += (emf(2, ii, jj, kk + 1) - ex) * dtdz;
-        bz += (emfY(ii + 1, jj, kk) - ey) * dtdx;
-        bz -= (emf(2, ii, jj + 1, kk) - ex) * dtdy;
-      };
-      ct(i, j, k, un[IA], un[IB], un[IC]);
-#pragma unroll
-      for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
-      if (inner) {
-        T bxp = U(IA, i + 1, j, k), byp = U(IB, i, j + 1, k), bzp = U(IC, i, j, k + 1), d0, d1;
-        d0 = U(IB, i + 1, j, k); d1 = U(IC, i + 1, j, k); ct(i + 1, j, k, bxp, d0, d1);
-        d0 = U(IA, i, j + 1, k); d1 = U(IC, i, j + 1, k); ct(i, j + 1, k, d0, byp, d1);
-        d0 = U(IA, i, j, k + 1); d1 = U(IB, i, j, k + 1); ct(i, j, k + 1, d0, d1, bzp);
-        T q[8];
-        dev::cons_to_prim_mhd(P, un, bxp, byp, bzp, T(0), q);
-        const T irho = dev::rcp(q[ID]);
-        const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
-        const T bb = a2 + b2 + c2;
-        const T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
-        const T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]) +
-                     T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
-        const T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
-        invDt = vx / P.dx + vy / P.dy + vz / P.dz;
-      }
+      invDt = update_cell_rot(P, U, Unew, F, E, F, E, i, j, k, dt, sh);
     }
+  }
+  if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
+}
+
+// The three cell columns of a shearing box whose update reads the y-remapped opposite x border (i = gw, nx+gw-1 and the
+// ghost-face column nx+gw), after the fused kernel has left the fluxes / emfs of the four border position columns in the
+// compact strips (BorderView): thread = (column, row j), plane = blockIdx.z
+template <typename T>
+__global__ void __launch_bounds__(128) k_update_rot_border(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold,
+                                                           T* __restrict__ Unew, const T* __restrict__ strips, int planes,
+                                                           int kbase, int k0, T dt, const ShearShift<T> sh,
+                                                           unsigned long long* __restrict__ dMaxInvDt) {
+  const int gw = P.gw, jN = P.jsize - gw;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nRows = jN - gw + 1;  // rows gw .. jN of the update box
+  const int c = t / nRows, j = gw + t - c * nRows;
+  const int k = k0 + blockIdx.z;
+  T invDt = T(0);
+  if (c < 3) {
+    const int i = (c == 0) ? gw : P.nx + gw - 2 + c;  // gw, nx+gw-1, nx+gw
+    const UView<T> U = uview(Uold, P);
+    const BorderView<const T> F{strips, P.jsize, planes, kbase, gw, P.nx, 0}, E{strips, P.jsize, planes, kbase, gw, P.nx, 15};
+    invDt = update_cell_rot(P, U, Unew, F, E, F, E, i, j, k, dt, sh);
   }
   if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
 }
@@ -701,9 +640,9 @@ __global__ void __launch_bounds__(BX) k_invdt(const __grid_constant__ KParams<T>
     if (P.dim == 3) {
       T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
       if (P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
-      invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+      invDt = vx * P.rdx + vy * P.rdy + vz * P.rdz;
     } else {
-      invDt = vx / P.dx + vy / P.dy;
+      invDt = vx * P.rdx + vy * P.rdy;
     }
   }
   reduceMaxToSlots(invDt, dMaxInvDt);
@@ -799,6 +738,11 @@ bool setTuning(const char* key, int value) {
   }
   if (k == "fused_a") {
     g_fusedA = value ? 1 : 0;
+    return true;
+  }
+  if (k == "hydro_rows") {
+    if (value != 0 && value != 12 && value != 16 && value != 20 && value != 24) return false;
+    g_hydroRows = value;
     return true;
   }
   if (k == "hydro_fused") {
@@ -1028,10 +972,17 @@ template <typename T>
 // 512 threads / 124 registers: a 384-thread build (152 registers) measured 7 % slower, 640 threads spill
 struct FusedSel { typedef FusedTile<T, 15, 7, 512> Cfg; };
 
+// the rotating-frame instantiation of the fused kernel: HLLD + 2-D HLLD in the rotating frame (any closure)
+template <typename T>
+static bool rotatingFusedPath(const KParams<T>& P) {
+  return P.Omega0 > T(0) && P.riemannSolver == RS_HLLD && P.magRiemannSolver == MAG_HLLD && P.slope_type != T(3) &&
+         !P.gravity;
+}
+
 template <typename T>
 bool MhdKernels<T>::fusedUpdateEligible(const KParams<T>& P) {
   typedef typename FusedSel<T>::Cfg C;
-  if (sizeof(T) != 8 || !fastPath(P) || P.dim != 3) return false;
+  if (sizeof(T) != 8 || !(fastPath(P) || rotatingFusedPath(P)) || P.dim != 3) return false;
   if (C::TW % 2 == 0 && (P.gw - 1) % 2 != 0) return false;  // box rows must start on an even cell index
   return ((size_t)P.isize * sizeof(T)) % 16 == 0;           // TMA: row pitch a multiple of 16 bytes
 }
@@ -1048,8 +999,10 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   static bool attrSetDev[MAX_DEVICES] = {false};
   bool& attrSet = attrSetDev[currentDevice()];
   if (!attrSet) {
-    if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
+            cudaSuccess) {
       cudaGetLastError();
       return;
     }
@@ -1060,7 +1013,8 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
 
 template <typename T>
 void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka,
-                                       int kb, T dt, unsigned long long* d, cudaStream_t s) {
+                                       int kb, T dt, unsigned long long* d, cudaStream_t s, int shearEnabled, int jplus,
+                                       T frac) {
   typedef typename FusedSel<T>::Cfg C;
   if (kb <= ka) return;
   const int nSM = smCount();
@@ -1083,8 +1037,23 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
   const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
   CUtensorMap map;
   memcpy(&map, sc.mapW, sizeof(map));
-  k_fused_flux_emf_update<T, C><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d);
+  const ShearShift<T> sh{shearEnabled, jplus, frac};
+  if (fastPath(P)) {
+    k_fused_flux_emf_update<T, C, true><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh,
+                                                                          nullptr, 0);
+    launched();
+    return;
+  }
+  // rotating frame; with shearing-box boundaries the three border cell columns follow from the strips
+  k_fused_flux_emf_update<T, C, false><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh,
+                                                                         sc.strips, sc.planes);
   launched();
+  if (shearEnabled) {
+    const int nRows = P.jsize - 2 * P.gw + 1;
+    k_update_rot_border<T><<<dim3((3 * nRows + 127) / 128, 1, kb - ka), 128, 0, s>>>(P, Uold, Unew, sc.strips, sc.planes,
+                                                                                       sc.kbase, ka, dt, sh, d);
+    launched();
+  }
 }
 
 template <typename T>

@@ -360,7 +360,159 @@ __device__ __forceinline__ T update_cell(const KParams<T>& P, const UV& U, T* __
     T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]);
     T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
     if (!FAST && P.Omega0 > T(0)) vy += T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
-    invDt = vx / P.dx + vy / P.dy + vz / P.dz;
+    invDt = vx * P.rdx + vy * P.rdy + vz * P.rdz;
+  }
+  return invDt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rotating frame / shearing box (Omega0 > 0): the y shift of the opposite x border, the compact strips that hold the
+// fluxes / emfs of the four border position columns, and the update of one cell
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct ShearShift {   // y shift of the opposite x border: deltay = 1.5 Omega0 Lx t, reference :3213-3216
+  int enabled;        // shearing-box boundaries in x
+  int jplus;          // whole cells
+  T frac;             // epsi / dy
+};
+
+template <typename T>
+__device__ __forceinline__ void remapRows(const KParams<T>& P, const ShearShift<T>& sh, int j, bool xmin, int& j0,
+                                          int& j1, T& eps) {
+  const int gw = P.gw, ny = P.ny;
+  if (xmin) {  // inner (xmin) border looks at the xmax border shifted by -jplus-1
+    j0 = j - sh.jplus - 1; j1 = j0 + 1; eps = T(1) - sh.frac;
+    if (j0 < gw) j0 += ny;
+    if (j1 < gw) j1 += ny;
+  } else {
+    j0 = j + sh.jplus; j1 = j0 + 1; eps = sh.frac;
+    if (j0 > ny + gw - 1) j0 -= ny;
+    if (j1 > ny + gw - 1) j1 -= ny;
+  }
+}
+
+
+// Fluxes (c0 = 0) / emfs (c0 = 15) of the x-border position columns i = gw, gw+1, nx+gw-1, nx+gw only, laid out
+// [comp][kk][j][4]: written by the fused kernel of the shearing box, read by k_update_rot_border (the cells next to an x
+// border read the y-remapped values of the OPPOSITE border, which belong to other tiles)
+template <typename T>
+struct BorderView {
+  T* p;
+  int jsize, planes, kbase, gw, nx, c0;
+  __device__ __forceinline__ static int slot(int i, int gw, int nx) { return (i <= gw + 1) ? i - gw : 2 + (i - (nx + gw - 1)); }
+  __device__ __forceinline__ static bool holds(int i, int gw, int nx) {
+    return i == gw || i == gw + 1 || i == nx + gw - 1 || i == nx + gw;
+  }
+  __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
+    return p[(((size_t)(c0 + c) * planes + (k - kbase)) * jsize + j) * 4 + slot(i, gw, nx)];
+  }
+};
+
+// Update of one cell of the update box in the rotating frame (reference MHDRunGodunov.cpp:2938-3348): Crank-Nicolson
+// Coriolis rotation of (rho u, rho v), alpha-mixed momentum fluxes, constrained transport, inverse dt of the new
+// state; with shearing-box boundaries the density flux and emf_y of the two x borders are averaged with the y-remapped
+// opposite border (:3237-3297), read through Fb / Eb (any row of the border columns), and the border density is floored.
+// F / E give the fluxes / emfs around the cell itself.  Returns the inverse time step (0 outside the inner cells).
+template <typename T, typename UV, typename FV, typename EV, typename FBV, typename EBV>
+__device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T* __restrict__ Unew, const FV& F,
+                                             const EV& E, const FBV& Fb, const EBV& Eb, int i, int j, int k, T dt,
+                                             const ShearShift<T>& sh) {
+  const int gw = P.gw;
+  const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * P.ksize;
+  const size_t idx = (size_t)k * plane + (size_t)j * P.isize + i;
+  const T dtdx = dt / P.dx, dtdy = dt / P.dy, dtdz = dt / P.dz;
+  const bool inner = i < iN && j < jN && k < kN;
+  T lambda = P.Omega0 * dt;
+  lambda = T(0.25) * lambda * lambda;
+  const T il = dev::rcp(T(1) + lambda);
+  const T ratio = (T(1) - lambda) * il, alpha1 = il, alpha2 = P.Omega0 * dt * il;
+  T invDt = T(0);
+  T un[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) un[v] = U(v, i, j, k);
+  if (inner) {
+    const T dsx = T(2) * P.Omega0 * dt * un[IV] * il, dsy = T(-0.5) * P.Omega0 * dt * un[IU] * il;
+    T m[5];
+    m[ID] = un[ID]; m[IP] = un[IP]; m[IW] = un[IW];
+    m[IU] = un[IU] * ratio + dsx;
+    m[IV] = un[IV] * ratio + dsy;
+    const bool bLo = sh.enabled && i == gw, bHi = sh.enabled && i == P.nx + gw - 1;
+    // flux contributions in the reference's order: +x(i) +y(j) +z(k) -x(i+1) -y(j+1) -z(k+1)
+    auto add = [&](int c0, int ii, int jj, int kk, T s, T dtd, bool skipDensity) {
+      const T fd = F(c0 + 0, ii, jj, kk), fp = F(c0 + 1, ii, jj, kk), fu = F(c0 + 2, ii, jj, kk),
+              fv = F(c0 + 3, ii, jj, kk), fw = F(c0 + 4, ii, jj, kk);
+      if (!skipDensity) m[ID] += s * fd * dtd;
+      m[IP] += s * fp * dtd;
+      m[IU] += s * (alpha1 * fu + alpha2 * fv) * dtd;
+      m[IV] += s * (alpha1 * fv - T(0.25) * alpha2 * fu) * dtd;
+      m[IW] += s * fw * dtd;
+    };
+    add(0, i, j, k, T(1), dtdx, bLo);
+    add(5, i, j, k, T(1), dtdy, false);
+    add(10, i, j, k, T(1), dtdz, false);
+    add(0, i + 1, j, k, T(-1), dtdx, bHi);
+    add(5, i, j + 1, k, T(-1), dtdy, false);
+    add(10, i, j, k + 1, T(-1), dtdz, false);
+    if (bLo || bHi) {  // remapped border density flux, :3237-3297
+      int j0, j1; T eps;
+      remapRows(P, sh, j, bLo, j0, j1, eps);
+      const int iOwn = bLo ? gw : P.nx + gw, iOpp = bLo ? P.nx + gw : gw;
+      const T own = F(0, iOwn, j, k) * dtdx;
+      const T rem = T(0.5) * (own + (T(1) - eps) * (Fb(0, iOpp, j0, k) * dtdx) + eps * (Fb(0, iOpp, j1, k) * dtdx));
+      m[ID] = bLo ? m[ID] + rem : m[ID] - rem;
+      m[ID] = dev::mx(m[ID], P.smallr);
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) un[v] = m[v];
+  }
+  // emf_y on the two x borders is the average with the remapped opposite border, :3251-3274
+  auto emfY = [&](int ii, int jj, int kk) -> T {
+    if (ii > iN || jj > jN || kk > kN) return T(0);
+    const T own = E(1, ii, jj, kk);
+    if (sh.enabled && (ii == gw || ii == P.nx + gw)) {
+      int j0, j1; T eps;
+      remapRows(P, sh, jj, ii == gw, j0, j1, eps);
+      const int iOpp = (ii == gw) ? P.nx + gw : gw;
+      return T(0.5) * (own + (T(1) - eps) * Eb(1, iOpp, j0, kk) + eps * Eb(1, iOpp, j1, kk));
+    }
+    return own;
+  };
+  auto emf = [&](int c, int ii, int jj, int kk) -> T {
+    return (ii > iN || jj > jN || kk > kN) ? T(0) : E(c, ii, jj, kk);
+  };
+  // constrained transport per face component (same operation order as the reference's per-cell sequence)
+  auto ctx = [&](int ii, int jj, int kk, T bx) -> T {
+    if (kk < kN) bx += (emf(0, ii, jj + 1, kk) - emf(0, ii, jj, kk)) * dtdy;
+    return bx - (emfY(ii, jj, kk + 1) - emfY(ii, jj, kk)) * dtdz;
+  };
+  auto cty = [&](int ii, int jj, int kk, T by) -> T {
+    if (kk < kN) by -= (emf(0, ii + 1, jj, kk) - emf(0, ii, jj, kk)) * dtdx;
+    return by + (emf(2, ii, jj, kk + 1) - emf(2, ii, jj, kk)) * dtdz;
+  };
+  auto ctz = [&](int ii, int jj, int kk, T bz) -> T {
+    bz += (emfY(ii + 1, jj, kk) - emfY(ii, jj, kk)) * dtdx;
+    return bz - (emf(2, ii, jj + 1, kk) - emf(2, ii, jj, kk)) * dtdy;
+  };
+  un[IA] = ctx(i, j, k, un[IA]);
+  un[IB] = cty(i, j, k, un[IB]);
+  un[IC] = ctz(i, j, k, un[IC]);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
+  if (inner) {
+    const T bxp = ctx(i + 1, j, k, U(IA, i + 1, j, k));
+    const T byp = cty(i, j + 1, k, U(IB, i, j + 1, k));
+    const T bzp = ctz(i, j, k + 1, U(IC, i, j, k + 1));
+    T q[8];
+    dev::cons_to_prim_mhd(P, un, bxp, byp, bzp, T(0), q);
+    const T irho = dev::rcp(q[ID]);
+    const T a2 = q[IA] * q[IA], b2 = q[IB] * q[IB], c2 = q[IC] * q[IC];
+    const T bb = a2 + b2 + c2;
+    const T vx = dev::fast_speed(P.gamma0, q[IP], irho, bb, a2) + dev::ab(q[IU]);
+    const T vy = dev::fast_speed(P.gamma0, q[IP], irho, bb, b2) + dev::ab(q[IV]) +
+                 T(1.5) * P.Omega0 * (P.xMax - P.xMin) * T(0.5);
+    const T vz = dev::fast_speed(P.gamma0, q[IP], irho, bb, c2) + dev::ab(q[IW]);
+    invDt = vx * P.rdx + vy * P.rdy + vz * P.rdz;
   }
   return invDt;
 }
@@ -369,7 +521,7 @@ __device__ __forceinline__ T update_cell(const KParams<T>& P, const UV& U, T* __
 // one face flux / one corner emf of the FAST configuration (adiabatic, non-rotating, HLLD + 2-D HLLD) from W;
 // W, F, E are any accessors: shared-memory tiles in the fused kernel, host arrays in the CPU test suite
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename WV, typename FV>
+template <bool FAST = true, typename T, typename WV, typename FV>
 __device__ __forceinline__ void fused_flux_task(const KParams<T>& P, const WV& W,
                                                 const FV& F, int dir, int i, int j, int k) {
   dev::State<T> L, R;
@@ -384,7 +536,23 @@ __device__ __forceinline__ void fused_flux_task(const KParams<T>& P, const WV& W
     R = face_state<T, 2>(P, W, i, j, k, T(-1));
   }
   T f[8];
-  dev::riemann_mhd<true>(P, L, R, f);
+  dev::riemann_hlld<FAST>(P, L, R, f);
+  if (!FAST && dir == 1 && P.Omega0 > T(0)) {
+    // rotating frame: upwind advection of the y flux by the background shear, as in flux_cell (MHDRunGodunov.cpp:2860-2899)
+    const T xPos = P.xMin + P.dx * T(0.5) + (i - P.gw) * P.dx;
+    const T shear_y = T(-1.5) * P.Omega0 * xPos;
+    const T bn = T(0.5) * (L.a + R.a);
+    const dev::State<T>& S = (shear_y > T(0)) ? L : R;
+    const T pS = (P.cIso > T(0)) ? S.r * P.cIso * P.cIso : S.p;
+    const T eMag = T(0.5) * (bn * bn + S.b * S.b + S.c * S.c);
+    const T eKin = T(0.5) * (S.u * S.u + S.v * S.v + S.w * S.w);
+    const T eTot = eKin + eMag + pS / (P.gamma0 - T(1));
+    f[ID] += shear_y * S.r;
+    f[IP] += shear_y * (eTot + eMag - bn * bn);
+    f[IU] += shear_y * S.r * S.u;
+    f[IV] += shear_y * S.r * S.v;
+    f[IW] += shear_y * S.r * S.w;
+  }
   const int c0 = 5 * dir;
   F(c0 + 0, i, j, k) = f[ID];
   F(c0 + 1, i, j, k) = f[IP];
@@ -393,7 +561,7 @@ __device__ __forceinline__ void fused_flux_task(const KParams<T>& P, const WV& W
   F(c0 + 4, i, j, k) = (dir == 2) ? f[IU] : f[IW];
 }
 
-template <typename T, typename WV, typename EV>
+template <bool FAST = true, typename T, typename WV, typename EV>
 __device__ __forceinline__ void fused_emf_task(const KParams<T>& P, const WV& W,
                                                const EV& E, int edir, int i, int j, int k) {
   dev::Corner<T> RT, RB, LT, LB;
@@ -413,7 +581,9 @@ __device__ __forceinline__ void fused_emf_task(const KParams<T>& P, const WV& W,
     LT = edge_state<T, 0>(P, W, i, j, k - 1, T(-1), T(1));
     LB = edge_state<T, 0>(P, W, i, j, k, T(-1), T(-1));
   }
-  E(2 - edir, i, j, k) = dev::compute_emf<true>(P, RT, RB, LT, LB, edir, T(0));
+  // the fused kernels run the 2-D HLLD solver only (the launch wrappers check magRiemannSolver); xPos: shear terms
+  const T xPos = FAST ? T(0) : P.xMin + P.dx * T(0.5) + (i - P.gw) * P.dx;
+  E(2 - edir, i, j, k) = dev::compute_emf<FAST, true>(P, RT, RB, LT, LB, edir, xPos);
 }
 
 // ------------------------------------------------------------------------------------------------

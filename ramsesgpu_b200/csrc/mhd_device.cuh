@@ -31,7 +31,15 @@ __device__ __forceinline__ double rcp(double x) {
   return fma(r, e, r);                                     // cubic step: 2^-20 -> 2^-60 + rounding
 }
 // FP32: the MUFU results (<= 2 ulp) without the IEEE slow-path branches of __frcp_rn / sqrtf
-__device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float rcp(float x) {
+#ifdef RG_HOST_EMULATION
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP (__fdividef(1, x) adds a multiply)
+  return r;
+#endif
+}
 __device__ __forceinline__ double rsq(double x) {
   double y;
 #ifdef RG_HOST_EMULATION
@@ -541,7 +549,7 @@ __device__ T mag_riemann2d_llf(const KParams<T>& P, const Corner<T> (&q)[4]) {
 //   s[0] = RT-state of cell (-1,-1), s[1] = RB of (-1,0), s[2] = LT of (0,-1), s[3] = LB of (0,0)
 // in the reference's (IRT, IRB, ILT, ILB) order, each as (r, p, u, v, w, a, b, c) edge-frame.
 // emfDir: 0 = X, 1 = Y, 2 = Z (shear terms only).
-template <bool FAST = false, typename T>
+template <bool FAST = false, bool HLLD_ONLY = false, typename T>
 __device__ __forceinline__ T compute_emf(const KParams<T>& P, const Corner<T>& RT, const Corner<T>& RB,
                                          const Corner<T>& LT, const Corner<T>& LB, int emfDir, T xPos) {
   Corner<T> q[4];  // LL <- RT, RL <- LT, LR <- RB, RR <- LB
@@ -555,7 +563,7 @@ __device__ __forceinline__ T compute_emf(const KParams<T>& P, const Corner<T>& R
   q[0].a = aT; q[1].a = aT; q[2].a = aB; q[3].a = aB;
   q[0].b = bR; q[1].b = bL; q[2].b = bR; q[3].b = bL;
   T emf = T(0);
-  if (FAST || P.magRiemannSolver == MAG_HLLD) emf = mag_riemann2d_hlld(P, q[0], q[1], q[2], q[3]);
+  if (FAST || HLLD_ONLY || P.magRiemannSolver == MAG_HLLD) emf = mag_riemann2d_hlld(P, q[0], q[1], q[2], q[3]);
   else if (P.magRiemannSolver == MAG_HLLA) emf = mag_riemann2d_hll(P, q, true);
   else if (P.magRiemannSolver == MAG_HLLF) emf = mag_riemann2d_hll(P, q, false);
   else if (P.magRiemannSolver == MAG_LLF) emf = mag_riemann2d_llf(P, q);

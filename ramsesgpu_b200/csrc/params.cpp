@@ -75,6 +75,7 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
   k.dx = (k.xMax - k.xMin) / rp.nx;
   k.dy = (k.yMax - k.yMin) / rp.ny;
   k.dz = (k.zMax - k.zMin) / rp.nz;
+  k.rdx = T(1) / k.dx; k.rdy = T(1) / k.dy; k.rdz = T(1) / k.dz;
   // hydro constants (HydroParameters.h:274-330)
   k.cfl = cfg.getFloat("hydro", "cfl", 0.5f);
   if (!k.cfl) k.cfl = T(0.5);

@@ -29,6 +29,7 @@ struct KParams {
   int nzGlobal;
   T xMin, yMin, zMin, xMax, yMax, zMax;
   T dx, dy, dz;
+  T rdx, rdy, rdz;  // 1/dx, 1/dy, 1/dz rounded once on the host (the inverse-dt estimates multiply instead of divide)
   T gamma0, smallr, smallc, smallp, smallpp, smalle, gamma6, cIso, Omega0, slope_type, cfl;
   int niter_riemann;
   int riemannSolver, magRiemannSolver;

@@ -761,7 +761,7 @@ class RunImpl final : public Run {
   // ---- scratch / chunking ------------------------------------------------------------------------
   void freeScratch() {
     if (sc_.W) {  // cudaFree(nullptr) is a no-op for the arrays the hydro path does not use
-      cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL);
+      cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL); cudaFree(sc_.strips);
       deviceBytes_ -= scratchBytes_;
     }
     sc_ = MhdScratch<T>();
@@ -801,6 +801,12 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMalloc(&sc_.EL, plane * sc_.planes * 3 * sizeof(T)));
     }
     scratchBytes_ = perPlane * sc_.planes;
+    if (shearingBox()) {  // fluxes / emfs of the four x-border position columns (fused kernels of the shearing box)
+      const size_t stripBytes = (size_t)18 * sc_.planes * kp_.jsize * 4 * sizeof(T);
+      RG_CUDA(cudaMalloc(&sc_.strips, stripBytes));
+      RG_CUDA(cudaMemsetAsync(sc_.strips, 0, stripBytes, stream_));
+      scratchBytes_ += stripBytes;
+    }
     deviceBytes_ += scratchBytes_;
     MhdKernels<T>::fusedPrepare(kp_, sc_);
   }
@@ -932,7 +938,11 @@ class RunImpl final : public Run {
   // ---- 3D MHD step in the rotating frame (Omega0 > 0), with or without shearing-box boundaries:
   //      reference godunov_unsplit_rotating_cpu / _gpu (MHDRunGodunov.cpp:1511, 2031)
   void stepMhd3dRotating(int src, int dst, T dt) {
-    ensureScratchMhd3d(true);
+    ensureScratchMhd3d(!fusedPairUsable());
+    if (!sc_.fused && !sc_.F) {
+      freeScratch();
+      ensureScratchMhd3d(true);
+    }
     const T* Uold = dU_[src];
     T* Unew = dU_[dst];
     const int gw = kp_.gw, kN = kp_.ksize - gw;
@@ -955,6 +965,13 @@ class RunImpl final : public Run {
         phase(PH_PRIM, [&] { MhdKernels<T>::prim(kp_, Uold, sc, ka - 2, fhi + 2, dt, stream_); });
         phase(PH_PRIM, [&] { MhdKernels<T>::elec(kp_, Uold, sc, ka - 1, fhi + 2, stream_); });
         phase(PH_TRACE, [&] { MhdKernels<T>::trace(kp_, Uold, sc, ka - 1, fhi + 1, dt, stream_); });
+      }
+      if (sc.fused && fusedRequested()) {  // fused flux + emf + update (+ the border columns of the shearing box)
+        phase(PH_FUSED, [&] {
+          MhdKernels<T>::fusedFluxEmfUpdate(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_, shear, jplus, frac);
+        });
+        phase(PH_COPY, [&] { MhdKernels<T>::copyOutsideBox(kp_, Uold, Unew, ka, kb, stream_); });
+        continue;
       }
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });

@@ -63,3 +63,41 @@ def test_chunked_pipeline_is_identical(native):
     ref, _, _, _ = run_gpu(str(g["ini"]), 5)
     got, _, _, _ = run_gpu(str(g["ini"]), 5, chunk=4)
     assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("mesh,chunk", [
+    ({"nx": 16, "ny": 32, "nz": 16}, 0),                                             # one tile column: both x borders in the same tile
+    ({"nx": 40, "ny": 36, "nz": 20}, 0),                                             # 3 x 6 tiles, partial last tiles
+    ({"nx": 30, "ny": 14, "nz": 24}, 9),                                             # exact tile multiples, z chunks
+    ({"nx": 34, "ny": 20, "nz": 12, "boundary_xmin": 3, "boundary_xmax": 3}, 0),     # rotating frame without the shearing border
+])
+def test_fused_rotating_kernel_equals_separate_kernels(native, mesh, chunk):
+    """The rotating-frame instantiation of the fused flux + emf + update kernel (shear terms in the y flux and the emfs,
+    update_cell_rot, border strips + k_update_rot_border for the three cell columns that read the y-remapped opposite
+    border) against the separate k_flux / k_emf / k_update_rot kernels: the same device functions on the same inputs;
+    the compiler contracts a few multiply-adds differently, so agreement is to the last bits."""
+    from ramsesgpu_b200 import set_tuning
+    g = load_golden("mri3d_16x32x16_s12")
+    ini = ini_override(str(g["ini"]), {"mesh": mesh})
+    try:
+        set_tuning("fused_b", 0)
+        ref, tr, dtr, gw = run_gpu(ini, 8, chunk=chunk)
+        set_tuning("fused_b", 1)
+        got, tg, dtg, _ = run_gpu(ini, 8, chunk=chunk)
+    finally:
+        set_tuning("fused_b", 1)
+    assert np.allclose(dtr, dtg, rtol=1e-13, atol=0)
+    names = ["d", "e", "mx", "my", "mz", "bx", "by", "bz"]
+    check(ref, got, names, 1e-13)            # whole arrays, ghosts included
+
+
+def test_many_tiles_shearing_box_vs_oracle(native, oracle64):
+    """several tile columns / rows of the fused kernels with both shearing borders, against the oracle (6 steps)"""
+    g = load_golden("mri3d_16x32x16_s12")
+    ini = ini_override(str(g["ini"]), {"mesh": {"nx": 48, "ny": 40, "nz": 12}})
+    p = oracle64.params(ini)
+    nsteps = 6
+    Ug, tg, dtg, gw = run_gpu(ini, nsteps)
+    Uo, to, dto = oracle64.run_steps(p, oracle64.init_problem(p), nsteps)
+    check(Uo, Ug, ["d", "e", "mx", "my", "mz", "bx", "by", "bz"], TOL_F64)
+    assert np.allclose(dtg, dto, rtol=1e-12)

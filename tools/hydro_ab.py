@@ -18,11 +18,12 @@ with HydroRunGodunov(ini, fp32=not F64) as run:
     s = (0, 0.0, 0.0)
     for _ in range(3): s = run.oneStepIntegration(*s)
     for rep in range(2):
-        for fused, tile in ((0, 0), (0, 1), (1, 1)):
+        for fused, tile, rows in ((0, 1, 0), (1, 1, 12), (1, 1, 16), (1, 1, 20), (1, 1, 24)):
             set_tuning("hydro_fused", fused)
             set_tuning("hydro_tile", tile)
+            set_tuning("hydro_rows", rows)
             for _ in range(2): s = run.oneStepIntegration(*s)
             run.profile_begin()
             for _ in range(5): s = run.oneStepIntegration(*s)
             tot, ph = run.profile_end()
-            print("hydro_fused=%d hydro_tile=%d total %.3f ms/step %.0f Mcell/s |" % (fused, tile, tot / 5, N**3 * 5 / tot / 1e3), " ".join("%s %.3f" % (k, v[0] / 5) for k, v in ph.items() if v[0] > 0), flush=True)
+            print("rows=%2d hydro_fused=%d hydro_tile=%d total %.3f ms/step %.0f Mcell/s |" % (rows, fused, tile, tot / 5, N**3 * 5 / tot / 1e3), " ".join("%s %.3f" % (k, v[0] / 5) for k, v in ph.items() if v[0] > 0), flush=True)
