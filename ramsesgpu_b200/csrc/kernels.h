@@ -38,6 +38,9 @@ struct MhdKernels {
   // ghost fill of one direction (0,1,2), both faces; reference make_boundary2
   static void fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
                            int kLo, int kHi, cudaStream_t s);
+  // z ghost planes of the stratified shearing box (BC_Z_STRATIFIED, reference make_boundary_base.h:1357-1647) on the
+  // faces this rank owns; floorDensity = [MRI] floor (no hydrostatic extrapolation)
+  static void fillBoundaryZStratified(const KParams<T>& P, T* U, bool lo, bool hi, bool floorDensity, cudaStream_t s);
   // jet inflow patch in the lower ghost rows (2D) / planes (3D), after the ghost fill of the last direction;
   // reference make_jet, HydroRunBase.cpp:2374-2408 (hydro variables only)
   static void jetInflow(const KParams<T>& P, T* U, cudaStream_t s);
@@ -159,6 +162,8 @@ unsigned long long kernelLaunchCount();
 bool setTuning(const char* key, int value);
 // "fused_b" knob (default on): use the fused flux+emf+update kernel when MhdScratch::fused is set
 bool fusedRequested();
+// "rot_dt" knob (default on): the rotating-frame fused kernel reduces the inverse dt of the new state itself
+bool rotDtInKernel();
 // "fused_a" knob (default on): fused prim+elec+trace kernel
 bool fusedTraceRequested();
 void resetKernelLaunchCount();

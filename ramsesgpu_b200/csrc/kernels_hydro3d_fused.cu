@@ -25,7 +25,7 @@
 namespace rg {
 
 int g_hydroFused = 1;  // run-time knob "hydro_fused": the one-kernel step (default) or trace + flux/update through W
-int g_hydroRows = 0;   // run-time knob "hydro_rows": rows of the thread block (0 = default: 16 in FP32, 12 in FP64)
+int g_hydroRows = 0;   // run-time knob "hydro_rows": rows of the thread block (0 = default: 20 in FP32, 12 in FP64)
 
 namespace {
 
@@ -217,7 +217,9 @@ template <typename T>
 void HydroKernels<T>::fusedStep(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, T dt, unsigned long long* slots,
                                 cudaStream_t s) {
   if (k1 <= k0) return;
-  const int rows = g_hydroRows ? g_hydroRows : (sizeof(T) == 4 ? 16 : 12);
+  // measured at 512^3 FP32 HLLC / 384^3 FP64 (profiles/r02_c_hydro_rows_ab.txt): 12 rows 7.80 / 6.24 ms, 16: 6.50 / 6.50,
+  // 20: 5.95 / 7.27 (spills in FP64), 24: 6.00 / 8.65
+  const int rows = g_hydroRows ? g_hydroRows : (sizeof(T) == 4 ? 20 : 12);
   if (rows == 24) launchHydroFused<T, HydroFusedTile<T, 24>>(P, Uold, Unew, k0, k1, dt, slots, s);
   else if (rows == 20) launchHydroFused<T, HydroFusedTile<T, 20>>(P, Uold, Unew, k0, k1, dt, slots, s);
   else if (rows == 16) launchHydroFused<T, HydroFusedTile<T, 16>>(P, Uold, Unew, k0, k1, dt, slots, s);

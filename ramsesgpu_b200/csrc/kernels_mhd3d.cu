@@ -9,6 +9,7 @@
 // Index ranges follow the reference: prim 0..size-2, trace gw-1..size-gw,
 // flux/emf/update gw..size-gw (inclusive), with the reference's write guards.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -23,6 +24,8 @@ namespace rg {
 
 unsigned long long g_launches = 0;
 int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
+int g_rotDt = 1;   // run-time knob "rot_dt": rotating fused kernel reduces the next dt itself (1) or leaves it to k_invdt (0)
+bool rotDtInKernel() { return g_rotDt != 0; }
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
@@ -340,7 +343,9 @@ __device__ __forceinline__ void waitCount(const int* c, int full) {
 // the shear terms of the y flux and of the emfs, update_cell_rot for the cells of the tile, and -- with shearing-box
 // boundaries -- the fluxes / emfs of the four x-border position columns copied to compact strips in HBM, from which
 // k_update_rot_border updates the three cell columns that read the y-remapped OPPOSITE border (other tiles' data).
-template <typename T, typename C, bool FAST>
+// ROTDT (FAST = false only): the inverse dt of the new state inside the update (true) or left to k_invdt (false: less
+// code in the hot loop, which has to fit the instruction cache; knob "rot_dt")
+template <typename T, typename C, bool FAST, bool ROTDT = true>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapW,
                         const T* __restrict__ Uold, T* __restrict__ Unew, int kbase, int ka, int kb, int lz, T dt,
@@ -463,7 +468,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
             invDt = update_cell<true>(P, U, Unew, F, E, i, j, p - 1, dt);
           } else if (!(sh.enabled && (i == gw || i == P.nx + gw - 1 || i == P.nx + gw))) {
             // (the three cell columns next to a shearing x border are updated by k_update_rot_border)
-            invDt = update_cell_rot(P, U, Unew, F, E, F, E, i, j, p - 1, dt, sh);
+            invDt = update_cell_rot<false, ROTDT>(P, U, Unew, F, E, F, E, i, j, p - 1, dt, sh);
           }
         }
         if (dMaxInvDt != nullptr) reduceMaxToSlots(invDt, dMaxInvDt);
@@ -689,6 +694,45 @@ __global__ void k_boundary(const __grid_constant__ KParams<T> P, T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// z ghost planes of the stratified shearing box (reference make_boundary2_z_stratified, make_boundary_base.h:1357-1647,
+// ghost width 3): hydrostatic extrapolation of the density (r1, r2, r3 = density ratios of successive planes, 1 with
+// [MRI] floor), horizontal momenta scaled with it, vertical momentum copied when it points outwards and zero otherwise,
+// zero horizontal field, B_z continued with div B = 0 (the ghost B_x, B_y are zero, so B_z is constant along z; the
+// last row / column is left alone like in the reference).  One thread per (i, j) column of one face.
+template <typename T>
+__global__ void k_boundary_zstrat(const __grid_constant__ KParams<T> P, T* __restrict__ U, int hi, T r1, T r2, T r3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= P.isize || j >= P.jsize) return;
+  const int ksz = P.ksize;
+  const int e = hi ? ksz - 4 : 3, s = hi ? 1 : -1;
+  const int g1 = e + s, g2 = e + 2 * s, g3 = e + 3 * s;
+  const size_t plane = (size_t)P.isize * P.jsize, comp = plane * ksz;
+  auto at = [&](int v, int k) -> T& { return U[(size_t)v * comp + (size_t)k * plane + (size_t)j * P.isize + i]; };
+  const T rho_e = at(ID, e);
+  const T rho1 = rho_e * r1, rho2 = rho_e * r1 * r2, rho3 = rho_e * r1 * r2 * r3;
+  at(ID, g1) = rho1; at(ID, g2) = rho2; at(ID, g3) = rho3;
+  for (int v = IU; v <= IV; ++v) {
+    const T m = at(v, e);
+    at(v, g3) = m / rho_e * rho3;
+    at(v, g2) = m / rho_e * rho2;
+    at(v, g1) = m / rho_e * rho1;
+  }
+  const T we = at(IW, e);
+  const T w = hi ? ((we > T(0)) ? we : T(0)) : ((we < T(0)) ? we : T(0));
+  at(IW, g1) = w; at(IW, g2) = w; at(IW, g3) = w;
+  for (int v = IA; v <= IB; ++v) { at(v, g1) = T(0); at(v, g2) = T(0); at(v, g3) = T(0); }
+  if (i < P.isize - 1 && j < P.jsize - 1) {
+    if (!hi) {  // B_z on the low faces of ghost planes 2, 1, 0 from the one of plane 3
+      const T bz = at(IC, 3);
+      at(IC, 2) = bz; at(IC, 1) = bz; at(IC, 0) = bz;
+    } else {    // planes ksize-2, ksize-1 from the low-face B_z of plane ksize-3 (set by the CT update)
+      const T bz = at(IC, ksz - 3);
+      at(IC, ksz - 2) = bz; at(IC, ksz - 1) = bz;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // probes for the known-answer tests
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -734,6 +778,10 @@ bool setTuning(const char* key, int value) {
   }
   if (k == "fused_b") {
     g_fusedB = value ? 1 : 0;
+    return true;
+  }
+  if (k == "rot_dt") {
+    g_rotDt = value ? 1 : 0;
     return true;
   }
   if (k == "fused_a") {
@@ -806,6 +854,32 @@ void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, i
   dim3 grid((sizes[d1] + 31) / 32, (sizes[d2] + 7) / 8, 2 * P.gw);
   k_boundary<T><<<grid, block, 0, s>>>(P, U, dir, bcLo, bcHi, skipLo ? 1 : 0, skipHi ? 1 : 0, kLo, kHi);
   launched();
+}
+
+template <typename T>
+void MhdKernels<T>::fillBoundaryZStratified(const KParams<T>& P, T* U, bool lo, bool hi, bool floorDensity, cudaStream_t s) {
+  // density ratios of successive ghost planes: exp(-dz / (2 H^2) (+-2 z_face + (2n - 1) dz)), H = cIso / Omega0
+  const T dz = P.dz, HALF = T(0.5);
+  const T H = P.cIso / P.Omega0;
+  const T factor = static_cast<T>(-dz / 2.0 / H / H);
+  const dim3 block(32, 8, 1), grid((P.isize + 31) / 32, (P.jsize + 7) / 8, 1);
+  for (int side = 0; side < 2; ++side) {
+    if (side == 0 ? !lo : !hi) continue;
+    T r1 = T(1), r2 = T(1), r3 = T(1);
+    if (!floorDensity) {
+      if (side == 0) {
+        r1 = static_cast<T>(std::exp(factor * (-2 * (P.zMin + HALF * dz) + dz)));
+        r2 = static_cast<T>(std::exp(factor * (-2 * (P.zMin + HALF * dz) + 3.0 * dz)));
+        r3 = static_cast<T>(std::exp(factor * (-2 * (P.zMin + HALF * dz) + 5.0 * dz)));
+      } else {
+        r1 = static_cast<T>(std::exp(factor * (2 * (P.zMax - HALF * dz) + dz)));
+        r2 = static_cast<T>(std::exp(factor * (2 * (P.zMax - HALF * dz) + 3.0 * dz)));
+        r3 = static_cast<T>(std::exp(factor * (2 * (P.zMax - HALF * dz) + 5.0 * dz)));
+      }
+    }
+    k_boundary_zstrat<T><<<grid, block, 0, s>>>(P, U, side, r1, r2, r3);
+    launched();
+  }
 }
 
 template <typename T>
@@ -1002,7 +1076,9 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
     if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
             cudaSuccess ||
         cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
-            cudaSuccess) {
+            cudaSuccess ||
+        cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)C::SMEM) != cudaSuccess) {
       cudaGetLastError();
       return;
     }
@@ -1045,13 +1121,17 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
     return;
   }
   // rotating frame; with shearing-box boundaries the three border cell columns follow from the strips
-  k_fused_flux_emf_update<T, C, false><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh,
-                                                                         sc.strips, sc.planes);
+  if (g_rotDt)
+    k_fused_flux_emf_update<T, C, false, true><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt,
+                                                                                 d, sh, sc.strips, sc.planes);
+  else
+    k_fused_flux_emf_update<T, C, false, false><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt,
+                                                                                  nullptr, sh, sc.strips, sc.planes);
   launched();
   if (shearEnabled) {
     const int nRows = P.jsize - 2 * P.gw + 1;
     k_update_rot_border<T><<<dim3((3 * nRows + 127) / 128, 1, kb - ka), 128, 0, s>>>(P, Uold, Unew, sc.strips, sc.planes,
-                                                                                       sc.kbase, ka, dt, sh, d);
+                                                                                       sc.kbase, ka, dt, sh, g_rotDt ? d : nullptr);
     launched();
   }
 }

@@ -24,6 +24,12 @@ enum {
 // there and W carries 38 components instead of 47.
 static_assert(W_DCLY + 1 == NW_MHD, "W layout");
 
+// vertical gravity of local plane k: the per-plane field of the stratified shearing box, else the uniform field
+template <typename T>
+__device__ __forceinline__ T grav_z(const KParams<T>& P, int k) {
+  return (P.gzPlane != nullptr) ? P.gzPlane[k] : P.gz;
+}
+
 // ------------------------------------------------------------------------------------------------
 // edge-centred electric field E = v x B at the LOW edges of a cell (reference cpu_v3.cpp:36-101)
 // ------------------------------------------------------------------------------------------------
@@ -207,7 +213,7 @@ __device__ __forceinline__ void trace_cell(const KParams<T>& P, const QV& Q, con
   }
   if (P.gravity) {  // gravity predictor on every traced velocity of the cell (reference cpu_v3.cpp:277-332):
     const T hdt = h * dt;  // face / edge states are centre +/- slopes, so it goes into the centre value
-    su0 += hdt * P.gx; sv0 += hdt * P.gy; sw0 += hdt * P.gz;
+    su0 += hdt * P.gx; sv0 += hdt * P.gy; sw0 += hdt * grav_z(P, k);
   }
   W(W_R, i, j, k) = r + sr0;  W(W_P, i, j, k) = p + sp0;
   W(W_U, i, j, k) = u + su0;  W(W_V, i, j, k) = v + sv0;  W(W_W, i, j, k) = w + sw0;
@@ -319,7 +325,7 @@ __device__ __forceinline__ T update_cell(const KParams<T>& P, const UV& U, T* __
     }
     if (P.gravity) {  // static gravity source term on the momenta, reference HydroRunBase.cpp:1962-1976
       const T hdt = T(0.5) * dt, rs = U(ID, i, j, k) + un[ID];
-      un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * P.gz * rs;
+      un[IU] += hdt * P.gx * rs; un[IV] += hdt * P.gy * rs; un[IW] += hdt * grav_z(P, k) * rs;
     }
   }
   // emf(c, ...) with the never-computed indexes (one past the upper ghost face) read as zero,
@@ -413,7 +419,10 @@ struct BorderView {
 // state; with shearing-box boundaries the density flux and emf_y of the two x borders are averaged with the y-remapped
 // opposite border (:3237-3297), read through Fb / Eb (any row of the border columns), and the border density is floored.
 // F / E give the fluxes / emfs around the cell itself.  Returns the inverse time step (0 outside the inner cells).
-template <typename T, typename UV, typename FV, typename EV, typename FBV, typename EBV>
+// BORDERS = false: a caller that never passes a cell next to a shearing x border (the fused kernel leaves those three
+// columns to k_update_rot_border) compiles the remap code away -- the fused kernel has to fit the instruction cache.
+// WITH_DT = false: no inverse-dt estimate of the new state (the caller runs the stand-alone reduction afterwards).
+template <bool BORDERS = true, bool WITH_DT = true, typename T, typename UV, typename FV, typename EV, typename FBV, typename EBV>
 __device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T* __restrict__ Unew, const FV& F,
                                              const EV& E, const FBV& Fb, const EBV& Eb, int i, int j, int k, T dt,
                                              const ShearShift<T>& sh) {
@@ -437,7 +446,7 @@ __device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T
     m[ID] = un[ID]; m[IP] = un[IP]; m[IW] = un[IW];
     m[IU] = un[IU] * ratio + dsx;
     m[IV] = un[IV] * ratio + dsy;
-    const bool bLo = sh.enabled && i == gw, bHi = sh.enabled && i == P.nx + gw - 1;
+    const bool bLo = BORDERS && sh.enabled && i == gw, bHi = BORDERS && sh.enabled && i == P.nx + gw - 1;
     // flux contributions in the reference's order: +x(i) +y(j) +z(k) -x(i+1) -y(j+1) -z(k+1)
     auto add = [&](int c0, int ii, int jj, int kk, T s, T dtd, bool skipDensity) {
       const T fd = F(c0 + 0, ii, jj, kk), fp = F(c0 + 1, ii, jj, kk), fu = F(c0 + 2, ii, jj, kk),
@@ -454,7 +463,12 @@ __device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T
     add(0, i + 1, j, k, T(-1), dtdx, bHi);
     add(5, i, j + 1, k, T(-1), dtdy, false);
     add(10, i, j, k + 1, T(-1), dtdz, false);
-    if (bLo || bHi) {  // remapped border density flux, :3237-3297
+    if (P.gravity) {  // gravity source term BEFORE the border remap of the density (MHDRunGodunov.cpp:3188-3192 vs :3203)
+      const T hdt = T(0.5) * dt, rs = un[ID] + m[ID];
+      m[IU] += hdt * P.gx * rs; m[IV] += hdt * P.gy * rs;
+      m[IW] += hdt * grav_z(P, k) * rs;
+    }
+    if (BORDERS && (bLo || bHi)) {  // remapped border density flux, :3237-3297
       int j0, j1; T eps;
       remapRows(P, sh, j, bLo, j0, j1, eps);
       const int iOwn = bLo ? gw : P.nx + gw, iOpp = bLo ? P.nx + gw : gw;
@@ -470,7 +484,7 @@ __device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T
   auto emfY = [&](int ii, int jj, int kk) -> T {
     if (ii > iN || jj > jN || kk > kN) return T(0);
     const T own = E(1, ii, jj, kk);
-    if (sh.enabled && (ii == gw || ii == P.nx + gw)) {
+    if (BORDERS && sh.enabled && (ii == gw || ii == P.nx + gw)) {
       int j0, j1; T eps;
       remapRows(P, sh, jj, ii == gw, j0, j1, eps);
       const int iOpp = (ii == gw) ? P.nx + gw : gw;
@@ -499,7 +513,7 @@ __device__ __forceinline__ T update_cell_rot(const KParams<T>& P, const UV& U, T
   un[IC] = ctz(i, j, k, un[IC]);
 #pragma unroll
   for (int v = 0; v < 8; ++v) Unew[v * comp + idx] = un[v];
-  if (inner) {
+  if (WITH_DT && inner) {
     const T bxp = ctx(i + 1, j, k, U(IA, i + 1, j, k));
     const T byp = cty(i, j + 1, k, U(IB, i, j + 1, k));
     const T bzp = ctz(i, j, k + 1, U(IC, i, j, k + 1));

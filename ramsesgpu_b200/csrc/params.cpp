@@ -114,6 +114,7 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
   k.eta = rp.mhdEnabled ? T(cfg.getFloat("MHD", "eta", 0.0f)) : T(0);
   k.gravity = (cfg.getBool("gravity", "static", false) || cfg.getBool("gravity", "self", false)) ? 1 : 0;
   k.gx = k.gy = k.gz = T(0);
+  k.gzPlane = nullptr;
   if (rp.problem == "Rayleigh-Taylor") {
     k.gravity = 1;
     k.gx = cfg.getFloat("gravity", "static_field_x", 0.0f);
@@ -129,6 +130,29 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
   k.cjet = std::sqrt(k.gamma0 * k.pjet / k.djet);
   return k;
 }
+
+template <typename T>
+bool stratifiedGravityPlanes(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& gz) {
+  const bool mri = rp.problem == "MRI" || rp.problem == "Mri" || rp.problem == "mri";
+  if (!kp.gravity || !rp.mhdEnabled || !mri) return false;
+  const bool smooth = cfg.getBool("MRI", "smoothGravity", false);
+  const double zFloor = cfg.getFloat("MRI", "zFloor", 5.0f);
+  const T Omega0 = kp.Omega0, dz = kp.dz, HALF = T(0.5);
+  gz.assign(kp.ksize, T(0));
+  for (int k = 0; k < kp.ksize; ++k) {
+    const T zPos = kp.zMin + dz / 2 + (k + kp.kglob0 - kp.gw) * dz;
+    double phi0 = HALF * Omega0 * Omega0 * (zPos - dz) * (zPos - dz);
+    double phi1 = HALF * Omega0 * Omega0 * (zPos + dz) * (zPos + dz);
+    if (smooth) {
+      if ((zPos - dz) > zFloor) phi0 = HALF * Omega0 * Omega0 * zFloor * zFloor;
+      if ((zPos + dz) > zFloor) phi1 = HALF * Omega0 * Omega0 * zFloor * zFloor;
+    }
+    gz[k] = static_cast<T>(-HALF * (phi1 - phi0) / dz);
+  }
+  return true;
+}
+template bool stratifiedGravityPlanes<double>(const ConfigMap&, const RunParams&, const KParams<double>&, std::vector<double>&);
+template bool stratifiedGravityPlanes<float>(const ConfigMap&, const RunParams&, const KParams<float>&, std::vector<float>&);
 
 template KParams<double> makeKParams<double>(const ConfigMap&, const RunParams&, int, int);
 template KParams<float> makeKParams<float>(const ConfigMap&, const RunParams&, int, int);

@@ -4,6 +4,7 @@
 // (__grid_constant__), replacing the reference's __constant__ gParams.
 #pragma once
 #include <string>
+#include <vector>
 
 #include "config_map.h"
 
@@ -39,6 +40,10 @@ struct KParams {
   T nu, eta;
   int gravity;
   T gx, gy, gz;
+  // vertical field of the stratified shearing box (MRI problem with [gravity] static=yes; reference
+  // init_mhd_mri_grav_field, MHDRunBase.cpp:3163-3211): g_z of every LOCAL plane, a device array of ksize reals owned
+  // by the run handle (null: the uniform field above)
+  const T* gzPlane;
   // jet inflow through a square patch of the lower ghost rows (2D: y) / planes (3D: z), problem "jet"
   // (reference HydroParameters.h:434-444, HydroRunBase.cpp:2374-2408)
   int jet, ijet, offsetJet;
@@ -66,6 +71,12 @@ struct RunParams {
 };
 
 RunParams parseRunParams(const ConfigMap& cfg);
+
+// g_z of the local planes of the stratified shearing box: -(phi(z+dz) - phi(z-dz)) / (2 dz) with phi = Omega0^2 z^2 / 2,
+// optionally flattened above [MRI] zFloor ([MRI] smoothGravity); phi is held in double like the reference.  Returns
+// false when the run has no such field (no gravity, or the uniform field of Rayleigh-Taylor).
+template <typename T>
+bool stratifiedGravityPlanes(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& gz);
 
 // Fills the kernel parameter block in precision T (derived quantities are computed IN T, like the
 // reference build for that precision).  nzLocal/kglob0 describe this rank's z-slab.

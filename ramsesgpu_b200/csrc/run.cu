@@ -85,8 +85,9 @@ class RunImpl final : public Run {
     kp_ = makeKParams<T>(cfg_, rp_, nzLocal, kOff);
     // variants of the reference that are not built must fail loudly, not run with silently different numerics
     for (int f = 0; f < 2 * rp_.dim; ++f)
-      if (rp_.bc[f] == BC_COPY || rp_.bc[f] == BC_Z_STRATIFIED)
-        throw std::runtime_error("boundary type " + std::to_string(rp_.bc[f]) + " (copy / z-stratified) is not available in this build");
+      if (rp_.bc[f] == BC_COPY || (rp_.bc[f] == BC_Z_STRATIFIED && !(f >= 4 && rp_.mhdEnabled && rp_.dim == 3)))
+        throw std::runtime_error("boundary type " + std::to_string(rp_.bc[f]) +
+                                 " (copy; z-stratified outside the z faces of a 3D MHD run) is not available in this build");
     // slope_type 3 (27-point slopes, slope_mhd.h:352-409) exists for the non-rotating 3D MHD step, like in the
     // reference (its rotating CPU step never fills the slopes for that type, its 2D and hydro steps ignore it)
     if (kp_.slope_type == T(3) && !(rp_.mhdEnabled && rp_.dim == 3 && !(kp_.Omega0 > T(0))))
@@ -110,6 +111,13 @@ class RunImpl final : public Run {
     RG_CUDA(cudaMalloc(&dMax_, 2 * MAX_SLOTS * sizeof(unsigned long long)));
     RG_CUDA(cudaMemset(dMax_, 0, 2 * MAX_SLOTS * sizeof(unsigned long long)));
     RG_CUDA(cudaMallocHost(&hMax_, MAX_SLOTS * sizeof(unsigned long long)));
+    // vertical gravity field of the stratified shearing box: one value per local plane
+    std::vector<T> gz;
+    if (stratifiedGravityPlanes<T>(cfg_, rp_, kp_, gz)) {
+      RG_CUDA(cudaMalloc(&dGz_, gz.size() * sizeof(T)));
+      RG_CUDA(cudaMemcpy(dGz_, gz.data(), gz.size() * sizeof(T), cudaMemcpyHostToDevice));
+      kp_.gzPlane = dGz_;
+    }
     if (nranks_ > 1) initComm(dist);
   }
 
@@ -120,6 +128,7 @@ class RunImpl final : public Run {
     for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
     cudaFree(dDiss_);
     cudaFree(dHist_);
+    cudaFree(dGz_);
     for (int b = 0; b < 2; ++b) {
       if (batchBuf_[b]) cudaFree(batchBuf_[b]);
       if (evH2D_[b]) cudaEventDestroy(evH2D_[b]);
@@ -278,8 +287,8 @@ class RunImpl final : public Run {
     const bool rotating = rp_.mhdEnabled && kp_.Omega0 > T(0);
     // the rotating-frame step fills the ghosts of UNew at its END (reference MHDRunGodunov.cpp:3429-3437)
     if (!rotating && !ghostsValid_[src]) make_all_boundaries(src);
-    if (kp_.gravity && (rotating || rp_.dim != 3))
-      throw std::runtime_error("static gravity is available for the non-rotating 3D solvers only");
+    if (kp_.gravity && rp_.dim != 3)
+      throw std::runtime_error("static gravity is available for the 3D solvers only");
     if ((kp_.nu > T(0) || kp_.eta > T(0)) && rp_.dim != 3)
       throw std::runtime_error("viscosity / resistivity are available for the 3D solvers only");
     if (rotating && rp_.dim == 3) {
@@ -674,6 +683,14 @@ class RunImpl final : public Run {
     *hasHi = rank_ < nranks_ - 1 || periodic;
   }
 
+  // physical z faces this rank owns: Dirichlet / Neumann / periodic copies, or the hydrostatic extrapolation of the
+  // stratified shearing box (BC_Z_STRATIFIED)
+  void fillZFaces(T* U, bool skipLo, bool skipHi) {
+    MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], skipLo, skipHi, 0, kp_.ksize, stream_);
+    const bool lo = rp_.bc[4] == BC_Z_STRATIFIED && !skipLo, hi = rp_.bc[5] == BC_Z_STRATIFIED && !skipHi;
+    if (lo || hi) MhdKernels<T>::fillBoundaryZStratified(kp_, U, lo, hi, cfg_.getBool("MRI", "floor", false), stream_);
+  }
+
   void fillGhosts(int b, int kLo, int kHi) {
     T* U = dU_[b];
     if (haloDone_[b]) {  // the z halo of this buffer was exchanged early (overlapped with the step)
@@ -683,7 +700,7 @@ class RunImpl final : public Run {
       MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
       MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
       if (rp_.dim == 3 && nranks_ == 1)
-        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
+        fillZFaces(U, false, false);
       // jet inflow patch after the last direction (reference HydroRunBase.cpp:2290, :2310); with slabs below
       if (kp_.jet && (rp_.dim == 2 || nranks_ == 1)) MhdKernels<T>::jetInflow(kp_, U, stream_);
     });
@@ -693,7 +710,7 @@ class RunImpl final : public Run {
     // physical z faces of the outermost slabs
     if (!hasLo || !hasHi)
       phase(PH_BOUNDARY, [&] {
-        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
+        fillZFaces(U, hasLo, hasHi);
         if (kp_.jet && !hasLo) MhdKernels<T>::jetInflow(kp_, U, stream_);  // the slab that owns the lower z face
       });
     if (haloDone_[b]) {
@@ -919,14 +936,14 @@ class RunImpl final : public Run {
     });
     if (nranks_ == 1) {
       phase(PH_BOUNDARY, [&] {
-        MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], false, false, 0, kp_.ksize, stream_);
+        fillZFaces(U, false, false);
       });
     } else {
       bool hasLo, hasHi;
       zNeighbours(&hasLo, &hasHi);
       if (!hasLo || !hasHi)
         phase(PH_BOUNDARY, [&] {
-          MhdKernels<T>::fillBoundary(kp_, U, 2, rp_.bc[4], rp_.bc[5], hasLo, hasHi, 0, kp_.ksize, stream_);
+          fillZFaces(U, hasLo, hasHi);
         });
       phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi, stream_); });
     }
@@ -955,6 +972,7 @@ class RunImpl final : public Run {
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, 0, gw, stream_);
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN + 1, kp_.ksize, stream_);
     });
+    bool fusedRotNoDt = false;
     for (int ka = gw; ka <= kN; ka += chunkPlanes_) {
       const int kb = std::min(ka + chunkPlanes_, kN + 1), fhi = std::min(kb, kN);
       MhdScratch<T> sc = sc_;
@@ -971,6 +989,7 @@ class RunImpl final : public Run {
           MhdKernels<T>::fusedFluxEmfUpdate(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_, shear, jplus, frac);
         });
         phase(PH_COPY, [&] { MhdKernels<T>::copyOutsideBox(kp_, Uold, Unew, ka, kb, stream_); });
+        fusedRotNoDt = !rotDtInKernel();
         continue;
       }
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
@@ -979,7 +998,7 @@ class RunImpl final : public Run {
         MhdKernels<T>::updateRotating(kp_, Uold, Unew, sc, ka, kb, dt, shear, jplus, frac, slots, stream_);
       });
     }
-    dtCached_[dst] = true;
+    dtCached_[dst] = !fusedRotNoDt;  // (knob rot_dt = 0: compute_dt runs the stand-alone reduction on the new state)
     if (dissipative()) {  // reference MHDRunGodunov.cpp:3379-3419: ghost refresh, then the dissipative terms
       if (shear) fillGhostsShear(dst, dt);
       else fillGhosts(dst, 0, kp_.ksize);
@@ -1109,6 +1128,7 @@ class RunImpl final : public Run {
   double resumeDt_ = 0.0;  // next dt read from a restart sidecar
   double* dHist_ = nullptr;  // partial sums of the history kernels
   std::vector<double> hHist_;
+  T* dGz_ = nullptr;    // g_z per local plane (stratified shearing box)
   T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;
