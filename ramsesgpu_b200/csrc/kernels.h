@@ -162,7 +162,7 @@ unsigned long long kernelLaunchCount();
 bool setTuning(const char* key, int value);
 // "fused_b" knob (default on): use the fused flux+emf+update kernel when MhdScratch::fused is set
 bool fusedRequested();
-// "rot_dt" knob (default on): the rotating-frame fused kernel reduces the inverse dt of the new state itself
+// "rot_dt" knob (default off): the rotating-frame fused kernel reduces the inverse dt of the new state itself
 bool rotDtInKernel();
 // "fused_a" knob (default on): fused prim+elec+trace kernel
 bool fusedTraceRequested();

@@ -119,7 +119,7 @@ def test_rotating_fused_kernel_dt_in_kernel_or_separate(native):
         set_tuning("rot_dt", 0)
         b, tb, dtb, _ = run_gpu(ini, 6)
     finally:
-        set_tuning("rot_dt", 1)
+        set_tuning("rot_dt", 0)
     assert np.array_equal(dta, dtb) and np.array_equal(a, b)
 
 

@@ -31,4 +31,4 @@ for rep in range(2):
         print("fused_b=%d rot_dt=%d total %.3f ms/step %.0f Mcell/s |" % (fused, rotdt, tot / 10, cells * 10 / tot / 1e3),
               " ".join("%s %.3f" % (k, v[0] / 10) for k, v in ph.items() if v[0] > 0), flush=True)
 set_tuning("fused_b", 1)
-set_tuning("rot_dt", 1)
+set_tuning("rot_dt", 0)
