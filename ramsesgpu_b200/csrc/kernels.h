@@ -76,7 +76,7 @@ struct MhdKernels {
   // y-shifted x ghost cells; (jplus, frac) = whole cells and fraction of dy of the border shift
   static void updateRotating(const KParams<T>& P, const T* Uold, T* Unew, MhdScratch<T> sc, int k0, int k1, T dt,
                              int shearEnabled, int jplus, T frac, unsigned long long* dMaxInvDt, cudaStream_t s);
-  static void shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, cudaStream_t s);
+  static void shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, int k0, int k1, cudaStream_t s);  // planes [k0, k1)
   // copy planes [k0,k1) of every variable (ghost planes that the update does not touch)
   static void copyPlanes(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, cudaStream_t s);
   // device probes for known-answer tests (n independent problems, arrays are [n][...])

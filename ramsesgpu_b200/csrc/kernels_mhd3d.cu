@@ -571,12 +571,12 @@ __global__ void __launch_bounds__(128) k_update_rot_border(const __grid_constant
 // deltay(t+dt), second order with limited y slopes (B_y: first-order difference slope)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_shear_ghosts(const __grid_constant__ KParams<T> P, T* __restrict__ U, const ShearShift<T> sh) {
+__global__ void k_shear_ghosts(const __grid_constant__ KParams<T> P, T* __restrict__ U, const ShearShift<T> sh, int k0) {
   const int gw = P.gw, nx = P.nx;
   // thread = (ghost slot g in [0, 2gw), inner row j, plane k)
   const int g = threadIdx.x % (2 * gw);
   const int j = gw + blockIdx.x * (blockDim.x / (2 * gw)) + threadIdx.x / (2 * gw);
-  const int k = blockIdx.y;
+  const int k = k0 + blockIdx.y;
   if (threadIdx.x >= (blockDim.x / (2 * gw)) * 2 * gw || j >= P.jsize - gw) return;
   const bool lo = g < gw;
   const int gg = lo ? g : g - gw;
@@ -735,6 +735,37 @@ __global__ void k_boundary_zstrat(const __grid_constant__ KParams<T> P, T* __res
   }
 }
 
+// x direction of the ghost fill with the 2 gw ghost cells of a row on CONSECUTIVE lanes: a warp touches 32 / (2 gw) rows
+// with one short contiguous segment per row and face, instead of 32 rows with one element each (k_boundary's mapping,
+// right for y and z where a warp runs along x).  Same copies, same values.
+template <typename T>
+__global__ void __launch_bounds__(256) k_boundary_x(const __grid_constant__ KParams<T> P, T* __restrict__ U, int bcLo, int bcHi,
+                                                    int skipLo, int skipHi, int kLo, int kHi) {
+  const int gw = P.gw, per = 2 * gw, n = P.nx;
+  const int rowsPerBlock = blockDim.x / per;
+  const int g = threadIdx.x % per;
+  const long row = (long)blockIdx.x * rowsPerBlock + threadIdx.x / per;  // row = j + jsize * k
+  if ((int)threadIdx.x >= rowsPerBlock * per || row >= (long)P.jsize * P.ksize) return;
+  const int k = (int)(row / P.jsize);
+  if (k < kLo || k >= kHi) return;
+  const bool hi = g >= gw;
+  if (hi ? skipHi : skipLo) return;
+  const int bct = hi ? bcHi : bcLo;
+  if (bct != BC_DIRICHLET && bct != BC_NEUMANN && bct != BC_PERIODIC) return;
+  const int gi = hi ? n + g : g;
+  int src;
+  if (bct == BC_DIRICHLET) src = hi ? 2 * n + 2 * gw - 1 - gi : 2 * gw - 1 - gi;
+  else if (bct == BC_NEUMANN) src = hi ? n + gw - 1 : gw;
+  else src = hi ? gi - n : gi + n;
+  const size_t comp = (size_t)P.isize * P.jsize * P.ksize;
+  const size_t base = (size_t)row * P.isize;
+  for (int v = 0; v < P.nvar; ++v) {
+    T val = U[v * comp + base + src];
+    if (bct == BC_DIRICHLET && v == IU) val = -val;
+    U[v * comp + base + gi] = val;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // probes for the known-answer tests
 // ------------------------------------------------------------------------------------------------
@@ -805,7 +836,7 @@ bool setTuning(const char* key, int value) {
     return true;
   }
   if (k == "trace_qy") {
-    if (value != 8 && value != 12) return false;
+    if (value != 8 && value != 12 && value != 16) return false;
     g_traceQY = value;
     return true;
   }
@@ -851,6 +882,14 @@ template <typename T>
 void MhdKernels<T>::fillBoundary(const KParams<T>& P, T* U, int dir, int bcLo, int bcHi, bool skipLo, bool skipHi,
                                  int kLo, int kHi, cudaStream_t s) {
   if (dir == 2 && P.dim == 2) return;
+  if (dir == 0) {
+    const int per = 2 * P.gw, rowsPerBlock = 256 / per;
+    const long rows = (long)P.jsize * P.ksize;
+    k_boundary_x<T><<<(unsigned)((rows + rowsPerBlock - 1) / rowsPerBlock), 256, 0, s>>>(P, U, bcLo, bcHi, skipLo ? 1 : 0,
+                                                                                         skipHi ? 1 : 0, kLo, kHi);
+    launched();
+    return;
+  }
   const int sizes[3] = {P.isize, P.jsize, P.ksize};
   const int d1 = (dir == 0) ? 1 : 0, d2 = (dir == 2) ? 1 : 2;
   dim3 block(32, 8, 1);
@@ -1004,6 +1043,8 @@ bool MhdKernels<T>::fusedTraceAvailable(const KParams<T>& P) {
   if (ok < 0)
     ok = (cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<8>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<8>::SMEM) == cudaSuccess &&
+          cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<16>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)TraceTileT<16>::SMEM) == cudaSuccess &&
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)TraceTileT<12>::SMEM) == cudaSuccess &&
           cudaFuncSetAttribute(k_fused_trace<T, TraceTileT<12>, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1041,6 +1082,7 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
   const int nSM = smCount();
   if (!fastPath(P)) launchFusedTrace<T, TraceTileT<12>, false>(P, U, sc, k0, k1, dt, nSM, s);
   else if (g_traceQY == 12) launchFusedTrace<T, TraceTileT<12>, true>(P, U, sc, k0, k1, dt, nSM, s);
+  else if (g_traceQY == 16) launchFusedTrace<T, TraceTileT<16>, true>(P, U, sc, k0, k1, dt, nSM, s);
   else launchFusedTrace<T, TraceTileT<8>, true>(P, U, sc, k0, k1, dt, nSM, s);
   launched();
 }
@@ -1158,11 +1200,12 @@ void MhdKernels<T>::updateRotating(const KParams<T>& P, const T* Uold, T* Unew, 
 }
 
 template <typename T>
-void MhdKernels<T>::shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, cudaStream_t s) {
+void MhdKernels<T>::shearGhosts(const KParams<T>& P, T* U, int jplus, T frac, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
   ShearShift<T> sh{1, jplus, frac};
   const int per = 2 * P.gw, rows = 128 / per;
-  dim3 grid((P.ny + rows - 1) / rows, P.ksize, 1);
-  k_shear_ghosts<T><<<grid, 128, 0, s>>>(P, U, sh);
+  dim3 grid((P.ny + rows - 1) / rows, k1 - k0, 1);
+  k_shear_ghosts<T><<<grid, 128, 0, s>>>(P, U, sh, k0);
   launched();
 }
 

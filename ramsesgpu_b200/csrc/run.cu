@@ -930,9 +930,28 @@ class RunImpl final : public Run {
     T* U = dU_[b];
     int jplus; T frac;
     shearShift(static_cast<T>(totalTime) + dt, &jplus, &frac);
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    if (haloDone_[b]) {
+      // the planes next to the slab interfaces were filled (Y, shear-X) and exchanged by startEarlyHaloShear() while the
+      // interior was being updated: the same per-plane operations on the remaining inner planes, then the order of the
+      // reference again (physical z faces, Y)
+      bool hasLo, hasHi;
+      zNeighbours(&hasLo, &hasHi);
+      phase(PH_BOUNDARY, [&] {
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 2 * gw, kN - gw, stream_);
+        MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, 2 * gw, kN - gw, stream_);
+      });
+      RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
+      haloDone_[b] = false;
+      phase(PH_BOUNDARY, [&] {
+        if (!hasLo || !hasHi) fillZFaces(U, hasLo, hasHi);
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, kp_.ksize, stream_);
+      });
+      return;
+    }
     phase(PH_BOUNDARY, [&] {
       MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, kp_.ksize, stream_);
-      MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, stream_);
+      MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, 0, kp_.ksize, stream_);
     });
     if (nranks_ == 1) {
       phase(PH_BOUNDARY, [&] {
@@ -950,6 +969,28 @@ class RunImpl final : public Run {
     phase(PH_BOUNDARY, [&] {
       MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, kp_.ksize, stream_);
     });
+  }
+
+  // Early halo of the shearing box: the rotating step fills the ghosts of the NEW state at its end (Y, shear-X, Z, Y).
+  // Y and shear-X act plane by plane, so as soon as the gw inner planes next to each slab interface are final they are
+  // filled and exchanged on the communication stream while the interior is still being updated; fillGhostsShear()
+  // finishes the remaining planes.  (Not with z-stratified faces: their ghost planes keep two entries of the first fill.)
+  void startEarlyHaloShear(int b, T dt) {
+    T* U = dU_[b];
+    const int gw = kp_.gw, kN = kp_.ksize - gw;
+    int jplus; T frac;
+    shearShift(static_cast<T>(totalTime) + dt, &jplus, &frac);
+    bool hasLo, hasHi;
+    zNeighbours(&hasLo, &hasHi);
+    RG_CUDA(cudaEventRecord(evEdge_, stream_));
+    RG_CUDA(cudaStreamWaitEvent(comm_stream_, evEdge_, 0));
+    MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, gw, 2 * gw, comm_stream_);
+    MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, gw, 2 * gw, comm_stream_);
+    MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kN - gw, kN, comm_stream_);
+    MhdKernels<T>::shearGhosts(kp_, U, jplus, frac, kN - gw, kN, comm_stream_);
+    exchangeZ(U, hasLo, hasHi, comm_stream_);
+    RG_CUDA(cudaEventRecord(evHalo_, comm_stream_));
+    haloDone_[b] = true;
   }
 
   // ---- 3D MHD step in the rotating frame (Omega0 > 0), with or without shearing-box boundaries:
@@ -973,8 +1014,8 @@ class RunImpl final : public Run {
       MhdKernels<T>::copyPlanes(kp_, Uold, Unew, kN + 1, kp_.ksize, stream_);
     });
     bool fusedRotNoDt = false;
-    for (int ka = gw; ka <= kN; ka += chunkPlanes_) {
-      const int kb = std::min(ka + chunkPlanes_, kN + 1), fhi = std::min(kb, kN);
+    auto runChunk = [&](int ka, int kb) {  // update planes [ka, kb)
+      const int fhi = std::min(kb, kN);
       MhdScratch<T> sc = sc_;
       sc.kbase = ka - 2;
       if (fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_)) {
@@ -990,13 +1031,29 @@ class RunImpl final : public Run {
         });
         phase(PH_COPY, [&] { MhdKernels<T>::copyOutsideBox(kp_, Uold, Unew, ka, kb, stream_); });
         fusedRotNoDt = !rotDtInKernel();
-        continue;
+        return;
       }
       phase(PH_FLUX, [&] { MhdKernels<T>::flux(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_EMF, [&] { MhdKernels<T>::emf(kp_, sc, ka, fhi + 1, stream_); });
       phase(PH_UPDATE, [&] {
         MhdKernels<T>::updateRotating(kp_, Uold, Unew, sc, ka, kb, dt, shear, jplus, frac, slots, stream_);
       });
+    };
+    auto runRange = [&](int k0, int k1) {
+      for (int ka = k0; ka < k1; ka += chunkPlanes_) runChunk(ka, std::min(ka + chunkPlanes_, k1));
+    };
+    // the ghosts of the new state are filled at the END of this step: with slabs, the planes next to the interfaces are
+    // updated first and travel on the communication stream while the interior is updated (see startEarlyHaloShear)
+    const bool stratZ = rp_.bc[4] == BC_Z_STRATIFIED || rp_.bc[5] == BC_Z_STRATIFIED;
+    const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative() && !stratZ;
+    if (overlap) {
+      runRange(gw, 2 * gw);
+      runRange(kN - gw, kN + 1);
+      if (shear) startEarlyHaloShear(dst, dt);
+      else startEarlyHalo(dst);
+      runRange(2 * gw, kN - gw);
+    } else {
+      runRange(gw, kN + 1);
     }
     dtCached_[dst] = !fusedRotNoDt;  // (knob rot_dt = 0: compute_dt runs the stand-alone reduction on the new state)
     if (dissipative()) {  // reference MHDRunGodunov.cpp:3379-3419: ghost refresh, then the dissipative terms
