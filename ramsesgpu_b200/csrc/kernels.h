@@ -25,6 +25,11 @@ struct MhdScratch {
   T* F = nullptr;     // 15 components: flux_x[5], flux_y[5], flux_z[5] at the LOW faces
   T* E = nullptr;     // 3 components: emf z, y, x at the LOW edges (reference order I_EMFZ=0..)
   T* EL = nullptr;    // 3 components: v x B at the LOW edges (x, y, z), input of the trace
+  // hand-off records of the fused update (closing column / row of a tile published by its neighbours) and the tile
+  // counter + per-tile progress flags; sized by fusedHandoffSize() for the largest launch of a chunk
+  T* hbuf = nullptr;
+  int* hsync = nullptr;
+  size_t hbufReals = 0, hsyncInts = 0;
   T* strips = nullptr;  // shearing box on the fused kernels: F[15] + E[3] of the 4 x-border position columns, [18][kk][j][4]
   int planes = 0;     // allocated planes per component
   int kbase = 0;      // k of scratch plane 0 for the chunk being processed
@@ -60,6 +65,8 @@ struct MhdKernels {
   static void fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc);
   // what fusedPrepare() will decide from the run parameters alone (before any scratch exists)
   static bool fusedUpdateEligible(const KParams<T>& P);
+  // reals / ints of the hand-off buffers a fused update of `planes` update planes needs (0 with knob fused_handoff = 0)
+  static void fusedHandoffSize(const KParams<T>& P, int planes, size_t* reals, size_t* ints);
   // rotating frame (Omega0 > 0, HLLD + 2-D HLLD): the FAST = false instantiation with update_cell_rot; with shearing-box
   // boundaries (shearEnabled; jplus, frac = y shift of the opposite border) the cells next to the x borders are updated
   // by a small second kernel from the border strips (sc.strips)

@@ -29,6 +29,7 @@ int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 // profiles/r02_d_mri_ab.txt)
 int g_rotDt = 0;
 bool rotDtInKernel() { return g_rotDt != 0; }
+extern int g_fusedHandoff;  // run-time knob "fused_handoff": 16 x 8 hand-off tiles (1, default) or 15 x 7 self-closing tiles (0)
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
 extern int g_fusedA;
@@ -288,27 +289,44 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
 //   run-ahead gate: a task of plane p starts only when plane p-2 is complete (ring safety)
 // The arithmetic is the one of k_flux / k_emf / k_update (same device functions).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TW_, int TH_, int THREADS_>
+// HANDOFF_ = true (default): a tile owns TW x TH = 16 x 8 CELLS and solves exactly the 16 x 8 low faces / edges of its
+// own cells; the faces / edges that close its last column and last row (x-face fluxes and emf_z, emf_y of column i0+16;
+// y-face fluxes and emf_z, emf_x of row j0+8) are NOT solved a second time: the tile to the right / above publishes
+// them plane by plane in a small HBM buffer (168 reals per tile and plane) and this tile's update reads them there.
+// Tiles take their index from an atomic counter in "right to left, top to bottom" order, so that a tile only ever waits
+// for tiles whose blocks are already running (no assumption on the block scheduler).  Every Riemann problem of the grid
+// is solved once: 128 cells per 128 solves instead of 105 (HANDOFF_ = false: the 15 x 7 tile that solves its closing
+// column / row itself, knob "fused_handoff" = 0).
+template <typename T, int TW_, int TH_, int THREADS_, bool HANDOFF_ = false>
 struct FusedTile {
   static constexpr int TW = TW_, TH = TH_, THREADS = THREADS_;
-  // W tile with one halo cell on every side.  TMA wants the first element of a box row on a 16-byte
-  // boundary: the box starts at the even cell index at or below i0-1 and is TW+3 (rounded up to even)
+  static constexpr bool HANDOFF = HANDOFF_;
+  static constexpr int PX = HANDOFF ? TW : TW + 1, PY = HANDOFF ? TH : TH + 1;  // faces / edges solved by the tile
+  // W tile with one halo cell on the low sides.  TMA wants the first element of a box row on a 16-byte
+  // boundary: the box starts at the even cell index at or below i0-1 and is PX+2 (rounded up to even)
   // reals wide
-  static constexpr int WX = (TW + 3) / 2 * 2, WY = TH + 2, WCELLS = WX * WY;  // even TW: i0-1 is even (gw = 3)
-  static constexpr int PX = TW + 1, PY = TH + 1;                     // low faces/edges of the cells + the closing ones
+  static constexpr int WX = (PX + 2) / 2 * 2, WY = PY + 1, WCELLS = WX * WY;  // i0-1 is even (gw = 3)
   // a warp task covers two rows of 16 positions: every half warp reads 16 consecutive reals of one
   // tile row, which keeps the 64-bit shared-memory loads free of bank conflicts
-  static constexpr int PXP = 16, NCH = PY / 2, NPOSP = PXP * PY;
+  static constexpr int PXP = 16, NCH = PY / 2;
   static_assert(PX <= PXP && PY % 2 == 0, "tile shape");
+  // flux / emf ring in shared memory: the tile's own PX x PY positions; a HANDOFF tile keeps one more column and row for
+  // the values imported from its neighbours, so that the update indexes one array without any branch
+  static constexpr int FEX = HANDOFF ? PXP + 1 : PXP, FEY = HANDOFF ? PY + 1 : PY, NPOSP = FEX * FEY;
   static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
-  static constexpr int NT = 1 + 7 * NCH;                             // tasks per plane
+  static constexpr int NT = 1 + 7 * NCH + (HANDOFF ? 1 : 0);         // tasks per plane (+ the import task)
+  static constexpr int T_IMPORT = 1 + 6 * NCH;                       // HANDOFF: after the solver tasks, before the updates
   static constexpr int LZMAX = 160;                                  // planes per block (counter arrays)
   static constexpr unsigned W_BYTES = (unsigned)(NW_MHD * WCELLS * sizeof(T));
   static constexpr unsigned W_STRIDE = (W_BYTES + 127u) / 128u * 128u;
   static constexpr unsigned FE_SLOT = (unsigned)(NFE * NPOSP);       // reals per plane slot
   static constexpr unsigned FE_BYTES = (unsigned)(3 * FE_SLOT * sizeof(T));
   static constexpr unsigned NBAR = LZMAX + 2, NCNT = LZMAX + 4;
-  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 3u * NCNT * 4u + 16u;
+  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 5u * NCNT * 4u + 32u;
+  // hand-off record of one tile and plane: row part [7][16] (flux_y[5], emf_z, emf_x of the tile's FIRST row), then
+  // column part [7][8] (flux_x[5], emf_z, emf_y of its FIRST column)
+  static constexpr int HROW = 7 * PXP, HREC = HROW + 7 * PY;
+  static constexpr int NPUB = 5 * NCH;                               // tasks of a plane that publish (all but flux_z)
 };
 
 template <typename T, typename C>
@@ -325,9 +343,23 @@ struct FETileView {  // fluxes (c0 = 0) or emfs (c0 = 15) of plane k (ring slot 
   T* buf;
   int i0, j0, c0;
   __device__ __forceinline__ T& operator()(int c, int i, int j, int k) const {
-    return buf[((unsigned)k % 3u) * C::FE_SLOT + (c0 + c) * C::NPOSP + (j - j0) * C::PXP + (i - i0)];
+    return buf[((unsigned)k % 3u) * C::FE_SLOT + (c0 + c) * C::NPOSP + (j - j0) * C::FEX + (i - i0)];
   }
 };
+
+// progress flags of the hand-off in global memory: release-store by the publishing tile, acquire-poll by its consumers
+__device__ __forceinline__ void publishProgress(int* flag, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ void waitProgress(const int* flag, int need) {
+  int v;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= need) break;
+    __nanosleep(200);
+    if (spins > (1u << 25)) __trap();  // several seconds without progress: fail loudly instead of hanging the device
+  }
+}
 
 // completion counters in shared memory: release-add by the finishing warp, acquire-poll by waiters
 __device__ __forceinline__ void signalCount(int* c) {
@@ -353,7 +385,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapW,
                         const T* __restrict__ Uold, T* __restrict__ Unew, int kbase, int ka, int kb, int lz, T dt,
                         unsigned long long* __restrict__ dMaxInvDt, const ShearShift<T> sh, T* __restrict__ strips,
-                        int stripPlanes) {
+                        int stripPlanes, T* __restrict__ hbuf, int* __restrict__ hsync, int ntx, int nty, int hplanes) {
   extern __shared__ unsigned char smemRaw[];
   // 128-byte alignment for the TMA destination, computed on the shared-window address so that the
   // compiler keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -364,12 +396,27 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   int* cntAll = reinterpret_cast<int*>(bars + C::NBAR);  // cnt*[pl + 2], pl = plane - za
   int* cntZ = cntAll + C::NCNT;
   int* cntXY = cntZ + C::NCNT;
-  int* ticket = cntXY + C::NCNT;
+  int* cntPub = cntXY + C::NCNT;
+  int* cntImp = cntPub + C::NCNT;
+  int* ticket = cntImp + C::NCNT;
 
   const int gw = P.gw;
   const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
-  const int i0 = gw + blockIdx.x * C::TW, j0 = gw + blockIdx.y * C::TH;
-  const int za = ka + blockIdx.z * lz, zb = min(za + lz, kb);  // update planes [za, zb) of this block
+  // tile of this block: from the block index, or (HANDOFF) from an atomic counter in right-to-left, top-to-bottom order:
+  // the producers of tile n are tiles n-1 (right), n-ntx (above) and n-ntx-1, whose blocks took their number earlier
+  int tbx = blockIdx.x, tby = blockIdx.y, tbz = blockIdx.z, tileId = 0;
+  if (C::HANDOFF) {
+    if (threadIdx.x == 0) *ticket = atomicAdd(hsync, 1);
+    __syncthreads();
+    tileId = *ticket;
+    __syncthreads();
+    const int r = tileId / ntx;
+    tbx = ntx - 1 - (tileId - r * ntx);
+    tbz = r / nty;
+    tby = nty - 1 - (r - tbz * nty);
+  }
+  const int i0 = gw + tbx * C::TW, j0 = gw + tby * C::TH;
+  const int za = ka + tbz * lz, zb = min(za + lz, kb);  // update planes [za, zb) of this block
   if (za >= zb) return;
   const int fhi = min(zb, kN);                       // last plane whose low faces / edges are needed
   const int nPl = fhi - za + 1 + (zb > fhi ? 1 : 0);  // + the pseudo plane that only updates plane kN
@@ -379,12 +426,21 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   const WTileView<T, C> W{wbuf, ib, j0 - 1};
   const FETileView<T, C> F{fe, i0, j0, 0}, E{fe, i0, j0, 15};
   const UView<T> U = uview(Uold, P);
+  // hand-off records: mine (written), and those of the producers (read by the update)
+  const bool hasRight = C::HANDOFF && tbx < ntx - 1, hasAbove = C::HANDOFF && tby < nty - 1;
+  T* const recMine = C::HANDOFF ? hbuf + (size_t)tileId * hplanes * C::HREC : nullptr;
+  const T* const recRight = hasRight ? hbuf + (size_t)(tileId - 1) * hplanes * C::HREC : nullptr;
+  const T* const recAbove = hasAbove ? hbuf + (size_t)(tileId - ntx) * hplanes * C::HREC : nullptr;
+  const T* const recCorner = (hasRight && hasAbove) ? hbuf + (size_t)(tileId - ntx - 1) * hplanes * C::HREC : nullptr;
+  int* const prog = hsync + 1;  // prog[tile] = planes published so far
 
   for (int n = tid; n < (int)C::NBAR; n += C::THREADS) tma::mbarInit(&bars[n], 1);
   for (int n = tid; n < (int)C::NCNT; n += C::THREADS) {
     cntAll[n] = (n < 2) ? C::NT : 0;      // planes za-2, za-1 count as complete
     cntZ[n] = (n < 2) ? 3 * C::NCH : 0;
     cntXY[n] = (n < 2) ? 3 * C::NCH : 0;
+    cntPub[n] = 0;
+    cntImp[n] = (n < 2) ? 1 : 0;
   }
   if (tid == 0) *ticket = 0;
   tma::fenceBarrierInit();
@@ -416,7 +472,45 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       if (lane == 0) signalCount(&cntAll[pl + 2]);
       continue;
     }
-    const int kind = (t - 1) / C::NCH, chunk = (t - 1) - kind * C::NCH;
+    if (C::HANDOFF && t == C::T_IMPORT) {
+      // import task: when the producers have published plane index pl, copy the closing column (tile to the right), the
+      // closing row (tile above) and their corner emf_z into the extra column / row of this plane's ring slot
+      if (lane == 0) {
+        if (hasRight) waitProgress(&prog[tileId - 1], pl + 1);
+        if (hasAbove) waitProgress(&prog[tileId - ntx], pl + 1);
+        if (hasRight && hasAbove) waitProgress(&prog[tileId - ntx - 1], pl + 1);
+      }
+      __syncwarp();
+      T* slot = fe + ((unsigned)p % 3u) * C::FE_SLOT;
+      // record component -> ring component: row part flux_y[5] (5..9), emf_z (15), emf_x (17); column part flux_x[5]
+      // (0..4), emf_z (15), emf_y (16)
+      if (hasAbove) {
+        const T* rec = recAbove + (size_t)pl * C::HREC;
+        for (int n = lane; n < C::HROW; n += 32) {
+          const int comp = n / C::PXP, x = n - comp * C::PXP;
+          const int c = comp < 5 ? 5 + comp : (comp == 5 ? 15 : 17);
+          slot[c * C::NPOSP + C::PY * C::FEX + x] = __ldcg(rec + n);
+        }
+      }
+      if (hasRight) {
+        const T* rec = recRight + (size_t)pl * C::HREC + C::HROW;
+        for (int n = lane; n < 7 * C::PY; n += 32) {
+          const int comp = n / C::PY, y = n - comp * C::PY;
+          const int c = comp < 5 ? comp : (comp == 5 ? 15 : 16);
+          slot[c * C::NPOSP + y * C::FEX + C::PXP] = __ldcg(rec + n);
+        }
+      }
+      if (hasRight && hasAbove && lane == 0)
+        slot[15 * C::NPOSP + C::PY * C::FEX + C::PXP] = __ldcg(recCorner + (size_t)pl * C::HREC + 5 * C::PXP);
+      __syncwarp();
+      if (lane == 0) {
+        signalCount(&cntImp[pl + 2]);
+        signalCount(&cntAll[pl + 2]);
+      }
+      continue;
+    }
+    const int ts = (C::HANDOFF && t > C::T_IMPORT) ? t - 2 : t - 1;  // solver / update task index without the two helpers
+    const int kind = ts / C::NCH, chunk = ts - kind * C::NCH;
     const int pi = lane & 15, pj = chunk * 2 + (lane >> 4);
     const int i = i0 + pi, j = j0 + pj;
     const bool ok = pi < C::PX && i <= iN && j <= jN;
@@ -438,6 +532,12 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
               const BorderView<T> Eb{strips, P.jsize, stripPlanes, kbase, gw, P.nx, 15};
               Eb(2 - dir, i, j, p) = E(2 - dir, i, j, p);
             }
+            if (C::HANDOFF) {  // first row: emf_z, emf_x; first column: emf_z, emf_y
+              const T e = E(2 - dir, i, j, p);
+              T* rec = recMine + (size_t)pl * C::HREC;
+              if (pj == 0 && dir != 1) rec[(dir == 2 ? 5 : 6) * C::PXP + pi] = e;
+              if (pi == 0 && dir != 0) rec[C::HROW + (dir == 2 ? 5 : 6) * C::PY + pj] = e;
+            }
           }
         } else {
           // a face is only needed where both transverse indexes are inner (k_flux)
@@ -449,8 +549,19 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
 #pragma unroll
               for (int c = 0; c < 5; ++c) Fb(5 * dir + c, i, j, p) = F(5 * dir + c, i, j, p);
             }
+            if (C::HANDOFF && ((dir == 1 && pj == 0) || (dir == 0 && pi == 0))) {  // first row: flux_y; first column: flux_x
+              T* rec = recMine + (size_t)pl * C::HREC + (dir == 1 ? pi : C::HROW + pj);
+              const int st = (dir == 1) ? C::PXP : C::PY;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) rec[c * st] = F(5 * dir + c, i, j, p);
+            }
           }
         }
+      }
+      if (C::HANDOFF && kind != 2) {  // every task of the five publishing kinds counts, whether it solved anything or not
+        __threadfence();              // this warp's record entries are visible device-wide before the count moves
+        __syncwarp();
+        if (lane == 0 && atomicAdd(&cntPub[pl], 1) == C::NPUB - 1) publishProgress(&prog[tileId], pl + 1);
       }
       __syncwarp();
       if (lane == 0) {
@@ -462,9 +573,13 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
         waitCount(&cntZ[pl + 2], 3 * C::NCH);
         waitCount(&cntZ[pl + 1], 3 * C::NCH);
         waitCount(&cntXY[pl + 1], 3 * C::NCH);
+        if (C::HANDOFF) {  // closing column / row of planes p-1 and p imported
+          waitCount(&cntImp[pl + 2], 1);
+          waitCount(&cntImp[pl + 1], 1);
+        }
         __syncwarp();
-        // a cell of the closing column/row belongs to this tile only when it is the ghost face (iN / jN)
-        const bool mine = ok && (i < i0 + C::TW || i == iN) && (j < j0 + C::TH || j == jN);
+        // legacy tile: a cell of the closing column/row belongs to this tile only when it is the ghost face (iN / jN)
+        const bool mine = C::HANDOFF ? ok : ok && (i < i0 + C::TW || i == iN) && (j < j0 + C::TH || j == jN);
         T invDt = T(0);
         if (mine) {
           if (FAST) {
@@ -814,6 +929,10 @@ bool setTuning(const char* key, int value) {
     g_fusedB = value ? 1 : 0;
     return true;
   }
+  if (k == "fused_handoff") {
+    g_fusedHandoff = value ? 1 : 0;
+    return true;
+  }
   if (k == "rot_dt") {
     g_rotDt = value ? 1 : 0;
     return true;
@@ -1087,9 +1206,13 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
   launched();
 }
 
-template <typename T>
 // 512 threads / 124 registers: a 384-thread build (152 registers) measured 7 % slower, 640 threads spill
-struct FusedSel { typedef FusedTile<T, 15, 7, 512> Cfg; };
+template <typename T>
+struct FusedSel {
+  typedef FusedTile<T, 16, 8, 512, true> Cfg;      // hand-off tile (default)
+  typedef FusedTile<T, 15, 7, 512, false> Legacy;  // knob "fused_handoff" = 0
+};
+int g_fusedHandoff = 1;
 
 // the rotating-frame instantiation of the fused kernel: HLLD + 2-D HLLD in the rotating frame (any closure)
 template <typename T>
@@ -1100,15 +1223,56 @@ static bool rotatingFusedPath(const KParams<T>& P) {
 
 template <typename T>
 bool MhdKernels<T>::fusedUpdateEligible(const KParams<T>& P) {
-  typedef typename FusedSel<T>::Cfg C;
   if (sizeof(T) != 8 || !(fastPath(P) || rotatingFusedPath(P)) || P.dim != 3) return false;
-  if (C::TW % 2 == 0 && (P.gw - 1) % 2 != 0) return false;  // box rows must start on an even cell index
+  if ((P.gw - 1) % 2 != 0) return false;                    // box rows must start on an even cell index
   return ((size_t)P.isize * sizeof(T)) % 16 == 0;           // TMA: row pitch a multiple of 16 bytes
+}
+
+// launch geometry of the fused update over `planes` update planes: tiles, z ranges (whole waves of one block per SM)
+struct FusedGeom { int ntx, nty, nz, lz; };
+template <typename T, typename C>
+static FusedGeom fusedGeometry(const KParams<T>& P, int planes) {
+  FusedGeom g;
+  if (C::HANDOFF) {  // every cell of the update box, ghost-face column / row included, belongs to exactly one tile
+    g.ntx = (P.nx + 1 + C::TW - 1) / C::TW;
+    g.nty = (P.ny + 1 + C::TH - 1) / C::TH;
+  } else {           // the ghost-face column / row is folded into the last tile when it would otherwise open a tile of its own
+    g.ntx = std::max(1, (P.nx + C::TW - 1) / C::TW);
+    g.nty = std::max(1, (P.ny + C::TH - 1) / C::TH);
+  }
+  const int nSM = smCount();
+  int bestNz = 1;
+  double bestCost = 1e300;
+  for (int nz = 1; nz <= planes; ++nz) {
+    const int lz = (planes + nz - 1) / nz;
+    if (lz > C::LZMAX) continue;
+    if (lz < 8 && nz > 1) break;
+    const long blocks = (long)g.ntx * g.nty * ((planes + lz - 1) / lz);
+    const double cost = (double)((blocks + nSM - 1) / nSM) * (lz + 1.5);
+    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
+  }
+  g.lz = (planes + bestNz - 1) / bestNz;
+  g.nz = (planes + g.lz - 1) / g.lz;
+  return g;
+}
+
+template <typename T>
+void MhdKernels<T>::fusedHandoffSize(const KParams<T>& P, int planes, size_t* reals, size_t* ints) {
+  typedef typename FusedSel<T>::Cfg C;
+  *reals = 0;
+  *ints = 0;
+  if (!g_fusedHandoff || planes <= 0) return;
+  const FusedGeom g = fusedGeometry<T, C>(P, planes);
+  const size_t blocks = (size_t)g.ntx * g.nty * g.nz;
+  *reals = blocks * (size_t)(g.lz + 2) * C::HREC;
+  *ints = blocks + 1;
 }
 
 template <typename T>
 void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   typedef typename FusedSel<T>::Cfg C;
+  typedef typename FusedSel<T>::Legacy L;
+  static_assert(C::WX == L::WX && C::WY == L::WY, "both tiles share the tensor map of W");
   sc.fused = 0;
   if (!fusedUpdateEligible(P) || sc.W == nullptr) return;
   CUtensorMap map;
@@ -1118,12 +1282,16 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   static bool attrSetDev[MAX_DEVICES] = {false};
   bool& attrSet = attrSetDev[currentDevice()];
   if (!attrSet) {
-    if (cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(k_fused_flux_emf_update<T, C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)C::SMEM) != cudaSuccess) {
+    bool ok = true;
+#define RG_ATTR(K, SM) ok = ok && cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)) == cudaSuccess
+    RG_ATTR((k_fused_flux_emf_update<T, C, true>), C::SMEM);
+    RG_ATTR((k_fused_flux_emf_update<T, C, false>), C::SMEM);
+    RG_ATTR((k_fused_flux_emf_update<T, C, false, false>), C::SMEM);
+    RG_ATTR((k_fused_flux_emf_update<T, L, true>), L::SMEM);
+    RG_ATTR((k_fused_flux_emf_update<T, L, false>), L::SMEM);
+    RG_ATTR((k_fused_flux_emf_update<T, L, false, false>), L::SMEM);
+#undef RG_ATTR
+    if (!ok) {
       cudaGetLastError();
       return;
     }
@@ -1132,46 +1300,40 @@ void MhdKernels<T>::fusedPrepare(const KParams<T>& P, MhdScratch<T>& sc) {
   sc.fused = 1;
 }
 
-template <typename T>
-void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka,
-                                       int kb, T dt, unsigned long long* d, cudaStream_t s, int shearEnabled, int jplus,
-                                       T frac) {
-  typedef typename FusedSel<T>::Cfg C;
-  if (kb <= ka) return;
-  const int nSM = smCount();
-  // tiles of TW x TH cells over the (nx+1) x (ny+1) update box; the ghost-face column/row is folded
-  // into the last tile when it would otherwise open a tile of its own
-  const int ntx = std::max(1, (P.nx + C::TW - 1) / C::TW), nty = std::max(1, (P.ny + C::TH - 1) / C::TH);
-  // split z into ranges so that the grid fills the SMs in whole waves (one block per SM)
-  const int planes = kb - ka;
-  int bestNz = 1;
-  double bestCost = 1e300;
-  for (int nz = 1; nz <= planes; ++nz) {
-    const int lz = (planes + nz - 1) / nz;
-    if (lz > C::LZMAX) continue;
-    if (lz < 8 && nz > 1) break;
-    const long blocks = (long)ntx * nty * ((planes + lz - 1) / lz);
-    const double cost = (double)((blocks + nSM - 1) / nSM) * (lz + 1.5);
-    if (cost < bestCost) { bestCost = cost; bestNz = nz; }
+template <typename T, typename C>
+static void launchFusedUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka, int kb, T dt,
+                              unsigned long long* d, cudaStream_t s, int shearEnabled, int jplus, T frac) {
+  const FusedGeom g = fusedGeometry<T, C>(P, kb - ka);
+  const dim3 grid(g.ntx, g.nty, g.nz);
+  const int lz = g.lz, hplanes = g.lz + 2;
+  T* hbuf = nullptr;
+  int* hsync = nullptr;
+  if (C::HANDOFF) {
+    const size_t blocks = (size_t)g.ntx * g.nty * g.nz;
+    if (sc.hbuf == nullptr || sc.hsync == nullptr || sc.hbufReals < blocks * (size_t)hplanes * C::HREC || sc.hsyncInts < blocks + 1)
+      throw std::runtime_error("fused update: the hand-off buffers are too small for this launch");
+    hbuf = sc.hbuf;
+    hsync = sc.hsync;
+    // tile counter and per-tile progress flags start at zero for every launch
+    if (cudaMemsetAsync(hsync, 0, (blocks + 1) * sizeof(int), s) != cudaSuccess)
+      throw std::runtime_error("CUDA error: cudaMemsetAsync(hand-off flags)");
   }
-  const int lz = (planes + bestNz - 1) / bestNz;
-  const dim3 grid(ntx, nty, (planes + lz - 1) / lz);
   CUtensorMap map;
   memcpy(&map, sc.mapW, sizeof(map));
   const ShearShift<T> sh{shearEnabled, jplus, frac};
   if (fastPath(P)) {
     k_fused_flux_emf_update<T, C, true><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh,
-                                                                          nullptr, 0);
+                                                                          nullptr, 0, hbuf, hsync, g.ntx, g.nty, hplanes);
     launched();
     return;
   }
   // rotating frame; with shearing-box boundaries the three border cell columns follow from the strips
   if (g_rotDt)
-    k_fused_flux_emf_update<T, C, false, true><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt,
-                                                                                 d, sh, sc.strips, sc.planes);
+    k_fused_flux_emf_update<T, C, false, true><<<grid, C::THREADS, C::SMEM, s>>>(
+        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes);
   else
-    k_fused_flux_emf_update<T, C, false, false><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt,
-                                                                                  nullptr, sh, sc.strips, sc.planes);
+    k_fused_flux_emf_update<T, C, false, false><<<grid, C::THREADS, C::SMEM, s>>>(
+        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, nullptr, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes);
   launched();
   if (shearEnabled) {
     const int nRows = P.jsize - 2 * P.gw + 1;
@@ -1179,6 +1341,17 @@ void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Un
                                                                                        sc.kbase, ka, dt, sh, g_rotDt ? d : nullptr);
     launched();
   }
+}
+
+template <typename T>
+void MhdKernels<T>::fusedFluxEmfUpdate(const KParams<T>& P, const T* Uold, T* Unew, const MhdScratch<T>& sc, int ka,
+                                       int kb, T dt, unsigned long long* d, cudaStream_t s, int shearEnabled, int jplus,
+                                       T frac) {
+  if (kb <= ka) return;
+  if (g_fusedHandoff)
+    launchFusedUpdate<T, typename FusedSel<T>::Cfg>(P, Uold, Unew, sc, ka, kb, dt, d, s, shearEnabled, jplus, frac);
+  else
+    launchFusedUpdate<T, typename FusedSel<T>::Legacy>(P, Uold, Unew, sc, ka, kb, dt, d, s, shearEnabled, jplus, frac);
 }
 
 template <typename T>

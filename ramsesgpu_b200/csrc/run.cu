@@ -779,6 +779,7 @@ class RunImpl final : public Run {
   void freeScratch() {
     if (sc_.W) {  // cudaFree(nullptr) is a no-op for the arrays the hydro path does not use
       cudaFree(sc_.Q); cudaFree(sc_.W); cudaFree(sc_.F); cudaFree(sc_.E); cudaFree(sc_.EL); cudaFree(sc_.strips);
+      cudaFree(sc_.hbuf); cudaFree(sc_.hsync);
       deviceBytes_ -= scratchBytes_;
     }
     sc_ = MhdScratch<T>();
@@ -824,8 +825,24 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMemsetAsync(sc_.strips, 0, stripBytes, stream_));
       scratchBytes_ += stripBytes;
     }
-    deviceBytes_ += scratchBytes_;
     MhdKernels<T>::fusedPrepare(kp_, sc_);
+    if (sc_.fused) {  // hand-off records of the fused update: the largest launch is a whole chunk (+ the ghost-face plane)
+      size_t reals = 0, ints = 0;
+      for (int n : {chunk + 1, chunk, std::max(chunk - 2 * kp_.gw, 1), kp_.gw, kp_.gw + 1}) {
+        size_t r = 0, i = 0;
+        MhdKernels<T>::fusedHandoffSize(kp_, n, &r, &i);
+        reals = std::max(reals, r);
+        ints = std::max(ints, i);
+      }
+      if (reals > 0) {
+        RG_CUDA(cudaMalloc(&sc_.hbuf, reals * sizeof(T)));
+        RG_CUDA(cudaMalloc(&sc_.hsync, ints * sizeof(int)));
+        sc_.hbufReals = reals;
+        sc_.hsyncInts = ints;
+        scratchBytes_ += reals * sizeof(T) + ints * sizeof(int);
+      }
+    }
+    deviceBytes_ += scratchBytes_;
   }
 
   // ---- 3D MHD step: reference godunov_unsplit_cpu/gpu (MHDRunGodunov.cpp:623-672, 1447-1503) ------
@@ -871,7 +888,23 @@ class RunImpl final : public Run {
     // overlap needs three disjoint plane ranges: bottom gw planes, top gw planes (+ the ghost-face
     // plane kN), interior
     const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative();
-    if (overlap) {
+    // one chunk holds the whole slab and both fused kernels run: the trace does not depend on the halo, so it runs ONCE
+    // over the slab and only the update is cut into the three ranges (two launches and their pipeline fills less)
+    const bool traceOnce = overlap && chunkPlanes_ >= kN + 1 - gw && sc_.fused && fusedRequested() &&
+                           fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_);
+    if (traceOnce) {
+      MhdScratch<T> sc = sc_;
+      sc.kbase = gw - 2;
+      phase(PH_TRACE, [&] { MhdKernels<T>::fusedTrace(kp_, Uold, sc, gw - 1, kN + 1, dt, stream_); });
+      auto updateRange = [&](int ka, int kb) {
+        phase(PH_FUSED, [&] { MhdKernels<T>::fusedFluxEmfUpdate(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_); });
+        phase(PH_COPY, [&] { MhdKernels<T>::copyOutsideBox(kp_, Uold, Unew, ka, kb, stream_); });
+      };
+      updateRange(gw, 2 * gw);
+      updateRange(kN - gw, kN + 1);
+      startEarlyHalo(dst);
+      updateRange(2 * gw, kN - gw);
+    } else if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN + 1);
       startEarlyHalo(dst);
@@ -1046,7 +1079,25 @@ class RunImpl final : public Run {
     // updated first and travel on the communication stream while the interior is updated (see startEarlyHaloShear)
     const bool stratZ = rp_.bc[4] == BC_Z_STRATIFIED || rp_.bc[5] == BC_Z_STRATIFIED;
     const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative() && !stratZ;
-    if (overlap) {
+    const bool traceOnce = overlap && chunkPlanes_ >= kN + 1 - gw && sc_.fused && fusedRequested() &&
+                           fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_);
+    if (traceOnce) {  // as in stepMhd3d: one trace launch over the slab, the update in three ranges
+      MhdScratch<T> sc = sc_;
+      sc.kbase = gw - 2;
+      phase(PH_TRACE, [&] { MhdKernels<T>::fusedTrace(kp_, Uold, sc, gw - 1, kN + 1, dt, stream_); });
+      auto updateRange = [&](int ka, int kb) {
+        phase(PH_FUSED, [&] {
+          MhdKernels<T>::fusedFluxEmfUpdate(kp_, Uold, Unew, sc, ka, kb, dt, slots, stream_, shear, jplus, frac);
+        });
+        phase(PH_COPY, [&] { MhdKernels<T>::copyOutsideBox(kp_, Uold, Unew, ka, kb, stream_); });
+      };
+      updateRange(gw, 2 * gw);
+      updateRange(kN - gw, kN + 1);
+      if (shear) startEarlyHaloShear(dst, dt);
+      else startEarlyHalo(dst);
+      updateRange(2 * gw, kN - gw);
+      fusedRotNoDt = !rotDtInKernel();
+    } else if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN + 1);
       if (shear) startEarlyHaloShear(dst, dt);
