@@ -399,6 +399,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   int* cntPub = cntXY + C::NCNT;
   int* cntImp = cntPub + C::NCNT;
   int* ticket = cntImp + C::NCNT;
+  int* pubSeq = ticket + 1;  // planes published so far, in order
 
   const int gw = P.gw;
   const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
@@ -442,7 +443,10 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
     cntPub[n] = 0;
     cntImp[n] = (n < 2) ? 1 : 0;
   }
-  if (tid == 0) *ticket = 0;
+  if (tid == 0) {
+    *ticket = 0;
+    *pubSeq = 0;
+  }
   tma::fenceBarrierInit();
   __syncthreads();
   auto loadPlane = [&](int q) {  // one thread
@@ -561,7 +565,13 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       if (C::HANDOFF && kind != 2) {  // every task of the five publishing kinds counts, whether it solved anything or not
         __threadfence();              // this warp's record entries are visible device-wide before the count moves
         __syncwarp();
-        if (lane == 0 && atomicAdd(&cntPub[pl], 1) == C::NPUB - 1) publishProgress(&prog[tileId], pl + 1);
+        if (lane == 0 && atomicAdd(&cntPub[pl], 1) == C::NPUB - 1) {
+          // planes may finish out of order (a block runs up to two planes ahead): the flag counts CONSECUTIVE published
+          // planes, so the last warp of plane pl waits for plane pl-1 to be out (earlier tickets: cannot deadlock)
+          waitCount(pubSeq, pl);
+          publishProgress(&prog[tileId], pl + 1);
+          signalCount(pubSeq);
+        }
       }
       __syncwarp();
       if (lane == 0) {

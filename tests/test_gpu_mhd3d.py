@@ -316,3 +316,29 @@ def test_bench_size_256cubed_every_plane_vs_oracle(native, oracle64, chunk):
         den = np.sqrt(np.sum(want[v] ** 2))
         errs = np.sqrt(np.sum((got[v] - want[v][None]) ** 2, axis=(1, 2))) / den   # L2-relative error of every plane
         assert errs.max() < TOL_F64, (v, int(errs.argmax()), float(errs.max()))
+
+
+@pytest.mark.parametrize("n,over,steps,chunk", [
+    ((40, 22, 12), {}, 6, 0),
+    ((50, 37, 30), {"OrszagTang": {"kt": 1.0}}, 12, 0),            # light last tile column / row, several z ranges
+    ((64, 48, 40), {"OrszagTang": {"kt": 1.0}, "mesh": {"boundary_xmin": 2, "boundary_xmax": 2, "boundary_ymin": 1,
+                                                        "boundary_ymax": 1, "boundary_zmin": 2, "boundary_zmax": 1}}, 8, 13),
+    ((256, 256, 64), {}, 12, 0),                                   # 17 x 33 tiles, many waves of blocks
+])
+def test_handoff_tiles_equal_self_closing_tiles(native, n, over, steps, chunk):
+    """The 16 x 8 hand-off tiles of the fused update (closing column / row imported from the neighbour tiles through HBM
+    records, tiles numbered by an atomic counter) against the 15 x 7 tiles that solve their closing column / row
+    themselves (knob fused_handoff = 0): the same Riemann problems with the same inputs, each solved once instead of up
+    to four times.  Several steps, so that a lost or late record would show."""
+    from ramsesgpu_b200 import set_tuning
+    ini = ot3d_ini(n, **over)
+    try:
+        set_tuning("fused_handoff", 0)
+        ref, tr, dtr, gw = run_gpu_steps(ini, steps, chunk=chunk)
+        set_tuning("fused_handoff", 1)
+        got, tg, dtg, _ = run_gpu_steps(ini, steps, chunk=chunk)
+    finally:
+        set_tuning("fused_handoff", 1)
+    assert np.allclose(dtr, dtg, rtol=1e-14, atol=0)
+    assert (np.abs(ref - got) <= 1e-13 * np.abs(ref).max()).all()      # ghosts included
+    print(n, "hand-off vs self-closing tiles:", "bitwise" if np.array_equal(ref, got) else "max diff %.2e" % float(np.abs(ref - got).max()))
