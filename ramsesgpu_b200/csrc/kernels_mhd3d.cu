@@ -322,11 +322,13 @@ struct FusedTile {
   static constexpr unsigned FE_SLOT = (unsigned)(NFE * NPOSP);       // reals per plane slot
   static constexpr unsigned FE_BYTES = (unsigned)(3 * FE_SLOT * sizeof(T));
   static constexpr unsigned NBAR = LZMAX + 2, NCNT = LZMAX + 4;
-  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 5u * NCNT * 4u + 32u;
+  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 6u * NCNT * 4u + 32u;
   // hand-off record of one tile and plane: row part [7][16] (flux_y[5], emf_z, emf_x of the tile's FIRST row), then
   // column part [7][8] (flux_x[5], emf_z, emf_y of its FIRST column)
   static constexpr int HROW = 7 * PXP, HREC = HROW + 7 * PY;
-  static constexpr int NPUB = 5 * NCH;                               // tasks of a plane that publish (all but flux_z)
+  // tasks of a plane that publish: emf_x, emf_y (z group: needed by the consumer's update one plane earlier than the
+  // rest) and emf_z, flux_x, flux_y (plane-local group); two progress flags per tile
+  static constexpr int NPUBZ = 2 * NCH, NPUBXY = 3 * NCH;
 };
 
 template <typename T, typename C>
@@ -361,6 +363,14 @@ __device__ __forceinline__ void waitProgress(const int* flag, int need) {
   }
 }
 
+// counter in shared memory bumped with acquire-release semantics at CTA scope (returns the old value): orders the warp's
+// hand-off record stores before the count and, by cumulativity, before the publisher's gpu-scope release store -- no
+// device-wide fence per task
+__device__ __forceinline__ int bumpCount(int* c) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(old) : "r"(tma::smemAddr(c)) : "memory");
+  return old;
+}
 // completion counters in shared memory: release-add by the finishing warp, acquire-poll by waiters
 __device__ __forceinline__ void signalCount(int* c) {
   asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(tma::smemAddr(c)) : "memory");
@@ -396,10 +406,11 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   int* cntAll = reinterpret_cast<int*>(bars + C::NBAR);  // cnt*[pl + 2], pl = plane - za
   int* cntZ = cntAll + C::NCNT;
   int* cntXY = cntZ + C::NCNT;
-  int* cntPub = cntXY + C::NCNT;
-  int* cntImp = cntPub + C::NCNT;
+  int* cntPubZ = cntXY + C::NCNT;
+  int* cntPubXY = cntPubZ + C::NCNT;
+  int* cntImp = cntPubXY + C::NCNT;
   int* ticket = cntImp + C::NCNT;
-  int* pubSeq = ticket + 1;  // planes published so far, in order
+  int* pubSeq = ticket + 1;  // [0] z-group, [1] plane-local group: planes published so far, in order
 
   const int gw = P.gw;
   const int iN = P.isize - gw, jN = P.jsize - gw, kN = P.ksize - gw;
@@ -433,19 +444,21 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   const T* const recRight = hasRight ? hbuf + (size_t)(tileId - 1) * hplanes * C::HREC : nullptr;
   const T* const recAbove = hasAbove ? hbuf + (size_t)(tileId - ntx) * hplanes * C::HREC : nullptr;
   const T* const recCorner = (hasRight && hasAbove) ? hbuf + (size_t)(tileId - ntx - 1) * hplanes * C::HREC : nullptr;
-  int* const prog = hsync + 1;  // prog[tile] = planes published so far
+  int* const prog = hsync + 1;  // prog[2 tile + g] = planes whose group g (0: emf_x, emf_y; 1: emf_z, flux_x, flux_y) is out
 
   for (int n = tid; n < (int)C::NBAR; n += C::THREADS) tma::mbarInit(&bars[n], 1);
   for (int n = tid; n < (int)C::NCNT; n += C::THREADS) {
     cntAll[n] = (n < 2) ? C::NT : 0;      // planes za-2, za-1 count as complete
     cntZ[n] = (n < 2) ? 3 * C::NCH : 0;
     cntXY[n] = (n < 2) ? 3 * C::NCH : 0;
-    cntPub[n] = 0;
+    cntPubZ[n] = 0;
+    cntPubXY[n] = 0;
     cntImp[n] = (n < 2) ? 1 : 0;
   }
   if (tid == 0) {
     *ticket = 0;
-    *pubSeq = 0;
+    pubSeq[0] = 0;
+    pubSeq[1] = 0;
   }
   tma::fenceBarrierInit();
   __syncthreads();
@@ -477,35 +490,49 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       continue;
     }
     if (C::HANDOFF && t == C::T_IMPORT) {
-      // import task: when the producers have published plane index pl, copy the closing column (tile to the right), the
-      // closing row (tile above) and their corner emf_z into the extra column / row of this plane's ring slot
+      // import task of plane p: copies what the update of plane p-1 (next tasks) still misses into the extra column / row
+      // of the flux / emf ring -- the z group (emf_x of the closing row, emf_y of the closing column) of plane p, whose
+      // producers' tasks ran a dozen tickets ago, and the plane-local group (flux_y, emf_z | flux_x, emf_z | corner
+      // emf_z) of plane p-1, finished a whole plane ago: in steady state no wait at all
+      const int R = tileId - 1, A = tileId - ntx, K = tileId - ntx - 1;
       if (lane == 0) {
-        if (hasRight) waitProgress(&prog[tileId - 1], pl + 1);
-        if (hasAbove) waitProgress(&prog[tileId - ntx], pl + 1);
-        if (hasRight && hasAbove) waitProgress(&prog[tileId - ntx - 1], pl + 1);
+        if (hasRight) waitProgress(&prog[2 * R], pl + 1);
+        if (hasAbove) waitProgress(&prog[2 * A], pl + 1);
+        if (pl >= 1) {
+          if (hasRight) waitProgress(&prog[2 * R + 1], pl);
+          if (hasAbove) waitProgress(&prog[2 * A + 1], pl);
+          if (hasRight && hasAbove) waitProgress(&prog[2 * K + 1], pl);
+        }
       }
       __syncwarp();
-      T* slot = fe + ((unsigned)p % 3u) * C::FE_SLOT;
+      T* slot = fe + ((unsigned)p % 3u) * C::FE_SLOT;         // plane p
+      T* slotm = fe + ((unsigned)(p + 2) % 3u) * C::FE_SLOT;  // plane p-1
       // record component -> ring component: row part flux_y[5] (5..9), emf_z (15), emf_x (17); column part flux_x[5]
       // (0..4), emf_z (15), emf_y (16)
       if (hasAbove) {
         const T* rec = recAbove + (size_t)pl * C::HREC;
-        for (int n = lane; n < C::HROW; n += 32) {
-          const int comp = n / C::PXP, x = n - comp * C::PXP;
-          const int c = comp < 5 ? 5 + comp : (comp == 5 ? 15 : 17);
-          slot[c * C::NPOSP + C::PY * C::FEX + x] = __ldcg(rec + n);
+        if (lane < C::PXP) slot[17 * C::NPOSP + C::PY * C::FEX + lane] = __ldcg(rec + 6 * C::PXP + lane);
+        if (pl >= 1) {
+          const T* recm = rec - C::HREC;
+          for (int n = lane; n < 6 * C::PXP; n += 32) {
+            const int comp = n / C::PXP, x = n - comp * C::PXP;
+            slotm[(comp < 5 ? 5 + comp : 15) * C::NPOSP + C::PY * C::FEX + x] = __ldcg(recm + n);
+          }
         }
       }
       if (hasRight) {
         const T* rec = recRight + (size_t)pl * C::HREC + C::HROW;
-        for (int n = lane; n < 7 * C::PY; n += 32) {
-          const int comp = n / C::PY, y = n - comp * C::PY;
-          const int c = comp < 5 ? comp : (comp == 5 ? 15 : 16);
-          slot[c * C::NPOSP + y * C::FEX + C::PXP] = __ldcg(rec + n);
+        if (lane < C::PY) slot[16 * C::NPOSP + lane * C::FEX + C::PXP] = __ldcg(rec + 6 * C::PY + lane);
+        if (pl >= 1) {
+          const T* recm = rec - C::HREC;
+          for (int n = lane; n < 6 * C::PY; n += 32) {
+            const int comp = n / C::PY, y = n - comp * C::PY;
+            slotm[(comp < 5 ? comp : 15) * C::NPOSP + y * C::FEX + C::PXP] = __ldcg(recm + n);
+          }
         }
       }
-      if (hasRight && hasAbove && lane == 0)
-        slot[15 * C::NPOSP + C::PY * C::FEX + C::PXP] = __ldcg(recCorner + (size_t)pl * C::HREC + 5 * C::PXP);
+      if (hasRight && hasAbove && pl >= 1 && lane == 0)
+        slotm[15 * C::NPOSP + C::PY * C::FEX + C::PXP] = __ldcg(recCorner + (size_t)(pl - 1) * C::HREC + 5 * C::PXP);
       __syncwarp();
       if (lane == 0) {
         signalCount(&cntImp[pl + 2]);
@@ -563,14 +590,14 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
         }
       }
       if (C::HANDOFF && kind != 2) {  // every task of the five publishing kinds counts, whether it solved anything or not
-        __threadfence();              // this warp's record entries are visible device-wide before the count moves
         __syncwarp();
-        if (lane == 0 && atomicAdd(&cntPub[pl], 1) == C::NPUB - 1) {
-          // planes may finish out of order (a block runs up to two planes ahead): the flag counts CONSECUTIVE published
+        const int g = zgrp ? 0 : 1;
+        if (lane == 0 && bumpCount(zgrp ? &cntPubZ[pl] : &cntPubXY[pl]) == (zgrp ? C::NPUBZ : C::NPUBXY) - 1) {
+          // planes may finish out of order (a block runs up to two planes ahead): a flag counts CONSECUTIVE published
           // planes, so the last warp of plane pl waits for plane pl-1 to be out (earlier tickets: cannot deadlock)
-          waitCount(pubSeq, pl);
-          publishProgress(&prog[tileId], pl + 1);
-          signalCount(pubSeq);
+          waitCount(&pubSeq[g], pl);
+          publishProgress(&prog[2 * tileId + g], pl + 1);
+          signalCount(&pubSeq[g]);
         }
       }
       __syncwarp();
@@ -583,7 +610,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
         waitCount(&cntZ[pl + 2], 3 * C::NCH);
         waitCount(&cntZ[pl + 1], 3 * C::NCH);
         waitCount(&cntXY[pl + 1], 3 * C::NCH);
-        if (C::HANDOFF) {  // closing column / row of planes p-1 and p imported
+        if (C::HANDOFF) {  // closing column / row imported: z group of planes p-1 and p, plane-local group of plane p-1
           waitCount(&cntImp[pl + 2], 1);
           waitCount(&cntImp[pl + 1], 1);
         }
@@ -1258,7 +1285,8 @@ static FusedGeom fusedGeometry(const KParams<T>& P, int planes) {
     if (lz > C::LZMAX) continue;
     if (lz < 8 && nz > 1) break;
     const long blocks = (long)g.ntx * g.nty * ((planes + lz - 1) / lz);
-    const double cost = (double)((blocks + nSM - 1) / nSM) * (lz + 1.5);
+    // a z range costs its planes + the pipeline fill (+ the start-up skew of the hand-off chain of a wave of tiles)
+    const double cost = (double)((blocks + nSM - 1) / nSM) * (lz + (C::HANDOFF ? 4.0 : 1.5));
     if (cost < bestCost) { bestCost = cost; bestNz = nz; }
   }
   g.lz = (planes + bestNz - 1) / bestNz;
@@ -1275,7 +1303,7 @@ void MhdKernels<T>::fusedHandoffSize(const KParams<T>& P, int planes, size_t* re
   const FusedGeom g = fusedGeometry<T, C>(P, planes);
   const size_t blocks = (size_t)g.ntx * g.nty * g.nz;
   *reals = blocks * (size_t)(g.lz + 2) * C::HREC;
-  *ints = blocks + 1;
+  *ints = 2 * blocks + 1;
 }
 
 template <typename T>
@@ -1320,12 +1348,12 @@ static void launchFusedUpdate(const KParams<T>& P, const T* Uold, T* Unew, const
   int* hsync = nullptr;
   if (C::HANDOFF) {
     const size_t blocks = (size_t)g.ntx * g.nty * g.nz;
-    if (sc.hbuf == nullptr || sc.hsync == nullptr || sc.hbufReals < blocks * (size_t)hplanes * C::HREC || sc.hsyncInts < blocks + 1)
+    if (sc.hbuf == nullptr || sc.hsync == nullptr || sc.hbufReals < blocks * (size_t)hplanes * C::HREC || sc.hsyncInts < 2 * blocks + 1)
       throw std::runtime_error("fused update: the hand-off buffers are too small for this launch");
     hbuf = sc.hbuf;
     hsync = sc.hsync;
     // tile counter and per-tile progress flags start at zero for every launch
-    if (cudaMemsetAsync(hsync, 0, (blocks + 1) * sizeof(int), s) != cudaSuccess)
+    if (cudaMemsetAsync(hsync, 0, (2 * blocks + 1) * sizeof(int), s) != cudaSuccess)
       throw std::runtime_error("CUDA error: cudaMemsetAsync(hand-off flags)");
   }
   CUtensorMap map;
