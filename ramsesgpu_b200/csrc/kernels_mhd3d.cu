@@ -314,8 +314,12 @@ struct FusedTile {
   // the values imported from its neighbours, so that the update indexes one array without any branch
   static constexpr int FEX = HANDOFF ? PXP + 1 : PXP, FEY = HANDOFF ? PY + 1 : PY, NPOSP = FEX * FEY;
   static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
-  static constexpr int NT = 1 + 7 * NCH + (HANDOFF ? 1 : 0);         // tasks per plane (+ the import task)
-  static constexpr int T_IMPORT = 1 + 6 * NCH;                       // HANDOFF: after the solver tasks, before the updates
+  static constexpr int NT = 1 + 7 * NCH + (HANDOFF ? 2 : 0);         // tasks per plane (+ the two import tasks)
+  // HANDOFF ticket order of a plane: TMA | import of the plane-local group of plane p-1 | z group | half of the
+  // plane-local group | import of the z group of plane p | rest of the plane-local group | updates of plane p-1.
+  // The imports sit several solver tasks ahead of the updates that read them: their two L2 round trips (flags, records)
+  // are hidden, and the data they wait for was produced a dozen tickets (z group) or a whole plane earlier.
+  static constexpr int T_IMPORT_XY = 1, T_IMPORT_Z = 2 + 3 * NCH + (3 * NCH) / 2;
   static constexpr int LZMAX = 160;                                  // planes per block (counter arrays)
   static constexpr unsigned W_BYTES = (unsigned)(NW_MHD * WCELLS * sizeof(T));
   static constexpr unsigned W_STRIDE = (W_BYTES + 127u) / 128u * 128u;
@@ -453,7 +457,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
     cntXY[n] = (n < 2) ? 3 * C::NCH : 0;
     cntPubZ[n] = 0;
     cntPubXY[n] = 0;
-    cntImp[n] = (n < 2) ? 1 : 0;
+    cntImp[n] = (n < 2) ? 2 : 0;
   }
   if (tid == 0) {
     *ticket = 0;
@@ -489,50 +493,47 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       if (lane == 0) signalCount(&cntAll[pl + 2]);
       continue;
     }
-    if (C::HANDOFF && t == C::T_IMPORT) {
-      // import task of plane p: copies what the update of plane p-1 (next tasks) still misses into the extra column / row
-      // of the flux / emf ring -- the z group (emf_x of the closing row, emf_y of the closing column) of plane p, whose
-      // producers' tasks ran a dozen tickets ago, and the plane-local group (flux_y, emf_z | flux_x, emf_z | corner
-      // emf_z) of plane p-1, finished a whole plane ago: in steady state no wait at all
-      const int R = tileId - 1, A = tileId - ntx, K = tileId - ntx - 1;
-      if (lane == 0) {
-        if (hasRight) waitProgress(&prog[2 * R], pl + 1);
-        if (hasAbove) waitProgress(&prog[2 * A], pl + 1);
-        if (pl >= 1) {
-          if (hasRight) waitProgress(&prog[2 * R + 1], pl);
-          if (hasAbove) waitProgress(&prog[2 * A + 1], pl);
-          if (hasRight && hasAbove) waitProgress(&prog[2 * K + 1], pl);
-        }
-      }
-      __syncwarp();
-      T* slot = fe + ((unsigned)p % 3u) * C::FE_SLOT;         // plane p
-      T* slotm = fe + ((unsigned)(p + 2) % 3u) * C::FE_SLOT;  // plane p-1
-      // record component -> ring component: row part flux_y[5] (5..9), emf_z (15), emf_x (17); column part flux_x[5]
-      // (0..4), emf_z (15), emf_y (16)
-      if (hasAbove) {
-        const T* rec = recAbove + (size_t)pl * C::HREC;
-        if (lane < C::PXP) slot[17 * C::NPOSP + C::PY * C::FEX + lane] = __ldcg(rec + 6 * C::PXP + lane);
-        if (pl >= 1) {
-          const T* recm = rec - C::HREC;
-          for (int n = lane; n < 6 * C::PXP; n += 32) {
-            const int comp = n / C::PXP, x = n - comp * C::PXP;
-            slotm[(comp < 5 ? 5 + comp : 15) * C::NPOSP + C::PY * C::FEX + x] = __ldcg(recm + n);
+    if (C::HANDOFF && (t == C::T_IMPORT_XY || t == C::T_IMPORT_Z)) {
+      // import tasks: copy what the update of plane p-1 misses into the extra column / row of the flux / emf ring.
+      // XY: flux_y, emf_z of the closing row | flux_x, emf_z of the closing column | corner emf_z, of plane p-1;
+      // Z: emf_x of the closing row, emf_y of the closing column, of plane p.
+      const bool isZ = t == C::T_IMPORT_Z;
+      const int need = isZ ? pl + 1 : pl, g = isZ ? 0 : 1;
+      if (need >= 1) {
+        // lanes 0..2 poll the flags of the tile to the right, above, and above-right at the same time
+        const int prod = lane == 0 ? tileId - 1 : (lane == 1 ? tileId - ntx : tileId - ntx - 1);
+        const bool poll = (lane == 0 && hasRight) || (lane == 1 && hasAbove) || (lane == 2 && hasRight && hasAbove && !isZ);
+        if (poll) waitProgress(&prog[2 * prod + g], need);
+        __syncwarp();
+        const int ps = isZ ? p : p - 1, pls = isZ ? pl : pl - 1;  // plane (and its index) whose values are imported
+        T* slot = fe + ((unsigned)(ps + 3) % 3u) * C::FE_SLOT;
+        // record component -> ring component: row part flux_y[5] (5..9), emf_z (15), emf_x (17); column part flux_x[5]
+        // (0..4), emf_z (15), emf_y (16)
+        if (hasAbove) {
+          const T* rec = recAbove + (size_t)pls * C::HREC;
+          if (isZ) {
+            if (lane < C::PXP) slot[17 * C::NPOSP + C::PY * C::FEX + lane] = __ldcg(rec + 6 * C::PXP + lane);
+          } else {
+            for (int n = lane; n < 6 * C::PXP; n += 32) {
+              const int comp = n / C::PXP, x = n - comp * C::PXP;
+              slot[(comp < 5 ? 5 + comp : 15) * C::NPOSP + C::PY * C::FEX + x] = __ldcg(rec + n);
+            }
           }
         }
-      }
-      if (hasRight) {
-        const T* rec = recRight + (size_t)pl * C::HREC + C::HROW;
-        if (lane < C::PY) slot[16 * C::NPOSP + lane * C::FEX + C::PXP] = __ldcg(rec + 6 * C::PY + lane);
-        if (pl >= 1) {
-          const T* recm = rec - C::HREC;
-          for (int n = lane; n < 6 * C::PY; n += 32) {
-            const int comp = n / C::PY, y = n - comp * C::PY;
-            slotm[(comp < 5 ? comp : 15) * C::NPOSP + y * C::FEX + C::PXP] = __ldcg(recm + n);
+        if (hasRight) {
+          const T* rec = recRight + (size_t)pls * C::HREC + C::HROW;
+          if (isZ) {
+            if (lane >= 16 && lane < 16 + C::PY) slot[16 * C::NPOSP + (lane - 16) * C::FEX + C::PXP] = __ldcg(rec + 6 * C::PY + lane - 16);
+          } else {
+            for (int n = lane; n < 6 * C::PY; n += 32) {
+              const int comp = n / C::PY, y = n - comp * C::PY;
+              slot[(comp < 5 ? comp : 15) * C::NPOSP + y * C::FEX + C::PXP] = __ldcg(rec + n);
+            }
           }
         }
+        if (!isZ && hasRight && hasAbove && lane == 0)
+          slot[15 * C::NPOSP + C::PY * C::FEX + C::PXP] = __ldcg(recCorner + (size_t)pls * C::HREC + 5 * C::PXP);
       }
-      if (hasRight && hasAbove && pl >= 1 && lane == 0)
-        slotm[15 * C::NPOSP + C::PY * C::FEX + C::PXP] = __ldcg(recCorner + (size_t)(pl - 1) * C::HREC + 5 * C::PXP);
       __syncwarp();
       if (lane == 0) {
         signalCount(&cntImp[pl + 2]);
@@ -540,7 +541,8 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       }
       continue;
     }
-    const int ts = (C::HANDOFF && t > C::T_IMPORT) ? t - 2 : t - 1;  // solver / update task index without the two helpers
+    // solver / update task index without the helper tasks
+    const int ts = !C::HANDOFF ? t - 1 : (t > C::T_IMPORT_Z ? t - 3 : t - 2);
     const int kind = ts / C::NCH, chunk = ts - kind * C::NCH;
     const int pi = lane & 15, pj = chunk * 2 + (lane >> 4);
     const int i = i0 + pi, j = j0 + pj;
@@ -611,8 +613,8 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
         waitCount(&cntZ[pl + 1], 3 * C::NCH);
         waitCount(&cntXY[pl + 1], 3 * C::NCH);
         if (C::HANDOFF) {  // closing column / row imported: z group of planes p-1 and p, plane-local group of plane p-1
-          waitCount(&cntImp[pl + 2], 1);
-          waitCount(&cntImp[pl + 1], 1);
+          waitCount(&cntImp[pl + 2], 2);
+          waitCount(&cntImp[pl + 1], 2);
         }
         __syncwarp();
         // legacy tile: a cell of the closing column/row belongs to this tile only when it is the ghost face (iN / jN)
