@@ -29,6 +29,7 @@ int g_tileX = 32;  // run-time knob "tile_x"; tile_y = BX / tile_x
 // profiles/r02_d_mri_ab.txt)
 int g_rotDt = 0;
 bool rotDtInKernel() { return g_rotDt != 0; }
+extern int g_handoffHead;
 extern int g_fusedHandoff;  // run-time knob "fused_handoff": 16 x 8 hand-off tiles (1, default) or 15 x 7 self-closing tiles (0)
 int g_fusedB = 1;  // run-time knob "fused_b": 1 = fused flux+emf+update when available, 0 = separate kernels
 bool fusedRequested() { return g_fusedB != 0; }
@@ -399,7 +400,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapW,
                         const T* __restrict__ Uold, T* __restrict__ Unew, int kbase, int ka, int kb, int lz, T dt,
                         unsigned long long* __restrict__ dMaxInvDt, const ShearShift<T> sh, T* __restrict__ strips,
-                        int stripPlanes, T* __restrict__ hbuf, int* __restrict__ hsync, int ntx, int nty, int hplanes) {
+                        int stripPlanes, T* __restrict__ hbuf, int* __restrict__ hsync, int ntx, int nty, int hplanes,
+                        int headPlanes) {
   extern __shared__ unsigned char smemRaw[];
   // 128-byte alignment for the TMA destination, computed on the shared-window address so that the
   // compiler keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -474,6 +476,17 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   if (tid == 0) {
     loadPlane(za - 1);
     loadPlane(za);
+  }
+  if (C::HANDOFF) {
+    // head start of the producers: a tile begins when the tiles to its right and above have published their first
+    // HEAD planes, so that from then on its import tasks find the records they need already there (tiles do equal work
+    // and keep their distance; the consumer can never overtake).  One-time skew of a wave of tiles: (columns + rows of
+    // the wave) x HEAD planes, about 2 % of a 130-plane march; without it every import waits about one task for the
+    // producer running in lockstep and the four updates behind it wait too.
+    const int head = min(headPlanes, nPl);
+    if (tid == 0 && hasRight) waitProgress(&prog[2 * (tileId - 1) + 1], head);
+    if (tid == 32 && hasAbove) waitProgress(&prog[2 * (tileId - ntx) + 1], head);
+    __syncthreads();
   }
 
   for (;;) {
@@ -968,6 +981,11 @@ bool setTuning(const char* key, int value) {
     g_fusedB = value ? 1 : 0;
     return true;
   }
+  if (k == "handoff_head") {
+    if (value < 0 || value > 8) return false;
+    g_handoffHead = value;
+    return true;
+  }
   if (k == "fused_handoff") {
     g_fusedHandoff = value ? 1 : 0;
     return true;
@@ -1252,6 +1270,7 @@ struct FusedSel {
   typedef FusedTile<T, 15, 7, 512, false> Legacy;  // knob "fused_handoff" = 0
 };
 int g_fusedHandoff = 1;
+int g_handoffHead = 1;  // run-time knob "handoff_head": planes of head start of a tile's producers (0 = none)
 
 // the rotating-frame instantiation of the fused kernel: HLLD + 2-D HLLD in the rotating frame (any closure)
 template <typename T>
@@ -1363,17 +1382,19 @@ static void launchFusedUpdate(const KParams<T>& P, const T* Uold, T* Unew, const
   const ShearShift<T> sh{shearEnabled, jplus, frac};
   if (fastPath(P)) {
     k_fused_flux_emf_update<T, C, true><<<grid, C::THREADS, C::SMEM, s>>>(P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh,
-                                                                          nullptr, 0, hbuf, hsync, g.ntx, g.nty, hplanes);
+                                                                          nullptr, 0, hbuf, hsync, g.ntx, g.nty, hplanes, g_handoffHead);
     launched();
     return;
   }
   // rotating frame; with shearing-box boundaries the three border cell columns follow from the strips
   if (g_rotDt)
     k_fused_flux_emf_update<T, C, false, true><<<grid, C::THREADS, C::SMEM, s>>>(
-        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes);
+        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, d, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes,
+        g_handoffHead);
   else
     k_fused_flux_emf_update<T, C, false, false><<<grid, C::THREADS, C::SMEM, s>>>(
-        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, nullptr, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes);
+        P, map, Uold, Unew, sc.kbase, ka, kb, lz, dt, nullptr, sh, sc.strips, sc.planes, hbuf, hsync, g.ntx, g.nty, hplanes,
+        g_handoffHead);
   launched();
   if (shearEnabled) {
     const int nRows = P.jsize - 2 * P.gw + 1;
