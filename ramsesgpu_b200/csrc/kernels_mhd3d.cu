@@ -315,25 +315,25 @@ struct FusedTile {
   // the values imported from its neighbours, so that the update indexes one array without any branch
   static constexpr int FEX = HANDOFF ? PXP + 1 : PXP, FEY = HANDOFF ? PY + 1 : PY, NPOSP = FEX * FEY;
   static constexpr int NFE = 18;                                     // flux_x[5] flux_y[5] flux_z[5] emf z,y,x
-  static constexpr int NT = 1 + 7 * NCH + (HANDOFF ? 2 : 0);         // tasks per plane (+ the two import tasks)
-  // HANDOFF ticket order of a plane: TMA | import of the plane-local group of plane p-1 | z group | half of the
-  // plane-local group | import of the z group of plane p | rest of the plane-local group | updates of plane p-1.
-  // The imports sit several solver tasks ahead of the updates that read them: their two L2 round trips (flags, records)
-  // are hidden, and the data they wait for was produced a dozen tickets (z group) or a whole plane earlier.
-  static constexpr int T_IMPORT_XY = 1, T_IMPORT_Z = 2 + 3 * NCH + (3 * NCH) / 2;
+  static constexpr int NT = 1 + 7 * NCH + (HANDOFF ? 4 : 0);         // tasks per plane (+ the four hand-off helpers)
+  // HANDOFF ticket order of a plane p: TMA | import, then publish, the plane-local group of plane p-1 | z group | half
+  // of the plane-local group | publish, then import, the z group of plane p | rest of the plane-local group | updates of
+  // plane p-1.  The solver tasks are exactly those of the self-closing tile (no global store, no extra atomic); ONE
+  // helper warp per group copies the tile's first row / column from the ring to the record and releases the flag, one
+  // imports the neighbours' records.  Helpers sit several solver tasks behind what they wait for and ahead of what
+  // waits for them, so their L2 round trips are hidden.
+  static constexpr int T_IMPORT_XY = 1, T_PUBLISH_XY = 2, T_FIRST = 3;
+  static constexpr int T_PUBLISH_Z = T_FIRST + 3 * NCH + (3 * NCH) / 2, T_IMPORT_Z = T_PUBLISH_Z + 1;
   static constexpr int LZMAX = 160;                                  // planes per block (counter arrays)
   static constexpr unsigned W_BYTES = (unsigned)(NW_MHD * WCELLS * sizeof(T));
   static constexpr unsigned W_STRIDE = (W_BYTES + 127u) / 128u * 128u;
   static constexpr unsigned FE_SLOT = (unsigned)(NFE * NPOSP);       // reals per plane slot
   static constexpr unsigned FE_BYTES = (unsigned)(3 * FE_SLOT * sizeof(T));
   static constexpr unsigned NBAR = LZMAX + 2, NCNT = LZMAX + 4;
-  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 6u * NCNT * 4u + 32u;
+  static constexpr unsigned SMEM = 128u + 3u * W_STRIDE + FE_BYTES + NBAR * 8u + 4u * NCNT * 4u + 32u;
   // hand-off record of one tile and plane: row part [7][16] (flux_y[5], emf_z, emf_x of the tile's FIRST row), then
   // column part [7][8] (flux_x[5], emf_z, emf_y of its FIRST column)
   static constexpr int HROW = 7 * PXP, HREC = HROW + 7 * PY;
-  // tasks of a plane that publish: emf_x, emf_y (z group: needed by the consumer's update one plane earlier than the
-  // rest) and emf_z, flux_x, flux_y (plane-local group); two progress flags per tile
-  static constexpr int NPUBZ = 2 * NCH, NPUBXY = 3 * NCH;
 };
 
 template <typename T, typename C>
@@ -368,14 +368,6 @@ __device__ __forceinline__ void waitProgress(const int* flag, int need) {
   }
 }
 
-// counter in shared memory bumped with acquire-release semantics at CTA scope (returns the old value): orders the warp's
-// hand-off record stores before the count and, by cumulativity, before the publisher's gpu-scope release store -- no
-// device-wide fence per task
-__device__ __forceinline__ int bumpCount(int* c) {
-  int old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(old) : "r"(tma::smemAddr(c)) : "memory");
-  return old;
-}
 // completion counters in shared memory: release-add by the finishing warp, acquire-poll by waiters
 __device__ __forceinline__ void signalCount(int* c) {
   asm volatile("red.release.cta.shared::cta.add.s32 [%0], 1;" ::"r"(tma::smemAddr(c)) : "memory");
@@ -412,9 +404,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
   int* cntAll = reinterpret_cast<int*>(bars + C::NBAR);  // cnt*[pl + 2], pl = plane - za
   int* cntZ = cntAll + C::NCNT;
   int* cntXY = cntZ + C::NCNT;
-  int* cntPubZ = cntXY + C::NCNT;
-  int* cntPubXY = cntPubZ + C::NCNT;
-  int* cntImp = cntPubXY + C::NCNT;
+  int* cntImp = cntXY + C::NCNT;
   int* ticket = cntImp + C::NCNT;
   int* pubSeq = ticket + 1;  // [0] z-group, [1] plane-local group: planes published so far, in order
 
@@ -457,8 +447,6 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
     cntAll[n] = (n < 2) ? C::NT : 0;      // planes za-2, za-1 count as complete
     cntZ[n] = (n < 2) ? 3 * C::NCH : 0;
     cntXY[n] = (n < 2) ? 3 * C::NCH : 0;
-    cntPubZ[n] = 0;
-    cntPubXY[n] = 0;
     cntImp[n] = (n < 2) ? 2 : 0;
   }
   if (tid == 0) {
@@ -501,6 +489,41 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       if (lane == 0 && p + 1 <= fhi) {
         tma::fenceProxyAsync();
         loadPlane(p + 1);
+      }
+      __syncwarp();
+      if (lane == 0) signalCount(&cntAll[pl + 2]);
+      continue;
+    }
+    if (C::HANDOFF && (t == C::T_PUBLISH_XY || t == C::T_PUBLISH_Z)) {
+      // publish tasks: when the group's solver tasks of the plane are done, copy the tile's FIRST row and column from the
+      // ring to the record of the plane and release-store the progress flag (in plane order).
+      // XY: flux_y, emf_z of row 0 | flux_x, emf_z of column 0, of plane p-1;  Z: emf_x of row 0, emf_y of column 0, of plane p
+      const bool isZ = t == C::T_PUBLISH_Z;
+      const int q = isZ ? pl : pl - 1, g = isZ ? 0 : 1;
+      if (q >= 0) {
+        waitCount(isZ ? &cntZ[q + 2] : &cntXY[q + 2], 3 * C::NCH);
+        const T* slot = fe + ((unsigned)(za + q) % 3u) * C::FE_SLOT;
+        T* rec = recMine + (size_t)q * C::HREC;
+        if (isZ) {
+          if (lane < C::PXP) rec[6 * C::PXP + lane] = slot[17 * C::NPOSP + lane];
+          else if (lane < C::PXP + C::PY) rec[C::HROW + 6 * C::PY + lane - C::PXP] = slot[16 * C::NPOSP + (lane - C::PXP) * C::FEX];
+        } else {
+          for (int n = lane; n < 6 * C::PXP; n += 32) {
+            const int comp = n / C::PXP, x = n - comp * C::PXP;
+            rec[n] = slot[(comp < 5 ? 5 + comp : 15) * C::NPOSP + x];
+          }
+          for (int n = lane; n < 6 * C::PY; n += 32) {
+            const int comp = n / C::PY, y = n - comp * C::PY;
+            rec[C::HROW + n] = slot[(comp < 5 ? comp : 15) * C::NPOSP + y * C::FEX];
+          }
+        }
+        __threadfence();  // every lane's record entries are visible device-wide before the flag moves
+        __syncwarp();
+        if (lane == 0) {
+          waitCount(&pubSeq[g], q);  // a flag counts CONSECUTIVE published planes (a block runs up to two planes ahead)
+          publishProgress(&prog[2 * tileId + g], q + 1);
+          signalCount(&pubSeq[g]);
+        }
       }
       __syncwarp();
       if (lane == 0) signalCount(&cntAll[pl + 2]);
@@ -555,7 +578,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
       continue;
     }
     // solver / update task index without the helper tasks
-    const int ts = !C::HANDOFF ? t - 1 : (t > C::T_IMPORT_Z ? t - 3 : t - 2);
+    const int ts = !C::HANDOFF ? t - 1 : (t > C::T_IMPORT_Z ? t - C::T_FIRST - 2 : t - C::T_FIRST);
     const int kind = ts / C::NCH, chunk = ts - kind * C::NCH;
     const int pi = lane & 15, pj = chunk * 2 + (lane >> 4);
     const int i = i0 + pi, j = j0 + pj;
@@ -578,12 +601,6 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
               const BorderView<T> Eb{strips, P.jsize, stripPlanes, kbase, gw, P.nx, 15};
               Eb(2 - dir, i, j, p) = E(2 - dir, i, j, p);
             }
-            if (C::HANDOFF) {  // first row: emf_z, emf_x; first column: emf_z, emf_y
-              const T e = E(2 - dir, i, j, p);
-              T* rec = recMine + (size_t)pl * C::HREC;
-              if (pj == 0 && dir != 1) rec[(dir == 2 ? 5 : 6) * C::PXP + pi] = e;
-              if (pi == 0 && dir != 0) rec[C::HROW + (dir == 2 ? 5 : 6) * C::PY + pj] = e;
-            }
           }
         } else {
           // a face is only needed where both transverse indexes are inner (k_flux)
@@ -595,24 +612,7 @@ k_fused_flux_emf_update(const __grid_constant__ KParams<T> P, const __grid_const
 #pragma unroll
               for (int c = 0; c < 5; ++c) Fb(5 * dir + c, i, j, p) = F(5 * dir + c, i, j, p);
             }
-            if (C::HANDOFF && ((dir == 1 && pj == 0) || (dir == 0 && pi == 0))) {  // first row: flux_y; first column: flux_x
-              T* rec = recMine + (size_t)pl * C::HREC + (dir == 1 ? pi : C::HROW + pj);
-              const int st = (dir == 1) ? C::PXP : C::PY;
-#pragma unroll
-              for (int c = 0; c < 5; ++c) rec[c * st] = F(5 * dir + c, i, j, p);
-            }
           }
-        }
-      }
-      if (C::HANDOFF && kind != 2) {  // every task of the five publishing kinds counts, whether it solved anything or not
-        __syncwarp();
-        const int g = zgrp ? 0 : 1;
-        if (lane == 0 && bumpCount(zgrp ? &cntPubZ[pl] : &cntPubXY[pl]) == (zgrp ? C::NPUBZ : C::NPUBXY) - 1) {
-          // planes may finish out of order (a block runs up to two planes ahead): a flag counts CONSECUTIVE published
-          // planes, so the last warp of plane pl waits for plane pl-1 to be out (earlier tickets: cannot deadlock)
-          waitCount(&pubSeq[g], pl);
-          publishProgress(&prog[2 * tileId + g], pl + 1);
-          signalCount(&pubSeq[g]);
         }
       }
       __syncwarp();
