@@ -171,6 +171,8 @@ bool setTuning(const char* key, int value);
 bool fusedRequested();
 // "rot_dt" knob (default off): the rotating-frame fused kernel reduces the inverse dt of the new state itself
 bool rotDtInKernel();
+// "fused_handoff" knob (default off): 16 x 8 hand-off tiles of the fused update
+bool fusedHandoffRequested();
 // "fused_a" knob (default on): fused prim+elec+trace kernel
 bool fusedTraceRequested();
 void resetKernelLaunchCount();

@@ -290,14 +290,14 @@ __global__ void __launch_bounds__(BX, MINB) k_update(const __grid_constant__ KPa
 //   run-ahead gate: a task of plane p starts only when plane p-2 is complete (ring safety)
 // The arithmetic is the one of k_flux / k_emf / k_update (same device functions).
 // ------------------------------------------------------------------------------------------------
-// HANDOFF_ = true (default): a tile owns TW x TH = 16 x 8 CELLS and solves exactly the 16 x 8 low faces / edges of its
+// HANDOFF_ = true (knob "fused_handoff" = 1; see the measurement at g_fusedHandoff): a tile owns TW x TH = 16 x 8 CELLS and solves exactly the 16 x 8 low faces / edges of its
 // own cells; the faces / edges that close its last column and last row (x-face fluxes and emf_z, emf_y of column i0+16;
 // y-face fluxes and emf_z, emf_x of row j0+8) are NOT solved a second time: the tile to the right / above publishes
 // them plane by plane in a small HBM buffer (168 reals per tile and plane) and this tile's update reads them there.
 // Tiles take their index from an atomic counter in "right to left, top to bottom" order, so that a tile only ever waits
 // for tiles whose blocks are already running (no assumption on the block scheduler).  Every Riemann problem of the grid
-// is solved once: 128 cells per 128 solves instead of 105 (HANDOFF_ = false: the 15 x 7 tile that solves its closing
-// column / row itself, knob "fused_handoff" = 0).
+// is solved once: 128 cells per 128 solves instead of 105.  HANDOFF_ = false (default): the 15 x 7 tile that solves its
+// closing column / row itself.
 template <typename T, int TW_, int TH_, int THREADS_, bool HANDOFF_ = false>
 struct FusedTile {
   static constexpr int TW = TW_, TH = TH_, THREADS = THREADS_;
@@ -1266,10 +1266,16 @@ void MhdKernels<T>::fusedTrace(const KParams<T>& P, const T* U, MhdScratch<T> sc
 // 512 threads / 124 registers: a 384-thread build (152 registers) measured 7 % slower, 640 threads spill
 template <typename T>
 struct FusedSel {
-  typedef FusedTile<T, 16, 8, 512, true> Cfg;      // hand-off tile (default)
-  typedef FusedTile<T, 15, 7, 512, false> Legacy;  // knob "fused_handoff" = 0
+  typedef FusedTile<T, 16, 8, 512, true> Cfg;      // hand-off tile (knob "fused_handoff" = 1)
+  typedef FusedTile<T, 15, 7, 512, false> Legacy;  // self-closing tile (default)
 };
-int g_fusedHandoff = 1;
+// Measured on the B200 (profiles/r02_l_handoff_vs_self_closing.txt): the hand-off kernel executes 15 % fewer instructions
+// (every Riemann problem solved once) but runs at 6.8 ms against 4.7 ms at 256^3: its 3400 SASS instructions (54 KB, the
+// four helper tasks on top of the solvers and the update) no longer fit the instruction cache that the 2856-instruction
+// self-closing kernel just fits (stall no_instruction 1.07 against 0.16 per issue, issue 42 % against 63 %).  Results are
+// bitwise identical; the self-closing tile stays the default until the solver code is small enough for both.
+int g_fusedHandoff = 0;
+bool fusedHandoffRequested() { return g_fusedHandoff != 0; }
 int g_handoffHead = 1;  // run-time knob "handoff_head": planes of head start of a tile's producers (0 = none)
 
 // the rotating-frame instantiation of the fused kernel: HLLD + 2-D HLLD in the rotating frame (any closure)

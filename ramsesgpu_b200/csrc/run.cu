@@ -795,6 +795,7 @@ class RunImpl final : public Run {
   }
   void ensureScratchMhd3d(bool generic) {
     if (sc_.W && generic && !sc_.F) freeScratch();  // a knob asked for the separate kernels after a W-only allocation
+    if (sc_.W && sc_.fused && fusedHandoffRequested() && !sc_.hbuf) freeScratch();  // ... or for the hand-off tiles
     if (sc_.W) return;
     const size_t plane = (size_t)kp_.isize * kp_.jsize;
     const size_t perPlane = plane * sizeof(T) * (generic ? (8 + NW_MHD + 15 + 3 + 3) : NW_MHD);
