@@ -95,7 +95,15 @@ class RunImpl final : public Run {
     cells_ = (size_t)kp_.isize * kp_.jsize * kp_.ksize;
     elems_ = cells_ * kp_.nvar;
     RG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    RG_CUDA(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+    // the communication stream gets the highest priority: the compute kernels are persistent (one block per SM, all of
+    // its registers and shared memory), so the NCCL send/recv blocks and the ghost fills of an early halo only find room
+    // when a compute block retires -- with priority they take the first SM that frees up instead of queueing behind the
+    // remaining waves of the interior update
+    {
+      int prLow = 0, prHigh = 0;
+      RG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+      RG_CUDA(cudaStreamCreateWithPriority(&comm_stream_, cudaStreamNonBlocking, prHigh));
+    }
     RG_CUDA(cudaEventCreate(&ev0_));
     RG_CUDA(cudaEventCreate(&ev1_));
     RG_CUDA(cudaEventCreateWithFlags(&ev_sync_, cudaEventDisableTiming));
