@@ -8,6 +8,7 @@
 #include <fstream>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -672,6 +673,10 @@ class RunImpl final : public Run {
   }
 
   void initComm(const DistInit& dist) {
+    // two point-to-point channels are plenty for 2 x gw planes per step and leave the SMs to the compute kernels the
+    // exchange overlaps with (no effect when the process has already initialised NCCL with other settings)
+    setenv("NCCL_MAX_P2P_NCHANNELS", "2", 0);
+    setenv("NCCL_MIN_P2P_NCHANNELS", "1", 0);
     const char* err = nullptr;
     nccl_ = NcclApi::get(&err);
     if (!nccl_) throw std::runtime_error(err ? err : "NCCL unavailable");
