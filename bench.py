@@ -25,11 +25,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# The halo of a slab is 2 x 3 planes per step: two NCCL point-to-point channels move it in a fraction of the interior
-# update; more channels only take more SMs away from the persistent compute kernels it overlaps with.
-# NCCL reads its environment once per process, so this has to precede the first communicator (torch's included).
-os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
-os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "1")
 
 METRIC = "Mcell-updates/s (FP64) on 3D MHD Godunov"
 UNIT = "Mcell-updates/s"

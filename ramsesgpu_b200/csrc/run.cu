@@ -96,15 +96,11 @@ class RunImpl final : public Run {
     cells_ = (size_t)kp_.isize * kp_.jsize * kp_.ksize;
     elems_ = cells_ * kp_.nvar;
     RG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    // the communication stream gets the highest priority: the compute kernels are persistent (one block per SM, all of
-    // its registers and shared memory), so the NCCL send/recv blocks and the ghost fills of an early halo only find room
-    // when a compute block retires -- with priority they take the first SM that frees up instead of queueing behind the
-    // remaining waves of the interior update
-    {
-      int prLow = 0, prHigh = 0;
-      RG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-      RG_CUDA(cudaStreamCreateWithPriority(&comm_stream_, cudaStreamNonBlocking, prHigh));
-    }
+    // (measured on 2 GPUs, profiles/r02_n_halo_overlap_notes.txt: a highest-priority communication stream lets the NCCL
+    // blocks take SMs from the persistent compute kernel mid-flight and spin there for the peer -- fused update 4.90 ->
+    // 5.11 ms, step 6.70 -> 6.84 ms; two point-to-point channels instead of the default starve the exchange -- config-4
+    // slab 3.97 -> 5.17 ms.  Default priority and channels it is.)
+    RG_CUDA(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
     RG_CUDA(cudaEventCreate(&ev0_));
     RG_CUDA(cudaEventCreate(&ev1_));
     RG_CUDA(cudaEventCreateWithFlags(&ev_sync_, cudaEventDisableTiming));
@@ -673,10 +669,6 @@ class RunImpl final : public Run {
   }
 
   void initComm(const DistInit& dist) {
-    // two point-to-point channels are plenty for 2 x gw planes per step and leave the SMs to the compute kernels the
-    // exchange overlaps with (no effect when the process has already initialised NCCL with other settings)
-    setenv("NCCL_MAX_P2P_NCHANNELS", "2", 0);
-    setenv("NCCL_MIN_P2P_NCHANNELS", "1", 0);
     const char* err = nullptr;
     nccl_ = NcclApi::get(&err);
     if (!nccl_) throw std::runtime_error(err ? err : "NCCL unavailable");
