@@ -16,30 +16,45 @@
 // two-kernel path through W[20] (reference: HydroRunGodunov.cpp:2658-2890 godunov_unsplit_cpu_v1, trace.h:544-661,
 // slope.h:324-427, riemann.h, and the GPU kernels godunov_unsplit.cuh:1829,3212 whose work this replaces).
 #include <algorithm>
+#include <cstring>
 
 #include "hydro_cells.cuh"
 #include "hydro_device.cuh"
 #include "kernel_common.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace rg {
 
 int g_hydroFused = 1;  // run-time knob "hydro_fused": the one-kernel step (default) or trace + flux/update through W
-int g_hydroRows = 0;   // run-time knob "hydro_rows": rows of the thread block (0 = default: 20 in FP32, 12 in FP64)
+int g_hydroTma = 1;    // run-time knob "hydro_tma": conservative tiles by TMA (default) or per-thread loads
+int g_hydroRows = 0;   // run-time knob "hydro_rows": rows of the thread block (0 = default: 24 in FP32, 16 in FP64 with TMA tiles; 20 / 12 without)
 
 namespace {
 
 template <typename T, int TY_>
 struct HydroFusedTile {
   static constexpr int CX = 32, CY = TY_, UX = CX - 4, UY = CY - 4, THREADS = CX * CY;
-  static constexpr unsigned SMEM = (unsigned)(3 * 5 * CY * CX * sizeof(T));  // primitives | high-y face states | low-y fluxes
+  static constexpr unsigned XCH = (unsigned)(3 * 5 * CY * CX * sizeof(T));   // primitives | high-y face states | low-y fluxes
+  // TMA path: ring of 4 planes of the conservative tile [5][CY][32] (plane p for the update, p+1, p+2 being converted,
+  // p+3 in flight) behind the exchange arrays, 128-byte aligned, + 4 mbarriers
+  static constexpr unsigned U_BYTES = (unsigned)(5 * CY * CX * sizeof(T));
+  static constexpr unsigned U_OFF = (XCH + 127u) / 128u * 128u;
+  static constexpr unsigned SMEM = XCH, SMEM_TMA = 128u + U_OFF + 4u * U_BYTES + 64u;
 };
 
-template <typename T, int RS, typename C>
+// TMAU = true: the conservative tile of a plane (all 5 variables, 32 x CY cells with the halo) arrives by ONE
+// cp.async.bulk.tensor.4d per plane (UTMALDG, mbarrier completion, issued three planes ahead by one thread) in a 4-plane
+// shared-memory ring; threads read their cell from there for cons->prim and again, two planes later, as the old state of
+// the update.  No per-thread global loads of U, no prefetch registers.  TMAU = false: per-thread coalesced loads (row
+// pitch not a multiple of 16 bytes).
+template <typename T, int RS, typename C, bool TMAU>
 __global__ void __launch_bounds__(C::THREADS, 1)
-k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, T* __restrict__ Unew, int k0, int k1, int lz,
-              T dt, unsigned long long* __restrict__ slots) {
-  extern __shared__ unsigned char smemRawH[];
+k_hydro_fused(const __grid_constant__ KParams<T> P, const __grid_constant__ CUtensorMap mapU, const T* __restrict__ Uold,
+              T* __restrict__ Unew, int k0, int k1, int lz, T dt, unsigned long long* __restrict__ slots) {
+  extern __shared__ unsigned char smemRawH0[];
+  // 128-byte alignment for the TMA destination (computed on the shared-window address: LDS/STS, not generic LD/ST)
+  unsigned char* smemRawH = smemRawH0 + (TMAU ? ((128u - (tma::smemAddr(smemRawH0) & 127u)) & 127u) : 0u);
   T* sQ = reinterpret_cast<T*>(smemRawH);   // [5][CY][32] primitives of the plane being traced
   T* sY = sQ + 5 * C::CY * C::CX;           // [5][CY][32] high-y face states
   T* sF = sY + 5 * C::CY * C::CX;           // [5][CY][32] low-y fluxes
@@ -60,7 +75,34 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
   const int sidx = ty * C::CX + tx;
   constexpr int SV = C::CY * C::CX;  // stride between variables in the shared tiles
 
+  // conservative tiles (TMA path): plane q lives in ring slot (q - (za-2)) & 3; out-of-range cells arrive as zeros
+  // (cons->prim floors them to a finite state, which no updated cell ever reads)
+  unsigned char* const uring = smemRawH + C::U_OFF;
+  uint64_t* const ubar = reinterpret_cast<uint64_t*>(uring + 4u * C::U_BYTES);
+  const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+  auto uslot = [&](int q) -> const T* { return reinterpret_cast<const T*>(uring + (unsigned)((q - (za - 2)) & 3) * C::U_BYTES); };
+  auto issue = [&](int q) {  // one thread
+    const int n = q - (za - 2);
+    tma::mbarExpectTx(&ubar[n & 3], C::U_BYTES);
+    tma::loadTile4D(uring + (unsigned)(n & 3) * C::U_BYTES, &mapU, &ubar[n & 3], gw + blockIdx.x * C::UX - 2,
+                    gw + blockIdx.y * C::UY - 2, q, 0);
+  };
+  auto arrived = [&](int q) {
+    const int n = q - (za - 2);
+    tma::mbarWait(&ubar[n & 3], (unsigned)(n >> 2) & 1u);
+  };
+  if (TMAU) {
+    if (leader) {
+      for (int n = 0; n < 4; ++n) tma::mbarInit(&ubar[n], 1);
+      tma::fenceBarrierInit();
+    }
+    __syncthreads();
+    if (leader)
+      for (int q = za - 2; q <= min(za + 1, zb + 1); ++q) issue(q);
+  }
+  T raw[5];
   auto loadRaw = [&](int q, T (&u)[5]) {
+    if (TMAU) return;  // (the tile is on its way)
     if (cellOK) {
 #pragma unroll
       for (int v = 0; v < 5; ++v) u[v] = __ldg(Uold + v * comp + (size_t)q * plane + col);
@@ -68,12 +110,20 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
       u[ID] = T(1); u[IP] = T(1); u[IU] = T(0); u[IV] = T(0); u[IW] = T(0);
     }
   };
-  auto toPrim = [&](const T (&u)[5], T (&q)[5]) { dev::cons_to_prim_hydro(P, u[ID], u[IP], u[IU], u[IV], u[IW], q); };
+  auto toPrim = [&](int q, const T (&u)[5], T (&pr)[5]) {
+    if (TMAU) {
+      arrived(q);
+      const T* t = uslot(q);
+      dev::cons_to_prim_hydro(P, t[ID * SV + sidx], t[IP * SV + sidx], t[IU * SV + sidx], t[IV * SV + sidx], t[IW * SV + sidx], pr);
+    } else {
+      dev::cons_to_prim_hydro(P, u[ID], u[IP], u[IU], u[IV], u[IW], pr);
+    }
+  };
 
-  T qm1[5], q0[5], qp1[5], raw[5];
-  loadRaw(za - 2, raw); toPrim(raw, qm1);
-  loadRaw(za - 1, raw); toPrim(raw, q0);
-  loadRaw(za, raw);     toPrim(raw, qp1);
+  T qm1[5], q0[5], qp1[5];
+  loadRaw(za - 2, raw); toPrim(za - 2, raw, qm1);
+  loadRaw(za - 1, raw); toPrim(za - 1, raw, q0);
+  loadRaw(za, raw);     toPrim(za, raw, qp1);
 #pragma unroll
   for (int v = 0; v < 5; ++v) sQ[v * SV + sidx] = q0[v];
   __syncthreads();
@@ -127,9 +177,15 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
     T fxl[5] = {T(0), T(0), T(0), T(0), T(0)}, fxh[5], fyl[5] = {T(0), T(0), T(0), T(0), T(0)};
     T un[5] = {T(0), T(0), T(0), T(0), T(0)};
     if (mid && upd) {  // old state of the cell: requested here, consumed after the two barriers below
-      const size_t idx = (size_t)p * plane + col;
+      if (TMAU) {
+        const T* t = uslot(p);
 #pragma unroll
-      for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
+        for (int v = 0; v < 5; ++v) un[v] = t[v * SV + sidx];
+      } else {
+        const size_t idx = (size_t)p * plane + col;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
+      }
     }
     if (mid) {
       // x faces: left state from lane-1, high flux from lane+1
@@ -146,6 +202,10 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
       sY[0 * SV + sidx] = hy.r; sY[1 * SV + sidx] = hy.p; sY[2 * SV + sidx] = hy.u; sY[3 * SV + sidx] = hy.v; sY[4 * SV + sidx] = hy.w;
     }
     __syncthreads();  // A: sY complete; every read of sQ (plane p) is done
+    if (TMAU && leader && p + 3 <= zb + 1) {  // the slot of plane p-1 (last read before this barrier) takes plane p+3
+      tma::fenceProxyAsync();
+      issue(p + 3);
+    }
     // the primitives of plane p+1 replace those of plane p for the next iteration
 #pragma unroll
     for (int v = 0; v < 5; ++v) sQ[v * SV + sidx] = qp1[v];
@@ -170,9 +230,28 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const T* __restrict__ Uold, 
     }
 #pragma unroll
     for (int v = 0; v < 5; ++v) { qm1[v] = q0[v]; q0[v] = qp1[v]; }
-    if (more) toPrim(raw, qp1);
+    if (more) toPrim(p + 2, raw, qp1);
   }
   if (slots != nullptr) reduceMaxToSlots(invDt, slots);
+}
+
+// tensor map of the state array [var][k][j][i] with a box of 32 x CY x 1 x 5 elements, cached per (array, shape)
+template <typename T, typename C>
+static const CUtensorMap* hydroTensorMap(const KParams<T>& P, const T* U) {
+  struct Entry { const void* base; int isize, jsize, ksize, dev; CUtensorMap map; bool ok; };
+  static Entry cache[8];
+  static int used = 0;
+  const int dev = currentDevice();
+  for (int n = 0; n < used; ++n)
+    if (cache[n].base == U && cache[n].isize == P.isize && cache[n].jsize == P.jsize && cache[n].ksize == P.ksize &&
+        cache[n].dev == dev)
+      return cache[n].ok ? &cache[n].map : nullptr;
+  Entry& e = cache[used < 8 ? used++ : (used = 1, 0)];
+  e.base = U; e.isize = P.isize; e.jsize = P.jsize; e.ksize = P.ksize; e.dev = dev;
+  // box rows start at cell gw - 2 + 28 bx: 16-byte aligned when (gw - 2) and 28 elements are
+  e.ok = ((P.gw - 2) * sizeof(T)) % 16 == 0 && (C::UX * sizeof(T)) % 16 == 0 &&
+         tma::encodeTile4D(&e.map, U, (int)sizeof(T), P.isize, P.jsize, P.ksize, 5, C::CX, C::CY);
+  return e.ok ? &e.map : nullptr;
 }
 
 template <typename T, typename C>
@@ -181,10 +260,11 @@ void launchHydroFused(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k
   static bool attrSetDev[MAX_DEVICES] = {false};
   bool& attrSet = attrSetDev[currentDevice()];
   if (!attrSet) {
-    cudaFuncSetAttribute(k_hydro_fused<T, RS_HLLC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    cudaFuncSetAttribute(k_hydro_fused<T, RS_HLL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    cudaFuncSetAttribute(k_hydro_fused<T, RS_APPROX, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    cudaFuncSetAttribute(k_hydro_fused<T, -1, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+#define RG_HATTR(RS)                                                                                                      \
+  cudaFuncSetAttribute(k_hydro_fused<T, RS, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);      \
+  cudaFuncSetAttribute(k_hydro_fused<T, RS, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_TMA)
+    RG_HATTR(RS_HLLC); RG_HATTR(RS_HLL); RG_HATTR(RS_APPROX); RG_HATTR(-1);
+#undef RG_HATTR
     attrSet = true;
   }
   const int ntx = (P.nx + C::UX - 1) / C::UX, nty = (P.ny + C::UY - 1) / C::UY, planes = k1 - k0, nSM = smCount();
@@ -200,11 +280,24 @@ void launchHydroFused(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k
   }
   const int lz = (planes + bestNz - 1) / bestNz;
   const dim3 g(ntx, nty, (planes + lz - 1) / lz), b(C::CX, C::CY, 1);
-  switch (P.riemannSolver) {  // one instantiation per Riemann solver: a single solver body in the kernel
-    case RS_HLLC: k_hydro_fused<T, RS_HLLC, C><<<g, b, C::SMEM, s>>>(P, Uold, Unew, k0, k1, lz, dt, slots); break;
-    case RS_HLL: k_hydro_fused<T, RS_HLL, C><<<g, b, C::SMEM, s>>>(P, Uold, Unew, k0, k1, lz, dt, slots); break;
-    case RS_APPROX: k_hydro_fused<T, RS_APPROX, C><<<g, b, C::SMEM, s>>>(P, Uold, Unew, k0, k1, lz, dt, slots); break;
-    default: k_hydro_fused<T, -1, C><<<g, b, C::SMEM, s>>>(P, Uold, Unew, k0, k1, lz, dt, slots); break;
+  const CUtensorMap* mp = g_hydroTma ? hydroTensorMap<T, C>(P, Uold) : nullptr;
+  if (mp != nullptr) {
+    const CUtensorMap map = *mp;
+    switch (P.riemannSolver) {  // one instantiation per Riemann solver: a single solver body in the kernel
+      case RS_HLLC: k_hydro_fused<T, RS_HLLC, C, true><<<g, b, C::SMEM_TMA, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      case RS_HLL: k_hydro_fused<T, RS_HLL, C, true><<<g, b, C::SMEM_TMA, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      case RS_APPROX: k_hydro_fused<T, RS_APPROX, C, true><<<g, b, C::SMEM_TMA, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      default: k_hydro_fused<T, -1, C, true><<<g, b, C::SMEM_TMA, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+    }
+  } else {
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    switch (P.riemannSolver) {
+      case RS_HLLC: k_hydro_fused<T, RS_HLLC, C, false><<<g, b, C::SMEM, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      case RS_HLL: k_hydro_fused<T, RS_HLL, C, false><<<g, b, C::SMEM, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      case RS_APPROX: k_hydro_fused<T, RS_APPROX, C, false><<<g, b, C::SMEM, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+      default: k_hydro_fused<T, -1, C, false><<<g, b, C::SMEM, s>>>(P, map, Uold, Unew, k0, k1, lz, dt, slots); break;
+    }
   }
   launched();
 }
@@ -217,9 +310,12 @@ template <typename T>
 void HydroKernels<T>::fusedStep(const KParams<T>& P, const T* Uold, T* Unew, int k0, int k1, T dt, unsigned long long* slots,
                                 cudaStream_t s) {
   if (k1 <= k0) return;
-  // measured at 512^3 FP32 HLLC / 384^3 FP64 (profiles/r02_c_hydro_rows_ab.txt): 12 rows 7.80 / 6.24 ms, 16: 6.50 / 6.50,
-  // 20: 5.95 / 7.27 (spills in FP64), 24: 6.00 / 8.65
-  const int rows = g_hydroRows ? g_hydroRows : (sizeof(T) == 4 ? 20 : 12);
+  // measured at 512^3 FP32 HLLC / 384^3 FP64 (profiles/r02_p_hydro_tma_ab.txt), ms per launch by rows of the block:
+  //   TMA tiles        12: 7.40 / 5.66   16: 6.21 / 5.37   20: 5.68 / 7.09   24: 5.60 / 9.01
+  //   per-thread loads 12: 7.81 / 6.24   16: 6.50 / 6.50   20: 5.96 / 7.26   24: 6.01 / 8.64   (FP64: spills from 20 rows on)
+  const bool tmaTiles = g_hydroTma && ((size_t)P.isize * sizeof(T)) % 16 == 0 && ((P.gw - 2) * sizeof(T)) % 16 == 0 &&
+                        (reinterpret_cast<uintptr_t>(Uold) & 15) == 0;
+  const int rows = g_hydroRows ? g_hydroRows : (sizeof(T) == 4 ? (tmaTiles ? 24 : 20) : (tmaTiles ? 16 : 12));
   if (rows == 24) launchHydroFused<T, HydroFusedTile<T, 24>>(P, Uold, Unew, k0, k1, dt, slots, s);
   else if (rows == 20) launchHydroFused<T, HydroFusedTile<T, 20>>(P, Uold, Unew, k0, k1, dt, slots, s);
   else if (rows == 16) launchHydroFused<T, HydroFusedTile<T, 16>>(P, Uold, Unew, k0, k1, dt, slots, s);

@@ -998,6 +998,10 @@ bool setTuning(const char* key, int value) {
     g_fusedA = value ? 1 : 0;
     return true;
   }
+  if (k == "hydro_tma") {
+    g_hydroTma = value ? 1 : 0;
+    return true;
+  }
   if (k == "hydro_rows") {
     if (value != 0 && value != 12 && value != 16 && value != 20 && value != 24) return false;
     g_hydroRows = value;

@@ -198,3 +198,27 @@ def test_fused_step_full_size_fp32_vs_oracle_slab(native, oracle32):
         norm = np.sqrt(np.sum(ref ** 2)) if v < 2 else mom
         assert np.sqrt(np.sum((ref - got) ** 2)) / norm < TOL_F32, v
     assert np.allclose(dtg, dto, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,mesh", [
+    ("kh3d_16x8x16_f32_s10", {"nx": 68, "ny": 20, "nz": 24}),          # FP32: row pitch 72 floats = 288 bytes (16-byte multiple)
+    ("kh3d_16x8x16_f64_s10", {"nx": 56, "ny": 16, "nz": 40}),
+    ("implode3d_16_s8", {"nx": 36, "ny": 30, "nz": 70}),               # walls, several z ranges
+])
+def test_fused_step_tma_tiles_equal_per_thread_loads(native, name, mesh):
+    """The conservative tiles of the fused hydro kernel arrive by TMA (one cp.async.bulk.tensor per plane into a 4-plane
+    shared-memory ring, knob hydro_tma = 1, default) or by per-thread loads (hydro_tma = 0, also the fallback for row
+    pitches that are not a multiple of 16 bytes): same values, same arithmetic, BITWISE equal results."""
+    from ramsesgpu_b200 import set_tuning
+    g = load_golden(name)
+    fp32 = str(g["precision"]) == "f32"
+    ini = ini_override(str(g["ini"]), {"mesh": mesh})
+    try:
+        set_tuning("hydro_tma", 0)
+        Ua, dta, gw = run_gpu(ini, 6, fp32=fp32)
+        set_tuning("hydro_tma", 1)
+        Ub, dtb, _ = run_gpu(ini, 6, fp32=fp32)
+    finally:
+        set_tuning("hydro_tma", 1)
+    inner = (slice(None), slice(gw, -gw), slice(gw, -gw), slice(gw, -gw))
+    assert np.array_equal(Ua[inner], Ub[inner]) and np.array_equal(dta, dtb)

@@ -1,5 +1,5 @@
 """A/B timing of the hydro step variants at 512^3 FP32 (BASELINE.json configs[2]) on the GPU box: the fused one-kernel
-step against trace + flux/update through W (register-tiled and gather flux kernels); `f64` as argument: 384^3 FP64.
+step (block rows, conservative tiles by TMA or per-thread loads) against trace + flux/update through W; `f64` as argument: 384^3 FP64.
    python tools/hydro_ab.py [f64]"""
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -18,12 +18,14 @@ with HydroRunGodunov(ini, fp32=not F64) as run:
     s = (0, 0.0, 0.0)
     for _ in range(3): s = run.oneStepIntegration(*s)
     for rep in range(2):
-        for fused, tile, rows in ((0, 1, 0), (1, 1, 12), (1, 1, 16), (1, 1, 20), (1, 1, 24)):
+        for fused, tile, rows, utma in ((0, 1, 0, 0), (1, 1, 12, 0), (1, 1, 12, 1), (1, 1, 16, 0), (1, 1, 16, 1), (1, 1, 20, 0),
+                                        (1, 1, 20, 1), (1, 1, 24, 0), (1, 1, 24, 1)):
             set_tuning("hydro_fused", fused)
+            set_tuning("hydro_tma", utma)
             set_tuning("hydro_tile", tile)
             set_tuning("hydro_rows", rows)
             for _ in range(2): s = run.oneStepIntegration(*s)
             run.profile_begin()
             for _ in range(5): s = run.oneStepIntegration(*s)
             tot, ph = run.profile_end()
-            print("rows=%2d hydro_fused=%d hydro_tile=%d total %.3f ms/step %.0f Mcell/s |" % (rows, fused, tile, tot / 5, N**3 * 5 / tot / 1e3), " ".join("%s %.3f" % (k, v[0] / 5) for k, v in ph.items() if v[0] > 0), flush=True)
+            print("rows=%2d tma=%d hydro_fused=%d hydro_tile=%d total %.3f ms/step %.0f Mcell/s |" % (rows, utma, fused, tile, tot / 5, N**3 * 5 / tot / 1e3), " ".join("%s %.3f" % (k, v[0] / 5) for k, v in ph.items() if v[0] > 0), flush=True)
