@@ -24,6 +24,7 @@ for tool in $TOOLS; do
   for ini in $CASES/*.ini; do
     name=$(basename "$ini" .ini)
     flag=""; case "$name" in *_f32) flag="--fp32";; esac
+    if [ -n "${ONLY:-}" ] && ! echo "$name" | grep -qE "$ONLY"; then continue; fi   # ONLY=<regex>: a subset of the cases
     # racecheck is slow: the kernels that synchronise without block barriers, and one case of the others
     if [ "$tool" = racecheck ]; then
       case "$name" in ot3d_16_s10|mri3d_16x32x16_s12|kh3d_16x8x16_f32_s10_f32|ot2d_32_s12|jet2d_hydro_24x32_s10) ;; *) continue;; esac
