@@ -333,6 +333,8 @@ def main():
                     help="headline as strong scaling: fixed global grid size x size x GLOBAL_NZ split into z slabs (default: weak, size^3 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-lines of configs 3 and 4 (`configs`)")
+    ap.add_argument("--halo", choices=["peer", "nccl"], default="peer",
+                    help="z halo at N > 1: copy engines over peer-mapped state arrays (default) or NCCL send/recv (A/B)")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-global-grid strong-scaling legs (`strong`)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-GPU == 1-GPU bitwise cases (`parity_multi`, N > 1)")
     ap.add_argument("--strong-grid", default="auto", help="auto | NXxNYxNZ of the strong-scaling legs (auto: 1024^3 when one GPU can hold it)")
@@ -368,6 +370,8 @@ def main():
     L = _lib.load()
     if L.rg_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    from ramsesgpu_b200 import set_tuning
+    set_tuning("halo_p2p", 0 if args.halo == "nccl" else 1)
     ctx = Ctx(rank, world, local_rank, torch, dist)
     peak, peak_src = measured_peaks()
     quiet = {"run": {"nstepmax": 1000000, "tend": 1.0e9, "noutput": -1},
@@ -471,6 +475,9 @@ def main():
             "config": {"workload": workload_name(n, nz_local, nz_total),
                        "parallelism": "z-slab x%d" % world, "cache": "inputs larger than L2 (state %.2f GB per GPU)" % (state_bytes / 1e9),
                        "chunk_planes": chunk_planes, "device_gb": device_gb,
+                       "halo": ("none (one GPU)" if world == 1 else
+                                "copy engines over peer-mapped state arrays + stream memory operations (no SM, no NCCL kernel)"
+                                if run.stats().halo_peer_copies else "NCCL send/recv"),
                        "timing": "%d back-to-back windows of exactly %d steps, each bracketed by barrier + synchronize, CUDA events, "
                                  "max over ranks; ms_per_step / value are the MEDIAN window" % (len(per_window), args.steps)},
             "windows_ms": per_window,

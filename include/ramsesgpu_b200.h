@@ -54,6 +54,7 @@ typedef struct rg_stats {
   double halo_bytes_per_step;         /* bytes this rank sends to its z-neighbours per ghost fill */
   size_t device_bytes;                /* device memory owned by the handle */
   int chunk_planes;                   /* z planes per chunk of the step pipeline */
+  int halo_peer_copies;               /* 1: the z halo travels by copy engines over peer-mapped memory; 0: NCCL send/recv (or one rank) */
 } rg_stats;
 
 const char* rg_last_error(void);

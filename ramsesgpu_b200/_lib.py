@@ -16,7 +16,8 @@ class RgLayout(C.Structure):
 
 class RgStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("last_step_ms", C.c_double),
-                ("halo_bytes_per_step", C.c_double), ("device_bytes", C.c_size_t), ("chunk_planes", C.c_int)]
+                ("halo_bytes_per_step", C.c_double), ("device_bytes", C.c_size_t), ("chunk_planes", C.c_int),
+                ("halo_peer_copies", C.c_int)]
 
 
 RG_FLAG_FP32 = 1

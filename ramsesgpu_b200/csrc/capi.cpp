@@ -216,6 +216,7 @@ int rg_get_stats(rg_handle h, rg_stats* out) {
     out->halo_bytes_per_step = s.haloBytesPerStep;
     out->device_bytes = s.deviceBytes;
     out->chunk_planes = s.chunkPlanes;
+    out->halo_peer_copies = s.haloPeerCopies;
   })
 }
 int rg_reset_launch_count(void) { rg::resetKernelLaunchCount(); return RG_OK; }

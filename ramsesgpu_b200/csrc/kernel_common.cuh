@@ -16,6 +16,7 @@ extern unsigned long long g_launches;  // kernels launched by this library
 extern int g_hydroTile;                // run-time knob "hydro_tile" (kernels_hydro3d.cu)
 extern int g_hydroFused;               // run-time knob "hydro_fused" (kernels_hydro3d_fused.cu)
 extern int g_hydroTma;                 // run-time knob "hydro_tma" (kernels_hydro3d_fused.cu)
+extern int g_haloP2p;                  // run-time knob "halo_p2p" (run.cu)
 extern int g_hydroRows;                // run-time knob "hydro_rows" (kernels_hydro3d_fused.cu)
 extern int g_tileX;                    // run-time knob "tile_x" (32 | 64 | 128); tile_y = BX / tile_x
 

@@ -998,6 +998,10 @@ bool setTuning(const char* key, int value) {
     g_fusedA = value ? 1 : 0;
     return true;
   }
+  if (k == "halo_p2p") {  // read when a multi-rank run is created
+    g_haloP2p = value ? 1 : 0;
+    return true;
+  }
   if (k == "hydro_tma") {
     g_hydroTma = value ? 1 : 0;
     return true;

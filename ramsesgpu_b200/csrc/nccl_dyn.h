@@ -10,7 +10,7 @@ namespace rg {
 struct NcclApi {
   typedef struct ncclComm* comm_t;
   struct UniqueId { char internal[128]; };
-  enum { kFloat32 = 7, kFloat64 = 8, kSum = 0, kMax = 2 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+  enum { kInt8 = 0, kFloat32 = 7, kFloat64 = 8, kSum = 0, kMax = 2 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
   int (*GetUniqueId)(UniqueId*) = nullptr;
   int (*CommInitRank)(comm_t*, int, UniqueId, int) = nullptr;
@@ -20,6 +20,7 @@ struct NcclApi {
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 
   // returns nullptr (and sets *err) when libnccl cannot be loaded

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <unistd.h>
 
 #include "init_conditions.h"
 #include "kernels.h"
@@ -51,6 +52,7 @@ const NcclApi* NcclApi::get(const char** err) {
       RG_SYM(GroupStart, "ncclGroupStart")
       RG_SYM(GroupEnd, "ncclGroupEnd")
       RG_SYM(AllReduce, "ncclAllReduce")
+      RG_SYM(AllGather, "ncclAllGather")
       RG_SYM(GetErrorString, "ncclGetErrorString")
 #undef RG_SYM
       ok = msg.empty();
@@ -62,6 +64,8 @@ const NcclApi* NcclApi::get(const char** err) {
   }
   return &api;
 }
+
+int g_haloP2p = 1;  // run-time knob "halo_p2p": z halo by copy engines over peer-mapped state arrays (default) or NCCL send/recv
 
 void slabExtent(int nzGlobal, int nranks, int rank, int* nzLocal, int* kOffset) {
   // contiguous slabs, the first (nz % nranks) ranks get one extra plane
@@ -123,11 +127,15 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMemcpy(dGz_, gz.data(), gz.size() * sizeof(T), cudaMemcpyHostToDevice));
       kp_.gzPlane = dGz_;
     }
-    if (nranks_ > 1) initComm(dist);
+    if (nranks_ > 1) {
+      initComm(dist);
+      initPeerHalo();
+    }
   }
 
   ~RunImpl() override {
     cudaDeviceSynchronize();
+    closePeerHalo();
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     freeScratch();
     for (int b = 0; b < 2; ++b) cudaFree(dU_[b]);
@@ -563,6 +571,7 @@ class RunImpl final : public Run {
         s.lastStepMs = ms;
     }
     s.haloBytesPerStep = haloBytesPerStep_;
+    s.haloPeerCopies = p2p_ ? 1 : 0;
     s.deviceBytes = deviceBytes_;
     s.chunkPlanes = chunkPlanes_;
     return s;
@@ -744,9 +753,194 @@ class RunImpl final : public Run {
     haloDone_[b] = true;
   }
 
+
+  // ---- z halo by copy engines over peer-mapped memory ----------------------------------------------
+  // Ranks of one node map each other's state arrays (CUDA IPC) and PUT their boundary planes straight into the
+  // neighbour's ghost planes with cudaMemcpyAsync (copy engines over NVLink: no SM, so the transfer runs while the
+  // persistent compute blocks own every SM -- NCCL's send/recv blocks wait for one to retire, profiles/r02_n_halo_overlap_notes.txt).
+  // Cross-process ordering without the host: 64-bit sequence flags in device memory, written into the neighbour's flag
+  // array by an 8-byte copy behind the data and awaited with a stream memory operation (cuStreamWaitValue64):
+  //   READY(s): "my ghost planes may be overwritten by exchange s" (everything that read them is earlier in my stream)
+  //   DATA(s) : "the planes of exchange s are in your ghost planes"
+  // Every rank calls the exchanges in the same order, so the exchange counter s agrees.  Falls back to NCCL send/recv when
+  // a rank is on another host, IPC or peer access is unavailable, or for arrays that are not the two state arrays.
+  struct PeerBlock {  // what a rank publishes through the all-gather
+    cudaIpcMemHandle_t state[2], flags;
+    unsigned long long host;
+    long long pid;
+    int ksize, want, pad[10];
+  };
+  static_assert(sizeof(PeerBlock) == 256, "peer block layout");
+  struct Peer {
+    T* U[2] = {nullptr, nullptr};
+    unsigned long long* flags = nullptr;
+    int ksize = 0;
+  };
+  enum { FL_DATA_FROM_LO = 0, FL_DATA_FROM_HI = 1, FL_READY_FROM_LO = 2, FL_READY_FROM_HI = 3, FL_SLOTS = 8, FL_NSLOT = 48 };
+  typedef int (*StreamMemOp)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+
+  static unsigned long long hostId() {
+    char name[256] = {0};
+    gethostname(name, sizeof name - 1);
+    unsigned long long h = 1469598103934665603ull;
+    for (const char* c = name; *c; ++c) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+    // the boot id tells two containers with the same host name apart
+    if (FILE* f = std::fopen("/proc/sys/kernel/random/boot_id", "r")) {
+      char b[64] = {0};
+      if (std::fgets(b, sizeof b, f))
+        for (const char* c = b; *c; ++c) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+      std::fclose(f);
+    }
+    return h;
+  }
+
+  void initPeerHalo() {
+    int want = g_haloP2p ? 1 : 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && fn) waitValue_ = (StreamMemOp)fn;
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && fn) writeValue_ = (StreamMemOp)fn;
+    if (!waitValue_ || !writeValue_) want = 0;
+    cudaGetLastError();
+    RG_CUDA(cudaMalloc(&dFlags_, (FL_SLOTS + FL_NSLOT) * sizeof(unsigned long long)));
+    RG_CUDA(cudaMemset(dFlags_, 0, (FL_SLOTS + FL_NSLOT) * sizeof(unsigned long long)));
+    if (want) {  // stream memory operations usable on this device / driver?
+      const unsigned long long a = (unsigned long long)(uintptr_t)(dFlags_ + FL_SLOTS);
+      if (writeValue_(stream_, a, 1ull, 0u) != 0 || waitValue_(stream_, a, 1ull, 0u) != 0 || cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        want = 0;
+      }
+    }
+    PeerBlock mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (cudaIpcGetMemHandle(&mine.state[0], dU_[0]) != cudaSuccess || cudaIpcGetMemHandle(&mine.state[1], dU_[1]) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.flags, dFlags_) != cudaSuccess) {
+      cudaGetLastError();
+      want = 0;
+    }
+    mine.host = hostId();
+    mine.pid = (long long)getpid();
+    mine.ksize = kp_.ksize;
+    mine.want = want;
+    // every rank learns every block (in-place all-gather), then opens its neighbours'
+    std::vector<PeerBlock> all(nranks_);
+    PeerBlock* dBlocks = nullptr;
+    RG_CUDA(cudaMalloc(&dBlocks, sizeof(PeerBlock) * nranks_));
+    RG_CUDA(cudaMemcpyAsync(dBlocks + rank_, &mine, sizeof mine, cudaMemcpyHostToDevice, stream_));
+    ncclCheck(nccl_->AllGather(dBlocks + rank_, dBlocks, sizeof(PeerBlock), NcclApi::kInt8, comm_, stream_), "allgather(peer handles)");
+    RG_CUDA(cudaMemcpyAsync(all.data(), dBlocks, sizeof(PeerBlock) * nranks_, cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    bool ok = want != 0;
+    for (int r = 0; r < nranks_ && ok; ++r) ok = all[r].want != 0 && all[r].host == mine.host && (r == rank_ || all[r].pid != mine.pid);
+    bool hasLo, hasHi;
+    zNeighbours(&hasLo, &hasHi);
+    const int lo = (rank_ + nranks_ - 1) % nranks_, hi = (rank_ + 1) % nranks_;
+    auto open = [&](int r, Peer* p) {
+      p->ksize = all[r].ksize;
+      const unsigned fl = cudaIpcMemLazyEnablePeerAccess;
+      if (cudaIpcOpenMemHandle((void**)&p->U[0], all[r].state[0], fl) != cudaSuccess ||
+          cudaIpcOpenMemHandle((void**)&p->U[1], all[r].state[1], fl) != cudaSuccess ||
+          cudaIpcOpenMemHandle((void**)&p->flags, all[r].flags, fl) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      return true;
+    };
+    if (ok && hasLo) { ok = open(lo, &peerLo_); peerLoOpened_ = true; }
+    if (ok && hasHi) {
+      if (hasLo && hi == lo) peerHi_ = peerLo_;  // two ranks, periodic: one neighbour on both sides (a handle opens once)
+      else { ok = open(hi, &peerHi_); peerHiOpened_ = true; }
+    }
+    // all or nothing: the exchange protocol of a rank must match its neighbours'
+    double* dFail = reinterpret_cast<double*>(dBlocks);
+    const double fail = ok ? 0.0 : 1.0;
+    double failAny = 1.0;
+    RG_CUDA(cudaMemcpyAsync(dFail, &fail, sizeof fail, cudaMemcpyHostToDevice, stream_));
+    ncclCheck(nccl_->AllReduce(dFail, dFail, 1, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_), "allreduce(peer halo)");
+    RG_CUDA(cudaMemcpyAsync(&failAny, dFail, sizeof failAny, cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    cudaFree(dBlocks);
+    p2p_ = failAny == 0.0;
+    p2pBase_[0] = dU_[0];
+    p2pBase_[1] = dU_[1];
+    if (!p2p_) closePeerMappings();
+  }
+
+  void closePeerMappings() {
+    auto close = [](Peer* p) {
+      for (int b = 0; b < 2; ++b) if (p->U[b]) cudaIpcCloseMemHandle(p->U[b]);
+      if (p->flags) cudaIpcCloseMemHandle(p->flags);
+      cudaGetLastError();
+    };
+    if (peerLoOpened_) close(&peerLo_);
+    if (peerHiOpened_) close(&peerHi_);
+    peerLo_ = Peer();
+    peerHi_ = Peer();
+    peerLoOpened_ = peerHiOpened_ = false;
+  }
+
+  // destruction with peer mappings is collective: no rank frees its arrays before every rank has unmapped them
+  void closePeerHalo() {
+    if (p2p_) {
+      closePeerMappings();
+      if (comm_ && nccl_ && dFlags_) {
+        double* d = reinterpret_cast<double*>(dFlags_);
+        if (nccl_->AllReduce(d, d, 1, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_) == 0) cudaStreamSynchronize(stream_);
+      }
+      p2p_ = false;
+    }
+    cudaFree(dFlags_);
+    dFlags_ = nullptr;
+  }
+
+  void memOp(StreamMemOp op, cudaStream_t st, const unsigned long long* addr, unsigned long long value, const char* what) {
+    const int rc = op(st, (unsigned long long)(uintptr_t)addr, value, 0u);  // wait: CU_STREAM_WAIT_VALUE_GEQ = 0
+    if (rc != 0) throw std::runtime_error(std::string("CUDA driver error ") + std::to_string(rc) + " in " + what);
+  }
+
+  // the gw boundary planes of variables [v0, v0+nv) of state array U to the z neighbours; false: not a peer-mapped array
+  bool peerExchange(T* U, int v0, int nv, bool hasLo, bool hasHi, cudaStream_t st) {
+    if (!p2p_) return false;
+    const int b = U == p2pBase_[0] ? 0 : (U == p2pBase_[1] ? 1 : -1);
+    if (b < 0) return false;
+    const unsigned long long s = ++haloSeq_;
+    const int gw = kp_.gw;
+    const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
+    auto signal = [&](unsigned long long* peerFlag) {
+      unsigned long long* slot = dFlags_ + FL_SLOTS + (signalCount_++ % FL_NSLOT);
+      memOp(writeValue_, st, slot, s, "cuStreamWriteValue64");
+      RG_CUDA(cudaMemcpyAsync(peerFlag, slot, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    };
+    // I am my lower neighbour's upper neighbour and the other way round
+    if (hasLo) signal(peerLo_.flags + FL_READY_FROM_HI);
+    if (hasHi) signal(peerHi_.flags + FL_READY_FROM_LO);
+    if (hasHi) {  // my top inner planes -> the low ghost planes of the rank above
+      memOp(waitValue_, st, dFlags_ + FL_READY_FROM_HI, s, "cuStreamWaitValue64");
+      const size_t compHi = plane * peerHi_.ksize;
+      for (int v = v0; v < v0 + nv; ++v)
+        RG_CUDA(cudaMemcpyAsync(peerHi_.U[b] + (size_t)v * compHi, U + (size_t)v * comp + (size_t)(kp_.ksize - 2 * gw) * plane,
+                                n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      signal(peerHi_.flags + FL_DATA_FROM_LO);
+    }
+    if (hasLo) {  // my bottom inner planes -> the high ghost planes of the rank below
+      memOp(waitValue_, st, dFlags_ + FL_READY_FROM_LO, s, "cuStreamWaitValue64");
+      const size_t compLo = plane * peerLo_.ksize;
+      for (int v = v0; v < v0 + nv; ++v)
+        RG_CUDA(cudaMemcpyAsync(peerLo_.U[b] + (size_t)v * compLo + (size_t)(peerLo_.ksize - gw) * plane,
+                                U + (size_t)v * comp + (size_t)gw * plane, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      signal(peerLo_.flags + FL_DATA_FROM_HI);
+    }
+    if (hasLo) memOp(waitValue_, st, dFlags_ + FL_DATA_FROM_LO, s, "cuStreamWaitValue64");
+    if (hasHi) memOp(waitValue_, st, dFlags_ + FL_DATA_FROM_HI, s, "cuStreamWaitValue64");
+    return true;
+  }
+
   void exchangeZ(T* U, bool hasLo, bool hasHi, cudaStream_t st) {
     const int gw = kp_.gw, lo = (rank_ + nranks_ - 1) % nranks_, hi = (rank_ + 1) % nranks_;
     const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
+    haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
+    if (peerExchange(U, 0, kp_.nvar, hasLo, hasHi, st)) return;
     const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
     ncclCheck(nccl_->GroupStart(), "group start");
     for (int v = 0; v < kp_.nvar; ++v) {
@@ -757,7 +951,6 @@ class RunImpl final : public Run {
       if (hasHi) ncclCheck(nccl_->Recv(base + (size_t)(kp_.ksize - gw) * plane, n, dtype, hi, comm_, st), "recv from above");
     }
     ncclCheck(nccl_->GroupEnd(), "group end");
-    haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
   }
 
   // B of the ghost planes next to INTERIOR slab interfaces only (no periodic wrap): used between the
@@ -768,6 +961,7 @@ class RunImpl final : public Run {
     const bool hasLo = rank_ > 0, hasHi = rank_ < nranks_ - 1;
     const int gw = kp_.gw, lo = rank_ - 1, hi = rank_ + 1;
     const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
+    if (peerExchange(U, IA, 3, hasLo, hasHi, st)) return;
     const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
     ncclCheck(nccl_->GroupStart(), "group start");
     for (int v = IA; v <= IC; ++v) {
@@ -1261,6 +1455,13 @@ class RunImpl final : public Run {
   const NcclApi* nccl_ = nullptr;
   NcclApi::comm_t comm_ = nullptr;
   double haloBytesPerStep_ = 0.0;
+  // copy-engine halo (initPeerHalo)
+  bool p2p_ = false, peerLoOpened_ = false, peerHiOpened_ = false;
+  Peer peerLo_, peerHi_;
+  T* p2pBase_[2] = {nullptr, nullptr};
+  unsigned long long* dFlags_ = nullptr;  // [0..4): flags written by the neighbours, [FL_SLOTS..): local sources of flag values
+  unsigned long long haloSeq_ = 0, signalCount_ = 0;
+  StreamMemOp waitValue_ = nullptr, writeValue_ = nullptr;
   std::string lastWarning_;
 };
 

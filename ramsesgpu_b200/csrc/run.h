@@ -27,6 +27,7 @@ struct Stats {
   double haloBytesPerStep;  // bytes sent to z-neighbours per step by this rank
   size_t deviceBytes;       // device memory owned by the handle
   int chunkPlanes;          // z planes per chunk of the step pipeline
+  int haloPeerCopies;       // 1: z halo by copy engines over peer-mapped memory, 0: NCCL send/recv
 };
 
 enum Phase { PH_BOUNDARY = 0, PH_PRIM, PH_TRACE, PH_FLUX, PH_EMF, PH_UPDATE, PH_DT, PH_COPY, PH_HALO, PH_FUSED, PH_DISS, PH_COUNT };

@@ -42,6 +42,7 @@ def slabs_match_single_gpu(torch, dist, Run, ini, nsteps, rank, world, local, fp
         U, dts = run_steps(run, nsteps)
         g, nzl = run.layout.ghost_width, run.layout.nz_local
         halo = run.stats().halo_bytes_per_step
+        peer = bool(run.stats().halo_peer_copies)
         lay = run.layout
         grid = (lay.nx, lay.ny, lay.nz)
     inner = torch.from_numpy(np.ascontiguousarray(U[:, g:g + nzl, g:-g, g:-g])).cuda()
@@ -66,4 +67,4 @@ def slabs_match_single_gpu(torch, dist, Run, ini, nsteps, rank, world, local, fp
     dist.broadcast(flag, 0)
     ok = bool(flag.item() == 1)
     return ok, {"grid": "%dx%dx%d" % grid, "steps": nsteps, "ranks": world, "identical": ok, "max_abs_diff": maxdiff,
-                "halo_bytes_per_step": halo, "overlap": bool(overlap)}
+                "halo_bytes_per_step": halo, "overlap": bool(overlap), "halo_peer_copies": peer}

@@ -27,6 +27,9 @@ def main():
     periodic_z = (sys.argv[3] == "periodic") if len(sys.argv) > 3 else True
     overlap = (sys.argv[4] != "nooverlap") if len(sys.argv) > 4 else True
     problem = sys.argv[5] if len(sys.argv) > 5 else "ot3d"
+    halo = sys.argv[6] if len(sys.argv) > 6 else "peer"   # "peer": copy engines over peer-mapped arrays (default), "nccl": send/recv
+    from ramsesgpu_b200 import set_tuning
+    set_tuning("halo_p2p", 0 if halo == "nccl" else 1)
     mesh = {} if periodic_z else {"boundary_zmin": 2, "boundary_zmax": 1}
     fp32 = False
     Run = MHDRunGodunov
@@ -50,8 +53,8 @@ def main():
     from ramsesgpu_b200.distcheck import slabs_match_single_gpu
     ok, info = slabs_match_single_gpu(torch, dist, Run, ini, nsteps, rank, world, local, fp32=fp32, overlap=overlap)
     if rank == 0:
-        print("dist check: problem=" + problem + " world=%d nz=%d steps=%d periodic_z=%s overlap=%s halo_bytes=%d identical=%s maxdiff=%.3e" %
-              (world, nz, nsteps, periodic_z, overlap, info["halo_bytes_per_step"], ok, info["max_abs_diff"]), flush=True)
+        print("dist check: problem=" + problem + " world=%d nz=%d steps=%d periodic_z=%s overlap=%s halo_bytes=%d peer_copies=%s identical=%s maxdiff=%.3e" %
+              (world, nz, nsteps, periodic_z, overlap, info["halo_bytes_per_step"], info["halo_peer_copies"], ok, info["max_abs_diff"]), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
