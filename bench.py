@@ -221,6 +221,8 @@ def measure_e2e(run, args, nstep, cells_all, barrier, max_over_ranks):
 class Ctx:
     """Process plumbing of one bench run: rank / world, barrier, max over ranks, NCCL unique ids."""
 
+    halo_overlap = True  # --no-halo-overlap: exchange after the whole update instead of early on the communication stream
+
     def __init__(self, rank, world, local_rank, torch=None, dist=None):
         self.rank, self.world, self.local, self.torch, self.dist = rank, world, local_rank, torch, dist
 
@@ -229,7 +231,10 @@ class Ctx:
         if self.world > 1:
             from ramsesgpu_b200.distcheck import broadcast_unique_id
             uid = broadcast_unique_id(self.torch, self.dist, self.rank)
-        return Run(ini, fp32=fp32, rank=self.rank, nranks=self.world, nccl_unique_id=uid, device=self.local)
+        run = Run(ini, fp32=fp32, rank=self.rank, nranks=self.world, nccl_unique_id=uid, device=self.local)
+        if self.world > 1 and not self.halo_overlap:
+            run.set_halo_overlap(False)
+        return run
 
     def barrier(self, run=None):
         if run is not None:
@@ -335,6 +340,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-lines of configs 3 and 4 (`configs`)")
     ap.add_argument("--halo", choices=["peer", "nccl"], default="peer",
                     help="z halo at N > 1: copy engines over peer-mapped state arrays (default) or NCCL send/recv (A/B)")
+    ap.add_argument("--no-halo-overlap", action="store_true",
+                    help="N > 1: one update launch and the halo after it, instead of boundary ranges first + early halo (A/B)")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-global-grid strong-scaling legs (`strong`)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-GPU == 1-GPU bitwise cases (`parity_multi`, N > 1)")
     ap.add_argument("--strong-grid", default="auto", help="auto | NXxNYxNZ of the strong-scaling legs (auto: 1024^3 when one GPU can hold it)")
@@ -373,6 +380,7 @@ def main():
     from ramsesgpu_b200 import set_tuning
     set_tuning("halo_p2p", 0 if args.halo == "nccl" else 1)
     ctx = Ctx(rank, world, local_rank, torch, dist)
+    ctx.halo_overlap = not args.no_halo_overlap
     peak, peak_src = measured_peaks()
     quiet = {"run": {"nstepmax": 1000000, "tend": 1.0e9, "noutput": -1},
              "output": {"outputVtk": "no", "outputXsm": "no", "outputHdf5": "no"}}
@@ -447,6 +455,7 @@ def main():
     if args.e2e_steps > 0:
         e2e_value, e2e_sync_value, njobs, pins = measure_e2e(run, args, nstep, cells_all, barrier, ctx.max_over_ranks)
     chunk_planes = run.stats().chunk_planes
+    halo_peer = bool(run.stats().halo_peer_copies)
     device_gb = run.stats().device_bytes / 1e9
     for p_ in pins:
         p_.free()
@@ -477,7 +486,7 @@ def main():
                        "chunk_planes": chunk_planes, "device_gb": device_gb,
                        "halo": ("none (one GPU)" if world == 1 else
                                 "copy engines over peer-mapped state arrays + stream memory operations (no SM, no NCCL kernel)"
-                                if run.stats().halo_peer_copies else "NCCL send/recv"),
+                                if halo_peer else "NCCL send/recv") + ("" if world == 1 or ctx.halo_overlap else ", not overlapped"),
                        "timing": "%d back-to-back windows of exactly %d steps, each bracketed by barrier + synchronize, CUDA events, "
                                  "max over ranks; ms_per_step / value are the MEDIAN window" % (len(per_window), args.steps)},
             "windows_ms": per_window,
