@@ -707,12 +707,28 @@ class RunImpl final : public Run {
 
   void fillGhosts(int b, int kLo, int kHi) {
     T* U = dU_[b];
-    if (haloDone_[b]) {  // the z halo of this buffer was exchanged early (overlapped with the step)
-      RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
+    const int gwz = kp_.gw, kTop = kp_.ksize - kp_.gw;
+    const bool early = haloDone_[b] && kLo == 0 && kHi == kp_.ksize && kTop - gwz > 2 * gwz;
+    if (early) {
+      // the z halo of this buffer is travelling (or has arrived) on the communication stream, which also filled the x/y
+      // ghosts of the gw planes next to each interface (startEarlyHalo).  The x/y fills act plane by plane: the planes in
+      // between go first and hide what is left of the transfer, the ghost planes follow after the wait
+      phase(PH_BOUNDARY, [&] {
+        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, 2 * gwz, kTop - gwz, stream_);
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 2 * gwz, kTop - gwz, stream_);
+      });
     }
+    if (haloDone_[b]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
     phase(PH_BOUNDARY, [&] {
-      MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
-      MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
+      if (early) {
+        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, 0, gwz, stream_);
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, gwz, stream_);
+        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kTop, kp_.ksize, stream_);
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kTop, kp_.ksize, stream_);
+      } else {
+        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
+        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
+      }
       if (rp_.dim == 3 && nranks_ == 1)
         fillZFaces(U, false, false);
       // jet inflow patch after the last direction (reference HydroRunBase.cpp:2290, :2310); with slabs below
@@ -864,7 +880,37 @@ class RunImpl final : public Run {
     p2p_ = failAny == 0.0;
     p2pBase_[0] = dU_[0];
     p2pBase_[1] = dU_[1];
-    if (!p2p_) closePeerMappings();
+    if (!p2p_) {
+      closePeerMappings();
+      return;
+    }
+    int dev = 0, pitch = 0;
+    RG_CUDA(cudaGetDevice(&dev));
+    if (cudaDeviceGetAttribute(&pitch, cudaDevAttrMaxPitch, dev) == cudaSuccess && pitch > 0) maxPitch_ = (size_t)pitch;
+    // can a stream memory operation write straight into the neighbour's flag array?  Probe slots 6 (written by the rank
+    // below) and 7 (by the rank above) and read them back through the mapping; otherwise flags travel by 8-byte copies.
+    // Every rank decides alike only if the answer is the same everywhere: agree through the communicator.
+    bool direct = true;
+    const unsigned long long magic = 0x5eedf1a9ull;
+    auto probe = [&](Peer& p, int slot) {
+      if (writeValue_(stream_, (unsigned long long)(uintptr_t)(p.flags + slot), magic, 0u) != 0) { direct = false; return; }
+      unsigned long long v = 0;
+      if (cudaStreamSynchronize(stream_) != cudaSuccess ||
+          cudaMemcpy(&v, p.flags + slot, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess || v != magic) direct = false;
+    };
+    if (hasHi) probe(peerHi_, 6);
+    if (hasLo && direct) probe(peerLo_, 7);
+    cudaGetLastError();
+    const double nd = direct ? 0.0 : 1.0;
+    double ndAny = 1.0;
+    double* dAgree = reinterpret_cast<double*>(dFlags_ + FL_SLOTS);
+    RG_CUDA(cudaMemcpyAsync(dAgree, &nd, sizeof nd, cudaMemcpyHostToDevice, stream_));
+    ncclCheck(nccl_->AllReduce(dAgree, dAgree, 1, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_), "allreduce(peer flags)");
+    RG_CUDA(cudaMemcpyAsync(&ndAny, dAgree, sizeof ndAny, cudaMemcpyDeviceToHost, stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    RG_CUDA(cudaMemsetAsync(dAgree, 0, sizeof(double), stream_));
+    RG_CUDA(cudaStreamSynchronize(stream_));
+    directFlags_ = ndAny == 0.0;
   }
 
   void closePeerMappings() {
@@ -908,9 +954,23 @@ class RunImpl final : public Run {
     const int gw = kp_.gw;
     const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
     auto signal = [&](unsigned long long* peerFlag) {
+      if (directFlags_) {  // one stream memory operation straight into the neighbour's flag
+        memOp(writeValue_, st, peerFlag, s, "cuStreamWriteValue64(peer)");
+        return;
+      }
       unsigned long long* slot = dFlags_ + FL_SLOTS + (signalCount_++ % FL_NSLOT);
       memOp(writeValue_, st, slot, s, "cuStreamWriteValue64");
       RG_CUDA(cudaMemcpyAsync(peerFlag, slot, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    };
+    // nv rows of gw planes, one row per variable: ONE strided copy per direction when the pitches allow it
+    auto put = [&](T* dst, size_t dstComp, const T* src) {
+      if (dstComp * sizeof(T) <= maxPitch_ && comp * sizeof(T) <= maxPitch_) {
+        RG_CUDA(cudaMemcpy2DAsync(dst, dstComp * sizeof(T), src, comp * sizeof(T), n * sizeof(T), (size_t)nv,
+                                  cudaMemcpyDeviceToDevice, st));
+      } else {
+        for (int v = 0; v < nv; ++v)
+          RG_CUDA(cudaMemcpyAsync(dst + (size_t)v * dstComp, src + (size_t)v * comp, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      }
     };
     // I am my lower neighbour's upper neighbour and the other way round
     if (hasLo) signal(peerLo_.flags + FL_READY_FROM_HI);
@@ -918,17 +978,13 @@ class RunImpl final : public Run {
     if (hasHi) {  // my top inner planes -> the low ghost planes of the rank above
       memOp(waitValue_, st, dFlags_ + FL_READY_FROM_HI, s, "cuStreamWaitValue64");
       const size_t compHi = plane * peerHi_.ksize;
-      for (int v = v0; v < v0 + nv; ++v)
-        RG_CUDA(cudaMemcpyAsync(peerHi_.U[b] + (size_t)v * compHi, U + (size_t)v * comp + (size_t)(kp_.ksize - 2 * gw) * plane,
-                                n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      put(peerHi_.U[b] + (size_t)v0 * compHi, compHi, U + (size_t)v0 * comp + (size_t)(kp_.ksize - 2 * gw) * plane);
       signal(peerHi_.flags + FL_DATA_FROM_LO);
     }
     if (hasLo) {  // my bottom inner planes -> the high ghost planes of the rank below
       memOp(waitValue_, st, dFlags_ + FL_READY_FROM_LO, s, "cuStreamWaitValue64");
       const size_t compLo = plane * peerLo_.ksize;
-      for (int v = v0; v < v0 + nv; ++v)
-        RG_CUDA(cudaMemcpyAsync(peerLo_.U[b] + (size_t)v * compLo + (size_t)(peerLo_.ksize - gw) * plane,
-                                U + (size_t)v * comp + (size_t)gw * plane, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      put(peerLo_.U[b] + (size_t)v0 * compLo + (size_t)(peerLo_.ksize - gw) * plane, compLo, U + (size_t)v0 * comp + (size_t)gw * plane);
       signal(peerLo_.flags + FL_DATA_FROM_HI);
     }
     if (hasLo) memOp(waitValue_, st, dFlags_ + FL_DATA_FROM_LO, s, "cuStreamWaitValue64");
@@ -1092,7 +1148,13 @@ class RunImpl final : public Run {
     // over the slab and only the update is cut into the three ranges (two launches and their pipeline fills less)
     const bool traceOnce = overlap && chunkPlanes_ >= kN + 1 - gw && sc_.fused && fusedRequested() &&
                            fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_);
-    if (traceOnce) {
+    if (overlap && p2p_) {
+      // copy-engine halo: it needs no SM, so nothing is gained by cutting the update into three launches -- the whole
+      // slab in one pass like on one GPU, then the halo of the NEW state on the communication stream, hidden behind
+      // the x/y ghost fill of the inner planes at the start of the next ghost fill (fillGhosts)
+      runRange(gw, kN + 1);
+      startEarlyHalo(dst);
+    } else if (traceOnce) {
       MhdScratch<T> sc = sc_;
       sc.kbase = gw - 2;
       phase(PH_TRACE, [&] { MhdKernels<T>::fusedTrace(kp_, Uold, sc, gw - 1, kN + 1, dt, stream_); });
@@ -1281,7 +1343,11 @@ class RunImpl final : public Run {
     const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative() && !stratZ;
     const bool traceOnce = overlap && chunkPlanes_ >= kN + 1 - gw && sc_.fused && fusedRequested() &&
                            fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_);
-    if (traceOnce) {  // as in stepMhd3d: one trace launch over the slab, the update in three ranges
+    if (overlap && p2p_) {  // as in stepMhd3d: copy-engine halo after ONE pass over the slab
+      runRange(gw, kN + 1);
+      if (shear) startEarlyHaloShear(dst, dt);
+      else startEarlyHalo(dst);
+    } else if (traceOnce) {  // as in stepMhd3d: one trace launch over the slab, the update in three ranges
       MhdScratch<T> sc = sc_;
       sc.kbase = gw - 2;
       phase(PH_TRACE, [&] { MhdKernels<T>::fusedTrace(kp_, Uold, sc, gw - 1, kN + 1, dt, stream_); });
@@ -1405,7 +1471,10 @@ class RunImpl final : public Run {
       }
     };
     const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative();
-    if (overlap) {
+    if (overlap && p2p_) {  // copy-engine halo after ONE pass over the slab (see stepMhd3d)
+      runRange(gw, kN);
+      startEarlyHalo(dst);
+    } else if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN);
       startEarlyHalo(dst);
@@ -1462,6 +1531,8 @@ class RunImpl final : public Run {
   unsigned long long* dFlags_ = nullptr;  // [0..4): flags written by the neighbours, [FL_SLOTS..): local sources of flag values
   unsigned long long haloSeq_ = 0, signalCount_ = 0;
   StreamMemOp waitValue_ = nullptr, writeValue_ = nullptr;
+  bool directFlags_ = false;    // flags written by cuStreamWriteValue64 straight into peer memory (probed at start-up)
+  size_t maxPitch_ = 0;         // cudaMemcpy2D pitch limit
   std::string lastWarning_;
 };
 
