@@ -707,28 +707,12 @@ class RunImpl final : public Run {
 
   void fillGhosts(int b, int kLo, int kHi) {
     T* U = dU_[b];
-    const int gwz = kp_.gw, kTop = kp_.ksize - kp_.gw;
-    const bool early = haloDone_[b] && kLo == 0 && kHi == kp_.ksize && kTop - gwz > 2 * gwz;
-    if (early) {
-      // the z halo of this buffer is travelling (or has arrived) on the communication stream, which also filled the x/y
-      // ghosts of the gw planes next to each interface (startEarlyHalo).  The x/y fills act plane by plane: the planes in
-      // between go first and hide what is left of the transfer, the ghost planes follow after the wait
-      phase(PH_BOUNDARY, [&] {
-        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, 2 * gwz, kTop - gwz, stream_);
-        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 2 * gwz, kTop - gwz, stream_);
-      });
+    if (haloDone_[b]) {  // the z halo of this buffer was exchanged on the communication stream
+      RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
     }
-    if (haloDone_[b]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
     phase(PH_BOUNDARY, [&] {
-      if (early) {
-        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, 0, gwz, stream_);
-        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, 0, gwz, stream_);
-        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kTop, kp_.ksize, stream_);
-        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kTop, kp_.ksize, stream_);
-      } else {
-        MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
-        MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
-      }
+      MhdKernels<T>::fillBoundary(kp_, U, 0, rp_.bc[0], rp_.bc[1], false, false, kLo, kHi, stream_);
+      MhdKernels<T>::fillBoundary(kp_, U, 1, rp_.bc[2], rp_.bc[3], false, false, kLo, kHi, stream_);
       if (rp_.dim == 3 && nranks_ == 1)
         fillZFaces(U, false, false);
       // jet inflow patch after the last direction (reference HydroRunBase.cpp:2290, :2310); with slabs below
@@ -750,9 +734,23 @@ class RunImpl final : public Run {
     phase(PH_HALO, [&] { exchangeZ(U, hasLo, hasHi, stream_); });
   }
 
-  // Early halo of the buffer being written by the current step: as soon as the gw inner planes next
-  // to each slab interface are final, fill their x/y ghosts and exchange them on the communication
-  // stream while the interior chunks are still being computed on the main stream.
+  // Copy-engine halo (p2p_): the transfer needs no SM, so the step makes ONE pass over the slab like on one GPU and the
+  // planes leave right after it on the communication stream, as they are: the x/y fills act plane by plane, so the
+  // receiver's ghost fill (x, y over all planes, ghost planes included, after the wait) gives them the x/y ghosts the
+  // sender would have.  The transfer hides behind the dt reduction and the host turn-around between two steps.
+  void startLateHalo(int b) {
+    bool hasLo, hasHi;
+    zNeighbours(&hasLo, &hasHi);
+    RG_CUDA(cudaEventRecord(evEdge_, stream_));
+    RG_CUDA(cudaStreamWaitEvent(comm_stream_, evEdge_, 0));
+    exchangeZ(dU_[b], hasLo, hasHi, comm_stream_);
+    RG_CUDA(cudaEventRecord(evHalo_, comm_stream_));
+    haloDone_[b] = true;
+  }
+
+  // NCCL halo (its send/recv blocks need SMs): early halo of the buffer being written by the current step -- as soon as
+  // the gw inner planes next to each slab interface are final, fill their x/y ghosts and exchange them on the
+  // communication stream while the interior chunks are still being computed on the main stream.
   void startEarlyHalo(int b) {
     T* U = dU_[b];
     const int gw = kp_.gw, kN = kp_.ksize - gw;
@@ -1150,10 +1148,9 @@ class RunImpl final : public Run {
                            fusedTraceRequested() && MhdKernels<T>::fusedTraceAvailable(kp_);
     if (overlap && p2p_) {
       // copy-engine halo: it needs no SM, so nothing is gained by cutting the update into three launches -- the whole
-      // slab in one pass like on one GPU, then the halo of the NEW state on the communication stream, hidden behind
-      // the x/y ghost fill of the inner planes at the start of the next ghost fill (fillGhosts)
+      // slab in one pass like on one GPU, then the halo of the NEW state on the communication stream (startLateHalo)
       runRange(gw, kN + 1);
-      startEarlyHalo(dst);
+      startLateHalo(dst);
     } else if (traceOnce) {
       MhdScratch<T> sc = sc_;
       sc.kbase = gw - 2;
@@ -1346,7 +1343,7 @@ class RunImpl final : public Run {
     if (overlap && p2p_) {  // as in stepMhd3d: copy-engine halo after ONE pass over the slab
       runRange(gw, kN + 1);
       if (shear) startEarlyHaloShear(dst, dt);
-      else startEarlyHalo(dst);
+      else startLateHalo(dst);
     } else if (traceOnce) {  // as in stepMhd3d: one trace launch over the slab, the update in three ranges
       MhdScratch<T> sc = sc_;
       sc.kbase = gw - 2;
@@ -1473,7 +1470,7 @@ class RunImpl final : public Run {
     const bool overlap = nranks_ > 1 && overlapHalo_ && (kN - gw) >= 3 * gw && !dissipative();
     if (overlap && p2p_) {  // copy-engine halo after ONE pass over the slab (see stepMhd3d)
       runRange(gw, kN);
-      startEarlyHalo(dst);
+      startLateHalo(dst);
     } else if (overlap) {
       runRange(gw, 2 * gw);
       runRange(kN - gw, kN);
