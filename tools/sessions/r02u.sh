@@ -24,8 +24,9 @@ except Exception as e: print("parse failed", e)
 PY
 }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-echo "== bench, peer copies (default), with the strong-scaling legs"
-timeout 900 $TR --master-port 29541 bench.py --gpus $N --steps 20 --warmup 3 > $O/r02u_bench${N}.json 2> $O/r02u_bench${N}.err
+echo "== bench, peer copies (default)"
+timeout 900 $TR --master-port 29541 bench.py --gpus $N --steps 20 --warmup 3 ${BENCH_FLAGS:---no-strong} > $O/r02u_bench${N}.json 2> $O/r02u_bench${N}.err
 tail -2 $O/r02u_bench${N}.err | cut -c1-300; show $O/r02u_bench${N}.json
+[ -n "${WITH_NCCL:-}" ] || exit 0
 echo "== bench, NCCL halo"
 timeout 600 $TR --master-port 29542 bench.py --gpus $N --steps 20 --warmup 3 --no-strong --no-parity --e2e-steps 0 --no-cpu-baseline --halo nccl > $O/r02u_bench${N}_nccl.json 2> $O/r02u_bench${N}_nccl.err; show $O/r02u_bench${N}_nccl.json
