@@ -275,7 +275,9 @@ class RunImpl final : public Run {
       dtCached_[b] = true;
     }
     if (nranks_ > 1) {  // slots hold bit patterns of non-negative doubles: a floating max is exact
-      if (haloDone_[0] || haloDone_[1]) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));  // one communicator: keep order
+      // an NCCL halo in flight on the communication stream shares the communicator: keep the order.  (A copy-engine halo
+      // does not: it keeps travelling behind this reduction and the host turn-around; the next ghost fill waits for it.)
+      if (haloOnNccl_ && (haloDone_[0] || haloDone_[1])) RG_CUDA(cudaStreamWaitEvent(stream_, evHalo_, 0));
       ncclCheck(nccl_->AllReduce(slots, slots, MAX_SLOTS, NcclApi::kFloat64, NcclApi::kMax, comm_, stream_),
                 "allreduce(dt)");
     }
@@ -994,7 +996,8 @@ class RunImpl final : public Run {
     const int gw = kp_.gw, lo = (rank_ + nranks_ - 1) % nranks_, hi = (rank_ + 1) % nranks_;
     const size_t plane = (size_t)kp_.isize * kp_.jsize, comp = plane * kp_.ksize, n = plane * gw;
     haloBytesPerStep_ = (double)((hasLo ? 1 : 0) + (hasHi ? 1 : 0)) * n * kp_.nvar * sizeof(T);
-    if (peerExchange(U, 0, kp_.nvar, hasLo, hasHi, st)) return;
+    haloOnNccl_ = !peerExchange(U, 0, kp_.nvar, hasLo, hasHi, st);
+    if (!haloOnNccl_) return;
     const int dtype = sizeof(T) == 8 ? NcclApi::kFloat64 : NcclApi::kFloat32;
     ncclCheck(nccl_->GroupStart(), "group start");
     for (int v = 0; v < kp_.nvar; ++v) {
@@ -1528,6 +1531,7 @@ class RunImpl final : public Run {
   unsigned long long* dFlags_ = nullptr;  // [0..4): flags written by the neighbours, [FL_SLOTS..): local sources of flag values
   unsigned long long haloSeq_ = 0, signalCount_ = 0;
   StreamMemOp waitValue_ = nullptr, writeValue_ = nullptr;
+  bool haloOnNccl_ = true;      // the last z halo went through NCCL send/recv (not through the copy engines)
   bool directFlags_ = false;    // flags written by cuStreamWriteValue64 straight into peer memory (probed at start-up)
   size_t maxPitch_ = 0;         // cudaMemcpy2D pitch limit
   std::string lastWarning_;
