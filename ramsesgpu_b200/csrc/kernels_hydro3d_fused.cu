@@ -176,16 +176,10 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const __grid_constant__ CUte
     zPrev = face_from_regs<T, 2>(P, w, T(1));
     T fxl[5] = {T(0), T(0), T(0), T(0), T(0)}, fxh[5], fyl[5] = {T(0), T(0), T(0), T(0), T(0)};
     T un[5] = {T(0), T(0), T(0), T(0), T(0)};
-    if (mid && upd) {  // old state of the cell: requested here, consumed after the two barriers below
-      if (TMAU) {
-        const T* t = uslot(p);
+    if (!TMAU && mid && upd) {  // old state of the cell: requested here, consumed after the two barriers below
+      const size_t idx = (size_t)p * plane + col;
 #pragma unroll
-        for (int v = 0; v < 5; ++v) un[v] = t[v * SV + sidx];
-      } else {
-        const size_t idx = (size_t)p * plane + col;
-#pragma unroll
-        for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
-      }
+      for (int v = 0; v < 5; ++v) un[v] = __ldg(Uold + v * comp + idx);
     }
     if (mid) {
       // x faces: left state from lane-1, high flux from lane+1
@@ -220,6 +214,11 @@ k_hydro_fused(const __grid_constant__ KParams<T> P, const __grid_constant__ CUte
     }
     __syncthreads();  // B: sF and the new sQ complete; every read of sY is done
     if (mid && upd) {
+      if (TMAU) {  // old state of the cell from the ring (the slot of plane p is refilled one iteration later)
+        const T* t = uslot(p);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) un[v] = t[v * SV + sidx];
+      }
 #pragma unroll
       for (int v = 0; v < 5; ++v) {  // summation order of the reference's serial scatter
         T s = un[v];
