@@ -310,7 +310,7 @@ void HydroKernels<T>::fusedStep(const KParams<T>& P, const T* Uold, T* Unew, int
                                 cudaStream_t s) {
   if (k1 <= k0) return;
   // measured at 512^3 FP32 HLLC / 384^3 FP64 (profiles/r02_p_hydro_tma_ab.txt), ms per launch by rows of the block:
-  //   TMA tiles        12: 7.40 / 5.66   16: 6.21 / 5.37   20: 5.68 / 7.09   24: 5.60 / 9.01
+  //   TMA tiles        12: 7.26 / 5.65   16: 6.13 / 5.24   20: 5.60 / 6.56   24: 5.44 / 8.74
   //   per-thread loads 12: 7.81 / 6.24   16: 6.50 / 6.50   20: 5.96 / 7.26   24: 6.01 / 8.64   (FP64: spills from 20 rows on)
   const bool tmaTiles = g_hydroTma && ((size_t)P.isize * sizeof(T)) % 16 == 0 && ((P.gw - 2) * sizeof(T)) % 16 == 0 &&
                         (reinterpret_cast<uintptr_t>(Uold) & 15) == 0;
