@@ -103,3 +103,41 @@ int main(void) {
     import torch
     if not torch.cuda.is_available():
         assert "rg_create -> 2" in text               # RG_ERR_NO_DEVICE, no CPU fallback
+
+
+def test_struct_layouts_match_the_header(native, tmp_path):
+    """rg_layout / rg_stats are filled by the library and read through ctypes mirrors: same size and the same field
+    offsets as the C compiler gives the header's structs (a field added on one side only would corrupt memory silently)"""
+    import shutil
+    import subprocess
+    from ramsesgpu_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    text = open(os.path.join(ROOT, "include", "ramsesgpu_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "ramsesgpu_b200.h"', 'int main(void) {']
+    mirrors = {"rg_layout": _lib.RgLayout, "rg_stats": _lib.RgStats}
+    for name in mirrors:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                first, *rest = decl.split(",")
+                fields += [first.split()[-1]] + [r.strip() for r in rest]
+        assert fields == [f[0] for f in mirrors[name]._fields_], name
+        prog.append('  printf("%s %%zu", sizeof(%s));' % (name, name))
+        prog += ['  printf(" %%zu", offsetof(%s, %s));' % (name, f) for f in fields]
+        prog.append('  printf("\\n");')
+    prog += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
+    for line in subprocess.run([str(exe)], stdout=subprocess.PIPE).stdout.decode().splitlines():
+        name, size, *offs = line.split()
+        m = mirrors[name]
+        assert int(size) == C.sizeof(m), name
+        assert [int(o) for o in offs] == [getattr(m, f[0]).offset for f in m._fields_], name
