@@ -2,7 +2,7 @@
 (slab extents from rg_slab_extent, local x/y ghost fill, z-halo exchange of gw planes with periodic
 wrap, dt = global max of the inverse dt) reproduces the mono-domain result BIT FOR BIT when every
 rank advances its slab with the oracle.  This is the host logic of run.cu::fillGhosts/exchangeZ/
-compute_dt, exercised without a GPU."""
+compute_dt, exercised without a GPU; one case follows the order of the copy-engine halo (startLateHalo)."""
 import os
 import socket
 
@@ -29,7 +29,7 @@ def _free_port():
 DISS = {"hydro": {"nu": 0.004}, "MHD": {"eta": 0.003}}
 
 
-def _worker(rank, world, port, out_dir, diss=False, refresh=True):
+def _worker(rank, world, port, out_dir, diss=False, refresh=True, late=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -52,6 +52,9 @@ def _worker(rank, world, port, out_dir, diss=False, refresh=True):
     def fill_ghosts(A):
         o.make_boundaries(pl, A, 1)
         o.make_boundaries(pl, A, 2)
+        exchange_z(A)
+
+    def exchange_z(A):
         top = torch.from_numpy(np.ascontiguousarray(A[:, nzl:nzl + gw]))      # my top inner planes
         bot = torch.from_numpy(np.ascontiguousarray(A[:, gw:2 * gw]))        # my bottom inner planes
         from_below, from_above = torch.empty_like(top), torch.empty_like(bot)
@@ -89,8 +92,14 @@ def _worker(rank, world, port, out_dir, diss=False, refresh=True):
         mn = torch.tensor([o.compute_dt(pl, a)], dtype=torch.float64)
         dist.all_reduce(mn, op=dist.ReduceOp.MIN)   # reference: allReduce(MIN) of dt, HydroRunBaseMpi.cpp:700
         dt = float(mn.item())
-        fill_ghosts(a)
+        if late:   # the z-ghost planes arrived raw at the end of the previous step: the x/y fill over ALL planes completes them
+            o.make_boundaries(pl, a, 1)
+            o.make_boundaries(pl, a, 2)
+        else:
+            fill_ghosts(a)
         o.step_no_boundaries(pl, a, b, dt)
+        if late:   # run.cu::startLateHalo (copy-engine halo): the boundary planes of the NEW state leave as they are
+            exchange_z(b)
         if diss:                                   # run.cu::stepMhd3d: ghost refresh, then the dissipative terms
             fill_ghosts(b)
             o.dissipative_stage(pl, b, dt, 0)
@@ -102,10 +111,10 @@ def _worker(rank, world, port, out_dir, diss=False, refresh=True):
     dist.destroy_process_group()
 
 
-def _run(tmp_path, oracle64, diss, refresh=True):
+def _run(tmp_path, oracle64, diss, refresh=True, late=False):
     world = 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path), diss, refresh), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), diss, refresh, late), nprocs=world, join=True)
     ini = ot3d_ini(N, OrszagTang={"kt": 1.0}, **(DISS if diss else {}))
     p = oracle64.params(ini)
     Uf, _, _ = oracle64.run_steps(p, oracle64.init_problem(p), NSTEPS)
@@ -116,6 +125,14 @@ def _run(tmp_path, oracle64, diss, refresh=True):
 
 def test_two_slabs_equal_mono_domain(tmp_path, oracle64):
     got, want = _run(tmp_path, oracle64, diss=False)
+    assert np.array_equal(got, want)
+
+
+def test_two_slabs_raw_planes_sent_after_the_step_equal_mono_domain(tmp_path, oracle64):
+    """the order of the copy-engine halo (run.cu::startLateHalo): the boundary planes of the new state are exchanged
+    right after the step WITHOUT their x/y ghosts; the receiver's x/y fill over all planes, ghost planes included, gives
+    them the same x/y ghosts the sender's fill would have (the fills act plane by plane)"""
+    got, want = _run(tmp_path, oracle64, diss=False, late=True)
     assert np.array_equal(got, want)
 
 
