@@ -144,6 +144,16 @@ if __name__ == "__main__":
         "khmhd2d_24x32_s8": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 24, "ny": 32}}, 8, "f64"),
         "khmhd3d_12x16x8_s5": ("mhd_kelvin_helmholtz_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8}, "MHD": {"implementationVersion": 4}}, 5, "f64"),
         "shearwave3d_16x12x8_s10": ("mhd_shearWave_3d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 8}}, 10, "f64"),
+        # SURVEY 8(f).4 -- further hydro test problems of the reference: Sod tube (Dirichlet walls), Gresho vortex
+        # (periodic, libm sin / cos / atan2 / log in the initial state), Lax-Liu 2D Riemann configurations (Neumann)
+        "sod2d_32x24_s8": ("hydro_sod2d.ini", {"mesh": {"nx": 32, "ny": 24}}, 8, "f64"),
+        "sod3d_16x12x10_s6": ("hydro_sod2d.ini", {"mesh": {"nx": 16, "ny": 12, "nz": 10}}, 6, "f64"),
+        "gresho2d_32_s8": ("Gresho_vortex2d.ini", {"mesh": {"nx": 32, "ny": 32}, "hydro": {"unsplitVersion": 1}}, 8, "f64"),
+        "gresho3d_16x16x8_s5": ("Gresho_vortex2d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 8}, "hydro": {"unsplitVersion": 1},
+                                                        "Gresho_vortex": {"v_bulk_z": 0.25}}, 5, "f64"),
+        "riemann2d_c2_32_s8": ("riemann2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 8, "f64"),
+        "riemann2d_c5_40x24_s6": ("riemann2d.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemann_config_number": 5},
+                                                    "riemann2d": {"x": 0.5, "y": 0.45}}, 6, "f64"),
     }
     for name, (ini, ov, steps, prec) in cases.items():
         if only and name not in only:

@@ -46,6 +46,9 @@ def _params_struct(real):
             ("djet", real), ("ujet", real), ("pjet", real), ("cjet", real), ("jet_bx", real), ("jet_by", real), ("jet_bz", real),
             ("gravityMode", C.c_int), ("mri_smoothGravity", C.c_int), ("mri_bcFloor", C.c_int), ("mri_zFloor", real),
             ("blast", real * 8),
+            ("gresho", real * 5),
+            ("riemann2d", real * 2),
+            ("riemannConfId", C.c_int),
         ]
     return OrcParams
 

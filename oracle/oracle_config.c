@@ -266,6 +266,14 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->blast[5] = get_float(&c, "blast", "density_out", 1.0f);
   p->blast[6] = get_float(&c, "blast", "pressure_in", 10.0f);
   p->blast[7] = get_float(&c, "blast", "pressure_out", 0.1f);
+  p->gresho[0] = get_float(&c, "Gresho_vortex", "center_x", (float)((p->xMax + p->xMin) / 2));
+  p->gresho[1] = get_float(&c, "Gresho_vortex", "center_y", (float)((p->yMax + p->yMin) / 2));
+  p->gresho[2] = get_float(&c, "Gresho_vortex", "v_bulk_x", 0.0f);
+  p->gresho[3] = get_float(&c, "Gresho_vortex", "v_bulk_y", 0.0f);
+  p->gresho[4] = get_float(&c, "Gresho_vortex", "v_bulk_z", 0.0f);
+  p->riemann2d[0] = get_float(&c, "riemann2d", "x", 0.5f);
+  p->riemann2d[1] = get_float(&c, "riemann2d", "y", 0.5f);
+  p->riemannConfId = (int)get_int(&c, "hydro", "riemann_config_number", 0);
   p->gravityMode = 0;
   if (p->gravityEnabled) {
     if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityMode = 1;

@@ -327,6 +327,126 @@ static int init_blast(const orc_params *P, real_t *U, const real_t par[8]) {
   return 0;
 }
 
+
+/* Sod shock tube along x (hydro 2D/3D), HydroRunBase.cpp:5358-5437 */
+static int init_sod(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  for (int k = (P->dim == 3 ? gw : 0); k < (P->dim == 3 ? ksz - gw : 1); ++k)
+    for (int j = gw; j < jsz - gw; ++j)
+      for (int i = gw; i < isz - gw; ++i) {
+        if (i < isz / 2) {
+          AT(U, i, j, k, ID) = 1.0f;
+          AT(U, i, j, k, IP) = 1.0f / (P->gamma0 - 1.0f);
+        } else {
+          AT(U, i, j, k, ID) = 0.125f;
+          AT(U, i, j, k, IP) = 0.1f / (P->gamma0 - 1.0f);
+        }
+      }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
+/* Gresho vortex (a vortex tube along z in 3D), HydroRunBase.cpp:5688-5838 */
+static int init_gresho_vortex(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  const real_t cx = P->gresho[0], cy = P->gresho[1], vbx = P->gresho[2], vby = P->gresho[3], vbz = P->gresho[4];
+  for (int k = (P->dim == 3 ? gw : 0); k < (P->dim == 3 ? ksz - gw : 1); ++k)
+    for (int j = gw; j < jsz - gw; ++j) {
+      real_t yPos = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+      for (int i = gw; i < isz - gw; ++i) {
+        real_t xPos = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+        real_t r = sqrt((xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy));
+        real_t phi = atan2(yPos - cy, xPos - cx);
+        real_t Pr, v_phi;
+        if (r < 0.2) {
+          Pr = 5 + 12.5 * r * r;
+          v_phi = 5 * r;
+        } else if (r < 0.4) {
+          Pr = 9 + 12.5 * r * r - 20 * r + 4 * log(5 * r);
+          v_phi = 2 - 5 * r;
+        } else {
+          Pr = 3 + 4 * log(2);
+          v_phi = 0.0f;
+        }
+        AT(U, i, j, k, ID) = 1.0f;
+        AT(U, i, j, k, IU) = -sin(phi) * v_phi + vbx;
+        AT(U, i, j, k, IV) = cos(phi) * v_phi + vby;
+        if (P->dim == 3) {
+          AT(U, i, j, k, IW) = vbz;
+          AT(U, i, j, k, IP) = Pr / (P->gamma0 - 1.0f) +
+              0.5 * (SQR(AT(U, i, j, k, IU)) + SQR(AT(U, i, j, k, IV)) + SQR(AT(U, i, j, k, IW))) / AT(U, i, j, k, ID);
+        } else {
+          AT(U, i, j, k, IP) = Pr / (P->gamma0 - 1.0f) +
+              0.5 * (SQR(AT(U, i, j, k, IU)) + SQR(AT(U, i, j, k, IV))) / AT(U, i, j, k, ID);
+        }
+      }
+    }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
+/* The 19 two-dimensional Riemann problems of Lax & Liu (SIAM J. Sci. Comput. 19, 1998), as tabulated by the reference
+ * (initHydro.cpp:25-420): primitive (rho, u, v, p) of quadrants 1 (upper right), 2 (upper left), 3 (lower left),
+ * 4 (lower right); single-precision literals like there. */
+static const float LAX_LIU[19][4][4] = {
+  {{1.0f, 0.0f, 0.0f, 1.0f}, {0.5197f, -0.7259f, 0.0f, 0.4f}, {0.1072f, -0.7259f, -1.4045f, 0.0439f}, {0.2579f, 0.0f, -1.4045f, 0.15f}},
+  {{1.0f, 0.0f, 0.0f, 1.0f}, {0.5197f, -0.7259f, 0.0f, 0.4f}, {1.0f, -0.7259f, -0.7259f, 1.0f}, {0.5197f, 0.0f, -0.7259f, 0.4f}},
+  {{1.5f, 0.0f, 0.0f, 1.5f}, {0.5323f, 1.206f, 0.0f, 0.3f}, {0.138f, 1.206f, 1.206f, 0.029f}, {0.5323f, 0.0f, 1.206f, 0.3f}},
+  {{1.1f, 0.0f, 0.0f, 1.1f}, {0.5065f, 0.8939f, 0.0f, 0.35f}, {1.1f, 0.8939f, 0.8939f, 1.1f}, {0.5065f, 0.0f, 0.8939f, 0.35f}},
+  {{1.0f, -0.75f, -0.5f, 1.0f}, {2.0f, -0.75f, 0.5f, 1.0f}, {1.0f, 0.75f, 0.5f, 1.0f}, {3.0f, 0.75f, -0.5f, 1.0f}},
+  {{1.0f, 0.75f, -0.5f, 1.0f}, {2.0f, 0.75f, 0.5f, 0.5f}, {1.0f, -0.75f, 0.5f, 1.0f}, {3.0f, -0.75f, -0.5f, 1.0f}},
+  {{1.0f, 0.1f, 0.1f, 1.0f}, {0.5197f, -0.6259f, 0.1f, 0.4f}, {0.8f, 0.1f, 0.1f, 0.4f}, {0.5197f, 0.1f, -0.6259f, 0.4f}},
+  {{0.5197f, 0.1f, 0.1f, 0.4f}, {1.0f, -0.6259f, 0.1f, 1.0f}, {0.8f, 0.1f, 0.1f, 1.0f}, {1.0f, 0.1f, -0.6259f, 1.0f}},
+  {{1.0f, 0.0f, 0.3f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.039f, 0.0f, -0.8133f, 0.4f}, {0.5197f, 0.0f, -0.4259f, 0.4f}},
+  {{1.0f, 0.0f, 0.4297f, 1.0f}, {0.5f, 0.0f, 0.6076f, 1.0f}, {0.2281f, 0.0f, -0.6076f, 0.3333f}, {0.4562f, 0.0f, -0.4259f, 0.3333f}},
+  {{1.0f, 0.1f, 0.0f, 1.0f}, {0.5313f, 0.8276f, 0.0f, 0.4f}, {0.8f, 0.1f, 0.0f, 0.4f}, {0.5313f, 0.1f, 0.7276f, 0.4f}},
+  {{0.5313f, 0.0f, 0.0f, 0.4f}, {1.0f, 0.7276f, 0.0f, 1.0f}, {0.8f, 0.0f, 0.0f, 1.0f}, {1.0f, 0.0f, 0.7276f, 1.0f}},
+  {{1.0f, 0.0f, -0.3f, 1.0f}, {2.0f, 0.0f, 0.3f, 1.0f}, {1.0625f, 0.0f, 0.8145f, 0.4f}, {0.5313f, 0.0f, 0.4276f, 0.4f}},
+  {{2.0f, 0.0f, -0.5606f, 8.0f}, {1.0f, 0.0f, -1.2172f, 8.0f}, {0.4736f, 0.0f, 1.2172f, 2.6667f}, {0.9474f, 0.0f, 1.1606f, 2.6667f}},
+  {{1.0f, 0.1f, -0.3f, 1.0f}, {0.5197f, -0.6259f, -0.3f, 0.4f}, {0.8f, 0.1f, -0.3f, 0.4f}, {0.5313f, 0.1f, 0.4276f, 0.4f}},
+  {{0.5313f, 0.1f, 0.1f, 0.4f}, {1.0222f, -0.6179f, 0.1f, 1.0f}, {0.8f, 0.1f, 0.1f, 1.0f}, {1.0f, 0.1f, 0.8276f, 1.0f}},
+  {{1.0f, 0.0f, -0.4f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, -1.1259f, 0.4f}},
+  {{1.0f, 0.0f, 1.0f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, 0.2741f, 0.4f}},
+  {{1.0f, 0.0f, 0.3f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, -0.4259f, 0.4f}},
+};
+
+/* four-quadrant 2D Riemann problem, HydroRunBase.cpp:6798-6910 (2D runs only, like the loops there) */
+static int init_riemann2d(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->dim != 2) {
+    fprintf(stderr, "oracle: riemann2d is a 2D problem\n");
+    return -1;
+  }
+  int nb = P->riemannConfId;
+  if (nb < 0) nb = 0;
+  else if (nb > 18) nb = 18;
+  const real_t xt = P->riemann2d[0], yt = P->riemann2d[1];
+  real_t q[4][4]; /* conservative (ID, IP, IU, IV) of the four quadrants, primToCons_2D (constoprim.h:221-234) */
+  for (int n = 0; n < 4; ++n) {
+    const real_t rho = LAX_LIU[nb][n][0], u = LAX_LIU[nb][n][1], v = LAX_LIU[nb][n][2], p = LAX_LIU[nb][n][3];
+    q[n][ID] = rho;
+    q[n][IU] = u * rho;
+    q[n][IV] = v * rho;
+    q[n][IP] = p / (P->gamma0 - 1.0f) + rho * (u * u + v * v) * 0.5f;
+  }
+  for (int j = gw; j < jsz - gw; ++j) {
+    real_t y = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+    for (int i = gw; i < isz - gw; ++i) {
+      real_t x = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+      const int n = (x < xt) ? ((y < yt) ? 2 : 1) : ((y < yt) ? 3 : 0);
+      AT(U, i, j, 0, ID) = q[n][ID];
+      AT(U, i, j, 0, IP) = q[n][IP];
+      AT(U, i, j, 0, IU) = q[n][IU];
+      AT(U, i, j, 0, IV) = q[n][IV];
+    }
+  }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
 /* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
 int orc_init_problem(const orc_params *P, real_t *U) {
   const char *n = P->problem;
@@ -341,6 +461,9 @@ int orc_init_problem(const orc_params *P, real_t *U) {
     if (!strcmp(n, "Rayleigh-Taylor")) return init_rayleigh_taylor(P, U);
     if (!strcmp(n, "implode")) { init_implode(P, U); return 0; }
     if (!strcmp(n, "Kelvin-Helmholtz")) return init_kelvin_helmholtz(P, U);
+    if (!strcmp(n, "sod")) return init_sod(P, U);
+    if (!strcmp(n, "Gresho-vortex")) return init_gresho_vortex(P, U);
+    if (!strcmp(n, "riemann2d")) return init_riemann2d(P, U);
   }
   fprintf(stderr, "oracle: problem '%s' not restated\n", n);
   return -1;

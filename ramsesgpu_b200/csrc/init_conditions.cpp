@@ -719,6 +719,122 @@ bool initBlast(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, 
   return true;
 }
 
+
+// Sod shock tube along x; reference HydroRunBase.cpp:5358-5437
+template <typename T>
+bool initSod(const ConfigMap&, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled) { if (msg) *msg = "sod is a hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  for (int k = (rp.dim == 3 ? gw : 0); k < (rp.dim == 3 ? kp.ksize - gw : 1); ++k)
+    for (int j = gw; j < kp.jsize - gw; ++j)
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        const bool left = i < kp.isize / 2;
+        g.at(ID, i, j, k) = left ? 1.0f : 0.125f;
+        g.at(IP, i, j, k) = (left ? 1.0f : 0.1f) / (kp.gamma0 - 1.0f);
+      }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
+// Gresho vortex (a vortex tube along z in 3D); reference HydroRunBase.cpp:5688-5838.  The radial profiles are
+// evaluated like there: real_t operands against double literals (libm sqrt / atan2 / log / sin / cos).
+template <typename T>
+bool initGreshoVortex(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled) { if (msg) *msg = "Gresho-vortex is a hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const T cx = cfg.getFloat("Gresho_vortex", "center_x", (float)((kp.xMax + kp.xMin) / 2));
+  const T cy = cfg.getFloat("Gresho_vortex", "center_y", (float)((kp.yMax + kp.yMin) / 2));
+  const T vbx = cfg.getFloat("Gresho_vortex", "v_bulk_x", 0.0f), vby = cfg.getFloat("Gresho_vortex", "v_bulk_y", 0.0f);
+  const T vbz = cfg.getFloat("Gresho_vortex", "v_bulk_z", 0.0f);
+  for (int k = (rp.dim == 3 ? gw : 0); k < (rp.dim == 3 ? kp.ksize - gw : 1); ++k)
+    for (int j = gw; j < kp.jsize - gw; ++j) {
+      const T yPos = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+      for (int i = gw; i < kp.isize - gw; ++i) {
+        const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+        const T r = std::sqrt((xPos - cx) * (xPos - cx) + (yPos - cy) * (yPos - cy));
+        const T phi = std::atan2(yPos - cy, xPos - cx);
+        T P, vphi;
+        if (r < 0.2) {
+          P = 5 + 12.5 * r * r;
+          vphi = 5 * r;
+        } else if (r < 0.4) {
+          P = 9 + 12.5 * r * r - 20 * r + 4 * std::log(5 * r);
+          vphi = 2 - 5 * r;
+        } else {
+          P = 3 + 4 * std::log(2.0);
+          vphi = T(0);
+        }
+        const T mu = -std::sin(phi) * vphi + vbx, mv = std::cos(phi) * vphi + vby;
+        g.at(ID, i, j, k) = 1.0f;
+        g.at(IU, i, j, k) = mu;
+        g.at(IV, i, j, k) = mv;
+        if (rp.dim == 3) {
+          g.at(IW, i, j, k) = vbz;
+          g.at(IP, i, j, k) = P / (kp.gamma0 - 1.0f) + 0.5 * (sqr(mu) + sqr(mv) + sqr(vbz)) / g.at(ID, i, j, k);
+        } else {
+          g.at(IP, i, j, k) = P / (kp.gamma0 - 1.0f) + 0.5 * (sqr(mu) + sqr(mv)) / g.at(ID, i, j, k);
+        }
+      }
+    }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
+// The 19 two-dimensional Riemann problems of Lax & Liu (SIAM J. Sci. Comput. 19, 1998) as the reference tabulates them
+// (initHydro.cpp:25-420): primitive (rho, u, v, p) of quadrants 1 (upper right), 2 (upper left), 3 (lower left),
+// 4 (lower right), single-precision literals.
+static const float kLaxLiu[19][4][4] = {
+    {{1.0f, 0.0f, 0.0f, 1.0f}, {0.5197f, -0.7259f, 0.0f, 0.4f}, {0.1072f, -0.7259f, -1.4045f, 0.0439f}, {0.2579f, 0.0f, -1.4045f, 0.15f}},
+    {{1.0f, 0.0f, 0.0f, 1.0f}, {0.5197f, -0.7259f, 0.0f, 0.4f}, {1.0f, -0.7259f, -0.7259f, 1.0f}, {0.5197f, 0.0f, -0.7259f, 0.4f}},
+    {{1.5f, 0.0f, 0.0f, 1.5f}, {0.5323f, 1.206f, 0.0f, 0.3f}, {0.138f, 1.206f, 1.206f, 0.029f}, {0.5323f, 0.0f, 1.206f, 0.3f}},
+    {{1.1f, 0.0f, 0.0f, 1.1f}, {0.5065f, 0.8939f, 0.0f, 0.35f}, {1.1f, 0.8939f, 0.8939f, 1.1f}, {0.5065f, 0.0f, 0.8939f, 0.35f}},
+    {{1.0f, -0.75f, -0.5f, 1.0f}, {2.0f, -0.75f, 0.5f, 1.0f}, {1.0f, 0.75f, 0.5f, 1.0f}, {3.0f, 0.75f, -0.5f, 1.0f}},
+    {{1.0f, 0.75f, -0.5f, 1.0f}, {2.0f, 0.75f, 0.5f, 0.5f}, {1.0f, -0.75f, 0.5f, 1.0f}, {3.0f, -0.75f, -0.5f, 1.0f}},
+    {{1.0f, 0.1f, 0.1f, 1.0f}, {0.5197f, -0.6259f, 0.1f, 0.4f}, {0.8f, 0.1f, 0.1f, 0.4f}, {0.5197f, 0.1f, -0.6259f, 0.4f}},
+    {{0.5197f, 0.1f, 0.1f, 0.4f}, {1.0f, -0.6259f, 0.1f, 1.0f}, {0.8f, 0.1f, 0.1f, 1.0f}, {1.0f, 0.1f, -0.6259f, 1.0f}},
+    {{1.0f, 0.0f, 0.3f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.039f, 0.0f, -0.8133f, 0.4f}, {0.5197f, 0.0f, -0.4259f, 0.4f}},
+    {{1.0f, 0.0f, 0.4297f, 1.0f}, {0.5f, 0.0f, 0.6076f, 1.0f}, {0.2281f, 0.0f, -0.6076f, 0.3333f}, {0.4562f, 0.0f, -0.4259f, 0.3333f}},
+    {{1.0f, 0.1f, 0.0f, 1.0f}, {0.5313f, 0.8276f, 0.0f, 0.4f}, {0.8f, 0.1f, 0.0f, 0.4f}, {0.5313f, 0.1f, 0.7276f, 0.4f}},
+    {{0.5313f, 0.0f, 0.0f, 0.4f}, {1.0f, 0.7276f, 0.0f, 1.0f}, {0.8f, 0.0f, 0.0f, 1.0f}, {1.0f, 0.0f, 0.7276f, 1.0f}},
+    {{1.0f, 0.0f, -0.3f, 1.0f}, {2.0f, 0.0f, 0.3f, 1.0f}, {1.0625f, 0.0f, 0.8145f, 0.4f}, {0.5313f, 0.0f, 0.4276f, 0.4f}},
+    {{2.0f, 0.0f, -0.5606f, 8.0f}, {1.0f, 0.0f, -1.2172f, 8.0f}, {0.4736f, 0.0f, 1.2172f, 2.6667f}, {0.9474f, 0.0f, 1.1606f, 2.6667f}},
+    {{1.0f, 0.1f, -0.3f, 1.0f}, {0.5197f, -0.6259f, -0.3f, 0.4f}, {0.8f, 0.1f, -0.3f, 0.4f}, {0.5313f, 0.1f, 0.4276f, 0.4f}},
+    {{0.5313f, 0.1f, 0.1f, 0.4f}, {1.0222f, -0.6179f, 0.1f, 1.0f}, {0.8f, 0.1f, 0.1f, 1.0f}, {1.0f, 0.1f, 0.8276f, 1.0f}},
+    {{1.0f, 0.0f, -0.4f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, -1.1259f, 0.4f}},
+    {{1.0f, 0.0f, 1.0f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, 0.2741f, 0.4f}},
+    {{1.0f, 0.0f, 0.3f, 1.0f}, {2.0f, 0.0f, -0.3f, 1.0f}, {1.0625f, 0.0f, 0.2145f, 0.4f}, {0.5197f, 0.0f, -0.4259f, 0.4f}},
+};
+
+// four-quadrant 2D Riemann problem; reference HydroRunBase.cpp:6798-6910 with primToCons_2D (constoprim.h:221-234)
+template <typename T>
+bool initRiemann2d(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled || rp.dim != 2) { if (msg) *msg = "riemann2d is a 2D hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const int nb = std::min(18, std::max(0, (int)cfg.getInteger("hydro", "riemann_config_number", 0)));
+  const T xt = cfg.getFloat("riemann2d", "x", 0.5f), yt = cfg.getFloat("riemann2d", "y", 0.5f);
+  T q[4][4];  // conservative (ID, IP, IU, IV) of the four quadrants
+  for (int n = 0; n < 4; ++n) {
+    const T rho = kLaxLiu[nb][n][0], u = kLaxLiu[nb][n][1], v = kLaxLiu[nb][n][2], p = kLaxLiu[nb][n][3];
+    q[n][ID] = rho;
+    q[n][IU] = u * rho;
+    q[n][IV] = v * rho;
+    q[n][IP] = p / (kp.gamma0 - 1.0f) + rho * (u * u + v * v) * 0.5f;
+  }
+  for (int j = gw; j < kp.jsize - gw; ++j) {
+    const T y = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+    for (int i = gw; i < kp.isize - gw; ++i) {
+      const T x = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+      const int n = (x < xt) ? ((y < yt) ? 2 : 1) : ((y < yt) ? 3 : 0);
+      for (int v = 0; v < 4; ++v) g.at(v, i, j, 0) = q[n][v];
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -745,6 +861,9 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Rayleigh-Taylor") return initRayleighTaylor(cfg, rp, kp, U, message);
     if (problem == "jet") return initJet(cfg, rp, kp, U, message);
     if (problem == "blast") return initBlast(cfg, rp, kp, U, message);
+    if (problem == "sod") return initSod(cfg, rp, kp, U, message);
+    if (problem == "Gresho-vortex") return initGreshoVortex(cfg, rp, kp, U, message);
+    if (problem == "riemann2d") return initRiemann2d(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

@@ -36,7 +36,7 @@ def test_initial_condition_matches_reference_bitwise(native, name):
 @pytest.mark.parametrize("name", ["fieldloop3d_16x12x10_s6", "rt3d_mhd_visc_rand_8x10x16_s5", "mri3d_12x20x8_s40",
                                   "kh3d_16x8x16_f32_s10", "implode3d_16_s8", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
                                   "currentsheet3d_16x16x8_s5", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10",
-                                  "blast3d_hllc_16x12x20_s8"])
+                                  "blast3d_hllc_16x12x20_s8", "sod3d_16x12x10_s6", "gresho3d_16x16x8_s5"])
 def test_initial_condition_is_slab_independent(native, name):
     """every slab generates its part of ONE global state: drand48 jump-ahead / rand() skip, global indices"""
     from ramsesgpu_b200 import initial_condition_host

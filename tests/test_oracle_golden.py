@@ -18,7 +18,10 @@ CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neu
          # boundaries in the rotating frame; slope_type 3 (27-point positivity-preserving slopes)
          "mri3d_strat_8x12x24_s10", "ot3d_slope3_16x12x20_s6",
          # ... and 2D hydro (godunov_unsplit_cpu_v1, TWO_D branch)
-         "implode2d_32_s10", "jet2d_hydro_24x32_s10", "blast2d_hllc_32_s8", "blast3d_hllc_16x12x20_s8"]
+         "implode2d_32_s10", "jet2d_hydro_24x32_s10", "blast2d_hllc_32_s8", "blast3d_hllc_16x12x20_s8",
+         # SURVEY 8(f).4, further hydro problems: Sod tube, Gresho vortex, Lax-Liu 2D Riemann configurations
+         "sod2d_32x24_s8", "sod3d_16x12x10_s6", "gresho2d_32_s8", "gresho3d_16x16x8_s5", "riemann2d_c2_32_s8",
+         "riemann2d_c5_40x24_s6"]
 
 
 @pytest.mark.parametrize("name", CASES)
