@@ -152,6 +152,13 @@ if __name__ == "__main__":
         "gresho3d_16x16x8_s5": ("Gresho_vortex2d.ini", {"mesh": {"nx": 16, "ny": 16, "nz": 8}, "hydro": {"unsplitVersion": 1},
                                                         "Gresho_vortex": {"v_bulk_z": 0.25}}, 5, "f64"),
         "riemann2d_c2_32_s8": ("riemann2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 8, "f64"),
+        # 2D Kelvin-Helmholtz (kelvin_helmholtz_cpu_2d.ini / _gpu_2d.ini): the four perturbation types of the 2D branch
+        "kh2d_rand_32_s8": ("kelvin_helmholtz_cpu_2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 8, "f64"),
+        "kh2d_robertson_32x40_s8": ("kelvin_helmholtz_gpu_2d.ini", {"mesh": {"nx": 32, "ny": 40}, "hydro": {"unsplitVersion": 1}}, 8, "f64"),
+        "kh2d_athena_40x32_s6": ("kelvin_helmholtz_cpu_2d.ini", {"mesh": {"nx": 40, "ny": 32, "ymin": -0.5, "ymax": 0.5},
+                                 "kelvin-helmholtz": {"perturbation_rand": "no", "perturbation_sine_athena": "yes"}}, 6, "f64"),
+        "kh2d_sine_32x48_s6": ("kelvin_helmholtz_cpu_2d.ini", {"mesh": {"nx": 32, "ny": 48}, "kelvin-helmholtz": {
+            "perturbation_rand": "no", "perturbation_sine": "yes", "inner_size": 0.1, "outer_size": 0.3}}, 6, "f64"),
         "riemann2d_c5_40x24_s6": ("riemann2d.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemann_config_number": 5},
                                                     "riemann2d": {"x": 0.5, "y": 0.45}}, 6, "f64"),
     }

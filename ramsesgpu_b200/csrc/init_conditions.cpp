@@ -279,15 +279,100 @@ bool initImplode(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
   return true;
 }
 
+// 2D Kelvin-Helmholtz (shear layers normal to y): random, Athena single-mode, Robertson et al. single-mode or plain
+// sine perturbation, in the reference's order of precedence; reference HydroRunBase.cpp:5857-5913 (parameters) and
+// :5915-6071 (2D branches).
+template <typename T>
+bool initKelvinHelmholtz2d(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
+                           std::string* msg) {
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const char* S = "kelvin-helmholtz";
+  std::srand((unsigned)cfg.getInteger(S, "seed", 1));
+  const T amplitude = cfg.getFloat(S, "amplitude", 0.01f);
+  const bool pRand = cfg.getBool(S, "perturbation_rand", true), pSine = cfg.getBool(S, "perturbation_sine", false);
+  const bool pAthena = cfg.getBool(S, "perturbation_sine_athena", false);
+  const bool pRobertson = cfg.getBool(S, "perturbation_sine_robertson", false);
+  const T rhoIn = cfg.getFloat(S, "rho_inner", 2.0f), rhoOut = cfg.getFloat(S, "rho_outer", 1.0f);
+  const T pressure = cfg.getFloat(S, "pressure", 2.5f);
+  const T innerSize = cfg.getFloat(S, "inner_size", 0.2f), outerSize = cfg.getFloat(S, "outer_size", 0.2f);
+  const T vIn = cfg.getFloat(S, "vflow_in", -0.5f), vOut = cfg.getFloat(S, "vflow_out", 0.5f);
+  const T xSize = kp.xMax - kp.xMin, ySize = kp.yMax - kp.yMin, yCenter = (kp.yMin + kp.yMax) * 0.5;
+  if (!pRand && !pAthena && !pRobertson && !pSine) {  // (the reference leaves a zero state)
+    if (msg) *msg = "Kelvin-Helmholtz: no perturbation type selected";
+    return false;
+  }
+  const int mode = (int)cfg.getInteger(S, "mode", 4);
+  const T w0 = cfg.getFloat(S, "w0", 0.1f), deltaY = cfg.getFloat(S, "deltaY", 0.03f);
+  const T y1 = kp.yMin + 0.25 * ySize, y2 = kp.yMin + 0.75 * ySize;
+  for (int j = gw; j < kp.jsize - gw; ++j) {
+    const T yPos = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+    const T ramp = 1.0 / (1.0 + std::exp(2 * (yPos - y1) / deltaY)) + 1.0 / (1.0 + std::exp(2 * (y2 - yPos) / deltaY));
+    for (int i = gw; i < kp.isize - gw; ++i) {
+      const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+      T& d = g.at(ID, i, j, 0);
+      T& mu = g.at(IU, i, j, 0);
+      T& mv = g.at(IV, i, j, 0);
+      if (pRand) {
+        const bool outer = std::fabs(yPos - yCenter) > outerSize * ySize;
+        const T rho = outer ? rhoOut : rhoIn, vf = outer ? vOut : vIn;
+        d = rho;
+        mu = rho * (vf + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5));
+        mv = rho * (0.0f + amplitude * (1.0 * std::rand() / RAND_MAX - 0.5));
+      } else if (pAthena) {
+        const T a = 0.05, sigma = 0.2, vflow = 0.5;
+        d = rhoIn;
+        mu = rhoIn * vflow * std::tanh(yPos / a);
+        mv = rhoIn * amplitude * std::sin(2.0 * M_PI * xPos) * std::exp(-(yPos * yPos) / (sigma * sigma));
+      } else if (pRobertson) {
+        d = rhoIn + ramp * (rhoOut - rhoIn);
+        mu = d * (vIn + ramp * (vOut - vIn));
+        mv = d * w0 * std::sin(mode * M_PI * xPos);
+      } else {
+        const T perturbVx = 0, perturbVy = amplitude * std::sin(2.0 * M_PI * xPos / xSize);
+        if (std::fabs(yPos - yCenter) > outerSize * ySize) {
+          d = rhoOut;
+          mu = rhoOut * vOut * (1.0 + perturbVx);
+          mv = rhoOut * perturbVy;
+        } else if (std::fabs(yPos - yCenter) <= innerSize * ySize) {
+          d = rhoIn;
+          mu = rhoIn * vIn * (1.0 + perturbVx);
+          mv = rhoIn * perturbVy;
+        } else {  // linear transition layer
+          const T interpSize = outerSize - innerSize;
+          const T rhoSlope = (rhoOut - rhoIn) / (interpSize * ySize), uSlope = (vOut - vIn) / (interpSize * ySize);
+          T dY, dRho, dU;
+          if (yPos > yCenter) {
+            dY = yPos - (yCenter + innerSize * ySize);
+            dRho = rhoSlope * dY;
+            dU = uSlope * dY;
+          } else {
+            dY = yPos - (yCenter - innerSize * ySize);
+            dRho = -rhoSlope * dY;
+            dU = -uSlope * dY;
+          }
+          d = rhoIn + dRho;
+          mu = d * (vIn + dU) * (1.0 + perturbVx);
+          mv = d * perturbVy;
+        }
+      }
+      g.at(IP, i, j, 0) = pressure / (kp.gamma0 - 1.0f) + 0.5 * (sqr(mu) + sqr(mv)) / d;
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 // 3D Kelvin-Helmholtz (shear layer normal to z), random or single-mode perturbation;
 // reference HydroRunBase.cpp:5857-5892 (parameters) and :6073-6175 (3D branches).
 template <typename T>
 bool initKelvinHelmholtz(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
                          std::string* msg) {
-  if (rp.mhdEnabled || rp.dim != 3) {
-    if (msg) *msg = "Kelvin-Helmholtz: only the 3D hydro variants are implemented";
+  if (rp.mhdEnabled) {
+    if (msg) *msg = "Kelvin-Helmholtz: this is the hydro variant";
     return false;
   }
+  if (rp.dim == 2) return initKelvinHelmholtz2d(cfg, rp, kp, U, msg);
   Grid<T> g(kp, U);
   const int gw = kp.gw;
   const char* S = "kelvin-helmholtz";
