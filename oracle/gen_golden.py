@@ -159,6 +159,11 @@ if __name__ == "__main__":
                                  "kelvin-helmholtz": {"perturbation_rand": "no", "perturbation_sine_athena": "yes"}}, 6, "f64"),
         "kh2d_sine_32x48_s6": ("kelvin_helmholtz_cpu_2d.ini", {"mesh": {"nx": 32, "ny": 48}, "kelvin-helmholtz": {
             "perturbation_rand": "no", "perturbation_sine": "yes", "inner_size": 0.1, "outer_size": 0.3}}, 6, "f64"),
+        # 2D hydro with static gravity: Rayleigh-Taylor (rayleigh_taylor_gpu_2d.ini), single mode and rand()
+        "rt2d_hydro_16x48_s10": ("rayleigh_taylor_gpu_2d.ini", {"mesh": {"nx": 16, "ny": 48}}, 10, "f64"),
+        "rt2d_hydro_rand_24x40_s8": ("rayleigh_taylor_gpu_2d.ini", {"mesh": {"nx": 24, "ny": 40}, "gravity": {"static_field_x": 0.02},
+                                     "rayleigh-taylor": {"randomEnabled": "yes", "random_seed": 5}, "hydro": {"riemannSolver": "hllc"}}, 8, "f64"),
+        "bubble2d_24x32_s10": ("falling_bubble_gpu_2d.ini", {"mesh": {"nx": 24, "ny": 32}, "falling-bubble": {"center_y": 0.7}}, 10, "f64"),
         "riemann2d_c5_40x24_s6": ("riemann2d.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemann_config_number": 5},
                                                     "riemann2d": {"x": 0.5, "y": 0.45}}, 6, "f64"),
     }

@@ -86,6 +86,7 @@ typedef struct orc_params {
   real_t gresho[5];    /* [Gresho_vortex] center_x/y, v_bulk_x/y/z (HydroRunBase.cpp:5706-5710) */
   real_t riemann2d[2]; /* [riemann2d] x, y: the transition point (HydroRunBase.cpp:6812-6813) */
   int riemannConfId;   /* [hydro] riemann_config_number (HydroRunBase.cpp:291) */
+  real_t bubble[7];    /* [falling-bubble] radius, center_x/y/z, v0, d0, d1 (HydroRunBase.cpp:6658-6668) */
 } orc_params;
 /* gravity field of cell plane k (reference h_gravity(i,j,k,0..2)) */
 void orc_gravity_at(const orc_params *p, int k, real_t g[3]);

@@ -49,6 +49,7 @@ def _params_struct(real):
             ("gresho", real * 5),
             ("riemann2d", real * 2),
             ("riemannConfId", C.c_int),
+            ("bubble", real * 7),
         ]
     return OrcParams
 

@@ -225,7 +225,7 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->gravityEnabled = get_bool(&c, "gravity", "static", 0) || get_bool(&c, "gravity", "self", 0);
   if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityEnabled = 1;
   p->gravity_x = p->gravity_y = p->gravity_z = 0;
-  if (!strcmp(p->problem, "Rayleigh-Taylor")) {
+  if (!strcmp(p->problem, "Rayleigh-Taylor") || !strcmp(p->problem, "falling-bubble")) {
     p->gravity_x = get_float(&c, "gravity", "static_field_x", 0.0f);
     p->gravity_y = get_float(&c, "gravity", "static_field_y", 0.0f);
     p->gravity_z = get_float(&c, "gravity", "static_field_z", 0.0f);
@@ -274,9 +274,16 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->riemann2d[0] = get_float(&c, "riemann2d", "x", 0.5f);
   p->riemann2d[1] = get_float(&c, "riemann2d", "y", 0.5f);
   p->riemannConfId = (int)get_int(&c, "hydro", "riemann_config_number", 0);
+  p->bubble[0] = get_float(&c, "falling-bubble", "radius", 0.1f);
+  p->bubble[1] = get_float(&c, "falling-bubble", "center_x", (float)((p->xMin + p->xMax) / 2));
+  p->bubble[2] = get_float(&c, "falling-bubble", "center_y", (float)(p->yMin + 0.8 * (p->yMax - p->yMin)));
+  p->bubble[3] = get_float(&c, "falling-bubble", "center_z", 0.0f);
+  p->bubble[4] = get_float(&c, "falling-bubble", "v0", 0.0f);
+  p->bubble[5] = get_float(&c, "falling-bubble", "d0", 2.0f);
+  p->bubble[6] = get_float(&c, "falling-bubble", "d1", 1.0f);
   p->gravityMode = 0;
   if (p->gravityEnabled) {
-    if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityMode = 1;
+    if (!strcmp(p->problem, "Rayleigh-Taylor") || !strcmp(p->problem, "falling-bubble")) p->gravityMode = 1;
     else if (p->mhdEnabled && (!strcmp(p->problem, "MRI") || !strcmp(p->problem, "Mri") || !strcmp(p->problem, "mri"))) p->gravityMode = 2;
   }
   return 0;

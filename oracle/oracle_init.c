@@ -241,13 +241,31 @@ static int init_kelvin_helmholtz(const orc_params *P, real_t *U) {
 static int init_rayleigh_taylor(const orc_params *P, real_t *U) {
   const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
   memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
-  if (P->dim != 3) {
-    fprintf(stderr, "oracle: Rayleigh-Taylor is restated in 3D only\n");
+  if (P->dim != 3 && P->mhdEnabled) {
+    fprintf(stderr, "oracle: Rayleigh-Taylor is restated in 3D (hydro, MHD) and 2D hydro only\n");
     return -1;
   }
   if (P->rt_random) srand(P->rt_seed);
   const real_t P0 = 1.0f / (P->gamma0 - 1.0f);
   const real_t Lx = P->xMax - P->xMin, Ly = P->yMax - P->yMin, Lz = P->zMax - P->zMin;
+  if (P->dim == 2) { /* HydroRunBase.cpp:6298-6330: heavy fluid above the mid-line in y, every cell incl. ghosts */
+    for (int j = 0; j < jsz; ++j) {
+      real_t y = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+      for (int i = 0; i < isz; ++i) {
+        real_t x = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+        real_t d = (y > (P->yMin + P->yMax) / 2) ? P->rt_d1 : P->rt_d0;
+        AT(U, i, j, 0, ID) = d;
+        AT(U, i, j, 0, IP) = P0 + d * (P->gravity_x * x + P->gravity_y * y);
+        AT(U, i, j, 0, IU) = 0.0f;
+        if (P->rt_random)
+          AT(U, i, j, 0, IV) = P->rt_amp * (rand() * 1.0 / RAND_MAX - 0.5);
+        else
+          AT(U, i, j, 0, IV) = P->rt_amp * (1 + cos(2 * M_PI * x / Lx)) * (1 + cos(2 * M_PI * y / Ly)) / 4;
+      }
+    }
+    fill_corners_gw2(P, U);
+    return 0;
+  }
   for (int k = 0; k < ksz; ++k) {
     real_t z = P->zMin + P->dz / 2 + (k - gw) * P->dz;
     for (int j = 0; j < jsz; ++j) {
@@ -447,6 +465,33 @@ static int init_riemann2d(const orc_params *P, real_t *U) {
   return 0;
 }
 
+/* falling bubble in a hydrostatic atmosphere (2D; the 3D branch of the reference indexes its 3D array with two
+ * indices, HydroRunBase.cpp:6737-6744, and is not restated), HydroRunBase.cpp:6633-6712: every cell incl. ghosts */
+static int init_falling_bubble(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->dim != 2) {
+    fprintf(stderr, "oracle: falling-bubble is restated in 2D only\n");
+    return -1;
+  }
+  const real_t P0 = 1.0f / (P->gamma0 - 1.0f), Ly = P->yMax - P->yMin;
+  const real_t radius = P->bubble[0], x_c = P->bubble[1], y_c = P->bubble[2], v0 = P->bubble[4], d0 = P->bubble[5], d1 = P->bubble[6];
+  for (int j = 0; j < jsz; ++j) {
+    real_t y = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+    for (int i = 0; i < isz; ++i) {
+      real_t x = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+      AT(U, i, j, 0, ID) = (y < P->yMin + 0.3 * Ly) ? d0 : d1;
+      real_t r2 = (x - x_c) * (x - x_c) + (y - y_c) * (y - y_c);
+      if (r2 < radius * radius) AT(U, i, j, 0, ID) = d0;
+      AT(U, i, j, 0, IP) = P0 + AT(U, i, j, 0, ID) * (P->gravity_x * x + P->gravity_y * y);
+      AT(U, i, j, 0, IU) = 0.0f;
+      AT(U, i, j, 0, IV) = (r2 < radius * radius) ? v0 : (real_t)0.0f;
+    }
+  }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
 /* MHDRunBase.cpp:1286-1342 (MHD) / HydroRunBase.cpp:7023-7100 (hydro) name dispatch */
 int orc_init_problem(const orc_params *P, real_t *U) {
   const char *n = P->problem;
@@ -464,6 +509,7 @@ int orc_init_problem(const orc_params *P, real_t *U) {
     if (!strcmp(n, "sod")) return init_sod(P, U);
     if (!strcmp(n, "Gresho-vortex")) return init_gresho_vortex(P, U);
     if (!strcmp(n, "riemann2d")) return init_riemann2d(P, U);
+    if (!strcmp(n, "falling-bubble")) return init_falling_bubble(P, U);
   }
   fprintf(stderr, "oracle: problem '%s' not restated\n", n);
   return -1;

@@ -424,8 +424,8 @@ bool initKelvinHelmholtz(const ConfigMap& cfg, const RunParams& rp, const KParam
 template <typename T>
 bool initRayleighTaylor(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U,
                         std::string* msg) {
-  if (rp.dim != 3) {
-    if (msg) *msg = "Rayleigh-Taylor: only the 3D variants are implemented";
+  if (rp.dim != 3 && rp.mhdEnabled) {
+    if (msg) *msg = "Rayleigh-Taylor: the 2D MHD variant is not implemented (3D hydro / MHD and 2D hydro are)";
     return false;
   }
   Grid<T> g(kp, U);
@@ -434,6 +434,26 @@ bool initRayleighTaylor(const ConfigMap& cfg, const RunParams& rp, const KParams
   const T amplitude = cfg.getFloat(S, "amplitude", 0.01f);
   const T d0 = cfg.getFloat(S, "d0", 1.0f), d1 = cfg.getFloat(S, "d1", 2.0f);
   const bool randomEnabled = cfg.getBool(S, "randomEnabled", false);
+  if (rp.dim == 2) {  // heavy fluid above the mid-line in y; every cell incl. ghosts (HydroRunBase.cpp:6298-6330)
+    if (randomEnabled) std::srand((unsigned)cfg.getInteger(S, "random_seed", 33));
+    const T P0 = 1.0f / (kp.gamma0 - 1.0f);
+    const T Lx = kp.xMax - kp.xMin, Ly = kp.yMax - kp.yMin;
+    for (int j = 0; j < kp.jsize; ++j) {
+      const T y = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+      for (int i = 0; i < kp.isize; ++i) {
+        const T x = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+        const T d = (y > (kp.yMin + kp.yMax) / 2) ? d1 : d0;
+        g.at(ID, i, j, 0) = d;
+        g.at(IP, i, j, 0) = P0 + d * (kp.gx * x + kp.gy * y);
+        if (randomEnabled)
+          g.at(IV, i, j, 0) = amplitude * (std::rand() * 1.0 / RAND_MAX - 0.5);
+        else
+          g.at(IV, i, j, 0) = amplitude * (1 + std::cos(2 * M_PI * x / Lx)) * (1 + std::cos(2 * M_PI * y / Ly)) / 4;
+      }
+    }
+    fillCornersGw2(rp, kp, g);
+    return true;
+  }
   if (randomEnabled) {
     std::srand((unsigned)cfg.getInteger(S, "random_seed", 33));
     // draws of the slabs below: the reference draws for every cell of the (global) array, ghosts included;
@@ -920,6 +940,37 @@ bool initRiemann2d(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& 
   return true;
 }
 
+// falling bubble in a hydrostatic atmosphere, 2D; reference HydroRunBase.cpp:6633-6712 (every cell incl. ghosts).  The
+// reference's 3D branch indexes its 3D array with two indices (:6737-6744) and is not reproduced.
+template <typename T>
+bool initFallingBubble(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled || rp.dim != 2) { if (msg) *msg = "falling-bubble is built as a 2D hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const char* S = "falling-bubble";
+  const T P0 = 1.0f / (kp.gamma0 - 1.0f), Ly = kp.yMax - kp.yMin;
+  const T radius = cfg.getFloat(S, "radius", 0.1f);
+  const T xc = cfg.getFloat(S, "center_x", (float)((kp.xMin + kp.xMax) / 2));
+  const T yc = cfg.getFloat(S, "center_y", (float)(kp.yMin + 0.8 * Ly));
+  const T v0 = cfg.getFloat(S, "v0", 0.0f), d0 = cfg.getFloat(S, "d0", 2.0f), d1 = cfg.getFloat(S, "d1", 1.0f);
+  // the pressure uses the configured field whether or not gravity is switched on ([gravity] static)
+  const T gx = cfg.getFloat("gravity", "static_field_x", 0.0f), gy = cfg.getFloat("gravity", "static_field_y", 0.0f);
+  for (int j = 0; j < kp.jsize; ++j) {
+    const T y = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+    for (int i = 0; i < kp.isize; ++i) {
+      const T x = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+      const T r2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
+      const bool in = r2 < radius * radius;
+      const T d = in ? d0 : ((y < kp.yMin + 0.3 * Ly) ? d0 : d1);
+      g.at(ID, i, j, 0) = d;
+      g.at(IP, i, j, 0) = P0 + d * (gx * x + gy * y);
+      g.at(IV, i, j, 0) = in ? v0 : T(0);
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -949,6 +1000,7 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "sod") return initSod(cfg, rp, kp, U, message);
     if (problem == "Gresho-vortex") return initGreshoVortex(cfg, rp, kp, U, message);
     if (problem == "riemann2d") return initRiemann2d(cfg, rp, kp, U, message);
+    if (problem == "falling-bubble") return initFallingBubble(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

@@ -1,6 +1,6 @@
 // 2D Euler (hydro) Godunov step for sm_100a, FP32 and FP64: what the reference's own regression harness runs
 // (test/test_run.sh.in:29-82 on test/makeConfigHydro.cpp:26-79, the 2D jet).
-//   trace      : U (5-point) -> cons->prim on the fly, TVD slopes, half-step predictor -> W (12 comps)
+//   trace      : U (5-point) -> cons->prim on the fly, TVD slopes, half-step predictor (+ static gravity) -> W (12 comps)
 //   fluxUpdate : per cell, the four face fluxes from W of the cell and its four neighbours (each face flux is
 //                evaluated by both adjacent cells with identical inputs and code, hence bitwise identical and
 //                conservative), conservative update, inverse dt of the new state; ghost cells keep the old values
@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(BX) k_hydro2d_trace(const __grid_constant__ KP
   const T su0 = (-u * dx_[IU] - dx_[IP] * ir) * dtdx + (-v * dy_[IU]) * dtdy;
   const T sv0 = (-u * dx_[IV]) * dtdx + (-v * dy_[IV] - dy_[IP] * ir) * dtdy;
   const T sp0 = (-u * dx_[IP] - dx_[IU] * g * p) * dtdx + (-v * dy_[IP] - dy_[IV] * g * p) * dtdy;
-  W(G_R, i, j) = r + sr0; W(G_P, i, j) = p + sp0; W(G_U, i, j) = u + su0; W(G_V, i, j) = v + sv0;
+  // static gravity: half-step predictor on the traced velocities (reference HydroRunGodunov.cpp:2485-2497 adds it to
+  // every face state; the face states are centre +/- slope, built by the flux kernel)
+  const T gpx = P.gravity ? T(0.5) * dt * P.gx : T(0), gpy = P.gravity ? T(0.5) * dt * P.gy : T(0);
+  W(G_R, i, j) = r + sr0; W(G_P, i, j) = p + sp0; W(G_U, i, j) = u + su0 + gpx; W(G_V, i, j) = v + sv0 + gpy;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     W(G_DX + c, i, j) = dx_[c];
@@ -126,6 +129,11 @@ __global__ void __launch_bounds__(BX) k_hydro2d_flux_update(const __grid_constan
         s += fxl[v] * dtdx; s += fyl[v] * dtdy;
         s -= fxh[v] * dtdx; s -= fyh[v] * dtdy;
         un[v] = s;
+      }
+      if (P.gravity) {  // static gravity source term, reference HydroRunBase.cpp:1946-1958
+        const T rs = __ldg(Uold + idx) + un[ID];
+        un[IU] += T(0.5) * dt * P.gx * rs;
+        un[IV] += T(0.5) * dt * P.gy * rs;
       }
       T q[5];
       const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], T(0), q);

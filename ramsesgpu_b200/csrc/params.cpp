@@ -115,6 +115,11 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
   k.gravity = (cfg.getBool("gravity", "static", false) || cfg.getBool("gravity", "self", false)) ? 1 : 0;
   k.gx = k.gy = k.gz = T(0);
   k.gzPlane = nullptr;
+  if (rp.problem == "falling-bubble" && k.gravity) {  // its set-up fills the gravity array too (HydroRunBase.cpp:6701-6706)
+    k.gx = cfg.getFloat("gravity", "static_field_x", 0.0f);
+    k.gy = cfg.getFloat("gravity", "static_field_y", 0.0f);
+    k.gz = cfg.getFloat("gravity", "static_field_z", 0.0f);
+  }
   if (rp.problem == "Rayleigh-Taylor") {
     k.gravity = 1;
     k.gx = cfg.getFloat("gravity", "static_field_x", 0.0f);

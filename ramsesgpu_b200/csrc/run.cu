@@ -302,8 +302,8 @@ class RunImpl final : public Run {
     const bool rotating = rp_.mhdEnabled && kp_.Omega0 > T(0);
     // the rotating-frame step fills the ghosts of UNew at its END (reference MHDRunGodunov.cpp:3429-3437)
     if (!rotating && !ghostsValid_[src]) make_all_boundaries(src);
-    if (kp_.gravity && rp_.dim != 3)
-      throw std::runtime_error("static gravity is available for the 3D solvers only");
+    if (kp_.gravity && rp_.dim != 3 && rp_.mhdEnabled)
+      throw std::runtime_error("static gravity is available for the 3D solvers and the 2D hydro solver only");
     if ((kp_.nu > T(0) || kp_.eta > T(0)) && rp_.dim != 3)
       throw std::runtime_error("viscosity / resistivity are available for the 3D solvers only");
     if (rotating && rp_.dim == 3) {
