@@ -163,6 +163,9 @@ if __name__ == "__main__":
         "rt2d_hydro_16x48_s10": ("rayleigh_taylor_gpu_2d.ini", {"mesh": {"nx": 16, "ny": 48}}, 10, "f64"),
         "rt2d_hydro_rand_24x40_s8": ("rayleigh_taylor_gpu_2d.ini", {"mesh": {"nx": 24, "ny": 40}, "gravity": {"static_field_x": 0.02},
                                      "rayleigh-taylor": {"randomEnabled": "yes", "random_seed": 5}, "hydro": {"riemannSolver": "hllc"}}, 8, "f64"),
+        # inertial wave in the rotating frame (periodic box, isothermal), 3D: mhd_inertialWave_2d.ini with nz > 1
+        "inertialwave3d_12x16x8_s12": ("mhd_inertialWave_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8},
+                                       "MHD": {"implementationVersion": 4, "omega0": 0.3}, "hydro": {"cIso": 0.05}}, 12, "f64"),
         "bubble2d_24x32_s10": ("falling_bubble_gpu_2d.ini", {"mesh": {"nx": 24, "ny": 32}, "falling-bubble": {"center_y": 0.7}}, 10, "f64"),
         "riemann2d_c5_40x24_s6": ("riemann2d.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemann_config_number": 5},
                                                     "riemann2d": {"x": 0.5, "y": 0.45}}, 6, "f64"),

@@ -940,6 +940,25 @@ bool initRiemann2d(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& 
   return true;
 }
 
+// inertial wave (test of the Omega0 terms): uniform state with an x velocity of delta_vx * cIso, every cell incl.
+// ghosts; reference MHDRunBase.cpp:2503-2556
+template <typename T>
+bool initInertialWave(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (!rp.mhdEnabled) { if (msg) *msg = "InertialWave is an MHD problem"; return false; }
+  Grid<T> g(kp, U);
+  const T density = cfg.getFloat("InertialWave", "density", 1.0f), energy = cfg.getFloat("InertialWave", "energy", 1.0f);
+  T deltaVx = cfg.getFloat("InertialWave", "delta_vx", 1.0f);
+  deltaVx *= kp.cIso;
+  for (int k = 0; k < kp.ksize; ++k)
+    for (int j = 0; j < kp.jsize; ++j)
+      for (int i = 0; i < kp.isize; ++i) {
+        g.at(ID, i, j, k) = density;
+        g.at(IP, i, j, k) = energy;
+        g.at(IU, i, j, k) = density * deltaVx;
+      }
+  return true;
+}
+
 // falling bubble in a hydrostatic atmosphere, 2D; reference HydroRunBase.cpp:6633-6712 (every cell incl. ghosts).  The
 // reference's 3D branch indexes its 3D array with two indices (:6737-6744) and is not reproduced.
 template <typename T>
@@ -989,6 +1008,9 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Rotor" || problem == "rotor") return initRotor(cfg, rp, kp, U, message);
     if (problem == "FieldLoop" || problem == "fieldloop" || problem == "Fieldloop" || problem == "field-loop" || problem == "Field-Loop")
       return initFieldLoop(cfg, rp, kp, U, message);
+    if (problem == "InertialWave" || problem == "inertialwave" || problem == "Inertial-Wave" || problem == "inertial-wave" ||
+        problem == "Inertialwave")
+      return initInertialWave(cfg, rp, kp, U, message);
     if (problem == "CurrentSheet" || problem == "currentsheet" || problem == "Current-Sheet" || problem == "current-sheet" || problem == "Currentsheet")
       return initCurrentSheet(cfg, rp, kp, U, message);
   } else {  // reference HydroRunBase.cpp:7023-7100

@@ -306,6 +306,8 @@ class RunImpl final : public Run {
       throw std::runtime_error("static gravity is available for the 3D solvers and the 2D hydro solver only");
     if ((kp_.nu > T(0) || kp_.eta > T(0)) && rp_.dim != 3)
       throw std::runtime_error("viscosity / resistivity are available for the 3D solvers only");
+    if (rotating && rp_.dim != 3)  // (the reference has a 2D rotating step, MHDRunGodunov.cpp:2089-2435: not built)
+      throw std::runtime_error("the rotating frame ([MHD] omega0 > 0) is available for the 3D MHD solver only");
     if (rotating && rp_.dim == 3) {
       stepMhd3dRotating(src, dst, static_cast<T>(dt));
     } else if (rp_.mhdEnabled && rp_.dim == 3) {

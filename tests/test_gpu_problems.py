@@ -14,6 +14,8 @@ CASES = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "b
          "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10",
          # jet inflow boundary patch + dt limit (hydro 3D, MHD 3D, MHD 2D)
          "jet3d_hydro_14x14x20_s8", "jet3d_mhd_15x15x20_s8", "jet2d_mhd_24x32_s10",
+         # inertial wave: rotating frame in a periodic box (no shearing-box borders), isothermal
+         "inertialwave3d_12x16x8_s12",
          # further hydro problems (2D kernels and the fused 3D hydro kernel): spherical blast, Sod tube (Dirichlet walls),
          # Gresho vortex (periodic), Lax-Liu 2D Riemann configurations 3 and 6 (Neumann)
          "blast3d_hllc_16x12x20_s8", "sod2d_32x24_s8", "sod3d_16x12x10_s6", "gresho2d_32_s8", "gresho3d_16x16x8_s5",
@@ -54,3 +56,17 @@ def test_golden_reference_run(native, name):
     if g["total_time"] == g["total_time"]:   # the hydro driver of the reference does not print these
         assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
         assert abs(dt - g["dt_last"]) < 1e-10 * g["dt_last"]
+
+
+def test_rotating_frame_in_2d_is_refused_not_ignored(native):
+    """[MHD] omega0 > 0 on a 2D grid (mhd_inertialWave_2d.ini as shipped): the reference has a 2D rotating step that is not
+    built here; the step must refuse instead of silently running the non-rotating 2D solver"""
+    from ramsesgpu_b200 import MHDRunGodunov
+    from ramsesgpu_b200._lib import RgError
+    from ramsesgpu_b200.io import ini_override
+    ini = ini_override(str(load_golden("inertialwave3d_12x16x8_s12")["ini"]), {"mesh": {"nz": 1}})
+    with MHDRunGodunov(ini) as run:
+        run.init_simulation()
+        assert run.layout.dim == 2
+        with pytest.raises(RgError, match="rotating frame"):
+            run.oneStepIntegration(0, 0.0, 0.0)

@@ -17,7 +17,8 @@ ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*
 NEW_PROBLEMS = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "briowu3d_xyz_12_s5",
                 "fieldloop2d_32x20_s8", "fieldloop3d_16x12x10_s6", "currentsheet2d_24_s8", "currentsheet3d_16x16x8_s5",
                 "khmhd2d_24x32_s8", "khmhd3d_12x16x8_s5", "shearwave3d_16x12x8_s10", "blast2d_hllc_32_s8",
-                "kh2d_rand_32_s8", "kh2d_robertson_32x40_s8", "kh2d_athena_40x32_s6", "kh2d_sine_32x48_s6"]
+                "kh2d_rand_32_s8", "kh2d_robertson_32x40_s8", "kh2d_athena_40x32_s6", "kh2d_sine_32x48_s6",
+                "inertialwave3d_12x16x8_s12"]
 # (the jet problems need the oracle's own boundary patch from step 0: they are in tests/test_oracle_golden.py)
 
 
