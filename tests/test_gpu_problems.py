@@ -52,6 +52,11 @@ def test_golden_reference_run(native, name):
         # isothermal runs (shear wave): the energy is carried along by the fluxes but never read (p = rho cIso^2);
         # it starts at 0 and is a sum of cancelling flux differences, measured 2e-12 against the reference
         tol = 1e-10 if (isothermal and v == 1) else TOL_F64
+        if isothermal and v == 1 and norm < 1e-12 * np.sqrt(np.sum(ref[0] ** 2)):
+            # (inertial wave: the unused energy stays at the round-off residue of cancelling fluxes, 1e-18 of the density:
+            # it has no digits to compare; bounded instead)
+            assert np.sqrt(np.sum(got[v] ** 2)) < 1e-12 * np.sqrt(np.sum(ref[0] ** 2)), (name, vname)
+            continue
         assert err < tol, (name, vname, err)
     if g["total_time"] == g["total_time"]:   # the hydro driver of the reference does not print these
         assert abs(t - g["total_time"]) < 1e-10 * g["total_time"]
