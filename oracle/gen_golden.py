@@ -166,6 +166,8 @@ if __name__ == "__main__":
         # inertial wave in the rotating frame (periodic box, isothermal), 3D: mhd_inertialWave_2d.ini with nz > 1
         "inertialwave3d_12x16x8_s12": ("mhd_inertialWave_2d.ini", {"mesh": {"nx": 12, "ny": 16, "nz": 8},
                                        "MHD": {"implementationVersion": 4, "omega0": 0.3}, "hydro": {"cIso": 0.05}}, 12, "f64"),
+        # 2D hydro with a gravity FIELD: Keplerian disc around a softened point mass (Keplerian_disk2d.ini)
+        "kepler2d_32_s10": ("Keplerian_disk2d.ini", {"mesh": {"nx": 32, "ny": 32}}, 10, "f64"),
         "bubble2d_24x32_s10": ("falling_bubble_gpu_2d.ini", {"mesh": {"nx": 24, "ny": 32}, "falling-bubble": {"center_y": 0.7}}, 10, "f64"),
         "riemann2d_c5_40x24_s6": ("riemann2d.ini", {"mesh": {"nx": 40, "ny": 24}, "hydro": {"riemann_config_number": 5},
                                                     "riemann2d": {"x": 0.5, "y": 0.45}}, 6, "f64"),

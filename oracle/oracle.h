@@ -87,9 +87,12 @@ typedef struct orc_params {
   real_t riemann2d[2]; /* [riemann2d] x, y: the transition point (HydroRunBase.cpp:6812-6813) */
   int riemannConfId;   /* [hydro] riemann_config_number (HydroRunBase.cpp:291) */
   real_t bubble[7];    /* [falling-bubble] radius, center_x/y/z, v0, d0, d1 (HydroRunBase.cpp:6658-6668) */
+  real_t kepler[5];    /* [Keplerian-disk] epsilon, pressure, xCenter, yCenter; [gravity] g (HydroRunBase.cpp:6465-6469) */
 } orc_params;
 /* gravity field of cell plane k (reference h_gravity(i,j,k,0..2)) */
 void orc_gravity_at(const orc_params *p, int k, real_t g[3]);
+/* ... of cell (i, j, k): the same, or the field of the 2D Keplerian disc (gravityMode 3, HydroRunBase.cpp:6488-6499) */
+void orc_gravity_cell(const orc_params *p, int i, int j, int k, real_t g[3]);
 
 /* parse ini TEXT with the reference's inih + ConfigMap semantics (float parse!) */
 int  orc_params_from_ini(const char *ini_text, orc_params *p);

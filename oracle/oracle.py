@@ -50,6 +50,7 @@ def _params_struct(real):
             ("riemann2d", real * 2),
             ("riemannConfId", C.c_int),
             ("bubble", real * 7),
+            ("kepler", real * 5),
         ]
     return OrcParams
 

@@ -223,7 +223,7 @@ int orc_params_from_ini(const char *text, orc_params *p) {
      Only init_hydro_Rayleigh_Taylor fills h_gravity with the static field (HydroRunBase.cpp:6400-6408);
      with any other problem the allocated array stays zero. */
   p->gravityEnabled = get_bool(&c, "gravity", "static", 0) || get_bool(&c, "gravity", "self", 0);
-  if (!strcmp(p->problem, "Rayleigh-Taylor")) p->gravityEnabled = 1;
+  if (!strcmp(p->problem, "Rayleigh-Taylor") || !strcmp(p->problem, "Keplerian-disk")) p->gravityEnabled = 1;
   p->gravity_x = p->gravity_y = p->gravity_z = 0;
   if (!strcmp(p->problem, "Rayleigh-Taylor") || !strcmp(p->problem, "falling-bubble")) {
     p->gravity_x = get_float(&c, "gravity", "static_field_x", 0.0f);
@@ -274,6 +274,11 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->riemann2d[0] = get_float(&c, "riemann2d", "x", 0.5f);
   p->riemann2d[1] = get_float(&c, "riemann2d", "y", 0.5f);
   p->riemannConfId = (int)get_int(&c, "hydro", "riemann_config_number", 0);
+  p->kepler[0] = get_float(&c, "Keplerian-disk", "epsilon", 0.01f);
+  p->kepler[1] = get_float(&c, "Keplerian-disk", "pressure", 1e-6f);
+  p->kepler[2] = get_float(&c, "Keplerian-disk", "xCenter", (float)((p->xMax + p->xMin) / 2.0));
+  p->kepler[3] = get_float(&c, "Keplerian-disk", "yCenter", (float)((p->yMax + p->yMin) / 2.0));
+  p->kepler[4] = get_float(&c, "gravity", "g", 1.0f);
   p->bubble[0] = get_float(&c, "falling-bubble", "radius", 0.1f);
   p->bubble[1] = get_float(&c, "falling-bubble", "center_x", (float)((p->xMin + p->xMax) / 2));
   p->bubble[2] = get_float(&c, "falling-bubble", "center_y", (float)(p->yMin + 0.8 * (p->yMax - p->yMin)));
@@ -284,6 +289,7 @@ int orc_params_from_ini(const char *text, orc_params *p) {
   p->gravityMode = 0;
   if (p->gravityEnabled) {
     if (!strcmp(p->problem, "Rayleigh-Taylor") || !strcmp(p->problem, "falling-bubble")) p->gravityMode = 1;
+    else if (!p->mhdEnabled && p->dim == 2 && !strcmp(p->problem, "Keplerian-disk")) p->gravityMode = 3;
     else if (p->mhdEnabled && (!strcmp(p->problem, "MRI") || !strcmp(p->problem, "Mri") || !strcmp(p->problem, "mri"))) p->gravityMode = 2;
   }
   return 0;

@@ -301,7 +301,7 @@ static void hydro2d_step_v1(const orc_params *P, const real_t *Uold, real_t *Une
       real_t sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v_ * dpy - dvy * gamma * p) * dtdy;
       r = r + sr0; u = u + su0; v_ = v_ + sv0; p = p + sp0;
       real_t gf[3];
-      orc_gravity_at(P, 0, gf);
+      orc_gravity_cell(P, i, j, 0, gf);
       for (int dd = 0; dd < 2; ++dd)
         for (int side = 0; side < 2; ++side) { /* side 0: qp (low face), 1: qm (high face) */
           real_t *dst = side ? qm_[dd] : qp_[dd];
@@ -333,9 +333,9 @@ static void hydro2d_step_v1(const orc_params *P, const real_t *Uold, real_t *Une
     }
   if (P->gravityEnabled) { /* HydroRunBase.cpp:1946-1958 */
     real_t gf[3];
-    orc_gravity_at(P, 0, gf);
     for (int j = gw; j < jsz - gw; ++j)
       for (int i = gw; i < isz - gw; ++i) {
+        orc_gravity_cell(P, i, j, 0, gf);
         real_t rhoOld = AT(Uold, i, j, 0, ID), rhoNew = AT(Unew, i, j, 0, ID);
         AT(Unew, i, j, 0, IU) += HALF * dt * gf[0] * (rhoOld + rhoNew);
         AT(Unew, i, j, 0, IV) += HALF * dt * gf[1] * (rhoOld + rhoNew);

@@ -465,6 +465,35 @@ static int init_riemann2d(const orc_params *P, real_t *U) {
   return 0;
 }
 
+/* Keplerian disc around a softened point mass, 2D (HydroRunBase.cpp:6445-6531), every cell incl. ghosts */
+static int init_keplerian_disk(const orc_params *P, real_t *U) {
+  const int isz = P->isize, jsz = P->jsize, ksz = P->ksize, gw = P->ghostWidth;
+  memset(U, 0, (size_t)orc_array_len(P) * sizeof(real_t));
+  if (P->dim != 2) {
+    fprintf(stderr, "oracle: Keplerian-disk is restated in 2D only\n");
+    return -1;
+  }
+  const real_t epsilon = P->kepler[0], P0 = P->kepler[1], xCenter = P->kepler[2], yCenter = P->kepler[3];
+  for (int j = 0; j < jsz; ++j) {
+    real_t yPos = P->yMin + P->dy / 2 + (j - gw) * P->dy;
+    for (int i = 0; i < isz; ++i) {
+      real_t xPos = P->xMin + P->dx / 2 + (i - gw) * P->dx;
+      real_t theta = atan2(yPos - yCenter, xPos - xCenter);
+      real_t r = sqrt((xPos - xCenter) * (xPos - xCenter) + (yPos - yCenter) * (yPos - yCenter));
+      real_t velocity = r * pow(r * r + epsilon * epsilon, -3.0 / 4.0);
+      if (r < 0.5) AT(U, i, j, 0, ID) = 0.01 + pow(r / 0.5, 3.0);
+      else if (r <= 2) AT(U, i, j, 0, ID) = 0.01 + 1;
+      else if (r > 2) AT(U, i, j, 0, ID) = 0.01 + pow(1 + (r - 2) / 0.1, -3.0);
+      AT(U, i, j, 0, IU) = -sin(theta) * velocity * AT(U, i, j, 0, ID);
+      AT(U, i, j, 0, IV) = cos(theta) * velocity * AT(U, i, j, 0, ID);
+      AT(U, i, j, 0, IP) = P0 / (P->gamma0 - (real_t)1) +
+          0.5 * (AT(U, i, j, 0, IU) * AT(U, i, j, 0, IU) + AT(U, i, j, 0, IV) * AT(U, i, j, 0, IV)) / AT(U, i, j, 0, ID);
+    }
+  }
+  fill_corners_gw2(P, U);
+  return 0;
+}
+
 /* falling bubble in a hydrostatic atmosphere (2D; the 3D branch of the reference indexes its 3D array with two
  * indices, HydroRunBase.cpp:6737-6744, and is not restated), HydroRunBase.cpp:6633-6712: every cell incl. ghosts */
 static int init_falling_bubble(const orc_params *P, real_t *U) {
@@ -510,6 +539,7 @@ int orc_init_problem(const orc_params *P, real_t *U) {
     if (!strcmp(n, "Gresho-vortex")) return init_gresho_vortex(P, U);
     if (!strcmp(n, "riemann2d")) return init_riemann2d(P, U);
     if (!strcmp(n, "falling-bubble")) return init_falling_bubble(P, U);
+    if (!strcmp(n, "Keplerian-disk")) return init_keplerian_disk(P, U);
   }
   fprintf(stderr, "oracle: problem '%s' not restated\n", n);
   return -1;

@@ -55,6 +55,24 @@ static void fill_face(const orc_params *P, real_t *U, int face, int bct) {
 /* reference h_gravity(i,j,k,:): uniform static field (HydroRunBase.cpp:6400-6408) or the vertical field of the
  * stratified shearing box, g_z = -(phi(z+dz) - phi(z-dz)) / (2 dz) with phi = Omega0^2 z^2 / 2, optionally
  * flattened above zFloor (MHDRunBase.cpp:3163-3211; phi is held in double) */
+void orc_gravity_cell(const orc_params *P, int i, int j, int k, real_t g[3]) {
+  if (P->gravityMode != 3) {
+    orc_gravity_at(P, k, g);
+    return;
+  }
+  /* 2D Keplerian disc: g = -grav grad(Phi), Phi = -(r^2 + eps^2)^(-1/2); x and y themselves multiply the power, not the
+     offsets to the centre (HydroRunBase.cpp:6488-6499) */
+  const real_t epsilon = P->kepler[0], xCenter = P->kepler[2], yCenter = P->kepler[3], grav = P->kepler[4];
+  real_t xPos = P->xMin + P->dx / 2 + (i - P->ghostWidth) * P->dx;
+  real_t yPos = P->yMin + P->dy / 2 + (j - P->ghostWidth) * P->dy;
+  real_t r = sqrt((xPos - xCenter) * (xPos - xCenter) + (yPos - yCenter) * (yPos - yCenter));
+  real_t dphi_dx = xPos * pow(r * r + epsilon * epsilon, -3.0 / 2);
+  real_t dphi_dy = yPos * pow(r * r + epsilon * epsilon, -3.0 / 2);
+  g[0] = -grav * dphi_dx;
+  g[1] = -grav * dphi_dy;
+  g[2] = 0;
+}
+
 void orc_gravity_at(const orc_params *P, int k, real_t g[3]) {
   g[0] = g[1] = g[2] = 0;
   if (P->gravityMode == 1) {

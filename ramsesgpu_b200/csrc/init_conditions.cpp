@@ -959,6 +959,38 @@ bool initInertialWave(const ConfigMap& cfg, const RunParams& rp, const KParams<T
   return true;
 }
 
+// Keplerian disc around a softened point mass, 2D; reference HydroRunBase.cpp:6445-6531 (every cell incl. ghosts; the
+// gravity field it also fills is keplerianGravityField, params.cpp).  libm atan2 / sqrt / pow / sin / cos.
+template <typename T>
+bool initKeplerianDisk(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& U, std::string* msg) {
+  if (rp.mhdEnabled || rp.dim != 2) { if (msg) *msg = "Keplerian-disk is built as a 2D hydro problem"; return false; }
+  Grid<T> g(kp, U);
+  const int gw = kp.gw;
+  const T epsilon = cfg.getFloat("Keplerian-disk", "epsilon", 0.01f), P0 = cfg.getFloat("Keplerian-disk", "pressure", 1e-6f);
+  const T xCenter = cfg.getFloat("Keplerian-disk", "xCenter", (float)((kp.xMax + kp.xMin) / 2.0));
+  const T yCenter = cfg.getFloat("Keplerian-disk", "yCenter", (float)((kp.yMax + kp.yMin) / 2.0));
+  for (int j = 0; j < kp.jsize; ++j) {
+    const T yPos = kp.yMin + kp.dy / 2 + (j - gw) * kp.dy;
+    for (int i = 0; i < kp.isize; ++i) {
+      const T xPos = kp.xMin + kp.dx / 2 + (i - gw) * kp.dx;
+      const T theta = std::atan2(yPos - yCenter, xPos - xCenter);
+      const T r = std::sqrt((xPos - xCenter) * (xPos - xCenter) + (yPos - yCenter) * (yPos - yCenter));
+      const T velocity = r * std::pow(r * r + epsilon * epsilon, -3.0 / 4.0);
+      T d = T(0);
+      if (r < 0.5) d = 0.01 + std::pow(r / 0.5, 3.0);
+      else if (r <= 2) d = 0.01 + 1;
+      else if (r > 2) d = 0.01 + std::pow(1 + (r - 2) / 0.1, -3.0);
+      const T mu = -std::sin(theta) * velocity * d, mv = std::cos(theta) * velocity * d;
+      g.at(ID, i, j, 0) = d;
+      g.at(IU, i, j, 0) = mu;
+      g.at(IV, i, j, 0) = mv;
+      g.at(IP, i, j, 0) = P0 / (kp.gamma0 - T(1)) + 0.5 * (mu * mu + mv * mv) / d;
+    }
+  }
+  fillCornersGw2(rp, kp, g);
+  return true;
+}
+
 // falling bubble in a hydrostatic atmosphere, 2D; reference HydroRunBase.cpp:6633-6712 (every cell incl. ghosts).  The
 // reference's 3D branch indexes its 3D array with two indices (:6737-6744) and is not reproduced.
 template <typename T>
@@ -1023,6 +1055,7 @@ bool initProblem(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp
     if (problem == "Gresho-vortex") return initGreshoVortex(cfg, rp, kp, U, message);
     if (problem == "riemann2d") return initRiemann2d(cfg, rp, kp, U, message);
     if (problem == "falling-bubble") return initFallingBubble(cfg, rp, kp, U, message);
+    if (problem == "Keplerian-disk") return initKeplerianDisk(cfg, rp, kp, U, message);
   }
   if (message) *message = "unknown problem name '" + problem + "' for this solver";
   return false;

@@ -66,7 +66,12 @@ __global__ void __launch_bounds__(BX) k_hydro2d_trace(const __grid_constant__ KP
   const T sp0 = (-u * dx_[IP] - dx_[IU] * g * p) * dtdx + (-v * dy_[IP] - dy_[IV] * g * p) * dtdy;
   // static gravity: half-step predictor on the traced velocities (reference HydroRunGodunov.cpp:2485-2497 adds it to
   // every face state; the face states are centre +/- slope, built by the flux kernel)
-  const T gpx = P.gravity ? T(0.5) * dt * P.gx : T(0), gpy = P.gravity ? T(0.5) * dt * P.gy : T(0);
+  T gpx = T(0), gpy = T(0);
+  if (P.gravity) {  // uniform field, or the field of the cell (Keplerian disc)
+    const int plane = P.isize * P.jsize, idx = j * P.isize + i;
+    gpx = T(0.5) * dt * (P.gCell ? __ldg(P.gCell + idx) : P.gx);
+    gpy = T(0.5) * dt * (P.gCell ? __ldg(P.gCell + plane + idx) : P.gy);
+  }
   W(G_R, i, j) = r + sr0; W(G_P, i, j) = p + sp0; W(G_U, i, j) = u + su0 + gpx; W(G_V, i, j) = v + sv0 + gpy;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(BX) k_hydro2d_flux_update(const __grid_constan
       }
       if (P.gravity) {  // static gravity source term, reference HydroRunBase.cpp:1946-1958
         const T rs = __ldg(Uold + idx) + un[ID];
-        un[IU] += T(0.5) * dt * P.gx * rs;
-        un[IV] += T(0.5) * dt * P.gy * rs;
+        un[IU] += T(0.5) * dt * (P.gCell ? __ldg(P.gCell + idx) : P.gx) * rs;
+        un[IV] += T(0.5) * dt * (P.gCell ? __ldg(P.gCell + plane + idx) : P.gy) * rs;
       }
       T q[5];
       const T c = dev::cons_to_prim_hydro(P, un[ID], un[IP], un[IU], un[IV], T(0), q);

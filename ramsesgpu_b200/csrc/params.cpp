@@ -115,6 +115,8 @@ KParams<T> makeKParams(const ConfigMap& cfg, const RunParams& rp, int nzLocal, i
   k.gravity = (cfg.getBool("gravity", "static", false) || cfg.getBool("gravity", "self", false)) ? 1 : 0;
   k.gx = k.gy = k.gz = T(0);
   k.gzPlane = nullptr;
+  k.gCell = nullptr;
+  if (rp.problem == "Keplerian-disk") k.gravity = 1;  // (HydroRunBase.cpp:258-260; the field itself: keplerianGravityField)
   if (rp.problem == "falling-bubble" && k.gravity) {  // its set-up fills the gravity array too (HydroRunBase.cpp:6701-6706)
     k.gx = cfg.getFloat("gravity", "static_field_x", 0.0f);
     k.gy = cfg.getFloat("gravity", "static_field_y", 0.0f);
@@ -156,6 +158,33 @@ bool stratifiedGravityPlanes(const ConfigMap& cfg, const RunParams& rp, const KP
   }
   return true;
 }
+// static gravity field of the Keplerian disc, g = -grav * grad(Phi) with the softened potential Phi = -(r^2 + eps^2)^(-1/2),
+// evaluated like the reference does (HydroRunBase.cpp:6488-6499: x and y themselves, not the offsets to the centre): 2D
+template <typename T>
+bool keplerianGravityField(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& g) {
+  if (rp.problem != "Keplerian-disk" || rp.mhdEnabled || rp.dim != 2) return false;
+  const T epsilon = cfg.getFloat("Keplerian-disk", "epsilon", 0.01f);
+  const T xCenter = cfg.getFloat("Keplerian-disk", "xCenter", (float)((kp.xMax + kp.xMin) / 2.0));
+  const T yCenter = cfg.getFloat("Keplerian-disk", "yCenter", (float)((kp.yMax + kp.yMin) / 2.0));
+  const T grav = cfg.getFloat("gravity", "g", 1.0f);
+  const size_t plane = (size_t)kp.isize * kp.jsize;
+  g.assign(2 * plane, T(0));
+  for (int j = 0; j < kp.jsize; ++j) {
+    const T yPos = kp.yMin + kp.dy / 2 + (j - kp.gw) * kp.dy;
+    for (int i = 0; i < kp.isize; ++i) {
+      const T xPos = kp.xMin + kp.dx / 2 + (i - kp.gw) * kp.dx;
+      const T r = std::sqrt((xPos - xCenter) * (xPos - xCenter) + (yPos - yCenter) * (yPos - yCenter));
+      const T dphi_dx = xPos * std::pow(r * r + epsilon * epsilon, -3.0 / 2);
+      const T dphi_dy = yPos * std::pow(r * r + epsilon * epsilon, -3.0 / 2);
+      g[(size_t)j * kp.isize + i] = -grav * dphi_dx;
+      g[plane + (size_t)j * kp.isize + i] = -grav * dphi_dy;
+    }
+  }
+  return true;
+}
+template bool keplerianGravityField<double>(const ConfigMap&, const RunParams&, const KParams<double>&, std::vector<double>&);
+template bool keplerianGravityField<float>(const ConfigMap&, const RunParams&, const KParams<float>&, std::vector<float>&);
+
 template bool stratifiedGravityPlanes<double>(const ConfigMap&, const RunParams&, const KParams<double>&, std::vector<double>&);
 template bool stratifiedGravityPlanes<float>(const ConfigMap&, const RunParams&, const KParams<float>&, std::vector<float>&);
 

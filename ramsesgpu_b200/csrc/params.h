@@ -44,6 +44,7 @@ struct KParams {
   // init_mhd_mri_grav_field, MHDRunBase.cpp:3163-3211): g_z of every LOCAL plane, a device array of ksize reals owned
   // by the run handle (null: the uniform field above)
   const T* gzPlane;
+  const T* gCell;  // 2D hydro: gravity field per cell, [2][jsize][isize] (Keplerian disc), or nullptr (uniform gx, gy)
   // jet inflow through a square patch of the lower ghost rows (2D: y) / planes (3D: z), problem "jet"
   // (reference HydroParameters.h:434-444, HydroRunBase.cpp:2374-2408)
   int jet, ijet, offsetJet;
@@ -77,6 +78,9 @@ RunParams parseRunParams(const ConfigMap& cfg);
 // false when the run has no such field (no gravity, or the uniform field of Rayleigh-Taylor).
 template <typename T>
 bool stratifiedGravityPlanes(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& gz);
+// per-cell gravity field of the 2D Keplerian disc ([2][jsize][isize]); false for every other run
+template <typename T>
+bool keplerianGravityField(const ConfigMap& cfg, const RunParams& rp, const KParams<T>& kp, std::vector<T>& g);
 
 // Fills the kernel parameter block in precision T (derived quantities are computed IN T, like the
 // reference build for that precision).  nzLocal/kglob0 describe this rank's z-slab.

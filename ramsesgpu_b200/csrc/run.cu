@@ -127,6 +127,12 @@ class RunImpl final : public Run {
       RG_CUDA(cudaMemcpy(dGz_, gz.data(), gz.size() * sizeof(T), cudaMemcpyHostToDevice));
       kp_.gzPlane = dGz_;
     }
+    std::vector<T> gc;
+    if (keplerianGravityField<T>(cfg_, rp_, kp_, gc)) {
+      RG_CUDA(cudaMalloc(&dGcell_, gc.size() * sizeof(T)));
+      RG_CUDA(cudaMemcpy(dGcell_, gc.data(), gc.size() * sizeof(T), cudaMemcpyHostToDevice));
+      kp_.gCell = dGcell_;
+    }
     if (nranks_ > 1) {
       initComm(dist);
       initPeerHalo();
@@ -142,6 +148,7 @@ class RunImpl final : public Run {
     cudaFree(dDiss_);
     cudaFree(dHist_);
     cudaFree(dGz_);
+    cudaFree(dGcell_);
     for (int b = 0; b < 2; ++b) {
       if (batchBuf_[b]) cudaFree(batchBuf_[b]);
       if (evH2D_[b]) cudaEventDestroy(evH2D_[b]);
@@ -1508,6 +1515,7 @@ class RunImpl final : public Run {
   double* dHist_ = nullptr;  // partial sums of the history kernels
   std::vector<double> hHist_;
   T* dGz_ = nullptr;    // g_z per local plane (stratified shearing box)
+  T* dGcell_ = nullptr; // (g_x, g_y) per cell of a 2D hydro run (Keplerian disc)
   T* dDiss_ = nullptr;  // 12-component scratch of the dissipative kernels (allocated on first use)
   int chunkPlanes_ = 0, userChunk_ = 0;
   unsigned long long* dMax_ = nullptr;

@@ -23,7 +23,9 @@ CASES = ["briowu2d_32x24_s8", "briowu2d_diag_24_s6", "briowu3d_z_10x8x16_s5", "b
          # 2D Kelvin-Helmholtz, the four perturbation types of the reference's 2D branch
          "kh2d_rand_32_s8", "kh2d_robertson_32x40_s8", "kh2d_athena_40x32_s6", "kh2d_sine_32x48_s6",
          # 2D hydro with static gravity: Rayleigh-Taylor, single mode and rand() perturbation
-         "rt2d_hydro_16x48_s10", "rt2d_hydro_rand_24x40_s8", "bubble2d_24x32_s10"]
+         "rt2d_hydro_16x48_s10", "rt2d_hydro_rand_24x40_s8", "bubble2d_24x32_s10",
+         # ... and a gravity FIELD (one vector per cell): Keplerian disc around a softened point mass
+         "kepler2d_32_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)

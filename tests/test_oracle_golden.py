@@ -23,7 +23,7 @@ CASES = ["ot3d_16_s10", "ot3d_24x16x20_s6", "ot3d_kt1_16x20x24_s8", "ot3d_16_neu
          "sod2d_32x24_s8", "sod3d_16x12x10_s6", "gresho2d_32_s8", "gresho3d_16x16x8_s5", "riemann2d_c2_32_s8",
          "riemann2d_c5_40x24_s6",
          # 2D hydro with static gravity (Rayleigh-Taylor, rayleigh_taylor_gpu_2d.ini)
-         "rt2d_hydro_16x48_s10", "rt2d_hydro_rand_24x40_s8", "bubble2d_24x32_s10"]
+         "rt2d_hydro_16x48_s10", "rt2d_hydro_rand_24x40_s8", "bubble2d_24x32_s10", "kepler2d_32_s10"]
 
 
 @pytest.mark.parametrize("name", CASES)
