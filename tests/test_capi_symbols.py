@@ -141,3 +141,15 @@ def test_struct_layouts_match_the_header(native, tmp_path):
         m = mirrors[name]
         assert int(size) == C.sizeof(m), name
         assert [int(o) for o in offs] == [getattr(m, f[0]).offset for f in m._fields_], name
+
+
+def test_sanitizer_cases_are_written(tmp_path):
+    """tools/sanitize_cases.py (parameter files of the compute-sanitizer pass) still finds its fixtures"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_cases.py"), str(tmp_path)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".ini"))
+    assert len(files) >= 13 and any(f.endswith("_f32.ini") for f in files)
+    assert "nstepmax=3" in open(tmp_path / "ot3d_16_s10.ini").read()

@@ -25,6 +25,9 @@ CASES = {
     "ot2d_32_s12": (3, None),                                        # 2D MHD
     "jet2d_hydro_24x32_s10": (3, None),                              # 2D hydro
     "jet3d_mhd_15x15x20_s8": (2, None),                              # odd sizes (no TMA: row pitch), jet inflow
+    "kepler2d_32_s10": (3, None),                                    # 2D hydro with a per-cell gravity field
+    "rt2d_hydro_16x48_s10": (3, None),                               # 2D hydro, uniform gravity, walls in y
+    "inertialwave3d_12x16x8_s12": (3, {"nx": 24, "ny": 24, "nz": 16}),  # rotating frame, periodic box (no border strips)
 }
 
 
