@@ -1,6 +1,6 @@
 """Runs the BASELINE.json configurations at their full sizes for a few steps on ONE GPU (GPU box) and
 prints device throughput + sanity checks (finite state, conserved mass where the box is periodic).
-   python tools/full_size_check.py [case ...]   cases: kh512f32 mri256 implode1024 ot1024 ot512"""
+   python tools/full_size_check.py [case ...]   cases: kh512f32 mri256 mri256slab implode512 implode1024 ot1024 ot512"""
 import os
 import sys
 import time
@@ -25,6 +25,7 @@ CASES = {
     "kh512f32": (HydroRunGodunov, "kh3d_16x8x16_f32_s10", {"mesh": {"nx": 512, "ny": 512, "nz": 512}}, True),
     "mri256": (MHDRunGodunov, "mri3d_16x32x16_s12", {"mesh": {"nx": 256, "ny": 512, "nz": 256}}, False),
     "mri256slab": (MHDRunGodunov, "mri3d_16x32x16_s12", {"mesh": {"nx": 256, "ny": 512, "nz": 64}}, False),
+    "implode512": (HydroRunGodunov, "implode3d_16_s8", {"mesh": {"nx": 512, "ny": 512, "nz": 512}}, False),
     "implode1024": (HydroRunGodunov, "implode3d_16_s8", {"mesh": {"nx": 1024, "ny": 1024, "nz": 1024}}, False),
     "ot1024": (MHDRunGodunov, "ot3d_16_s10", {"mesh": {"nx": 1024, "ny": 1024, "nz": 1024}}, False),
     "ot512": (MHDRunGodunov, "ot3d_16_s10", {"mesh": {"nx": 512, "ny": 512, "nz": 512}}, False),
