@@ -22,7 +22,7 @@ class RgStats(C.Structure):
 
 RG_FLAG_FP32 = 1
 PHASES = ["boundary", "prim", "trace", "flux", "emf", "update", "dt", "copy", "halo", "fused", "diss"]
-RG_ERR_NO_DEVICE = 2
+RG_OK, RG_ERR_INVALID, RG_ERR_NO_DEVICE, RG_ERR_CUDA, RG_ERR_UNSUPPORTED, RG_ERR_IO, RG_ERR_NCCL = range(7)  # include/ramsesgpu_b200.h
 
 # name -> (restype, argtypes); also the list the symbol-export test checks against the header
 H = C.c_void_p

@@ -48,6 +48,7 @@ template <typename T>
 static int initialConditionHost(const rg::ConfigMap& cfg, int rank, int nranks, void* dst, size_t bytes, rg_layout* lay) {
   const rg::RunParams rp = rg::parseRunParams(cfg);
   int nzLocal = rp.nz, kOff = 0;
+  if (rp.dim != 3 && nranks > 1) return fail(RG_ERR_INVALID, "z-slab decomposition needs a 3D run");
   if (rp.dim == 3) rg::slabExtent(rp.nz, nranks, rank, &nzLocal, &kOff);
   const rg::KParams<T> kp = rg::makeKParams<T>(cfg, rp, nzLocal, kOff);
   const size_t n = (size_t)kp.isize * kp.jsize * kp.ksize * kp.nvar;
